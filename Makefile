@@ -1,0 +1,20 @@
+# Builds libnerfb200.so (sm_100a only) in-tree, plus the C oracle helpers.
+NVCC      ?= nvcc
+ARCH      := -gencode arch=compute_100a,code=sm_100a
+NVCCFLAGS := -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC -Xcompiler -Wall -Iinclude
+CSRC      := nerf_b200/csrc
+SRCS      := $(CSRC)/nb2_api.cu $(CSRC)/nb2_ops.cu $(CSRC)/nb2_pack.cu $(CSRC)/nb2_mlp_simt.cu $(CSRC)/nb2_mlp_tc.cu
+OBJS      := $(SRCS:.cu=.o)
+LIB       := nerf_b200/libnerfb200.so
+
+all: $(LIB)
+
+$(CSRC)/%.o: $(CSRC)/%.cu $(CSRC)/nb2_common.cuh $(CSRC)/nb2_rowio.cuh $(CSRC)/nb2_tc_ptx.cuh include/nerf_b200.h
+	$(NVCC) $(NVCCFLAGS) $(EXTRA) -c $< -o $@
+
+$(LIB): $(OBJS)
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -lcudart
+
+clean:
+	rm -f $(OBJS) $(LIB)
+.PHONY: all clean

@@ -1,0 +1,211 @@
+/*
+ * nerf_b200.h — C ABI of libnerfb200.so, the B200 (sm_100a) ray-marching engine.
+ *
+ * Drop-in boundary for the render hot path of Enigmatisms/NeRF.  The reference has no FFI
+ * layer: its "operator API" is a set of Python call signatures.  Each entry
+ * point below names the reference function (file:line under /root/reference) it replaces; the
+ * Python package `nerf_b200` binds them with ctypes and re-exposes the reference signatures.
+ *
+ * Conventions (all entry points):
+ *   - extern "C", plain pointers and sizes, no torch / C++ types.
+ *   - return 0 on success, <0 on error; nb2_last_error() returns a thread-local message.
+ *   - every data pointer is a DEVICE pointer on the handle's device unless the name ends in
+ *     `_host`; tensors are fp32, row-major, contiguous; indices are int64 (torch.long).
+ *   - kernels are enqueued on `stream` (a cudaStream_t passed as void*) and the call returns
+ *     without synchronising.  Outputs are pre-allocated by the caller; the library never
+ *     allocates or frees caller-visible memory (scratch comes from the caller-provided
+ *     workspace, sized by nb2_render_workspace_bytes()).
+ *   - one handle per device per process; a handle owns only its packed-weight buffers.
+ *   - `jitter` / `u` pointers may be NULL: the library then draws the uniforms on the device
+ *     with Philox4x32-10 keyed by (seed, ray_offset + ray index, sample index), so results do
+ *     not depend on how rays are sharded across launches or GPUs.
+ */
+#ifndef NERF_B200_H_
+#define NERF_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NB2_VERSION 100 /* 0.1.0 */
+
+typedef struct nb2_handle nb2_handle;
+
+/* Network ids (layer tables are fixed by the reference architectures). */
+enum {
+  NB2_NET_PROPOSAL = 0, /* nerf/addtional.py:53-72   ProposalNetwork(10, 256): 63-256-256-256-256-1 */
+  NB2_NET_NERF = 1      /* nerf/mip_model.py:14-38   MipNeRF(10, 4, 256): 8x256 trunk + heads       */
+};
+
+/* Arithmetic of the MLP contraction. */
+enum {
+  NB2_PREC_FP32 = 0,   /* fp32 FFMA on CUDA cores (strict mode; reference arithmetic)               */
+  NB2_PREC_BF16X3 = 1, /* tcgen05, operands split hi+lo bf16, 3 MMAs, fp32 accumulate (fp32-faithful)*/
+  NB2_PREC_BF16 = 2    /* tcgen05, single bf16 pass, fp32 accumulate                                */
+};
+
+/* Flags for nb2_composite / nb2_render_rays. */
+enum {
+  NB2_WHITE_BKG = 1,      /* rgb += 1 - sum(w)                    nerf/nerf_base.py:103-105 */
+  NB2_DENSITY_SOFTPLUS = 2 /* proposal density softplus'd (train.py:169) instead of raw     */
+};
+
+/* Error codes. */
+enum {
+  NB2_OK = 0,
+  NB2_ERR_INVALID = -1, /* bad argument                 */
+  NB2_ERR_CUDA = -2,    /* CUDA runtime error           */
+  NB2_ERR_STATE = -3,   /* e.g. weights not packed      */
+  NB2_ERR_UNSUPPORTED = -4
+};
+
+const char* nb2_last_error(void);
+int nb2_version(void);
+
+/* ---- lifetime ------------------------------------------------------------------------- */
+int nb2_create(nb2_handle** out, int device);
+int nb2_destroy(nb2_handle* h);
+
+/*
+ * Pack one network's fp32 parameters into the layouts the kernels consume (fp32 K-major
+ * transposes for NB2_PREC_FP32; pre-swizzled 128x64 bf16 hi/lo operand tiles for tcgen05).
+ * `W_ptrs[i]` / `b_ptrs[i]` are HOST arrays of DEVICE pointers to nn.Linear weight (out,in)
+ * and bias (out), in reference state_dict order:
+ *   NB2_NET_PROPOSAL (5): layers.{0,2,4,6,8}                      nerf/addtional.py:67-71
+ *   NB2_NET_NERF    (11): lin_block1.{0,2,4,6}, lin_block2.{0,2,4}, bottle_neck.0,
+ *                         opacity_head.0, rgb_layer.{0,2}         nerf/mip_model.py:19-37
+ * Must be re-run after every parameter update (the handle keeps a version stamp).  Setup call:
+ * allocates the handle's packed buffers on first use and synchronises `stream` once.
+ */
+int nb2_pack_weights(nb2_handle* h, int net_id, const float* const* W_ptrs_host,
+                     const float* const* b_ptrs_host, int n_layers, int pos_levels,
+                     int dir_levels, int hidden, void* stream);
+int nb2_weights_version(nb2_handle* h, int net_id);
+
+/* ---- a1: pixel grid -> camera rays           nerf/procedures.py:43-51,64 ----------------
+ * pose: 12 floats (3x4 row-major, device).  rays_out: (n_rays, 6) = [origin, R*(cx/fx, cy/fy, -1)],
+ * raster order; ray i of the launch is pixel (pix_offset + i) of the H x W image. */
+int nb2_generate_rays(nb2_handle* h, const float* pose, int H, int W, float focal_x,
+                      float focal_y, int64_t pix_offset, int64_t n_rays, float* rays_out,
+                      void* stream);
+
+/* ---- a3+a4: stratified coarse depths and points  nerf/procedures.py:52,59,65-66 ---------
+ * z[r,s] = base_z[s] + jitter[r,s] * resolution ; pts = o + z*d.  pts_out may be NULL. */
+int nb2_sample_coarse(nb2_handle* h, const float* rays, const float* base_z,
+                      const float* jitter, float resolution, uint64_t seed,
+                      int64_t ray_offset, int64_t n_rays, int n_samples, float* z_out,
+                      float* pts_out, void* stream);
+
+/* ---- a5: sinusoidal positional encoding       nerf/nerf_helper.py:38-48 -----------------
+ * x: (n, 3) -> out: (n, 6*levels), per level [sin(2^l x)(3), cos(2^l x)(3)].  `dims` = 3. */
+int nb2_posenc(nb2_handle* h, const float* x, int64_t n, int dims, int levels, float* out,
+               void* stream);
+
+/* ---- a14: integrated positional encoding      nerf/mip_methods.py:15-58 -----------------
+ * zvals (R, C+1), rays (R, 6) -> feat (R, C, 6L), mu (R, C, 3), mu_t (R, C).
+ * Keeps the reference's batch-global ||d||_F (mip_methods.py:31); `scratch` >= 8 bytes. */
+int nb2_ipe(nb2_handle* h, const float* zvals, const float* rays, int64_t n_rays, int n_cones,
+            int levels, float radius, float* feat_out, float* mu_out, float* mu_t_out,
+            void* scratch, void* stream);
+
+/* ---- a7 (+ weights half of a12): density -> alpha-compositing weights --------------------
+ * nerf/addtional.py:99-107, nerf/nerf_base.py:79-86.  dirs may be NULL (no ||d|| scaling).
+ * act: 0 = relu, 1 = softplus, 2 = identity. */
+int nb2_weights_from_sigma(nb2_handle* h, const float* sigma, const float* z,
+                           const float* dirs, int dir_stride, int64_t n_rays, int n_samples,
+                           int act, float* weights_out, void* stream);
+
+/* ---- a8: 2-tap max + 2-tap blur               nerf/mip_methods.py:61-66 ----------------- */
+int nb2_max_blur(nb2_handle* h, const float* weights, int64_t n_rays, int n_samples,
+                 float alpha, float* out, void* stream);
+
+/* ---- a9: inverse-CDF sampling                 nerf/utils.py:34-44,108-133 ----------------
+ * nb2_sample_pdf == sample_pdf: bins (R, B), weights (R, B-1), u (R, N) or NULL ->
+ *   samples (R, N) fp32, below (R, N) int64, above (R, N) int64 (unsorted).
+ * nb2_inverse_sample == inverseSample(weights (R,P), z (R,P), N, sort): bins = mid(z),
+ *   weights[1:-1]; if sort != 0 samples ascend and `below` is gathered by the sort permutation. */
+int nb2_sample_pdf(nb2_handle* h, const float* bins, const float* weights, const float* u,
+                   uint64_t seed, int64_t ray_offset, int64_t n_rays, int n_bins,
+                   int n_draw, float* samples_out, int64_t* below_out, int64_t* above_out,
+                   void* stream);
+int nb2_inverse_sample(nb2_handle* h, const float* weights, const float* z, const float* u,
+                       uint64_t seed, int64_t ray_offset, int64_t n_rays, int n_samples,
+                       int n_draw, int sort, float* samples_out, int64_t* below_out,
+                       void* stream);
+/* Search stage only: identical (cdf, u) -> indices bit-exact (SURVEY.md §7 hard part 1a). */
+int nb2_search_cdf(nb2_handle* h, const float* cdf, const float* u, int64_t n_rays,
+                   int n_cdf, int n_draw, int64_t* inds_out, void* stream);
+
+/* ---- a7+a8+a9+drop-last fused (render path)   nerf/procedures.py:68-70,76 ----------------
+ * sigma (R,P) raw proposal density, z (R,P), rays (R,6) -> z_fine (R, n_draw-1) ascending. */
+int nb2_resample(nb2_handle* h, const float* sigma, const float* z, const float* rays,
+                 const float* u, uint64_t seed, int64_t ray_offset, int64_t n_rays,
+                 int n_samples, int n_draw, float blur_alpha, int flags, float* z_fine_out,
+                 void* stream);
+
+/* ---- a10: depths -> sample points             nerf/nerf_base.py:52-56 -------------------
+ * rays (R,6), z (R,P) -> (R,P,6) = [o + z*d, d]. */
+int nb2_length2pts(nb2_handle* h, const float* rays, const float* z, int64_t n_rays,
+                   int n_samples, float* pts_out, void* stream);
+
+/* ---- a13: coarse/fine merge (Ref-NeRF branch) nerf/nerf_base.py:58-73 -------------------
+ * cat(f_z (R,F), c_z (R,C)) -> sort -> drop last -> z (R,F+C-1), pts (R,F+C-1,6). */
+int nb2_coarse_fine_merge(nb2_handle* h, const float* rays, const float* c_z, const float* f_z,
+                          int64_t n_rays, int n_coarse, int n_fine, float* z_out,
+                          float* pts_out, void* stream);
+
+/* ---- a6 / a11: MLP forward ---------------------------------------------------------------
+ * NB2_NET_PROPOSAL: pts (R*P, 3) -> out (R*P) raw density.  ProposalNetwork.forward
+ *                   nerf/addtional.py:88-96.  `pts_stride` = 3.
+ * NB2_NET_NERF:     pts (R*P, 6) = [xyz, dir] -> out (R*P, 4) = [sigmoid rgb, raw sigma].
+ *                   MipNeRF.forward nerf/mip_model.py:41-60.  `pts_stride` = 6. */
+int nb2_mlp_forward(nb2_handle* h, int net_id, int precision, const float* pts,
+                    int pts_stride, int64_t n_points, float* out, void* stream);
+
+/* ---- a12: alpha compositing                   nerf/nerf_base.py:90-113 ------------------
+ * rgbo (R,P,4), z (R,P), dirs (R, dir_stride>=3) -> rgb (R,3), weights (R,P) or NULL,
+ * depth (R) or NULL = (sum w*z*||d|| - near) / (far - near), acc (R) or NULL. */
+int nb2_composite(nb2_handle* h, const float* rgbo, const float* z, const float* dirs,
+                  int dir_stride, int64_t n_rays, int n_samples, int flags, float near_t,
+                  float far_t, float* rgb_out, float* weights_out, float* depth_out,
+                  float* acc_out, void* stream);
+
+/* ---- the fused path: render_image's per-ray work   nerf/procedures.py:64-85 --------------
+ * rays (R,6) -> rgb (R,3), depth (R) or NULL, acc (R) or NULL.  Three launches: fused
+ * sample+encode+proposal-MLP, resample, fused encode+NeRF-MLP+composite.
+ * Optional debug outputs (NULL to skip): z_coarse (R,Pc), sigma_prop (R,Pc), z_fine (R,Pf). */
+typedef struct nb2_render_params {
+  int n_coarse;       /* 64   RENDER_COARSE_PNUM, nerf/procedures.py:22 */
+  int n_fine;         /* 128  sample_num; n_fine+1 are drawn, the largest dropped */
+  float near_t, far_t;
+  float resolution;   /* (far-near)/sample_num, nerf/procedures.py:59 */
+  float blur_alpha;   /* 0.01, nerf/procedures.py:69 */
+  int flags;          /* NB2_WHITE_BKG | NB2_DENSITY_SOFTPLUS */
+  int precision;      /* NB2_PREC_* */
+  uint64_t seed;      /* Philox key when jitter/u are NULL */
+  int64_t ray_offset; /* global index of rays[0] (shard invariance) */
+} nb2_render_params;
+
+int64_t nb2_render_workspace_bytes(int64_t n_rays, const nb2_render_params* p);
+int nb2_render_rays(nb2_handle* h, const nb2_render_params* p, const float* rays,
+                    const float* base_z, const float* jitter, const float* u, int64_t n_rays,
+                    float* rgb_out, float* depth_out, float* acc_out, float* z_coarse_out,
+                    float* sigma_prop_out, float* z_fine_out, void* workspace,
+                    int64_t workspace_bytes, void* stream);
+
+/* Kernel-launch counter (all launches made through this handle since creation). */
+int64_t nb2_launch_count(nb2_handle* h);
+
+/* Device-side self-test of the tcgen05 building blocks: D (128x128 fp32) = A (128x64 bf16,
+ * row-major) * B^T (128x64 bf16, row-major), computed by ONE UMMA sequence through the same
+ * operand swizzle, descriptors, bulk copy, commit and TMEM read-out the MLP kernel uses.
+ * scratch_16k: 16 KB of device scratch. */
+int nb2_selftest_umma(nb2_handle* h, const void* A_bf16, const void* B_bf16, void* scratch_16k,
+                      float* D_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NERF_B200_H_ */

@@ -1,0 +1,223 @@
+// nb2_common.cuh — shared declarations for libnerfb200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <algorithm>
+
+#include "../../include/nerf_b200.h"
+
+#if defined(__CUDA_ARCH__) && !defined(__CUDA_ARCH_FEAT_SM100_ALL)
+#error "libnerfb200 is written for sm_100a only: compile with -gencode arch=compute_100a,code=sm_100a"
+#endif
+
+namespace nb2 {
+
+// ------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+#define NB2_CHECK_ARG(cond, ...)                      \
+  do {                                                \
+    if (!(cond)) {                                    \
+      nb2::set_error(__VA_ARGS__);                    \
+      return NB2_ERR_INVALID;                         \
+    }                                                 \
+  } while (0)
+#define NB2_CUDA(call)                                                                   \
+  do {                                                                                   \
+    cudaError_t e_ = (call);                                                             \
+    if (e_ != cudaSuccess) {                                                             \
+      nb2::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__,   \
+                     __LINE__);                                                          \
+      return NB2_ERR_CUDA;                                                               \
+    }                                                                                    \
+  } while (0)
+#define NB2_LAUNCH_CHECK(h)                                                              \
+  do {                                                                                   \
+    cudaError_t e_ = cudaGetLastError();                                                 \
+    if (e_ != cudaSuccess) {                                                             \
+      nb2::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(e_),         \
+                     __FILE__, __LINE__);                                                \
+      return NB2_ERR_CUDA;                                                               \
+    }                                                                                    \
+    (h)->launches++;                                                                     \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------
+// network description shared by the pack step and the MLP kernels
+// ------------------------------------------------------------------------------------------
+constexpr int kHidden = 256;       // trunk width (reference default --nerf_net_width / --prop_net_width)
+constexpr int kEncCols = 64;       // 3 + 6*10 = 63 encoded position columns, padded to 64
+constexpr int kDirCols = 32;       // 3 + 6*4  = 27 encoded direction columns, padded to 32
+constexpr int kRgbHidden = 128;    // rgb_layer.0 width (nerf/mip_model.py:35)
+constexpr int kMaxPosLevels = 10;
+constexpr int kMaxDirLevels = 4;
+
+// Tensor-core operand tile: 128 rows x 64 bf16 columns, K-major, 128-byte swizzle (16 KB).
+constexpr int kTileRows = 128;
+constexpr int kTileCols = 64;
+constexpr int kTileBytes = kTileRows * kTileCols * 2;  // 16384
+
+// A-operand chunk ids inside one slot's activation buffer.
+constexpr int kChunkH0 = 0;  // hidden activation columns [0,64) ... kChunkH0+3 = [192,256)
+constexpr int kChunkE = 4;   // encoded position (later re-used for the encoded direction)
+constexpr int kChunksPerSlot = 5;
+
+enum EpiKind {
+  EPI_RELU = 0,        // h = relu(acc + b)                       -> H
+  EPI_RELU_SIGMA = 1,  // h = relu(acc + b); sigma = w_s.h + b_s  -> H (+ dir encoding into E)
+  EPI_LINEAR = 2,      // h = acc + b                             -> H          (bottle_neck)
+  EPI_RGB = 3,         // t = relu(acc + b); rgb = sigmoid(W1 t + b1)           (rgb_layer)
+  EPI_SIGMA_OUT = 4    // h = relu(acc + b); out = w_s.h + b_s                  (proposal tail)
+};
+
+constexpr int kMaxTcLayers = 9;
+struct TcLayer {
+  int kc;        // number of 64-wide K chunks
+  int nc;        // number of 128-wide N chunks
+  int a_src[5];  // A chunk id for each K chunk
+  int epi;       // EpiKind
+  int bias_off;  // offset (floats) into the bias array
+  int chunk0;    // first weight chunk of this layer in the packed stream
+};
+struct TcNet {
+  int n_layers;
+  int n_chunks;
+  TcLayer layer[kMaxTcLayers];
+};
+
+// fp32 (CUDA-core) layer table: out = act(sum_seg X_seg . Wt_seg + b)
+constexpr int kMaxSimtLayers = 9;
+struct SimtLayer {
+  int k0, k1;      // K of segment 0 (read from buffer src0) and segment 1 (src1); k1 = 0 if unused
+  int src0, src1;  // 0 = E (encoded position), 1 = H, 2 = D (encoded direction)
+  int n;           // output width (256 or 128)
+  int epi;         // EpiKind
+  int wt_off;      // offset (floats) of the transposed weight [(k0+k1) x n]
+  int bias_off;
+};
+struct SimtNet {
+  int n_layers;
+  SimtLayer layer[kMaxSimtLayers];
+};
+
+struct PackedNet {
+  bool packed = false;
+  int version = 0;
+  int pos_levels = 0, dir_levels = 0;
+  TcNet tc;
+  SimtNet simt;
+  __nv_bfloat16* d_wchunks = nullptr;  // [n_chunks][2 (hi, lo)][8192] pre-swizzled tiles
+  float* d_bias = nullptr;             // all MMA-layer biases, concatenated
+  float* d_head = nullptr;             // sigma head: w[256], b ; rgb head: W1[3][128], b1[3]
+  float* d_wt32 = nullptr;             // fp32 transposed weights for the CUDA-core path
+};
+constexpr int kHeadSigmaW = 0;      // 256 floats
+constexpr int kHeadSigmaB = 256;    // 1 float
+constexpr int kHeadRgbW = 260;      // 3 x 128 floats
+constexpr int kHeadRgbB = 260 + 384;  // 3 floats
+constexpr int kHeadFloats = 652;
+
+}  // namespace nb2
+
+struct nb2_handle {
+  int device = 0;
+  int sm_count = 0;
+  int64_t launches = 0;
+  nb2::PackedNet net[2];
+};
+
+namespace nb2 {
+
+// ------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+// Philox4x32-10 (Salmon et al. 2011).  counter = (c0,c1,c2,c3), key = (k0,k1).
+__host__ __device__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint64_t p0 = (uint64_t)M0 * c[0];
+    uint64_t p1 = (uint64_t)M1 * c[2];
+    uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0;
+    uint32_t n1 = (uint32_t)p1;
+    uint32_t n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1;
+    uint32_t n3 = (uint32_t)p0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+    k0 += W0; k1 += W1;
+  }
+}
+// Uniform in [0,1) with 24 random bits.  stream: 0 = coarse jitter, 1 = inverse-CDF u.
+__host__ __device__ __forceinline__ float philox_uniform(uint64_t seed, uint64_t ray, uint32_t sample,
+                                                         uint32_t stream) {
+  uint32_t c[4] = {(uint32_t)ray, (uint32_t)(ray >> 32), sample >> 2, stream};
+  philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+  return (float)(c[sample & 3] >> 8) * (1.0f / 16777216.0f);
+}
+
+__device__ __forceinline__ float softplus_f(float x) {
+  // torch.nn.functional.softplus(beta=1, threshold=20)
+  return x > 20.f ? x : log1pf(expf(x));
+}
+__device__ __forceinline__ float apply_density_act(float x, int act) {
+  return act == 0 ? fmaxf(x, 0.f) : (act == 1 ? softplus_f(x) : x);
+}
+
+// Inclusive product scan over a warp.
+__device__ __forceinline__ float warp_scan_mul(float v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    float t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v *= t;
+  }
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+#endif  // __CUDACC__
+
+// launchers implemented in the other translation units --------------------------------------
+struct MlpIo {
+  // input selection
+  int in_mode;            // 0 = explicit points, 1 = rays + z, 2 = rays + stratified sampling
+  const float* pts;       // in_mode 0: (n_rows, pts_stride)
+  int pts_stride;
+  const float* rays;      // in_mode 1/2: (n_rays, 6)
+  const float* z;         // in_mode 1:   (n_rays, P)
+  const float* base_z;    // in_mode 2:   (P)
+  const float* jitter;    // in_mode 2:   (n_rays, P) or NULL -> Philox
+  float resolution;
+  uint64_t seed;
+  int64_t ray_offset;
+  int P;                  // samples per ray (in_mode 1/2)
+  int64_t n_rows;         // total MLP rows (= n_rays * P)
+  // output selection
+  int out_mode;           // 0 = sigma (n_rows), 1 = rgbo (n_rows,4), 2 = composite per ray
+  float* out;             // out_mode 0/1
+  float* z_out;           // in_mode 2: sampled depths (n_rays, P) or NULL
+  float* rgb_out;         // out_mode 2: (n_rays, 3)
+  float* depth_out;       // out_mode 2: (n_rays) or NULL
+  float* acc_out;         // out_mode 2: (n_rays) or NULL
+  int flags;
+  float near_t, far_t;
+};
+int launch_mlp_simt(nb2_handle* h, int net_id, const MlpIo& io, cudaStream_t st);
+int launch_mlp_tc(nb2_handle* h, int net_id, int precision, const MlpIo& io, cudaStream_t st);
+int pack_network(nb2_handle* h, int net_id, const float* const* W, const float* const* b,
+                 int n_layers, int pos_levels, int dir_levels, cudaStream_t st);
+
+}  // namespace nb2

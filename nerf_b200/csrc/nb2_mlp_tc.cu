@@ -1,0 +1,527 @@
+// nb2_mlp_tc.cu — the per-sample MLP (proposal 4x256 / NeRF 8x256 + heads) as ONE persistent,
+// warp-specialised tcgen05 kernel.  NB2_PREC_BF16 and NB2_PREC_BF16X3.
+//
+//   warp 0      weight streamer: cp.async.bulk (TMA unit) of pre-swizzled 128x64 bf16 weight
+//               tiles from L2 into a 4-stage shared-memory ring, mbarrier full/empty handshake
+//   warp 1      MMA issuer: one thread issues tcgen05.mma (M=128, N=128, K=16) with both
+//               operands in shared memory and the fp32 accumulator in TMEM
+//   warp 2      TMEM allocator
+//   warps 4..   one 128-thread "slot group" per resident 128-row tile: it produces the tile's
+//               first A operand (sample point -> sinusoidal encoding -> swizzled bf16 rows),
+//               and after every layer drains the accumulator from TMEM (tcgen05.ld), applies
+//               bias / ReLU, re-quantises to bf16 (hi [+ lo]) and writes the next layer's A
+//               operand in place.  The last epilogue evaluates the 128->3 / 256->1 heads on the
+//               fp32 values and either stores rgb-sigma or alpha-composites the ray.
+//
+// NB2_PREC_BF16  : two slots ping-pong, so one tile's epilogue overlaps the other tile's MMAs.
+// NB2_PREC_BF16X3: every operand is split x = hi + lo (both bf16); each product is evaluated as
+//                  hi*hi + lo*hi + hi*lo with fp32 accumulation (~2^-16 relative per product),
+//                  one slot (the hi/lo activation pair fills the shared memory of two slots).
+//
+// Shared memory (bytes):  activations NSLOTS * (SPLIT ? 2 : 1) * 5 * 16 KB = 160 KB,
+//                         weight ring 4 * 16 KB = 64 KB, barriers + scratch < 1 KB.
+// TMEM: 512 columns; slot s owns columns [256 s, 256 s + 256) (128 lanes x 256 fp32).
+#include "nb2_common.cuh"
+#include "nb2_rowio.cuh"
+#include "nb2_tc_ptx.cuh"
+
+namespace nb2 {
+using namespace ptx;
+
+constexpr int kStages = 4;
+constexpr int kRolesThreads = 128;  // warps 0..3
+
+struct TcParams {
+  TcNet net;
+  MlpIo io;
+  const __nv_bfloat16* wchunks;
+  const float* bias;
+  const float* head;
+  int pos_levels, dir_levels, has_dir;
+  int64_t n_tiles;
+};
+
+struct TcMisc {
+  uint64_t w_full[kStages];
+  uint64_t w_empty[kStages];
+  uint64_t a_ready[2];
+  uint64_t acc_full[2];
+  uint32_t tmem_base;
+  uint32_t pad;
+  float scratch[2][4][8];  // per slot, per warp: cross-warp scan / reduction staging
+};
+
+template <int NSLOTS, bool SPLIT>
+struct TcLayout {
+  static constexpr int kActTiles = kChunksPerSlot * (SPLIT ? 2 : 1);
+  static constexpr int kSlotBytes = kActTiles * kTileBytes;
+  static constexpr int kActBytes = NSLOTS * kSlotBytes;
+  static constexpr int kRingBytes = kStages * kTileBytes;
+  static constexpr int kMiscBytes = 1024;
+  static constexpr int kTotal = kActBytes + kRingBytes + kMiscBytes + 1024 /* alignment slack */;
+  static_assert(sizeof(TcMisc) <= kMiscBytes, "misc region too small");
+  static_assert(kTotal <= 232448, "exceeds 227 KB of shared memory");
+};
+
+// ---- writing one row of an A-operand tile ---------------------------------------------------
+// v[0..8) are 8 consecutive columns starting at column `col` (multiple of 8) of row `row`.
+template <bool SPLIT>
+__device__ __forceinline__ void store_a8(uint32_t tile_hi, uint32_t tile_lo, int row, int col, const float (&v)[8]) {
+  const uint32_t off = (uint32_t)row * 128u + ((((uint32_t)col >> 3) ^ ((uint32_t)row & 7u)) << 4);
+  uint32_t h[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+  st_shared_v4(tile_hi + off, h[0], h[1], h[2], h[3]);
+  if (SPLIT) {
+    uint32_t l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      l[i] = pack_bf16x2(v[2 * i] - bf16_lo_to_f32(h[i]), v[2 * i + 1] - bf16_hi_to_f32(h[i]));
+    st_shared_v4(tile_lo + off, l[0], l[1], l[2], l[3]);
+  }
+}
+
+// Encoded position / direction row -> E tile.  NCOLS = 64 (position) or 32 (direction).
+template <bool SPLIT, int NCOLS, int MAXLEV>
+__device__ __forceinline__ void write_enc_row(uint32_t tile_hi, uint32_t tile_lo, int row, const float x[3],
+                                              int levels, bool valid) {
+  float v[NCOLS];
+#pragma unroll
+  for (int c = 0; c < NCOLS; ++c) v[c] = 0.f;
+  if (valid) {
+    v[0] = x[0]; v[1] = x[1]; v[2] = x[2];
+#pragma unroll
+    for (int l = 0; l < MAXLEV; ++l) {
+      if (l < levels) {
+        const float sc = (float)(1 << l);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          float s, c;
+          sincosf(x[k] * sc, &s, &c);
+          v[3 + 6 * l + k] = s;
+          v[3 + 6 * l + 3 + k] = c;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int g = 0; g < NCOLS / 8; ++g) {
+    float w[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) w[i] = v[8 * g + i];
+    store_a8<SPLIT>(tile_hi, tile_lo, row, 8 * g, w);
+  }
+}
+
+// ---- the kernel ----------------------------------------------------------------------------------
+template <int NSLOTS, bool SPLIT>
+__global__ void __launch_bounds__(kRolesThreads + 128 * NSLOTS, 1) mlp_tc_kernel(const __grid_constant__ TcParams p) {
+  using LT = TcLayout<NSLOTS, SPLIT>;
+  extern __shared__ unsigned char smem_dyn[];
+  const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+  unsigned char* smem_al = smem_dyn + (smem_base - smem_u32(smem_dyn));
+  const uint32_t act_base = smem_base;
+  const uint32_t ring_base = smem_base + LT::kActBytes;
+  TcMisc* misc = reinterpret_cast<TcMisc*>(smem_al + LT::kActBytes + LT::kRingBytes);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const TcNet& net = p.net;
+  const int64_t tiles_per_iter = (int64_t)gridDim.x * NSLOTS;
+  const int64_t n_iters = (p.n_tiles + tiles_per_iter - 1) / tiles_per_iter;
+
+  // ---- one-time setup ---------------------------------------------------------------------------
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(smem_u32(&misc->w_full[i]), 1);
+      mbar_init(smem_u32(&misc->w_empty[i]), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&misc->a_ready[s]), 128);
+      mbar_init(smem_u32(&misc->acc_full[s]), 1);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(smem_u32(&misc->tmem_base), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = misc->tmem_base;
+
+  if (warp == 0) {
+    // =========================== weight streamer ==================================================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int64_t it = 0; it < n_iters; ++it) {
+        for (int l = 0; l < net.n_layers; ++l) {
+          const int n_chunks = net.layer[l].kc * net.layer[l].nc;
+          const int chunk0 = net.layer[l].chunk0;
+          for (int s = 0; s < NSLOTS; ++s) {
+            const int64_t tile = (it * gridDim.x + blockIdx.x) * NSLOTS + s;
+            if (tile >= p.n_tiles) continue;
+            for (int c = 0; c < n_chunks; ++c) {
+#pragma unroll
+              for (int part = 0; part < (SPLIT ? 2 : 1); ++part) {
+                mbar_wait(smem_u32(&misc->w_empty[stage]), phase ^ 1u);
+                const uint32_t full = smem_u32(&misc->w_full[stage]);
+                mbar_arrive_expect_tx(full, kTileBytes);
+                bulk_g2s(ring_base + stage * kTileBytes,
+                         p.wchunks + ((size_t)(chunk0 + c) * 2 + part) * (kTileBytes / 2), kTileBytes, full);
+                if (++stage == kStages) { stage = 0; phase ^= 1u; }
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer =======================================================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(128, 128);
+      uint32_t stage = 0, phase = 0;
+      uint32_t pa[2] = {0u, 0u};
+      for (int64_t it = 0; it < n_iters; ++it) {
+        for (int l = 0; l < net.n_layers; ++l) {
+          const TcLayer& L = net.layer[l];
+          for (int s = 0; s < NSLOTS; ++s) {
+            const int64_t tile = (it * gridDim.x + blockIdx.x) * NSLOTS + s;
+            if (tile >= p.n_tiles) continue;
+            mbar_wait(smem_u32(&misc->a_ready[s]), pa[s]);
+            pa[s] ^= 1u;
+            tc_fence_after();
+            const uint32_t slot_base = act_base + s * LT::kSlotBytes;
+            const uint32_t acc = tmem_base + (uint32_t)(s * 256);
+            for (int n = 0; n < L.nc; ++n) {
+              for (int k = 0; k < L.kc; ++k) {
+                const uint32_t a_hi = slot_base + (uint32_t)L.a_src[k] * kTileBytes;
+                const uint32_t a_lo = a_hi + kChunksPerSlot * kTileBytes;
+                mbar_wait(smem_u32(&misc->w_full[stage]), phase);
+                tc_fence_after();
+                const uint32_t w_hi = ring_base + stage * kTileBytes;
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)
+                  umma_bf16_ss(acc + n * 128, umma_smem_desc(a_hi + ks * 32), umma_smem_desc(w_hi + ks * 32), idesc,
+                               (uint32_t)((k | ks) != 0));
+                if (SPLIT) {
+#pragma unroll
+                  for (int ks = 0; ks < 4; ++ks)
+                    umma_bf16_ss(acc + n * 128, umma_smem_desc(a_lo + ks * 32), umma_smem_desc(w_hi + ks * 32), idesc, 1u);
+                }
+                umma_commit(smem_u32(&misc->w_empty[stage]));
+                if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                if (SPLIT) {
+                  mbar_wait(smem_u32(&misc->w_full[stage]), phase);
+                  tc_fence_after();
+                  const uint32_t w_lo = ring_base + stage * kTileBytes;
+#pragma unroll
+                  for (int ks = 0; ks < 4; ++ks)
+                    umma_bf16_ss(acc + n * 128, umma_smem_desc(a_hi + ks * 32), umma_smem_desc(w_lo + ks * 32), idesc, 1u);
+                  umma_commit(smem_u32(&misc->w_empty[stage]));
+                  if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                }
+              }
+            }
+            umma_commit(smem_u32(&misc->acc_full[s]));
+          }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // =========================== slot group: producer + epilogue ====================================
+    const int s = (warp - 4) >> 2;
+    const int wq = warp & 3;            // TMEM lane quadrant this warp may access
+    const int row = wq * 32 + lane;     // row of the tile == TMEM lane
+    const uint32_t slot_base = act_base + s * LT::kSlotBytes;
+    const uint32_t lo_off = kChunksPerSlot * kTileBytes;
+    const uint32_t e_hi = slot_base + kChunkE * kTileBytes, e_lo = e_hi + lo_off;
+    const uint32_t acc = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(s * 256);
+    const uint32_t a_ready = smem_u32(&misc->a_ready[s]);
+    const uint32_t acc_full = smem_u32(&misc->acc_full[s]);
+    float* scratch = &misc->scratch[s][0][0];
+    uint32_t pacc = 0;
+
+    for (int64_t it = 0; it < n_iters; ++it) {
+      const int64_t tile = (it * gridDim.x + blockIdx.x) * NSLOTS + s;
+      if (tile >= p.n_tiles) break;
+      const int64_t grow = tile * kTileRows + row;
+      const RowIn in = load_row(p.io, grow);
+      write_enc_row<SPLIT, kEncCols, kMaxPosLevels>(e_hi, e_lo, row, in.p, p.pos_levels, in.valid);
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(a_ready);
+
+      float sigma = 0.f;
+      for (int l = 0; l < net.n_layers; ++l) {
+        const TcLayer& L = net.layer[l];
+        const float* bias = p.bias + L.bias_off;
+        mbar_wait(acc_full, pacc);
+        pacc ^= 1u;
+        tc_fence_after();
+
+        if (L.epi == EPI_RGB) {
+          // ---- rgb_layer: t = relu(acc + b) (128 wide), rgb = sigmoid(W1 t + b1) ---------------
+          float c0 = 0.f, c1 = 0.f, c2 = 0.f;
+#pragma unroll 1
+          for (int cb = 0; cb < kRgbHidden / 32; ++cb) {
+            uint32_t r[32];
+            tmem_ld32(acc + cb * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int col = cb * 32 + j;
+              const float t = fmaxf(__uint_as_float(r[j]) + __ldg(bias + col), 0.f);
+              c0 = fmaf(t, __ldg(p.head + kHeadRgbW + col), c0);
+              c1 = fmaf(t, __ldg(p.head + kHeadRgbW + 128 + col), c1);
+              c2 = fmaf(t, __ldg(p.head + kHeadRgbW + 256 + col), c2);
+            }
+          }
+          c0 = 1.f / (1.f + expf(-(c0 + __ldg(p.head + kHeadRgbB + 0))));
+          c1 = 1.f / (1.f + expf(-(c1 + __ldg(p.head + kHeadRgbB + 1))));
+          c2 = 1.f / (1.f + expf(-(c2 + __ldg(p.head + kHeadRgbB + 2))));
+          if (p.io.out_mode == 1) {
+            if (in.valid) reinterpret_cast<float4*>(p.io.out)[grow] = make_float4(c0, c1, c2, sigma);
+          } else {
+            // ---- alpha compositing over the rows of each ray (nerf_base.py:79-113) -------------
+            const int P = p.io.P;                 // 32, 64 or 128: rays cover whole warps
+            const int wpr = P >> 5;               // warps per ray
+            const int wseg = wq % wpr;            // this warp's position inside its ray
+            const float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(in.d[0], in.d[0]), __fmul_rn(in.d[1], in.d[1])),
+                                              __fmul_rn(in.d[2], in.d[2])));
+            const float depth = __fmul_rn(in.z, nrm);
+            float next = __shfl_down_sync(0xffffffffu, depth, 1);
+            if (lane == 0) scratch[wq * 8 + 0] = depth;
+            named_bar_sync(1 + s, 128);
+            if (lane == 31 && wq < 3) next = scratch[(wq + 1) * 8 + 0];
+            const bool last = (in.s == P - 1);
+            const float delta = last ? 1e10f : __fsub_rn(next, depth);
+            const float m = in.valid ? expf(-fmaxf(sigma, 0.f) * delta) : 1.f;
+            const float alpha = 1.f - m;
+            const float inc = warp_scan_mul(m + 1e-10f, lane);
+            float exc = __shfl_up_sync(0xffffffffu, inc, 1);
+            if (lane == 0) exc = 1.f;
+            if (lane == 31) scratch[wq * 8 + 1] = inc;
+            named_bar_sync(1 + s, 128);
+            float carry = 1.f;
+            for (int w = wq - wseg; w < wq; ++w) carry *= scratch[w * 8 + 1];
+            const float wgt = in.valid ? alpha * (carry * exc) : 0.f;
+            float sr = warp_sum(wgt * c0), sg = warp_sum(wgt * c1), sb = warp_sum(wgt * c2);
+            float sa = warp_sum(wgt), sd = warp_sum(wgt * depth);
+            if (lane == 0) {
+              scratch[wq * 8 + 2] = sr; scratch[wq * 8 + 3] = sg; scratch[wq * 8 + 4] = sb;
+              scratch[wq * 8 + 5] = sa; scratch[wq * 8 + 6] = sd;
+            }
+            named_bar_sync(1 + s, 128);
+            if (lane == 0 && wseg == 0 && in.valid) {
+              for (int w = wq + 1; w < wq + wpr; ++w) {
+                sr += scratch[w * 8 + 2]; sg += scratch[w * 8 + 3]; sb += scratch[w * 8 + 4];
+                sa += scratch[w * 8 + 5]; sd += scratch[w * 8 + 6];
+              }
+              if (p.io.flags & NB2_WHITE_BKG) {
+                const float bg = 1.f - sa;
+                sr += bg; sg += bg; sb += bg;
+              }
+              p.io.rgb_out[in.ray * 3 + 0] = sr;
+              p.io.rgb_out[in.ray * 3 + 1] = sg;
+              p.io.rgb_out[in.ray * 3 + 2] = sb;
+              if (p.io.depth_out) p.io.depth_out[in.ray] = (sd - p.io.near_t) / (p.io.far_t - p.io.near_t);
+              if (p.io.acc_out) p.io.acc_out[in.ray] = sa;
+            }
+            named_bar_sync(1 + s, 128);  // scratch is reused by the next tile
+          }
+        } else {
+          // ---- hidden layer: h = act(acc + b) -> bf16 (hi [+ lo]) A operand, in place ------------
+          const bool relu = (L.epi != EPI_LINEAR);
+          const bool want_sigma = (L.epi == EPI_RELU_SIGMA || L.epi == EPI_SIGMA_OUT);
+          float sg = 0.f;
+#pragma unroll 1
+          for (int cb = 0; cb < kHidden / 32; ++cb) {
+            uint32_t r[32];
+            tmem_ld32(acc + cb * 32, r);
+            tmem_ld_wait();
+            const uint32_t h_hi = slot_base + (uint32_t)(cb >> 1) * kTileBytes;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const int col = cb * 32 + g * 8;
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + col));
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + col + 4));
+              float v[8] = {__uint_as_float(r[g * 8 + 0]) + b0.x, __uint_as_float(r[g * 8 + 1]) + b0.y,
+                            __uint_as_float(r[g * 8 + 2]) + b0.z, __uint_as_float(r[g * 8 + 3]) + b0.w,
+                            __uint_as_float(r[g * 8 + 4]) + b1.x, __uint_as_float(r[g * 8 + 5]) + b1.y,
+                            __uint_as_float(r[g * 8 + 6]) + b1.z, __uint_as_float(r[g * 8 + 7]) + b1.w};
+              if (relu) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+              }
+              if (want_sigma) {
+                const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.head + kHeadSigmaW + col));
+                const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.head + kHeadSigmaW + col + 4));
+                sg = fmaf(v[0], w0.x, sg); sg = fmaf(v[1], w0.y, sg); sg = fmaf(v[2], w0.z, sg); sg = fmaf(v[3], w0.w, sg);
+                sg = fmaf(v[4], w1.x, sg); sg = fmaf(v[5], w1.y, sg); sg = fmaf(v[6], w1.z, sg); sg = fmaf(v[7], w1.w, sg);
+              }
+              if (L.epi != EPI_SIGMA_OUT) store_a8<SPLIT>(h_hi, h_hi + lo_off, row, col & 63, v);
+            }
+          }
+          if (want_sigma) sigma = sg + __ldg(p.head + kHeadSigmaB);
+          if (L.epi == EPI_SIGMA_OUT) {
+            if (in.valid) p.io.out[grow] = sigma;
+          } else if (L.epi == EPI_RELU_SIGMA && p.has_dir) {
+            // the encoded position is dead after the skip layer: re-use its tile for the direction
+            float rot[3] = {0.f, 0.f, 0.f};
+            if (in.valid) normalize_dir(in.d, rot);
+            write_enc_row<SPLIT, kDirCols, kMaxDirLevels>(e_hi, e_lo, row, rot, p.dir_levels, in.valid);
+          }
+        }
+        if (l + 1 < net.n_layers) {
+          fence_proxy_async_smem();
+          tc_fence_before();
+          mbar_arrive(a_ready);
+        }
+      }
+      tc_fence_before();  // accumulator reads of the last layer precede the next tile's a_ready arrive
+    }
+  }
+
+  // ---- teardown -----------------------------------------------------------------------------------
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---- host side ----------------------------------------------------------------------------------------
+template <int NSLOTS, bool SPLIT>
+static int launch_tc_impl(nb2_handle* h, const TcParams& prm, cudaStream_t st) {
+  using LT = TcLayout<NSLOTS, SPLIT>;
+  auto kern = mlp_tc_kernel<NSLOTS, SPLIT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    NB2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, LT::kTotal));
+    attr_set = true;
+  }
+  int64_t ctas = (prm.n_tiles + NSLOTS - 1) / NSLOTS;
+  int grid = (int)std::min<int64_t>(ctas, (int64_t)h->sm_count);
+  kern<<<grid, kRolesThreads + 128 * NSLOTS, LT::kTotal, st>>>(prm);
+  NB2_LAUNCH_CHECK(h);
+  return NB2_OK;
+}
+
+int launch_mlp_tc(nb2_handle* h, int net_id, int precision, const MlpIo& io, cudaStream_t st) {
+  PackedNet& pn = h->net[net_id];
+  if (!pn.packed) {
+    set_error("mlp_forward: weights of network %d have not been packed (call nb2_pack_weights)", net_id);
+    return NB2_ERR_STATE;
+  }
+  if (io.out_mode == 2 && !(io.in_mode != 0 && (io.P == 32 || io.P == 64 || io.P == 128))) {
+    set_error("mlp_forward: fused compositing needs rays + depths with 32, 64 or 128 samples per ray (got %d)", io.P);
+    return NB2_ERR_UNSUPPORTED;
+  }
+  if (io.n_rows == 0) return NB2_OK;
+  TcParams prm;
+  prm.net = pn.tc;
+  prm.io = io;
+  prm.wchunks = pn.d_wchunks;
+  prm.bias = pn.d_bias;
+  prm.head = pn.d_head;
+  prm.pos_levels = pn.pos_levels;
+  prm.dir_levels = pn.dir_levels;
+  prm.has_dir = (net_id == NB2_NET_NERF);
+  prm.n_tiles = (io.n_rows + kTileRows - 1) / kTileRows;
+  if (precision == NB2_PREC_BF16) return launch_tc_impl<2, false>(h, prm, st);
+  if (precision == NB2_PREC_BF16X3) return launch_tc_impl<1, true>(h, prm, st);
+  set_error("mlp_forward: unknown tensor-core precision %d", precision);
+  return NB2_ERR_INVALID;
+}
+
+// ======================================================================================================
+// Self-test: D (128x128 fp32) = A (128x64 bf16) * B^T (128x64 bf16) through exactly the operand layout,
+// descriptors, bulk copy, commit and TMEM read-out used above.  A is written with generic stores (as
+// the epilogue does), B arrives through cp.async.bulk from a pre-swizzled global image (as weights do).
+// ======================================================================================================
+__global__ void __launch_bounds__(128, 1)
+umma_selftest_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __restrict__ Bswz, float* __restrict__ D) {
+  extern __shared__ unsigned char smem_dyn[];
+  const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+  unsigned char* al = smem_dyn + (base - smem_u32(smem_dyn));
+  const uint32_t a_tile = base, b_tile = base + kTileBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(al + 2 * kTileBytes);  // [0] = B landed, [1] = MMA done
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(al + 2 * kTileBytes + 64);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, row = threadIdx.x;
+
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(&bars[0]), 1);
+    mbar_init(smem_u32(&bars[1]), 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(smem_u32(tptr), 128);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tptr;
+
+  for (int g = 0; g < 8; ++g) {
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __bfloat162float(A[row * 64 + g * 8 + i]);
+    store_a8<false>(a_tile, a_tile, row, g * 8, v);
+  }
+  fence_proxy_async_smem();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_arrive_expect_tx(smem_u32(&bars[0]), kTileBytes);
+    bulk_g2s(b_tile, Bswz, kTileBytes, smem_u32(&bars[0]));
+    mbar_wait(smem_u32(&bars[0]), 0);
+    tc_fence_after();
+    const uint32_t idesc = umma_idesc_bf16(128, 128);
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks)
+      umma_bf16_ss(tmem, umma_smem_desc(a_tile + ks * 32), umma_smem_desc(b_tile + ks * 32), idesc, (uint32_t)(ks != 0));
+    umma_commit(smem_u32(&bars[1]));
+  }
+  mbar_wait(smem_u32(&bars[1]), 0);
+  tc_fence_after();
+  for (int cb = 0; cb < 4; ++cb) {
+    uint32_t r[32];
+    tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + cb * 32, r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) D[row * 128 + cb * 32 + j] = __uint_as_float(r[j]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 128);
+  }
+}
+
+// Swizzle a row-major 128x64 bf16 matrix into the tile image (used by the self-test and by tests).
+__global__ void swizzle_tile_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= kTileRows * kTileCols) return;
+  int r = i / kTileCols, c = i % kTileCols;
+  dst[swz128_offset(r, c) / 2] = src[i];
+}
+
+int selftest_umma(nb2_handle* h, const void* A, const void* B, void* Bswz_scratch, float* D, cudaStream_t st) {
+  swizzle_tile_kernel<<<(kTileRows * kTileCols + 255) / 256, 256, 0, st>>>((const __nv_bfloat16*)B,
+                                                                          (__nv_bfloat16*)Bswz_scratch);
+  NB2_LAUNCH_CHECK(h);
+  const int smem = 2 * kTileBytes + 1024 + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    NB2_CUDA(cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  umma_selftest_kernel<<<1, 128, smem, st>>>((const __nv_bfloat16*)A, (const __nv_bfloat16*)Bswz_scratch, D);
+  NB2_LAUNCH_CHECK(h);
+  return NB2_OK;
+}
+
+}  // namespace nb2

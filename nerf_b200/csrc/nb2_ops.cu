@@ -1,0 +1,664 @@
+// nb2_ops.cu — the HBM-bound stages of the ray-marching path: ray generation, stratified
+// sampling, sinusoidal / integrated positional encoding, density->weights, max-blur,
+// inverse-CDF resampling (search + sort), coarse/fine merge, alpha compositing.
+//
+// All kernels are coalesced streaming kernels: one thread per output element for the
+// elementwise stages, one warp per ray for the scan / search / sort stages (row data staged in
+// shared memory, transmittance via a warp exclusive product scan).
+#include "nb2_common.cuh"
+
+namespace nb2 {
+
+static inline int grid_for(int64_t n, int block) { return (int)((n + block - 1) / block); }
+
+// ------------------------------------------------------------------------------------------
+// a1  ray generation                                   /root/reference/nerf/procedures.py:43-51
+//   coords = (col - W/2 + 0.5, H/2 - row + 0.5) / focal ; d_i = sum_j coords_j * R_ij, c_2 = -1
+// ------------------------------------------------------------------------------------------
+__global__ void generate_rays_kernel(const float* __restrict__ pose, int H, int W, float fx,
+                                     float fy, int64_t pix_offset, int64_t n,
+                                     float* __restrict__ rays) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int64_t pix = pix_offset + i;
+  int row = (int)(pix / W), col = (int)(pix % W);
+  // the reference builds integer-valued float grids, subtracts the half extents, adds 0.5
+  float cx = __fadd_rn(__fsub_rn((float)col, (float)W / 2.f), 0.5f);
+  float cy = __fadd_rn(__fsub_rn((float)H / 2.f, (float)row), 0.5f);
+  cx = __fdiv_rn(cx, fx);
+  cy = __fdiv_rn(cy, fy);
+  float* o = rays + i * 6;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    float r0 = __ldg(pose + k * 4 + 0), r1 = __ldg(pose + k * 4 + 1), r2 = __ldg(pose + k * 4 + 2);
+    o[k] = __ldg(pose + k * 4 + 3);
+    // torch.sum over the last (size-3) axis: ((c0*r0 + c1*r1) + c2*r2), products rounded first
+    o[3 + k] = __fadd_rn(__fadd_rn(__fmul_rn(cx, r0), __fmul_rn(cy, r1)), __fmul_rn(-1.f, r2));
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// a3+a4  stratified coarse depths and points        /root/reference/nerf/procedures.py:65-66
+// ------------------------------------------------------------------------------------------
+__global__ void sample_coarse_kernel(const float* __restrict__ rays, const float* __restrict__ base_z,
+                                     const float* __restrict__ jitter, float resolution,
+                                     uint64_t seed, int64_t ray_offset, int64_t n_rays, int P,
+                                     float* __restrict__ z_out, float* __restrict__ pts_out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rays * P) return;
+  int64_t r = i / P;
+  int s = (int)(i % P);
+  float j = jitter ? jitter[i] : philox_uniform(seed, (uint64_t)(ray_offset + r), (uint32_t)s, 0u);
+  float z = __fadd_rn(__ldg(base_z + s), __fmul_rn(j, resolution));
+  z_out[i] = z;
+  if (pts_out) {
+    const float* ray = rays + r * 6;
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+      pts_out[i * 3 + k] = __fadd_rn(__ldg(ray + k), __fmul_rn(z, __ldg(ray + 3 + k)));
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// a5  sinusoidal positional encoding                /root/reference/nerf/nerf_helper.py:38-48
+//   out[p, 6l + c] = sin(2^l x[p,c]), out[p, 6l + 3 + c] = cos(2^l x[p,c])
+// One block = 128 consecutive points; (point, level, component) triples are spread over the
+// threads, the 128 x 6L tile is assembled in shared memory and written back with float4 stores.
+// ------------------------------------------------------------------------------------------
+constexpr int kPeBlockPts = 128;
+__global__ void __launch_bounds__(256) posenc_kernel(const float* __restrict__ x, int64_t n, int dims,
+                                                     int levels, float* __restrict__ out) {
+  extern __shared__ float pe_tile[];  // [kPeBlockPts][2*dims*levels]
+  const int width = 2 * dims * levels;
+  const int64_t p0 = (int64_t)blockIdx.x * kPeBlockPts;
+  const int npts = (int)min((int64_t)kPeBlockPts, n - p0);
+  const int per_pt = dims * levels;
+  for (int t = threadIdx.x; t < npts * per_pt; t += blockDim.x) {
+    int p = t / per_pt, j = t % per_pt;
+    int l = j / dims, c = j % dims;
+    float v = __ldg(x + (p0 + p) * dims + c) * exp2f((float)l);  // exact power-of-two scale
+    float s, co;
+    sincosf(v, &s, &co);
+    pe_tile[p * width + 2 * dims * l + c] = s;
+    pe_tile[p * width + 2 * dims * l + dims + c] = co;
+  }
+  __syncthreads();
+  float* dst = out + p0 * width;
+  const int total = npts * width;
+  if ((total & 3) == 0 && ((((uintptr_t)dst) & 15) == 0)) {
+    for (int t = threadIdx.x; t < total / 4; t += blockDim.x)
+      reinterpret_cast<float4*>(dst)[t] = reinterpret_cast<const float4*>(pe_tile)[t];
+  } else {
+    for (int t = threadIdx.x; t < total; t += blockDim.x) dst[t] = pe_tile[t];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// a14  integrated positional encoding              /root/reference/nerf/mip_methods.py:15-58
+// ------------------------------------------------------------------------------------------
+__global__ void ipe_sumsq_kernel(const float* __restrict__ rays, int64_t n_rays, double* __restrict__ acc) {
+  double s = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_rays; i += (int64_t)gridDim.x * blockDim.x) {
+    float a = rays[i * 6 + 3], b = rays[i * 6 + 4], c = rays[i * 6 + 5];
+    s += (double)a * a + (double)b * b + (double)c * c;
+  }
+  s = warp_sum_d(s);
+  if ((threadIdx.x & 31) == 0) atomicAdd(acc, s);
+}
+
+__global__ void ipe_kernel(const float* __restrict__ zvals, const float* __restrict__ rays,
+                           int64_t n_rays, int C, int L, float radius, const double* __restrict__ sumsq,
+                           float* __restrict__ feat, float* __restrict__ mu_out, float* __restrict__ mu_t_out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rays * C) return;
+  int64_t r = i / C;
+  int c = (int)(i % C);
+  const float gnorm = (float)sqrt(*sumsq);  // batch-global ||d||_F  (mip_methods.py:31)
+  float z0 = zvals[r * (C + 1) + c], z1 = zvals[r * (C + 1) + c + 1];
+  // coneParameters (mip_methods.py:15-23)
+  float mid = (z1 + z0) / 2.f;
+  float hw = (z1 - z0) / 2.f;
+  float diff = hw * hw;
+  float tmp1 = 3.f * mid * mid + diff;
+  float mu_t = mid + 2.f * mid * diff / tmp1;
+  float sigma_t2 = diff / 3.f - 4.f * (diff * diff) * (12.f * mid * mid - diff) / 15.f / (tmp1 * tmp1);
+  float sigma_r2 = (radius * radius) * (0.25f * mid * mid + 5.f / 12.f * diff - 4.f * diff * diff / (15.f * tmp1));
+  if (mu_t_out) mu_t_out[i] = mu_t;
+  const float* ray = rays + r * 6;
+  float* f = feat + i * (int64_t)(6 * L);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    float o = __ldg(ray + k), d = __ldg(ray + 3 + k);
+    float mu = o + mu_t * d;                       // coneMeanCov (mip_methods.py:27-33)
+    float dd = d * d;
+    float diag = sigma_t2 * dd + sigma_r2 * (1.f - dd / gnorm);
+    if (mu_out) mu_out[i * 3 + k] = mu;
+    for (int l = 0; l < L; ++l) {                   // multFreq + ipe_feature (mip_methods.py:36-58)
+      float scale = exp2f((float)l);
+      float damp = expf(-0.5f * (scale * scale * diag));
+      float s, co;
+      sincosf(scale * mu, &s, &co);
+      f[6 * l + k] = s * damp;
+      f[6 * l + 3 + k] = co * damp;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// shared warp-per-ray machinery
+// ------------------------------------------------------------------------------------------
+constexpr int kMaxSamples = 256;  // per-ray sample count supported by the warp kernels
+constexpr int kWarpsPerBlock = 8;
+
+// weights w_i = (1 - m_i) * prod_{j<i} (m_j + 1e-10), m_i = exp(-act(sigma_i) * delta_i),
+// delta_i = depth_{i+1} - depth_i (last = 1e10), depth = z * ||d||   (nerf_base.py:79-86)
+// sh_z holds the (already scaled) depths, sh_s the densities; weights are written to sh_w.
+__device__ __forceinline__ void ray_weights_warp(const float* sh_depth, const float* sh_sigma,
+                                                 float* sh_w, int P, int act, int lane) {
+  float carry = 1.f;
+  for (int base = 0; base < P; base += 32) {
+    int i = base + lane;
+    float m = 1.f, alpha = 0.f;
+    if (i < P) {
+      float delta = (i + 1 < P) ? __fsub_rn(sh_depth[i + 1], sh_depth[i]) : 1e10f;
+      m = expf(-apply_density_act(sh_sigma[i], act) * delta);
+      alpha = 1.f - m;
+    }
+    float f = (i < P) ? (m + 1e-10f) : 1.f;
+    float inc = warp_scan_mul(f, lane);
+    float exc = __shfl_up_sync(0xffffffffu, inc, 1);
+    if (lane == 0) exc = 1.f;
+    if (i < P) sh_w[i] = alpha * (carry * exc);
+    carry *= __shfl_sync(0xffffffffu, inc, 31);
+  }
+  __syncwarp();
+}
+
+__device__ __forceinline__ float dir_norm(const float* d) {
+  return sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])), __fmul_rn(d[2], d[2])));
+}
+
+// a7  ProposalNetwork.get_weights / NeRF.getNormedWeight
+__global__ void __launch_bounds__(32 * kWarpsPerBlock)
+weights_kernel(const float* __restrict__ sigma, const float* __restrict__ z, const float* __restrict__ dirs,
+               int dir_stride, int64_t n_rays, int P, int act, float* __restrict__ w_out) {
+  __shared__ float sh[kWarpsPerBlock][3][kMaxSamples];
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int64_t r = (int64_t)blockIdx.x * kWarpsPerBlock + warp;
+  if (r >= n_rays) return;
+  float nrm = 1.f;
+  if (dirs) nrm = dir_norm(dirs + r * dir_stride);
+  for (int i = lane; i < P; i += 32) {
+    float zz = z[r * P + i];
+    sh[warp][0][i] = dirs ? __fmul_rn(zz, nrm) : zz;
+    sh[warp][1][i] = sigma[r * P + i];
+  }
+  __syncwarp();
+  ray_weights_warp(sh[warp][0], sh[warp][1], sh[warp][2], P, act, lane);
+  for (int i = lane; i < P; i += 32) w_out[r * P + i] = sh[warp][2][i];
+}
+
+// a8  maxBlurFilter                                  /root/reference/nerf/mip_methods.py:61-66
+__device__ __forceinline__ float max_blur_at(const float* w, int i, int P, float alpha) {
+  float front = (i == 0) ? w[0] : fmaxf(w[i - 1], w[i]);
+  float rear = (i == P - 1) ? w[P - 1] : fmaxf(w[i], w[i + 1]);
+  return __fadd_rn(__fmul_rn(0.5f, __fadd_rn(front, rear)), alpha);
+}
+__global__ void max_blur_kernel(const float* __restrict__ w, int64_t n_rays, int P, float alpha,
+                                float* __restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rays * P) return;
+  int64_t r = i / P;
+  int s = (int)(i % P);
+  out[i] = max_blur_at(w + r * P, s, P, alpha);
+}
+
+// ------------------------------------------------------------------------------------------
+// a9  inverse-CDF sampling                       /root/reference/nerf/utils.py:34-44,108-133
+//
+// Reduction order (documented; see DESIGN.md "staged exactness"):
+//   total = fp32( sum_i (double)(w_i + 1e-5) )         (warp tree in fp64, rounded once)
+//   pdf_i = fp32(w_i + 1e-5) / total                   (IEEE fp32 divide)
+//   cdf_k = fp32( sum_{i<k} (double)pdf_i )            (fp64 running sum, rounded per element —
+//            what torch.cumsum produces on CPU for fp32 input)
+// ------------------------------------------------------------------------------------------
+// Builds cdf[0..B-1] in shared memory from B-1 weights.  sh_cdf may alias nothing else.
+__device__ __forceinline__ void build_cdf_warp(const float* sh_wgt /*B-1*/, float* sh_cdf /*B*/, int B,
+                                               int lane) {
+  const int nw = B - 1;
+  double part = 0.0;
+  for (int i = lane; i < nw; i += 32) part += (double)__fadd_rn(sh_wgt[i], 1e-5f);
+  const float total = (float)warp_sum_d(part);
+  double carry = 0.0;
+  if (lane == 0) sh_cdf[0] = 0.f;
+  for (int base = 0; base < nw; base += 32) {
+    int i = base + lane;
+    double v = (i < nw) ? (double)__fdiv_rn(__fadd_rn(sh_wgt[i], 1e-5f), total) : 0.0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      double t = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += t;
+    }
+    if (i < nw) sh_cdf[i + 1] = (float)(carry + v);
+    carry += __shfl_sync(0xffffffffu, v, 31);
+  }
+  __syncwarp();
+}
+
+// torch.searchsorted(cdf, u, right=True): first index with cdf[idx] > u, in [0, B].
+__device__ __forceinline__ int upper_bound(const float* cdf, int B, float u) {
+  int lo = 0, hi = B;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (cdf[mid] <= u) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// One draw: returns the sample, writes below/above.
+__device__ __forceinline__ float invert_cdf(const float* cdf, const float* bins, int B, float u,
+                                            int* below_o, int* above_o) {
+  int idx = upper_bound(cdf, B, u);
+  int below = max(idx - 1, 0);
+  int above = min(idx, B - 1);
+  float cb = cdf[below], ca = cdf[above];
+  float denom = __fsub_rn(ca, cb);
+  if (denom < 1e-5f) denom = 1.f;
+  float t = __fdiv_rn(__fsub_rn(u, cb), denom);
+  float bb = bins[below], ba = bins[above];
+  *below_o = below;
+  *above_o = above;
+  return __fadd_rn(bb, __fmul_rn(t, __fsub_rn(ba, bb)));
+}
+
+// Rank sort of n keys held in shared memory (ascending, ties broken by original index so the
+// result is the stable order).  Each lane owns keys lane, lane+32, ...; writes rank[] in place
+// of a scatter: out_key[rank] = key, out_pay[rank] = payload.
+__device__ __forceinline__ void rank_sort_warp(const float* sh_key, const int* sh_pay, int n,
+                                               float* sh_key_out, int* sh_pay_out, int lane) {
+  for (int i = lane; i < n; i += 32) {
+    float k = sh_key[i];
+    int rank = 0;
+    for (int j = 0; j < n; ++j) {
+      float o = sh_key[j];
+      rank += (o < k) || (o == k && j < i);
+    }
+    sh_key_out[rank] = k;
+    if (sh_pay) sh_pay_out[rank] = sh_pay[i];
+  }
+  __syncwarp();
+}
+
+constexpr int kMaxDraw = 264;  // >= 129 (Mip), 193 merged (Ref)
+
+// sample_pdf: bins (R,B), weights (R,B-1), u (R,N)
+__global__ void __launch_bounds__(32 * kWarpsPerBlock)
+sample_pdf_kernel(const float* __restrict__ bins, const float* __restrict__ weights, const float* __restrict__ u,
+                  uint64_t seed, int64_t ray_offset, int64_t n_rays, int B, int N,
+                  float* __restrict__ samples, int64_t* __restrict__ below_o, int64_t* __restrict__ above_o) {
+  __shared__ float sh_bins[kWarpsPerBlock][kMaxSamples];
+  __shared__ float sh_wgt[kWarpsPerBlock][kMaxSamples];
+  __shared__ float sh_cdf[kWarpsPerBlock][kMaxSamples];
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int64_t r = (int64_t)blockIdx.x * kWarpsPerBlock + warp;
+  if (r >= n_rays) return;
+  for (int i = lane; i < B; i += 32) sh_bins[warp][i] = bins[r * B + i];
+  for (int i = lane; i < B - 1; i += 32) sh_wgt[warp][i] = weights[r * (B - 1) + i];
+  __syncwarp();
+  build_cdf_warp(sh_wgt[warp], sh_cdf[warp], B, lane);
+  for (int i = lane; i < N; i += 32) {
+    float uu = u ? u[r * N + i] : philox_uniform(seed, (uint64_t)(ray_offset + r), (uint32_t)i, 1u);
+    int b, a;
+    samples[r * N + i] = invert_cdf(sh_cdf[warp], sh_bins[warp], B, uu, &b, &a);
+    below_o[r * N + i] = b;
+    if (above_o) above_o[r * N + i] = a;
+  }
+}
+
+__global__ void search_cdf_kernel(const float* __restrict__ cdf, const float* __restrict__ u, int64_t n_rays,
+                                  int B, int N, int64_t* __restrict__ inds) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rays * N) return;
+  int64_t r = i / N;
+  inds[i] = upper_bound(cdf + r * B, B, u[i]);
+}
+
+// The per-ray resampling core shared by inverse_sample (weights given) and resample (density
+// given).  mode 0: sh_w already holds the P proposal weights to sample from (already blurred).
+//          mode 1: sh_w holds raw density; do get_weights + maxBlur first.
+struct ResampleSmem {
+  float z[kMaxSamples];      // coarse depths
+  float a[kMaxSamples];      // density / weights scratch
+  float w[kMaxSamples];      // weights
+  float bins[kMaxSamples];   // mid points
+  float cdf[kMaxSamples];
+  float key[kMaxDraw];
+  float key_sorted[kMaxDraw];
+  int pay[kMaxDraw];
+  int pay_sorted[kMaxDraw];
+};
+
+constexpr int kResampleWarps = 4;
+__global__ void __launch_bounds__(32 * kResampleWarps)
+resample_kernel(int mode, const float* __restrict__ win /*weights or sigma (R,P)*/, const float* __restrict__ z,
+                const float* __restrict__ rays, const float* __restrict__ u, uint64_t seed, int64_t ray_offset,
+                int64_t n_rays, int P, int N, int sort, int n_keep, float blur_alpha, int act,
+                float* __restrict__ samples_out, int64_t* __restrict__ below_out) {
+  __shared__ ResampleSmem sm[kResampleWarps];
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int64_t r = (int64_t)blockIdx.x * kResampleWarps + warp;
+  if (r >= n_rays) return;
+  ResampleSmem& s = sm[warp];
+  for (int i = lane; i < P; i += 32) {
+    s.z[i] = z[r * P + i];
+    s.a[i] = win[r * P + i];
+  }
+  __syncwarp();
+  if (mode == 1) {
+    // ProposalNetwork.get_weights(density, z, dirs)     (addtional.py:99-107)
+    float nrm = dir_norm(rays + r * 6 + 3);
+    for (int i = lane; i < P; i += 32) s.bins[i] = __fmul_rn(s.z[i], nrm);  // scaled depths (temp)
+    __syncwarp();
+    ray_weights_warp(s.bins, s.a, s.cdf, P, act, lane);                      // raw weights -> cdf (temp)
+    for (int i = lane; i < P; i += 32) s.w[i] = max_blur_at(s.cdf, i, P, blur_alpha);
+    __syncwarp();
+  } else {
+    for (int i = lane; i < P; i += 32) s.w[i] = s.a[i];
+    __syncwarp();
+  }
+  // inverseSample (utils.py:34-44): bins = mid(z) (P-1), weights[1:-1] (P-2)
+  const int B = P - 1;
+  for (int i = lane; i < B; i += 32) s.bins[i] = __fmul_rn(0.5f, __fadd_rn(s.z[i + 1], s.z[i]));
+  __syncwarp();
+  build_cdf_warp(s.w + 1, s.cdf, B, lane);
+  for (int i = lane; i < N; i += 32) {
+    float uu = u ? u[r * N + i] : philox_uniform(seed, (uint64_t)(ray_offset + r), (uint32_t)i, 1u);
+    int b, a;
+    s.key[i] = invert_cdf(s.cdf, s.bins, B, uu, &b, &a);
+    s.pay[i] = b;
+  }
+  __syncwarp();
+  const float* kk = s.key;
+  const int* pp = s.pay;
+  if (sort) {
+    rank_sort_warp(s.key, s.pay, N, s.key_sorted, s.pay_sorted, lane);
+    kk = s.key_sorted;
+    pp = s.pay_sorted;
+  }
+  for (int i = lane; i < n_keep; i += 32) {
+    samples_out[r * n_keep + i] = kk[i];
+    if (below_out) below_out[r * n_keep + i] = pp[i];
+  }
+}
+
+// a10  NeRF.length2pts                               /root/reference/nerf/nerf_base.py:52-56
+__global__ void length2pts_kernel(const float* __restrict__ rays, const float* __restrict__ z, int64_t n_rays,
+                                  int P, float* __restrict__ pts) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rays * P) return;
+  int64_t r = i / P;
+  const float* ray = rays + r * 6;
+  float zz = z[i];
+  float* o = pts + i * 6;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    float d = __ldg(ray + 3 + k);
+    o[k] = __fadd_rn(__ldg(ray + k), __fmul_rn(d, zz));
+    o[3 + k] = d;
+  }
+}
+
+// a13  NeRF.coarseFineMerge                          /root/reference/nerf/nerf_base.py:58-73
+__global__ void __launch_bounds__(32 * kResampleWarps)
+merge_kernel(const float* __restrict__ rays, const float* __restrict__ cz, const float* __restrict__ fz,
+             int64_t n_rays, int C, int F, float* __restrict__ z_out, float* __restrict__ pts_out) {
+  __shared__ float key[kResampleWarps][2 * kMaxDraw];
+  __shared__ float srt[kResampleWarps][2 * kMaxDraw];
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int64_t r = (int64_t)blockIdx.x * kResampleWarps + warp;
+  if (r >= n_rays) return;
+  const int n = C + F;
+  for (int i = lane; i < F; i += 32) key[warp][i] = fz[r * F + i];      // cat((f_zvals, c_zvals))
+  for (int i = lane; i < C; i += 32) key[warp][F + i] = cz[r * C + i];
+  __syncwarp();
+  rank_sort_warp(key[warp], nullptr, n, srt[warp], nullptr, lane);
+  const float* ray = rays + r * 6;
+  for (int i = lane; i < n - 1; i += 32) {
+    float zz = srt[warp][i];
+    z_out[r * (n - 1) + i] = zz;
+    if (pts_out) {
+      float* o = pts_out + (r * (n - 1) + i) * 6;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        float d = __ldg(ray + 3 + k);
+        o[k] = __fadd_rn(__ldg(ray + k), __fmul_rn(d, zz));
+        o[3 + k] = d;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// a12  NeRF.render                                  /root/reference/nerf/nerf_base.py:90-113
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32 * kWarpsPerBlock)
+composite_kernel(const float* __restrict__ rgbo, const float* __restrict__ z, const float* __restrict__ dirs,
+                 int dir_stride, int64_t n_rays, int P, int flags, float near_t, float far_t,
+                 float* __restrict__ rgb_out, float* __restrict__ w_out, float* __restrict__ depth_out,
+                 float* __restrict__ acc_out) {
+  __shared__ float sh[kWarpsPerBlock][3][kMaxSamples];
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int64_t r = (int64_t)blockIdx.x * kWarpsPerBlock + warp;
+  if (r >= n_rays) return;
+  float nrm = dir_norm(dirs + r * dir_stride);
+  const float4* c4 = reinterpret_cast<const float4*>(rgbo) + r * P;
+  for (int i = lane; i < P; i += 32) {
+    sh[warp][0][i] = __fmul_rn(z[r * P + i], nrm);
+    sh[warp][1][i] = c4[i].w;
+  }
+  __syncwarp();
+  ray_weights_warp(sh[warp][0], sh[warp][1], sh[warp][2], P, 0, lane);
+  float cr = 0.f, cg = 0.f, cb = 0.f, acc = 0.f, dep = 0.f;
+  for (int i = lane; i < P; i += 32) {
+    float w = sh[warp][2][i];
+    float4 c = c4[i];
+    cr = fmaf(w, c.x, cr);
+    cg = fmaf(w, c.y, cg);
+    cb = fmaf(w, c.z, cb);
+    acc += w;
+    dep = fmaf(w, sh[warp][0][i], dep);
+    if (w_out) w_out[r * P + i] = w;
+  }
+  cr = warp_sum(cr); cg = warp_sum(cg); cb = warp_sum(cb); acc = warp_sum(acc); dep = warp_sum(dep);
+  if (lane == 0) {
+    if (flags & NB2_WHITE_BKG) {
+      float bg = 1.f - acc;
+      cr += bg; cg += bg; cb += bg;
+    }
+    rgb_out[r * 3 + 0] = cr;
+    rgb_out[r * 3 + 1] = cg;
+    rgb_out[r * 3 + 2] = cb;
+    if (depth_out) depth_out[r] = (dep - near_t) / (far_t - near_t);
+    if (acc_out) acc_out[r] = acc;
+  }
+}
+
+}  // namespace nb2
+
+// ==========================================================================================
+// C ABI wrappers for the stages above
+// ==========================================================================================
+using namespace nb2;
+
+#define NB2_H(h) NB2_CHECK_ARG((h) != nullptr, "null handle")
+
+extern "C" int nb2_generate_rays(nb2_handle* h, const float* pose, int H, int W, float fx, float fy,
+                                 int64_t pix_offset, int64_t n, float* rays_out, void* stream) {
+  NB2_H(h);
+  NB2_CHECK_ARG(pose && rays_out && H > 0 && W > 0 && fx != 0.f && fy != 0.f, "generate_rays: bad arguments");
+  NB2_CHECK_ARG(pix_offset >= 0 && n >= 0 && pix_offset + n <= (int64_t)H * W, "generate_rays: pixel range outside image");
+  if (n == 0) return NB2_OK;
+  generate_rays_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(pose, H, W, fx, fy, pix_offset, n, rays_out);
+  NB2_LAUNCH_CHECK(h);
+  return NB2_OK;
+}
+
+extern "C" int nb2_sample_coarse(nb2_handle* h, const float* rays, const float* base_z, const float* jitter,
+                                 float resolution, uint64_t seed, int64_t ray_offset, int64_t n_rays,
+                                 int n_samples, float* z_out, float* pts_out, void* stream) {
+  NB2_H(h);
+  NB2_CHECK_ARG(base_z && z_out && n_samples > 0 && n_rays >= 0, "sample_coarse: bad arguments");
+  NB2_CHECK_ARG(!pts_out || rays, "sample_coarse: pts_out requires rays");
+  if (n_rays == 0) return NB2_OK;
+  sample_coarse_kernel<<<grid_for(n_rays * n_samples, 256), 256, 0, (cudaStream_t)stream>>>(
+      rays, base_z, jitter, resolution, seed, ray_offset, n_rays, n_samples, z_out, pts_out);
+  NB2_LAUNCH_CHECK(h);
+  return NB2_OK;
+}
+
+extern "C" int nb2_posenc(nb2_handle* h, const float* x, int64_t n, int dims, int levels, float* out, void* stream) {
+  NB2_H(h);
+  NB2_CHECK_ARG(x && out && n >= 0 && dims >= 1 && dims <= 4 && levels >= 1 && levels <= 16, "posenc: bad arguments");
+  if (n == 0) return NB2_OK;
+  size_t smem = (size_t)kPeBlockPts * 2 * dims * levels * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    NB2_CUDA(cudaFuncSetAttribute(posenc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+    attr_set = true;
+  }
+  posenc_kernel<<<grid_for(n, kPeBlockPts), 256, smem, (cudaStream_t)stream>>>(x, n, dims, levels, out);
+  NB2_LAUNCH_CHECK(h);
+  return NB2_OK;
+}
+
+extern "C" int nb2_ipe(nb2_handle* h, const float* zvals, const float* rays, int64_t n_rays, int n_cones,
+                       int levels, float radius, float* feat_out, float* mu_out, float* mu_t_out,
+                       void* scratch, void* stream) {
+  NB2_H(h);
+  NB2_CHECK_ARG(zvals && rays && feat_out && scratch && n_cones > 0 && levels >= 1 && levels <= 16, "ipe: bad arguments");
+  if (n_rays == 0) return NB2_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  NB2_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double), st));
+  int g = (int)std::min<int64_t>(grid_for(n_rays, 256), 1184);
+  ipe_sumsq_kernel<<<g, 256, 0, st>>>(rays, n_rays, (double*)scratch);
+  NB2_LAUNCH_CHECK(h);
+  ipe_kernel<<<grid_for(n_rays * n_cones, 128), 128, 0, st>>>(zvals, rays, n_rays, n_cones, levels, radius,
+                                                             (const double*)scratch, feat_out, mu_out, mu_t_out);
+  NB2_LAUNCH_CHECK(h);
+  return NB2_OK;
+}
+
+extern "C" int nb2_weights_from_sigma(nb2_handle* h, const float* sigma, const float* z, const float* dirs,
+                                      int dir_stride, int64_t n_rays, int n_samples, int act, float* weights_out,
+                                      void* stream) {
+  NB2_H(h);
+  NB2_CHECK_ARG(sigma && z && weights_out && n_samples >= 1 && n_samples <= kMaxSamples, "weights_from_sigma: n_samples must be in [1,%d]", kMaxSamples);
+  NB2_CHECK_ARG(!dirs || dir_stride >= 3, "weights_from_sigma: dir_stride < 3");
+  NB2_CHECK_ARG(act >= 0 && act <= 2, "weights_from_sigma: unknown activation %d", act);
+  if (n_rays == 0) return NB2_OK;
+  weights_kernel<<<grid_for(n_rays, kWarpsPerBlock), 32 * kWarpsPerBlock, 0, (cudaStream_t)stream>>>(
+      sigma, z, dirs, dir_stride, n_rays, n_samples, act, weights_out);
+  NB2_LAUNCH_CHECK(h);
+  return NB2_OK;
+}
+
+extern "C" int nb2_max_blur(nb2_handle* h, const float* weights, int64_t n_rays, int n_samples, float alpha,
+                            float* out, void* stream) {
+  NB2_H(h);
+  NB2_CHECK_ARG(weights && out && n_samples >= 1, "max_blur: bad arguments");
+  if (n_rays == 0) return NB2_OK;
+  max_blur_kernel<<<grid_for(n_rays * n_samples, 256), 256, 0, (cudaStream_t)stream>>>(weights, n_rays, n_samples, alpha, out);
+  NB2_LAUNCH_CHECK(h);
+  return NB2_OK;
+}
+
+extern "C" int nb2_sample_pdf(nb2_handle* h, const float* bins, const float* weights, const float* u, uint64_t seed,
+                              int64_t ray_offset, int64_t n_rays, int n_bins, int n_draw, float* samples_out,
+                              int64_t* below_out, int64_t* above_out, void* stream) {
+  NB2_H(h);
+  NB2_CHECK_ARG(bins && weights && samples_out && below_out, "sample_pdf: null pointer");
+  NB2_CHECK_ARG(n_bins >= 2 && n_bins <= kMaxSamples, "sample_pdf: n_bins must be in [2,%d]", kMaxSamples);
+  NB2_CHECK_ARG(n_draw >= 1, "sample_pdf: n_draw < 1");
+  if (n_rays == 0) return NB2_OK;
+  sample_pdf_kernel<<<grid_for(n_rays, kWarpsPerBlock), 32 * kWarpsPerBlock, 0, (cudaStream_t)stream>>>(
+      bins, weights, u, seed, ray_offset, n_rays, n_bins, n_draw, samples_out, below_out, above_out);
+  NB2_LAUNCH_CHECK(h);
+  return NB2_OK;
+}
+
+extern "C" int nb2_search_cdf(nb2_handle* h, const float* cdf, const float* u, int64_t n_rays, int n_cdf, int n_draw,
+                              int64_t* inds_out, void* stream) {
+  NB2_H(h);
+  NB2_CHECK_ARG(cdf && u && inds_out && n_cdf >= 1 && n_draw >= 1, "search_cdf: bad arguments");
+  if (n_rays == 0) return NB2_OK;
+  search_cdf_kernel<<<grid_for(n_rays * n_draw, 256), 256, 0, (cudaStream_t)stream>>>(cdf, u, n_rays, n_cdf, n_draw, inds_out);
+  NB2_LAUNCH_CHECK(h);
+  return NB2_OK;
+}
+
+extern "C" int nb2_inverse_sample(nb2_handle* h, const float* weights, const float* z, const float* u, uint64_t seed,
+                                  int64_t ray_offset, int64_t n_rays, int n_samples, int n_draw, int sort,
+                                  float* samples_out, int64_t* below_out, void* stream) {
+  NB2_H(h);
+  NB2_CHECK_ARG(weights && z && samples_out, "inverse_sample: null pointer");
+  NB2_CHECK_ARG(n_samples >= 3 && n_samples <= kMaxSamples, "inverse_sample: n_samples must be in [3,%d]", kMaxSamples);
+  NB2_CHECK_ARG(n_draw >= 1 && n_draw <= kMaxDraw, "inverse_sample: n_draw must be in [1,%d]", kMaxDraw);
+  if (n_rays == 0) return NB2_OK;
+  resample_kernel<<<grid_for(n_rays, kResampleWarps), 32 * kResampleWarps, 0, (cudaStream_t)stream>>>(
+      0, weights, z, nullptr, u, seed, ray_offset, n_rays, n_samples, n_draw, sort, n_draw, 0.f, 0, samples_out, below_out);
+  NB2_LAUNCH_CHECK(h);
+  return NB2_OK;
+}
+
+extern "C" int nb2_resample(nb2_handle* h, const float* sigma, const float* z, const float* rays, const float* u,
+                            uint64_t seed, int64_t ray_offset, int64_t n_rays, int n_samples, int n_draw,
+                            float blur_alpha, int flags, float* z_fine_out, void* stream) {
+  NB2_H(h);
+  NB2_CHECK_ARG(sigma && z && rays && z_fine_out, "resample: null pointer");
+  NB2_CHECK_ARG(n_samples >= 3 && n_samples <= kMaxSamples, "resample: n_samples must be in [3,%d]", kMaxSamples);
+  NB2_CHECK_ARG(n_draw >= 2 && n_draw <= kMaxDraw, "resample: n_draw must be in [2,%d]", kMaxDraw);
+  if (n_rays == 0) return NB2_OK;
+  int act = (flags & NB2_DENSITY_SOFTPLUS) ? 1 : 0;
+  // softplus'd density is then passed through get_weights' own relu (a no-op on positives)
+  resample_kernel<<<grid_for(n_rays, kResampleWarps), 32 * kResampleWarps, 0, (cudaStream_t)stream>>>(
+      1, sigma, z, rays, u, seed, ray_offset, n_rays, n_samples, n_draw, 1, n_draw - 1, blur_alpha, act, z_fine_out, nullptr);
+  NB2_LAUNCH_CHECK(h);
+  return NB2_OK;
+}
+
+extern "C" int nb2_length2pts(nb2_handle* h, const float* rays, const float* z, int64_t n_rays, int n_samples,
+                              float* pts_out, void* stream) {
+  NB2_H(h);
+  NB2_CHECK_ARG(rays && z && pts_out && n_samples >= 1, "length2pts: bad arguments");
+  if (n_rays == 0) return NB2_OK;
+  length2pts_kernel<<<grid_for(n_rays * n_samples, 256), 256, 0, (cudaStream_t)stream>>>(rays, z, n_rays, n_samples, pts_out);
+  NB2_LAUNCH_CHECK(h);
+  return NB2_OK;
+}
+
+extern "C" int nb2_coarse_fine_merge(nb2_handle* h, const float* rays, const float* c_z, const float* f_z,
+                                     int64_t n_rays, int n_coarse, int n_fine, float* z_out, float* pts_out,
+                                     void* stream) {
+  NB2_H(h);
+  NB2_CHECK_ARG(rays && c_z && f_z && z_out, "coarse_fine_merge: null pointer");
+  NB2_CHECK_ARG(n_coarse >= 1 && n_fine >= 1 && n_coarse + n_fine <= 2 * kMaxDraw, "coarse_fine_merge: too many samples");
+  if (n_rays == 0) return NB2_OK;
+  merge_kernel<<<grid_for(n_rays, kResampleWarps), 32 * kResampleWarps, 0, (cudaStream_t)stream>>>(
+      rays, c_z, f_z, n_rays, n_coarse, n_fine, z_out, pts_out);
+  NB2_LAUNCH_CHECK(h);
+  return NB2_OK;
+}
+
+extern "C" int nb2_composite(nb2_handle* h, const float* rgbo, const float* z, const float* dirs, int dir_stride,
+                             int64_t n_rays, int n_samples, int flags, float near_t, float far_t, float* rgb_out,
+                             float* weights_out, float* depth_out, float* acc_out, void* stream) {
+  NB2_H(h);
+  NB2_CHECK_ARG(rgbo && z && dirs && rgb_out, "composite: null pointer");
+  NB2_CHECK_ARG(dir_stride >= 3, "composite: dir_stride < 3");
+  NB2_CHECK_ARG(n_samples >= 1 && n_samples <= kMaxSamples, "composite: n_samples must be in [1,%d]", kMaxSamples);
+  if (n_rays == 0) return NB2_OK;
+  composite_kernel<<<grid_for(n_rays, kWarpsPerBlock), 32 * kWarpsPerBlock, 0, (cudaStream_t)stream>>>(
+      rgbo, z, dirs, dir_stride, n_rays, n_samples, flags, near_t, far_t, rgb_out, weights_out, depth_out, acc_out);
+  NB2_LAUNCH_CHECK(h);
+  return NB2_OK;
+}

@@ -1,0 +1,74 @@
+// nb2_rowio.cuh — how an MLP row (one sample on one ray) gets its inputs.  Shared by the
+// CUDA-core and the tcgen05 MLP kernels so both see bit-identical points and encodings.
+#pragma once
+#include "nb2_common.cuh"
+
+namespace nb2 {
+
+struct RowIn {
+  float p[3];   // sample position
+  float d[3];   // ray direction (un-normalised), zero if the network takes none
+  float z;      // depth along the ray (0 for explicit points)
+  int64_t ray;  // ray index (row / P), or the row itself for explicit points
+  int s;        // sample index on the ray
+  bool valid;
+};
+
+__device__ __forceinline__ RowIn load_row(const MlpIo& io, int64_t row) {
+  RowIn r;
+  r.valid = row < io.n_rows;
+  r.z = 0.f;
+  r.ray = row;
+  r.s = 0;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { r.p[k] = 0.f; r.d[k] = 0.f; }
+  if (!r.valid) return r;
+  if (io.in_mode == 0) {
+    const float* src = io.pts + row * io.pts_stride;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) r.p[k] = __ldg(src + k);
+    if (io.pts_stride >= 6) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) r.d[k] = __ldg(src + 3 + k);
+    }
+    return r;
+  }
+  r.ray = row / io.P;
+  r.s = (int)(row - r.ray * io.P);
+  const float* ray = io.rays + r.ray * 6;
+  if (io.in_mode == 1) {
+    r.z = __ldg(io.z + row);
+  } else {
+    // z = linspace[s] + U[0,1) * resolution       /root/reference/nerf/procedures.py:65
+    float j = io.jitter ? __ldg(io.jitter + row)
+                        : philox_uniform(io.seed, (uint64_t)(io.ray_offset + r.ray), (uint32_t)r.s, 0u);
+    r.z = __fadd_rn(__ldg(io.base_z + r.s), __fmul_rn(j, io.resolution));
+    if (io.z_out) io.z_out[row] = r.z;
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    r.d[k] = __ldg(ray + 3 + k);
+    r.p[k] = __fadd_rn(__ldg(ray + k), __fmul_rn(r.d[k], r.z));  // o + z*d, nerf_base.py:54
+  }
+  return r;
+}
+
+// rotation = d / ||d||                             /root/reference/nerf/mip_model.py:44-45
+__device__ __forceinline__ void normalize_dir(const float d[3], float out[3]) {
+  float n = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])), __fmul_rn(d[2], d[2])));
+#pragma unroll
+  for (int k = 0; k < 3; ++k) out[k] = __fdiv_rn(d[k], n);
+}
+
+// Column c of the encoded vector [x(3), sin(2^0 x)(3), cos(2^0 x)(3), sin(2^1 x)(3), ...]
+// (cat_origin = True; nerf_helper.py:38-48 + mip_model.py:50-52).  Returns 0 past 3 + 6*levels.
+__device__ __forceinline__ float enc_column(const float x[3], int c, int levels) {
+  if (c < 3) return x[c];
+  int j = c - 3;
+  int l = j / 6, w = j % 6;
+  if (l >= levels) return 0.f;
+  float a = x[w % 3] * exp2f((float)l);
+  return (w < 3) ? sinf(a) : cosf(a);
+}
+
+}  // namespace nb2
