@@ -1,0 +1,149 @@
+"""ctypes binding of libnerfb200.so (include/nerf_b200.h).
+
+The shared library is the product: there is no Python/CPU fallback.  Importing this module
+never touches the GPU; the first call that needs the library loads it and fails loudly if it
+(or a CUDA device) is missing.
+"""
+import ctypes
+import os
+import threading
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libnerfb200.so")
+
+NET_PROPOSAL, NET_NERF = 0, 1
+PREC_FP32, PREC_BF16X3, PREC_BF16 = 0, 1, 2
+PRECISIONS = {"fp32": PREC_FP32, "bf16x3": PREC_BF16X3, "bf16": PREC_BF16}
+WHITE_BKG, DENSITY_SOFTPLUS = 1, 2
+
+c_f32p = ctypes.c_void_p
+c_i64 = ctypes.c_int64
+c_u64 = ctypes.c_uint64
+c_int = ctypes.c_int
+c_float = ctypes.c_float
+c_vp = ctypes.c_void_p
+
+
+class RenderParams(ctypes.Structure):
+    """Mirror of nb2_render_params."""
+    _fields_ = [
+        ("n_coarse", c_int), ("n_fine", c_int),
+        ("near_t", c_float), ("far_t", c_float),
+        ("resolution", c_float), ("blur_alpha", c_float),
+        ("flags", c_int), ("precision", c_int),
+        ("seed", c_u64), ("ray_offset", c_i64),
+    ]
+
+
+# name -> (restype, argtypes).  Every symbol include/nerf_b200.h declares is listed here; the
+# CPU test-suite checks the library exports all of them.
+SIGNATURES = {
+    "nb2_last_error": (ctypes.c_char_p, []),
+    "nb2_version": (c_int, []),
+    "nb2_create": (c_int, [ctypes.POINTER(c_vp), c_int]),
+    "nb2_destroy": (c_int, [c_vp]),
+    "nb2_pack_weights": (c_int, [c_vp, c_int, ctypes.POINTER(c_vp), ctypes.POINTER(c_vp), c_int, c_int, c_int, c_int, c_vp]),
+    "nb2_weights_version": (c_int, [c_vp, c_int]),
+    "nb2_generate_rays": (c_int, [c_vp, c_f32p, c_int, c_int, c_float, c_float, c_i64, c_i64, c_f32p, c_vp]),
+    "nb2_sample_coarse": (c_int, [c_vp, c_f32p, c_f32p, c_f32p, c_float, c_u64, c_i64, c_i64, c_int, c_f32p, c_f32p, c_vp]),
+    "nb2_posenc": (c_int, [c_vp, c_f32p, c_i64, c_int, c_int, c_f32p, c_vp]),
+    "nb2_ipe": (c_int, [c_vp, c_f32p, c_f32p, c_i64, c_int, c_int, c_float, c_f32p, c_f32p, c_f32p, c_vp, c_vp]),
+    "nb2_weights_from_sigma": (c_int, [c_vp, c_f32p, c_f32p, c_f32p, c_int, c_i64, c_int, c_int, c_f32p, c_vp]),
+    "nb2_max_blur": (c_int, [c_vp, c_f32p, c_i64, c_int, c_float, c_f32p, c_vp]),
+    "nb2_sample_pdf": (c_int, [c_vp, c_f32p, c_f32p, c_f32p, c_u64, c_i64, c_i64, c_int, c_int, c_f32p, c_vp, c_vp, c_vp]),
+    "nb2_inverse_sample": (c_int, [c_vp, c_f32p, c_f32p, c_f32p, c_u64, c_i64, c_i64, c_int, c_int, c_int, c_f32p, c_vp, c_vp]),
+    "nb2_search_cdf": (c_int, [c_vp, c_f32p, c_f32p, c_i64, c_int, c_int, c_vp, c_vp]),
+    "nb2_resample": (c_int, [c_vp, c_f32p, c_f32p, c_f32p, c_f32p, c_u64, c_i64, c_i64, c_int, c_int, c_float, c_int, c_f32p, c_vp]),
+    "nb2_length2pts": (c_int, [c_vp, c_f32p, c_f32p, c_i64, c_int, c_f32p, c_vp]),
+    "nb2_coarse_fine_merge": (c_int, [c_vp, c_f32p, c_f32p, c_f32p, c_i64, c_int, c_int, c_f32p, c_f32p, c_vp]),
+    "nb2_mlp_forward": (c_int, [c_vp, c_int, c_int, c_f32p, c_int, c_i64, c_f32p, c_vp]),
+    "nb2_composite": (c_int, [c_vp, c_f32p, c_f32p, c_f32p, c_int, c_i64, c_int, c_int, c_float, c_float, c_f32p, c_f32p, c_f32p, c_f32p, c_vp]),
+    "nb2_render_workspace_bytes": (c_i64, [c_i64, ctypes.POINTER(RenderParams)]),
+    "nb2_render_rays": (c_int, [c_vp, ctypes.POINTER(RenderParams), c_f32p, c_f32p, c_f32p, c_f32p, c_i64, c_f32p, c_f32p,
+                                c_f32p, c_f32p, c_f32p, c_f32p, c_vp, c_i64, c_vp]),
+    "nb2_launch_count": (c_i64, [c_vp]),
+    "nb2_selftest_umma": (c_int, [c_vp, c_vp, c_vp, c_vp, c_f32p, c_vp]),
+}
+
+_lib = None
+_lib_lock = threading.Lock()
+_handles = {}
+
+
+class NB2Error(RuntimeError):
+    pass
+
+
+def load():
+    """Load libnerfb200.so (no GPU needed for the load itself)."""
+    global _lib
+    with _lib_lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise NB2Error(
+                f"{LIB_PATH} is missing: build it with `make` (or `python -c 'import __graft_entry__ as g; g.build()'`). "
+                "nerf_b200 has no CPU or PyTorch fallback.")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+        return lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = load().nb2_last_error()
+        raise NB2Error(f"libnerfb200 error {rc}: {msg.decode() if msg else '?'}")
+
+
+def handle(device=None):
+    """One nb2_handle per CUDA device per process."""
+    if not torch.cuda.is_available():
+        raise NB2Error("nerf_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    if device is None:
+        device = torch.cuda.current_device()
+    idx = torch.device(device).index if not isinstance(device, int) else device
+    if idx is None:
+        idx = torch.cuda.current_device()
+    h = _handles.get(idx)
+    if h is None:
+        lib = load()
+        out = c_vp()
+        torch.cuda.init()
+        check(lib.nb2_create(ctypes.byref(out), idx))
+        h = out
+        _handles[idx] = h
+    return h
+
+
+def stream_ptr():
+    return c_vp(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    """Device pointer of a contiguous fp32/int64 CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise NB2Error("nerf_b200 ops take CUDA tensors (there is no CPU path)")
+    if not t.is_contiguous():
+        raise NB2Error("tensor must be contiguous")
+    return c_vp(t.data_ptr())
+
+
+def f32(t):
+    """Contiguous fp32 view/copy of a CUDA tensor."""
+    if not t.is_cuda:
+        raise NB2Error("nerf_b200 ops take CUDA tensors (there is no CPU path)")
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def launch_count(device=None):
+    return int(load().nb2_launch_count(handle(device)))

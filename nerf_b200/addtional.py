@@ -1,0 +1,92 @@
+"""Mirror of the reference's nerf/addtional.py (sic): ProposalNetwork and the PSNR helper.
+
+ProposalNetwork.forward -> nb2_mlp_forward(NB2_NET_PROPOSAL)   (reference nerf/addtional.py:88-96)
+ProposalNetwork.get_weights -> nb2_weights_from_sigma           (reference nerf/addtional.py:99-107)
+"""
+import torch
+from torch import nn
+
+from . import _lib, ops
+from .nerf_base import PackedModule
+from .nerf_helper import makeMLP
+
+
+class SoftL1Loss(nn.Module):
+    """Despite the name this is MSE, as in the reference (nerf/addtional.py:38-43)."""
+
+    def __init__(self, epsilon=0.001) -> None:
+        super().__init__()
+        self.eps = epsilon
+
+    def forward(self, pred: torch.Tensor, target: torch.Tensor):
+        return torch.mean((pred - target) ** 2)
+
+
+class LossPSNR(nn.Module):
+    """-10 ln(x) / ln 10 with the reference's constant (nerf/addtional.py:45-51)."""
+    __LOG_10__ = 2.3025851249694824
+
+    def forward(self, x):
+        return -10. * torch.log(x) / LossPSNR.__LOG_10__
+
+
+class ProposalNetwork(PackedModule):
+    _nb2_net_id = _lib.NET_PROPOSAL
+
+    @staticmethod
+    def init_weight(m):
+        if isinstance(m, nn.Linear):
+            nn.init.trunc_normal_(m.weight, std=.02)
+            if m.bias is not None:
+                nn.init.constant_(m.bias, 0)
+
+    def __init__(self, position_flevel, hidden_unit=128, cat_origin=True) -> None:
+        super().__init__()
+        self.position_dims = position_flevel * 6
+        self.position_flevel = position_flevel
+        self.cat_origin = cat_origin
+        self.hidden_unit = hidden_unit
+        extra_dims = 3 if cat_origin else 0
+        self.layers = nn.Sequential(
+            *makeMLP(self.position_dims + extra_dims, hidden_unit),
+            *makeMLP(hidden_unit, hidden_unit), *makeMLP(hidden_unit, hidden_unit), *makeMLP(hidden_unit, hidden_unit),
+            *makeMLP(hidden_unit, 1, None)
+        )
+        self.apply(self.init_weight)
+        self.precision = None
+
+    def loadFromFile(self, load_path: str, use_amp=False, other_stuff=None):
+        save = torch.load(load_path, map_location="cpu")
+        save_model = save['model']
+        state_dict = {k: save_model[k] for k in self.state_dict().keys()}
+        model_dict = self.state_dict()
+        model_dict.update(state_dict)
+        self.load_state_dict(model_dict)
+        if use_amp:
+            raise _lib.NB2Error("apex amp state is not supported by nerf_b200 (precision is chosen per call)")
+        print("NeRF Model loaded from '%s'" % (load_path))
+        if other_stuff is not None:
+            return [save[k] for k in other_stuff]
+
+    def _nb2_linears(self):
+        return [self.layers[0], self.layers[2], self.layers[4], self.layers[6], self.layers[8]]
+
+    def _nb2_levels(self):
+        if not self.cat_origin:
+            raise _lib.NB2Error("ProposalNetwork(cat_origin=False) is not supported by the CUDA kernels")
+        return self.position_flevel, 0, self.hidden_unit
+
+    def forward(self, pts: torch.Tensor, encoded_pt: torch.Tensor = None) -> torch.Tensor:
+        """pts (ray_num, point_num, 3) -> raw density (ray_num, point_num)."""
+        if encoded_pt is not None:
+            raise _lib.NB2Error("ProposalNetwork.forward(encoded_pt=...): externally encoded inputs (IPE) are not wired into "
+                                "the fused kernel yet; no reference call site uses this argument")
+        if torch.is_grad_enabled() and pts.requires_grad:
+            raise _lib.NB2Error("ProposalNetwork.forward: backward is not built yet; call under torch.no_grad()")
+        self._nb2_sync()
+        out = ops.mlp_forward(_lib.NET_PROPOSAL, pts.reshape(-1, 3), self.precision)
+        return out.view(pts.shape[0], pts.shape[1])
+
+    @staticmethod
+    def get_weights(density: torch.Tensor, zvals: torch.Tensor, ray_dirs: torch.Tensor = None) -> torch.Tensor:
+        return ops.weights_from_sigma(density, zvals, ray_dirs, "relu")

@@ -1,0 +1,144 @@
+"""Mirror of the reference's nerf/nerf_base.py: the NeRF base class and its static ray utilities.
+
+Static methods keep the reference signatures and run as CUDA kernels:
+  length2pts      -> nb2_length2pts         (reference nerf/nerf_base.py:52-56)
+  coarseFineMerge -> nb2_coarse_fine_merge  (reference nerf/nerf_base.py:58-73)
+  getNormedWeight -> nb2_weights_from_sigma (reference nerf/nerf_base.py:79-86)
+  render          -> nb2_composite          (reference nerf/nerf_base.py:90-113)
+"""
+from typing import Optional, Tuple
+
+import torch
+from torch import nn
+from torch.nn import functional as F
+
+from . import _lib, ops
+
+
+def _act_name(density_act):
+    if density_act is F.relu or density_act is torch.relu:
+        return "relu"
+    if density_act is F.softplus:
+        return "softplus"
+    if density_act is None:
+        return "identity"
+    raise _lib.NB2Error("density_act must be F.relu, F.softplus or None for the CUDA compositing kernels")
+
+
+class PackedModule(nn.Module):
+    """nn.Module whose Linear parameters are mirrored into libnerfb200's packed operand images.
+
+    Packing is lazy and keyed on the parameters' storage pointers and in-place version counters,
+    so optimizer steps and load_state_dict() trigger a re-pack on the next forward.
+    """
+    _nb2_net_id = None
+
+    def _nb2_linears(self):
+        raise NotImplementedError
+
+    def _nb2_levels(self):
+        raise NotImplementedError
+
+    def _nb2_sync(self):
+        lin = self._nb2_linears()
+        params = [p for l in lin for p in (l.weight, l.bias)]
+        if not params[0].is_cuda:
+            raise _lib.NB2Error("nerf_b200 modules run on CUDA only: call .cuda() first (there is no CPU path)")
+        key = (params[0].device.index,) + tuple((p.data_ptr(), p._version) for p in params)
+        if getattr(self, "_nb2_key", None) != key:
+            pos, dirl, hidden = self._nb2_levels()
+            # one handle per device holds ONE network of each kind: re-packing is also how several
+            # module instances share the engine (last forward wins).
+            self._nb2_keepalive = ops.pack_weights(self._nb2_net_id, [l.weight for l in lin], [l.bias for l in lin], pos, dirl,
+                                                   hidden, device=params[0].device)
+            self._nb2_key = key
+            _OWNER[(params[0].device.index, self._nb2_net_id)] = id(self)
+        elif _OWNER.get((params[0].device.index, self._nb2_net_id)) != id(self):
+            self._nb2_key = None
+            return self._nb2_sync()
+
+
+_OWNER = {}
+
+
+class NeRF(PackedModule):
+    @staticmethod
+    def init_weight(m):
+        if isinstance(m, nn.Linear):
+            nn.init.trunc_normal_(m.weight, std=.02)
+            if m.bias is not None:
+                nn.init.constant_(m.bias, 0)
+        elif isinstance(m, nn.BatchNorm1d):
+            nn.init.constant_(m.bias, 0)
+            nn.init.constant_(m.weight, 1.0)
+
+    def __init__(self, position_flevel, cat_origin=True, density_act=F.relu) -> None:
+        super().__init__()
+        self.position_flevel = position_flevel
+        self.cat_origin = cat_origin
+        self.density_act = density_act
+
+    def loadFromFile(self, load_path: str, use_amp=False, opt=None, other_stuff=None):
+        """Checkpoint loader with the reference's 'module.' prefix stripping (nerf_base.py:30-50)."""
+        save = torch.load(load_path, map_location="cpu")
+        save_model = save['model']
+        filtered_model = {(k[7:] if k.startswith("module") else k): v for k, v in save_model.items()}
+        state_dict = {k: filtered_model[k] for k in self.state_dict().keys()}
+        model_dict = self.state_dict()
+        model_dict.update(state_dict)
+        self.load_state_dict(model_dict)
+        if opt is not None:
+            opt.load_state_dict(save['optimizer'])
+        if use_amp:
+            raise _lib.NB2Error("apex amp state is not supported by nerf_b200 (precision is chosen per call)")
+        print("NeRF Model loaded from '%s'" % (load_path))
+        if other_stuff is not None:
+            return [save[k] for k in other_stuff]
+
+    @staticmethod
+    def length2pts(rays: torch.Tensor, f_zvals: torch.Tensor) -> torch.Tensor:
+        return ops.length2pts(rays, f_zvals)
+
+    @staticmethod
+    def coarseFineMerge(rays: torch.Tensor, c_zvals: torch.Tensor, f_zvals: torch.Tensor, f_inds: Optional[torch.Tensor] = None):
+        if f_inds is not None:
+            raise _lib.NB2Error("coarseFineMerge with index bookkeeping (training of Ref-NeRF) is not built yet")
+        return ops.coarse_fine_merge(rays, c_zvals, f_zvals)
+
+    @staticmethod
+    def getNormedWeight(opacity: torch.Tensor, depth: torch.Tensor, density_act=F.relu) -> torch.Tensor:
+        return ops.weights_from_sigma(opacity, depth, None, _act_name(density_act))
+
+    @staticmethod
+    def render(rgbo: torch.Tensor, depth: torch.Tensor, ray_dirs: torch.Tensor, mul_norm: bool = True, white_bkg: bool = False,
+               density_act=F.relu, render_depth: Optional[Tuple[float, float]] = None, normal_info: Optional[Tuple] = None):
+        if normal_info is not None:
+            raise _lib.NB2Error("normal rendering belongs to the Ref-NeRF branch, which is not built yet")
+        if _act_name(density_act) != "relu":
+            raise _lib.NB2Error("render(): the compositing kernel implements density_act = relu (the render path's choice)")
+        if not mul_norm:
+            ray_dirs = torch.zeros_like(ray_dirs[..., :3])
+            ray_dirs[..., 0] = 1.0  # unit norm: depth is used as given
+        rgb, weights, d, _ = ops.composite(rgbo, depth, ray_dirs, white_bkg=white_bkg, near_far=render_depth)
+        extras = dict()
+        if render_depth is not None:
+            extras["depth_img"] = d
+        return rgb, weights, extras
+
+
+class DecayLrScheduler:
+    """Host-side scalar schedule, same formula as reference nerf/nerf_base.py:115-134."""
+
+    def __init__(self, min_r, decay_r, step, lr, warmup_step=0):
+        self.min_ratio, self.decay_rate, self.decay_step, self.warmup_step, self.lr = min_r, decay_r, step, warmup_step, lr
+
+    def update_opt_lr(self, train_cnt, opt: torch.optim.Optimizer = None):
+        if train_cnt < self.warmup_step:
+            ratio = train_cnt / self.warmup_step
+            new_lrate = self.lr * (self.min_ratio * (1. - ratio) + ratio)
+        else:
+            new_lrate = self.lr * max((self.decay_rate ** ((train_cnt - self.warmup_step) / self.decay_step)), self.min_ratio)
+        if opt is not None:
+            for param_group in opt.param_groups:
+                param_group['lr'] = new_lrate
+        return opt, new_lrate

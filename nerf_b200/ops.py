@@ -1,0 +1,276 @@
+"""Tensor-level wrappers over the C ABI (one function per entry point of include/nerf_b200.h).
+
+Everything here takes and returns CUDA tensors on the current device and enqueues on the
+current CUDA stream.  Reference-named functions (positional_encoding, inverseSample, ...) live
+in the sibling modules that mirror the reference's package layout and call into this file.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import NB2Error, PRECISIONS, check, f32, handle, load, ptr, stream_ptr
+
+_default_precision = "bf16x3"
+
+
+def set_default_precision(name):
+    """'fp32' (CUDA cores, strict), 'bf16x3' (tcgen05, fp32-faithful split) or 'bf16' (tcgen05)."""
+    global _default_precision
+    if name not in PRECISIONS:
+        raise ValueError(f"unknown precision {name!r}; choose from {sorted(PRECISIONS)}")
+    _default_precision = name
+
+
+def get_default_precision():
+    return _default_precision
+
+
+def _prec(name):
+    name = _default_precision if name is None else name
+    if name not in PRECISIONS:
+        raise ValueError(f"unknown precision {name!r}; choose from {sorted(PRECISIONS)}")
+    return PRECISIONS[name]
+
+
+def _seed_from_torch():
+    """A 63-bit Philox key drawn from torch's default CPU generator (so torch.manual_seed applies)."""
+    return int(torch.randint(0, 2**62, (1,), dtype=torch.int64).item())
+
+
+# ---- a1 ---------------------------------------------------------------------------------------
+def generate_rays(pose, H, W, focal_x, focal_y, pix_offset=0, n_rays=None):
+    pose = f32(pose[:3, :4])
+    n = H * W - pix_offset if n_rays is None else n_rays
+    rays = torch.empty((n, 6), dtype=torch.float32, device=pose.device)
+    check(load().nb2_generate_rays(handle(pose.device), ptr(pose), H, W, float(focal_x), float(focal_y), pix_offset, n,
+                                   ptr(rays), stream_ptr()))
+    return rays
+
+
+# ---- a3 + a4 ----------------------------------------------------------------------------------
+def sample_coarse(rays, base_z, resolution, jitter=None, seed=0, ray_offset=0, want_pts=True):
+    rays, base_z = f32(rays), f32(base_z)
+    R, P = rays.shape[0], base_z.numel()
+    if jitter is not None:
+        jitter = f32(jitter).view(R, P)
+    z = torch.empty((R, P), dtype=torch.float32, device=rays.device)
+    pts = torch.empty((R, P, 3), dtype=torch.float32, device=rays.device) if want_pts else None
+    check(load().nb2_sample_coarse(handle(rays.device), ptr(rays), ptr(base_z), ptr(jitter), float(resolution), seed,
+                                   ray_offset, R, P, ptr(z), ptr(pts), stream_ptr()))
+    return z, pts
+
+
+# ---- a5 ---------------------------------------------------------------------------------------
+def posenc(x, levels):
+    x = f32(x)
+    dims = x.shape[-1]
+    n = x.numel() // dims
+    out = torch.empty((n, 2 * dims * levels), dtype=torch.float32, device=x.device)
+    check(load().nb2_posenc(handle(x.device), ptr(x), n, dims, levels, ptr(out), stream_ptr()))
+    return out
+
+
+# ---- a14 --------------------------------------------------------------------------------------
+def ipe(zvals, cam_rays, levels, radius):
+    zvals, cam_rays = f32(zvals), f32(cam_rays)
+    R, C = zvals.shape[0], zvals.shape[1] - 1
+    dev = zvals.device
+    feat = torch.empty((R, C, 6 * levels), dtype=torch.float32, device=dev)
+    mu = torch.empty((R, C, 3), dtype=torch.float32, device=dev)
+    mu_t = torch.empty((R, C), dtype=torch.float32, device=dev)
+    scratch = torch.empty(2, dtype=torch.float64, device=dev)
+    check(load().nb2_ipe(handle(dev), ptr(zvals), ptr(cam_rays), R, C, levels, float(radius), ptr(feat), ptr(mu),
+                         ptr(mu_t), ptr(scratch), stream_ptr()))
+    return feat, mu, mu_t
+
+
+# ---- a7 ---------------------------------------------------------------------------------------
+_ACTS = {"relu": 0, "softplus": 1, "identity": 2}
+
+
+def weights_from_sigma(sigma, z, dirs=None, act="relu"):
+    sigma, z = f32(sigma), f32(z)
+    R, P = z.shape
+    stride = 0
+    if dirs is not None:
+        dirs = f32(dirs)
+        stride = dirs.shape[-1]
+    w = torch.empty((R, P), dtype=torch.float32, device=z.device)
+    check(load().nb2_weights_from_sigma(handle(z.device), ptr(sigma), ptr(z), ptr(dirs), stride, R, P, _ACTS[act],
+                                        ptr(w), stream_ptr()))
+    return w
+
+
+# ---- a8 ---------------------------------------------------------------------------------------
+def max_blur(weights, alpha):
+    weights = f32(weights)
+    P = weights.shape[-1]
+    R = weights.numel() // P
+    out = torch.empty_like(weights)
+    check(load().nb2_max_blur(handle(weights.device), ptr(weights), R, P, float(alpha), ptr(out), stream_ptr()))
+    return out
+
+
+# ---- a9 ---------------------------------------------------------------------------------------
+def sample_pdf(bins, weights, n_draw, u=None, seed=None, ray_offset=0):
+    bins, weights = f32(bins), f32(weights)
+    R, B = bins.shape
+    if weights.shape != (R, B - 1):
+        raise NB2Error(f"sample_pdf: weights must be (R, len(bins) - 1), got {tuple(weights.shape)} for bins {tuple(bins.shape)}")
+    dev = bins.device
+    if u is not None:
+        u = f32(u).view(R, n_draw)
+    elif seed is None:
+        seed = _seed_from_torch()
+    samples = torch.empty((R, n_draw), dtype=torch.float32, device=dev)
+    below = torch.empty((R, n_draw), dtype=torch.int64, device=dev)
+    above = torch.empty((R, n_draw), dtype=torch.int64, device=dev)
+    check(load().nb2_sample_pdf(handle(dev), ptr(bins), ptr(weights), ptr(u), seed or 0, ray_offset, R, B, n_draw,
+                                ptr(samples), ptr(below), ptr(above), stream_ptr()))
+    return samples, below, above
+
+
+def inverse_sample(weights, z, n_draw, sort=False, u=None, seed=None, ray_offset=0):
+    weights, z = f32(weights), f32(z)
+    R, P = z.shape
+    dev = z.device
+    if u is not None:
+        u = f32(u).view(R, n_draw)
+    elif seed is None:
+        seed = _seed_from_torch()
+    samples = torch.empty((R, n_draw), dtype=torch.float32, device=dev)
+    below = torch.empty((R, n_draw), dtype=torch.int64, device=dev)
+    check(load().nb2_inverse_sample(handle(dev), ptr(weights), ptr(z), ptr(u), seed or 0, ray_offset, R, P, n_draw,
+                                    1 if sort else 0, ptr(samples), ptr(below), stream_ptr()))
+    return samples, below
+
+
+def search_cdf(cdf, u):
+    cdf, u = f32(cdf), f32(u)
+    R, B = cdf.shape
+    N = u.shape[1]
+    inds = torch.empty((R, N), dtype=torch.int64, device=cdf.device)
+    check(load().nb2_search_cdf(handle(cdf.device), ptr(cdf), ptr(u), R, B, N, ptr(inds), stream_ptr()))
+    return inds
+
+
+def resample(sigma, z, rays, n_draw, blur_alpha=0.01, u=None, seed=0, ray_offset=0, softplus=False):
+    sigma, z, rays = f32(sigma), f32(z), f32(rays)
+    R, P = z.shape
+    if u is not None:
+        u = f32(u).view(R, n_draw)
+    out = torch.empty((R, n_draw - 1), dtype=torch.float32, device=z.device)
+    flags = _lib.DENSITY_SOFTPLUS if softplus else 0
+    check(load().nb2_resample(handle(z.device), ptr(sigma), ptr(z), ptr(rays), ptr(u), seed, ray_offset, R, P, n_draw,
+                              float(blur_alpha), flags, ptr(out), stream_ptr()))
+    return out
+
+
+# ---- a10 / a13 ----------------------------------------------------------------------------------
+def length2pts(rays, z):
+    rays, z = f32(rays), f32(z)
+    R, P = z.shape
+    pts = torch.empty((R, P, 6), dtype=torch.float32, device=z.device)
+    check(load().nb2_length2pts(handle(z.device), ptr(rays), ptr(z), R, P, ptr(pts), stream_ptr()))
+    return pts
+
+
+def coarse_fine_merge(rays, c_z, f_z):
+    rays, c_z, f_z = f32(rays), f32(c_z), f32(f_z)
+    R, C, F = c_z.shape[0], c_z.shape[1], f_z.shape[1]
+    z = torch.empty((R, C + F - 1), dtype=torch.float32, device=c_z.device)
+    pts = torch.empty((R, C + F - 1, 6), dtype=torch.float32, device=c_z.device)
+    check(load().nb2_coarse_fine_merge(handle(c_z.device), ptr(rays), ptr(c_z), ptr(f_z), R, C, F, ptr(z), ptr(pts),
+                                       stream_ptr()))
+    return pts, z
+
+
+# ---- weights / MLP --------------------------------------------------------------------------------
+def pack_weights(net_id, weights, biases, pos_levels, dir_levels, hidden, device=None):
+    """weights/biases: lists of fp32 CUDA tensors in reference state_dict order."""
+    ws = [f32(w.detach()) for w in weights]
+    bs = [f32(b.detach()) for b in biases]
+    n = len(ws)
+    W = (ctypes.c_void_p * n)(*[w.data_ptr() for w in ws])
+    B = (ctypes.c_void_p * n)(*[b.data_ptr() for b in bs])
+    dev = ws[0].device if device is None else device
+    check(load().nb2_pack_weights(handle(dev), net_id, W, B, n, pos_levels, dir_levels, hidden, stream_ptr()))
+    return ws, bs  # keep-alive until the stream has consumed them
+
+
+def mlp_forward(net_id, pts, precision=None):
+    pts = f32(pts)
+    stride = pts.shape[-1]
+    n = pts.numel() // stride
+    dev = pts.device
+    out = torch.empty((n, 4) if net_id == _lib.NET_NERF else (n,), dtype=torch.float32, device=dev)
+    check(load().nb2_mlp_forward(handle(dev), net_id, _prec(precision), ptr(pts), stride, n, ptr(out), stream_ptr()))
+    return out
+
+
+# ---- a12 ------------------------------------------------------------------------------------------
+def composite(rgbo, z, dirs, white_bkg=False, near_far=None, want_weights=True):
+    rgbo, z, dirs = f32(rgbo), f32(z), f32(dirs)
+    R, P = z.shape
+    dev = z.device
+    rgb = torch.empty((R, 3), dtype=torch.float32, device=dev)
+    w = torch.empty((R, P), dtype=torch.float32, device=dev) if want_weights else None
+    depth = torch.empty((R,), dtype=torch.float32, device=dev) if near_far is not None else None
+    acc = torch.empty((R,), dtype=torch.float32, device=dev)
+    near, far = near_far if near_far is not None else (0.0, 1.0)
+    check(load().nb2_composite(handle(dev), ptr(rgbo), ptr(z), ptr(dirs), dirs.shape[-1], R, P,
+                               _lib.WHITE_BKG if white_bkg else 0, float(near), float(far), ptr(rgb), ptr(w), ptr(depth),
+                               ptr(acc), stream_ptr()))
+    return rgb, w, depth, acc
+
+
+# ---- the fused path ---------------------------------------------------------------------------------
+def render_rays(rays, base_z, near, far, n_fine=128, white_bkg=False, precision=None, jitter=None, u=None, seed=0,
+                ray_offset=0, resolution=None, blur_alpha=0.01, softplus=False, debug=False, workspace=None):
+    """rays (R,6) -> dict(rgb (R,3), depth (R), acc (R) [, z_coarse, sigma_prop, z_fine])."""
+    rays, base_z = f32(rays), f32(base_z)
+    R, Pc = rays.shape[0], base_z.numel()
+    dev = rays.device
+    p = _lib.RenderParams()
+    p.n_coarse, p.n_fine = Pc, n_fine
+    p.near_t, p.far_t = float(near), float(far)
+    p.resolution = float((far - near) / n_fine if resolution is None else resolution)
+    p.blur_alpha = float(blur_alpha)
+    p.flags = (_lib.WHITE_BKG if white_bkg else 0) | (_lib.DENSITY_SOFTPLUS if softplus else 0)
+    p.precision = _prec(precision)
+    p.seed, p.ray_offset = seed, ray_offset
+    lib = load()
+    need = lib.nb2_render_workspace_bytes(R, ctypes.byref(p))
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty(max(need, 256), dtype=torch.uint8, device=dev)
+    if jitter is not None:
+        jitter = f32(jitter).view(R, Pc)
+    if u is not None:
+        u = f32(u).view(R, n_fine + 1)
+    out = {
+        "rgb": torch.empty((R, 3), dtype=torch.float32, device=dev),
+        "depth": torch.empty((R,), dtype=torch.float32, device=dev),
+        "acc": torch.empty((R,), dtype=torch.float32, device=dev),
+    }
+    zc = sp = zf = None
+    if debug:
+        zc = torch.empty((R, Pc), dtype=torch.float32, device=dev)
+        sp = torch.empty((R, Pc), dtype=torch.float32, device=dev)
+        zf = torch.empty((R, n_fine), dtype=torch.float32, device=dev)
+        out.update(z_coarse=zc, sigma_prop=sp, z_fine=zf)
+    check(lib.nb2_render_rays(handle(dev), ctypes.byref(p), ptr(rays), ptr(base_z), ptr(jitter), ptr(u), R, ptr(out["rgb"]),
+                              ptr(out["depth"]), ptr(out["acc"]), ptr(zc), ptr(sp), ptr(zf), ptr(workspace),
+                              workspace.numel(), stream_ptr()))
+    out["_workspace"] = workspace
+    return out
+
+
+def selftest_umma(A, B):
+    """D = A @ B.T through one tcgen05 MMA sequence; A, B: (128, 64) bf16 CUDA tensors."""
+    A = A.to(torch.bfloat16).contiguous()
+    B = B.to(torch.bfloat16).contiguous()
+    D = torch.empty((128, 128), dtype=torch.float32, device=A.device)
+    scratch = torch.empty(16384, dtype=torch.uint8, device=A.device)
+    check(load().nb2_selftest_umma(handle(A.device), ptr(A), ptr(B), ptr(scratch), ptr(D), stream_ptr()))
+    return D

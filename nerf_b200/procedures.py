@@ -1,0 +1,94 @@
+"""Mirror of the reference's nerf/procedures.py: render_image, the hot path.
+
+The reference walks 50x50-pixel tiles serially, ~1.1k PyTorch ops and two CPU-RNG -> GPU copies
+per tile (reference nerf/procedures.py:60-90).  Here the whole image is one ray batch: rays are
+generated on the device, and nb2_render_rays runs three kernels (fused sample+encode+proposal
+MLP, resample, fused encode+NeRF MLP+composite) over all H*W rays.
+"""
+from collections.abc import Iterable
+
+import torch
+
+from . import _lib, ops
+from .addtional import ProposalNetwork
+from .nerf_base import NeRF
+
+POSSIBLE_PATCH_SIZE = [50, 40, 60, 30]
+RENDER_COARSE_PNUM = 64
+
+
+def get_patch_size(image_size):
+    """Tile size the reference would use (nerf/procedures.py:24-31).  Only the 'reference' RNG mode
+    needs it (to replay the reference's per-tile draw order); unlike the reference it returns a
+    single whole-image tile instead of crashing when no candidate divides the width."""
+    for patch_size in POSSIBLE_PATCH_SIZE:
+        if image_size[1] % patch_size == 0 and image_size[0] % patch_size == 0:
+            return patch_size, (image_size[0] // patch_size, image_size[1] // patch_size)
+    return None, (1, 1)
+
+
+def _reference_rng_draws(image_size, n_coarse, n_draw):
+    """Replay the reference's CPU draws in its tile order and scatter them to raster order:
+    per tile torch.rand((sz, sz, 64)) for the jitter (procedures.py:65) then torch.rand((sz*sz, 129))
+    inside sample_pdf (utils.py:115)."""
+    H, W = image_size
+    sz, patch_num = get_patch_size(image_size)
+    jitter = torch.empty((H, W, n_coarse), dtype=torch.float32)
+    u = torch.empty((H, W, n_draw), dtype=torch.float32)
+    if sz is None:
+        jitter.copy_(torch.rand((H, W, n_coarse)))
+        u.copy_(torch.rand((H * W, n_draw)).view(H, W, n_draw))
+        return jitter.view(H * W, n_coarse), u.view(H * W, n_draw)
+    for k in range(patch_num[0]):
+        for j in range(patch_num[1]):
+            jitter[sz * k:sz * (k + 1), sz * j:sz * (j + 1)] = torch.rand((sz, sz, n_coarse))
+            u[sz * k:sz * (k + 1), sz * j:sz * (j + 1)] = torch.rand((sz * sz, n_draw)).view(sz, sz, n_draw)
+    return jitter.view(H * W, n_coarse), u.view(H * W, n_draw)
+
+
+def render_image(
+    network: NeRF, prop_net: ProposalNetwork, render_pose: torch.Tensor, image_size, focal,
+    near: float, far: float, sample_num: int = 128, white_bkg: bool = False, render_depth=False, render_normal=False,
+    *, precision=None, rng="philox", seed=None, jitter=None, u=None,
+):
+    """Same positional signature and return value as the reference (nerf/procedures.py:34-97):
+    {"rgb": (3,H,W)[, "depth_img": (3,H,W)]} on render_pose.device.
+
+    Keyword-only extensions: `precision` ('fp32' | 'bf16x3' | 'bf16'); `rng` = 'philox' (device
+    counter-based RNG, seed from torch's CPU generator unless `seed` is given) or 'reference'
+    (replays the reference's CPU torch.rand draws tile by tile, so the same torch.manual_seed gives
+    the same samples as the reference); `jitter` (H*W, 64) / `u` (H*W, sample_num+1) inject the
+    uniforms directly (raster order).
+    """
+    if not isinstance(image_size, Iterable):
+        image_size = (image_size, image_size)
+    H, W = int(image_size[0]), int(image_size[1])
+    if render_normal:
+        raise _lib.NB2Error("render_normal is a Ref-NeRF feature, which is not built yet")
+    dev = render_pose.device
+    if dev.type != "cuda":
+        raise _lib.NB2Error("render_image: render_pose must live on a CUDA device (there is no CPU path)")
+    if isinstance(focal, Iterable):
+        fx, fy = float(focal[1]), float(focal[0])
+    else:
+        fx = fy = float(focal)
+    with torch.no_grad():
+        network._nb2_sync()
+        prop_net._nb2_sync()
+        rays = ops.generate_rays(render_pose, H, W, fx, fy)
+        base_z = torch.linspace(near, far, RENDER_COARSE_PNUM, device=dev)       # procedures.py:52
+        resolution = (far - near) / sample_num                                    # procedures.py:59
+        if jitter is None and u is None and rng == "reference":
+            jitter, u = _reference_rng_draws((H, W), RENDER_COARSE_PNUM, sample_num + 1)
+            jitter, u = jitter.to(dev, non_blocking=True), u.to(dev, non_blocking=True)
+        elif rng not in ("philox", "reference"):
+            raise ValueError(f"unknown rng mode {rng!r}")
+        if seed is None:
+            seed = ops._seed_from_torch() if (jitter is None or u is None) else 0
+        prec = precision if precision is not None else (network.precision or prop_net.precision)
+        out = ops.render_rays(rays, base_z, near, far, n_fine=sample_num, white_bkg=white_bkg, precision=prec,
+                              jitter=jitter, u=u, seed=seed, resolution=resolution)
+        result = {"rgb": out["rgb"].view(H, W, 3).permute(2, 0, 1).contiguous()}
+        if render_depth:
+            result["depth_img"] = out["depth"].view(1, H, W).expand(3, H, W).contiguous()
+    return result

@@ -1,0 +1,386 @@
+"""oracle/nerf_oracle.py — CPU restatement of the reference's ray-marching path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing under nerf_b200/ imports this file; only tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may.  It is the
+checker, never the thing measured or shipped.
+
+What it is: the algorithm of Enigmatisms/NeRF's `render_image` hot path (SURVEY.md §8a rows
+a1-a14) written as plain functions over explicit parameter dictionaries, with every random
+draw passed in as an argument (the reference draws `torch.rand` on the CPU in the middle of the
+computation: nerf/procedures.py:65, nerf/utils.py:115).  The arithmetic is fp32 PyTorch tensor
+ops, because that is what the reference's arithmetic *is*: all its numerics live in the
+third-party dependency PyTorch (requirements.txt pins torch==2.6.0; this image has 2.11.0 —
+version drift that no reference test pins).  The functions are device-agnostic: tests run them
+on the CPU at small sizes and on `cuda` for full-size parity (the reference's own GPU path).
+
+Pinning: the reference ships no tests, golden vectors or fixtures.  The oracle
+is pinned instead against outputs of the reference itself: tests/golden/make_golden.py imports
+/root/reference/nerf unmodified (with import shims), runs its functions on seeded inputs and
+commits the results as tests/golden/*.npz; tests/test_oracle_golden.py checks this file against
+them.
+
+Each function cites the reference lines it restates (paths relative to /root/reference).
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+# ----------------------------------------------------------------------------------------------
+# deterministic parameters (platform-independent: integer hashing + exact float conversions)
+# ----------------------------------------------------------------------------------------------
+_MASK = (1 << 64) - 1
+
+
+def _mix64(x):
+    """splitmix64 finaliser on a numpy uint64 array."""
+    x = (x + np.uint64(0x9E3779B97F4A7C15)) & np.uint64(_MASK)
+    x = ((x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)) & np.uint64(_MASK)
+    x = ((x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)) & np.uint64(_MASK)
+    return x ^ (x >> np.uint64(31))
+
+
+def det_uniform(shape, seed, lo=-1.0, hi=1.0):
+    """Deterministic fp32 uniforms in [lo, hi): 24-bit hash -> exact float32 arithmetic."""
+    n = int(np.prod(shape))
+    with np.errstate(over="ignore"):
+        idx = np.arange(n, dtype=np.uint64) + np.uint64(seed) * np.uint64(0x100000001B3)
+        bits = _mix64(idx) >> np.uint64(40)
+    u = bits.astype(np.float32) * np.float32(1.0 / 16777216.0)
+    out = (np.float32(lo) + u * np.float32(hi - lo)).astype(np.float32)
+    return torch.from_numpy(out.reshape(shape))
+
+
+PROPOSAL_KEYS = ["layers.0", "layers.2", "layers.4", "layers.6", "layers.8"]
+NERF_KEYS = ["lin_block1.0", "lin_block1.2", "lin_block1.4", "lin_block1.6", "lin_block2.0", "lin_block2.2",
+             "lin_block2.4", "bottle_neck.0", "opacity_head.0", "rgb_layer.0", "rgb_layer.2"]
+
+
+def layer_shapes(kind, pos_levels=10, dir_levels=4, hidden=256):
+    """(out, in) of every nn.Linear, in state_dict order (nerf/addtional.py:67-71, nerf/mip_model.py:19-37)."""
+    enc, denc = 3 + 6 * pos_levels, 3 + 6 * dir_levels
+    if kind == "proposal":
+        return [(hidden, enc), (hidden, hidden), (hidden, hidden), (hidden, hidden), (1, hidden)]
+    return [(hidden, enc), (hidden, hidden), (hidden, hidden), (hidden, hidden), (hidden, hidden + enc),
+            (hidden, hidden), (256, hidden), (256, 256), (1, 256), (128, 256 + denc), (3, 128)]
+
+
+def np_forward(kind, sd, pts, pos_levels=10, dir_levels=4):
+    """fp64 numpy forward of either MLP (same citations as proposal_forward / nerf_forward below).
+    Used to calibrate the synthetic density head and as the "infinitely precise" yardstick when the
+    tests compare the error of the engine with the error of the reference's own fp32 arithmetic."""
+    g = {k: v.numpy().astype(np.float64) for k, v in sd.items()}
+    pts = np.asarray(pts, dtype=np.float64)
+
+    def enc(x, levels):
+        parts = [x]
+        for f in range(levels):
+            parts += [np.sin((2.0 ** f) * x), np.cos((2.0 ** f) * x)]
+        return np.concatenate(parts, axis=-1)
+
+    def lin(h, key, relu=True):
+        y = h @ g[key + ".weight"].T + g[key + ".bias"]
+        return np.maximum(y, 0.0) if relu else y
+
+    x = pts[..., :3]
+    ex = enc(x, pos_levels)
+    if kind == "proposal":
+        h = ex
+        for key in PROPOSAL_KEYS[:-1]:
+            h = lin(h, key)
+        return lin(h, "layers.8", relu=False)[..., 0]
+    d = pts[..., 3:6]
+    er = enc(d / np.linalg.norm(d, axis=-1, keepdims=True), dir_levels)
+    h = ex
+    for key in NERF_KEYS[:4]:
+        h = lin(h, key)
+    h = np.concatenate((ex, h), axis=-1)
+    for key in NERF_KEYS[4:7]:
+        h = lin(h, key)
+    sigma = lin(h, "opacity_head.0", relu=False)
+    b = lin(h, "bottle_neck.0", relu=False)
+    t = lin(np.concatenate((b, er), axis=-1), "rgb_layer.0")
+    rgb = 1.0 / (1.0 + np.exp(-lin(t, "rgb_layer.2", relu=False)))
+    return np.concatenate((rgb, sigma), axis=-1)
+
+
+def make_params(kind, seed, style="he", pos_levels=10, dir_levels=4, hidden=256, sigma_std=25.0, sigma_mean=5.0):
+    """state_dict-shaped deterministic parameters.
+
+    style 'he'      : uniform with He variance and small biases; the density head is then rescaled and
+                      re-biased (from an fp64 forward over fixed probe points) so the raw density has
+                      mean `sigma_mean` and std `sigma_std` over the scene volume -> a non-degenerate
+                      random field with empty and opaque regions.  (A deep ReLU net at init is almost
+                      constant in space, so without this every sample would have the same sign.)
+    style 'refinit' : the reference's init scale (std 0.02, zero bias; nerf/nerf_base.py:14-22) ->
+                      the tiny-activation regime every freshly constructed reference model is in.
+    """
+    keys = PROPOSAL_KEYS if kind == "proposal" else NERF_KEYS
+    head = "layers.8" if kind == "proposal" else "opacity_head.0"
+    sd = {}
+    for i, (key, (o, k)) in enumerate(zip(keys, layer_shapes(kind, pos_levels, dir_levels, hidden))):
+        if style == "he":
+            bound = math.sqrt(6.0 / k)
+            w = det_uniform((o, k), seed * 1000 + 2 * i, -bound, bound)
+            b = det_uniform((o,), seed * 1000 + 2 * i + 1, -0.1, 0.1)
+        else:
+            bound = 0.02 * math.sqrt(3.0)
+            w = det_uniform((o, k), seed * 1000 + 2 * i, -bound, bound)
+            b = torch.zeros(o)
+        sd[key + ".weight"], sd[key + ".bias"] = w, b
+    if style == "he":
+        probe = torch.cat((det_uniform((1024, 3), seed * 1000 + 777, -2.0, 2.0),
+                           det_uniform((1024, 3), seed * 1000 + 778, -1.0, 1.0)), dim=-1).numpy()
+        out = np_forward(kind, sd, probe, pos_levels, dir_levels)
+        sig = out if kind == "proposal" else out[..., 3]
+        gain = sigma_std / float(sig.std())
+        # round the calibration constants to 6 significant digits: robust to last-bit fp64 differences
+        gain = float(f"{gain:.6g}")
+        shift = float(f"{sigma_mean - gain * float(sig.mean() - sd[head + '.bias'].item()):.6g}")
+        sd[head + ".weight"] = (sd[head + ".weight"].numpy() * np.float32(gain)).astype(np.float32)
+        sd[head + ".weight"] = torch.from_numpy(sd[head + ".weight"])
+        sd[head + ".bias"] = torch.tensor([shift], dtype=torch.float32)
+    return sd
+
+
+def params_to(sd, device=None, dtype=None):
+    return {k: v.to(device=device, dtype=dtype) for k, v in sd.items()}
+
+
+# ----------------------------------------------------------------------------------------------
+# a5  positional encoding                                      nerf/nerf_helper.py:38-48
+# ----------------------------------------------------------------------------------------------
+def positional_encoding(x, levels):
+    parts = []
+    for f in range(levels):
+        parts.append(torch.sin((2.0 ** f) * x))
+        parts.append(torch.cos((2.0 ** f) * x))
+    return torch.cat(parts, dim=-1)
+
+
+# ----------------------------------------------------------------------------------------------
+# a6  proposal MLP                                             nerf/addtional.py:61-72,88-96
+# ----------------------------------------------------------------------------------------------
+def proposal_forward(sd, pts, pos_levels=10):
+    """pts (..., 3) -> raw density (...)."""
+    h = torch.cat((pts, positional_encoding(pts, pos_levels)), dim=-1)       # cat_origin
+    for key in PROPOSAL_KEYS[:-1]:
+        h = F.relu(F.linear(h, sd[key + ".weight"], sd[key + ".bias"]))
+    return F.linear(h, sd["layers.8.weight"], sd["layers.8.bias"]).squeeze(-1)
+
+
+# ----------------------------------------------------------------------------------------------
+# a11  NeRF MLP                                                nerf/mip_model.py:41-60
+# ----------------------------------------------------------------------------------------------
+def nerf_forward(sd, pts6, pos_levels=10, dir_levels=4):
+    """pts6 (..., 6) = [xyz, dir] -> (..., 4) = [sigmoid rgb, raw sigma]."""
+    x, d = pts6[..., :3], pts6[..., 3:6]
+    rot = d / d.norm(dim=-1, keepdim=True)                                    # :44-45
+    enc_x = torch.cat((x, positional_encoding(x, pos_levels)), dim=-1)       # :50-51
+    enc_r = torch.cat((rot, positional_encoding(rot, dir_levels)), dim=-1)   # :52
+    h = enc_x
+    for key in NERF_KEYS[:4]:                                                 # lin_block1  :54
+        h = F.relu(F.linear(h, sd[key + ".weight"], sd[key + ".bias"]))
+    h = torch.cat((enc_x, h), dim=-1)                                         # skip concat :55
+    for key in NERF_KEYS[4:7]:                                                # lin_block2  :56
+        h = F.relu(F.linear(h, sd[key + ".weight"], sd[key + ".bias"]))
+    sigma = F.linear(h, sd["opacity_head.0.weight"], sd["opacity_head.0.bias"])   # :57
+    b = F.linear(h, sd["bottle_neck.0.weight"], sd["bottle_neck.0.bias"])         # :58
+    t = F.relu(F.linear(torch.cat((b, enc_r), dim=-1), sd["rgb_layer.0.weight"], sd["rgb_layer.0.bias"]))
+    rgb = torch.sigmoid(F.linear(t, sd["rgb_layer.2.weight"], sd["rgb_layer.2.bias"]))  # :59
+    return torch.cat((rgb, sigma), dim=-1)                                    # :60
+
+
+# ----------------------------------------------------------------------------------------------
+# a7  density -> weights                nerf/addtional.py:99-107 (relu) == nerf/nerf_base.py:79-86
+# ----------------------------------------------------------------------------------------------
+def weights_from_sigma(sigma, z, dirs=None, act=F.relu):
+    if dirs is not None:
+        z = z * dirs.norm(dim=-1, keepdim=True)
+    big = torch.full((z.shape[0], 1), 1e10, dtype=z.dtype, device=z.device)
+    delta = torch.cat((z[:, 1:] - z[:, :-1], big), dim=-1)
+    mult = torch.exp(-(act(sigma) if act is not None else sigma) * delta)
+    alpha = 1.0 - mult
+    ones = torch.ones((z.shape[0], 1), dtype=z.dtype, device=z.device)
+    trans = torch.cumprod(torch.cat((ones, mult + 1e-10), dim=-1), dim=-1)[:, :-1]
+    return alpha * trans
+
+
+# ----------------------------------------------------------------------------------------------
+# a8  max-blur filter                                          nerf/mip_methods.py:61-66
+# ----------------------------------------------------------------------------------------------
+def max_blur(w, alpha):
+    mx = torch.maximum(w[..., :-1], w[..., 1:])
+    front = torch.cat((w[..., :1], mx), dim=-1)
+    rear = torch.cat((mx, w[..., -1:]), dim=-1)
+    return 0.5 * (front + rear) + alpha
+
+
+# ----------------------------------------------------------------------------------------------
+# a9  inverse-CDF sampling                                     nerf/utils.py:108-133, :34-44
+# ----------------------------------------------------------------------------------------------
+def build_cdf(weights):
+    """pdf / cdf of sample_pdf (utils.py:110-113), in the reduction order the CUDA kernel documents:
+    total = fp32(sum in fp64), cdf_k = fp32(running fp64 sum of fp32 pdf) — the latter is what
+    torch.cumsum does on the CPU for fp32 input."""
+    w = weights + 1e-5
+    total = w.double().sum(dim=-1, keepdim=True).to(w.dtype)
+    pdf = w / total
+    cdf = torch.cumsum(pdf.double(), dim=-1).to(w.dtype)
+    return torch.cat((torch.zeros_like(cdf[..., :1]), cdf), dim=-1)
+
+
+def build_cdf_torch(weights):
+    """The same with torch's own fp32 `sum` (utils.py:110-113 verbatim semantics; reduction order is
+    whatever ATen picks on this machine)."""
+    w = weights + 1e-5
+    pdf = w / torch.sum(w, -1, keepdim=True)
+    cdf = torch.cumsum(pdf, -1)
+    return torch.cat((torch.zeros_like(cdf[..., :1]), cdf), dim=-1)
+
+
+def invert_cdf(cdf, bins, u):
+    """utils.py:119-131: searchsorted(right=True), clamp, gather, guarded lerp."""
+    u = u.contiguous()
+    inds = torch.searchsorted(cdf.contiguous(), u, right=True)
+    below = torch.clamp(inds - 1, min=0)
+    above = torch.clamp(inds, max=cdf.shape[-1] - 1)
+    cdf_b, cdf_a = torch.gather(cdf, -1, below), torch.gather(cdf, -1, above)
+    bins_b, bins_a = torch.gather(bins, -1, below), torch.gather(bins, -1, above)
+    denom = cdf_a - cdf_b
+    denom = torch.where(denom < 1e-5, torch.ones_like(denom), denom)
+    t = (u - cdf_b) / denom
+    return bins_b + t * (bins_a - bins_b), below, above
+
+
+def sample_pdf(bins, weights, u, torch_sum=False):
+    cdf = build_cdf_torch(weights) if torch_sum else build_cdf(weights)
+    return invert_cdf(cdf, bins, u)
+
+
+def inverse_sample(weights, z, u, sort=True, torch_sum=False):
+    """utils.py:34-44: mid-point bins, interior weights, optional sort with index gather."""
+    mids = 0.5 * (z[..., 1:] + z[..., :-1])
+    samples, below, _ = sample_pdf(mids, weights[..., 1:-1], u, torch_sum=torch_sum)
+    if sort:
+        samples, order = torch.sort(samples, dim=-1)
+        below = torch.gather(below, -1, order)
+    return samples, below
+
+
+# ----------------------------------------------------------------------------------------------
+# a10 / a13  sample points                                     nerf/nerf_base.py:52-56, :58-73
+# ----------------------------------------------------------------------------------------------
+def length2pts(rays, z):
+    pts = rays[:, None, :3] + rays[:, None, 3:] * z[:, :, None]
+    return torch.cat((pts, rays[:, None, 3:].expand(-1, z.shape[1], -1)), dim=-1)
+
+
+def coarse_fine_merge(rays, c_z, f_z):
+    z, _ = torch.sort(torch.cat((f_z, c_z), dim=-1), dim=-1)
+    z = z[..., :-1]
+    return length2pts(rays, z), z
+
+
+# ----------------------------------------------------------------------------------------------
+# a12  alpha compositing                                       nerf/nerf_base.py:90-113
+# ----------------------------------------------------------------------------------------------
+def composite(rgbo, z, dirs, white_bkg=False, near_far=None):
+    depth = z * dirs.norm(dim=-1, keepdim=True)
+    w = weights_from_sigma(rgbo[..., -1], depth, None, F.relu)
+    rgb = torch.sum(w[:, :, None] * rgbo[..., :3], dim=-2)
+    acc = torch.sum(w, -1)
+    if white_bkg:
+        rgb = rgb + (1.0 - acc[..., None])
+    out = {"rgb": rgb, "weights": w, "acc": acc}
+    if near_far is not None:
+        near, far = near_far
+        out["depth"] = (torch.sum(w * depth, dim=-1) - near) / (far - near)
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# a1  ray generation                                           nerf/procedures.py:43-51
+# ----------------------------------------------------------------------------------------------
+def generate_rays(pose, H, W, focal):
+    """pose (3,4) -> rays (H*W, 6) in raster order: [origin, R @ (cx/fx, cy/fy, -1)] (un-normalised)."""
+    col, row = torch.meshgrid(torch.arange(W), torch.arange(H), indexing="xy")
+    coords = torch.stack((col - W / 2, H / 2 - row), dim=-1).to(pose.device) + 0.5
+    fx, fy = (focal[1], focal[0]) if isinstance(focal, (tuple, list)) else (focal, focal)
+    coords = torch.stack((coords[..., 0] / fx, coords[..., 1] / fy), dim=-1)
+    coords = torch.cat((coords, -torch.ones(H, W, 1, dtype=torch.float32, device=pose.device)), dim=-1)
+    dirs = torch.sum(coords.unsqueeze(-2) * pose[..., :-1], dim=-1)
+    origin = pose[:, -1].expand(H, W, -1)
+    return torch.cat((origin, dirs), dim=-1).reshape(-1, 6)
+
+
+# ----------------------------------------------------------------------------------------------
+# a14  integrated positional encoding                          nerf/mip_methods.py:15-58
+# ----------------------------------------------------------------------------------------------
+def ipe_feature(zvals, rays, levels, r):
+    mid = (zvals[:, 1:] + zvals[:, :-1]) / 2
+    diff = ((zvals[:, 1:] - zvals[:, :-1]) / 2) ** 2
+    t1 = 3 * mid ** 2 + diff
+    mu_t = mid + 2 * mid * diff / t1
+    sig_t2 = diff / 3 - 4 * (diff ** 2) * (12 * mid ** 2 - diff) / 15 / (t1 ** 2)
+    sig_r2 = (r ** 2) * (0.25 * mid ** 2 + 5 / 12 * diff - 4 * diff ** 2 / (15 * t1))
+    d = rays[:, 3:]
+    mu = rays[:, None, :3] + mu_t[:, :, None] * d[:, None, :]
+    dd = d * d
+    i_m = 1.0 - dd / d.norm()                                   # batch-global norm, :31
+    diag = sig_t2[:, :, None] * dd[:, None, :] + sig_r2[:, :, None] * i_m[:, None, :]
+    scales = torch.tensor([2.0 ** i for i in range(levels)], dtype=zvals.dtype, device=zvals.device)
+    mu_r = scales[None, None, :, None] * mu[:, :, None, :]                       # (R,C,L,3)
+    damp = torch.exp(-0.5 * (scales ** 2)[None, None, :, None] * diag[:, :, None, :])
+    feat = torch.cat((torch.sin(mu_r) * damp, torch.cos(mu_r) * damp), dim=-1)   # (R,C,L,6)
+    return feat.reshape(zvals.shape[0], zvals.shape[1] - 1, 6 * levels), mu, mu_t
+
+
+# ----------------------------------------------------------------------------------------------
+# the per-ray path of render_image                             nerf/procedures.py:64-85
+# ----------------------------------------------------------------------------------------------
+def render_rays(sd_prop, sd_nerf, rays, base_z, jitter, u, near, far, n_fine=128, white_bkg=False, resolution=None,
+                blur_alpha=0.01, softplus=False, pos_levels=10, dir_levels=4, torch_sum=False, chunk=4096):
+    """rays (R,6), jitter (R,Pc), u (R,n_fine+1) -> dict with every intermediate the tests compare."""
+    resolution = (far - near) / n_fine if resolution is None else resolution
+    outs = {k: [] for k in ("rgb", "depth", "acc", "z_coarse", "sigma_prop", "z_fine", "below", "weights", "rgbo")}
+    for s in range(0, rays.shape[0], chunk):
+        r, j, uu = rays[s:s + chunk], jitter[s:s + chunk], u[s:s + chunk]
+        z_c = base_z + j * resolution                                             # :65
+        pts = r[:, None, :3] + z_c[..., None] * r[:, None, 3:]                    # :66
+        sigma_p = proposal_forward(sd_prop, pts, pos_levels)                      # :67
+        if softplus:
+            sigma_p = F.softplus(sigma_p)                                         # train.py:169
+        w_p = max_blur(weights_from_sigma(sigma_p, z_c, r[:, 3:]), blur_alpha)    # :68-69
+        z_f, below = inverse_sample(w_p, z_c, uu, sort=True, torch_sum=torch_sum)  # :70
+        z_keep = z_f[..., :-1]                                                    # :76
+        rgbo = nerf_forward(sd_nerf, length2pts(r, z_keep), pos_levels, dir_levels)  # :77-78
+        comp = composite(rgbo, z_keep, r[:, 3:], white_bkg, (near, far))          # :80-85
+        for k, v in (("rgb", comp["rgb"]), ("depth", comp["depth"]), ("acc", comp["acc"]), ("z_coarse", z_c),
+                     ("sigma_prop", sigma_p), ("z_fine", z_keep), ("below", below), ("weights", comp["weights"]),
+                     ("rgbo", rgbo)):
+            outs[k].append(v)
+    return {k: torch.cat(v, dim=0) for k, v in outs.items()}
+
+
+# ----------------------------------------------------------------------------------------------
+# Philox4x32-10 restatement (the engine's own device RNG; Salmon et al., SC'11) for stream parity
+# ----------------------------------------------------------------------------------------------
+def philox_uniform(seed, ray_ids, n_samples, stream):
+    """Uniforms the CUDA kernels draw for (seed, ray, sample, stream): returns (len(ray_ids), n_samples) fp32."""
+    ray = np.asarray(ray_ids, dtype=np.uint64)[:, None]
+    smp = np.arange(n_samples, dtype=np.uint64)[None, :]
+    c = [np.broadcast_to(ray & np.uint64(0xFFFFFFFF), (ray.shape[0], n_samples)).copy(),
+         np.broadcast_to(ray >> np.uint64(32), (ray.shape[0], n_samples)).copy(),
+         np.broadcast_to(smp >> np.uint64(2), (ray.shape[0], n_samples)).copy(),
+         np.full((ray.shape[0], n_samples), stream, dtype=np.uint64)]
+    k0, k1 = np.uint64(seed & 0xFFFFFFFF), np.uint64((seed >> 32) & 0xFFFFFFFF)
+    M0, M1, W0, W1, m32 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57), np.uint64(0x9E3779B9), np.uint64(0xBB67AE85), np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0, p1 = M0 * c[0], M1 * c[2]
+        c = [(p1 >> np.uint64(32)) ^ c[1] ^ k0, p1 & m32, (p0 >> np.uint64(32)) ^ c[3] ^ k1, p0 & m32]
+        k0, k1 = (k0 + W0) & m32, (k1 + W1) & m32
+    sel = np.broadcast_to(smp & np.uint64(3), c[0].shape)
+    x = np.choose(sel.astype(np.int64), c)
+    return torch.from_numpy(((x >> np.uint64(8)).astype(np.float32) * np.float32(1.0 / 16777216.0)))

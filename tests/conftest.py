@@ -1,0 +1,37 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with `-m gpu`)")
+
+
+def pytest_collection_modifyitems(config, items):
+    if torch.cuda.is_available():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+@pytest.fixture(scope="session")
+def golden():
+    """Outputs of the unmodified reference (tests/golden/make_golden.py)."""
+    z = np.load(os.path.join(ROOT, "tests", "golden", "reference_outputs.npz"))
+    return {k: torch.from_numpy(z[k].astype(np.int64) if z[k].dtype == np.int16 else z[k]) for k in z.files}
+
+
+@pytest.fixture(scope="session")
+def gin():
+    """The seeded inputs the golden outputs were produced from."""
+    from tests.golden.make_golden import inputs_ops
+    return inputs_ops()

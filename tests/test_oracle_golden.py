@@ -1,0 +1,153 @@
+"""CPU: the oracle (oracle/nerf_oracle.py) against outputs of the unmodified reference.
+
+Tolerances: the oracle uses the same PyTorch ops as the reference, so on the machine that produced
+the fixtures it is bit-identical; a few ulp are allowed because the GPU box's host CPU may pick
+different SIMD kernels for exp/sin/sum.
+"""
+import numpy as np
+import torch
+
+from oracle import nerf_oracle as O
+from tests.golden.make_golden import render_case
+
+TOL = dict(rtol=2e-6, atol=2e-6)
+
+
+def close(a, b, **kw):
+    kw = {**TOL, **kw}
+    assert a.shape == b.shape, (a.shape, b.shape)
+    assert torch.allclose(a, b, **kw), float((a - b).abs().max())
+
+
+def test_positional_encoding(golden, gin):
+    close(O.positional_encoding(gin["pe_x"], 10), golden["pe"], atol=1e-6)
+    close(O.positional_encoding(gin["pe_x3"], 4), golden["pe3"], atol=1e-6)
+
+
+def test_weights_and_blur(golden, gin):
+    w = O.weights_from_sigma(gin["sigma"], gin["z"], gin["dirs"])
+    close(w, golden["weights"])
+    close(O.weights_from_sigma(gin["sigma"], gin["z"]), golden["weights_nodir"])
+    close(O.max_blur(golden["weights"], 0.01), golden["blur"], atol=1e-7)
+    # edge rows: empty ray -> zero weights; opaque first sample -> all weight on sample 0
+    assert float(golden["weights"][0].abs().max()) == 0.0
+    assert abs(float(golden["weights"][2, 0]) - 1.0) < 1e-6
+
+
+def test_search_is_exact_given_cdf(golden, gin):
+    """Stage (a): identical (cdf, u) -> identical indices (pure comparisons)."""
+    mids = 0.5 * (gin["z"][:, 1:] + gin["z"][:, :-1])
+    s, below, above = O.invert_cdf(golden["cdf"], mids, gin["u"])
+    assert torch.equal(below, golden["pdf_below"])
+    assert torch.equal(above, golden["pdf_above"])
+    close(s, golden["pdf_samples"], atol=1e-6)
+
+
+def _index_agreement(mine, ref):
+    return float((mine == ref).float().mean())
+
+
+def test_sample_pdf_and_inverse_sample(golden, gin):
+    mids = 0.5 * (gin["z"][:, 1:] + gin["z"][:, :-1])
+    w = golden["blur"]
+    for torch_sum in (True, False):
+        s, below, above = O.sample_pdf(mids, w[:, 1:-1], gin["u"], torch_sum=torch_sum)
+        # documented-order cdf may differ from ATen's fp32 cascade sum by 1 ulp -> rare index flips
+        assert _index_agreement(below, golden["pdf_below"]) >= 0.995
+        bad = below != golden["pdf_below"]
+        ok = ~bad
+        close(s[ok], golden["pdf_samples"][ok], atol=2e-6)
+        z, b = O.inverse_sample(w, gin["z"], gin["u"], sort=True, torch_sum=torch_sum)
+        assert bool((z[:, 1:] >= z[:, :-1]).all())
+        assert float((z - golden["inv_z"]).abs().max()) < 0.07   # a flipped index moves one z by < bin width
+        assert float((z - golden["inv_z"]).abs().median()) < 1e-6
+    zu = O.inverse_sample(w, gin["z"], gin["u"], sort=False, torch_sum=True)[0]
+    assert float((zu - golden["inv_z_unsorted"]).abs().median()) < 1e-6
+
+
+def test_points_merge_composite(golden, gin):
+    close(O.length2pts(gin["rays"], gin["z_fine"]), golden["l2p"], atol=1e-6)
+    pts, z = O.coarse_fine_merge(gin["rays"], gin["z"], golden["inv_z"])
+    close(z, golden["merge_z"], atol=1e-6)
+    close(pts, golden["merge_pts"], atol=1e-5)
+    c = O.composite(gin["rgbo"], gin["z_fine"], gin["dirs"], white_bkg=True, near_far=(2.0, 6.0))
+    close(c["rgb"], golden["comp_rgb"], atol=1e-6)
+    close(c["weights"], golden["comp_w"], atol=1e-6)
+    close(c["depth"], golden["comp_depth"], atol=1e-5)
+    close(O.composite(gin["rgbo"], gin["z_fine"], gin["dirs"])["rgb"], golden["comp_rgb_black"], atol=1e-6)
+
+
+def test_ipe(golden, gin):
+    f, mu, mu_t = O.ipe_feature(gin["ipe_z"], gin["ipe_rays"], 10, 0.01)
+    close(f, golden["ipe_feat"], atol=2e-6)
+    close(mu, golden["ipe_mu"], atol=1e-6)
+    close(mu_t, golden["ipe_mu_t"], atol=1e-6)
+
+
+def test_mlps(golden, gin):
+    for style in ("he", "refinit"):
+        sp, sn = O.make_params("proposal", 1, style), O.make_params("nerf", 2, style)
+        p = O.proposal_forward(sp, gin["mlp_pts"][..., :3])
+        n = O.nerf_forward(sn, gin["mlp_pts"])
+        close(p, golden[f"prop_fwd_{style}"], rtol=1e-5, atol=1e-5 * float(golden[f"prop_fwd_{style}"].abs().max()))
+        close(n, golden[f"nerf_fwd_{style}"], rtol=1e-5, atol=1e-5 * float(golden[f"nerf_fwd_{style}"].abs().max()))
+    # the 'he' field is non-degenerate: densities of both signs, colours away from 0.5
+    g = golden["nerf_fwd_he"]
+    assert float(g[..., 3].max()) > 1.0 and float(g[..., 3].min()) < -1.0
+    assert float(g[..., :3].std()) > 0.05
+
+
+def test_render_image_tile(golden):
+    """The reference's render_image on one 50x50 tile == oracle.render_rays on the same rays/uniforms."""
+    H = W = 50
+    pose, jitter, u, focal = render_case(H, W)
+    rays = O.generate_rays(pose, H, W, focal)
+    base_z = torch.linspace(2.0, 6.0, 64)
+    for style in ("he", "refinit"):
+        sp, sn = O.make_params("proposal", 1, style), O.make_params("nerf", 2, style)
+        out = O.render_rays(sp, sn, rays, base_z, jitter, u, 2.0, 6.0, 128, white_bkg=True, torch_sum=True)
+        rgb = out["rgb"].view(H, W, 3).permute(2, 0, 1)
+        err = (rgb - golden[f"img_rgb_{style}"]).abs()
+        assert float(err.max()) < 1e-4, float(err.max())
+        derr = (out["depth"].view(H, W) - golden[f"img_depth_{style}"]).abs()
+        assert float(derr.max()) < 1e-4, float(derr.max())
+
+
+def test_config1_trainer_composition(golden):
+    """Config 1 (64x64, 32 coarse samples): oracle vs the trainer-style composition of the reference."""
+    sp, sn = O.make_params("proposal", 1, "he"), O.make_params("nerf", 2, "he")
+    rays, lengths = golden["c1_rays"], golden["c1_lengths"]
+    pts = rays[:, None, :3] + rays[:, None, 3:] * lengths[:, :, None]
+    density = torch.nn.functional.softplus(O.proposal_forward(sp, pts))
+    close(density, golden["c1_density"], rtol=1e-5, atol=1e-4)
+    w = O.max_blur(O.weights_from_sigma(density, lengths, rays[:, 3:]), 0.01)
+    u = O.det_uniform((256, 129), 42, 0.0, 1.0)
+    fine, below = O.inverse_sample(w, lengths, u, sort=True, torch_sum=True)
+    assert _index_agreement(below, golden["c1_below"]) >= 0.995
+    fine = fine[..., :-1]
+    rgbo = O.nerf_forward(sn, O.length2pts(rays, fine))
+    rgb = O.composite(rgbo, fine, rays[:, 3:])["rgb"]
+    assert float((rgb - golden["c1_rgb"]).abs().max()) < 1e-4
+
+
+def test_philox_known_answers():
+    """Philox4x32-10 known-answer vectors (Random123 kat_vectors)."""
+    import numpy as np
+
+    def raw(ctr, key):
+        c = [np.array([[x]], dtype=np.uint64) for x in ctr]
+        k0, k1 = np.uint64(key[0]), np.uint64(key[1])
+        M0, M1, W0, W1, m32 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57), np.uint64(0x9E3779B9), np.uint64(0xBB67AE85), np.uint64(0xFFFFFFFF)
+        for _ in range(10):
+            p0, p1 = M0 * c[0], M1 * c[2]
+            c = [(p1 >> np.uint64(32)) ^ c[1] ^ k0, p1 & m32, (p0 >> np.uint64(32)) ^ c[3] ^ k1, p0 & m32]
+            k0, k1 = (k0 + W0) & m32, (k1 + W1) & m32
+        return [int(x[0, 0]) for x in c]
+
+    assert raw([0, 0, 0, 0], [0, 0]) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert raw([0xffffffff] * 4, [0xffffffff] * 2) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    assert raw([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0]) == [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+    # and the wrapper the CUDA kernels mirror: ray 0, samples 0..3, stream 0, seed 0 -> the first vector
+    u = O.philox_uniform(0, [0], 4, 0)[0]
+    exp = torch.tensor([(x >> 8) / 16777216.0 for x in [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]], dtype=torch.float32)
+    assert torch.equal(u, exp)
