@@ -1,0 +1,196 @@
+"""GPU: the HBM-bound stages through the C ABI against the golden vectors (reference outputs) and the oracle."""
+import pytest
+import torch
+
+import nerf_b200
+from nerf_b200 import ops
+from oracle import nerf_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def cu(t):
+    return t.to(DEV)
+
+
+def maxerr(a, b):
+    return float((a.cpu() - b.cpu()).abs().max())
+
+
+def test_generate_rays_matches_reference_raygen():
+    pose = nerf_b200.pose_spherical(30.0, -30.0, 4.0)[:3, :]
+    for (H, W, focal) in ((50, 50, 138.9), (64, 48, (120.0, 90.0)), (400, 400, 1111.1)):
+        ref = O.generate_rays(pose, H, W, focal)
+        fx, fy = (focal[1], focal[0]) if isinstance(focal, tuple) else (focal, focal)
+        got = ops.generate_rays(cu(pose), H, W, fx, fy)
+        assert got.shape == (H * W, 6)
+        assert maxerr(got, ref) < 1e-6
+    part = ops.generate_rays(cu(pose), 400, 400, 1111.1, 1111.1, pix_offset=12345, n_rays=777)
+    assert torch.equal(part.cpu(), ops.generate_rays(cu(pose), 400, 400, 1111.1, 1111.1).cpu()[12345:12345 + 777])
+
+
+def test_sample_coarse_bit_exact(gin):
+    rays = gin["rays"]
+    base = torch.linspace(2.0, 6.0, 64)
+    jit = O.det_uniform((rays.shape[0], 64), 77, 0.0, 1.0)
+    res = 4.0 / 128
+    z, pts = ops.sample_coarse(cu(rays), cu(base), res, jitter=cu(jit))
+    z_ref = base + jit * res
+    pts_ref = rays[:, None, :3] + z_ref[..., None] * rays[:, None, 3:]
+    assert torch.equal(z.cpu(), z_ref)
+    assert torch.equal(pts.cpu(), pts_ref)
+    # device RNG: Philox keyed on (seed, global ray id, sample) -> identical to the numpy restatement
+    z2, _ = ops.sample_coarse(cu(rays), cu(base), res, seed=1234, ray_offset=1000, want_pts=False)
+    u = O.philox_uniform(1234, [1000 + i for i in range(rays.shape[0])], 64, 0)
+    assert torch.equal(z2.cpu(), base + u * res)
+    # empty input
+    z0, _ = ops.sample_coarse(cu(rays[:0]), cu(base), res, want_pts=False)
+    assert z0.shape == (0, 64)
+
+
+def test_positional_encoding(golden, gin):
+    got = nerf_b200.positional_encoding(cu(gin["pe_x"]), 10)
+    assert got.shape == golden["pe"].shape and maxerr(got, golden["pe"]) < 2e-6
+    got3 = nerf_b200.positional_encoding(cu(gin["pe_x3"]), 4)
+    assert got3.shape == golden["pe3"].shape and maxerr(got3, golden["pe3"]) < 2e-6
+    # ragged / large: arguments up to 512 * 6.5 rad need full range reduction
+    x = O.det_uniform((100003, 3), 3, -6.5, 6.5)
+    big = nerf_b200.positional_encoding(cu(x), 10)
+    assert maxerr(big, O.positional_encoding(x, 10)) < 2e-6
+
+
+def test_ipe(golden, gin):
+    f, mu, mu_t = nerf_b200.ipe_feature(cu(gin["ipe_z"]), cu(gin["ipe_rays"]), 10, 0.01)
+    assert maxerr(f, golden["ipe_feat"]) < 1e-5
+    assert maxerr(mu, golden["ipe_mu"]) < 2e-6 and maxerr(mu_t, golden["ipe_mu_t"]) < 2e-6
+
+
+def test_weights_from_sigma(golden, gin):
+    w = nerf_b200.ProposalNetwork.get_weights(cu(gin["sigma"]), cu(gin["z"]), cu(gin["dirs"]))
+    assert maxerr(w, golden["weights"]) < 2e-6
+    w2 = nerf_b200.NeRF.getNormedWeight(cu(gin["sigma"]), cu(gin["z"]))
+    assert maxerr(w2, golden["weights_nodir"]) < 2e-6
+    assert float(w[0].abs().max()) == 0.0 and abs(float(w[2, 0]) - 1.0) < 1e-6
+    # full-size property: weights are a sub-probability vector on every ray
+    R = 160000
+    sig = torch.randn(R, 128, device=DEV) * 30
+    z = torch.sort(torch.rand(R, 128, device=DEV) * 4 + 2, dim=-1)[0]
+    wb = ops.weights_from_sigma(sig, z, None)
+    s = wb.sum(-1)
+    assert float(wb.min()) >= 0.0 and float(s.max()) <= 1.0 + 1e-5
+    ref = O.weights_from_sigma(sig, z)
+    assert maxerr(wb, ref) < 5e-6
+
+
+def test_max_blur_bit_exact(golden):
+    got = nerf_b200.maxBlurFilter(cu(golden["weights"]), 0.01)
+    assert torch.equal(got.cpu(), golden["blur"])
+
+
+def test_search_stage_bit_exact(golden, gin):
+    """Stage (a): identical (cdf, u) -> identical indices."""
+    inds = ops.search_cdf(cu(golden["cdf"]), cu(gin["u"])).cpu()
+    ref = torch.searchsorted(golden["cdf"], gin["u"], right=True)
+    assert torch.equal(inds, ref)
+    assert torch.equal(torch.clamp(inds - 1, min=0), golden["pdf_below"])
+    # full size
+    R = 160000
+    cdf = torch.cumsum(torch.rand(R, 62, device=DEV) + 1e-3, -1)
+    cdf = torch.cat((torch.zeros(R, 1, device=DEV), cdf / cdf[:, -1:]), -1)
+    u = torch.rand(R, 129, device=DEV)
+    assert torch.equal(ops.search_cdf(cdf, u), torch.searchsorted(cdf, u, right=True))
+
+
+def _check_ties(below, ref_below, cdf, u):
+    """Every index mismatch must sit on a cdf knot within a few ulp of u (SURVEY.md §7 hard part 1b)."""
+    bad = (below != ref_below).nonzero()
+    for r, i in bad.tolist():
+        k = max(int(below[r, i]), int(ref_below[r, i]))
+        assert abs(float(cdf[r, k]) - float(u[r, i])) <= 4e-7 * max(1.0, abs(float(u[r, i]))), (r, i, k)
+    return bad.shape[0]
+
+
+def test_sample_pdf_against_reference(golden, gin):
+    mids = 0.5 * (gin["z"][:, 1:] + gin["z"][:, :-1])
+    w = golden["blur"][:, 1:-1].contiguous()
+    s, below, above = nerf_b200.sample_pdf(cu(mids), cu(w), 129, u=cu(gin["u"]))
+    s, below, above = s.cpu(), below.cpu(), above.cpu()
+    # vs the oracle in the documented reduction order: exact indices
+    so, bo, ao = O.sample_pdf(mids, w, gin["u"])
+    assert torch.equal(below, bo) and torch.equal(above, ao)
+    assert maxerr(s, so) < 1e-6
+    # vs the reference itself (ATen's fp32 cascade sum): agreement up to proven 1-ulp ties
+    n_bad = _check_ties(below, golden["pdf_below"], golden["cdf"], gin["u"])
+    assert n_bad <= 0.005 * below.numel()
+    ok = below == golden["pdf_below"]
+    assert float((s - golden["pdf_samples"])[ok].abs().max()) < 2e-6
+
+
+def test_inverse_sample_sorted(golden, gin):
+    z, below = nerf_b200.inverseSample(cu(golden["blur"]), cu(gin["z"]), 129, sort=True, u=cu(gin["u"]))
+    z, below = z.cpu(), below.cpu()
+    assert bool((z[:, 1:] >= z[:, :-1]).all())
+    zo, bo = O.inverse_sample(golden["blur"], gin["z"], gin["u"], sort=True)
+    assert maxerr(z, zo) < 1e-6 and torch.equal(below, bo)
+    assert float((z - golden["inv_z"]).abs().median()) < 1e-6
+    zu = nerf_b200.inverseSample(cu(golden["blur"]), cu(gin["z"]), 129, sort=False, u=cu(gin["u"]))
+    assert float((zu.cpu() - golden["inv_z_unsorted"]).abs().median()) < 1e-6
+    # device RNG path reproduces the Philox stream
+    z2, _ = ops.inverse_sample(cu(golden["blur"]), cu(gin["z"]), 129, sort=True, seed=5, ray_offset=10)
+    up = O.philox_uniform(5, [10 + i for i in range(gin["z"].shape[0])], 129, 1)
+    assert maxerr(z2, O.inverse_sample(golden["blur"], gin["z"], up, sort=True)[0]) < 1e-6
+
+
+def test_resample_fused_equals_staged(golden, gin):
+    """get_weights + maxBlur + inverseSample + drop-last in one kernel == the staged ops."""
+    zf = ops.resample(cu(gin["sigma"]), cu(gin["z"]), cu(gin["rays"]), 129, 0.01, u=cu(gin["u"])).cpu()
+    assert zf.shape == (gin["z"].shape[0], 128)
+    assert maxerr(zf, golden["inv_z"][:, :-1]) < 0.07
+    assert float((zf - golden["inv_z"][:, :-1]).abs().median()) < 1e-6
+    w = ops.max_blur(ops.weights_from_sigma(cu(gin["sigma"]), cu(gin["z"]), cu(gin["rays"][:, 3:].contiguous())), 0.01)
+    zs, _ = ops.inverse_sample(w, cu(gin["z"]), 129, sort=True, u=cu(gin["u"]))
+    assert torch.equal(zf, zs.cpu()[:, :-1])
+
+
+def test_length2pts_and_merge(golden, gin):
+    pts = nerf_b200.NeRF.length2pts(cu(gin["rays"]), cu(gin["z_fine"]))
+    assert torch.equal(pts.cpu(), golden["l2p"])
+    mp, mz = nerf_b200.NeRF.coarseFineMerge(cu(gin["rays"]), cu(gin["z"]), cu(golden["inv_z"]))
+    assert torch.equal(mz.cpu(), golden["merge_z"])
+    assert maxerr(mp, golden["merge_pts"]) < 1e-6
+
+
+def test_composite(golden, gin):
+    rgb, w, ex = nerf_b200.NeRF.render(cu(gin["rgbo"]), cu(gin["z_fine"]), cu(gin["dirs"]), white_bkg=True, render_depth=(2.0, 6.0))
+    assert maxerr(rgb, golden["comp_rgb"]) < 2e-6
+    assert maxerr(w, golden["comp_w"]) < 2e-6
+    assert maxerr(ex["depth_img"], golden["comp_depth"]) < 1e-5
+    rgb2, _, _ = nerf_b200.NeRF.render(cu(gin["rgbo"]), cu(gin["z_fine"]), cu(gin["dirs"]))
+    assert maxerr(rgb2, golden["comp_rgb_black"]) < 2e-6
+    # properties at full size: zero density -> exactly the white background; linear in the colours
+    R = 160000
+    z = torch.sort(torch.rand(R, 128, device=DEV) * 4 + 2, dim=-1)[0]
+    d = torch.randn(R, 3, device=DEV)
+    rgbo = torch.rand(R, 128, 4, device=DEV)
+    rgbo[..., 3] = -1.0
+    out, _, _, acc = ops.composite(rgbo, z, d, white_bkg=True)
+    assert float((out - 1.0).abs().max()) == 0.0 and float(acc.abs().max()) == 0.0
+    rgbo[..., 3] = torch.randn(R, 128, device=DEV) * 20
+    a, _, _, _ = ops.composite(rgbo, z, d)
+    rgbo2 = rgbo.clone()
+    rgbo2[..., :3] *= 0.5
+    b, _, _, _ = ops.composite(rgbo2, z, d)
+    assert float((a * 0.5 - b).abs().max()) < 1e-6
+    ref = O.composite(rgbo, z, d)
+    assert maxerr(a, ref["rgb"]) < 5e-6
+
+
+def test_argument_errors_are_loud(gin):
+    with pytest.raises(nerf_b200.NB2Error):
+        ops.inverse_sample(cu(torch.rand(4, 300)), cu(torch.rand(4, 300)), 129, u=cu(torch.rand(4, 129)))
+    with pytest.raises(nerf_b200.NB2Error):
+        nerf_b200.positional_encoding(torch.zeros(4, 3), 10)  # CPU tensor
+    m = nerf_b200.MipNeRF(10, 4)
+    with pytest.raises(nerf_b200.NB2Error):
+        m.forward(torch.zeros(2, 4, 6))  # module on the CPU

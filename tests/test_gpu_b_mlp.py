@@ -1,0 +1,114 @@
+"""GPU: the MLP kernels (CUDA-core fp32, tcgen05 bf16x3, tcgen05 bf16) against the reference outputs
+(golden) and against the oracle run on the same inputs."""
+import pytest
+import torch
+
+import nerf_b200
+from nerf_b200 import _lib, ops
+from oracle import nerf_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+# max |err| relative to max |reference| per precision.  fp32: reordering noise only.  bf16x3: products
+# carry ~2^-16 relative error.  bf16: 2^-8 per operand through up to 9 layers.
+REL_TOL = {"fp32": 2e-5, "bf16x3": 1e-4, "bf16": 6e-2}
+
+
+def load(module, sd):
+    module.load_state_dict({k: v.clone() for k, v in sd.items()})
+    return module.to(DEV)
+
+
+def test_tcgen05_building_blocks():
+    """One UMMA sequence through the kernel's swizzle / descriptors / bulk copy / TMEM read-out."""
+    g = torch.Generator().manual_seed(1)
+    A = torch.randn(128, 64, generator=g).to(torch.bfloat16).to(DEV)
+    B = torch.randn(128, 64, generator=g).to(torch.bfloat16).to(DEV)
+    D = ops.selftest_umma(A, B)
+    torch.cuda.synchronize()
+    ref = A.float() @ B.float().T
+    assert float((D - ref).abs().max()) < 1e-3, float((D - ref).abs().max())
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3", "bf16"])
+@pytest.mark.parametrize("style", ["he", "refinit"])
+def test_mlp_forward_vs_reference(golden, gin, precision, style):
+    prop = load(nerf_b200.ProposalNetwork(10, 256), O.make_params("proposal", 1, style))
+    net = load(nerf_b200.MipNeRF(10, 4, 256), O.make_params("nerf", 2, style))
+    prop.precision = net.precision = precision
+    pts = gin["mlp_pts"].to(DEV)
+    with torch.no_grad():
+        p = prop.forward(pts[..., :3].contiguous()).cpu()
+        n = net.forward(pts).cpu()
+    gp, gn = golden[f"prop_fwd_{style}"], golden[f"nerf_fwd_{style}"]
+    assert p.shape == gp.shape and n.shape == gn.shape
+    tol = REL_TOL[precision]
+    assert float((p - gp).abs().max()) <= tol * float(gp.abs().max()), (float((p - gp).abs().max()), float(gp.abs().max()))
+    assert float((n[..., 3] - gn[..., 3]).abs().max()) <= tol * float(gn[..., 3].abs().max())
+    rgb_tol = {"fp32": 2e-6, "bf16x3": 2e-5, "bf16": 2e-2}[precision]
+    assert float((n[..., :3] - gn[..., :3]).abs().max()) <= rgb_tol
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3", "bf16"])
+@pytest.mark.parametrize("n_points", [1, 127, 128, 129, 300 * 128 + 5])
+def test_mlp_ragged_sizes(precision, n_points):
+    sp, sn = O.make_params("proposal", 1, "he"), O.make_params("nerf", 2, "he")
+    prop = load(nerf_b200.ProposalNetwork(10, 256), sp)
+    net = load(nerf_b200.MipNeRF(10, 4, 256), sn)
+    prop.precision = net.precision = precision
+    pts = torch.cat((O.det_uniform((n_points, 3), 9, -2.0, 2.0), O.det_uniform((n_points, 3), 10, -1.0, 1.0)), -1).to(DEV)
+    with torch.no_grad():
+        p = prop.forward(pts[None, :, :3].contiguous())[0]
+        n = net.forward(pts[None])[0]
+    spd, snd = O.params_to(sp, DEV), O.params_to(sn, DEV)
+    rp, rn = O.proposal_forward(spd, pts[:, :3]), O.nerf_forward(snd, pts)
+    tol = REL_TOL[precision]
+    assert float((p - rp).abs().max()) <= tol * float(rp.abs().max())
+    assert float((n[:, 3] - rn[:, 3]).abs().max()) <= tol * float(rn[:, 3].abs().max())
+    assert float((n[:, :3] - rn[:, :3]).abs().max()) <= {"fp32": 5e-6, "bf16x3": 3e-5, "bf16": 3e-2}[precision]
+
+
+def test_engine_error_is_at_the_reference_own_fp32_noise_level():
+    """bf16x3 vs an fp64 evaluation, next to the reference's own fp32 path vs fp64 (informational bound)."""
+    sn = O.make_params("nerf", 2, "he")
+    net = load(nerf_b200.MipNeRF(10, 4, 256), sn)
+    pts = torch.cat((O.det_uniform((4096, 3), 9, -2.0, 2.0), O.det_uniform((4096, 3), 10, -1.0, 1.0)), -1)
+    ref64 = torch.from_numpy(O.np_forward("nerf", sn, pts.numpy()))
+    ref32 = O.nerf_forward(sn, pts).double()
+    errs = {}
+    for precision in ("fp32", "bf16x3"):
+        net.precision = precision
+        with torch.no_grad():
+            out = net.forward(pts[None].to(DEV))[0].cpu().double()
+        errs[precision] = float((out[:, :3] - ref64[:, :3]).abs().max())
+    e_ref = float((ref32[:, :3] - ref64[:, :3]).abs().max())
+    print("rgb max|err| vs fp64: reference fp32", e_ref, "engine", errs)
+    assert errs["fp32"] <= 5e-6 and errs["bf16x3"] <= 3e-5
+
+
+def test_repack_after_parameter_update():
+    sn = O.make_params("nerf", 2, "he")
+    net = load(nerf_b200.MipNeRF(10, 4, 256), sn)
+    net.precision = "fp32"
+    pts = torch.cat((O.det_uniform((256, 3), 9, -2.0, 2.0), O.det_uniform((256, 3), 10, -1.0, 1.0)), -1).to(DEV)[None]
+    with torch.no_grad():
+        a = net.forward(pts).clone()
+        v0 = _lib.load().nb2_weights_version(_lib.handle(), _lib.NET_NERF)
+        net.rgb_layer[2].bias.add_(0.5)          # in-place update, like an optimizer step
+        b = net.forward(pts)
+        v1 = _lib.load().nb2_weights_version(_lib.handle(), _lib.NET_NERF)
+    assert v1 == v0 + 1
+    assert float((a[..., :3] - b[..., :3]).abs().max()) > 1e-3 and torch.equal(a[..., 3], b[..., 3])
+
+
+def test_unpacked_network_is_an_error():
+    lib = _lib.load()
+    import ctypes
+    h = ctypes.c_void_p()
+    _lib.check(lib.nb2_create(ctypes.byref(h), torch.cuda.current_device()))
+    x = torch.zeros(128, 6, device=DEV)
+    out = torch.zeros(128, 4, device=DEV)
+    rc = lib.nb2_mlp_forward(h, _lib.NET_NERF, _lib.PREC_BF16, _lib.ptr(x), 6, 128, _lib.ptr(out), _lib.stream_ptr())
+    assert rc == -3 and b"not been packed" in lib.nb2_last_error()
+    lib.nb2_destroy(h)

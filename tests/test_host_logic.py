@@ -1,0 +1,61 @@
+"""CPU: host-side logic of the boundary — tile-order RNG replay, sharding arithmetic, pose/focal math."""
+import math
+
+import numpy as np
+import torch
+
+import nerf_b200
+from nerf_b200 import procedures, sharding
+
+
+def test_get_patch_size_and_64x64():
+    assert procedures.get_patch_size((400, 400)) == (50, (8, 8))
+    assert procedures.get_patch_size((800, 800)) == (50, (16, 16))
+    assert procedures.get_patch_size((120, 120)) == (40, (3, 3))
+    # the reference raises UnboundLocalError here (nerf/procedures.py:24-31); the engine renders one tile
+    assert procedures.get_patch_size((64, 64)) == (None, (1, 1))
+
+
+def test_reference_rng_replay_order():
+    """'reference' RNG mode consumes torch's CPU generator exactly like the reference's tile loop."""
+    H = W = 100
+    torch.manual_seed(7)
+    jit, u = procedures._reference_rng_draws((H, W), 64, 129)
+    torch.manual_seed(7)
+    sz = 50
+    for k in range(2):
+        for j in range(2):
+            a = torch.rand((sz, sz, 64))          # procedures.py:65
+            b = torch.rand([sz * sz, 129])        # utils.py:115
+            assert torch.equal(jit.view(H, W, 64)[sz * k:sz * (k + 1), sz * j:sz * (j + 1)], a)
+            assert torch.equal(u.view(H, W, 129)[sz * k:sz * (k + 1), sz * j:sz * (j + 1)], b.view(sz, sz, 129))
+
+
+def test_shard_range_covers_and_aligns():
+    for n in (0, 1, 7, 160000, 640000, 640001):
+        for world in (1, 2, 3, 4, 8):
+            spans = [sharding.shard_range(n, r, world, align=2) for r in range(world)]
+            assert sum(c for _, c in spans) == n
+            pos = 0
+            for s, c in spans:
+                assert s == min(pos, n) or c == 0
+                pos += c
+            assert all(c % 2 == 0 for _, c in spans[:-1] if c and _ + c < n)
+
+
+def test_fov2focal_and_pose():
+    f = nerf_b200.fov2Focal(0.6911112070083618, (400, 400))
+    assert abs(f[0] - 400 / math.tan(0.5 * 0.6911112070083618)) < 1e-9 and f[0] == f[1]
+    fx = nerf_b200.fov2Focal((0.7, 0.5), (300, 400))
+    assert abs(fx[0] - 0.5 * 300 / math.tan(0.25)) < 1e-9 and abs(fx[1] - 0.5 * 400 / math.tan(0.35)) < 1e-9
+    p = nerf_b200.pose_spherical(30.0, -30.0, 4.0)
+    assert p.shape == (4, 4) and abs(float(p[:3, 3].norm()) - 4.0) < 1e-5
+    R = p[:3, :3]
+    assert torch.allclose(R @ R.T, torch.eye(3), atol=1e-6)
+
+
+def test_lr_schedule_matches_formula():
+    s = nerf_b200.DecayLrScheduler(0.1, 0.5, 100, 1e-3, warmup_step=10)
+    assert abs(s.update_opt_lr(5)[1] - 1e-3 * (0.1 * 0.5 + 0.5)) < 1e-12
+    assert abs(s.update_opt_lr(110)[1] - 1e-3 * 0.5) < 1e-12
+    assert abs(s.update_opt_lr(100000)[1] - 1e-4) < 1e-12
