@@ -9,6 +9,9 @@ LIB       := nerf_b200/libnerfb200.so
 
 all: $(LIB)
 
+# the HBM-bound stages mirror PyTorch's unfused elementwise arithmetic: no FMA contraction there
+$(CSRC)/nb2_ops.o: EXTRA += -fmad=false
+
 $(CSRC)/%.o: $(CSRC)/%.cu $(CSRC)/nb2_common.cuh $(CSRC)/nb2_rowio.cuh $(CSRC)/nb2_tc_ptx.cuh include/nerf_b200.h
 	$(NVCC) $(NVCCFLAGS) $(EXTRA) -c $< -o $@
 

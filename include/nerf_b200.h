@@ -41,9 +41,12 @@ enum {
 
 /* Arithmetic of the MLP contraction. */
 enum {
-  NB2_PREC_FP32 = 0,   /* fp32 FFMA on CUDA cores (strict mode; reference arithmetic)               */
-  NB2_PREC_BF16X3 = 1, /* tcgen05, operands split hi+lo bf16, 3 MMAs, fp32 accumulate (fp32-faithful)*/
-  NB2_PREC_BF16 = 2    /* tcgen05, single bf16 pass, fp32 accumulate                                */
+  NB2_PREC_FP32 = 0,   /* fp32 FFMA on CUDA cores (strict mode; reference arithmetic)                 */
+  NB2_PREC_FP16X3 = 1, /* tcgen05, operands split hi+lo fp16 (22-bit), 3 MMAs, fp32 accumulate:
+                          products exact to ~2^-22 -> fp32-faithful                                   */
+  NB2_PREC_BF16 = 2,   /* tcgen05, single bf16 pass, fp32 accumulate                                  */
+  NB2_PREC_FP16 = 3,   /* tcgen05, single fp16 pass (the reference's own AMP dtype), fp32 accumulate  */
+  NB2_PREC_BF16X3 = 4  /* tcgen05, hi+lo bf16 split (16-bit), 3 MMAs                                  */
 };
 
 /* Flags for nb2_composite / nb2_render_rays. */
@@ -197,6 +200,10 @@ int nb2_render_rays(nb2_handle* h, const nb2_render_params* p, const float* rays
 
 /* Kernel-launch counter (all launches made through this handle since creation). */
 int64_t nb2_launch_count(nb2_handle* h);
+
+/* Optional per-kernel timing of nb2_render_rays: four cudaEvent_t (created by the caller with timing
+ * enabled) recorded on the render stream before launch 1 and after launches 1, 2, 3.  NULL disables. */
+int nb2_set_profile_events(nb2_handle* h, void* const* events4);
 
 /* Device-side self-test of the tcgen05 building blocks: D (128x128 fp32) = A (128x64 bf16,
  * row-major) * B^T (128x64 bf16, row-major), computed by ONE UMMA sequence through the same

@@ -14,8 +14,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libnerfb200.so")
 
 NET_PROPOSAL, NET_NERF = 0, 1
-PREC_FP32, PREC_BF16X3, PREC_BF16 = 0, 1, 2
-PRECISIONS = {"fp32": PREC_FP32, "bf16x3": PREC_BF16X3, "bf16": PREC_BF16}
+PREC_FP32, PREC_FP16X3, PREC_BF16, PREC_FP16, PREC_BF16X3 = 0, 1, 2, 3, 4
+PRECISIONS = {"fp32": PREC_FP32, "fp16x3": PREC_FP16X3, "bf16": PREC_BF16, "fp16": PREC_FP16, "bf16x3": PREC_BF16X3}
 WHITE_BKG, DENSITY_SOFTPLUS = 1, 2
 
 c_f32p = ctypes.c_void_p
@@ -64,6 +64,7 @@ SIGNATURES = {
     "nb2_render_rays": (c_int, [c_vp, ctypes.POINTER(RenderParams), c_f32p, c_f32p, c_f32p, c_f32p, c_i64, c_f32p, c_f32p,
                                 c_f32p, c_f32p, c_f32p, c_f32p, c_vp, c_i64, c_vp]),
     "nb2_launch_count": (c_i64, [c_vp]),
+    "nb2_set_profile_events": (c_int, [c_vp, ctypes.POINTER(c_vp)]),
     "nb2_selftest_umma": (c_int, [c_vp, c_vp, c_vp, c_vp, c_f32p, c_vp]),
 }
 

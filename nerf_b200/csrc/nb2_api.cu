@@ -59,6 +59,12 @@ extern "C" int nb2_destroy(nb2_handle* h) {
 
 extern "C" int64_t nb2_launch_count(nb2_handle* h) { return h ? h->launches : -1; }
 
+extern "C" int nb2_set_profile_events(nb2_handle* h, void* const* events4) {
+  NB2_CHECK_ARG(h != nullptr, "null handle");
+  for (int i = 0; i < 4; ++i) h->prof[i] = events4 ? (cudaEvent_t)events4[i] : nullptr;
+  return NB2_OK;
+}
+
 extern "C" int nb2_pack_weights(nb2_handle* h, int net_id, const float* const* W, const float* const* b, int n_layers,
                                 int pos_levels, int dir_levels, int hidden, void* stream) {
   NB2_CHECK_ARG(h != nullptr, "null handle");
@@ -82,7 +88,8 @@ extern "C" int nb2_weights_version(nb2_handle* h, int net_id) {
 
 static int mlp_dispatch(nb2_handle* h, int net_id, int precision, const MlpIo& io, cudaStream_t st) {
   if (precision == NB2_PREC_FP32) return launch_mlp_simt(h, net_id, io, st);
-  if (precision == NB2_PREC_BF16 || precision == NB2_PREC_BF16X3) return launch_mlp_tc(h, net_id, precision, io, st);
+  if (precision == NB2_PREC_BF16 || precision == NB2_PREC_BF16X3 || precision == NB2_PREC_FP16 || precision == NB2_PREC_FP16X3)
+    return launch_mlp_tc(h, net_id, precision, io, st);
   set_error("unknown precision %d", precision);
   return NB2_ERR_INVALID;
 }
@@ -91,7 +98,8 @@ extern "C" int nb2_mlp_forward(nb2_handle* h, int net_id, int precision, const f
                                int64_t n_points, float* out, void* stream) {
   NB2_CHECK_ARG(h != nullptr, "null handle");
   NB2_CHECK_ARG(net_id == NB2_NET_PROPOSAL || net_id == NB2_NET_NERF, "mlp_forward: unknown network id %d", net_id);
-  NB2_CHECK_ARG(pts && out && n_points >= 0, "mlp_forward: bad arguments");
+  if (n_points == 0) return NB2_OK;
+  NB2_CHECK_ARG(pts && out && n_points > 0, "mlp_forward: bad arguments");
   NB2_CHECK_ARG(pts_stride >= (net_id == NB2_NET_NERF ? 6 : 3), "mlp_forward: pts_stride %d too small for network %d", pts_stride, net_id);
   MlpIo io;
   memset(&io, 0, sizeof(io));
@@ -123,14 +131,15 @@ extern "C" int nb2_render_rays(nb2_handle* h, const nb2_render_params* p, const 
                                float* acc_out, float* z_coarse_out, float* sigma_prop_out, float* z_fine_out,
                                void* workspace, int64_t workspace_bytes, void* stream) {
   NB2_CHECK_ARG(h != nullptr, "null handle");
-  NB2_CHECK_ARG(p && rays && base_z && rgb_out, "render_rays: null pointer");
+  NB2_CHECK_ARG(p != nullptr, "render_rays: null parameter block");
+  if (n_rays == 0) return NB2_OK;
+  NB2_CHECK_ARG(rays && base_z && rgb_out, "render_rays: null pointer");
   NB2_CHECK_ARG(p->n_coarse >= 3 && p->n_coarse <= 256, "render_rays: n_coarse must be in [3,256]");
   NB2_CHECK_ARG(p->n_fine >= 1 && p->n_fine + 1 <= 264, "render_rays: n_fine must be in [1,263]");
   NB2_CHECK_ARG(p->far_t != p->near_t, "render_rays: near == far");
   const int64_t need = nb2_render_workspace_bytes(n_rays, p);
   NB2_CHECK_ARG(workspace && workspace_bytes >= need, "render_rays: workspace too small (%lld < %lld bytes)",
                 (long long)workspace_bytes, (long long)need);
-  if (n_rays == 0) return NB2_OK;
   cudaStream_t st = (cudaStream_t)stream;
   char* ws = (char*)workspace;
   float* z_coarse = (float*)ws; ws += align256(n_rays * p->n_coarse * 4);
@@ -156,13 +165,16 @@ extern "C" int nb2_render_rays(nb2_handle* h, const nb2_render_params* p, const 
   io.out_mode = 0;
   io.out = sigma_prop;
   io.z_out = z_coarse;
+  if (h->prof[0]) NB2_CUDA(cudaEventRecord(h->prof[0], st));
   int rc = mlp_dispatch(h, NB2_NET_PROPOSAL, p->precision, io, st);
   if (rc != NB2_OK) return rc;
+  if (h->prof[1]) NB2_CUDA(cudaEventRecord(h->prof[1], st));
 
   // 2. density -> weights -> max-blur -> inverse CDF -> sort -> drop last      :68-70,76
   rc = nb2_resample(h, sigma_prop, z_coarse, rays, u, p->seed, p->ray_offset, n_rays, p->n_coarse, p->n_fine + 1,
                     p->blur_alpha, p->flags, z_fine, stream);
   if (rc != NB2_OK) return rc;
+  if (h->prof[2]) NB2_CUDA(cudaEventRecord(h->prof[2], st));
 
   // 3. encoding + NeRF MLP + alpha compositing                                    :77-85
   memset(&io, 0, sizeof(io));
@@ -179,15 +191,19 @@ extern "C" int nb2_render_rays(nb2_handle* h, const nb2_render_params* p, const 
     io.rgb_out = rgb_out;
     io.depth_out = depth_out;
     io.acc_out = acc_out;
-    return mlp_dispatch(h, NB2_NET_NERF, p->precision, io, st);
+    rc = mlp_dispatch(h, NB2_NET_NERF, p->precision, io, st);
+    if (rc == NB2_OK && h->prof[3]) NB2_CUDA(cudaEventRecord(h->prof[3], st));
+    return rc;
   }
   float* rgbo = (float*)ws;
   io.out_mode = 1;
   io.out = rgbo;
   rc = mlp_dispatch(h, NB2_NET_NERF, p->precision, io, st);
   if (rc != NB2_OK) return rc;
-  return nb2_composite(h, rgbo, z_fine, rays + 3, 6, n_rays, p->n_fine, p->flags, p->near_t, p->far_t, rgb_out, nullptr,
-                       depth_out, acc_out, stream);
+  rc = nb2_composite(h, rgbo, z_fine, rays + 3, 6, n_rays, p->n_fine, p->flags, p->near_t, p->far_t, rgb_out, nullptr,
+                     depth_out, acc_out, stream);
+  if (rc == NB2_OK && h->prof[3]) NB2_CUDA(cudaEventRecord(h->prof[3], st));
+  return rc;
 }
 
 extern "C" int nb2_selftest_umma(nb2_handle* h, const void* A_bf16, const void* B_bf16, void* scratch_16k, float* D_out,

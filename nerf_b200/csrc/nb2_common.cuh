@@ -110,7 +110,7 @@ struct PackedNet {
   int pos_levels = 0, dir_levels = 0;
   TcNet tc;
   SimtNet simt;
-  __nv_bfloat16* d_wchunks = nullptr;  // [n_chunks][2 (hi, lo)][8192] pre-swizzled tiles
+  __nv_bfloat16* d_wchunks = nullptr;  // [n_chunks][4 (bf16 hi, lo, fp16 hi, lo)][8192] pre-swizzled tiles
   float* d_bias = nullptr;             // all MMA-layer biases, concatenated
   float* d_head = nullptr;             // sigma head: w[256], b ; rgb head: W1[3][128], b1[3]
   float* d_wt32 = nullptr;             // fp32 transposed weights for the CUDA-core path
@@ -127,6 +127,7 @@ struct nb2_handle {
   int device = 0;
   int sm_count = 0;
   int64_t launches = 0;
+  cudaEvent_t prof[4] = {nullptr, nullptr, nullptr, nullptr};
   nb2::PackedNet net[2];
 };
 

@@ -1,5 +1,5 @@
 // nb2_mlp_tc.cu — the per-sample MLP (proposal 4x256 / NeRF 8x256 + heads) as ONE persistent,
-// warp-specialised tcgen05 kernel.  NB2_PREC_BF16 and NB2_PREC_BF16X3.
+// warp-specialised tcgen05 kernel.  NB2_PREC_BF16 / NB2_PREC_FP16 (single pass) and NB2_PREC_FP16X3 / NB2_PREC_BF16X3 (split).
 //
 //   warp 0      weight streamer: cp.async.bulk (TMA unit) of pre-swizzled 128x64 bf16 weight
 //               tiles from L2 into a 4-stage shared-memory ring, mbarrier full/empty handshake
@@ -13,10 +13,11 @@
 //               operand in place.  The last epilogue evaluates the 128->3 / 256->1 heads on the
 //               fp32 values and either stores rgb-sigma or alpha-composites the ray.
 //
-// NB2_PREC_BF16  : two slots ping-pong, so one tile's epilogue overlaps the other tile's MMAs.
-// NB2_PREC_BF16X3: every operand is split x = hi + lo (both bf16); each product is evaluated as
-//                  hi*hi + lo*hi + hi*lo with fp32 accumulation (~2^-16 relative per product),
-//                  one slot (the hi/lo activation pair fills the shared memory of two slots).
+// single pass (bf16 | fp16): two slots ping-pong, so one tile's epilogue overlaps the other tile's MMAs.
+// split (fp16x3 | bf16x3)   : every operand is split x = hi + lo (both 16-bit); each product is evaluated
+//                  as hi*hi + lo*hi + hi*lo with fp32 accumulation (fp16: 22-bit operands, ~2^-22 relative
+//                  per product, i.e. fp32-faithful; bf16: ~2^-16), one slot (the hi/lo activation pair
+//                  fills the shared memory of two slots).
 //
 // Shared memory (bytes):  activations NSLOTS * (SPLIT ? 2 : 1) * 5 * 16 KB = 160 KB,
 //                         weight ring 4 * 16 KB = 64 KB, barriers + scratch < 1 KB.
@@ -65,24 +66,23 @@ struct TcLayout {
 
 // ---- writing one row of an A-operand tile ---------------------------------------------------
 // v[0..8) are 8 consecutive columns starting at column `col` (multiple of 8) of row `row`.
-template <bool SPLIT>
+template <bool SPLIT, bool F16>
 __device__ __forceinline__ void store_a8(uint32_t tile_hi, uint32_t tile_lo, int row, int col, const float (&v)[8]) {
   const uint32_t off = (uint32_t)row * 128u + ((((uint32_t)col >> 3) ^ ((uint32_t)row & 7u)) << 4);
   uint32_t h[4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) h[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+  for (int i = 0; i < 4; ++i) h[i] = pack16x2<F16>(v[2 * i], v[2 * i + 1]);
   st_shared_v4(tile_hi + off, h[0], h[1], h[2], h[3]);
   if (SPLIT) {
     uint32_t l[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-      l[i] = pack_bf16x2(v[2 * i] - bf16_lo_to_f32(h[i]), v[2 * i + 1] - bf16_hi_to_f32(h[i]));
+    for (int i = 0; i < 4; ++i) l[i] = residual16x2<F16>(v[2 * i], v[2 * i + 1], h[i]);
     st_shared_v4(tile_lo + off, l[0], l[1], l[2], l[3]);
   }
 }
 
 // Encoded position / direction row -> E tile.  NCOLS = 64 (position) or 32 (direction).
-template <bool SPLIT, int NCOLS, int MAXLEV>
+template <bool SPLIT, bool F16, int NCOLS, int MAXLEV>
 __device__ __forceinline__ void write_enc_row(uint32_t tile_hi, uint32_t tile_lo, int row, const float x[3],
                                               int levels, bool valid) {
   float v[NCOLS];
@@ -109,12 +109,12 @@ __device__ __forceinline__ void write_enc_row(uint32_t tile_hi, uint32_t tile_lo
     float w[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) w[i] = v[8 * g + i];
-    store_a8<SPLIT>(tile_hi, tile_lo, row, 8 * g, w);
+    store_a8<SPLIT, F16>(tile_hi, tile_lo, row, 8 * g, w);
   }
 }
 
 // ---- the kernel ----------------------------------------------------------------------------------
-template <int NSLOTS, bool SPLIT>
+template <int NSLOTS, bool SPLIT, bool F16>
 __global__ void __launch_bounds__(kRolesThreads + 128 * NSLOTS, 1) mlp_tc_kernel(const __grid_constant__ TcParams p) {
   using LT = TcLayout<NSLOTS, SPLIT>;
   extern __shared__ unsigned char smem_dyn[];
@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(kRolesThreads + 128 * NSLOTS, 1) mlp_tc_kernel
                 const uint32_t full = smem_u32(&misc->w_full[stage]);
                 mbar_arrive_expect_tx(full, kTileBytes);
                 bulk_g2s(ring_base + stage * kTileBytes,
-                         p.wchunks + ((size_t)(chunk0 + c) * 2 + part) * (kTileBytes / 2), kTileBytes, full);
+                         p.wchunks + ((size_t)(chunk0 + c) * 4 + (F16 ? 2 : 0) + part) * (kTileBytes / 2), kTileBytes, full);
                 if (++stage == kStages) { stage = 0; phase ^= 1u; }
               }
             }
@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(kRolesThreads + 128 * NSLOTS, 1) mlp_tc_kernel
   } else if (warp == 1) {
     // =========================== MMA issuer =======================================================
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(128, 128);
+      const uint32_t idesc = umma_idesc_16(128, 128, F16);
       uint32_t stage = 0, phase = 0;
       uint32_t pa[2] = {0u, 0u};
       for (int64_t it = 0; it < n_iters; ++it) {
@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(kRolesThreads + 128 * NSLOTS, 1) mlp_tc_kernel
       if (tile >= p.n_tiles) break;
       const int64_t grow = tile * kTileRows + row;
       const RowIn in = load_row(p.io, grow);
-      write_enc_row<SPLIT, kEncCols, kMaxPosLevels>(e_hi, e_lo, row, in.p, p.pos_levels, in.valid);
+      write_enc_row<SPLIT, F16, kEncCols, kMaxPosLevels>(e_hi, e_lo, row, in.p, p.pos_levels, in.valid);
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(a_ready);
@@ -258,6 +258,7 @@ __global__ void __launch_bounds__(kRolesThreads + 128 * NSLOTS, 1) mlp_tc_kernel
         const float* bias = p.bias + L.bias_off;
         mbar_wait(acc_full, pacc);
         pacc ^= 1u;
+        __syncwarp();
         tc_fence_after();
 
         if (L.epi == EPI_RGB) {
@@ -360,7 +361,7 @@ __global__ void __launch_bounds__(kRolesThreads + 128 * NSLOTS, 1) mlp_tc_kernel
                 sg = fmaf(v[0], w0.x, sg); sg = fmaf(v[1], w0.y, sg); sg = fmaf(v[2], w0.z, sg); sg = fmaf(v[3], w0.w, sg);
                 sg = fmaf(v[4], w1.x, sg); sg = fmaf(v[5], w1.y, sg); sg = fmaf(v[6], w1.z, sg); sg = fmaf(v[7], w1.w, sg);
               }
-              if (L.epi != EPI_SIGMA_OUT) store_a8<SPLIT>(h_hi, h_hi + lo_off, row, col & 63, v);
+              if (L.epi != EPI_SIGMA_OUT) store_a8<SPLIT, F16>(h_hi, h_hi + lo_off, row, col & 63, v);
             }
           }
           if (want_sigma) sigma = sg + __ldg(p.head + kHeadSigmaB);
@@ -370,7 +371,7 @@ __global__ void __launch_bounds__(kRolesThreads + 128 * NSLOTS, 1) mlp_tc_kernel
             // the encoded position is dead after the skip layer: re-use its tile for the direction
             float rot[3] = {0.f, 0.f, 0.f};
             if (in.valid) normalize_dir(in.d, rot);
-            write_enc_row<SPLIT, kDirCols, kMaxDirLevels>(e_hi, e_lo, row, rot, p.dir_levels, in.valid);
+            write_enc_row<SPLIT, F16, kDirCols, kMaxDirLevels>(e_hi, e_lo, row, rot, p.dir_levels, in.valid);
           }
         }
         if (l + 1 < net.n_layers) {
@@ -393,10 +394,10 @@ __global__ void __launch_bounds__(kRolesThreads + 128 * NSLOTS, 1) mlp_tc_kernel
 }
 
 // ---- host side ----------------------------------------------------------------------------------------
-template <int NSLOTS, bool SPLIT>
+template <int NSLOTS, bool SPLIT, bool F16>
 static int launch_tc_impl(nb2_handle* h, const TcParams& prm, cudaStream_t st) {
   using LT = TcLayout<NSLOTS, SPLIT>;
-  auto kern = mlp_tc_kernel<NSLOTS, SPLIT>;
+  auto kern = mlp_tc_kernel<NSLOTS, SPLIT, F16>;
   static bool attr_set = false;
   if (!attr_set) {
     NB2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, LT::kTotal));
@@ -430,8 +431,10 @@ int launch_mlp_tc(nb2_handle* h, int net_id, int precision, const MlpIo& io, cud
   prm.dir_levels = pn.dir_levels;
   prm.has_dir = (net_id == NB2_NET_NERF);
   prm.n_tiles = (io.n_rows + kTileRows - 1) / kTileRows;
-  if (precision == NB2_PREC_BF16) return launch_tc_impl<2, false>(h, prm, st);
-  if (precision == NB2_PREC_BF16X3) return launch_tc_impl<1, true>(h, prm, st);
+  if (precision == NB2_PREC_BF16) return launch_tc_impl<2, false, false>(h, prm, st);
+  if (precision == NB2_PREC_FP16) return launch_tc_impl<2, false, true>(h, prm, st);
+  if (precision == NB2_PREC_BF16X3) return launch_tc_impl<1, true, false>(h, prm, st);
+  if (precision == NB2_PREC_FP16X3) return launch_tc_impl<1, true, true>(h, prm, st);
   set_error("mlp_forward: unknown tensor-core precision %d", precision);
   return NB2_ERR_INVALID;
 }
@@ -469,7 +472,7 @@ umma_selftest_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* _
     float v[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = __bfloat162float(A[row * 64 + g * 8 + i]);
-    store_a8<false>(a_tile, a_tile, row, g * 8, v);
+    store_a8<false, false>(a_tile, a_tile, row, g * 8, v);
   }
   fence_proxy_async_smem();
   __syncthreads();
@@ -478,13 +481,14 @@ umma_selftest_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* _
     bulk_g2s(b_tile, Bswz, kTileBytes, smem_u32(&bars[0]));
     mbar_wait(smem_u32(&bars[0]), 0);
     tc_fence_after();
-    const uint32_t idesc = umma_idesc_bf16(128, 128);
+    const uint32_t idesc = umma_idesc_16(128, 128, false);
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks)
       umma_bf16_ss(tmem, umma_smem_desc(a_tile + ks * 32), umma_smem_desc(b_tile + ks * 32), idesc, (uint32_t)(ks != 0));
     umma_commit(smem_u32(&bars[1]));
   }
   mbar_wait(smem_u32(&bars[1]), 0);
+  __syncwarp();
   tc_fence_after();
   for (int cb = 0; cb < 4; ++cb) {
     uint32_t r[32];

@@ -495,6 +495,7 @@ using namespace nb2;
 extern "C" int nb2_generate_rays(nb2_handle* h, const float* pose, int H, int W, float fx, float fy,
                                  int64_t pix_offset, int64_t n, float* rays_out, void* stream) {
   NB2_H(h);
+  if (n == 0) return NB2_OK;
   NB2_CHECK_ARG(pose && rays_out && H > 0 && W > 0 && fx != 0.f && fy != 0.f, "generate_rays: bad arguments");
   NB2_CHECK_ARG(pix_offset >= 0 && n >= 0 && pix_offset + n <= (int64_t)H * W, "generate_rays: pixel range outside image");
   if (n == 0) return NB2_OK;
@@ -507,6 +508,7 @@ extern "C" int nb2_sample_coarse(nb2_handle* h, const float* rays, const float* 
                                  float resolution, uint64_t seed, int64_t ray_offset, int64_t n_rays,
                                  int n_samples, float* z_out, float* pts_out, void* stream) {
   NB2_H(h);
+  if (n_rays == 0) return NB2_OK;
   NB2_CHECK_ARG(base_z && z_out && n_samples > 0 && n_rays >= 0, "sample_coarse: bad arguments");
   NB2_CHECK_ARG(!pts_out || rays, "sample_coarse: pts_out requires rays");
   if (n_rays == 0) return NB2_OK;
@@ -518,6 +520,7 @@ extern "C" int nb2_sample_coarse(nb2_handle* h, const float* rays, const float* 
 
 extern "C" int nb2_posenc(nb2_handle* h, const float* x, int64_t n, int dims, int levels, float* out, void* stream) {
   NB2_H(h);
+  if (n == 0) return NB2_OK;
   NB2_CHECK_ARG(x && out && n >= 0 && dims >= 1 && dims <= 4 && levels >= 1 && levels <= 16, "posenc: bad arguments");
   if (n == 0) return NB2_OK;
   size_t smem = (size_t)kPeBlockPts * 2 * dims * levels * sizeof(float);
@@ -535,6 +538,7 @@ extern "C" int nb2_ipe(nb2_handle* h, const float* zvals, const float* rays, int
                        int levels, float radius, float* feat_out, float* mu_out, float* mu_t_out,
                        void* scratch, void* stream) {
   NB2_H(h);
+  if (n_rays == 0) return NB2_OK;
   NB2_CHECK_ARG(zvals && rays && feat_out && scratch && n_cones > 0 && levels >= 1 && levels <= 16, "ipe: bad arguments");
   if (n_rays == 0) return NB2_OK;
   cudaStream_t st = (cudaStream_t)stream;
@@ -552,6 +556,7 @@ extern "C" int nb2_weights_from_sigma(nb2_handle* h, const float* sigma, const f
                                       int dir_stride, int64_t n_rays, int n_samples, int act, float* weights_out,
                                       void* stream) {
   NB2_H(h);
+  if (n_rays == 0) return NB2_OK;
   NB2_CHECK_ARG(sigma && z && weights_out && n_samples >= 1 && n_samples <= kMaxSamples, "weights_from_sigma: n_samples must be in [1,%d]", kMaxSamples);
   NB2_CHECK_ARG(!dirs || dir_stride >= 3, "weights_from_sigma: dir_stride < 3");
   NB2_CHECK_ARG(act >= 0 && act <= 2, "weights_from_sigma: unknown activation %d", act);
@@ -565,6 +570,7 @@ extern "C" int nb2_weights_from_sigma(nb2_handle* h, const float* sigma, const f
 extern "C" int nb2_max_blur(nb2_handle* h, const float* weights, int64_t n_rays, int n_samples, float alpha,
                             float* out, void* stream) {
   NB2_H(h);
+  if (n_rays == 0) return NB2_OK;
   NB2_CHECK_ARG(weights && out && n_samples >= 1, "max_blur: bad arguments");
   if (n_rays == 0) return NB2_OK;
   max_blur_kernel<<<grid_for(n_rays * n_samples, 256), 256, 0, (cudaStream_t)stream>>>(weights, n_rays, n_samples, alpha, out);
@@ -576,6 +582,7 @@ extern "C" int nb2_sample_pdf(nb2_handle* h, const float* bins, const float* wei
                               int64_t ray_offset, int64_t n_rays, int n_bins, int n_draw, float* samples_out,
                               int64_t* below_out, int64_t* above_out, void* stream) {
   NB2_H(h);
+  if (n_rays == 0) return NB2_OK;
   NB2_CHECK_ARG(bins && weights && samples_out && below_out, "sample_pdf: null pointer");
   NB2_CHECK_ARG(n_bins >= 2 && n_bins <= kMaxSamples, "sample_pdf: n_bins must be in [2,%d]", kMaxSamples);
   NB2_CHECK_ARG(n_draw >= 1, "sample_pdf: n_draw < 1");
@@ -589,6 +596,7 @@ extern "C" int nb2_sample_pdf(nb2_handle* h, const float* bins, const float* wei
 extern "C" int nb2_search_cdf(nb2_handle* h, const float* cdf, const float* u, int64_t n_rays, int n_cdf, int n_draw,
                               int64_t* inds_out, void* stream) {
   NB2_H(h);
+  if (n_rays == 0) return NB2_OK;
   NB2_CHECK_ARG(cdf && u && inds_out && n_cdf >= 1 && n_draw >= 1, "search_cdf: bad arguments");
   if (n_rays == 0) return NB2_OK;
   search_cdf_kernel<<<grid_for(n_rays * n_draw, 256), 256, 0, (cudaStream_t)stream>>>(cdf, u, n_rays, n_cdf, n_draw, inds_out);
@@ -600,6 +608,7 @@ extern "C" int nb2_inverse_sample(nb2_handle* h, const float* weights, const flo
                                   int64_t ray_offset, int64_t n_rays, int n_samples, int n_draw, int sort,
                                   float* samples_out, int64_t* below_out, void* stream) {
   NB2_H(h);
+  if (n_rays == 0) return NB2_OK;
   NB2_CHECK_ARG(weights && z && samples_out, "inverse_sample: null pointer");
   NB2_CHECK_ARG(n_samples >= 3 && n_samples <= kMaxSamples, "inverse_sample: n_samples must be in [3,%d]", kMaxSamples);
   NB2_CHECK_ARG(n_draw >= 1 && n_draw <= kMaxDraw, "inverse_sample: n_draw must be in [1,%d]", kMaxDraw);
@@ -614,6 +623,7 @@ extern "C" int nb2_resample(nb2_handle* h, const float* sigma, const float* z, c
                             uint64_t seed, int64_t ray_offset, int64_t n_rays, int n_samples, int n_draw,
                             float blur_alpha, int flags, float* z_fine_out, void* stream) {
   NB2_H(h);
+  if (n_rays == 0) return NB2_OK;
   NB2_CHECK_ARG(sigma && z && rays && z_fine_out, "resample: null pointer");
   NB2_CHECK_ARG(n_samples >= 3 && n_samples <= kMaxSamples, "resample: n_samples must be in [3,%d]", kMaxSamples);
   NB2_CHECK_ARG(n_draw >= 2 && n_draw <= kMaxDraw, "resample: n_draw must be in [2,%d]", kMaxDraw);
@@ -629,6 +639,7 @@ extern "C" int nb2_resample(nb2_handle* h, const float* sigma, const float* z, c
 extern "C" int nb2_length2pts(nb2_handle* h, const float* rays, const float* z, int64_t n_rays, int n_samples,
                               float* pts_out, void* stream) {
   NB2_H(h);
+  if (n_rays == 0) return NB2_OK;
   NB2_CHECK_ARG(rays && z && pts_out && n_samples >= 1, "length2pts: bad arguments");
   if (n_rays == 0) return NB2_OK;
   length2pts_kernel<<<grid_for(n_rays * n_samples, 256), 256, 0, (cudaStream_t)stream>>>(rays, z, n_rays, n_samples, pts_out);
@@ -640,6 +651,7 @@ extern "C" int nb2_coarse_fine_merge(nb2_handle* h, const float* rays, const flo
                                      int64_t n_rays, int n_coarse, int n_fine, float* z_out, float* pts_out,
                                      void* stream) {
   NB2_H(h);
+  if (n_rays == 0) return NB2_OK;
   NB2_CHECK_ARG(rays && c_z && f_z && z_out, "coarse_fine_merge: null pointer");
   NB2_CHECK_ARG(n_coarse >= 1 && n_fine >= 1 && n_coarse + n_fine <= 2 * kMaxDraw, "coarse_fine_merge: too many samples");
   if (n_rays == 0) return NB2_OK;
@@ -653,6 +665,7 @@ extern "C" int nb2_composite(nb2_handle* h, const float* rgbo, const float* z, c
                              int64_t n_rays, int n_samples, int flags, float near_t, float far_t, float* rgb_out,
                              float* weights_out, float* depth_out, float* acc_out, void* stream) {
   NB2_H(h);
+  if (n_rays == 0) return NB2_OK;
   NB2_CHECK_ARG(rgbo && z && dirs && rgb_out, "composite: null pointer");
   NB2_CHECK_ARG(dir_stride >= 3, "composite: dir_stride < 3");
   NB2_CHECK_ARG(n_samples >= 1 && n_samples <= kMaxSamples, "composite: n_samples must be in [1,%d]", kMaxSamples);

@@ -10,6 +10,8 @@
 #include <algorithm>
 #include <vector>
 
+#include <cuda_fp16.h>
+
 #include "nb2_common.cuh"
 #include "nb2_tc_ptx.cuh"
 
@@ -32,16 +34,21 @@ struct PackSimtDesc {
 
 __global__ void pack_chunks_kernel(const PackChunkDesc* __restrict__ descs, __nv_bfloat16* __restrict__ out) {
   const PackChunkDesc d = descs[blockIdx.x];
-  __nv_bfloat16* hi = out + ((size_t)blockIdx.x * 2 + 0) * (kTileBytes / 2);
-  __nv_bfloat16* lo = out + ((size_t)blockIdx.x * 2 + 1) * (kTileBytes / 2);
+  // per chunk: [bf16 hi][bf16 lo][fp16 hi][fp16 lo], 16 KB each
+  __nv_bfloat16* bhi = out + ((size_t)blockIdx.x * 4 + 0) * (kTileBytes / 2);
+  __nv_bfloat16* blo = out + ((size_t)blockIdx.x * 4 + 1) * (kTileBytes / 2);
+  __half* hhi = reinterpret_cast<__half*>(out + ((size_t)blockIdx.x * 4 + 2) * (kTileBytes / 2));
+  __half* hlo = reinterpret_cast<__half*>(out + ((size_t)blockIdx.x * 4 + 3) * (kTileBytes / 2));
   for (int i = threadIdx.x; i < kTileRows * kTileCols; i += blockDim.x) {
     const int n = i / kTileCols, k = i % kTileCols;
     const float w = (k < d.valid_cols) ? d.W[(size_t)(d.n0 + n) * d.ld + d.col_off + k] : 0.f;
-    const __nv_bfloat16 h = __float2bfloat16_rn(w);
-    const __nv_bfloat16 l = __float2bfloat16_rn(w - __bfloat162float(h));
     const uint32_t o = ptx::swz128_offset(n, k) / 2;
-    hi[o] = h;
-    lo[o] = l;
+    const __nv_bfloat16 bh = __float2bfloat16_rn(w);
+    bhi[o] = bh;
+    blo[o] = __float2bfloat16_rn(w - __bfloat162float(bh));
+    const __half hh = __float2half_rn(w);
+    hhi[o] = hh;
+    hlo[o] = __float2half_rn(w - __half2float(hh));
   }
 }
 
@@ -108,7 +115,7 @@ int pack_network(nb2_handle* h, int net_id, const float* const* W, const float* 
   if (!pn.d_wchunks) {
     const size_t max_chunks = 65;
     const size_t max_wt = (size_t)64 * 256 + 7 * 256 * 256 + 64 * 256 + 288 * 128;
-    NB2_CUDA(cudaMalloc(&pn.d_wchunks, max_chunks * 2 * kTileBytes));
+    NB2_CUDA(cudaMalloc(&pn.d_wchunks, max_chunks * 4 * kTileBytes));
     NB2_CUDA(cudaMalloc(&pn.d_bias, n_bias_floats * sizeof(float)));
     NB2_CUDA(cudaMalloc(&pn.d_head, kHeadFloats * sizeof(float)));
     NB2_CUDA(cudaMalloc(&pn.d_wt32, max_wt * sizeof(float)));

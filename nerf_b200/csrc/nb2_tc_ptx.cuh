@@ -73,14 +73,14 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr) {
   d |= (uint64_t)2 << 61;              // SWIZZLE_128B
   return d;
 }
-// Instruction descriptor for kind::f16, bf16 x bf16 -> fp32, both operands K-major.
-// Field layout: cute::UMMA::InstrDescriptor.
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
-  return (1u << 4)                       // c_format  = F32
-         | (1u << 7)                     // a_format  = BF16
-         | (1u << 10)                    // b_format  = BF16
-         | ((uint32_t)(N >> 3) << 17)    // n_dim
-         | ((uint32_t)(M >> 4) << 24);   // m_dim
+// Instruction descriptor for kind::f16, (fp16 | bf16) x same -> fp32, both operands K-major.
+// Field layout: cute::UMMA::InstrDescriptor (a/b format: 0 = F16, 1 = BF16).
+__host__ __device__ constexpr uint32_t umma_idesc_16(int M, int N, bool f16) {
+  return (1u << 4)                             // c_format  = F32
+         | ((f16 ? 0u : 1u) << 7)              // a_format
+         | ((f16 ? 0u : 1u) << 10)             // b_format
+         | ((uint32_t)(N >> 3) << 17)          // n_dim
+         | ((uint32_t)(M >> 4) << 24);         // m_dim
 }
 
 // D[tmem] (+)= A[smem] * B[smem]^T ; issued by ONE thread on behalf of the CTA.
@@ -128,6 +128,28 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 }
 __device__ __forceinline__ float bf16_lo_to_f32(uint32_t packed) { return __uint_as_float(packed << 16); }
 __device__ __forceinline__ float bf16_hi_to_f32(uint32_t packed) { return __uint_as_float(packed & 0xFFFF0000u); }
+// two fp32 -> packed f16x2 (lo half = first argument), round-to-nearest-even (overflow -> inf)
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ float2 f16x2_to_f32(uint32_t packed) {
+  float2 f;
+  asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, h;\n\t}" : "=f"(f.x), "=f"(f.y) : "r"(packed));
+  return f;
+}
+// Split helpers: 16-bit "hi" of a pair and the 16-bit residual "lo" (x ~= hi + lo).
+template <bool F16>
+__device__ __forceinline__ uint32_t pack16x2(float lo, float hi) { return F16 ? pack_f16x2(lo, hi) : pack_bf16x2(lo, hi); }
+template <bool F16>
+__device__ __forceinline__ uint32_t residual16x2(float a, float b, uint32_t hi_packed) {
+  if (F16) {
+    const float2 h = f16x2_to_f32(hi_packed);
+    return pack_f16x2(a - h.x, b - h.y);
+  }
+  return pack_bf16x2(a - bf16_lo_to_f32(hi_packed), b - bf16_hi_to_f32(hi_packed));
+}
 
 // Byte offset of element (row, col) inside a 128-row x 64-col bf16 tile with the 128 B swizzle.
 __host__ __device__ constexpr uint32_t swz128_offset(int row, int col) {

@@ -11,11 +11,12 @@ import torch
 from . import _lib
 from ._lib import NB2Error, PRECISIONS, check, f32, handle, load, ptr, stream_ptr
 
-_default_precision = "bf16x3"
+_default_precision = "fp16x3"
 
 
 def set_default_precision(name):
-    """'fp32' (CUDA cores, strict), 'bf16x3' (tcgen05, fp32-faithful split) or 'bf16' (tcgen05)."""
+    """'fp32' (CUDA cores, strict), 'fp16x3' (tcgen05, fp32-faithful hi/lo split; default), 'bf16' / 'fp16'
+    (tcgen05 single pass) or 'bf16x3'."""
     global _default_precision
     if name not in PRECISIONS:
         raise ValueError(f"unknown precision {name!r}; choose from {sorted(PRECISIONS)}")

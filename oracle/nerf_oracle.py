@@ -105,7 +105,7 @@ def np_forward(kind, sd, pts, pos_levels=10, dir_levels=4):
     return np.concatenate((rgb, sigma), axis=-1)
 
 
-def make_params(kind, seed, style="he", pos_levels=10, dir_levels=4, hidden=256, sigma_std=25.0, sigma_mean=5.0):
+def make_params(kind, seed, style="he", pos_levels=10, dir_levels=4, hidden=256, sigma_std=25.0, sigma_mean=-15.0):
     """state_dict-shaped deterministic parameters.
 
     style 'he'      : uniform with He variance and small biases; the density head is then rescaled and
@@ -113,6 +113,12 @@ def make_params(kind, seed, style="he", pos_levels=10, dir_levels=4, hidden=256,
                       mean `sigma_mean` and std `sigma_std` over the scene volume -> a non-degenerate
                       random field with empty and opaque regions.  (A deep ReLU net at init is almost
                       constant in space, so without this every sample would have the same sign.)
+    style 'smooth'  : as 'he', but the first-layer / skip-layer columns that read encoding level l are damped
+                      by 2^-l.  'he' is a *chaotic* field: its outputs move by ~1e-4 when a sample depth moves by
+                      one fp32 ulp (the 2^9 encoding frequency times an O(1) gain), so no two implementations
+                      of the reference (not even its own CPU and GPU paths) agree to 1e-4 end to end on it.
+                      'smooth' is band-limited the way trained radiance fields are, and is the field used for
+                      end-to-end parity.
     style 'refinit' : the reference's init scale (std 0.02, zero bias; nerf/nerf_base.py:14-22) ->
                       the tiny-activation regime every freshly constructed reference model is in.
     """
@@ -120,7 +126,7 @@ def make_params(kind, seed, style="he", pos_levels=10, dir_levels=4, hidden=256,
     head = "layers.8" if kind == "proposal" else "opacity_head.0"
     sd = {}
     for i, (key, (o, k)) in enumerate(zip(keys, layer_shapes(kind, pos_levels, dir_levels, hidden))):
-        if style == "he":
+        if style in ("he", "smooth"):
             bound = math.sqrt(6.0 / k)
             w = det_uniform((o, k), seed * 1000 + 2 * i, -bound, bound)
             b = det_uniform((o,), seed * 1000 + 2 * i + 1, -0.1, 0.1)
@@ -128,8 +134,16 @@ def make_params(kind, seed, style="he", pos_levels=10, dir_levels=4, hidden=256,
             bound = 0.02 * math.sqrt(3.0)
             w = det_uniform((o, k), seed * 1000 + 2 * i, -bound, bound)
             b = torch.zeros(o)
+        if style == "smooth" and key in ("layers.0", "lin_block1.0", "lin_block2.0"):
+            # band-limit the field like a trained network: the columns fed by encoding level l are damped
+            # by 2^-l, so d(output)/d(position) stays O(1) instead of O(2^9)
+            damp = np.ones(k, dtype=np.float32)
+            for l in range(pos_levels):
+                damp[3 + 6 * l: 9 + 6 * l] = np.float32(2.0 ** -l)
+            damp[:3 + 6 * pos_levels] *= np.float32(2.5)
+            w = torch.from_numpy((w.numpy() * damp[None, :]).astype(np.float32))
         sd[key + ".weight"], sd[key + ".bias"] = w, b
-    if style == "he":
+    if style in ("he", "smooth"):
         probe = torch.cat((det_uniform((1024, 3), seed * 1000 + 777, -2.0, 2.0),
                            det_uniform((1024, 3), seed * 1000 + 778, -1.0, 1.0)), dim=-1).numpy()
         out = np_forward(kind, sd, probe, pos_levels, dir_levels)

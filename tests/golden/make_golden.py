@@ -144,7 +144,7 @@ def main():
         f, mu, mu_t = ref.mip_methods.ipe_feature(g["ipe_z"], g["ipe_rays"], 10, 0.01)
         out["ipe_feat"], out["ipe_mu"], out["ipe_mu_t"] = f, mu, mu_t
 
-        for style in ("he", "refinit"):
+        for style in ("he", "smooth", "refinit"):
             prop = load_sd(ref.ProposalNetwork(10, 256), make_params("proposal", 1, style))
             net = load_sd(ref.MipNeRF(10, 4, 256), make_params("nerf", 2, style))
             out[f"prop_fwd_{style}"] = prop.forward(g["mlp_pts"][..., :3].contiguous())

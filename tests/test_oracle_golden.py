@@ -85,7 +85,7 @@ def test_ipe(golden, gin):
 
 
 def test_mlps(golden, gin):
-    for style in ("he", "refinit"):
+    for style in ("he", "smooth", "refinit"):
         sp, sn = O.make_params("proposal", 1, style), O.make_params("nerf", 2, style)
         p = O.proposal_forward(sp, gin["mlp_pts"][..., :3])
         n = O.nerf_forward(sn, gin["mlp_pts"])
@@ -93,7 +93,7 @@ def test_mlps(golden, gin):
         close(n, golden[f"nerf_fwd_{style}"], rtol=1e-5, atol=1e-5 * float(golden[f"nerf_fwd_{style}"].abs().max()))
     # the 'he' field is non-degenerate: densities of both signs, colours away from 0.5
     g = golden["nerf_fwd_he"]
-    assert float(g[..., 3].max()) > 1.0 and float(g[..., 3].min()) < -1.0
+    assert float(g[..., 3].max()) > 1.0 and float(g[..., 3].min()) < -1.0, (float(g[..., 3].max()), float(g[..., 3].min()))
     assert float(g[..., :3].std()) > 0.05
 
 
@@ -103,14 +103,38 @@ def test_render_image_tile(golden):
     pose, jitter, u, focal = render_case(H, W)
     rays = O.generate_rays(pose, H, W, focal)
     base_z = torch.linspace(2.0, 6.0, 64)
-    for style in ("he", "refinit"):
+    for style in ("he", "smooth", "refinit"):
         sp, sn = O.make_params("proposal", 1, style), O.make_params("nerf", 2, style)
         out = O.render_rays(sp, sn, rays, base_z, jitter, u, 2.0, 6.0, 128, white_bkg=True, torch_sum=True)
         rgb = out["rgb"].view(H, W, 3).permute(2, 0, 1)
         err = (rgb - golden[f"img_rgb_{style}"]).abs()
-        assert float(err.max()) < 1e-4, float(err.max())
+        # same ops on the same machine: (near) bit-identical; on another host CPU the chaotic 'he' field
+        # amplifies ulp-level exp/sin differences (see test_he_field_is_ill_conditioned)
+        tol = 2e-3 if style == "he" else 1e-4
+        assert float(err.max()) < tol, float(err.max())
         derr = (out["depth"].view(H, W) - golden[f"img_depth_{style}"]).abs()
-        assert float(derr.max()) < 1e-4, float(derr.max())
+        assert float(derr.max()) < tol, float(derr.max())
+
+
+def test_he_field_is_ill_conditioned():
+    """Why end-to-end 1e-4 parity is asserted on the band-limited field: on the He-init field a ONE-ulp change
+    of the fine depths already moves the reference's own output by more than 1e-4."""
+    H = W = 50
+    pose, jitter, u, focal = render_case(H, W)
+    rays = O.generate_rays(pose, H, W, focal)[::4]
+    jitter, u = jitter[::4], u[::4]
+    base_z = torch.linspace(2.0, 6.0, 64)
+    moved = {}
+    for style in ("he", "smooth"):
+        sp, sn = O.make_params("proposal", 1, style), O.make_params("nerf", 2, style)
+        z = O.render_rays(sp, sn, rays, base_z, jitter, u, 2.0, 6.0, 128, white_bkg=True)["z_fine"]
+        z1 = torch.nextafter(z, torch.full_like(z, 10.0))
+
+        def fine(zz):
+            return O.composite(O.nerf_forward(sn, O.length2pts(rays, zz)), zz, rays[:, 3:], True, (2.0, 6.0))["rgb"]
+
+        moved[style] = float((fine(z) - fine(z1)).abs().max())
+    assert moved["he"] > 1e-4 and moved["smooth"] < 2e-5, moved
 
 
 def test_config1_trainer_composition(golden):

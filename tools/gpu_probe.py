@@ -1,0 +1,79 @@
+"""Staged GPU bring-up probe: each stage runs in its own process (a hang or fault in one cannot mask the
+others) and dumps raw outputs under gpurun_out/ for offline analysis."""
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import nerf_b200  # noqa: E402
+from nerf_b200 import _lib, ops  # noqa: E402
+from oracle import nerf_oracle as O  # noqa: E402
+
+OUT = os.path.join(ROOT, "gpurun_out")
+os.makedirs(OUT, exist_ok=True)
+DEV = "cuda"
+
+
+def load(module, sd):
+    module.load_state_dict({k: v.clone() for k, v in sd.items()})
+    return module.to(DEV)
+
+
+def stage_selftest():
+    g = torch.Generator().manual_seed(1)
+    A = torch.randn(128, 64, generator=g).to(torch.bfloat16)
+    B = torch.randn(128, 64, generator=g).to(torch.bfloat16)
+    D = ops.selftest_umma(A.to(DEV), B.to(DEV))
+    torch.cuda.synchronize()
+    ref = A.float() @ B.float().T
+    err = (D.cpu() - ref).abs()
+    print("selftest max err", float(err.max()), "mean |ref|", float(ref.abs().mean()), "frac bad", float((err > 1e-2).float().mean()))
+    np.savez(os.path.join(OUT, "selftest.npz"), A=A.float().numpy(), B=B.float().numpy(), D=D.cpu().numpy())
+
+
+def stage_mlp(kind, precision, n=1000):
+    sd = O.make_params(kind, 1 if kind == "proposal" else 2, "he")
+    mod = load(nerf_b200.ProposalNetwork(10, 256) if kind == "proposal" else nerf_b200.MipNeRF(10, 4, 256), sd)
+    mod.precision = precision
+    pts = torch.cat((O.det_uniform((n, 3), 9, -2.0, 2.0), O.det_uniform((n, 3), 10, -1.0, 1.0)), -1)
+    with torch.no_grad():
+        t0 = time.time()
+        out = mod.forward(pts[None].to(DEV) if kind == "nerf" else pts[None, :, :3].contiguous().to(DEV))[0]
+        torch.cuda.synchronize()
+        print("launch+sync s", time.time() - t0)
+    ref = O.nerf_forward(sd, pts) if kind == "nerf" else O.proposal_forward(sd, pts[:, :3])
+    err = (out.cpu() - ref).abs()
+    print(kind, precision, "max err", float(err.max()), "max |ref|", float(ref.abs().max()), "nan", int(torch.isnan(out).sum()))
+    if kind == "nerf":
+        print("  rgb max err", float(err[:, :3].max()), "sigma max err", float(err[:, 3].max()))
+    np.savez(os.path.join(OUT, f"mlp_{kind}_{precision}.npz"), out=out.cpu().numpy(), ref=ref.numpy())
+
+
+def stage_time(precision, H=400):
+    net = load(nerf_b200.MipNeRF(10, 4, 256), O.make_params("nerf", 2, "he"))
+    prop = load(nerf_b200.ProposalNetwork(10, 256), O.make_params("proposal", 1, "he"))
+    pose = nerf_b200.pose_spherical(30.0, -30.0, 4.0)[:3, :].to(DEV)
+    focal = nerf_b200.fov2Focal(0.6911112070083618, (H, H))[0]
+    for i in range(3):
+        torch.cuda.synchronize()
+        t0 = time.time()
+        nerf_b200.render_image(net, prop, pose, (H, H), focal, 2.0, 6.0, 128, white_bkg=True, precision=precision, seed=1)
+        torch.cuda.synchronize()
+        dt = time.time() - t0
+        print(f"render {H}x{H} {precision}: {dt * 1e3:.2f} ms  {H * H / dt / 1e6:.3f} Mrays/s")
+
+
+if __name__ == "__main__":
+    stage = sys.argv[1]
+    print("== stage", stage, sys.argv[2:], "on", torch.cuda.get_device_name(0))
+    if stage == "selftest":
+        stage_selftest()
+    elif stage == "mlp":
+        stage_mlp(sys.argv[2], sys.argv[3], int(sys.argv[4]) if len(sys.argv) > 4 else 1000)
+    elif stage == "time":
+        stage_time(sys.argv[2], int(sys.argv[3]) if len(sys.argv) > 3 else 400)
+    print("== done", stage)
