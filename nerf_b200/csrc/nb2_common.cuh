@@ -79,8 +79,9 @@ struct TcLayer {
   int kc;        // number of 64-wide K chunks
   int nc;        // number of 128-wide N chunks
   int a_src[5];  // A chunk id for each K chunk
+  int ks0[5];    // first 16-wide k-step of each K chunk (3 for a bias-only chunk, else 0)
   int epi;       // EpiKind
-  int bias_off;  // offset (floats) into the bias array
+  int bias_off;  // offset (floats) into the fp32 bias array (CUDA-core path)
   int chunk0;    // first weight chunk of this layer in the packed stream
 };
 struct TcNet {

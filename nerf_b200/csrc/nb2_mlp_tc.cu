@@ -21,7 +21,12 @@
 //
 // Shared memory (bytes):  activations NSLOTS * (SPLIT ? 2 : 1) * 5 * 16 KB = 160 KB,
 //                         weight ring 4 * 16 KB = 64 KB, barriers + scratch < 1 KB.
-// TMEM: 512 columns; slot s owns columns [256 s, 256 s + 256) (128 lanes x 256 fp32).
+// TMEM: 512 columns; slot s owns columns [256 s, 256 s + 256) (128 lanes x 256 fp32).  Split mode has one
+//       slot and uses columns [256, 512) as a second accumulator for the hi*lo + lo*hi cross terms, so the
+//       main accumulator sees a third of the (truncating) tensor-core additions; the two are summed in fp32
+//       by the epilogue.
+// Biases ride on the tensor core: encoding column 63 is the constant 1 and the matching weight column is
+// the bias (layers without an encoding K-chunk get a one-k-step "bias chunk").
 #include "nb2_common.cuh"
 #include "nb2_rowio.cuh"
 #include "nb2_tc_ptx.cuh"
@@ -82,6 +87,8 @@ __device__ __forceinline__ void store_a8(uint32_t tile_hi, uint32_t tile_lo, int
 }
 
 // Encoded position / direction row -> E tile.  NCOLS = 64 (position) or 32 (direction).
+// Column 63 of the position row is the constant 1: the matching weight column carries the layer bias,
+// so biases are added by the tensor core (see nb2_pack.cu) and never touch the epilogue.
 template <bool SPLIT, bool F16, int NCOLS, int MAXLEV>
 __device__ __forceinline__ void write_enc_row(uint32_t tile_hi, uint32_t tile_lo, int row, const float x[3],
                                               int levels, bool valid) {
@@ -104,6 +111,7 @@ __device__ __forceinline__ void write_enc_row(uint32_t tile_hi, uint32_t tile_lo
       }
     }
   }
+  if (NCOLS == 64) v[NCOLS - 1] = 1.f;
 #pragma unroll
   for (int g = 0; g < NCOLS / 8; ++g) {
     float w[8];
@@ -111,6 +119,64 @@ __device__ __forceinline__ void write_enc_row(uint32_t tile_hi, uint32_t tile_lo
     for (int i = 0; i < 8; ++i) w[i] = v[8 * g + i];
     store_a8<SPLIT, F16>(tile_hi, tile_lo, row, 8 * g, w);
   }
+}
+
+// ---- hidden-layer epilogue: TMEM accumulator -> act -> 16-bit A operand of the next layer (in place) ----
+// EPI: EPI_RELU / EPI_LINEAR / EPI_RELU_SIGMA / EPI_SIGMA_OUT.  Returns the density-head dot product
+// (without its bias) for the *_SIGMA kinds.  In SPLIT mode the cross terms live in a second accumulator
+// (columns +256) and are added here in fp32.
+template <int EPI, bool SPLIT, bool F16>
+__device__ __forceinline__ float epilogue_hidden(uint32_t acc, uint32_t slot_base, uint32_t lo_off, int row,
+                                                 const float* __restrict__ head) {
+  constexpr bool kRelu = (EPI != EPI_LINEAR);
+  constexpr bool kSigma = (EPI == EPI_RELU_SIGMA || EPI == EPI_SIGMA_OUT);
+  constexpr bool kStore = (EPI != EPI_SIGMA_OUT);
+  float sg = 0.f;
+#pragma unroll 1
+  for (int cb = 0; cb < kHidden / 32; ++cb) {
+    uint32_t r[32];
+    tmem_ld32(acc + cb * 32, r);
+    if (SPLIT) {
+      uint32_t c[32];
+      tmem_ld32(acc + 256 + cb * 32, c);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(c[j]));
+    } else {
+      tmem_ld_wait();
+    }
+    const uint32_t h_hi = slot_base + (uint32_t)(cb >> 1) * kTileBytes;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const int col = cb * 32 + g * 8;
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]);
+      if (kRelu && (SPLIT || kSigma)) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+      }
+      if (kSigma) {
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(head + kHeadSigmaW + col));
+        const float4 w1 = __ldg(reinterpret_cast<const float4*>(head + kHeadSigmaW + col + 4));
+        sg = fmaf(v[0], w0.x, sg); sg = fmaf(v[1], w0.y, sg); sg = fmaf(v[2], w0.z, sg); sg = fmaf(v[3], w0.w, sg);
+        sg = fmaf(v[4], w1.x, sg); sg = fmaf(v[5], w1.y, sg); sg = fmaf(v[6], w1.z, sg); sg = fmaf(v[7], w1.w, sg);
+      }
+      if (kStore) {
+        if (SPLIT || kSigma || !kRelu) {
+          store_a8<SPLIT, F16>(h_hi, h_hi + lo_off, row, col & 63, v);
+        } else {
+          // single pass: relu fused into the fp32 -> 16-bit conversion
+          const uint32_t off = (uint32_t)row * 128u + (((((uint32_t)col & 63u) >> 3) ^ ((uint32_t)row & 7u)) << 4);
+          uint32_t h[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) h[i] = pack16x2_relu<F16>(v[2 * i], v[2 * i + 1]);
+          st_shared_v4(h_hi + off, h[0], h[1], h[2], h[3]);
+        }
+      }
+    }
+  }
+  return sg;
 }
 
 // ---- the kernel ----------------------------------------------------------------------------------
@@ -194,20 +260,22 @@ __global__ void __launch_bounds__(kRolesThreads + 128 * NSLOTS, 1) mlp_tc_kernel
             const uint32_t slot_base = act_base + s * LT::kSlotBytes;
             const uint32_t acc = tmem_base + (uint32_t)(s * 256);
             for (int n = 0; n < L.nc; ++n) {
+              const uint32_t d_main = acc + n * 128;
+              const uint32_t d_corr = d_main + 256;   // SPLIT only: cross terms hi*lo + lo*hi
               for (int k = 0; k < L.kc; ++k) {
                 const uint32_t a_hi = slot_base + (uint32_t)L.a_src[k] * kTileBytes;
                 const uint32_t a_lo = a_hi + kChunksPerSlot * kTileBytes;
+                const int ks0 = L.ks0[k];
                 mbar_wait(smem_u32(&misc->w_full[stage]), phase);
                 tc_fence_after();
                 const uint32_t w_hi = ring_base + stage * kTileBytes;
-#pragma unroll
-                for (int ks = 0; ks < 4; ++ks)
-                  umma_bf16_ss(acc + n * 128, umma_smem_desc(a_hi + ks * 32), umma_smem_desc(w_hi + ks * 32), idesc,
+                for (int ks = ks0; ks < 4; ++ks)
+                  umma_bf16_ss(d_main, umma_smem_desc(a_hi + ks * 32), umma_smem_desc(w_hi + ks * 32), idesc,
                                (uint32_t)((k | ks) != 0));
                 if (SPLIT) {
-#pragma unroll
-                  for (int ks = 0; ks < 4; ++ks)
-                    umma_bf16_ss(acc + n * 128, umma_smem_desc(a_lo + ks * 32), umma_smem_desc(w_hi + ks * 32), idesc, 1u);
+                  for (int ks = ks0; ks < 4; ++ks)
+                    umma_bf16_ss(d_corr, umma_smem_desc(a_lo + ks * 32), umma_smem_desc(w_hi + ks * 32), idesc,
+                                 (uint32_t)((k | ks) != 0));
                 }
                 umma_commit(smem_u32(&misc->w_empty[stage]));
                 if (++stage == kStages) { stage = 0; phase ^= 1u; }
@@ -215,9 +283,8 @@ __global__ void __launch_bounds__(kRolesThreads + 128 * NSLOTS, 1) mlp_tc_kernel
                   mbar_wait(smem_u32(&misc->w_full[stage]), phase);
                   tc_fence_after();
                   const uint32_t w_lo = ring_base + stage * kTileBytes;
-#pragma unroll
-                  for (int ks = 0; ks < 4; ++ks)
-                    umma_bf16_ss(acc + n * 128, umma_smem_desc(a_hi + ks * 32), umma_smem_desc(w_lo + ks * 32), idesc, 1u);
+                  for (int ks = ks0; ks < 4; ++ks)
+                    umma_bf16_ss(d_corr, umma_smem_desc(a_hi + ks * 32), umma_smem_desc(w_lo + ks * 32), idesc, 1u);
                   umma_commit(smem_u32(&misc->w_empty[stage]));
                   if (++stage == kStages) { stage = 0; phase ^= 1u; }
                 }
@@ -254,28 +321,39 @@ __global__ void __launch_bounds__(kRolesThreads + 128 * NSLOTS, 1) mlp_tc_kernel
 
       float sigma = 0.f;
       for (int l = 0; l < net.n_layers; ++l) {
-        const TcLayer& L = net.layer[l];
-        const float* bias = p.bias + L.bias_off;
+        const int epi = net.layer[l].epi;
         mbar_wait(acc_full, pacc);
         pacc ^= 1u;
         __syncwarp();
         tc_fence_after();
 
-        if (L.epi == EPI_RGB) {
-          // ---- rgb_layer: t = relu(acc + b) (128 wide), rgb = sigmoid(W1 t + b1) ---------------
+        if (epi == EPI_RGB) {
+          // ---- rgb_layer: t = relu(acc) (128 wide, bias folded), rgb = sigmoid(W1 t + b1) --------
           float c0 = 0.f, c1 = 0.f, c2 = 0.f;
 #pragma unroll 1
           for (int cb = 0; cb < kRgbHidden / 32; ++cb) {
             uint32_t r[32];
             tmem_ld32(acc + cb * 32, r);
-            tmem_ld_wait();
+            if (SPLIT) {
+              uint32_t c[32];
+              tmem_ld32(acc + 256 + cb * 32, c);
+              tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int col = cb * 32 + j;
-              const float t = fmaxf(__uint_as_float(r[j]) + __ldg(bias + col), 0.f);
-              c0 = fmaf(t, __ldg(p.head + kHeadRgbW + col), c0);
-              c1 = fmaf(t, __ldg(p.head + kHeadRgbW + 128 + col), c1);
-              c2 = fmaf(t, __ldg(p.head + kHeadRgbW + 256 + col), c2);
+              for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(c[j]));
+            } else {
+              tmem_ld_wait();
+            }
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              const int col = cb * 32 + g * 4;
+              const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.head + kHeadRgbW + col));
+              const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.head + kHeadRgbW + 128 + col));
+              const float4 w2 = __ldg(reinterpret_cast<const float4*>(p.head + kHeadRgbW + 256 + col));
+              const float t0 = fmaxf(__uint_as_float(r[g * 4 + 0]), 0.f), t1 = fmaxf(__uint_as_float(r[g * 4 + 1]), 0.f);
+              const float t2 = fmaxf(__uint_as_float(r[g * 4 + 2]), 0.f), t3 = fmaxf(__uint_as_float(r[g * 4 + 3]), 0.f);
+              c0 = fmaf(t0, w0.x, c0); c0 = fmaf(t1, w0.y, c0); c0 = fmaf(t2, w0.z, c0); c0 = fmaf(t3, w0.w, c0);
+              c1 = fmaf(t0, w1.x, c1); c1 = fmaf(t1, w1.y, c1); c1 = fmaf(t2, w1.z, c1); c1 = fmaf(t3, w1.w, c1);
+              c2 = fmaf(t0, w2.x, c2); c2 = fmaf(t1, w2.y, c2); c2 = fmaf(t2, w2.z, c2); c2 = fmaf(t3, w2.w, c2);
             }
           }
           c0 = 1.f / (1.f + expf(-(c0 + __ldg(p.head + kHeadRgbB + 0))));
@@ -331,48 +409,21 @@ __global__ void __launch_bounds__(kRolesThreads + 128 * NSLOTS, 1) mlp_tc_kernel
             }
             named_bar_sync(1 + s, 128);  // scratch is reused by the next tile
           }
-        } else {
-          // ---- hidden layer: h = act(acc + b) -> bf16 (hi [+ lo]) A operand, in place ------------
-          const bool relu = (L.epi != EPI_LINEAR);
-          const bool want_sigma = (L.epi == EPI_RELU_SIGMA || L.epi == EPI_SIGMA_OUT);
-          float sg = 0.f;
-#pragma unroll 1
-          for (int cb = 0; cb < kHidden / 32; ++cb) {
-            uint32_t r[32];
-            tmem_ld32(acc + cb * 32, r);
-            tmem_ld_wait();
-            const uint32_t h_hi = slot_base + (uint32_t)(cb >> 1) * kTileBytes;
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const int col = cb * 32 + g * 8;
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + col));
-              const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + col + 4));
-              float v[8] = {__uint_as_float(r[g * 8 + 0]) + b0.x, __uint_as_float(r[g * 8 + 1]) + b0.y,
-                            __uint_as_float(r[g * 8 + 2]) + b0.z, __uint_as_float(r[g * 8 + 3]) + b0.w,
-                            __uint_as_float(r[g * 8 + 4]) + b1.x, __uint_as_float(r[g * 8 + 5]) + b1.y,
-                            __uint_as_float(r[g * 8 + 6]) + b1.z, __uint_as_float(r[g * 8 + 7]) + b1.w};
-              if (relu) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
-              }
-              if (want_sigma) {
-                const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.head + kHeadSigmaW + col));
-                const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.head + kHeadSigmaW + col + 4));
-                sg = fmaf(v[0], w0.x, sg); sg = fmaf(v[1], w0.y, sg); sg = fmaf(v[2], w0.z, sg); sg = fmaf(v[3], w0.w, sg);
-                sg = fmaf(v[4], w1.x, sg); sg = fmaf(v[5], w1.y, sg); sg = fmaf(v[6], w1.z, sg); sg = fmaf(v[7], w1.w, sg);
-              }
-              if (L.epi != EPI_SIGMA_OUT) store_a8<SPLIT, F16>(h_hi, h_hi + lo_off, row, col & 63, v);
-            }
-          }
-          if (want_sigma) sigma = sg + __ldg(p.head + kHeadSigmaB);
-          if (L.epi == EPI_SIGMA_OUT) {
-            if (in.valid) p.io.out[grow] = sigma;
-          } else if (L.epi == EPI_RELU_SIGMA && p.has_dir) {
+        } else if (epi == EPI_RELU) {
+          epilogue_hidden<EPI_RELU, SPLIT, F16>(acc, slot_base, lo_off, row, p.head);
+        } else if (epi == EPI_LINEAR) {
+          epilogue_hidden<EPI_LINEAR, SPLIT, F16>(acc, slot_base, lo_off, row, p.head);
+        } else if (epi == EPI_RELU_SIGMA) {
+          sigma = epilogue_hidden<EPI_RELU_SIGMA, SPLIT, F16>(acc, slot_base, lo_off, row, p.head) + __ldg(p.head + kHeadSigmaB);
+          if (p.has_dir) {
             // the encoded position is dead after the skip layer: re-use its tile for the direction
             float rot[3] = {0.f, 0.f, 0.f};
             if (in.valid) normalize_dir(in.d, rot);
             write_enc_row<SPLIT, F16, kDirCols, kMaxDirLevels>(e_hi, e_lo, row, rot, p.dir_levels, in.valid);
           }
+        } else {  // EPI_SIGMA_OUT
+          sigma = epilogue_hidden<EPI_SIGMA_OUT, SPLIT, F16>(acc, slot_base, lo_off, row, p.head) + __ldg(p.head + kHeadSigmaB);
+          if (in.valid) p.io.out[grow] = sigma;
         }
         if (l + 1 < net.n_layers) {
           fence_proxy_async_smem();

@@ -18,11 +18,12 @@
 namespace nb2 {
 
 struct PackChunkDesc {
-  const float* W;
-  int ld;          // in_features of the source matrix
-  int n0;          // first output row of this tile
-  int col_off;     // first source column
-  int valid_cols;  // columns past this are zero padding
+  const float* W;     // may be null for a bias-only chunk
+  const float* bias;  // if non-null, tile column 63 carries bias[n0 + n] (the A operand's column 63 is 1)
+  int ld;             // in_features of the source matrix
+  int n0;             // first output row of this tile
+  int col_off;        // first source column
+  int valid_cols;     // columns past this are zero padding
 };
 struct PackSimtDesc {
   const float* W;
@@ -41,7 +42,8 @@ __global__ void pack_chunks_kernel(const PackChunkDesc* __restrict__ descs, __nv
   __half* hlo = reinterpret_cast<__half*>(out + ((size_t)blockIdx.x * 4 + 3) * (kTileBytes / 2));
   for (int i = threadIdx.x; i < kTileRows * kTileCols; i += blockDim.x) {
     const int n = i / kTileCols, k = i % kTileCols;
-    const float w = (k < d.valid_cols) ? d.W[(size_t)(d.n0 + n) * d.ld + d.col_off + k] : 0.f;
+    float w = (d.W != nullptr && k < d.valid_cols) ? d.W[(size_t)(d.n0 + n) * d.ld + d.col_off + k] : 0.f;
+    if (d.bias != nullptr && k == kTileCols - 1) w = d.bias[d.n0 + n];
     const uint32_t o = ptx::swz128_offset(n, k) / 2;
     const __nv_bfloat16 bh = __float2bfloat16_rn(w);
     bhi[o] = bh;
@@ -68,17 +70,33 @@ __global__ void pack_simt_kernel(const PackSimtDesc* __restrict__ descs, float* 
   }
 }
 
-static void add_tc_layer(TcNet& net, std::vector<PackChunkDesc>& chunks, const float* W, int ld, int kc, int nc,
-                         const int* a_src, const int* col_off, const int* valid, int epi, int bias_off) {
+// One MMA layer = nc N-chunks x kc K-chunks of weight tiles.  The bias is folded into the K-chunk that reads the
+// encoding tile (column 63); layers without one get an extra bias-only chunk whose MMA runs a single k-step.
+static void add_tc_layer(TcNet& net, std::vector<PackChunkDesc>& chunks, const float* W, const float* bias, int ld,
+                         int kc, int nc, const int* a_src, const int* col_off, const int* valid, int epi, int bias_off) {
   TcLayer& L = net.layer[net.n_layers++];
-  L.kc = kc;
+  int e_chunk = -1;
+  for (int k = 0; k < kc; ++k) {
+    L.a_src[k] = a_src[k];
+    L.ks0[k] = 0;
+    if (a_src[k] == kChunkE) e_chunk = k;
+  }
+  const bool extra = (e_chunk < 0);
+  if (extra) {
+    L.a_src[kc] = kChunkE;
+    L.ks0[kc] = 3;
+  }
+  L.kc = kc + (extra ? 1 : 0);
   L.nc = nc;
-  for (int k = 0; k < 5; ++k) L.a_src[k] = (k < kc) ? a_src[k] : 0;
+  for (int k = L.kc; k < 5; ++k) { L.a_src[k] = 0; L.ks0[k] = 0; }
   L.epi = epi;
   L.bias_off = bias_off;
   L.chunk0 = (int)chunks.size();
-  for (int n = 0; n < nc; ++n)
-    for (int k = 0; k < kc; ++k) chunks.push_back({W, ld, n * kTileRows, col_off[k], valid[k]});
+  for (int n = 0; n < nc; ++n) {
+    for (int k = 0; k < kc; ++k)
+      chunks.push_back({W, (k == e_chunk) ? bias : nullptr, ld, n * kTileRows, col_off[k], valid[k]});
+    if (extra) chunks.push_back({nullptr, bias, ld, n * kTileRows, 0, 0});
+  }
   net.n_chunks = (int)chunks.size();
 }
 
@@ -113,7 +131,7 @@ int pack_network(nb2_handle* h, int net_id, const float* const* W, const float* 
 
   // first use: allocate this network's device buffers (worst-case sizes, fixed by the architecture)
   if (!pn.d_wchunks) {
-    const size_t max_chunks = 65;
+    const size_t max_chunks = 80;
     const size_t max_wt = (size_t)64 * 256 + 7 * 256 * 256 + 64 * 256 + 288 * 128;
     NB2_CUDA(cudaMalloc(&pn.d_wchunks, max_chunks * 4 * kTileBytes));
     NB2_CUDA(cudaMalloc(&pn.d_bias, n_bias_floats * sizeof(float)));
@@ -126,12 +144,12 @@ int pack_network(nb2_handle* h, int net_id, const float* const* W, const float* 
   if (net_id == NB2_NET_PROPOSAL) {
     NB2_CHECK_ARG(n_layers == 5, "pack_weights: the proposal network has 5 linear layers, got %d", n_layers);
     const int eE[1] = {kChunkE}, eo[1] = {0}, ev[1] = {enc};
-    add_tc_layer(tc, chunks, W[0], enc, 1, 2, eE, eo, ev, EPI_RELU, 0);
+    add_tc_layer(tc, chunks, W[0], b[0], enc, 1, 2, eE, eo, ev, EPI_RELU, 0);
     add_simt_layer(simt, sdescs, wt_off, W[0], enc, kHidden, kEncCols, 0, 0, enc, 0, 0, 0, 0, EPI_RELU, 0);
     copies.push_back({pn.d_bias + 0, b[0], kHidden});
     for (int l = 1; l <= 3; ++l) {
       const int epi = (l == 3) ? EPI_SIGMA_OUT : EPI_RELU;
-      add_tc_layer(tc, chunks, W[l], kHidden, 4, 2, H4, off4, v4, epi, l * kHidden);
+      add_tc_layer(tc, chunks, W[l], b[l], kHidden, 4, 2, H4, off4, v4, epi, l * kHidden);
       add_simt_layer(simt, sdescs, wt_off, W[l], kHidden, kHidden, kHidden, 1, 0, kHidden, 0, 0, 0, 0, epi, l * kHidden);
       copies.push_back({pn.d_bias + l * kHidden, b[l], kHidden});
     }
@@ -141,10 +159,10 @@ int pack_network(nb2_handle* h, int net_id, const float* const* W, const float* 
     NB2_CHECK_ARG(n_layers == 11, "pack_weights: the NeRF network has 11 linear layers, got %d", n_layers);
     // lin_block1                                         mip_model.py:19-23
     const int eE[1] = {kChunkE}, eo[1] = {0}, ev[1] = {enc};
-    add_tc_layer(tc, chunks, W[0], enc, 1, 2, eE, eo, ev, EPI_RELU, 0);
+    add_tc_layer(tc, chunks, W[0], b[0], enc, 1, 2, eE, eo, ev, EPI_RELU, 0);
     add_simt_layer(simt, sdescs, wt_off, W[0], enc, kHidden, kEncCols, 0, 0, enc, 0, 0, 0, 0, EPI_RELU, 0);
     for (int l = 1; l <= 3; ++l) {
-      add_tc_layer(tc, chunks, W[l], kHidden, 4, 2, H4, off4, v4, EPI_RELU, l * kHidden);
+      add_tc_layer(tc, chunks, W[l], b[l], kHidden, 4, 2, H4, off4, v4, EPI_RELU, l * kHidden);
       add_simt_layer(simt, sdescs, wt_off, W[l], kHidden, kHidden, kHidden, 1, 0, kHidden, 0, 0, 0, 0, EPI_RELU, l * kHidden);
     }
     // lin_block2.0 on cat(enc, h)                        mip_model.py:24-27,55
@@ -152,23 +170,23 @@ int pack_network(nb2_handle* h, int net_id, const float* const* W, const float* 
       const int src[5] = {kChunkE, kChunkH0, kChunkH0 + 1, kChunkH0 + 2, kChunkH0 + 3};
       const int off[5] = {0, enc, enc + 64, enc + 128, enc + 192};
       const int val[5] = {enc, 64, 64, 64, 64};
-      add_tc_layer(tc, chunks, W[4], enc + kHidden, 5, 2, src, off, val, EPI_RELU, 4 * kHidden);
+      add_tc_layer(tc, chunks, W[4], b[4], enc + kHidden, 5, 2, src, off, val, EPI_RELU, 4 * kHidden);
       add_simt_layer(simt, sdescs, wt_off, W[4], enc + kHidden, kHidden, kEncCols, 0, 0, enc, kHidden, 1, enc, kHidden,
                      EPI_RELU, 4 * kHidden);
     }
-    add_tc_layer(tc, chunks, W[5], kHidden, 4, 2, H4, off4, v4, EPI_RELU, 5 * kHidden);
+    add_tc_layer(tc, chunks, W[5], b[5], kHidden, 4, 2, H4, off4, v4, EPI_RELU, 5 * kHidden);
     add_simt_layer(simt, sdescs, wt_off, W[5], kHidden, kHidden, kHidden, 1, 0, kHidden, 0, 0, 0, 0, EPI_RELU, 5 * kHidden);
     // lin_block2.4 feeds both opacity_head and bottle_neck   mip_model.py:56-58
-    add_tc_layer(tc, chunks, W[6], kHidden, 4, 2, H4, off4, v4, EPI_RELU_SIGMA, 6 * kHidden);
+    add_tc_layer(tc, chunks, W[6], b[6], kHidden, 4, 2, H4, off4, v4, EPI_RELU_SIGMA, 6 * kHidden);
     add_simt_layer(simt, sdescs, wt_off, W[6], kHidden, kHidden, kHidden, 1, 0, kHidden, 0, 0, 0, 0, EPI_RELU_SIGMA, 6 * kHidden);
-    add_tc_layer(tc, chunks, W[7], kHidden, 4, 2, H4, off4, v4, EPI_LINEAR, 7 * kHidden);
+    add_tc_layer(tc, chunks, W[7], b[7], kHidden, 4, 2, H4, off4, v4, EPI_LINEAR, 7 * kHidden);
     add_simt_layer(simt, sdescs, wt_off, W[7], kHidden, kHidden, kHidden, 1, 0, kHidden, 0, 0, 0, 0, EPI_LINEAR, 7 * kHidden);
     // rgb_layer.0 on cat(bottleneck, enc_dir)            mip_model.py:34-37,59
     {
       const int src[5] = {kChunkH0, kChunkH0 + 1, kChunkH0 + 2, kChunkH0 + 3, kChunkE};
       const int off[5] = {0, 64, 128, 192, 256};
       const int val[5] = {64, 64, 64, 64, dir};
-      add_tc_layer(tc, chunks, W[9], kHidden + dir, 5, 1, src, off, val, EPI_RGB, 8 * kHidden);
+      add_tc_layer(tc, chunks, W[9], b[9], kHidden + dir, 5, 1, src, off, val, EPI_RGB, 8 * kHidden);
       add_simt_layer(simt, sdescs, wt_off, W[9], kHidden + dir, kRgbHidden, kHidden, 1, 0, kHidden, kDirCols, 2, kHidden,
                      dir, EPI_RGB, 8 * kHidden);
     }

@@ -117,8 +117,10 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+// (no "memory" clobber: ordering against the async proxy is established by the fence before the mbarrier
+//  arrive; leaving it out lets the compiler hoist independent global loads across the stores)
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d));
 }
 // two fp32 -> packed bf16x2 (lo half = first argument), round-to-nearest-even
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
@@ -138,6 +140,14 @@ __device__ __forceinline__ float2 f16x2_to_f32(uint32_t packed) {
   float2 f;
   asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, h;\n\t}" : "=f"(f.x), "=f"(f.y) : "r"(packed));
   return f;
+}
+// relu fused into the conversion (PTX cvt.rn.relu.{bf16x2,f16x2}.f32, sm_80+)
+template <bool F16>
+__device__ __forceinline__ uint32_t pack16x2_relu(float lo, float hi) {
+  uint32_t r;
+  if (F16) asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  else     asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
 }
 // Split helpers: 16-bit "hi" of a pair and the 16-bit residual "lo" (x ~= hi + lo).
 template <bool F16>
