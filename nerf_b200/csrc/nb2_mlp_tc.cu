@@ -27,6 +27,8 @@
 //       by the epilogue.
 // Biases ride on the tensor core: encoding column 63 is the constant 1 and the matching weight column is
 // the bias (layers without an encoding K-chunk get a one-k-step "bias chunk").
+#include <stdlib.h>
+
 #include "nb2_common.cuh"
 #include "nb2_rowio.cuh"
 #include "nb2_tc_ptx.cuh"
@@ -44,6 +46,7 @@ struct TcParams {
   const float* bias;
   const float* head;
   int pos_levels, dir_levels, has_dir;
+  int cluster;   // CTAs per cluster sharing every weight tile through multicast bulk copies (1, 2 or 4)
   int64_t n_tiles;
 };
 
@@ -180,7 +183,9 @@ __device__ __forceinline__ float epilogue_hidden(uint32_t acc, uint32_t slot_bas
 }
 
 // ---- the kernel ----------------------------------------------------------------------------------
-template <int NSLOTS, bool SPLIT, bool F16>
+// LOCKSTEP (two-slot mode only): both resident tiles consume every weight tile back to back, halving the
+// L2 -> SM weight traffic per FLOP at the price of not overlapping one tile's epilogue with the other's MMAs.
+template <int NSLOTS, bool SPLIT, bool F16, bool LOCKSTEP>
 __global__ void __launch_bounds__(kRolesThreads + 128 * NSLOTS, 1) mlp_tc_kernel(const __grid_constant__ TcParams p) {
   using LT = TcLayout<NSLOTS, SPLIT>;
   extern __shared__ unsigned char smem_dyn[];
@@ -193,13 +198,17 @@ __global__ void __launch_bounds__(kRolesThreads + 128 * NSLOTS, 1) mlp_tc_kernel
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const TcNet& net = p.net;
   const int64_t tiles_per_iter = (int64_t)gridDim.x * NSLOTS;
-  const int64_t n_iters = (p.n_tiles + tiles_per_iter - 1) / tiles_per_iter;
+  const int64_t n_iters = (p.n_tiles + tiles_per_iter - 1) / tiles_per_iter;   // identical for every CTA: the
+  // CTAs of a cluster walk the same (iteration, layer, slot) schedule; tiles past n_tiles run on zero rows
+  const uint32_t cl_size = (uint32_t)p.cluster;
+  const uint32_t cl_rank = cl_size > 1 ? cluster_ctarank() : 0u;
+  const uint16_t cl_mask = (uint16_t)((1u << cl_size) - 1u);
 
   // ---- one-time setup ---------------------------------------------------------------------------
   if (threadIdx.x == 0) {
     for (int i = 0; i < kStages; ++i) {
       mbar_init(smem_u32(&misc->w_full[i]), 1);
-      mbar_init(smem_u32(&misc->w_empty[i]), 1);
+      mbar_init(smem_u32(&misc->w_empty[i]), cl_size);   // one arrive per consumer CTA of the cluster
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(smem_u32(&misc->a_ready[s]), 128);
@@ -213,28 +222,29 @@ __global__ void __launch_bounds__(kRolesThreads + 128 * NSLOTS, 1) mlp_tc_kernel
   }
   tc_fence_before();
   __syncthreads();
+  if (cl_size > 1) cluster_sync_all();   // every CTA's barriers exist before any remote arrive / multicast
   tc_fence_after();
   const uint32_t tmem_base = misc->tmem_base;
 
   if (warp == 0) {
     // =========================== weight streamer ==================================================
     if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
+      uint32_t stage = 0, phase = 0, q = 0;
       for (int64_t it = 0; it < n_iters; ++it) {
         for (int l = 0; l < net.n_layers; ++l) {
           const int n_chunks = net.layer[l].kc * net.layer[l].nc;
           const int chunk0 = net.layer[l].chunk0;
-          for (int s = 0; s < NSLOTS; ++s) {
-            const int64_t tile = (it * gridDim.x + blockIdx.x) * NSLOTS + s;
-            if (tile >= p.n_tiles) continue;
+          for (int s = 0; s < (LOCKSTEP ? 1 : NSLOTS); ++s) {
             for (int c = 0; c < n_chunks; ++c) {
 #pragma unroll
               for (int part = 0; part < (SPLIT ? 2 : 1); ++part) {
-                mbar_wait(smem_u32(&misc->w_empty[stage]), phase ^ 1u);
+                mbar_wait(smem_u32(&misc->w_empty[stage]), phase ^ 1u);   // all consumers of the cluster released it
                 const uint32_t full = smem_u32(&misc->w_full[stage]);
                 mbar_arrive_expect_tx(full, kTileBytes);
-                bulk_g2s(ring_base + stage * kTileBytes,
-                         p.wchunks + ((size_t)(chunk0 + c) * 4 + (F16 ? 2 : 0) + part) * (kTileBytes / 2), kTileBytes, full);
+                const __nv_bfloat16* src = p.wchunks + ((size_t)(chunk0 + c) * 4 + (F16 ? 2 : 0) + part) * (kTileBytes / 2);
+                if (cl_size == 1) bulk_g2s(ring_base + stage * kTileBytes, src, kTileBytes, full);
+                else if (q % cl_size == cl_rank) bulk_g2s_mcast(ring_base + stage * kTileBytes, src, kTileBytes, full, cl_mask);
+                ++q;
                 if (++stage == kStages) { stage = 0; phase ^= 1u; }
               }
             }
@@ -248,12 +258,40 @@ __global__ void __launch_bounds__(kRolesThreads + 128 * NSLOTS, 1) mlp_tc_kernel
       const uint32_t idesc = umma_idesc_16(128, 128, F16);
       uint32_t stage = 0, phase = 0;
       uint32_t pa[2] = {0u, 0u};
+      auto release = [&](uint32_t bar) {
+        if (cl_size == 1) umma_commit(bar); else umma_commit_mcast(bar, cl_mask);
+      };
       for (int64_t it = 0; it < n_iters; ++it) {
         for (int l = 0; l < net.n_layers; ++l) {
           const TcLayer& L = net.layer[l];
+          if (LOCKSTEP) {
+            // both tiles' operands are ready -> every weight tile is used twice
+            for (int s = 0; s < NSLOTS; ++s) {
+              mbar_wait(smem_u32(&misc->a_ready[s]), pa[s]);
+              pa[s] ^= 1u;
+            }
+            tc_fence_after();
+            for (int n = 0; n < L.nc; ++n) {
+              for (int k = 0; k < L.kc; ++k) {
+                const int ks0 = L.ks0[k];
+                mbar_wait(smem_u32(&misc->w_full[stage]), phase);
+                tc_fence_after();
+                const uint32_t w_hi = ring_base + stage * kTileBytes;
+                for (int s = 0; s < NSLOTS; ++s) {
+                  const uint32_t a_hi = act_base + s * LT::kSlotBytes + (uint32_t)L.a_src[k] * kTileBytes;
+                  const uint32_t d_main = tmem_base + (uint32_t)(s * 256) + n * 128;
+                  for (int ks = ks0; ks < 4; ++ks)
+                    umma_bf16_ss(d_main, umma_smem_desc(a_hi + ks * 32), umma_smem_desc(w_hi + ks * 32), idesc,
+                                 (uint32_t)((k | ks) != 0));
+                }
+                release(smem_u32(&misc->w_empty[stage]));
+                if (++stage == kStages) { stage = 0; phase ^= 1u; }
+              }
+            }
+            for (int s = 0; s < NSLOTS; ++s) umma_commit(smem_u32(&misc->acc_full[s]));
+            continue;
+          }
           for (int s = 0; s < NSLOTS; ++s) {
-            const int64_t tile = (it * gridDim.x + blockIdx.x) * NSLOTS + s;
-            if (tile >= p.n_tiles) continue;
             mbar_wait(smem_u32(&misc->a_ready[s]), pa[s]);
             pa[s] ^= 1u;
             tc_fence_after();
@@ -277,7 +315,7 @@ __global__ void __launch_bounds__(kRolesThreads + 128 * NSLOTS, 1) mlp_tc_kernel
                     umma_bf16_ss(d_corr, umma_smem_desc(a_lo + ks * 32), umma_smem_desc(w_hi + ks * 32), idesc,
                                  (uint32_t)((k | ks) != 0));
                 }
-                umma_commit(smem_u32(&misc->w_empty[stage]));
+                release(smem_u32(&misc->w_empty[stage]));
                 if (++stage == kStages) { stage = 0; phase ^= 1u; }
                 if (SPLIT) {
                   mbar_wait(smem_u32(&misc->w_full[stage]), phase);
@@ -285,7 +323,7 @@ __global__ void __launch_bounds__(kRolesThreads + 128 * NSLOTS, 1) mlp_tc_kernel
                   const uint32_t w_lo = ring_base + stage * kTileBytes;
                   for (int ks = ks0; ks < 4; ++ks)
                     umma_bf16_ss(d_corr, umma_smem_desc(a_hi + ks * 32), umma_smem_desc(w_lo + ks * 32), idesc, 1u);
-                  umma_commit(smem_u32(&misc->w_empty[stage]));
+                  release(smem_u32(&misc->w_empty[stage]));
                   if (++stage == kStages) { stage = 0; phase ^= 1u; }
                 }
               }
@@ -310,8 +348,7 @@ __global__ void __launch_bounds__(kRolesThreads + 128 * NSLOTS, 1) mlp_tc_kernel
     uint32_t pacc = 0;
 
     for (int64_t it = 0; it < n_iters; ++it) {
-      const int64_t tile = (it * gridDim.x + blockIdx.x) * NSLOTS + s;
-      if (tile >= p.n_tiles) break;
+      const int64_t tile = (it * gridDim.x + blockIdx.x) * NSLOTS + s;   // may lie past n_tiles: rows invalid
       const int64_t grow = tile * kTileRows + row;
       const RowIn in = load_row(p.io, grow);
       write_enc_row<SPLIT, F16, kEncCols, kMaxPosLevels>(e_hi, e_lo, row, in.p, p.pos_levels, in.valid);
@@ -438,6 +475,7 @@ __global__ void __launch_bounds__(kRolesThreads + 128 * NSLOTS, 1) mlp_tc_kernel
   // ---- teardown -----------------------------------------------------------------------------------
   tc_fence_before();
   __syncthreads();
+  if (cl_size > 1) cluster_sync_all();   // no CTA leaves while a peer may still multicast into it
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
@@ -445,19 +483,53 @@ __global__ void __launch_bounds__(kRolesThreads + 128 * NSLOTS, 1) mlp_tc_kernel
 }
 
 // ---- host side ----------------------------------------------------------------------------------------
-template <int NSLOTS, bool SPLIT, bool F16>
-static int launch_tc_impl(nb2_handle* h, const TcParams& prm, cudaStream_t st) {
+// Variant knobs (defaults chosen from measurements; overridable for experiments):
+//   NB2_TC_CLUSTER = 1 | 2 | 4      CTAs sharing each weight tile via multicast
+//   NB2_TC_LOCKSTEP = 0 | 1         two-slot modes: both tiles consume each weight tile
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
+template <int NSLOTS, bool SPLIT, bool F16, bool LOCKSTEP>
+static int launch_tc_impl(nb2_handle* h, TcParams& prm, cudaStream_t st) {
   using LT = TcLayout<NSLOTS, SPLIT>;
-  auto kern = mlp_tc_kernel<NSLOTS, SPLIT, F16>;
+  auto kern = mlp_tc_kernel<NSLOTS, SPLIT, F16, LOCKSTEP>;
   static bool attr_set = false;
   if (!attr_set) {
     NB2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, LT::kTotal));
     attr_set = true;
   }
+  const int cluster = prm.cluster;
   int64_t ctas = (prm.n_tiles + NSLOTS - 1) / NSLOTS;
-  int grid = (int)std::min<int64_t>(ctas, (int64_t)h->sm_count);
-  kern<<<grid, kRolesThreads + 128 * NSLOTS, LT::kTotal, st>>>(prm);
-  NB2_LAUNCH_CHECK(h);
+  ctas = (ctas + cluster - 1) / cluster * cluster;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.blockDim = dim3(kRolesThreads + 128 * NSLOTS);
+  cfg.dynamicSmemBytes = LT::kTotal;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int max_ctas = h->sm_count / cluster * cluster;
+  if (cluster > 1) {
+    // co-resident clusters are limited by GPC boundaries: ask the driver
+    static int cached[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (!cached[cluster]) {
+      cfg.gridDim = dim3(max_ctas);
+      int n = 0;
+      NB2_CUDA(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
+      cached[cluster] = n > 0 ? n : 1;
+    }
+    max_ctas = cached[cluster] * cluster;
+  }
+  cfg.gridDim = dim3((unsigned)std::min<int64_t>(ctas, (int64_t)max_ctas));
+  NB2_CUDA(cudaLaunchKernelEx(&cfg, kern, prm));
+  h->launches++;
   return NB2_OK;
 }
 
@@ -482,10 +554,19 @@ int launch_mlp_tc(nb2_handle* h, int net_id, int precision, const MlpIo& io, cud
   prm.dir_levels = pn.dir_levels;
   prm.has_dir = (net_id == NB2_NET_NERF);
   prm.n_tiles = (io.n_rows + kTileRows - 1) / kTileRows;
-  if (precision == NB2_PREC_BF16) return launch_tc_impl<2, false, false>(h, prm, st);
-  if (precision == NB2_PREC_FP16) return launch_tc_impl<2, false, true>(h, prm, st);
-  if (precision == NB2_PREC_BF16X3) return launch_tc_impl<1, true, false>(h, prm, st);
-  if (precision == NB2_PREC_FP16X3) return launch_tc_impl<1, true, true>(h, prm, st);
+  const bool split = (precision == NB2_PREC_BF16X3 || precision == NB2_PREC_FP16X3);
+  int cluster = env_int("NB2_TC_CLUSTER", split ? 2 : 2);
+  if (cluster != 1 && cluster != 2 && cluster != 4) {
+    set_error("NB2_TC_CLUSTER must be 1, 2 or 4 (got %d)", cluster);
+    return NB2_ERR_INVALID;
+  }
+  if (prm.n_tiles < 2 * cluster) cluster = 1;
+  prm.cluster = cluster;
+  const bool lockstep = env_int("NB2_TC_LOCKSTEP", 1) != 0;
+  if (precision == NB2_PREC_BF16) return lockstep ? launch_tc_impl<2, false, false, true>(h, prm, st) : launch_tc_impl<2, false, false, false>(h, prm, st);
+  if (precision == NB2_PREC_FP16) return lockstep ? launch_tc_impl<2, false, true, true>(h, prm, st) : launch_tc_impl<2, false, true, false>(h, prm, st);
+  if (precision == NB2_PREC_BF16X3) return launch_tc_impl<1, true, false, false>(h, prm, st);
+  if (precision == NB2_PREC_FP16X3) return launch_tc_impl<1, true, true, false>(h, prm, st);
   set_error("mlp_forward: unknown tensor-core precision %d", precision);
   return NB2_ERR_INVALID;
 }

@@ -43,6 +43,26 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
                : "memory");
 }
 
+// Same, multicast: the bytes land at the same CTA-relative offset in every CTA of `cta_mask`, and each
+// destination CTA's mbarrier (same offset) receives the complete_tx.
+__device__ __forceinline__ void bulk_g2s_mcast(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst_smem),
+      "l"(src), "r"(bytes), "r"(bar), "h"(cta_mask)
+      : "memory");
+}
+
+// ---- thread-block cluster -----------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // ---- proxy / tcgen05 fences ----------------------------------------------------------------
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -96,6 +116,13 @@ __device__ __forceinline__ void umma_bf16_ss(uint32_t tmem_d, uint64_t adesc, ui
 // Arrive on an mbarrier once every previously issued tcgen05.mma of this thread has completed.
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// Same, arriving on the barrier at this offset in every CTA of `cta_mask` (weight-ring "empty" across a cluster).
+__device__ __forceinline__ void umma_commit_mcast(uint32_t bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(cta_mask)
+               : "memory");
 }
 
 // ---- TMEM -> registers: this warp's 32 lanes x 32 consecutive fp32 columns ---------------------
