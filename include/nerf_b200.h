@@ -205,6 +205,18 @@ int64_t nb2_launch_count(nb2_handle* h);
  * enabled) recorded on the render stream before launch 1 and after launches 1, 2, 3.  NULL disables. */
 int nb2_set_profile_events(nb2_handle* h, void* const* events4);
 
+/* Debug instrumentation of the tensor-core MLP kernel.  First call (any arguments) enables it; later calls
+ * synchronise the device and copy 16 cycle counters per CTA of the LAST launch into out_host (n_ctas <= 256):
+ * weight-streamer / MMA-issuer / slot-group wait and work times (see nb2_api.cu). */
+int nb2_debug_tc_profile(nb2_handle* h, long long* out_host, int n_ctas);
+
+/* Debug: MMA micro-benchmark / 2-CTA convention check.  mode 0: cta_group::1 M128 N128, 1: cta_group::1 M128 N256,
+ * 2: cta_group::2 M256 N256.  A, B: (256 x 64) bf16 row-major; D_out: (256 x 256) fp32 (rows/cols the mode covers);
+ * cycles_out[cta]: cycles per MMA instruction on every SM (all SMs run the loop concurrently).
+ * flags: stressors running beside the MMA loop (see nb2_mlp_tc.cu); gsrc_1mb: 1 MB of device memory to stream from. */
+int nb2_debug_umma_bench(nb2_handle* h, const void* A_bf16, const void* B_bf16, float* D_out, long long* cycles_out,
+                         int mode, int iters, int flags, const void* gsrc_1mb, void* stream);
+
 /* Device-side self-test of the tcgen05 building blocks: D (128x128 fp32) = A (128x64 bf16,
  * row-major) * B^T (128x64 bf16, row-major), computed by ONE UMMA sequence through the same
  * operand swizzle, descriptors, bulk copy, commit and TMEM read-out the MLP kernel uses.

@@ -65,6 +65,8 @@ SIGNATURES = {
                                 c_f32p, c_f32p, c_f32p, c_f32p, c_vp, c_i64, c_vp]),
     "nb2_launch_count": (c_i64, [c_vp]),
     "nb2_set_profile_events": (c_int, [c_vp, ctypes.POINTER(c_vp)]),
+    "nb2_debug_tc_profile": (c_int, [c_vp, ctypes.POINTER(ctypes.c_longlong), c_int]),
+    "nb2_debug_umma_bench": (c_int, [c_vp, c_vp, c_vp, c_f32p, c_vp, c_int, c_int, c_int, c_vp, c_vp]),
     "nb2_selftest_umma": (c_int, [c_vp, c_vp, c_vp, c_vp, c_f32p, c_vp]),
 }
 

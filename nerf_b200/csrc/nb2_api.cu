@@ -14,6 +14,8 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 int selftest_umma(nb2_handle* h, const void* A, const void* B, void* Bswz_scratch, float* D, cudaStream_t st);
+int umma_bench(nb2_handle* h, const void* A, const void* B, float* D, long long* cycles, int mode, int iters, int flags,
+               const void* gsrc, cudaStream_t st);
 }  // namespace nb2
 using namespace nb2;
 
@@ -58,6 +60,23 @@ extern "C" int nb2_destroy(nb2_handle* h) {
 }
 
 extern "C" int64_t nb2_launch_count(nb2_handle* h) { return h ? h->launches : -1; }
+
+// Debug: enable (n_ctas_max > 0) / read back the per-CTA role cycle counters of the LAST tensor-kernel launch.
+// 16 counters per CTA: [0] streamer wait-empty, [1] streamer total, [2] ring entries, [3] MMA wait-A, [4] MMA wait-W,
+// [5] MMA total, [6] group0 encode, [7] group0 wait-acc, [8] group0 hidden epilogues, [9] group0 last epilogue,
+// [10] group0 total, [11] iterations, [12] layers.  Synchronises the device.
+extern "C" int nb2_debug_tc_profile(nb2_handle* h, long long* out_host, int n_ctas) {
+  NB2_CHECK_ARG(h != nullptr, "null handle");
+  if (!h->tc_prof) {
+    NB2_CUDA(cudaMalloc(&h->tc_prof, 256 * 16 * sizeof(long long)));
+    NB2_CUDA(cudaMemset(h->tc_prof, 0, 256 * 16 * sizeof(long long)));
+    return NB2_OK;
+  }
+  NB2_CHECK_ARG(out_host && n_ctas > 0 && n_ctas <= 256, "debug_tc_profile: bad arguments");
+  NB2_CUDA(cudaDeviceSynchronize());
+  NB2_CUDA(cudaMemcpy(out_host, h->tc_prof, (size_t)n_ctas * 16 * sizeof(long long), cudaMemcpyDeviceToHost));
+  return NB2_OK;
+}
 
 extern "C" int nb2_set_profile_events(nb2_handle* h, void* const* events4) {
   NB2_CHECK_ARG(h != nullptr, "null handle");
@@ -210,4 +229,10 @@ extern "C" int nb2_selftest_umma(nb2_handle* h, const void* A_bf16, const void* 
                                  void* stream) {
   NB2_CHECK_ARG(h && A_bf16 && B_bf16 && scratch_16k && D_out, "selftest_umma: null pointer");
   return selftest_umma(h, A_bf16, B_bf16, scratch_16k, D_out, (cudaStream_t)stream);
+}
+
+extern "C" int nb2_debug_umma_bench(nb2_handle* h, const void* A_bf16, const void* B_bf16, float* D_out, long long* cycles_out,
+                                    int mode, int iters, int flags, const void* gsrc_1mb, void* stream) {
+  NB2_CHECK_ARG(h && A_bf16 && B_bf16 && D_out && cycles_out && gsrc_1mb && mode >= 0 && mode <= 2 && iters > 0, "debug_umma_bench: bad arguments");
+  return umma_bench(h, A_bf16, B_bf16, D_out, cycles_out, mode, iters, flags, gsrc_1mb, (cudaStream_t)stream);
 }

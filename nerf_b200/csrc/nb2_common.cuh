@@ -129,6 +129,7 @@ struct nb2_handle {
   int sm_count = 0;
   int64_t launches = 0;
   cudaEvent_t prof[4] = {nullptr, nullptr, nullptr, nullptr};
+  long long* tc_prof = nullptr;  // debug: per-CTA role cycle counters of the last tensor-kernel launch
   nb2::PackedNet net[2];
 };
 

@@ -48,11 +48,14 @@ struct TcParams {
   int pos_levels, dir_levels, has_dir;
   int cluster;   // CTAs per cluster sharing every weight tile through multicast bulk copies (1, 2 or 4)
   int64_t n_tiles;
+  long long* prof;   // optional (debug): 16 cycle counters per CTA, see nb2_debug_tc_profile
 };
+#define NB2_CLK() (p.prof ? clock64() : 0ll)
 
 struct TcMisc {
   uint64_t w_full[kStages];
   uint64_t w_empty[kStages];
+  uint64_t w_peer[kStages];   // pair kernel, leader only: the peer CTA's half of the weight tile has landed
   uint64_t a_ready[2];
   uint64_t acc_full[2];
   uint32_t tmem_base;
@@ -183,6 +186,167 @@ __device__ __forceinline__ float epilogue_hidden(uint32_t acc, uint32_t slot_bas
 }
 
 // ---- the kernel ----------------------------------------------------------------------------------
+// ---- slot group: per-tile producer (sample -> encoding) and per-layer epilogue ------------------------------------
+// Shared by the single-CTA kernel and the CTA-pair kernel (PAIR: the operand-ready barrier lives in the pair's leader).
+template <int NSLOTS, bool SPLIT, bool F16, bool PAIR>
+__device__ __forceinline__ void slot_group_run(const TcParams& p, TcMisc* misc, uint32_t act_base, uint32_t tmem_base,
+                                               int64_t n_iters, int warp, int lane, uint32_t cl_rank) {
+  using LT = TcLayout<NSLOTS, SPLIT>;
+  const TcNet& net = p.net;
+  auto arrive_a = [&](uint32_t bar) {
+    if (PAIR && cl_rank != 0) mbar_arrive_remote(bar, 0); else mbar_arrive(bar);
+  };
+  // =========================== slot group: producer + epilogue ====================================
+  const int s = (warp - 4) >> 2;
+  const int wq = warp & 3;            // TMEM lane quadrant this warp may access
+  const int row = wq * 32 + lane;     // row of the tile == TMEM lane
+  const uint32_t slot_base = act_base + s * LT::kSlotBytes;
+  const uint32_t lo_off = kChunksPerSlot * kTileBytes;
+  const uint32_t e_hi = slot_base + kChunkE * kTileBytes, e_lo = e_hi + lo_off;
+  const uint32_t acc = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(s * 256);
+  const uint32_t a_ready = smem_u32(&misc->a_ready[s]);
+  const uint32_t acc_full = smem_u32(&misc->acc_full[s]);
+  float* scratch = &misc->scratch[s][0][0];
+  uint32_t pacc = 0;
+  long long t_pe = 0, t_wacc = 0, t_epi = 0, t_last = 0, t0e = NB2_CLK();
+
+  for (int64_t it = 0; it < n_iters; ++it) {
+    const int64_t tile = (it * gridDim.x + blockIdx.x) * NSLOTS + s;   // may lie past n_tiles: rows invalid
+    const int64_t grow = tile * kTileRows + row;
+    const long long cpe = NB2_CLK();
+    const RowIn in = load_row(p.io, grow);
+    write_enc_row<SPLIT, F16, kEncCols, kMaxPosLevels>(e_hi, e_lo, row, in.p, p.pos_levels, in.valid);
+    t_pe += NB2_CLK() - cpe;
+    fence_proxy_async_smem();
+    tc_fence_before();
+    arrive_a(a_ready);
+
+    float sigma = 0.f;
+    for (int l = 0; l < net.n_layers; ++l) {
+      const int epi = net.layer[l].epi;
+      const long long cw = NB2_CLK();
+      mbar_wait(acc_full, pacc);
+      pacc ^= 1u;
+      __syncwarp();
+      tc_fence_after();
+      const long long ce = NB2_CLK();
+      t_wacc += ce - cw;
+
+      if (epi == EPI_RGB) {
+        // ---- rgb_layer: t = relu(acc) (128 wide, bias folded), rgb = sigmoid(W1 t + b1) --------
+        float c0 = 0.f, c1 = 0.f, c2 = 0.f;
+#pragma unroll 1
+        for (int cb = 0; cb < kRgbHidden / 32; ++cb) {
+          uint32_t r[32];
+          tmem_ld32(acc + cb * 32, r);
+          if (SPLIT) {
+            uint32_t c[32];
+            tmem_ld32(acc + 256 + cb * 32, c);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(c[j]));
+          } else {
+            tmem_ld_wait();
+          }
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const int col = cb * 32 + g * 4;
+            const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.head + kHeadRgbW + col));
+            const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.head + kHeadRgbW + 128 + col));
+            const float4 w2 = __ldg(reinterpret_cast<const float4*>(p.head + kHeadRgbW + 256 + col));
+            const float t0 = fmaxf(__uint_as_float(r[g * 4 + 0]), 0.f), t1 = fmaxf(__uint_as_float(r[g * 4 + 1]), 0.f);
+            const float t2 = fmaxf(__uint_as_float(r[g * 4 + 2]), 0.f), t3 = fmaxf(__uint_as_float(r[g * 4 + 3]), 0.f);
+            c0 = fmaf(t0, w0.x, c0); c0 = fmaf(t1, w0.y, c0); c0 = fmaf(t2, w0.z, c0); c0 = fmaf(t3, w0.w, c0);
+            c1 = fmaf(t0, w1.x, c1); c1 = fmaf(t1, w1.y, c1); c1 = fmaf(t2, w1.z, c1); c1 = fmaf(t3, w1.w, c1);
+            c2 = fmaf(t0, w2.x, c2); c2 = fmaf(t1, w2.y, c2); c2 = fmaf(t2, w2.z, c2); c2 = fmaf(t3, w2.w, c2);
+          }
+        }
+        c0 = 1.f / (1.f + expf(-(c0 + __ldg(p.head + kHeadRgbB + 0))));
+        c1 = 1.f / (1.f + expf(-(c1 + __ldg(p.head + kHeadRgbB + 1))));
+        c2 = 1.f / (1.f + expf(-(c2 + __ldg(p.head + kHeadRgbB + 2))));
+        if (p.io.out_mode == 1) {
+          if (in.valid) reinterpret_cast<float4*>(p.io.out)[grow] = make_float4(c0, c1, c2, sigma);
+        } else {
+          // ---- alpha compositing over the rows of each ray (nerf_base.py:79-113) -------------
+          const int P = p.io.P;                 // 32, 64 or 128: rays cover whole warps
+          const int wpr = P >> 5;               // warps per ray
+          const int wseg = wq % wpr;            // this warp's position inside its ray
+          const float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(in.d[0], in.d[0]), __fmul_rn(in.d[1], in.d[1])),
+                                            __fmul_rn(in.d[2], in.d[2])));
+          const float depth = __fmul_rn(in.z, nrm);
+          float next = __shfl_down_sync(0xffffffffu, depth, 1);
+          if (lane == 0) scratch[wq * 8 + 0] = depth;
+          named_bar_sync(1 + s, 128);
+          if (lane == 31 && wq < 3) next = scratch[(wq + 1) * 8 + 0];
+          const bool last = (in.s == P - 1);
+          const float delta = last ? 1e10f : __fsub_rn(next, depth);
+          const float m = in.valid ? expf(-fmaxf(sigma, 0.f) * delta) : 1.f;
+          const float alpha = 1.f - m;
+          const float inc = warp_scan_mul(m + 1e-10f, lane);
+          float exc = __shfl_up_sync(0xffffffffu, inc, 1);
+          if (lane == 0) exc = 1.f;
+          if (lane == 31) scratch[wq * 8 + 1] = inc;
+          named_bar_sync(1 + s, 128);
+          float carry = 1.f;
+          for (int w = wq - wseg; w < wq; ++w) carry *= scratch[w * 8 + 1];
+          const float wgt = in.valid ? alpha * (carry * exc) : 0.f;
+          float sr = warp_sum(wgt * c0), sg = warp_sum(wgt * c1), sb = warp_sum(wgt * c2);
+          float sa = warp_sum(wgt), sd = warp_sum(wgt * depth);
+          if (lane == 0) {
+            scratch[wq * 8 + 2] = sr; scratch[wq * 8 + 3] = sg; scratch[wq * 8 + 4] = sb;
+            scratch[wq * 8 + 5] = sa; scratch[wq * 8 + 6] = sd;
+          }
+          named_bar_sync(1 + s, 128);
+          if (lane == 0 && wseg == 0 && in.valid) {
+            for (int w = wq + 1; w < wq + wpr; ++w) {
+              sr += scratch[w * 8 + 2]; sg += scratch[w * 8 + 3]; sb += scratch[w * 8 + 4];
+              sa += scratch[w * 8 + 5]; sd += scratch[w * 8 + 6];
+            }
+            if (p.io.flags & NB2_WHITE_BKG) {
+              const float bg = 1.f - sa;
+              sr += bg; sg += bg; sb += bg;
+            }
+            p.io.rgb_out[in.ray * 3 + 0] = sr;
+            p.io.rgb_out[in.ray * 3 + 1] = sg;
+            p.io.rgb_out[in.ray * 3 + 2] = sb;
+            if (p.io.depth_out) p.io.depth_out[in.ray] = (sd - p.io.near_t) / (p.io.far_t - p.io.near_t);
+            if (p.io.acc_out) p.io.acc_out[in.ray] = sa;
+          }
+          named_bar_sync(1 + s, 128);  // scratch is reused by the next tile
+        }
+      } else if (epi == EPI_RELU) {
+        epilogue_hidden<EPI_RELU, SPLIT, F16>(acc, slot_base, lo_off, row, p.head);
+      } else if (epi == EPI_LINEAR) {
+        epilogue_hidden<EPI_LINEAR, SPLIT, F16>(acc, slot_base, lo_off, row, p.head);
+      } else if (epi == EPI_RELU_SIGMA) {
+        sigma = epilogue_hidden<EPI_RELU_SIGMA, SPLIT, F16>(acc, slot_base, lo_off, row, p.head) + __ldg(p.head + kHeadSigmaB);
+        if (p.has_dir) {
+          // the encoded position is dead after the skip layer: re-use its tile for the direction
+          float rot[3] = {0.f, 0.f, 0.f};
+          if (in.valid) normalize_dir(in.d, rot);
+          write_enc_row<SPLIT, F16, kDirCols, kMaxDirLevels>(e_hi, e_lo, row, rot, p.dir_levels, in.valid);
+        }
+      } else {  // EPI_SIGMA_OUT
+        sigma = epilogue_hidden<EPI_SIGMA_OUT, SPLIT, F16>(acc, slot_base, lo_off, row, p.head) + __ldg(p.head + kHeadSigmaB);
+        if (in.valid) p.io.out[grow] = sigma;
+      }
+      if (l + 1 < net.n_layers) {
+        fence_proxy_async_smem();
+        tc_fence_before();
+        arrive_a(a_ready);
+        t_epi += NB2_CLK() - ce;
+      } else {
+        t_last += NB2_CLK() - ce;
+      }
+    }
+    tc_fence_before();  // accumulator reads of the last layer precede the next tile's a_ready arrive
+  }
+  if (p.prof && threadIdx.x == kRolesThreads) {
+    long long* o = p.prof + blockIdx.x * 16;
+    o[6] = t_pe; o[7] = t_wacc; o[8] = t_epi; o[9] = t_last; o[10] = clock64() - t0e; o[11] = n_iters; o[12] = net.n_layers;
+  }
+}
+
 // LOCKSTEP (two-slot mode only): both resident tiles consume every weight tile back to back, halving the
 // L2 -> SM weight traffic per FLOP at the price of not overlapping one tile's epilogue with the other's MMAs.
 template <int NSLOTS, bool SPLIT, bool F16, bool LOCKSTEP>
@@ -230,6 +394,7 @@ __global__ void __launch_bounds__(kRolesThreads + 128 * NSLOTS, 1) mlp_tc_kernel
     // =========================== weight streamer ==================================================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0, q = 0;
+      long long t_empty = 0, t0s = NB2_CLK();
       for (int64_t it = 0; it < n_iters; ++it) {
         for (int l = 0; l < net.n_layers; ++l) {
           const int n_chunks = net.layer[l].kc * net.layer[l].nc;
@@ -238,7 +403,9 @@ __global__ void __launch_bounds__(kRolesThreads + 128 * NSLOTS, 1) mlp_tc_kernel
             for (int c = 0; c < n_chunks; ++c) {
 #pragma unroll
               for (int part = 0; part < (SPLIT ? 2 : 1); ++part) {
+                const long long c0 = NB2_CLK();
                 mbar_wait(smem_u32(&misc->w_empty[stage]), phase ^ 1u);   // all consumers of the cluster released it
+                t_empty += NB2_CLK() - c0;
                 const uint32_t full = smem_u32(&misc->w_full[stage]);
                 mbar_arrive_expect_tx(full, kTileBytes);
                 const __nv_bfloat16* src = p.wchunks + ((size_t)(chunk0 + c) * 4 + (F16 ? 2 : 0) + part) * (kTileBytes / 2);
@@ -251,6 +418,7 @@ __global__ void __launch_bounds__(kRolesThreads + 128 * NSLOTS, 1) mlp_tc_kernel
           }
         }
       }
+      if (p.prof) { p.prof[blockIdx.x * 16 + 0] = t_empty; p.prof[blockIdx.x * 16 + 1] = clock64() - t0s; p.prof[blockIdx.x * 16 + 2] = q; }
     }
   } else if (warp == 1) {
     // =========================== MMA issuer =======================================================
@@ -258,6 +426,7 @@ __global__ void __launch_bounds__(kRolesThreads + 128 * NSLOTS, 1) mlp_tc_kernel
       const uint32_t idesc = umma_idesc_16(128, 128, F16);
       uint32_t stage = 0, phase = 0;
       uint32_t pa[2] = {0u, 0u};
+      long long t_wa = 0, t_ww = 0, t0m = NB2_CLK();
       auto release = [&](uint32_t bar) {
         if (cl_size == 1) umma_commit(bar); else umma_commit_mcast(bar, cl_mask);
       };
@@ -266,15 +435,19 @@ __global__ void __launch_bounds__(kRolesThreads + 128 * NSLOTS, 1) mlp_tc_kernel
           const TcLayer& L = net.layer[l];
           if (LOCKSTEP) {
             // both tiles' operands are ready -> every weight tile is used twice
+            { const long long c0 = NB2_CLK();
             for (int s = 0; s < NSLOTS; ++s) {
               mbar_wait(smem_u32(&misc->a_ready[s]), pa[s]);
               pa[s] ^= 1u;
             }
+            t_wa += NB2_CLK() - c0; }
             tc_fence_after();
             for (int n = 0; n < L.nc; ++n) {
               for (int k = 0; k < L.kc; ++k) {
                 const int ks0 = L.ks0[k];
+                { const long long c0 = NB2_CLK();
                 mbar_wait(smem_u32(&misc->w_full[stage]), phase);
+                t_ww += NB2_CLK() - c0; }
                 tc_fence_after();
                 const uint32_t w_hi = ring_base + stage * kTileBytes;
                 for (int s = 0; s < NSLOTS; ++s) {
@@ -292,7 +465,9 @@ __global__ void __launch_bounds__(kRolesThreads + 128 * NSLOTS, 1) mlp_tc_kernel
             continue;
           }
           for (int s = 0; s < NSLOTS; ++s) {
+            { const long long c0 = NB2_CLK();
             mbar_wait(smem_u32(&misc->a_ready[s]), pa[s]);
+            t_wa += NB2_CLK() - c0; }
             pa[s] ^= 1u;
             tc_fence_after();
             const uint32_t slot_base = act_base + s * LT::kSlotBytes;
@@ -304,7 +479,9 @@ __global__ void __launch_bounds__(kRolesThreads + 128 * NSLOTS, 1) mlp_tc_kernel
                 const uint32_t a_hi = slot_base + (uint32_t)L.a_src[k] * kTileBytes;
                 const uint32_t a_lo = a_hi + kChunksPerSlot * kTileBytes;
                 const int ks0 = L.ks0[k];
+                { const long long c0 = NB2_CLK();
                 mbar_wait(smem_u32(&misc->w_full[stage]), phase);
+                t_ww += NB2_CLK() - c0; }
                 tc_fence_after();
                 const uint32_t w_hi = ring_base + stage * kTileBytes;
                 for (int ks = ks0; ks < 4; ++ks)
@@ -332,144 +509,10 @@ __global__ void __launch_bounds__(kRolesThreads + 128 * NSLOTS, 1) mlp_tc_kernel
           }
         }
       }
+      if (p.prof) { p.prof[blockIdx.x * 16 + 3] = t_wa; p.prof[blockIdx.x * 16 + 4] = t_ww; p.prof[blockIdx.x * 16 + 5] = clock64() - t0m; }
     }
   } else if (warp >= 4) {
-    // =========================== slot group: producer + epilogue ====================================
-    const int s = (warp - 4) >> 2;
-    const int wq = warp & 3;            // TMEM lane quadrant this warp may access
-    const int row = wq * 32 + lane;     // row of the tile == TMEM lane
-    const uint32_t slot_base = act_base + s * LT::kSlotBytes;
-    const uint32_t lo_off = kChunksPerSlot * kTileBytes;
-    const uint32_t e_hi = slot_base + kChunkE * kTileBytes, e_lo = e_hi + lo_off;
-    const uint32_t acc = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(s * 256);
-    const uint32_t a_ready = smem_u32(&misc->a_ready[s]);
-    const uint32_t acc_full = smem_u32(&misc->acc_full[s]);
-    float* scratch = &misc->scratch[s][0][0];
-    uint32_t pacc = 0;
-
-    for (int64_t it = 0; it < n_iters; ++it) {
-      const int64_t tile = (it * gridDim.x + blockIdx.x) * NSLOTS + s;   // may lie past n_tiles: rows invalid
-      const int64_t grow = tile * kTileRows + row;
-      const RowIn in = load_row(p.io, grow);
-      write_enc_row<SPLIT, F16, kEncCols, kMaxPosLevels>(e_hi, e_lo, row, in.p, p.pos_levels, in.valid);
-      fence_proxy_async_smem();
-      tc_fence_before();
-      mbar_arrive(a_ready);
-
-      float sigma = 0.f;
-      for (int l = 0; l < net.n_layers; ++l) {
-        const int epi = net.layer[l].epi;
-        mbar_wait(acc_full, pacc);
-        pacc ^= 1u;
-        __syncwarp();
-        tc_fence_after();
-
-        if (epi == EPI_RGB) {
-          // ---- rgb_layer: t = relu(acc) (128 wide, bias folded), rgb = sigmoid(W1 t + b1) --------
-          float c0 = 0.f, c1 = 0.f, c2 = 0.f;
-#pragma unroll 1
-          for (int cb = 0; cb < kRgbHidden / 32; ++cb) {
-            uint32_t r[32];
-            tmem_ld32(acc + cb * 32, r);
-            if (SPLIT) {
-              uint32_t c[32];
-              tmem_ld32(acc + 256 + cb * 32, c);
-              tmem_ld_wait();
-#pragma unroll
-              for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(c[j]));
-            } else {
-              tmem_ld_wait();
-            }
-#pragma unroll
-            for (int g = 0; g < 8; ++g) {
-              const int col = cb * 32 + g * 4;
-              const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.head + kHeadRgbW + col));
-              const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.head + kHeadRgbW + 128 + col));
-              const float4 w2 = __ldg(reinterpret_cast<const float4*>(p.head + kHeadRgbW + 256 + col));
-              const float t0 = fmaxf(__uint_as_float(r[g * 4 + 0]), 0.f), t1 = fmaxf(__uint_as_float(r[g * 4 + 1]), 0.f);
-              const float t2 = fmaxf(__uint_as_float(r[g * 4 + 2]), 0.f), t3 = fmaxf(__uint_as_float(r[g * 4 + 3]), 0.f);
-              c0 = fmaf(t0, w0.x, c0); c0 = fmaf(t1, w0.y, c0); c0 = fmaf(t2, w0.z, c0); c0 = fmaf(t3, w0.w, c0);
-              c1 = fmaf(t0, w1.x, c1); c1 = fmaf(t1, w1.y, c1); c1 = fmaf(t2, w1.z, c1); c1 = fmaf(t3, w1.w, c1);
-              c2 = fmaf(t0, w2.x, c2); c2 = fmaf(t1, w2.y, c2); c2 = fmaf(t2, w2.z, c2); c2 = fmaf(t3, w2.w, c2);
-            }
-          }
-          c0 = 1.f / (1.f + expf(-(c0 + __ldg(p.head + kHeadRgbB + 0))));
-          c1 = 1.f / (1.f + expf(-(c1 + __ldg(p.head + kHeadRgbB + 1))));
-          c2 = 1.f / (1.f + expf(-(c2 + __ldg(p.head + kHeadRgbB + 2))));
-          if (p.io.out_mode == 1) {
-            if (in.valid) reinterpret_cast<float4*>(p.io.out)[grow] = make_float4(c0, c1, c2, sigma);
-          } else {
-            // ---- alpha compositing over the rows of each ray (nerf_base.py:79-113) -------------
-            const int P = p.io.P;                 // 32, 64 or 128: rays cover whole warps
-            const int wpr = P >> 5;               // warps per ray
-            const int wseg = wq % wpr;            // this warp's position inside its ray
-            const float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(in.d[0], in.d[0]), __fmul_rn(in.d[1], in.d[1])),
-                                              __fmul_rn(in.d[2], in.d[2])));
-            const float depth = __fmul_rn(in.z, nrm);
-            float next = __shfl_down_sync(0xffffffffu, depth, 1);
-            if (lane == 0) scratch[wq * 8 + 0] = depth;
-            named_bar_sync(1 + s, 128);
-            if (lane == 31 && wq < 3) next = scratch[(wq + 1) * 8 + 0];
-            const bool last = (in.s == P - 1);
-            const float delta = last ? 1e10f : __fsub_rn(next, depth);
-            const float m = in.valid ? expf(-fmaxf(sigma, 0.f) * delta) : 1.f;
-            const float alpha = 1.f - m;
-            const float inc = warp_scan_mul(m + 1e-10f, lane);
-            float exc = __shfl_up_sync(0xffffffffu, inc, 1);
-            if (lane == 0) exc = 1.f;
-            if (lane == 31) scratch[wq * 8 + 1] = inc;
-            named_bar_sync(1 + s, 128);
-            float carry = 1.f;
-            for (int w = wq - wseg; w < wq; ++w) carry *= scratch[w * 8 + 1];
-            const float wgt = in.valid ? alpha * (carry * exc) : 0.f;
-            float sr = warp_sum(wgt * c0), sg = warp_sum(wgt * c1), sb = warp_sum(wgt * c2);
-            float sa = warp_sum(wgt), sd = warp_sum(wgt * depth);
-            if (lane == 0) {
-              scratch[wq * 8 + 2] = sr; scratch[wq * 8 + 3] = sg; scratch[wq * 8 + 4] = sb;
-              scratch[wq * 8 + 5] = sa; scratch[wq * 8 + 6] = sd;
-            }
-            named_bar_sync(1 + s, 128);
-            if (lane == 0 && wseg == 0 && in.valid) {
-              for (int w = wq + 1; w < wq + wpr; ++w) {
-                sr += scratch[w * 8 + 2]; sg += scratch[w * 8 + 3]; sb += scratch[w * 8 + 4];
-                sa += scratch[w * 8 + 5]; sd += scratch[w * 8 + 6];
-              }
-              if (p.io.flags & NB2_WHITE_BKG) {
-                const float bg = 1.f - sa;
-                sr += bg; sg += bg; sb += bg;
-              }
-              p.io.rgb_out[in.ray * 3 + 0] = sr;
-              p.io.rgb_out[in.ray * 3 + 1] = sg;
-              p.io.rgb_out[in.ray * 3 + 2] = sb;
-              if (p.io.depth_out) p.io.depth_out[in.ray] = (sd - p.io.near_t) / (p.io.far_t - p.io.near_t);
-              if (p.io.acc_out) p.io.acc_out[in.ray] = sa;
-            }
-            named_bar_sync(1 + s, 128);  // scratch is reused by the next tile
-          }
-        } else if (epi == EPI_RELU) {
-          epilogue_hidden<EPI_RELU, SPLIT, F16>(acc, slot_base, lo_off, row, p.head);
-        } else if (epi == EPI_LINEAR) {
-          epilogue_hidden<EPI_LINEAR, SPLIT, F16>(acc, slot_base, lo_off, row, p.head);
-        } else if (epi == EPI_RELU_SIGMA) {
-          sigma = epilogue_hidden<EPI_RELU_SIGMA, SPLIT, F16>(acc, slot_base, lo_off, row, p.head) + __ldg(p.head + kHeadSigmaB);
-          if (p.has_dir) {
-            // the encoded position is dead after the skip layer: re-use its tile for the direction
-            float rot[3] = {0.f, 0.f, 0.f};
-            if (in.valid) normalize_dir(in.d, rot);
-            write_enc_row<SPLIT, F16, kDirCols, kMaxDirLevels>(e_hi, e_lo, row, rot, p.dir_levels, in.valid);
-          }
-        } else {  // EPI_SIGMA_OUT
-          sigma = epilogue_hidden<EPI_SIGMA_OUT, SPLIT, F16>(acc, slot_base, lo_off, row, p.head) + __ldg(p.head + kHeadSigmaB);
-          if (in.valid) p.io.out[grow] = sigma;
-        }
-        if (l + 1 < net.n_layers) {
-          fence_proxy_async_smem();
-          tc_fence_before();
-          mbar_arrive(a_ready);
-        }
-      }
-      tc_fence_before();  // accumulator reads of the last layer precede the next tile's a_ready arrive
-    }
+    slot_group_run<NSLOTS, SPLIT, F16, false>(p, misc, act_base, tmem_base, n_iters, warp, lane, 0u);
   }
 
   // ---- teardown -----------------------------------------------------------------------------------
@@ -479,6 +522,168 @@ __global__ void __launch_bounds__(kRolesThreads + 128 * NSLOTS, 1) mlp_tc_kernel
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ======================================================================================================
+// CTA-pair kernel (cta_group::2).  Two CTAs of a cluster run ONE M=256 x N=256 x K=16 tcgen05.mma per k-step:
+// each CTA contributes its own 128 activation rows (A, from its shared memory) and HALF of the weight tile (B rows
+// [128 r, 128 r + 128) of the N=256 output columns), and receives its 128 rows of the fp32 accumulator in its own TMEM.
+// Versus the single-CTA kernel this halves (a) the MMA instructions issued per FLOP (the issuing thread is the scarce
+// resource: ~100 cycles of dependent issue latency per instruction), (b) the weight bytes each SM pulls from L2 and
+// writes to shared memory, so the 4 x 16 KB ring now covers 4 full K-chunks.
+//   leader CTA (rank 0): warp 1 issues all MMAs; waits for both CTAs' operands (a_ready counts 2 x 128 arrivals per slot)
+//                        and for both halves of each weight tile (own w_full + w_peer, relayed by the peer's warp 1);
+//   both CTAs          : warp 0 streams this CTA's half tiles; slot groups as in the single-CTA kernel; completion
+//                        (tcgen05.commit .multicast::cluster) is signalled into both CTAs.
+// Two-slot (single pass) mode runs the slots in lockstep: every weight half-tile feeds 2 x 4 MMAs = 1024 tensor cycles.
+// ======================================================================================================
+template <int NSLOTS, bool SPLIT, bool F16>
+__global__ void __launch_bounds__(kRolesThreads + 128 * NSLOTS, 1) mlp_tc2_kernel(const __grid_constant__ TcParams p) {
+  using LT = TcLayout<NSLOTS, SPLIT>;
+  extern __shared__ unsigned char smem_dyn[];
+  const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+  unsigned char* smem_al = smem_dyn + (smem_base - smem_u32(smem_dyn));
+  const uint32_t act_base = smem_base;
+  const uint32_t ring_base = smem_base + LT::kActBytes;
+  TcMisc* misc = reinterpret_cast<TcMisc*>(smem_al + LT::kActBytes + LT::kRingBytes);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const TcNet& net = p.net;
+  const int64_t tiles_per_iter = (int64_t)gridDim.x * NSLOTS;
+  const int64_t n_iters = (p.n_tiles + tiles_per_iter - 1) / tiles_per_iter;
+  const uint32_t rank = cluster_ctarank();
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(smem_u32(&misc->w_full[i]), 1);
+      mbar_init(smem_u32(&misc->w_peer[i]), 1);
+      mbar_init(smem_u32(&misc->w_empty[i]), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&misc->a_ready[s]), 256);   // 128 threads of each CTA of the pair
+      mbar_init(smem_u32(&misc->acc_full[s]), 1);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 2) {
+    tmem_alloc2(smem_u32(&misc->tmem_base), 512);
+    tmem_relinquish2();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = misc->tmem_base;
+
+  if (warp == 0) {
+    // =========================== weight streamer: this CTA's half of every tile =====================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int64_t it = 0; it < n_iters; ++it) {
+        for (int l = 0; l < net.n_layers; ++l) {
+          const TcLayer& L = net.layer[l];
+          // nc == 2: this CTA owns N-chunk `rank` (16 KB per K-chunk); nc == 1: rows [64 rank, 64 rank + 64) (8 KB)
+          const int c_first = L.chunk0 + (L.nc == 2 ? (int)rank * L.kc : 0);
+          const uint32_t bytes = L.nc == 2 ? kTileBytes : kTileBytes / 2;
+          const size_t sub = L.nc == 2 ? 0 : (size_t)rank * (kTileBytes / 4);   // in 16-bit elements
+          for (int k = 0; k < L.kc; ++k) {
+#pragma unroll
+            for (int part = 0; part < (SPLIT ? 2 : 1); ++part) {
+              mbar_wait(smem_u32(&misc->w_empty[stage]), phase ^ 1u);
+              const uint32_t full = smem_u32(&misc->w_full[stage]);
+              mbar_arrive_expect_tx(full, bytes);
+              bulk_g2s(ring_base + stage * kTileBytes,
+                       p.wchunks + ((size_t)(c_first + k) * 4 + (F16 ? 2 : 0) + part) * (kTileBytes / 2) + sub, bytes, full);
+              if (++stage == kStages) { stage = 0; phase ^= 1u; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank != 0) {
+      // =========================== peer: relay "my half has landed" to the leader =====================
+      uint32_t stage = 0, phase = 0;
+      for (int64_t it = 0; it < n_iters; ++it)
+        for (int l = 0; l < net.n_layers; ++l) {
+          const int n_entries = net.layer[l].kc * (SPLIT ? 2 : 1);
+          for (int e = 0; e < n_entries; ++e) {
+            mbar_wait(smem_u32(&misc->w_full[stage]), phase);
+            mbar_arrive_remote(smem_u32(&misc->w_peer[stage]), 0);
+            if (++stage == kStages) { stage = 0; phase ^= 1u; }
+          }
+        }
+    } else if (lane == 0) {
+      // =========================== leader: MMA issuer for the pair ====================================
+      uint32_t stage = 0, phase = 0;
+      uint32_t pa[2] = {0u, 0u};
+      long long t_wa = 0, t_ww = 0, t0m = NB2_CLK();
+      const uint32_t ring_lo = umma_desc_lo(ring_base);
+      for (int64_t it = 0; it < n_iters; ++it) {
+        for (int l = 0; l < net.n_layers; ++l) {
+          const TcLayer& L = net.layer[l];
+          const uint32_t idesc = umma_idesc_16(256, L.nc * 128, F16);
+          { const long long c0 = NB2_CLK();
+          for (int s = 0; s < NSLOTS; ++s) {
+            mbar_wait_cluster(smem_u32(&misc->a_ready[s]), pa[s]);
+            pa[s] ^= 1u;
+          }
+          t_wa += NB2_CLK() - c0; }
+          tc_fence_after();
+          for (int k = 0; k < L.kc; ++k) {
+            const int ks0 = L.ks0[k];
+            const uint32_t a_lo0 = umma_desc_lo(act_base + (uint32_t)L.a_src[k] * kTileBytes);   // slot 0, hi part
+            { const long long c0 = NB2_CLK();
+            mbar_wait(smem_u32(&misc->w_full[stage]), phase);
+            mbar_wait_cluster(smem_u32(&misc->w_peer[stage]), phase);
+            t_ww += NB2_CLK() - c0; }
+            tc_fence_after();
+            const uint32_t w_lo0 = ring_lo + stage * (kTileBytes >> 4);
+#pragma unroll
+            for (int s = 0; s < NSLOTS; ++s) {
+              const uint32_t a_s = a_lo0 + s * (LT::kSlotBytes >> 4);
+              const uint32_t d_main = tmem_base + (uint32_t)(s * 256);
+              for (int ks = ks0; ks < 4; ++ks)
+                umma2_bf16_ss(d_main, umma_desc_from_lo(a_s + 2 * ks), umma_desc_from_lo(w_lo0 + 2 * ks), idesc,
+                              (uint32_t)((k | ks) != 0));
+              if (SPLIT) {
+                const uint32_t a_l = a_s + (kChunksPerSlot * kTileBytes >> 4);
+                for (int ks = ks0; ks < 4; ++ks)
+                  umma2_bf16_ss(d_main + 256, umma_desc_from_lo(a_l + 2 * ks), umma_desc_from_lo(w_lo0 + 2 * ks), idesc,
+                                (uint32_t)((k | ks) != 0));
+              }
+            }
+            umma2_commit_mcast(smem_u32(&misc->w_empty[stage]), 3);
+            if (++stage == kStages) { stage = 0; phase ^= 1u; }
+            if (SPLIT) {
+              { const long long c0 = NB2_CLK();
+              mbar_wait(smem_u32(&misc->w_full[stage]), phase);
+              mbar_wait_cluster(smem_u32(&misc->w_peer[stage]), phase);
+              t_ww += NB2_CLK() - c0; }
+              tc_fence_after();
+              const uint32_t wl = ring_lo + stage * (kTileBytes >> 4);
+              for (int ks = ks0; ks < 4; ++ks)
+                umma2_bf16_ss(tmem_base + 256, umma_desc_from_lo(a_lo0 + 2 * ks), umma_desc_from_lo(wl + 2 * ks), idesc, 1u);
+              umma2_commit_mcast(smem_u32(&misc->w_empty[stage]), 3);
+              if (++stage == kStages) { stage = 0; phase ^= 1u; }
+            }
+          }
+          for (int s = 0; s < NSLOTS; ++s) umma2_commit_mcast(smem_u32(&misc->acc_full[s]), 3);
+        }
+      }
+      if (p.prof) { p.prof[blockIdx.x * 16 + 3] = t_wa; p.prof[blockIdx.x * 16 + 4] = t_ww; p.prof[blockIdx.x * 16 + 5] = clock64() - t0m; }
+    }
+  } else if (warp >= 4) {
+    slot_group_run<NSLOTS, SPLIT, F16, true>(p, misc, act_base, tmem_base, n_iters, warp, lane, rank);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, 512);
   }
 }
 
@@ -533,6 +738,43 @@ static int launch_tc_impl(nb2_handle* h, TcParams& prm, cudaStream_t st) {
   return NB2_OK;
 }
 
+template <int NSLOTS, bool SPLIT, bool F16>
+static int launch_tc2_impl(nb2_handle* h, TcParams& prm, cudaStream_t st) {
+  using LT = TcLayout<NSLOTS, SPLIT>;
+  auto kern = mlp_tc2_kernel<NSLOTS, SPLIT, F16>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    NB2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, LT::kTotal));
+    attr_set = true;
+  }
+  int64_t ctas = (prm.n_tiles + NSLOTS - 1) / NSLOTS;
+  ctas = (ctas + 1) / 2 * 2;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.blockDim = dim3(kRolesThreads + 128 * NSLOTS);
+  cfg.dynamicSmemBytes = LT::kTotal;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  static int max_clusters = 0;
+  if (!max_clusters) {
+    cfg.gridDim = dim3(h->sm_count / 2 * 2);
+    int n = 0;
+    NB2_CUDA(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
+    max_clusters = n > 0 ? n : 1;
+  }
+  cfg.gridDim = dim3((unsigned)std::min<int64_t>(ctas, (int64_t)max_clusters * 2));
+  prm.cluster = 2;
+  NB2_CUDA(cudaLaunchKernelEx(&cfg, kern, prm));
+  h->launches++;
+  return NB2_OK;
+}
+
 int launch_mlp_tc(nb2_handle* h, int net_id, int precision, const MlpIo& io, cudaStream_t st) {
   PackedNet& pn = h->net[net_id];
   if (!pn.packed) {
@@ -554,8 +796,15 @@ int launch_mlp_tc(nb2_handle* h, int net_id, int precision, const MlpIo& io, cud
   prm.dir_levels = pn.dir_levels;
   prm.has_dir = (net_id == NB2_NET_NERF);
   prm.n_tiles = (io.n_rows + kTileRows - 1) / kTileRows;
+  prm.prof = h->tc_prof;
   const bool split = (precision == NB2_PREC_BF16X3 || precision == NB2_PREC_FP16X3);
-  int cluster = env_int("NB2_TC_CLUSTER", split ? 2 : 2);
+  if (env_int("NB2_TC_PAIR", 1) != 0) {
+    if (precision == NB2_PREC_BF16) return launch_tc2_impl<2, false, false>(h, prm, st);
+    if (precision == NB2_PREC_FP16) return launch_tc2_impl<2, false, true>(h, prm, st);
+    if (precision == NB2_PREC_BF16X3) return launch_tc2_impl<1, true, false>(h, prm, st);
+    if (precision == NB2_PREC_FP16X3) return launch_tc2_impl<1, true, true>(h, prm, st);
+  }
+  int cluster = env_int("NB2_TC_CLUSTER", 1);
   if (cluster != 1 && cluster != 2 && cluster != 4) {
     set_error("NB2_TC_CLUSTER must be 1, 2 or 4 (got %d)", cluster);
     return NB2_ERR_INVALID;
@@ -635,6 +884,166 @@ umma_selftest_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* _
     tc_fence_after();
     tmem_dealloc(tmem, 128);
   }
+}
+
+// ======================================================================================================
+// 2-CTA self-test + MMA micro-benchmark.  mode 0: cta_group::1 M128 N128; mode 1: cta_group::1 M128 N256;
+// mode 2: cta_group::2 M256 N256 (cluster of 2).  A: (256 x 64) bf16 row-major, rows 128r.. belong to CTA r.
+// B: (256 x 64) bf16 row-major (n-major).  D_out: (256 x 256) fp32.  cycles_out[cta] = cycles per MMA instruction
+// over `iters` back-to-back K=64 sweeps (4 MMAs each).
+// ======================================================================================================
+// (a kernel that contains cta_group::2 instructions can only be launched as a cluster of 2: one instantiation per mode)
+// `flags` (stressors, cta_group::1 modes): 1 = alternate between two accumulators every 4 MMAs; 2 = walk A over 8 and B over
+// 4 distinct tiles; 4 = a second warp streams 16 KB bulk copies into a 4-stage ring concurrently; 8 = two warps issue
+// 16-byte shared stores concurrently; 16 = commit + wait after every 4 MMAs (per-chunk barrier round trip).
+template <int mode>
+__global__ void __launch_bounds__(256, 1)
+umma_bench_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __restrict__ B, float* __restrict__ D,
+                  long long* __restrict__ cycles_out, int iters, int flags, const __nv_bfloat16* __restrict__ gsrc) {
+  extern __shared__ unsigned char smem_dyn[];
+  const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+  unsigned char* al = smem_dyn + (base - smem_u32(smem_dyn));
+  // layout: A tiles 8 x 16 KB | B tiles 4 x 16 KB (mode 1/2 use 32 KB of it) | 1 KB misc
+  const uint32_t a_tile = base, b_tile = base + 8 * kTileBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(al + 12 * kTileBytes);   // [0] done, [1..4] ring full, [5] chunk
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(al + 12 * kTileBytes + 64);
+  volatile int* stop = reinterpret_cast<volatile int*>(al + 12 * kTileBytes + 72);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, row = threadIdx.x & 127;
+  constexpr bool pair = (mode == 2);
+  const uint32_t rank = pair ? cluster_ctarank() : 0u;
+  const int b_rows = (mode == 0) ? 128 : (pair ? 128 : 256);                // B rows held by THIS CTA
+  const int N = (mode == 0) ? 128 : 256;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 6; ++i) mbar_init(smem_u32(&bars[i]), 1);
+    *stop = 0;
+    mbar_fence_init();
+  }
+  if (warp == 0) {
+    if (pair) { tmem_alloc2(smem_u32(tptr), 512); tmem_relinquish2(); }
+    else      { tmem_alloc(smem_u32(tptr), 512); tmem_relinquish(); }
+  }
+  const int a_row0 = pair ? 128 * (int)rank : 0;
+  if (threadIdx.x < 128) {
+    for (int t = 0; t < 8; ++t)
+      for (int g = 0; g < 8; ++g) {
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = __bfloat162float(A[(a_row0 + row) * 64 + g * 8 + i]);
+        store_a8<false, false>(a_tile + t * kTileBytes, 0, row, g * 8, v);
+      }
+    const int b_row0 = pair ? 128 * (int)rank : 0;
+    for (int t = 0; t < (mode == 0 ? 4 : 1); ++t)
+      for (int r = row; r < b_rows; r += 128)
+        for (int g = 0; g < 8; ++g) {
+          float v[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = __bfloat162float(B[(b_row0 + r) * 64 + g * 8 + i]);
+          store_a8<false, false>(b_tile + t * kTileBytes, 0, r, g * 8, v);
+        }
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  if (pair) cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem = *tptr;
+
+  if (threadIdx.x == 0 && rank == 0) {
+    const uint32_t idesc = umma_idesc_16(pair ? 256 : 128, N, false);
+    uint32_t ph = 0;
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+      const uint32_t d = tmem + (((flags & 1) && (it & 1)) ? 256u : 0u);
+      const uint32_t at = a_tile + ((flags & 2) ? (uint32_t)(it & 7) * kTileBytes : 0u);
+      const uint32_t bt = b_tile + (((flags & 2) && mode == 0) ? (uint32_t)(it & 3) * kTileBytes : 0u);
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const uint32_t acc = (uint32_t)((it > ((flags & 1) ? 1 : 0)) || ks != 0);
+        if (pair) umma2_bf16_ss(d, umma_smem_desc(at + ks * 32), umma_smem_desc(bt + ks * 32), idesc, acc);
+        else      umma_bf16_ss(d, umma_smem_desc(at + ks * 32), umma_smem_desc(bt + ks * 32), idesc, acc);
+      }
+      if (flags & 16) {
+        umma_commit(smem_u32(&bars[5]));
+        mbar_wait(smem_u32(&bars[5]), ph);
+        ph ^= 1u;
+        tc_fence_after();
+      }
+    }
+    if (pair) umma2_commit_mcast(smem_u32(&bars[0]), 3); else umma_commit(smem_u32(&bars[0]));
+    mbar_wait(smem_u32(&bars[0]), 0);
+    cycles_out[blockIdx.x] = (clock64() - t0) / (4ll * iters);
+    *stop = 1;
+  } else if (warp == 4 && lane == 0 && (flags & 4) && !pair) {
+    // concurrent weight-style traffic: 16 KB bulk copies into a 4-stage ring (placed after the B tiles is not possible in
+    // this layout, so the ring aliases A tiles 4..7, unused unless flag 2)
+    uint32_t st = 0, ph = 0, n = 0;
+    while (!*stop && n < 100000) {
+      const uint32_t full = smem_u32(&bars[1 + st]);
+      mbar_arrive_expect_tx(full, kTileBytes);
+      bulk_g2s(a_tile + (4 + st) * kTileBytes, gsrc + (size_t)(n & 63) * (kTileBytes / 2), kTileBytes, full);
+      if (st == 3) {   // wait for the whole batch of 4 before re-arming (keeps <= 4 in flight)
+        for (int i = 0; i < 4; ++i) mbar_wait(smem_u32(&bars[1 + i]), ph);
+        ph ^= 1u;
+      }
+      st = (st + 1) & 3;
+      ++n;
+    }
+    if (st != 0) for (uint32_t i = 0; i < st; ++i) mbar_wait(smem_u32(&bars[1 + i]), ph);
+  } else if ((warp == 5 || warp == 6) && (flags & 8) && !pair) {
+    // concurrent epilogue-style traffic: 16-byte shared stores, conflict-free pattern, into A tiles 4..7 region end
+    uint32_t n = 0;
+    const uint32_t dst = a_tile + 7 * kTileBytes + (uint32_t)(warp - 5) * 8192u;
+    while (!*stop && n < 4000000) {
+      st_shared_v4(dst + ((n & 15) * 512u) + lane * 16u, n, n, n, n);
+      ++n;
+    }
+  }
+  mbar_wait(smem_u32(&bars[0]), 0);
+  __syncwarp();
+  tc_fence_after();
+  if (blockIdx.x < (pair ? 2 : 1) && threadIdx.x < 128) {
+    const float scale = 1.f / (float)(((flags & 1) ? (iters + 1) / 2 : iters));
+    for (int cb = 0; cb < N / 32; ++cb) {
+      uint32_t r[32];
+      tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + cb * 32, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) D[(size_t)(a_row0 + row) * 256 + cb * 32 + j] = __uint_as_float(r[j]) * scale;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (pair) cluster_sync_all();
+  if (warp == 0) {
+    tc_fence_after();
+    if (pair) tmem_dealloc2(tmem, 512); else tmem_dealloc(tmem, 512);
+  }
+}
+
+int umma_bench(nb2_handle* h, const void* A, const void* B, float* D, long long* cycles, int mode, int iters, int flags,
+               const void* gsrc, cudaStream_t st) {
+  const int smem = 12 * kTileBytes + 1024 + 1024;
+  void (*kern)(const __nv_bfloat16*, const __nv_bfloat16*, float*, long long*, int, int, const __nv_bfloat16*) =
+      mode == 0 ? umma_bench_kernel<0> : (mode == 1 ? umma_bench_kernel<1> : umma_bench_kernel<2>);
+  NB2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.blockDim = dim3(256);
+  cfg.gridDim = dim3(h->sm_count / 2 * 2);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (mode == 2) ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  NB2_CUDA(cudaLaunchKernelEx(&cfg, kern, (const __nv_bfloat16*)A, (const __nv_bfloat16*)B, D, cycles, iters, flags,
+                              (const __nv_bfloat16*)gsrc));
+  h->launches++;
+  return NB2_OK;
 }
 
 // Swizzle a row-major 128x64 bf16 matrix into the tile image (used by the self-test and by tests).

@@ -70,6 +70,56 @@ def stage_time(precision, H=400):
           f"ms={dt * 1e3:.2f} checksum={float(img.double().sum()):.6f} nan={int(torch.isnan(img).sum())}")
 
 
+def stage_ummabench():
+    lib, h = _lib.load(), _lib.handle()
+    g = torch.Generator().manual_seed(1)
+    A = torch.randn(256, 64, generator=g).to(torch.bfloat16).to(DEV)
+    B = torch.randn(256, 64, generator=g).to(torch.bfloat16).to(DEV)
+    gsrc = torch.zeros(1 << 20, dtype=torch.uint8, device=DEV)
+    ref = (A.float() @ B.float().T).cpu()
+
+    def run(mode, iters, flags):
+        D = torch.zeros(256, 256, device=DEV)
+        cyc = torch.zeros(256, dtype=torch.int64, device=DEV)
+        _lib.check(lib.nb2_debug_umma_bench(h, _lib.ptr(A), _lib.ptr(B), _lib.ptr(D), _lib.ptr(cyc), mode, iters, flags, _lib.ptr(gsrc), _lib.stream_ptr()))
+        torch.cuda.synchronize()
+        mr, nr = ((128, 128), (128, 256), (256, 256))[mode]
+        err = float((D.cpu()[:mr, :nr] - ref[:mr, :nr]).abs().max())
+        c = cyc.cpu()[:148]
+        c = c[c > 0]
+        print(f"UMMABENCH mode={mode} iters={iters} flags={flags:2d}: max|D-ref|={err:.2e} cycles/MMA median={float(c.float().median()):.1f} min={int(c.min())} max={int(c.max())}")
+
+    for mode in (0, 1, 2):
+        run(mode, 1, 0)
+        run(mode, 400, 0)
+    for flags in (1, 2, 3, 4, 8, 12, 16, 6, 7, 15, 31):
+        run(0, 400, flags)
+    for flags in (1, 2, 16):
+        run(1, 400, flags)
+
+
+def stage_roles(precision, H=400):
+    """Per-role cycle accounting of the fine kernel (debug counters)."""
+    import ctypes
+    lib, h = _lib.load(), _lib.handle()
+    _lib.check(lib.nb2_debug_tc_profile(h, None, 0))      # enable
+    net = load(nerf_b200.MipNeRF(10, 4, 256), O.make_params("nerf", 2, "smooth"))
+    prop = load(nerf_b200.ProposalNetwork(10, 256), O.make_params("proposal", 1, "smooth"))
+    pose = nerf_b200.pose_spherical(30.0, -30.0, 4.0)[:3, :].to(DEV)
+    focal = nerf_b200.fov2Focal(0.6911112070083618, (H, H))[0]
+    for i in range(2):
+        nerf_b200.render_image(net, prop, pose, (H, H), focal, 2.0, 6.0, 128, white_bkg=True, precision=precision, seed=1)
+    buf = (ctypes.c_longlong * (148 * 16))()
+    _lib.check(lib.nb2_debug_tc_profile(h, buf, 148))
+    a = np.array(buf[:], dtype=np.int64).reshape(148, 16)
+    names = ["str_wait_empty", "str_total", "ring_entries", "mma_wait_A", "mma_wait_W", "mma_total", "g0_encode", "g0_wait_acc",
+             "g0_epi_hidden", "g0_epi_last", "g0_total", "iters", "layers"]
+    print(f"ROLES {precision} cluster={os.environ.get('NB2_TC_CLUSTER','dflt')} lockstep={os.environ.get('NB2_TC_LOCKSTEP','dflt')} (median over CTAs, cycles; last launch = fine kernel)")
+    med = np.median(a, axis=0)
+    for i, n in enumerate(names):
+        print(f"   {n:16s} {med[i]:14.0f}   per-iter {med[i] / max(med[11], 1):12.0f}")
+
+
 if __name__ == "__main__":
     stage = sys.argv[1]
     print("== stage", stage, sys.argv[2:], "on", torch.cuda.get_device_name(0))
@@ -77,6 +127,10 @@ if __name__ == "__main__":
         stage_selftest()
     elif stage == "mlp":
         stage_mlp(sys.argv[2], sys.argv[3], int(sys.argv[4]) if len(sys.argv) > 4 else 1000)
+    elif stage == "ummabench":
+        stage_ummabench()
+    elif stage == "roles":
+        stage_roles(sys.argv[2], int(sys.argv[3]) if len(sys.argv) > 3 else 400)
     elif stage == "time":
         stage_time(sys.argv[2], int(sys.argv[3]) if len(sys.argv) > 3 else 400)
     print("== done", stage)
