@@ -50,7 +50,17 @@ struct TcParams {
   int64_t n_tiles;
   long long* prof;   // optional (debug): 16 cycle counters per CTA, see nb2_debug_tc_profile
 };
+// Role cycle counters are compiled in only with -DNB2_TC_PROFILE=1 (make PROFILE=1): they cost ~12 registers.
+#ifndef NB2_TC_PROFILE
+#define NB2_TC_PROFILE 0
+#endif
+#if NB2_TC_PROFILE
 #define NB2_CLK() (p.prof ? clock64() : 0ll)
+#define NB2_PROF_ON (p.prof != nullptr)
+#else
+#define NB2_CLK() 0ll
+#define NB2_PROF_ON false
+#endif
 
 struct TcMisc {
   uint64_t w_full[kStages];
@@ -127,16 +137,54 @@ __device__ __forceinline__ void write_enc_row(uint32_t tile_hi, uint32_t tile_lo
   }
 }
 
-// ---- hidden-layer epilogue: TMEM accumulator -> act -> 16-bit A operand of the next layer (in place) ----
-// EPI: EPI_RELU / EPI_LINEAR / EPI_RELU_SIGMA / EPI_SIGMA_OUT.  Returns the density-head dot product
-// (without its bias) for the *_SIGMA kinds.  In SPLIT mode the cross terms live in a second accumulator
-// (columns +256) and are added here in fp32.
+// One 32-column block of the hidden epilogue: values (already summed with the correction accumulator in SPLIT mode)
+// -> activation -> 16-bit A operand rows (+ running density-head dot product).
 template <int EPI, bool SPLIT, bool F16>
-__device__ __forceinline__ float epilogue_hidden(uint32_t acc, uint32_t slot_base, uint32_t lo_off, int row,
-                                                 const float* __restrict__ head) {
+__device__ __forceinline__ void epilogue_block(const uint32_t (&r)[32], int cb, uint32_t slot_base, uint32_t lo_off, int row,
+                                               const float* __restrict__ head, float& sg) {
   constexpr bool kRelu = (EPI != EPI_LINEAR);
   constexpr bool kSigma = (EPI == EPI_RELU_SIGMA || EPI == EPI_SIGMA_OUT);
   constexpr bool kStore = (EPI != EPI_SIGMA_OUT);
+  const uint32_t h_hi = slot_base + (uint32_t)(cb >> 1) * kTileBytes;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const int col = cb * 32 + g * 8;
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]);
+    if (kRelu && (SPLIT || kSigma)) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+    }
+    if (kSigma) {
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(head + kHeadSigmaW + col));
+      const float4 w1 = __ldg(reinterpret_cast<const float4*>(head + kHeadSigmaW + col + 4));
+      sg = fmaf(v[0], w0.x, sg); sg = fmaf(v[1], w0.y, sg); sg = fmaf(v[2], w0.z, sg); sg = fmaf(v[3], w0.w, sg);
+      sg = fmaf(v[4], w1.x, sg); sg = fmaf(v[5], w1.y, sg); sg = fmaf(v[6], w1.z, sg); sg = fmaf(v[7], w1.w, sg);
+    }
+    if (kStore) {
+      if (SPLIT || kSigma || !kRelu) {
+        store_a8<SPLIT, F16>(h_hi, h_hi + lo_off, row, col & 63, v);
+      } else {
+        // single pass: relu fused into the fp32 -> 16-bit conversion
+        const uint32_t off = (uint32_t)row * 128u + (((((uint32_t)col & 63u) >> 3) ^ ((uint32_t)row & 7u)) << 4);
+        uint32_t h[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) h[i] = pack16x2_relu<F16>(v[2 * i], v[2 * i + 1]);
+        st_shared_v4(h_hi + off, h[0], h[1], h[2], h[3]);
+      }
+    }
+  }
+}
+
+// ---- hidden-layer epilogue: TMEM accumulator -> act -> 16-bit A operand of the next layer (in place) ----
+// EPI: EPI_RELU / EPI_LINEAR / EPI_RELU_SIGMA / EPI_SIGMA_OUT.  Returns the density-head dot product
+// (without its bias) for the *_SIGMA kinds.  In SPLIT mode the cross terms live in a second accumulator
+// (columns +256) and are added here in fp32.  (A software-pipelined variant that kept the next block's
+// tcgen05.ld in flight during the conversion measured 4-15 % SLOWER on B200 and was dropped.)
+template <int EPI, bool SPLIT, bool F16>
+__device__ __forceinline__ float epilogue_hidden(uint32_t acc, uint32_t slot_base, uint32_t lo_off, int row,
+                                                 const float* __restrict__ head) {
   float sg = 0.f;
 #pragma unroll 1
   for (int cb = 0; cb < kHidden / 32; ++cb) {
@@ -151,41 +199,11 @@ __device__ __forceinline__ float epilogue_hidden(uint32_t acc, uint32_t slot_bas
     } else {
       tmem_ld_wait();
     }
-    const uint32_t h_hi = slot_base + (uint32_t)(cb >> 1) * kTileBytes;
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      const int col = cb * 32 + g * 8;
-      float v[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]);
-      if (kRelu && (SPLIT || kSigma)) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
-      }
-      if (kSigma) {
-        const float4 w0 = __ldg(reinterpret_cast<const float4*>(head + kHeadSigmaW + col));
-        const float4 w1 = __ldg(reinterpret_cast<const float4*>(head + kHeadSigmaW + col + 4));
-        sg = fmaf(v[0], w0.x, sg); sg = fmaf(v[1], w0.y, sg); sg = fmaf(v[2], w0.z, sg); sg = fmaf(v[3], w0.w, sg);
-        sg = fmaf(v[4], w1.x, sg); sg = fmaf(v[5], w1.y, sg); sg = fmaf(v[6], w1.z, sg); sg = fmaf(v[7], w1.w, sg);
-      }
-      if (kStore) {
-        if (SPLIT || kSigma || !kRelu) {
-          store_a8<SPLIT, F16>(h_hi, h_hi + lo_off, row, col & 63, v);
-        } else {
-          // single pass: relu fused into the fp32 -> 16-bit conversion
-          const uint32_t off = (uint32_t)row * 128u + (((((uint32_t)col & 63u) >> 3) ^ ((uint32_t)row & 7u)) << 4);
-          uint32_t h[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) h[i] = pack16x2_relu<F16>(v[2 * i], v[2 * i + 1]);
-          st_shared_v4(h_hi + off, h[0], h[1], h[2], h[3]);
-        }
-      }
-    }
+    epilogue_block<EPI, SPLIT, F16>(r, cb, slot_base, lo_off, row, head, sg);
   }
   return sg;
 }
 
-// ---- the kernel ----------------------------------------------------------------------------------
 // ---- slot group: per-tile producer (sample -> encoding) and per-layer epilogue ------------------------------------
 // Shared by the single-CTA kernel and the CTA-pair kernel (PAIR: the operand-ready barrier lives in the pair's leader).
 template <int NSLOTS, bool SPLIT, bool F16, bool PAIR>
@@ -341,9 +359,9 @@ __device__ __forceinline__ void slot_group_run(const TcParams& p, TcMisc* misc, 
     }
     tc_fence_before();  // accumulator reads of the last layer precede the next tile's a_ready arrive
   }
-  if (p.prof && threadIdx.x == kRolesThreads) {
+  if (NB2_PROF_ON && threadIdx.x == kRolesThreads) {
     long long* o = p.prof + blockIdx.x * 16;
-    o[6] = t_pe; o[7] = t_wacc; o[8] = t_epi; o[9] = t_last; o[10] = clock64() - t0e; o[11] = n_iters; o[12] = net.n_layers;
+    o[6] = t_pe; o[7] = t_wacc; o[8] = t_epi; o[9] = t_last; o[10] = NB2_CLK() - t0e; o[11] = n_iters; o[12] = net.n_layers;
   }
 }
 
@@ -418,7 +436,7 @@ __global__ void __launch_bounds__(kRolesThreads + 128 * NSLOTS, 1) mlp_tc_kernel
           }
         }
       }
-      if (p.prof) { p.prof[blockIdx.x * 16 + 0] = t_empty; p.prof[blockIdx.x * 16 + 1] = clock64() - t0s; p.prof[blockIdx.x * 16 + 2] = q; }
+      if (NB2_PROF_ON) { p.prof[blockIdx.x * 16 + 0] = t_empty; p.prof[blockIdx.x * 16 + 1] = NB2_CLK() - t0s; p.prof[blockIdx.x * 16 + 2] = q; }
     }
   } else if (warp == 1) {
     // =========================== MMA issuer =======================================================
@@ -509,7 +527,7 @@ __global__ void __launch_bounds__(kRolesThreads + 128 * NSLOTS, 1) mlp_tc_kernel
           }
         }
       }
-      if (p.prof) { p.prof[blockIdx.x * 16 + 3] = t_wa; p.prof[blockIdx.x * 16 + 4] = t_ww; p.prof[blockIdx.x * 16 + 5] = clock64() - t0m; }
+      if (NB2_PROF_ON) { p.prof[blockIdx.x * 16 + 3] = t_wa; p.prof[blockIdx.x * 16 + 4] = t_ww; p.prof[blockIdx.x * 16 + 5] = NB2_CLK() - t0m; }
     }
   } else if (warp >= 4) {
     slot_group_run<NSLOTS, SPLIT, F16, false>(p, misc, act_base, tmem_base, n_iters, warp, lane, 0u);
@@ -538,8 +556,9 @@ __global__ void __launch_bounds__(kRolesThreads + 128 * NSLOTS, 1) mlp_tc_kernel
 //                        (tcgen05.commit .multicast::cluster) is signalled into both CTAs.
 // Two-slot (single pass) mode runs the slots in lockstep: every weight half-tile feeds 2 x 4 MMAs = 1024 tensor cycles.
 // ======================================================================================================
-template <int NSLOTS, bool SPLIT, bool F16>
+template <int NSLOTS, bool SPLIT, bool F16, bool LOCKSTEP>
 __global__ void __launch_bounds__(kRolesThreads + 128 * NSLOTS, 1) mlp_tc2_kernel(const __grid_constant__ TcParams p) {
+  constexpr int kPasses = LOCKSTEP ? 1 : NSLOTS;   // how many times a layer's weight stream is consumed per iteration
   using LT = TcLayout<NSLOTS, SPLIT>;
   extern __shared__ unsigned char smem_dyn[];
   const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
@@ -587,6 +606,7 @@ __global__ void __launch_bounds__(kRolesThreads + 128 * NSLOTS, 1) mlp_tc2_kerne
           const int c_first = L.chunk0 + (L.nc == 2 ? (int)rank * L.kc : 0);
           const uint32_t bytes = L.nc == 2 ? kTileBytes : kTileBytes / 2;
           const size_t sub = L.nc == 2 ? 0 : (size_t)rank * (kTileBytes / 4);   // in 16-bit elements
+          for (int pass = 0; pass < kPasses; ++pass)
           for (int k = 0; k < L.kc; ++k) {
 #pragma unroll
             for (int part = 0; part < (SPLIT ? 2 : 1); ++part) {
@@ -607,7 +627,7 @@ __global__ void __launch_bounds__(kRolesThreads + 128 * NSLOTS, 1) mlp_tc2_kerne
       uint32_t stage = 0, phase = 0;
       for (int64_t it = 0; it < n_iters; ++it)
         for (int l = 0; l < net.n_layers; ++l) {
-          const int n_entries = net.layer[l].kc * (SPLIT ? 2 : 1);
+          const int n_entries = net.layer[l].kc * (SPLIT ? 2 : 1) * kPasses;
           for (int e = 0; e < n_entries; ++e) {
             mbar_wait(smem_u32(&misc->w_full[stage]), phase);
             mbar_arrive_remote(smem_u32(&misc->w_peer[stage]), 0);
@@ -624,55 +644,59 @@ __global__ void __launch_bounds__(kRolesThreads + 128 * NSLOTS, 1) mlp_tc2_kerne
         for (int l = 0; l < net.n_layers; ++l) {
           const TcLayer& L = net.layer[l];
           const uint32_t idesc = umma_idesc_16(256, L.nc * 128, F16);
-          { const long long c0 = NB2_CLK();
-          for (int s = 0; s < NSLOTS; ++s) {
-            mbar_wait_cluster(smem_u32(&misc->a_ready[s]), pa[s]);
-            pa[s] ^= 1u;
-          }
-          t_wa += NB2_CLK() - c0; }
-          tc_fence_after();
-          for (int k = 0; k < L.kc; ++k) {
-            const int ks0 = L.ks0[k];
-            const uint32_t a_lo0 = umma_desc_lo(act_base + (uint32_t)L.a_src[k] * kTileBytes);   // slot 0, hi part
+          for (int pass = 0; pass < kPasses; ++pass) {
+            // LOCKSTEP: one pass, both slots share every weight half-tile.  Otherwise one pass per slot (ping-pong):
+            // the other slot's epilogue runs while this slot's MMAs execute.
+            const int s_lo = LOCKSTEP ? 0 : pass, s_hi = LOCKSTEP ? NSLOTS : pass + 1;
             { const long long c0 = NB2_CLK();
-            mbar_wait(smem_u32(&misc->w_full[stage]), phase);
-            mbar_wait_cluster(smem_u32(&misc->w_peer[stage]), phase);
-            t_ww += NB2_CLK() - c0; }
-            tc_fence_after();
-            const uint32_t w_lo0 = ring_lo + stage * (kTileBytes >> 4);
-#pragma unroll
-            for (int s = 0; s < NSLOTS; ++s) {
-              const uint32_t a_s = a_lo0 + s * (LT::kSlotBytes >> 4);
-              const uint32_t d_main = tmem_base + (uint32_t)(s * 256);
-              for (int ks = ks0; ks < 4; ++ks)
-                umma2_bf16_ss(d_main, umma_desc_from_lo(a_s + 2 * ks), umma_desc_from_lo(w_lo0 + 2 * ks), idesc,
-                              (uint32_t)((k | ks) != 0));
-              if (SPLIT) {
-                const uint32_t a_l = a_s + (kChunksPerSlot * kTileBytes >> 4);
-                for (int ks = ks0; ks < 4; ++ks)
-                  umma2_bf16_ss(d_main + 256, umma_desc_from_lo(a_l + 2 * ks), umma_desc_from_lo(w_lo0 + 2 * ks), idesc,
-                                (uint32_t)((k | ks) != 0));
-              }
+            for (int s = s_lo; s < s_hi; ++s) {
+              mbar_wait_cluster(smem_u32(&misc->a_ready[s]), pa[s]);
+              pa[s] ^= 1u;
             }
-            umma2_commit_mcast(smem_u32(&misc->w_empty[stage]), 3);
-            if (++stage == kStages) { stage = 0; phase ^= 1u; }
-            if (SPLIT) {
+            t_wa += NB2_CLK() - c0; }
+            tc_fence_after();
+            for (int k = 0; k < L.kc; ++k) {
+              const int ks0 = L.ks0[k];
+              const uint32_t a_lo0 = umma_desc_lo(act_base + (uint32_t)L.a_src[k] * kTileBytes);   // slot 0, hi part
               { const long long c0 = NB2_CLK();
               mbar_wait(smem_u32(&misc->w_full[stage]), phase);
               mbar_wait_cluster(smem_u32(&misc->w_peer[stage]), phase);
               t_ww += NB2_CLK() - c0; }
               tc_fence_after();
-              const uint32_t wl = ring_lo + stage * (kTileBytes >> 4);
-              for (int ks = ks0; ks < 4; ++ks)
-                umma2_bf16_ss(tmem_base + 256, umma_desc_from_lo(a_lo0 + 2 * ks), umma_desc_from_lo(wl + 2 * ks), idesc, 1u);
+              const uint32_t w_lo0 = ring_lo + stage * (kTileBytes >> 4);
+              for (int s = s_lo; s < s_hi; ++s) {
+                const uint32_t a_s = a_lo0 + s * (LT::kSlotBytes >> 4);
+                const uint32_t d_main = tmem_base + (uint32_t)(s * 256);
+                for (int ks = ks0; ks < 4; ++ks)
+                  umma2_bf16_ss(d_main, umma_desc_from_lo(a_s + 2 * ks), umma_desc_from_lo(w_lo0 + 2 * ks), idesc,
+                                (uint32_t)((k | ks) != 0));
+                if (SPLIT) {
+                  const uint32_t a_l = a_s + (kChunksPerSlot * kTileBytes >> 4);
+                  for (int ks = ks0; ks < 4; ++ks)
+                    umma2_bf16_ss(d_main + 256, umma_desc_from_lo(a_l + 2 * ks), umma_desc_from_lo(w_lo0 + 2 * ks), idesc,
+                                  (uint32_t)((k | ks) != 0));
+                }
+              }
               umma2_commit_mcast(smem_u32(&misc->w_empty[stage]), 3);
               if (++stage == kStages) { stage = 0; phase ^= 1u; }
+              if (SPLIT) {
+                { const long long c0 = NB2_CLK();
+                mbar_wait(smem_u32(&misc->w_full[stage]), phase);
+                mbar_wait_cluster(smem_u32(&misc->w_peer[stage]), phase);
+                t_ww += NB2_CLK() - c0; }
+                tc_fence_after();
+                const uint32_t wl = ring_lo + stage * (kTileBytes >> 4);
+                for (int ks = ks0; ks < 4; ++ks)
+                  umma2_bf16_ss(tmem_base + 256, umma_desc_from_lo(a_lo0 + 2 * ks), umma_desc_from_lo(wl + 2 * ks), idesc, 1u);
+                umma2_commit_mcast(smem_u32(&misc->w_empty[stage]), 3);
+                if (++stage == kStages) { stage = 0; phase ^= 1u; }
+              }
             }
+            for (int s = s_lo; s < s_hi; ++s) umma2_commit_mcast(smem_u32(&misc->acc_full[s]), 3);
           }
-          for (int s = 0; s < NSLOTS; ++s) umma2_commit_mcast(smem_u32(&misc->acc_full[s]), 3);
         }
       }
-      if (p.prof) { p.prof[blockIdx.x * 16 + 3] = t_wa; p.prof[blockIdx.x * 16 + 4] = t_ww; p.prof[blockIdx.x * 16 + 5] = clock64() - t0m; }
+      if (NB2_PROF_ON) { p.prof[blockIdx.x * 16 + 3] = t_wa; p.prof[blockIdx.x * 16 + 4] = t_ww; p.prof[blockIdx.x * 16 + 5] = NB2_CLK() - t0m; }
     }
   } else if (warp >= 4) {
     slot_group_run<NSLOTS, SPLIT, F16, true>(p, misc, act_base, tmem_base, n_iters, warp, lane, rank);
@@ -738,10 +762,10 @@ static int launch_tc_impl(nb2_handle* h, TcParams& prm, cudaStream_t st) {
   return NB2_OK;
 }
 
-template <int NSLOTS, bool SPLIT, bool F16>
+template <int NSLOTS, bool SPLIT, bool F16, bool LOCKSTEP>
 static int launch_tc2_impl(nb2_handle* h, TcParams& prm, cudaStream_t st) {
   using LT = TcLayout<NSLOTS, SPLIT>;
-  auto kern = mlp_tc2_kernel<NSLOTS, SPLIT, F16>;
+  auto kern = mlp_tc2_kernel<NSLOTS, SPLIT, F16, LOCKSTEP>;
   static bool attr_set = false;
   if (!attr_set) {
     NB2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, LT::kTotal));
@@ -799,10 +823,11 @@ int launch_mlp_tc(nb2_handle* h, int net_id, int precision, const MlpIo& io, cud
   prm.prof = h->tc_prof;
   const bool split = (precision == NB2_PREC_BF16X3 || precision == NB2_PREC_FP16X3);
   if (env_int("NB2_TC_PAIR", 1) != 0) {
-    if (precision == NB2_PREC_BF16) return launch_tc2_impl<2, false, false>(h, prm, st);
-    if (precision == NB2_PREC_FP16) return launch_tc2_impl<2, false, true>(h, prm, st);
-    if (precision == NB2_PREC_BF16X3) return launch_tc2_impl<1, true, false>(h, prm, st);
-    if (precision == NB2_PREC_FP16X3) return launch_tc2_impl<1, true, true>(h, prm, st);
+    const bool ls = env_int("NB2_TC_LOCKSTEP", 1) != 0;
+    if (precision == NB2_PREC_BF16) return ls ? launch_tc2_impl<2, false, false, true>(h, prm, st) : launch_tc2_impl<2, false, false, false>(h, prm, st);
+    if (precision == NB2_PREC_FP16) return ls ? launch_tc2_impl<2, false, true, true>(h, prm, st) : launch_tc2_impl<2, false, true, false>(h, prm, st);
+    if (precision == NB2_PREC_BF16X3) return launch_tc2_impl<1, true, false, true>(h, prm, st);
+    if (precision == NB2_PREC_FP16X3) return launch_tc2_impl<1, true, true, true>(h, prm, st);
   }
   int cluster = env_int("NB2_TC_CLUSTER", 1);
   if (cluster != 1 && cluster != 2 && cluster != 4) {
