@@ -37,6 +37,9 @@ namespace nb2 {
 using namespace ptx;
 
 constexpr int kStages = 4;
+// two-slot kernels (384 threads, 168 registers at launch): warps 0-3 give registers back, the slot groups take them
+constexpr int kRoleRegs = 72;    // 128 x 72 + 256 x 216 = 64512 <= 65536
+constexpr int kGroupRegs = 216;
 constexpr int kRolesThreads = 128;  // warps 0..3
 
 struct TcParams {
@@ -186,20 +189,38 @@ template <int EPI, bool SPLIT, bool F16>
 __device__ __forceinline__ float epilogue_hidden(uint32_t acc, uint32_t slot_base, uint32_t lo_off, int row,
                                                  const float* __restrict__ head) {
   float sg = 0.f;
+  if (SPLIT) {
+    // two blocks (main + correction each) per tcgen05.wait::ld round trip
 #pragma unroll 1
-  for (int cb = 0; cb < kHidden / 32; ++cb) {
-    uint32_t r[32];
-    tmem_ld32(acc + cb * 32, r);
-    if (SPLIT) {
-      uint32_t c[32];
-      tmem_ld32(acc + 256 + cb * 32, c);
+    for (int cb = 0; cb < kHidden / 32; cb += 2) {
+      uint32_t m0[32], c0[32], m1[32], c1[32];
+      tmem_ld32(acc + cb * 32, m0);
+      tmem_ld32(acc + 256 + cb * 32, c0);
+      tmem_ld32(acc + (cb + 1) * 32, m1);
+      tmem_ld32(acc + 256 + (cb + 1) * 32, c1);
       tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(c[j]));
-    } else {
-      tmem_ld_wait();
+      for (int j = 0; j < 32; ++j) m0[j] = __float_as_uint(__uint_as_float(m0[j]) + __uint_as_float(c0[j]));
+      epilogue_block<EPI, SPLIT, F16>(m0, cb, slot_base, lo_off, row, head, sg);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) m1[j] = __float_as_uint(__uint_as_float(m1[j]) + __uint_as_float(c1[j]));
+      epilogue_block<EPI, SPLIT, F16>(m1, cb + 1, slot_base, lo_off, row, head, sg);
     }
-    epilogue_block<EPI, SPLIT, F16>(r, cb, slot_base, lo_off, row, head, sg);
+  } else {
+    // four blocks per tcgen05.wait::ld round trip: the load latency (~250 cycles) is paid twice per layer, not 8 times
+#pragma unroll 1
+    for (int cb = 0; cb < kHidden / 32; cb += 4) {
+      uint32_t r0[32], r1[32], r2[32], r3[32];
+      tmem_ld32(acc + cb * 32, r0);
+      tmem_ld32(acc + (cb + 1) * 32, r1);
+      tmem_ld32(acc + (cb + 2) * 32, r2);
+      tmem_ld32(acc + (cb + 3) * 32, r3);
+      tmem_ld_wait();
+      epilogue_block<EPI, SPLIT, F16>(r0, cb, slot_base, lo_off, row, head, sg);
+      epilogue_block<EPI, SPLIT, F16>(r1, cb + 1, slot_base, lo_off, row, head, sg);
+      epilogue_block<EPI, SPLIT, F16>(r2, cb + 2, slot_base, lo_off, row, head, sg);
+      epilogue_block<EPI, SPLIT, F16>(r3, cb + 3, slot_base, lo_off, row, head, sg);
+    }
   }
   return sg;
 }
@@ -410,6 +431,7 @@ __global__ void __launch_bounds__(kRolesThreads + 128 * NSLOTS, 1) mlp_tc_kernel
 
   if (warp == 0) {
     // =========================== weight streamer ==================================================
+    if (NSLOTS == 2) reg_dealloc<kRoleRegs>();
     if (lane == 0) {
       uint32_t stage = 0, phase = 0, q = 0;
       long long t_empty = 0, t0s = NB2_CLK();
@@ -440,6 +462,7 @@ __global__ void __launch_bounds__(kRolesThreads + 128 * NSLOTS, 1) mlp_tc_kernel
     }
   } else if (warp == 1) {
     // =========================== MMA issuer =======================================================
+    if (NSLOTS == 2) reg_dealloc<kRoleRegs>();
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_16(128, 128, F16);
       uint32_t stage = 0, phase = 0;
@@ -530,7 +553,10 @@ __global__ void __launch_bounds__(kRolesThreads + 128 * NSLOTS, 1) mlp_tc_kernel
       if (NB2_PROF_ON) { p.prof[blockIdx.x * 16 + 3] = t_wa; p.prof[blockIdx.x * 16 + 4] = t_ww; p.prof[blockIdx.x * 16 + 5] = NB2_CLK() - t0m; }
     }
   } else if (warp >= 4) {
+    if (NSLOTS == 2) reg_alloc<kGroupRegs>();
     slot_group_run<NSLOTS, SPLIT, F16, false>(p, misc, act_base, tmem_base, n_iters, warp, lane, 0u);
+  } else {
+    if (NSLOTS == 2) reg_dealloc<kRoleRegs>();
   }
 
   // ---- teardown -----------------------------------------------------------------------------------
@@ -597,6 +623,7 @@ __global__ void __launch_bounds__(kRolesThreads + 128 * NSLOTS, 1) mlp_tc2_kerne
 
   if (warp == 0) {
     // =========================== weight streamer: this CTA's half of every tile =====================
+    if (NSLOTS == 2) reg_dealloc<kRoleRegs>();
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
       for (int64_t it = 0; it < n_iters; ++it) {
@@ -622,6 +649,7 @@ __global__ void __launch_bounds__(kRolesThreads + 128 * NSLOTS, 1) mlp_tc2_kerne
       }
     }
   } else if (warp == 1) {
+    if (NSLOTS == 2) reg_dealloc<kRoleRegs>();
     if (lane == 0 && rank != 0) {
       // =========================== peer: relay "my half has landed" to the leader =====================
       uint32_t stage = 0, phase = 0;
@@ -699,7 +727,10 @@ __global__ void __launch_bounds__(kRolesThreads + 128 * NSLOTS, 1) mlp_tc2_kerne
       if (NB2_PROF_ON) { p.prof[blockIdx.x * 16 + 3] = t_wa; p.prof[blockIdx.x * 16 + 4] = t_ww; p.prof[blockIdx.x * 16 + 5] = NB2_CLK() - t0m; }
     }
   } else if (warp >= 4) {
+    if (NSLOTS == 2) reg_alloc<kGroupRegs>();
     slot_group_run<NSLOTS, SPLIT, F16, true>(p, misc, act_base, tmem_base, n_iters, warp, lane, rank);
+  } else {
+    if (NSLOTS == 2) reg_dealloc<kRoleRegs>();
   }
 
   tc_fence_before();

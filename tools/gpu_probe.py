@@ -115,7 +115,9 @@ def stage_roles(precision, H=400):
     names = ["str_wait_empty", "str_total", "ring_entries", "mma_wait_A", "mma_wait_W", "mma_total", "g0_encode", "g0_wait_acc",
              "g0_epi_hidden", "g0_epi_last", "g0_total", "iters", "layers"]
     print(f"ROLES {precision} cluster={os.environ.get('NB2_TC_CLUSTER','dflt')} lockstep={os.environ.get('NB2_TC_LOCKSTEP','dflt')} (median over CTAs, cycles; last launch = fine kernel)")
+    lead = a[a[:, 5] > 0] if (a[:, 5] > 0).any() else a       # MMA counters exist on issuing CTAs only
     med = np.median(a, axis=0)
+    med[3:6] = np.median(lead[:, 3:6], axis=0)
     for i, n in enumerate(names):
         print(f"   {n:16s} {med[i]:14.0f}   per-iter {med[i] / max(med[11], 1):12.0f}")
 

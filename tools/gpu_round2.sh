@@ -10,6 +10,6 @@ run smoke python __graft_entry__.py smoke
 TAILN=3 run bench python bench.py
 TAILN=3 run bench_ref python bench.py --impl reference --steps 3 --warmup 1
 run ncu_launches ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches_r01.csv python bench.py --steps 2 --warmup 1 --no-extras
-run ncu_full_bf16 ncu --set full --clock-control none --import-source on -k regex:mlp_tc_kernel -s 3 -c 2 -f -o gpurun_out/prof_bf16 python tools/gpu_probe.py time bf16 200
-run ncu_full_fp16x3 ncu --set full --clock-control none --import-source on -k regex:mlp_tc_kernel -s 3 -c 2 -f -o gpurun_out/prof_fp16x3 python tools/gpu_probe.py time fp16x3 200
+run ncu_full_bf16 ncu --set full --clock-control none --import-source on -k regex:mlp_tc -s 3 -c 2 -f -o gpurun_out/prof_bf16 python tools/gpu_probe.py time bf16 200
+run ncu_full_fp16x3 ncu --set full --clock-control none --import-source on -k regex:mlp_tc -s 3 -c 2 -f -o gpurun_out/prof_fp16x3 python tools/gpu_probe.py time fp16x3 200
 ls -la gpurun_out | head -40
