@@ -41,6 +41,11 @@ constexpr int kStages = 4;
 constexpr int kRoleRegs = 72;    // 128 x 72 + 256 x 216 = 64512 <= 65536
 constexpr int kGroupRegs = 216;
 constexpr int kRolesThreads = 128;  // warps 0..3
+// Every tensor kernel runs 128 role threads + two 128-thread warpgroups.  Single-pass modes: one warpgroup per
+// resident tile (two slots).  Split modes (one slot): both warpgroups work on the same tile, each on half of the
+// columns (a TMEM lane quadrant is reachable from any warp with the same warp % 4).
+constexpr int kTcThreads = 384;
+template <int NSLOTS> struct GroupsPerSlot { static constexpr int value = 2 / NSLOTS; };
 
 struct TcParams {
   TcNet net;
@@ -110,7 +115,9 @@ __device__ __forceinline__ void store_a8(uint32_t tile_hi, uint32_t tile_lo, int
 // so biases are added by the tensor core (see nb2_pack.cu) and never touch the epilogue.
 template <bool SPLIT, bool F16, int NCOLS, int MAXLEV>
 __device__ __forceinline__ void write_enc_row(uint32_t tile_hi, uint32_t tile_lo, int row, const float x[3],
-                                              int levels, bool valid) {
+                                              int levels, bool valid, int g_begin = 0, int g_end = NCOLS / 8) {
+  // only column groups [g_begin, g_end) (8 columns each) are produced by this thread; a frequency level is
+  // evaluated when any of its six columns [3 + 6l, 9 + 6l) falls inside that range
   float v[NCOLS];
 #pragma unroll
   for (int c = 0; c < NCOLS; ++c) v[c] = 0.f;
@@ -118,7 +125,7 @@ __device__ __forceinline__ void write_enc_row(uint32_t tile_hi, uint32_t tile_lo
     v[0] = x[0]; v[1] = x[1]; v[2] = x[2];
 #pragma unroll
     for (int l = 0; l < MAXLEV; ++l) {
-      if (l < levels) {
+      if (l < levels && 3 + 6 * l < 8 * g_end && 9 + 6 * l > 8 * g_begin) {
         const float sc = (float)(1 << l);
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
@@ -133,10 +140,12 @@ __device__ __forceinline__ void write_enc_row(uint32_t tile_hi, uint32_t tile_lo
   if (NCOLS == 64) v[NCOLS - 1] = 1.f;
 #pragma unroll
   for (int g = 0; g < NCOLS / 8; ++g) {
-    float w[8];
+    if (g >= g_begin && g < g_end) {
+      float w[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) w[i] = v[8 * g + i];
-    store_a8<SPLIT, F16>(tile_hi, tile_lo, row, 8 * g, w);
+      for (int i = 0; i < 8; ++i) w[i] = v[8 * g + i];
+      store_a8<SPLIT, F16>(tile_hi, tile_lo, row, 8 * g, w);
+    }
   }
 }
 
@@ -187,12 +196,12 @@ __device__ __forceinline__ void epilogue_block(const uint32_t (&r)[32], int cb, 
 // tcgen05.ld in flight during the conversion measured 4-15 % SLOWER on B200 and was dropped.)
 template <int EPI, bool SPLIT, bool F16>
 __device__ __forceinline__ float epilogue_hidden(uint32_t acc, uint32_t slot_base, uint32_t lo_off, int row,
-                                                 const float* __restrict__ head) {
+                                                 const float* __restrict__ head, int cb_begin, int cb_end) {
   float sg = 0.f;
   if (SPLIT) {
     // two blocks (main + correction each) per tcgen05.wait::ld round trip
 #pragma unroll 1
-    for (int cb = 0; cb < kHidden / 32; cb += 2) {
+    for (int cb = cb_begin; cb < cb_end; cb += 2) {
       uint32_t m0[32], c0[32], m1[32], c1[32];
       tmem_ld32(acc + cb * 32, m0);
       tmem_ld32(acc + 256 + cb * 32, c0);
@@ -209,7 +218,7 @@ __device__ __forceinline__ float epilogue_hidden(uint32_t acc, uint32_t slot_bas
   } else {
     // four blocks per tcgen05.wait::ld round trip: the load latency (~250 cycles) is paid twice per layer, not 8 times
 #pragma unroll 1
-    for (int cb = 0; cb < kHidden / 32; cb += 4) {
+    for (int cb = cb_begin; cb < cb_end; cb += 4) {
       uint32_t r0[32], r1[32], r2[32], r3[32];
       tmem_ld32(acc + cb * 32, r0);
       tmem_ld32(acc + (cb + 1) * 32, r1);
@@ -236,7 +245,11 @@ __device__ __forceinline__ void slot_group_run(const TcParams& p, TcMisc* misc, 
     if (PAIR && cl_rank != 0) mbar_arrive_remote(bar, 0); else mbar_arrive(bar);
   };
   // =========================== slot group: producer + epilogue ====================================
-  const int s = (warp - 4) >> 2;
+  constexpr int EW = GroupsPerSlot<NSLOTS>::value;   // warpgroups sharing one tile (column halves)
+  const int wg = (warp - 4) >> 2;
+  const int s = (EW == 2) ? 0 : wg;
+  const int half = (EW == 2) ? wg : 0;
+  const int cb0 = half * (8 / EW), cb1 = cb0 + 8 / EW;   // this thread's 32-column blocks of a 256-wide layer
   const int wq = warp & 3;            // TMEM lane quadrant this warp may access
   const int row = wq * 32 + lane;     // row of the tile == TMEM lane
   const uint32_t slot_base = act_base + s * LT::kSlotBytes;
@@ -254,7 +267,8 @@ __device__ __forceinline__ void slot_group_run(const TcParams& p, TcMisc* misc, 
     const int64_t grow = tile * kTileRows + row;
     const long long cpe = NB2_CLK();
     const RowIn in = load_row(p.io, grow);
-    write_enc_row<SPLIT, F16, kEncCols, kMaxPosLevels>(e_hi, e_lo, row, in.p, p.pos_levels, in.valid);
+    write_enc_row<SPLIT, F16, kEncCols, kMaxPosLevels>(e_hi, e_lo, row, in.p, p.pos_levels, in.valid, half * (8 / EW),
+                                                       half * (8 / EW) + 8 / EW);
     t_pe += NB2_CLK() - cpe;
     fence_proxy_async_smem();
     tc_fence_before();
@@ -274,8 +288,9 @@ __device__ __forceinline__ void slot_group_run(const TcParams& p, TcMisc* misc, 
       if (epi == EPI_RGB) {
         // ---- rgb_layer: t = relu(acc) (128 wide, bias folded), rgb = sigmoid(W1 t + b1) --------
         float c0 = 0.f, c1 = 0.f, c2 = 0.f;
+        bool continue_flag = true;   // group 1 of a two-group tile stops after handing over its partial sums
 #pragma unroll 1
-        for (int cb = 0; cb < kRgbHidden / 32; ++cb) {
+        for (int cb = half * (4 / EW); cb < half * (4 / EW) + 4 / EW; ++cb) {
           uint32_t r[32];
           tmem_ld32(acc + cb * 32, r);
           if (SPLIT) {
@@ -300,6 +315,20 @@ __device__ __forceinline__ void slot_group_run(const TcParams& p, TcMisc* misc, 
             c2 = fmaf(t0, w2.x, c2); c2 = fmaf(t1, w2.y, c2); c2 = fmaf(t2, w2.z, c2); c2 = fmaf(t3, w2.w, c2);
           }
         }
+        if (EW == 2) {
+          // combine the two column halves: group 1 parks its partial sums (and its half of the density dot
+          // product) in the slot's first activation tile, which is dead once this layer's MMAs completed
+          const uint32_t xaddr = slot_base + (uint32_t)row * 16u;
+          if (half == 1) st_shared_v4(xaddr, __float_as_uint(sigma), __float_as_uint(c0), __float_as_uint(c1), __float_as_uint(c2));
+          named_bar_sync(3, 256);
+          if (half == 1) continue_flag = false;
+          else {
+            uint32_t x0, x1, x2, x3;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3) : "r"(xaddr));
+            sigma += __uint_as_float(x0); c0 += __uint_as_float(x1); c1 += __uint_as_float(x2); c2 += __uint_as_float(x3);
+          }
+        }
+        if (continue_flag) {
         c0 = 1.f / (1.f + expf(-(c0 + __ldg(p.head + kHeadRgbB + 0))));
         c1 = 1.f / (1.f + expf(-(c1 + __ldg(p.head + kHeadRgbB + 1))));
         c2 = 1.f / (1.f + expf(-(c2 + __ldg(p.head + kHeadRgbB + 2))));
@@ -353,21 +382,35 @@ __device__ __forceinline__ void slot_group_run(const TcParams& p, TcMisc* misc, 
           }
           named_bar_sync(1 + s, 128);  // scratch is reused by the next tile
         }
+        }  // continue_flag
       } else if (epi == EPI_RELU) {
-        epilogue_hidden<EPI_RELU, SPLIT, F16>(acc, slot_base, lo_off, row, p.head);
+        epilogue_hidden<EPI_RELU, SPLIT, F16>(acc, slot_base, lo_off, row, p.head, cb0, cb1);
       } else if (epi == EPI_LINEAR) {
-        epilogue_hidden<EPI_LINEAR, SPLIT, F16>(acc, slot_base, lo_off, row, p.head);
+        epilogue_hidden<EPI_LINEAR, SPLIT, F16>(acc, slot_base, lo_off, row, p.head, cb0, cb1);
       } else if (epi == EPI_RELU_SIGMA) {
-        sigma = epilogue_hidden<EPI_RELU_SIGMA, SPLIT, F16>(acc, slot_base, lo_off, row, p.head) + __ldg(p.head + kHeadSigmaB);
-        if (p.has_dir) {
+        // (with two groups per tile each keeps the dot product over its own columns; the bias is added once)
+        sigma = epilogue_hidden<EPI_RELU_SIGMA, SPLIT, F16>(acc, slot_base, lo_off, row, p.head, cb0, cb1) +
+                (half == 0 ? __ldg(p.head + kHeadSigmaB) : 0.f);
+        if (p.has_dir && half == 0) {
           // the encoded position is dead after the skip layer: re-use its tile for the direction
           float rot[3] = {0.f, 0.f, 0.f};
           if (in.valid) normalize_dir(in.d, rot);
           write_enc_row<SPLIT, F16, kDirCols, kMaxDirLevels>(e_hi, e_lo, row, rot, p.dir_levels, in.valid);
         }
       } else {  // EPI_SIGMA_OUT
-        sigma = epilogue_hidden<EPI_SIGMA_OUT, SPLIT, F16>(acc, slot_base, lo_off, row, p.head) + __ldg(p.head + kHeadSigmaB);
-        if (in.valid) p.io.out[grow] = sigma;
+        sigma = epilogue_hidden<EPI_SIGMA_OUT, SPLIT, F16>(acc, slot_base, lo_off, row, p.head, cb0, cb1) +
+                (half == 0 ? __ldg(p.head + kHeadSigmaB) : 0.f);
+        if (EW == 2) {
+          const uint32_t xaddr = slot_base + (uint32_t)row * 4u;
+          if (half == 1) asm volatile("st.shared.b32 [%0], %1;" ::"r"(xaddr), "r"(__float_as_uint(sigma)));
+          named_bar_sync(3, 256);
+          if (half == 0) {
+            uint32_t x0;
+            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(x0) : "r"(xaddr));
+            sigma += __uint_as_float(x0);
+          }
+        }
+        if (in.valid && half == 0) p.io.out[grow] = sigma;
       }
       if (l + 1 < net.n_layers) {
         fence_proxy_async_smem();
@@ -389,7 +432,7 @@ __device__ __forceinline__ void slot_group_run(const TcParams& p, TcMisc* misc, 
 // LOCKSTEP (two-slot mode only): both resident tiles consume every weight tile back to back, halving the
 // L2 -> SM weight traffic per FLOP at the price of not overlapping one tile's epilogue with the other's MMAs.
 template <int NSLOTS, bool SPLIT, bool F16, bool LOCKSTEP>
-__global__ void __launch_bounds__(kRolesThreads + 128 * NSLOTS, 1) mlp_tc_kernel(const __grid_constant__ TcParams p) {
+__global__ void __launch_bounds__(kTcThreads, 1) mlp_tc_kernel(const __grid_constant__ TcParams p) {
   using LT = TcLayout<NSLOTS, SPLIT>;
   extern __shared__ unsigned char smem_dyn[];
   const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
@@ -414,7 +457,7 @@ __global__ void __launch_bounds__(kRolesThreads + 128 * NSLOTS, 1) mlp_tc_kernel
       mbar_init(smem_u32(&misc->w_empty[i]), cl_size);   // one arrive per consumer CTA of the cluster
     }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(smem_u32(&misc->a_ready[s]), 128);
+      mbar_init(smem_u32(&misc->a_ready[s]), 128 * GroupsPerSlot<NSLOTS>::value);
       mbar_init(smem_u32(&misc->acc_full[s]), 1);
     }
     mbar_fence_init();
@@ -431,7 +474,7 @@ __global__ void __launch_bounds__(kRolesThreads + 128 * NSLOTS, 1) mlp_tc_kernel
 
   if (warp == 0) {
     // =========================== weight streamer ==================================================
-    if (NSLOTS == 2) reg_dealloc<kRoleRegs>();
+    reg_dealloc<kRoleRegs>();
     if (lane == 0) {
       uint32_t stage = 0, phase = 0, q = 0;
       long long t_empty = 0, t0s = NB2_CLK();
@@ -462,7 +505,7 @@ __global__ void __launch_bounds__(kRolesThreads + 128 * NSLOTS, 1) mlp_tc_kernel
     }
   } else if (warp == 1) {
     // =========================== MMA issuer =======================================================
-    if (NSLOTS == 2) reg_dealloc<kRoleRegs>();
+    reg_dealloc<kRoleRegs>();
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_16(128, 128, F16);
       uint32_t stage = 0, phase = 0;
@@ -553,10 +596,10 @@ __global__ void __launch_bounds__(kRolesThreads + 128 * NSLOTS, 1) mlp_tc_kernel
       if (NB2_PROF_ON) { p.prof[blockIdx.x * 16 + 3] = t_wa; p.prof[blockIdx.x * 16 + 4] = t_ww; p.prof[blockIdx.x * 16 + 5] = NB2_CLK() - t0m; }
     }
   } else if (warp >= 4) {
-    if (NSLOTS == 2) reg_alloc<kGroupRegs>();
+    reg_alloc<kGroupRegs>();
     slot_group_run<NSLOTS, SPLIT, F16, false>(p, misc, act_base, tmem_base, n_iters, warp, lane, 0u);
   } else {
-    if (NSLOTS == 2) reg_dealloc<kRoleRegs>();
+    reg_dealloc<kRoleRegs>();
   }
 
   // ---- teardown -----------------------------------------------------------------------------------
@@ -583,7 +626,7 @@ __global__ void __launch_bounds__(kRolesThreads + 128 * NSLOTS, 1) mlp_tc_kernel
 // Two-slot (single pass) mode runs the slots in lockstep: every weight half-tile feeds 2 x 4 MMAs = 1024 tensor cycles.
 // ======================================================================================================
 template <int NSLOTS, bool SPLIT, bool F16, bool LOCKSTEP>
-__global__ void __launch_bounds__(kRolesThreads + 128 * NSLOTS, 1) mlp_tc2_kernel(const __grid_constant__ TcParams p) {
+__global__ void __launch_bounds__(kTcThreads, 1) mlp_tc2_kernel(const __grid_constant__ TcParams p) {
   constexpr int kPasses = LOCKSTEP ? 1 : NSLOTS;   // how many times a layer's weight stream is consumed per iteration
   using LT = TcLayout<NSLOTS, SPLIT>;
   extern __shared__ unsigned char smem_dyn[];
@@ -606,7 +649,7 @@ __global__ void __launch_bounds__(kRolesThreads + 128 * NSLOTS, 1) mlp_tc2_kerne
       mbar_init(smem_u32(&misc->w_empty[i]), 1);
     }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(smem_u32(&misc->a_ready[s]), 256);   // 128 threads of each CTA of the pair
+      mbar_init(smem_u32(&misc->a_ready[s]), 256 * GroupsPerSlot<NSLOTS>::value);   // every slot-group thread of both CTAs
       mbar_init(smem_u32(&misc->acc_full[s]), 1);
     }
     mbar_fence_init();
@@ -623,7 +666,7 @@ __global__ void __launch_bounds__(kRolesThreads + 128 * NSLOTS, 1) mlp_tc2_kerne
 
   if (warp == 0) {
     // =========================== weight streamer: this CTA's half of every tile =====================
-    if (NSLOTS == 2) reg_dealloc<kRoleRegs>();
+    reg_dealloc<kRoleRegs>();
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
       for (int64_t it = 0; it < n_iters; ++it) {
@@ -649,7 +692,7 @@ __global__ void __launch_bounds__(kRolesThreads + 128 * NSLOTS, 1) mlp_tc2_kerne
       }
     }
   } else if (warp == 1) {
-    if (NSLOTS == 2) reg_dealloc<kRoleRegs>();
+    reg_dealloc<kRoleRegs>();
     if (lane == 0 && rank != 0) {
       // =========================== peer: relay "my half has landed" to the leader =====================
       uint32_t stage = 0, phase = 0;
@@ -727,10 +770,10 @@ __global__ void __launch_bounds__(kRolesThreads + 128 * NSLOTS, 1) mlp_tc2_kerne
       if (NB2_PROF_ON) { p.prof[blockIdx.x * 16 + 3] = t_wa; p.prof[blockIdx.x * 16 + 4] = t_ww; p.prof[blockIdx.x * 16 + 5] = NB2_CLK() - t0m; }
     }
   } else if (warp >= 4) {
-    if (NSLOTS == 2) reg_alloc<kGroupRegs>();
+    reg_alloc<kGroupRegs>();
     slot_group_run<NSLOTS, SPLIT, F16, true>(p, misc, act_base, tmem_base, n_iters, warp, lane, rank);
   } else {
-    if (NSLOTS == 2) reg_dealloc<kRoleRegs>();
+    reg_dealloc<kRoleRegs>();
   }
 
   tc_fence_before();
@@ -765,7 +808,7 @@ static int launch_tc_impl(nb2_handle* h, TcParams& prm, cudaStream_t st) {
   ctas = (ctas + cluster - 1) / cluster * cluster;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cfg.blockDim = dim3(kRolesThreads + 128 * NSLOTS);
+  cfg.blockDim = dim3(kTcThreads);
   cfg.dynamicSmemBytes = LT::kTotal;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -806,7 +849,7 @@ static int launch_tc2_impl(nb2_handle* h, TcParams& prm, cudaStream_t st) {
   ctas = (ctas + 1) / 2 * 2;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cfg.blockDim = dim3(kRolesThreads + 128 * NSLOTS);
+  cfg.blockDim = dim3(kTcThreads);
   cfg.dynamicSmemBytes = LT::kTotal;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
