@@ -33,6 +33,10 @@ NEAR, FAR, N_COARSE, N_FINE = 2.0, 6.0, 64, 128
 FLOP_PROP_PER_RAY = 27262976       # 2*(63*256 + 3*256^2 + 256) * 64
 FLOP_NERF_PER_RAY = 135135232      # 2*(63*256 + 3*256^2 + 319*256 + 2*256^2 + 256^2 + 256 + 283*128 + 128*3) * 128
 METRIC = "rays/sec (64c+128f samples)"
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE fine-kernel launch over 160,000 rays, from the ncu --set full
+# captures summarised in profiles/r01_ncu_{fp16x3_pair2wg,fp16_pair}.txt (algorithmic: 556 B/ray = 89 MB; the
+# 2.4 MB of packed weights stay L2-resident)
+NCU_FINE_TRAFFIC_BYTES_160K = {"fp16x3": 92.6e6, "bf16x3": 92.6e6, "fp16": 91.0e6, "bf16": 91.0e6}
 
 
 def load_peaks():
@@ -295,7 +299,9 @@ def main():
     achieved = FLOP_NERF_PER_RAY * n_rays / (fine_ms * 1e-3) / 1e12
     passes = 3 if args.precision in ("fp16x3", "bf16x3") else 1
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
-                "traffic": None, "kernel": "mlp_tc_kernel (fine: encode + 8x256 MLP + composite)", "kernel_ms": fine_ms,
+                "traffic": (NCU_FINE_TRAFFIC_BYTES_160K.get(args.precision) if n_rays == 160000 else None),
+                "traffic_unit": "bytes per launch (ncu dram read+write; algorithmic 556 B/ray)",
+                "kernel": "mlp_tc2_kernel (fine: encode + 8x256 MLP + composite; CTA-pair tcgen05)", "kernel_ms": fine_ms,
                 "algorithmic_flop_per_launch": FLOP_NERF_PER_RAY * n_rays, "peak_source": peaks["src"], "mma_passes_per_product": passes,
                 "issued_tensor_tflops": achieved * passes * 528384.0 / 527872.0, "step_share": {"proposal_kernel_ms": kms[0], "resample_kernel_ms": kms[1], "fine_kernel_ms": kms[2]}}
     for mode, m in extras.items():

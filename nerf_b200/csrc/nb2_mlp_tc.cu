@@ -149,6 +149,55 @@ __device__ __forceinline__ void write_enc_row(uint32_t tile_hi, uint32_t tile_lo
   }
 }
 
+// The same encoding, split in two steps so the arithmetic of the NEXT tile can run while the current tile's first
+// MMAs execute: enc_compute fills packed 16-bit registers for column groups [G0, G0 + NG) of the 64-column position
+// tile, enc_store writes them (16 bytes per group and row) once the tile buffer is free.
+template <bool SPLIT, bool F16, int G0, int NG>
+struct EncRegs {
+  uint32_t hi[NG * 4];
+  uint32_t lo[SPLIT ? NG * 4 : 1];
+};
+template <bool SPLIT, bool F16, int G0, int NG>
+__device__ __forceinline__ void enc_compute(EncRegs<SPLIT, F16, G0, NG>& e, const float x[3], int levels, bool valid) {
+  float v[kEncCols];
+#pragma unroll
+  for (int c = 0; c < kEncCols; ++c) v[c] = 0.f;
+  if (valid) {
+    v[0] = x[0]; v[1] = x[1]; v[2] = x[2];
+#pragma unroll
+    for (int l = 0; l < kMaxPosLevels; ++l) {
+      if (l < levels && 3 + 6 * l < 8 * (G0 + NG) && 9 + 6 * l > 8 * G0) {
+        const float sc = (float)(1 << l);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          float sn, cs;
+          sincosf(x[k] * sc, &sn, &cs);
+          v[3 + 6 * l + k] = sn;
+          v[3 + 6 * l + 3 + k] = cs;
+        }
+      }
+    }
+  }
+  v[kEncCols - 1] = 1.f;   // bias column
+#pragma unroll
+  for (int g = 0; g < NG; ++g)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float a = v[8 * (G0 + g) + 2 * i], b = v[8 * (G0 + g) + 2 * i + 1];
+      e.hi[4 * g + i] = pack16x2<F16>(a, b);
+      if (SPLIT) e.lo[4 * g + i] = residual16x2<F16>(a, b, e.hi[4 * g + i]);
+    }
+}
+template <bool SPLIT, bool F16, int G0, int NG>
+__device__ __forceinline__ void enc_store(const EncRegs<SPLIT, F16, G0, NG>& e, uint32_t tile_hi, uint32_t tile_lo, int row) {
+#pragma unroll
+  for (int g = 0; g < NG; ++g) {
+    const uint32_t off = (uint32_t)row * 128u + ((((uint32_t)(G0 + g)) ^ ((uint32_t)row & 7u)) << 4);
+    st_shared_v4(tile_hi + off, e.hi[4 * g], e.hi[4 * g + 1], e.hi[4 * g + 2], e.hi[4 * g + 3]);
+    if (SPLIT) st_shared_v4(tile_lo + off, e.lo[4 * g], e.lo[4 * g + 1], e.lo[4 * g + 2], e.lo[4 * g + 3]);
+  }
+}
+
 // One 32-column block of the hidden epilogue: values (already summed with the correction accumulator in SPLIT mode)
 // -> activation -> 16-bit A operand rows (+ running density-head dot product).
 template <int EPI, bool SPLIT, bool F16>
@@ -262,17 +311,34 @@ __device__ __forceinline__ void slot_group_run(const TcParams& p, TcMisc* misc, 
   uint32_t pacc = 0;
   long long t_pe = 0, t_wacc = 0, t_epi = 0, t_last = 0, t0e = NB2_CLK();
 
-  for (int64_t it = 0; it < n_iters; ++it) {
-    const int64_t tile = (it * gridDim.x + blockIdx.x) * NSLOTS + s;   // may lie past n_tiles: rows invalid
-    const int64_t grow = tile * kTileRows + row;
-    const long long cpe = NB2_CLK();
-    const RowIn in = load_row(p.io, grow);
-    write_enc_row<SPLIT, F16, kEncCols, kMaxPosLevels>(e_hi, e_lo, row, in.p, p.pos_levels, in.valid, half * (8 / EW),
-                                                       half * (8 / EW) + 8 / EW);
-    t_pe += NB2_CLK() - cpe;
+  // The encoding of tile it+1 is computed while tile it's first layer runs on the tensor core, and stored (tile
+  // "begun") inside tile it's last epilogue, as soon as its accumulator has been read.
+  auto tile_of = [&](int64_t it) { return (it * gridDim.x + blockIdx.x) * NSLOTS + s; };   // may lie past n_tiles
+  EncRegs<SPLIT, F16, 0, 8 / EW> enc_a;          // column groups of warpgroup 0 (all 8 groups when EW == 1)
+  EncRegs<SPLIT, F16, 8 - 8 / EW, 8 / EW> enc_b; // column groups of warpgroup 1 (EW == 2 only)
+  auto enc_make = [&](const RowIn& r) {
+    if (EW == 1 || half == 0) enc_compute(enc_a, r.p, p.pos_levels, r.valid); else enc_compute(enc_b, r.p, p.pos_levels, r.valid);
+  };
+  auto begin_tile = [&]() {
+    if (EW == 1 || half == 0) enc_store(enc_a, e_hi, e_lo, row); else enc_store(enc_b, e_hi, e_lo, row);
     fence_proxy_async_smem();
     tc_fence_before();
     arrive_a(a_ready);
+  };
+  RowIn in = load_row(p.io, tile_of(0) * kTileRows + row);
+  enc_make(in);
+  begin_tile();
+
+  for (int64_t it = 0; it < n_iters; ++it) {
+    const int64_t grow = tile_of(it) * kTileRows + row;
+    const bool has_next = (it + 1 < n_iters);
+    RowIn in_next = in;
+    const long long cpe = NB2_CLK();
+    if (has_next) {
+      in_next = load_row(p.io, tile_of(it + 1) * kTileRows + row);
+      enc_make(in_next);
+    }
+    t_pe += NB2_CLK() - cpe;
 
     float sigma = 0.f;
     for (int l = 0; l < net.n_layers; ++l) {
@@ -328,6 +394,7 @@ __device__ __forceinline__ void slot_group_run(const TcParams& p, TcMisc* misc, 
             sigma += __uint_as_float(x0); c0 += __uint_as_float(x1); c1 += __uint_as_float(x2); c2 += __uint_as_float(x3);
           }
         }
+        if (has_next) begin_tile();   // accumulator and activation tiles of this tile are no longer needed
         if (continue_flag) {
         c0 = 1.f / (1.f + expf(-(c0 + __ldg(p.head + kHeadRgbB + 0))));
         c1 = 1.f / (1.f + expf(-(c1 + __ldg(p.head + kHeadRgbB + 1))));
@@ -410,6 +477,7 @@ __device__ __forceinline__ void slot_group_run(const TcParams& p, TcMisc* misc, 
             sigma += __uint_as_float(x0);
           }
         }
+        if (has_next) begin_tile();
         if (in.valid && half == 0) p.io.out[grow] = sigma;
       }
       if (l + 1 < net.n_layers) {
@@ -421,7 +489,7 @@ __device__ __forceinline__ void slot_group_run(const TcParams& p, TcMisc* misc, 
         t_last += NB2_CLK() - ce;
       }
     }
-    tc_fence_before();  // accumulator reads of the last layer precede the next tile's a_ready arrive
+    in = in_next;
   }
   if (NB2_PROF_ON && threadIdx.x == kRolesThreads) {
     long long* o = p.prof + blockIdx.x * 16;
