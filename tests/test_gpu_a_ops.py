@@ -51,13 +51,18 @@ def test_sample_coarse_bit_exact(gin):
 
 def test_positional_encoding(golden, gin):
     got = nerf_b200.positional_encoding(cu(gin["pe_x"]), 10)
-    assert got.shape == golden["pe"].shape and maxerr(got, golden["pe"]) < 2e-6
+    assert got.shape == golden["pe"].shape
+    assert maxerr(got, golden["pe"]) < 2e-6, maxerr(got, golden["pe"])
     got3 = nerf_b200.positional_encoding(cu(gin["pe_x3"]), 4)
-    assert got3.shape == golden["pe3"].shape and maxerr(got3, golden["pe3"]) < 2e-6
-    # ragged / large: arguments up to 512 * 6.5 rad need full range reduction
+    assert got3.shape == golden["pe3"].shape
+    assert maxerr(got3, golden["pe3"]) < 2e-6, maxerr(got3, golden["pe3"])
+    # ragged / large: arguments up to 512 * 6.5 rad need full range reduction.  The comparison is against the host
+    # CPU's vectorised sin/cos, whose error at |x| ~ 3000 depends on the SIMD path -> a few ulp of slack
     x = O.det_uniform((100003, 3), 3, -6.5, 6.5)
     big = nerf_b200.positional_encoding(cu(x), 10)
-    assert maxerr(big, O.positional_encoding(x, 10)) < 2e-6
+    ref64 = torch.cat([f(((2.0 ** l) * x).double()) for l in range(10) for f in (torch.sin, torch.cos)], dim=-1)
+    assert float((big.cpu().double() - ref64).abs().max()) < 5e-7      # vs an fp64 evaluation: CUDA sincosf is ~2 ulp
+    assert maxerr(big, O.positional_encoding(x, 10)) < 5e-6, maxerr(big, O.positional_encoding(x, 10))
 
 
 def test_ipe(golden, gin):
