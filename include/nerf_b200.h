@@ -159,6 +159,18 @@ int nb2_coarse_fine_merge(nb2_handle* h, const float* rays, const float* c_z, co
                           int64_t n_rays, int n_coarse, int n_fine, float* z_out,
                           float* pts_out, void* stream);
 
+/* ---- f1 (training-side callers of the path, forward only) -----------------------------------
+ * validSampler  nerf/utils.py:72-94: ray r takes pixel indices[r] (NULL -> device Philox) of the flattened image:
+ *   rgbs (N,3), coords (N,2) int64 = (col - W/2, H/2 - row); cam_tf 12 floats; base_z (P) = linspace(near, far-res, P);
+ *   -> pts (R,P,3), lengths (R,P), rgb (R,3), rays (R,6).
+ * getBounds     nerf/addtional.py:14-18: weights (R,P), inds (R,K) int64 -> (R,K-1) summed-area-table differences. */
+int nb2_valid_sampler(nb2_handle* h, const float* rgbs, const int64_t* coords, const float* cam_tf,
+                      const int64_t* indices, const float* base_z, const float* jitter, float focal_x, float focal_y,
+                      float resolution, uint64_t seed, int64_t ray_offset, int64_t n_pixels, int64_t n_rays,
+                      int n_samples, float* pts_out, float* lengths_out, float* rgb_out, float* rays_out, void* stream);
+int nb2_get_bounds(nb2_handle* h, const float* weights, const int64_t* inds, int64_t n_rays, int n_samples,
+                   int n_inds, float* out, void* stream);
+
 /* ---- a6 / a11: MLP forward ---------------------------------------------------------------
  * NB2_NET_PROPOSAL: pts (R*P, 3) -> out (R*P) raw density.  ProposalNetwork.forward
  *                   nerf/addtional.py:88-96.  `pts_stride` = 3.
@@ -166,6 +178,11 @@ int nb2_coarse_fine_merge(nb2_handle* h, const float* rays, const float* c_z, co
  *                   MipNeRF.forward nerf/mip_model.py:41-60.  `pts_stride` = 6. */
 int nb2_mlp_forward(nb2_handle* h, int net_id, int precision, const float* pts,
                     int pts_stride, int64_t n_points, float* out, void* stream);
+
+/* ProposalNetwork.forward(pts, encoded_pt): `encoded` (n, 6 * pos_levels) replaces the sinusoidal columns of the
+ * network input (the hook through which integrated positional encoding enters; nerf/addtional.py:88-91). */
+int nb2_mlp_forward_encoded(nb2_handle* h, int net_id, int precision, const float* pts, int pts_stride,
+                            const float* encoded, int64_t n_points, float* out, void* stream);
 
 /* ---- a12: alpha compositing                   nerf/nerf_base.py:90-113 ------------------
  * rgbo (R,P,4), z (R,P), dirs (R, dir_stride>=3) -> rgb (R,3), weights (R,P) or NULL,

@@ -11,9 +11,9 @@ from .ops import get_default_precision, set_default_precision  # noqa: F401
 from .nerf_helper import makeMLP, positional_encoding, saveModel  # noqa: F401
 from .nerf_base import NeRF, DecayLrScheduler  # noqa: F401
 from .mip_model import MipNeRF  # noqa: F401
-from .addtional import ProposalNetwork, LossPSNR, SoftL1Loss  # noqa: F401
+from .addtional import ProposalNetwork, LossPSNR, SoftL1Loss, ProposalLoss, getBounds  # noqa: F401
 from .mip_methods import maxBlurFilter, ipe_feature  # noqa: F401
-from .utils import inverseSample, sample_pdf, fov2Focal, pose_spherical  # noqa: F401
+from .utils import inverseSample, sample_pdf, fov2Focal, pose_spherical, validSampler  # noqa: F401
 from .procedures import render_image, get_patch_size  # noqa: F401
 
 __version__ = "0.1.0"

@@ -58,7 +58,11 @@ SIGNATURES = {
     "nb2_resample": (c_int, [c_vp, c_f32p, c_f32p, c_f32p, c_f32p, c_u64, c_i64, c_i64, c_int, c_int, c_float, c_int, c_f32p, c_vp]),
     "nb2_length2pts": (c_int, [c_vp, c_f32p, c_f32p, c_i64, c_int, c_f32p, c_vp]),
     "nb2_coarse_fine_merge": (c_int, [c_vp, c_f32p, c_f32p, c_f32p, c_i64, c_int, c_int, c_f32p, c_f32p, c_vp]),
+    "nb2_valid_sampler": (c_int, [c_vp, c_f32p, c_vp, c_f32p, c_vp, c_f32p, c_f32p, c_float, c_float, c_float, c_u64, c_i64, c_i64, c_i64,
+                                  c_int, c_f32p, c_f32p, c_f32p, c_f32p, c_vp]),
+    "nb2_get_bounds": (c_int, [c_vp, c_f32p, c_vp, c_i64, c_int, c_int, c_f32p, c_vp]),
     "nb2_mlp_forward": (c_int, [c_vp, c_int, c_int, c_f32p, c_int, c_i64, c_f32p, c_vp]),
+    "nb2_mlp_forward_encoded": (c_int, [c_vp, c_int, c_int, c_f32p, c_int, c_f32p, c_i64, c_f32p, c_vp]),
     "nb2_composite": (c_int, [c_vp, c_f32p, c_f32p, c_f32p, c_int, c_i64, c_int, c_int, c_float, c_float, c_f32p, c_f32p, c_f32p, c_f32p, c_vp]),
     "nb2_render_workspace_bytes": (c_i64, [c_i64, ctypes.POINTER(RenderParams)]),
     "nb2_render_rays": (c_int, [c_vp, ctypes.POINTER(RenderParams), c_f32p, c_f32p, c_f32p, c_f32p, c_i64, c_f32p, c_f32p,

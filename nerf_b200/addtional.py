@@ -11,6 +11,19 @@ from .nerf_base import PackedModule
 from .nerf_helper import makeMLP
 
 
+def getBounds(weights: torch.Tensor, inds: torch.Tensor):
+    """Proposal-weight mass between consecutive fine samples (reference nerf/addtional.py:14-18)."""
+    return ops.get_bounds(weights, inds)
+
+
+class ProposalLoss(nn.Module):
+    """reference nerf/addtional.py:20-24 (host-side reduction over CUDA tensors)."""
+
+    def forward(self, prop_bounds: torch.Tensor, nerf_weights: torch.Tensor) -> torch.Tensor:
+        bound_diff = (torch.relu(nerf_weights - prop_bounds)) ** 2
+        return torch.sum(bound_diff / (nerf_weights + 1e-8))
+
+
 class SoftL1Loss(nn.Module):
     """Despite the name this is MSE, as in the reference (nerf/addtional.py:38-43)."""
 
@@ -78,12 +91,14 @@ class ProposalNetwork(PackedModule):
 
     def forward(self, pts: torch.Tensor, encoded_pt: torch.Tensor = None) -> torch.Tensor:
         """pts (ray_num, point_num, 3) -> raw density (ray_num, point_num)."""
-        if encoded_pt is not None:
-            raise _lib.NB2Error("ProposalNetwork.forward(encoded_pt=...): externally encoded inputs (IPE) are not wired into "
-                                "the fused kernel yet; no reference call site uses this argument")
         if torch.is_grad_enabled() and pts.requires_grad:
             raise _lib.NB2Error("ProposalNetwork.forward: backward is not built yet; call under torch.no_grad()")
         self._nb2_sync()
+        if encoded_pt is not None:
+            # the reference views encoded_pt as (R, P, position_dims) and concatenates it behind the raw points
+            enc = encoded_pt.reshape(-1, self.position_dims)
+            out = ops.mlp_forward_encoded(_lib.NET_PROPOSAL, pts.reshape(-1, 3), enc, self.precision)
+            return out.view(pts.shape[0], pts.shape[1])
         out = ops.mlp_forward(_lib.NET_PROPOSAL, pts.reshape(-1, 3), self.precision)
         return out.view(pts.shape[0], pts.shape[1])
 

@@ -132,6 +132,29 @@ extern "C" int nb2_mlp_forward(nb2_handle* h, int net_id, int precision, const f
   return mlp_dispatch(h, net_id, precision, io, (cudaStream_t)stream);
 }
 
+extern "C" int nb2_mlp_forward_encoded(nb2_handle* h, int net_id, int precision, const float* pts, int pts_stride,
+                                       const float* encoded, int64_t n_points, float* out, void* stream) {
+  NB2_CHECK_ARG(h != nullptr, "null handle");
+  NB2_CHECK_ARG(net_id == NB2_NET_PROPOSAL, "mlp_forward_encoded: only the proposal network takes encoded_pt (nerf/addtional.py:88-91)");
+  if (n_points == 0) return NB2_OK;
+  NB2_CHECK_ARG(pts && encoded && out && n_points > 0 && pts_stride >= 3, "mlp_forward_encoded: bad arguments");
+  if (!h->net[net_id].packed) {
+    set_error("mlp_forward_encoded: weights of network %d have not been packed", net_id);
+    return NB2_ERR_STATE;
+  }
+  MlpIo io;
+  memset(&io, 0, sizeof(io));
+  io.in_mode = 0;
+  io.pts = pts;
+  io.pts_stride = pts_stride;
+  io.enc = encoded;
+  io.P = h->net[net_id].pos_levels;   // row stride of `encoded` is 6 * pos_levels
+  io.n_rows = n_points;
+  io.out_mode = 0;
+  io.out = out;
+  return mlp_dispatch(h, net_id, precision, io, (cudaStream_t)stream);
+}
+
 static inline int64_t align256(int64_t x) { return (x + 255) & ~(int64_t)255; }
 
 extern "C" int64_t nb2_render_workspace_bytes(int64_t n_rays, const nb2_render_params* p) {

@@ -198,6 +198,8 @@ struct MlpIo {
   // input selection
   int in_mode;            // 0 = explicit points, 1 = rays + z, 2 = rays + stratified sampling
   const float* pts;       // in_mode 0: (n_rows, pts_stride)
+  const float* enc;       // in_mode 0, optional: (n_rows, 6 * pos_levels) externally encoded position features
+                          // that replace the sin/cos columns (ProposalNetwork.forward(pts, encoded_pt), addtional.py:88-91)
   int pts_stride;
   const float* rays;      // in_mode 1/2: (n_rays, 6)
   const float* z;         // in_mode 1:   (n_rays, P)

@@ -158,11 +158,18 @@ struct EncRegs {
   uint32_t lo[SPLIT ? NG * 4 : 1];
 };
 template <bool SPLIT, bool F16, int G0, int NG>
-__device__ __forceinline__ void enc_compute(EncRegs<SPLIT, F16, G0, NG>& e, const float x[3], int levels, bool valid) {
+__device__ __forceinline__ void enc_compute(EncRegs<SPLIT, F16, G0, NG>& e, const float x[3], int levels, bool valid,
+                                            const float* ext) {
   float v[kEncCols];
 #pragma unroll
   for (int c = 0; c < kEncCols; ++c) v[c] = 0.f;
-  if (valid) {
+  if (valid && ext != nullptr) {
+    // externally encoded features (e.g. integrated positional encoding) take the place of the sin/cos columns
+    v[0] = x[0]; v[1] = x[1]; v[2] = x[2];
+#pragma unroll
+    for (int c = 3; c < kEncCols - 1; ++c)
+      if (c - 3 < 6 * levels && c >= 8 * G0 && c < 8 * (G0 + NG)) v[c] = __ldg(ext + c - 3);
+  } else if (valid) {
     v[0] = x[0]; v[1] = x[1]; v[2] = x[2];
 #pragma unroll
     for (int l = 0; l < kMaxPosLevels; ++l) {
@@ -290,8 +297,13 @@ __device__ __forceinline__ void slot_group_run(const TcParams& p, TcMisc* misc, 
                                                int64_t n_iters, int warp, int lane, uint32_t cl_rank) {
   using LT = TcLayout<NSLOTS, SPLIT>;
   const TcNet& net = p.net;
+  // one arrival per warp: every lane has fenced its own shared-memory writes / TMEM reads, __syncwarp orders them
+  // before the elected lane's (release) arrive
   auto arrive_a = [&](uint32_t bar) {
-    if (PAIR && cl_rank != 0) mbar_arrive_remote(bar, 0); else mbar_arrive(bar);
+    __syncwarp();
+    if (lane == 0) {
+      if (PAIR && cl_rank != 0) mbar_arrive_remote(bar, 0); else mbar_arrive(bar);
+    }
   };
   // =========================== slot group: producer + epilogue ====================================
   constexpr int EW = GroupsPerSlot<NSLOTS>::value;   // warpgroups sharing one tile (column halves)
@@ -317,7 +329,7 @@ __device__ __forceinline__ void slot_group_run(const TcParams& p, TcMisc* misc, 
   EncRegs<SPLIT, F16, 0, 8 / EW> enc_a;          // column groups of warpgroup 0 (all 8 groups when EW == 1)
   EncRegs<SPLIT, F16, 8 - 8 / EW, 8 / EW> enc_b; // column groups of warpgroup 1 (EW == 2 only)
   auto enc_make = [&](const RowIn& r) {
-    if (EW == 1 || half == 0) enc_compute(enc_a, r.p, p.pos_levels, r.valid); else enc_compute(enc_b, r.p, p.pos_levels, r.valid);
+    if (EW == 1 || half == 0) enc_compute(enc_a, r.p, p.pos_levels, r.valid, r.enc); else enc_compute(enc_b, r.p, p.pos_levels, r.valid, r.enc);
   };
   auto begin_tile = [&]() {
     if (EW == 1 || half == 0) enc_store(enc_a, e_hi, e_lo, row); else enc_store(enc_b, e_hi, e_lo, row);
@@ -525,7 +537,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_tc_kernel(const __grid_cons
       mbar_init(smem_u32(&misc->w_empty[i]), cl_size);   // one arrive per consumer CTA of the cluster
     }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(smem_u32(&misc->a_ready[s]), 128 * GroupsPerSlot<NSLOTS>::value);
+      mbar_init(smem_u32(&misc->a_ready[s]), 4 * GroupsPerSlot<NSLOTS>::value);   // one arrival per slot-group warp
       mbar_init(smem_u32(&misc->acc_full[s]), 1);
     }
     mbar_fence_init();
@@ -717,7 +729,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_tc2_kernel(const __grid_con
       mbar_init(smem_u32(&misc->w_empty[i]), 1);
     }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(smem_u32(&misc->a_ready[s]), 256 * GroupsPerSlot<NSLOTS>::value);   // every slot-group thread of both CTAs
+      mbar_init(smem_u32(&misc->a_ready[s]), 8 * GroupsPerSlot<NSLOTS>::value);   // every slot-group warp of both CTAs
       mbar_init(smem_u32(&misc->acc_full[s]), 1);
     }
     mbar_fence_init();

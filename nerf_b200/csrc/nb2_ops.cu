@@ -483,6 +483,85 @@ composite_kernel(const float* __restrict__ rgbo, const float* __restrict__ z, co
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// f1  validSampler (training-side ray sampler)          /root/reference/nerf/utils.py:72-94
+//   ray r picks pixel indices[r]; dir = R * ((cx + .5)/fx, (cy + .5)/fy, -1); z = base[s] + U * res; pts = o + dir * z
+// ------------------------------------------------------------------------------------------
+__global__ void valid_sampler_kernel(const float* __restrict__ rgbs, const int64_t* __restrict__ coords,
+                                     const float* __restrict__ cam_tf, const int64_t* __restrict__ indices,
+                                     const float* __restrict__ base_z, const float* __restrict__ jitter, float fx, float fy,
+                                     float resolution, uint64_t seed, int64_t ray_offset, int64_t n_pixels, int64_t n_rays, int P,
+                                     float* __restrict__ pts_out, float* __restrict__ len_out, float* __restrict__ rgb_out,
+                                     float* __restrict__ rays_out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rays * P) return;
+  int64_t r = i / P;
+  int s = (int)(i % P);
+  int64_t pix;
+  if (indices) {
+    pix = indices[r];
+  } else {   // device RNG: stream 2, one draw per ray
+    uint32_t c[4] = {(uint32_t)(ray_offset + r), (uint32_t)((uint64_t)(ray_offset + r) >> 32), 0u, 2u};
+    philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    pix = (int64_t)((((uint64_t)c[0] << 32) | c[1]) % (uint64_t)n_pixels);
+  }
+  float cx = __fdiv_rn(__fadd_rn((float)coords[pix * 2 + 0], 0.5f), fx);
+  float cy = __fdiv_rn(__fadd_rn((float)coords[pix * 2 + 1], 0.5f), fy);
+  float d[3], o[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    float r0 = __ldg(cam_tf + k * 4 + 0), r1 = __ldg(cam_tf + k * 4 + 1), r2 = __ldg(cam_tf + k * 4 + 2);
+    o[k] = __ldg(cam_tf + k * 4 + 3);
+    d[k] = __fadd_rn(__fadd_rn(__fmul_rn(cx, r0), __fmul_rn(cy, r1)), __fmul_rn(-1.f, r2));
+  }
+  float j = jitter ? jitter[i] : philox_uniform(seed, (uint64_t)(ray_offset + r), (uint32_t)s, 0u);
+  float z = __fadd_rn(__ldg(base_z + s), __fmul_rn(j, resolution));
+  len_out[i] = z;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) pts_out[i * 3 + k] = __fadd_rn(o[k], __fmul_rn(d[k], z));
+  if (s == 0) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      rgb_out[r * 3 + k] = rgbs[pix * 3 + k];
+      rays_out[r * 6 + k] = o[k];
+      rays_out[r * 6 + 3 + k] = d[k];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// f1  getBounds (proposal-loss bounds)                 /root/reference/nerf/addtional.py:14-18
+//   sat = [0, cumsum(w)]; out[r, j] = sat[inds[r, j+1] + 1] - sat[inds[r, j]]
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32 * kWarpsPerBlock)
+get_bounds_kernel(const float* __restrict__ w, const int64_t* __restrict__ inds, int64_t n_rays, int P, int K,
+                  float* __restrict__ out) {
+  __shared__ float sat[kWarpsPerBlock][kMaxSamples + 1];
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int64_t r = (int64_t)blockIdx.x * kWarpsPerBlock + warp;
+  if (r >= n_rays) return;
+  double carry = 0.0;
+  if (lane == 0) sat[warp][0] = 0.f;
+  for (int base = 0; base < P; base += 32) {      // torch.cumsum on fp32 == fp64 running sum rounded per element
+    int i = base + lane;
+    double v = (i < P) ? (double)w[r * P + i] : 0.0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      double t = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += t;
+    }
+    if (i < P) sat[warp][i + 1] = (float)(carry + v);
+    carry += __shfl_sync(0xffffffffu, v, 31);
+  }
+  __syncwarp();
+  for (int j = lane; j < K - 1; j += 32) {
+    int64_t st = inds[r * K + j], en = inds[r * K + j + 1] + 1;
+    st = st < 0 ? 0 : (st > P ? P : st);
+    en = en < 0 ? 0 : (en > P ? P : en);
+    out[r * (K - 1) + j] = __fsub_rn(sat[warp][en], sat[warp][st]);
+  }
+}
+
 }  // namespace nb2
 
 // ==========================================================================================
@@ -672,6 +751,33 @@ extern "C" int nb2_composite(nb2_handle* h, const float* rgbo, const float* z, c
   if (n_rays == 0) return NB2_OK;
   composite_kernel<<<grid_for(n_rays, kWarpsPerBlock), 32 * kWarpsPerBlock, 0, (cudaStream_t)stream>>>(
       rgbo, z, dirs, dir_stride, n_rays, n_samples, flags, near_t, far_t, rgb_out, weights_out, depth_out, acc_out);
+  NB2_LAUNCH_CHECK(h);
+  return NB2_OK;
+}
+
+extern "C" int nb2_valid_sampler(nb2_handle* h, const float* rgbs, const int64_t* coords, const float* cam_tf,
+                                 const int64_t* indices, const float* base_z, const float* jitter, float focal_x, float focal_y,
+                                 float resolution, uint64_t seed, int64_t ray_offset, int64_t n_pixels, int64_t n_rays,
+                                 int n_samples, float* pts_out, float* lengths_out, float* rgb_out, float* rays_out, void* stream) {
+  NB2_H(h);
+  if (n_rays == 0) return NB2_OK;
+  NB2_CHECK_ARG(rgbs && coords && cam_tf && base_z && pts_out && lengths_out && rgb_out && rays_out, "valid_sampler: null pointer");
+  NB2_CHECK_ARG(n_pixels > 0 && n_samples > 0 && focal_x != 0.f && focal_y != 0.f, "valid_sampler: bad arguments");
+  valid_sampler_kernel<<<grid_for(n_rays * n_samples, 256), 256, 0, (cudaStream_t)stream>>>(
+      rgbs, coords, cam_tf, indices, base_z, jitter, focal_x, focal_y, resolution, seed, ray_offset, n_pixels, n_rays, n_samples,
+      pts_out, lengths_out, rgb_out, rays_out);
+  NB2_LAUNCH_CHECK(h);
+  return NB2_OK;
+}
+
+extern "C" int nb2_get_bounds(nb2_handle* h, const float* weights, const int64_t* inds, int64_t n_rays, int n_samples,
+                              int n_inds, float* out, void* stream) {
+  NB2_H(h);
+  if (n_rays == 0) return NB2_OK;
+  NB2_CHECK_ARG(weights && inds && out, "get_bounds: null pointer");
+  NB2_CHECK_ARG(n_samples >= 1 && n_samples <= kMaxSamples && n_inds >= 2, "get_bounds: n_samples must be in [1,%d], n_inds >= 2", kMaxSamples);
+  get_bounds_kernel<<<grid_for(n_rays, kWarpsPerBlock), 32 * kWarpsPerBlock, 0, (cudaStream_t)stream>>>(weights, inds, n_rays,
+                                                                                                     n_samples, n_inds, out);
   NB2_LAUNCH_CHECK(h);
   return NB2_OK;
 }

@@ -11,6 +11,7 @@ struct RowIn {
   float z;      // depth along the ray (0 for explicit points)
   int64_t ray;  // ray index (row / P), or the row itself for explicit points
   int s;        // sample index on the ray
+  const float* enc;  // externally encoded position features of this row, or nullptr
   bool valid;
 };
 
@@ -20,11 +21,13 @@ __device__ __forceinline__ RowIn load_row(const MlpIo& io, int64_t row) {
   r.z = 0.f;
   r.ray = row;
   r.s = 0;
+  r.enc = nullptr;
 #pragma unroll
   for (int k = 0; k < 3; ++k) { r.p[k] = 0.f; r.d[k] = 0.f; }
   if (!r.valid) return r;
   if (io.in_mode == 0) {
     const float* src = io.pts + row * io.pts_stride;
+    if (io.enc) r.enc = io.enc + row * (int64_t)(6 * io.P);   // io.P carries pos_levels in this mode (see nb2_api.cu)
 #pragma unroll
     for (int k = 0; k < 3; ++k) r.p[k] = __ldg(src + k);
     if (io.pts_stride >= 6) {
@@ -62,11 +65,12 @@ __device__ __forceinline__ void normalize_dir(const float d[3], float out[3]) {
 
 // Column c of the encoded vector [x(3), sin(2^0 x)(3), cos(2^0 x)(3), sin(2^1 x)(3), ...]
 // (cat_origin = True; nerf_helper.py:38-48 + mip_model.py:50-52).  Returns 0 past 3 + 6*levels.
-__device__ __forceinline__ float enc_column(const float x[3], int c, int levels) {
+__device__ __forceinline__ float enc_column(const float x[3], int c, int levels, const float* ext = nullptr) {
   if (c < 3) return x[c];
   int j = c - 3;
   int l = j / 6, w = j % 6;
   if (l >= levels) return 0.f;
+  if (ext) return __ldg(ext + j);
   float a = x[w % 3] * exp2f((float)l);
   return (w < 3) ? sinf(a) : cosf(a);
 }

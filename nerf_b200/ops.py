@@ -187,6 +187,39 @@ def coarse_fine_merge(rays, c_z, f_z):
     return pts, z
 
 
+# ---- f1: training-side callers (forward only) -------------------------------------------------------
+def valid_sampler(rgbs, coords, cam_tf, ray_num, point_num, focal_x, focal_y, near, far, indices=None, jitter=None, seed=None):
+    rgbs, cam_tf = f32(rgbs), f32(cam_tf[:3, :4])
+    coords = coords.to(torch.int64).contiguous()
+    dev = rgbs.device
+    resolution = (far - near) / point_num
+    base_z = torch.linspace(near, far - resolution, point_num).to(dev)              # utils.py:88
+    if indices is not None:
+        indices = indices.to(device=dev, dtype=torch.int64).contiguous()
+    if jitter is not None:
+        jitter = f32(jitter).view(ray_num, point_num)
+    if seed is None:
+        seed = _seed_from_torch() if (indices is None or jitter is None) else 0
+    pts = torch.empty((ray_num, point_num, 3), dtype=torch.float32, device=dev)
+    lengths = torch.empty((ray_num, point_num), dtype=torch.float32, device=dev)
+    rgb = torch.empty((ray_num, 3), dtype=torch.float32, device=dev)
+    rays = torch.empty((ray_num, 6), dtype=torch.float32, device=dev)
+    check(load().nb2_valid_sampler(handle(dev), ptr(rgbs), ptr(coords), ptr(cam_tf), ptr(indices), ptr(base_z), ptr(jitter),
+                                   float(focal_x), float(focal_y), float(resolution), seed, 0, coords.shape[0], ray_num, point_num,
+                                   ptr(pts), ptr(lengths), ptr(rgb), ptr(rays), stream_ptr()))
+    return pts, lengths, rgb, rays
+
+
+def get_bounds(weights, inds):
+    weights = f32(weights)
+    inds = inds.to(torch.int64).contiguous()
+    R, P = weights.shape
+    K = inds.shape[1]
+    out = torch.empty((R, K - 1), dtype=torch.float32, device=weights.device)
+    check(load().nb2_get_bounds(handle(weights.device), ptr(weights), ptr(inds), R, P, K, ptr(out), stream_ptr()))
+    return out
+
+
 # ---- weights / MLP --------------------------------------------------------------------------------
 def pack_weights(net_id, weights, biases, pos_levels, dir_levels, hidden, device=None):
     """weights/biases: lists of fp32 CUDA tensors in reference state_dict order."""
@@ -207,6 +240,18 @@ def mlp_forward(net_id, pts, precision=None):
     dev = pts.device
     out = torch.empty((n, 4) if net_id == _lib.NET_NERF else (n,), dtype=torch.float32, device=dev)
     check(load().nb2_mlp_forward(handle(dev), net_id, _prec(precision), ptr(pts), stride, n, ptr(out), stream_ptr()))
+    return out
+
+
+def mlp_forward_encoded(net_id, pts, encoded, precision=None):
+    """Proposal network on externally encoded position features (n, 6 * levels) + raw points (n, >=3)."""
+    pts, encoded = f32(pts), f32(encoded)
+    stride = pts.shape[-1]
+    n = pts.numel() // stride
+    if encoded.numel() % n != 0:
+        raise NB2Error("mlp_forward_encoded: encoded features do not match the number of points")
+    out = torch.empty((n,), dtype=torch.float32, device=pts.device)
+    check(load().nb2_mlp_forward_encoded(handle(pts.device), net_id, _prec(precision), ptr(pts), stride, ptr(encoded), n, ptr(out), stream_ptr()))
     return out
 
 

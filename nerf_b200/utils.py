@@ -26,6 +26,19 @@ def inverseSample(weights, coarse_depth, sample_pnum, sort=False, u=None):
     return z
 
 
+def validSampler(rgbs, coords, cam_tf, ray_num, point_num, focal, near, far, output_samples=True, indices=None, jitter=None):
+    """Training-side ray sampler (reference nerf/utils.py:72-94): random pixels of one image -> rays, true stratified
+    depths and sample points.  `indices` / `jitter` inject the reference's CPU draws (torch.randint / torch.rand)."""
+    if isinstance(focal, Iterable):
+        fx, fy = float(focal[1]), float(focal[0])
+    else:
+        fx = fy = float(focal)
+    pts, lengths, rgb, rays = ops.valid_sampler(rgbs, coords, cam_tf, ray_num, point_num, fx, fy, near, far, indices=indices, jitter=jitter)
+    if output_samples:
+        return pts, lengths, rgb, rays
+    return rgb, rays
+
+
 def fov2Focal(fov, img_size):
     """reference nerf/utils.py:96-105 (including the missing 1/2 for a scalar fov)."""
     if isinstance(fov, Iterable):

@@ -176,9 +176,10 @@ def positional_encoding(x, levels):
 # ----------------------------------------------------------------------------------------------
 # a6  proposal MLP                                             nerf/addtional.py:61-72,88-96
 # ----------------------------------------------------------------------------------------------
-def proposal_forward(sd, pts, pos_levels=10):
-    """pts (..., 3) -> raw density (...)."""
-    h = torch.cat((pts, positional_encoding(pts, pos_levels)), dim=-1)       # cat_origin
+def proposal_forward(sd, pts, pos_levels=10, encoded=None):
+    """pts (..., 3) -> raw density (...).  `encoded` (..., 6L) replaces the sinusoidal features (addtional.py:89-91)."""
+    enc = positional_encoding(pts, pos_levels) if encoded is None else encoded.reshape(*pts.shape[:-1], 6 * pos_levels)
+    h = torch.cat((pts, enc), dim=-1)       # cat_origin
     for key in PROPOSAL_KEYS[:-1]:
         h = F.relu(F.linear(h, sd[key + ".weight"], sd[key + ".bias"]))
     return F.linear(h, sd["layers.8.weight"], sd["layers.8.bias"]).squeeze(-1)
@@ -349,6 +350,28 @@ def ipe_feature(zvals, rays, levels, r):
     damp = torch.exp(-0.5 * (scales ** 2)[None, None, :, None] * diag[:, :, None, :])
     feat = torch.cat((torch.sin(mu_r) * damp, torch.cos(mu_r) * damp), dim=-1)   # (R,C,L,6)
     return feat.reshape(zvals.shape[0], zvals.shape[1] - 1, 6 * levels), mu, mu_t
+
+
+# ----------------------------------------------------------------------------------------------
+# f1  training-side callers                                   nerf/utils.py:72-94, nerf/addtional.py:14-18
+# ----------------------------------------------------------------------------------------------
+def valid_sampler(rgbs, coords, cam_tf, indices, jitter, point_num, focal, near, far):
+    out_rgb = rgbs[indices]
+    sc = coords[indices].to(torch.float32) + 0.5
+    fx, fy = (focal[1], focal[0]) if isinstance(focal, (tuple, list)) else (focal, focal)
+    sc = torch.stack((sc[..., 0] / fx, sc[..., 1] / fy), dim=-1)
+    ray_raw = torch.sum(torch.cat([sc, -torch.ones(sc.shape[0], 1)], dim=-1).unsqueeze(-2) * cam_tf[:, :-1], dim=-1)
+    res = (far - near) / point_num
+    lengths = torch.linspace(near, far - res, point_num) + jitter * res
+    pts = cam_tf[:, -1] + ray_raw[:, None, :] * lengths[:, :, None]
+    rays = torch.cat((cam_tf[:, -1].unsqueeze(0).expand(ray_raw.shape[0], -1), ray_raw), dim=-1)
+    return pts, lengths, out_rgb, rays
+
+
+def get_bounds(weights, inds):
+    starts, ends = inds[:, :-1], inds[:, 1:] + 1
+    sat = torch.cat((torch.zeros(weights.shape[0], 1), torch.cumsum(weights, dim=-1)), dim=-1)
+    return torch.gather(sat, -1, ends) - torch.gather(sat, -1, starts)
 
 
 # ----------------------------------------------------------------------------------------------

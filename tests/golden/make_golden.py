@@ -90,6 +90,16 @@ def inputs_ops():
     return g
 
 
+def inputs_train():
+    """One 40x30 'training image' worth of pixels for validSampler."""
+    Hh, Ww = 30, 40
+    from nerf_b200.utils import pose_spherical
+    rows, cols = torch.meshgrid(torch.arange(Hh), torch.arange(Ww), indexing="ij")
+    coords = torch.stack((cols - Ww // 2, Hh // 2 - rows), dim=-1).reshape(-1, 2)
+    return {"rgbs": det_uniform((Hh * Ww, 3), 61, 0.0, 1.0), "coords": coords, "cam_tf": pose_spherical(-40.0, -30.0, 4.0)[:3, :].contiguous(),
+            "indices": (torch.arange(96) * 37 + 5) % (Hh * Ww), "jitter": det_uniform((96, 64), 62, 0.0, 1.0), "focal": (55.0, 60.0)}
+
+
 def render_case(H, W):
     from nerf_b200.utils import pose_spherical  # same formula as the reference; pure host math
     pose = pose_spherical(30.0, -30.0, 4.0)[:3, :].contiguous()
@@ -143,6 +153,23 @@ def main():
         out["comp_rgb_black"] = rgb2
         f, mu, mu_t = ref.mip_methods.ipe_feature(g["ipe_z"], g["ipe_rays"], 10, 0.01)
         out["ipe_feat"], out["ipe_mu"], out["ipe_mu_t"] = f, mu, mu_t
+
+        # training-side callers: validSampler (utils.py:72-94) with injected randint / rand, getBounds (addtional.py:14-18)
+        import nerf.addtional as addtional
+        vs = inputs_train()
+        real_randint = torch.randint
+        torch.randint = lambda *a, **k: vs["indices"].clone()
+        torch.rand = rq
+        rq.push(vs["jitter"])
+        vp, vl, vrgb, vrays = ref.utils.validSampler(vs["rgbs"], vs["coords"], vs["cam_tf"], vs["indices"].numel(), 64, vs["focal"], 2.0, 6.0, True)
+        torch.rand = rq.real
+        torch.randint = real_randint
+        out["vs_pts"], out["vs_len"], out["vs_rgb"], out["vs_rays"] = vp, vl, vrgb, vrays
+        out["bounds"] = addtional.getBounds(w_blur, bs)
+
+        # integrated positional encoding fed through the proposal network's encoded_pt hook (addtional.py:88-91)
+        prop_ipe = load_sd(ref.ProposalNetwork(10, 256), make_params("proposal", 1, "smooth"))
+        out["prop_fwd_ipe"] = prop_ipe.forward(mu, encoded_pt=f)
 
         for style in ("he", "smooth", "refinit"):
             prop = load_sd(ref.ProposalNetwork(10, 256), make_params("proposal", 1, style))

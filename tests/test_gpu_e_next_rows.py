@@ -1,0 +1,51 @@
+"""GPU: the first 'next' rows of SURVEY §8f, forward only — validSampler, getBounds, and the proposal network's
+encoded_pt hook fed by ipe_feature — against outputs of the unmodified reference (golden)."""
+import pytest
+import torch
+
+import nerf_b200
+from oracle import nerf_oracle as O
+from tests.golden.make_golden import inputs_train
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def test_valid_sampler_matches_reference(golden):
+    vs = inputs_train()
+    pts, lengths, rgb, rays = nerf_b200.validSampler(vs["rgbs"].to(DEV), vs["coords"].to(DEV), vs["cam_tf"].to(DEV), 96, 64, vs["focal"], 2.0, 6.0,
+                                                     True, indices=vs["indices"], jitter=vs["jitter"].to(DEV))
+    assert torch.equal(lengths.cpu(), golden["vs_len"])          # true stratified depths: bit-exact
+    assert torch.equal(rgb.cpu(), golden["vs_rgb"])
+    assert float((rays.cpu() - golden["vs_rays"]).abs().max()) < 1e-6
+    assert float((pts.cpu() - golden["vs_pts"]).abs().max()) < 1e-5
+    # device RNG path: pixels in range, depths stratified
+    p2, l2, c2, r2 = nerf_b200.validSampler(vs["rgbs"].to(DEV), vs["coords"].to(DEV), vs["cam_tf"].to(DEV), 4096, 64, vs["focal"], 2.0, 6.0)
+    res = 4.0 / 64
+    base = torch.linspace(2.0, 6.0 - res, 64, device=DEV)
+    assert bool((l2 >= base).all()) and bool((l2 < base + res + 1e-6).all())
+    assert float(r2[:, :3].std(dim=0).max()) == 0.0 and float(r2[:, 3:].std()) > 0.01
+
+
+def test_get_bounds_matches_reference(golden):
+    out = nerf_b200.getBounds(golden["blur"].to(DEV), golden["inv_below"].to(DEV))
+    assert out.shape == golden["bounds"].shape
+    assert float((out.cpu() - golden["bounds"]).abs().max()) < 1e-6
+    loss = nerf_b200.ProposalLoss()(out, torch.rand_like(out))
+    assert torch.isfinite(loss)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16x3", "bf16"])
+def test_ipe_through_proposal_network(golden, gin, precision):
+    """ipe_feature -> ProposalNetwork.forward(mu, encoded_pt=feat): the reference's (unused) IPE hook, end to end."""
+    prop = nerf_b200.ProposalNetwork(10, 256)
+    prop.load_state_dict(O.make_params("proposal", 1, "smooth"))
+    prop = prop.to(DEV)
+    prop.precision = precision
+    feat, mu, _ = nerf_b200.ipe_feature(gin["ipe_z"].to(DEV), gin["ipe_rays"].to(DEV), 10, 0.01)
+    with torch.no_grad():
+        out = prop.forward(mu, encoded_pt=feat).cpu()
+    ref = golden["prop_fwd_ipe"]
+    tol = {"fp32": 2e-5, "fp16x3": 5e-5, "bf16": 6e-2}[precision]
+    assert out.shape == ref.shape
+    assert float((out - ref).abs().max()) <= tol * max(50.0, float(ref.abs().max())), float((out - ref).abs().max())

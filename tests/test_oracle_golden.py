@@ -175,3 +175,17 @@ def test_philox_known_answers():
     u = O.philox_uniform(0, [0], 4, 0)[0]
     exp = torch.tensor([(x >> 8) / 16777216.0 for x in [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]], dtype=torch.float32)
     assert torch.equal(u, exp)
+
+
+def test_training_side_callers(golden, gin):
+    """validSampler / getBounds / encoded_pt restatements against the reference."""
+    from tests.golden.make_golden import inputs_train
+    vs = inputs_train()
+    pts, lengths, rgb, rays = O.valid_sampler(vs["rgbs"], vs["coords"], vs["cam_tf"], vs["indices"], vs["jitter"], 64, vs["focal"], 2.0, 6.0)
+    assert torch.equal(lengths, golden["vs_len"]) and torch.equal(rgb, golden["vs_rgb"])
+    close(rays, golden["vs_rays"], atol=1e-6)
+    close(pts, golden["vs_pts"], atol=1e-5)
+    close(O.get_bounds(golden["blur"], golden["inv_below"]), golden["bounds"], atol=1e-6)
+    sp = O.make_params("proposal", 1, "smooth")
+    out = O.proposal_forward(sp, golden["ipe_mu"], 10, encoded=golden["ipe_feat"])
+    close(out, golden["prop_fwd_ipe"], rtol=1e-5, atol=1e-4)
