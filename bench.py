@@ -303,7 +303,8 @@ def main():
                 "traffic_unit": "bytes per launch (ncu dram read+write; algorithmic 556 B/ray)",
                 "kernel": "mlp_tc2_kernel (fine: encode + 8x256 MLP + composite; CTA-pair tcgen05)", "kernel_ms": fine_ms,
                 "algorithmic_flop_per_launch": FLOP_NERF_PER_RAY * n_rays, "peak_source": peaks["src"], "mma_passes_per_product": passes,
-                "issued_tensor_tflops": achieved * passes * 528384.0 / 527872.0, "step_share": {"proposal_kernel_ms": kms[0], "resample_kernel_ms": kms[1], "fine_kernel_ms": kms[2]}}
+                "issued_tensor_tflops": achieved * passes * 528384.0 / 527872.0,
+                "frac_issued": achieved * passes * 528384.0 / 527872.0 / peaks["tflops"], "step_share": {"proposal_kernel_ms": kms[0], "resample_kernel_ms": kms[1], "fine_kernel_ms": kms[2]}}
     for mode, m in extras.items():
         m["fine_kernel_frac_of_peak"] = m["fine_kernel_tflops"] / peaks["tflops"]
 
