@@ -234,6 +234,15 @@ int nb2_debug_tc_profile(nb2_handle* h, long long* out_host, int n_ctas);
 int nb2_debug_umma_bench(nb2_handle* h, const void* A_bf16, const void* B_bf16, float* D_out, long long* cycles_out,
                          int mode, int iters, int flags, const void* gsrc_1mb, void* stream);
 
+/* Debug: hardware micro-benchmarks behind the MLP kernel's design numbers (nb2_microbench.cu).
+ * kind 0 / 1: TMEM -> register load / register -> TMEM store bandwidth (a0 = warps 4|8|16, a1 = loads in flight per
+ * wait 1|2|4, a2 = sweeps over the 128 x 512 x 4 B TMEM);  kind 2: L2 -> shared bulk-copy stream of 16 KB tiles that
+ * every CTA reads in the same order (a0 = multicast cluster size 1|2|4|8, a1 = ring stages <= 12, a2 = loads per CTA,
+ * a3 = per-cluster address skew in tiles, a4 = 1: even/odd CTAs read alternate tiles like a CTA pair; src = n_chunks x 16 KB).
+ * out_dev: 3 x int64 per CTA (cycles, bytes, checksum) in device memory; *grid_out = CTAs launched. */
+int nb2_debug_microbench(nb2_handle* h, int kind, int a0, int a1, int a2, int a3, int a4, const void* src, int n_chunks,
+                         long long* out_dev, int* grid_out, void* stream);
+
 /* Device-side self-test of the tcgen05 building blocks: D (128x128 fp32) = A (128x64 bf16,
  * row-major) * B^T (128x64 bf16, row-major), computed by ONE UMMA sequence through the same
  * operand swizzle, descriptors, bulk copy, commit and TMEM read-out the MLP kernel uses.

@@ -11,7 +11,8 @@ import threading
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnerfb200.so")
+# NB2_LIB selects another build of the same library (e.g. libnerfb200_prof.so: role cycle counters compiled in)
+LIB_PATH = os.path.join(_HERE, os.environ.get("NB2_LIB", "libnerfb200.so"))
 
 NET_PROPOSAL, NET_NERF = 0, 1
 PREC_FP32, PREC_FP16X3, PREC_BF16, PREC_FP16, PREC_BF16X3 = 0, 1, 2, 3, 4
@@ -71,6 +72,7 @@ SIGNATURES = {
     "nb2_set_profile_events": (c_int, [c_vp, ctypes.POINTER(c_vp)]),
     "nb2_debug_tc_profile": (c_int, [c_vp, ctypes.POINTER(ctypes.c_longlong), c_int]),
     "nb2_debug_umma_bench": (c_int, [c_vp, c_vp, c_vp, c_f32p, c_vp, c_int, c_int, c_int, c_vp, c_vp]),
+    "nb2_debug_microbench": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_int, c_vp, ctypes.POINTER(c_int), c_vp]),
     "nb2_selftest_umma": (c_int, [c_vp, c_vp, c_vp, c_vp, c_f32p, c_vp]),
 }
 

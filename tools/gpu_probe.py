@@ -122,6 +122,38 @@ def stage_roles(precision, H=400):
         print(f"   {n:16s} {med[i]:14.0f}   per-iter {med[i] / max(med[11], 1):12.0f}")
 
 
+def stage_microbench():
+    """TMEM load/store bandwidth and the L2 -> shared weight-stream ceiling (nb2_microbench.cu)."""
+    import ctypes
+    lib, h = _lib.load(), _lib.handle()
+    out = torch.zeros(3 * 256, dtype=torch.int64, device=DEV)
+    grid = ctypes.c_int(0)
+
+    def run(kind, a0, a1, a2, a3=0, a4=0, src=None, n_chunks=0):
+        out.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.check(lib.nb2_debug_microbench(h, kind, a0, a1, a2, a3, a4, _lib.ptr(src) if src is not None else None, n_chunks,
+                                            _lib.ptr(out), ctypes.byref(grid), _lib.stream_ptr()))
+        e1.record()
+        torch.cuda.synchronize()
+        o = out.cpu().view(-1, 3)[:grid.value]
+        cyc, byt = o[:, 0].double(), o[:, 1].double()
+        return float((byt / cyc).median()), float((byt / cyc).min()), float(byt.sum()) / (e0.elapsed_time(e1) * 1e-3) / 1e12, grid.value
+
+    for kind, name in ((0, "LDTM"), (1, "STTM")):
+        for warps, batch in ((4, 1), (4, 2), (4, 4), (8, 1), (8, 2), (8, 4), (16, 1), (16, 2)):
+            run(kind, warps, batch, 50)
+            med, mn, tbs, g = run(kind, warps, batch, 400)
+            print(f"MICRO {name} warps={warps:2d} in_flight={batch}: {med:7.1f} B/cycle/SM (min {mn:.1f}); 128x256 fp32 accumulator = {131072 / med:6.0f} cycles")
+    src = torch.randint(0, 255, (256 * 16384,), dtype=torch.uint8, device=DEV)
+    for cl, stages, skew, pairlike in ((1, 4, 0, 0), (1, 4, 0, 1), (1, 8, 0, 1), (1, 12, 0, 1), (1, 4, 7, 0), (1, 12, 7, 0),
+                                       (2, 4, 0, 0), (2, 8, 0, 0), (4, 4, 0, 0), (4, 8, 0, 0), (4, 12, 0, 0), (8, 4, 0, 0), (8, 8, 0, 0), (8, 12, 0, 0)):
+        run(2, cl, stages, 200, skew, pairlike, src, 256)
+        med, mn, tbs, g = run(2, cl, stages, 4000, skew, pairlike, src, 256)
+        print(f"MICRO L2STREAM cluster={cl} stages={stages:2d} skew={skew} pairlike={pairlike} grid={g}: {med:6.1f} B/cycle/SM (min {mn:.1f}), {tbs:5.2f} TB/s aggregate into shared memory")
+
+
 if __name__ == "__main__":
     stage = sys.argv[1]
     print("== stage", stage, sys.argv[2:], "on", torch.cuda.get_device_name(0))
@@ -129,6 +161,8 @@ if __name__ == "__main__":
         stage_selftest()
     elif stage == "mlp":
         stage_mlp(sys.argv[2], sys.argv[3], int(sys.argv[4]) if len(sys.argv) > 4 else 1000)
+    elif stage == "microbench":
+        stage_microbench()
     elif stage == "ummabench":
         stage_ummabench()
     elif stage == "roles":
