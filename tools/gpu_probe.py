@@ -66,7 +66,7 @@ def stage_time(precision, H=400):
         dt = time.time() - t0
         print(f"render {H}x{H} {precision}: {dt * 1e3:.2f} ms  {H * H / dt / 1e6:.3f} Mrays/s")
     img = nerf_b200.render_image(net, prop, pose, (H, H), focal, 2.0, 6.0, 128, white_bkg=True, precision=precision, seed=1)["rgb"]
-    print(f"VARIANT cluster={os.environ.get('NB2_TC_CLUSTER','dflt')} lockstep={os.environ.get('NB2_TC_LOCKSTEP','dflt')} {precision} "
+    print(f"VARIANT nhalf={os.environ.get('NB2_TC_NHALF','dflt')} cluster={os.environ.get('NB2_TC_CLUSTER','dflt')} lockstep={os.environ.get('NB2_TC_LOCKSTEP','dflt')} {precision} "
           f"ms={dt * 1e3:.2f} checksum={float(img.double().sum()):.6f} nan={int(torch.isnan(img).sum())}")
 
 
