@@ -15,8 +15,11 @@
 //     other chunks when the rest is.  Exposed per layer: one store + fence + arrive, instead of the whole epilogue.
 //   * the next tile's encoding and the direction encoding are computed in the windows where a slot group would
 //     otherwise spin on an accumulator barrier, and are stored when their tile is free.
-// Biases of layers without an encoding K chunk are added in fp32 by the epilogue (no bias chunk: 20 % fewer weight
-// bytes per layer), the others still ride on the tensor core through encoding column 63.
+// Biases ride on the tensor core as in mlp_tc2_kernel (a first version added them in the epilogue to save the bias
+// chunks' weight bytes: 128 dependent L1 loads per thread and layer made the epilogue 3x slower).
+//   * TWO threads issue MMAs (leader CTA, warps 1 and 3): an N = 128 instruction occupies the tensor pipe for 64 cycles,
+//     but one thread sustains only one tcgen05.mma per ~110 cycles.  Single pass: one issuer per resident tile;
+//     split: one issuer per accumulator (main / correction), so no accumulator is ever written from two threads.
 // Roles, operand layouts, weight image, precisions and the last-layer epilogues are those of mlp_tc2_kernel.
 #include <stdlib.h>
 
@@ -31,8 +34,9 @@ constexpr int kStageBytes3 = kTileBytes / 2;
 // Per-layer issue plan (host-built, lives in the kernel parameters): K chunks in issue order — first those reading
 // H chunks 0-1 (available early), then the rest — without the bias-only chunk.
 struct Tc3Layer {
-  unsigned char n, n_early, bias_epi, pad;
-  unsigned char k[4 + 4];
+  unsigned char n, n_early, pad0, pad1;
+  unsigned char k[6];     // K chunk (index into TcLayer::a_src / the layer's weight tiles) per issue position
+  unsigned char ks0[6];   // first 16-wide k-step of that chunk (3 for the bias-only chunk)
 };
 struct Tc3Params {
   TcParams base;
@@ -54,7 +58,7 @@ static_assert(sizeof(Tc3Misc) <= 1024, "misc region too small");
 
 // ---- one 32-column block of an N-half: fp32 accumulator (+ correction) -> (+ bias) -> activation -> packed 16-bit ------
 template <int EPI, bool SPLIT, bool F16>
-__device__ __forceinline__ void block_pack(uint32_t (&m)[32], const uint32_t (&c)[32], int col, const float* __restrict__ bias,
+__device__ __forceinline__ void block_pack(uint32_t (&m)[32], const uint32_t (&c)[32], int col,
                                            const float* __restrict__ head, float& sg, uint32_t (&hi)[16], uint32_t (&lo)[16]) {
   constexpr bool kRelu = (EPI != EPI_LINEAR);
   constexpr bool kSigma = (EPI == EPI_RELU_SIGMA || EPI == EPI_SIGMA_OUT);
@@ -65,10 +69,6 @@ __device__ __forceinline__ void block_pack(uint32_t (&m)[32], const uint32_t (&c
     for (int i = 0; i < 4; ++i) {
       v[i] = __uint_as_float(m[4 * q + i]);
       if (SPLIT) v[i] += __uint_as_float(c[4 * q + i]);
-    }
-    if (bias != nullptr) {
-      const float4 b = __ldg(reinterpret_cast<const float4*>(bias + col + 4 * q));
-      v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
     }
     if (kRelu && (SPLIT || kSigma)) {
 #pragma unroll
@@ -114,8 +114,7 @@ struct HeldHalf {
 
 // Drain W columns starting at absolute column c0 and keep the packed result (half 0: off the critical path).
 template <int EPI, bool SPLIT, bool F16, int W>
-__device__ __forceinline__ void drain_hold(uint32_t acc, int c0, const float* bias, const float* head, float& sg,
-                                           HeldHalf<SPLIT, W>& held) {
+__device__ __forceinline__ void drain_hold(uint32_t acc, int c0, const float* head, float& sg, HeldHalf<SPLIT, W>& held) {
   constexpr int NB = W / 32;
   if (SPLIT) {
 #pragma unroll
@@ -124,7 +123,7 @@ __device__ __forceinline__ void drain_hold(uint32_t acc, int c0, const float* bi
       tmem_ld32(acc + c0 + 32 * b, m);
       tmem_ld32(acc + 256 + c0 + 32 * b, c);
       tmem_ld_wait();
-      block_pack<EPI, SPLIT, F16>(m, c, c0 + 32 * b, bias, head, sg, held.hi[b], held.lo[b]);
+      block_pack<EPI, SPLIT, F16>(m, c, c0 + 32 * b, head, sg, held.hi[b], held.lo[b]);
     }
   } else {
 #pragma unroll
@@ -133,8 +132,8 @@ __device__ __forceinline__ void drain_hold(uint32_t acc, int c0, const float* bi
       tmem_ld32(acc + c0 + 32 * b, m0);
       tmem_ld32(acc + c0 + 32 * b + 32, m1);
       tmem_ld_wait();
-      block_pack<EPI, SPLIT, F16>(m0, m0, c0 + 32 * b, bias, head, sg, held.hi[b], held.lo[0]);
-      block_pack<EPI, SPLIT, F16>(m1, m1, c0 + 32 * b + 32, bias, head, sg, held.hi[b + 1], held.lo[0]);
+      block_pack<EPI, SPLIT, F16>(m0, m0, c0 + 32 * b, head, sg, held.hi[b], held.lo[0]);
+      block_pack<EPI, SPLIT, F16>(m1, m1, c0 + 32 * b + 32, head, sg, held.hi[b + 1], held.lo[0]);
     }
   }
 }
@@ -163,7 +162,7 @@ __device__ __forceinline__ void slot_group_run3(const Tc3Params& q, Tc3Misc* mis
   const uint32_t full0 = smem_u32(&misc->acc_full[0]), full1 = smem_u32(&misc->acc_full[1]);
   float* scratch = &misc->scratch[s][0][0];
   uint32_t ph0 = 0, ph1 = 0;
-  long long t_wacc = 0, t_enc = 0, t_last = 0, t0e = NB2_CLK();
+  long long t_wacc0 = 0, t_wacc1 = 0, t_h0 = 0, t_st0 = 0, t_h1 = 0, t_enc = 0, t_last = 0, t0e = NB2_CLK();
 
   // one arrival per warp (every lane fenced its own shared-memory writes / TMEM reads before the __syncwarp)
   auto arrive = [&](uint32_t bar) {
@@ -177,13 +176,13 @@ __device__ __forceinline__ void slot_group_run3(const Tc3Params& q, Tc3Misc* mis
     tc_fence_before();
     arrive(bar);
   };
-  auto wait_acc = [&](uint32_t bar, uint32_t& ph) {
+  auto wait_acc = [&](uint32_t bar, uint32_t& ph, long long& t) {
     const long long c0 = NB2_CLK();
     mbar_wait(bar, ph);
     ph ^= 1u;
     __syncwarp();
     tc_fence_after();
-    t_wacc += NB2_CLK() - c0;
+    t += NB2_CLK() - c0;
   };
 
   auto tile_of = [&](int64_t it) { return (it * gridDim.x + blockIdx.x) * NSLOTS + s; };
@@ -218,11 +217,10 @@ __device__ __forceinline__ void slot_group_run3(const Tc3Params& q, Tc3Misc* mis
     float sigma = 0.f;
     for (int l = 0; l < net.n_layers; ++l) {
       const int epi = net.layer[l].epi;
-      const float* bias = q.plan[l].bias_epi ? p.bias + net.layer[l].bias_off : nullptr;
 
       if (epi == EPI_RGB) {
         // ---- rgb_layer (N = 128: half 0 only): t = relu(acc), rgb = sigmoid(W1 t + b1), then alpha compositing ----------
-        wait_acc(full0, ph0);
+        wait_acc(full0, ph0, t_wacc0);
         const long long ce = NB2_CLK();
         float c0 = 0.f, c1 = 0.f, c2 = 0.f;
         bool continue_flag = true;
@@ -327,18 +325,22 @@ __device__ __forceinline__ void slot_group_run3(const Tc3Params& q, Tc3Misc* mis
       // ---- 256-wide layers: half 0 is drained into registers while half 1 accumulates ---------------------------------
       const int c_h0 = W * g, c_h1 = 128 + W * g;   // this thread's columns of each half
       HeldHalf<SPLIT, W> held;
-      wait_acc(full0, ph0);
-      if (epi == EPI_RELU) drain_hold<EPI_RELU, SPLIT, F16, W>(acc, c_h0, bias, p.head, sigma, held);
-      else if (epi == EPI_LINEAR) drain_hold<EPI_LINEAR, SPLIT, F16, W>(acc, c_h0, bias, p.head, sigma, held);
-      else if (epi == EPI_RELU_SIGMA) drain_hold<EPI_RELU_SIGMA, SPLIT, F16, W>(acc, c_h0, bias, p.head, sigma, held);
-      else drain_hold<EPI_SIGMA_OUT, SPLIT, F16, W>(acc, c_h0, bias, p.head, sigma, held);
+      wait_acc(full0, ph0, t_wacc0);
+      const long long ch0 = NB2_CLK();
+      if (epi == EPI_RELU) drain_hold<EPI_RELU, SPLIT, F16, W>(acc, c_h0, p.head, sigma, held);
+      else if (epi == EPI_LINEAR) drain_hold<EPI_LINEAR, SPLIT, F16, W>(acc, c_h0, p.head, sigma, held);
+      else if (epi == EPI_RELU_SIGMA) drain_hold<EPI_RELU_SIGMA, SPLIT, F16, W>(acc, c_h0, p.head, sigma, held);
+      else drain_hold<EPI_SIGMA_OUT, SPLIT, F16, W>(acc, c_h0, p.head, sigma, held);
 
-      wait_acc(full1, ph1);
+      t_h0 += NB2_CLK() - ch0;
+      wait_acc(full1, ph1, t_wacc1);
+      const long long cs0 = NB2_CLK();
       if (epi != EPI_SIGMA_OUT) {
         // all MMAs of this layer are complete: the activation tiles may be rewritten.  Half 0 first (K chunks 0-1).
 #pragma unroll
         for (int b = 0; b < W / 32; ++b) store_block<SPLIT>(slot_base, lo_off, row, c_h0 + 32 * b, held.hi[b], held.lo[SPLIT ? b : 0]);
         publish(ready0);
+        t_st0 += NB2_CLK() - cs0;
         // half 1 -> K chunks 2-3
 #pragma unroll
         for (int b = 0; b < W / 32; b += (SPLIT ? 1 : 2)) {
@@ -348,9 +350,9 @@ __device__ __forceinline__ void slot_group_run3(const Tc3Params& q, Tc3Misc* mis
             tmem_ld32(acc + c_h1 + 32 * b, m);
             tmem_ld32(acc + 256 + c_h1 + 32 * b, c);
             tmem_ld_wait();
-            if (epi == EPI_RELU) block_pack<EPI_RELU, SPLIT, F16>(m, c, c_h1 + 32 * b, bias, p.head, sigma, hi0, lo0);
-            else if (epi == EPI_LINEAR) block_pack<EPI_LINEAR, SPLIT, F16>(m, c, c_h1 + 32 * b, bias, p.head, sigma, hi0, lo0);
-            else block_pack<EPI_RELU_SIGMA, SPLIT, F16>(m, c, c_h1 + 32 * b, bias, p.head, sigma, hi0, lo0);
+            if (epi == EPI_RELU) block_pack<EPI_RELU, SPLIT, F16>(m, c, c_h1 + 32 * b, p.head, sigma, hi0, lo0);
+            else if (epi == EPI_LINEAR) block_pack<EPI_LINEAR, SPLIT, F16>(m, c, c_h1 + 32 * b, p.head, sigma, hi0, lo0);
+            else block_pack<EPI_RELU_SIGMA, SPLIT, F16>(m, c, c_h1 + 32 * b, p.head, sigma, hi0, lo0);
             store_block<SPLIT>(slot_base, lo_off, row, c_h1 + 32 * b, hi0, lo0);
           } else {
             uint32_t m0[32], m1[32], hi1[16];
@@ -358,14 +360,14 @@ __device__ __forceinline__ void slot_group_run3(const Tc3Params& q, Tc3Misc* mis
             tmem_ld32(acc + c_h1 + 32 * b + 32, m1);
             tmem_ld_wait();
             if (epi == EPI_RELU) {
-              block_pack<EPI_RELU, SPLIT, F16>(m0, m0, c_h1 + 32 * b, bias, p.head, sigma, hi0, lo0);
-              block_pack<EPI_RELU, SPLIT, F16>(m1, m1, c_h1 + 32 * b + 32, bias, p.head, sigma, hi1, lo0);
+              block_pack<EPI_RELU, SPLIT, F16>(m0, m0, c_h1 + 32 * b, p.head, sigma, hi0, lo0);
+              block_pack<EPI_RELU, SPLIT, F16>(m1, m1, c_h1 + 32 * b + 32, p.head, sigma, hi1, lo0);
             } else if (epi == EPI_LINEAR) {
-              block_pack<EPI_LINEAR, SPLIT, F16>(m0, m0, c_h1 + 32 * b, bias, p.head, sigma, hi0, lo0);
-              block_pack<EPI_LINEAR, SPLIT, F16>(m1, m1, c_h1 + 32 * b + 32, bias, p.head, sigma, hi1, lo0);
+              block_pack<EPI_LINEAR, SPLIT, F16>(m0, m0, c_h1 + 32 * b, p.head, sigma, hi0, lo0);
+              block_pack<EPI_LINEAR, SPLIT, F16>(m1, m1, c_h1 + 32 * b + 32, p.head, sigma, hi1, lo0);
             } else {
-              block_pack<EPI_RELU_SIGMA, SPLIT, F16>(m0, m0, c_h1 + 32 * b, bias, p.head, sigma, hi0, lo0);
-              block_pack<EPI_RELU_SIGMA, SPLIT, F16>(m1, m1, c_h1 + 32 * b + 32, bias, p.head, sigma, hi1, lo0);
+              block_pack<EPI_RELU_SIGMA, SPLIT, F16>(m0, m0, c_h1 + 32 * b, p.head, sigma, hi0, lo0);
+              block_pack<EPI_RELU_SIGMA, SPLIT, F16>(m1, m1, c_h1 + 32 * b + 32, p.head, sigma, hi1, lo0);
             }
             store_block<SPLIT>(slot_base, lo_off, row, c_h1 + 32 * b, hi0, lo0);
             store_block<SPLIT>(slot_base, lo_off, row, c_h1 + 32 * b + 32, hi1, lo0);
@@ -381,7 +383,7 @@ __device__ __forceinline__ void slot_group_run3(const Tc3Params& q, Tc3Misc* mis
           tmem_ld32(acc + c_h1 + 32 * b, m);
           if (SPLIT) tmem_ld32(acc + 256 + c_h1 + 32 * b, c);
           tmem_ld_wait();
-          block_pack<EPI_SIGMA_OUT, SPLIT, F16>(m, SPLIT ? c : m, c_h1 + 32 * b, bias, p.head, sigma, hi0, lo0);
+          block_pack<EPI_SIGMA_OUT, SPLIT, F16>(m, SPLIT ? c : m, c_h1 + 32 * b, p.head, sigma, hi0, lo0);
         }
         if (g == 0) sigma += __ldg(p.head + kHeadSigmaB);
         if (EW == 2) {
@@ -400,6 +402,7 @@ __device__ __forceinline__ void slot_group_run3(const Tc3Params& q, Tc3Misc* mis
 
       // ---- work that fits into the wait for the next layer's half 0 -----------------------------------------------------
       const long long cw = NB2_CLK();
+      t_h1 += cw - cs0;
       if (has_next && l == 0) enc_phase(in_next, 0);
       if (has_next && l == 1 && EW == 1) enc_phase(in_next, 1);
       if (l == q.dir_layer && g == 0) {
@@ -415,8 +418,94 @@ __device__ __forceinline__ void slot_group_run3(const Tc3Params& q, Tc3Misc* mis
   }
   if (NB2_PROF_ON && threadIdx.x == kRolesThreads) {
     long long* o = p.prof + blockIdx.x * 16;
-    o[6] = t_enc; o[7] = t_wacc; o[8] = 0; o[9] = t_last; o[10] = NB2_CLK() - t0e; o[11] = n_iters; o[12] = net.n_layers;
+    o[6] = t_enc; o[7] = t_wacc0; o[8] = t_h0; o[9] = t_last; o[10] = NB2_CLK() - t0e; o[11] = n_iters; o[12] = net.n_layers;
+    o[13] = t_wacc1; o[14] = t_st0; o[15] = t_h1;   // t_h1 includes t_st0 (everything after "half 1 complete")
   }
+}
+
+// ---- MMA issuer (leader CTA; one elected thread per issuing warp) ----------------------------------------------------------
+// ISSUER is a template parameter so that every descriptor stays in uniform registers (a value derived from the warp
+// index is not provably uniform and would cost three R2UR transfers per instruction).
+// Single pass: issuer i owns resident tile i.  Split: issuer 0 owns the main accumulator (hi x Wh), issuer 1 the
+// correction accumulator (lo x Wh, hi x Wl).  Both walk every ring stage and both commit every stage and every N-half
+// (those barriers count two arrivals).
+template <int NSLOTS, bool SPLIT, bool F16, int ISSUER>
+__device__ __forceinline__ void mma_issuer3(const Tc3Params& q, Tc3Misc* misc, uint32_t act_base, uint32_t ring_base,
+                                            uint32_t tmem_base, int64_t n_iters) {
+  using LT = TcLayout<NSLOTS, SPLIT>;
+  const TcParams& p = q.base;
+  const TcNet& net = p.net;
+  constexpr int issuer = ISSUER;
+  uint32_t stage = 0, phase = 0, pr0 = 0, pr1 = 0;
+  long long t_wa = 0, t_ww = 0, t0m = NB2_CLK();
+  const uint32_t ring_lo = umma_desc_lo(ring_base);
+  const uint32_t idesc = umma_idesc_16(256, 128, F16);
+  constexpr uint32_t kLoPart = (uint32_t)(kChunksPerSlot * kTileBytes) >> 4;
+  // single pass: this issuer's tile; split: the only tile
+  const uint32_t act_lo = umma_desc_lo(act_base + (SPLIT ? 0u : (uint32_t)issuer * (uint32_t)LT::kSlotBytes));
+  const uint32_t d_base = tmem_base + (SPLIT ? (uint32_t)(256 * issuer) : (uint32_t)(256 * issuer));
+  auto wait_stage = [&]() {
+    const long long c0 = NB2_CLK();
+    mbar_wait(smem_u32(&misc->w_full[stage]), phase);
+    mbar_wait_cluster(smem_u32(&misc->w_peer[stage]), phase);
+    t_ww += NB2_CLK() - c0;
+    tc_fence_after();
+  };
+  auto release_stage = [&]() {
+    umma2_commit_mcast(smem_u32(&misc->w_empty[stage]), 3);
+    if (++stage == kStages3) { stage = 0; phase ^= 1u; }
+  };
+  auto wait_ready = [&](int which, uint32_t& par) {
+    const long long c0 = NB2_CLK();
+    mbar_wait_cluster(smem_u32(&misc->a_ready[which]), par);
+    par ^= 1u;
+    t_wa += NB2_CLK() - c0;
+    tc_fence_after();
+  };
+  for (int64_t it = 0; it < n_iters; ++it) {
+    for (int l = 0; l < net.n_layers; ++l) {
+      const TcLayer& L = net.layer[l];
+      const Tc3Layer& P = q.plan[l];
+      for (int h = 0; h < L.nc; ++h) {
+        const uint32_t d = d_base + (uint32_t)(128 * h);
+        for (int j = 0; j < P.n; ++j) {
+          if (h == 0 && j == 0) wait_ready(0, pr0);
+          if (h == 0 && j == P.n_early) wait_ready(1, pr1);
+          const int ks0 = P.ks0[j];
+          const uint32_t a_hi = act_lo + (uint32_t)L.a_src[P.k[j]] * (kTileBytes >> 4);
+          wait_stage();
+          const uint32_t w0 = ring_lo + stage * (kStageBytes3 >> 4);
+          // single pass: hi x W;   split issuer 0: hi x Wh -> main;   split issuer 1: lo x Wh -> correction
+          const uint32_t a_op = (SPLIT && issuer == 1) ? a_hi + kLoPart : a_hi;
+          if (ks0 == 0) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              umma2_bf16_ss(d, umma_desc_from_lo(a_op + 2 * ks), umma_desc_from_lo(w0 + 2 * ks), idesc, (uint32_t)((j | ks) != 0));
+          } else {   // bias-only chunk: the one k-step that holds the constant-1 column
+            umma2_bf16_ss(d, umma_desc_from_lo(a_op + 6), umma_desc_from_lo(w0 + 6), idesc, (uint32_t)(j != 0));
+          }
+          release_stage();
+          if (SPLIT) {
+            wait_stage();
+            if (issuer == 1) {
+              const uint32_t wl = ring_lo + stage * (kStageBytes3 >> 4);
+              if (ks0 == 0) {
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)
+                  umma2_bf16_ss(d, umma_desc_from_lo(a_hi + 2 * ks), umma_desc_from_lo(wl + 2 * ks), idesc, 1u);
+              } else {
+                umma2_bf16_ss(d, umma_desc_from_lo(a_hi + 6), umma_desc_from_lo(wl + 6), idesc, 1u);
+              }
+            }
+            release_stage();
+          }
+        }
+        if (h == 0 && P.n_early >= P.n) wait_ready(1, pr1);   // (no late chunks: still consume the second barrier)
+        umma2_commit_mcast(smem_u32(&misc->acc_full[h]), 3);
+      }
+    }
+  }
+  if (NB2_PROF_ON && issuer == 0) { p.prof[blockIdx.x * 16 + 3] = t_wa; p.prof[blockIdx.x * 16 + 4] = t_ww; p.prof[blockIdx.x * 16 + 5] = NB2_CLK() - t0m; }
 }
 
 template <int NSLOTS, bool SPLIT, bool F16>
@@ -442,11 +531,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_tc3_kernel(const __grid_con
     for (int i = 0; i < kStages3; ++i) {
       mbar_init(smem_u32(&misc->w_full[i]), 1);
       mbar_init(smem_u32(&misc->w_peer[i]), 1);
-      mbar_init(smem_u32(&misc->w_empty[i]), 1);
+      mbar_init(smem_u32(&misc->w_empty[i]), 2);    // both MMA issuers release every stage
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&misc->a_ready[i]), 16);   // every slot-group warp of both CTAs
-      mbar_init(smem_u32(&misc->acc_full[i]), 1);
+      mbar_init(smem_u32(&misc->acc_full[i]), 2);   // both MMA issuers commit every N-half
     }
     mbar_fence_init();
   }
@@ -487,9 +576,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_tc3_kernel(const __grid_con
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 || warp == 3) {
     reg_dealloc<kRoleRegs>();
-    if (lane == 0 && rank != 0) {
+    if (lane == 0 && rank != 0 && warp == 1) {
       // =========================== peer: relay "my half has landed" to the leader =====================
       uint32_t stage = 0, phase = 0;
       for (int64_t it = 0; it < n_iters; ++it)
@@ -501,83 +590,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_tc3_kernel(const __grid_con
             if (++stage == kStages3) { stage = 0; phase ^= 1u; }
           }
         }
-    } else if (lane == 0) {
-      // =========================== leader: MMA issuer for the pair ====================================
-      uint32_t stage = 0, phase = 0, pr0 = 0, pr1 = 0;
-      long long t_wa = 0, t_ww = 0, t0m = NB2_CLK();
-      const uint32_t ring_lo = umma_desc_lo(ring_base);
-      const uint32_t idesc = umma_idesc_16(256, 128, F16);
-      const uint32_t act_lo = umma_desc_lo(act_base);
-      constexpr uint32_t kLoPart = (uint32_t)(kChunksPerSlot * kTileBytes) >> 4;
-      auto wait_stage = [&]() {
-        const long long c0 = NB2_CLK();
-        mbar_wait(smem_u32(&misc->w_full[stage]), phase);
-        mbar_wait_cluster(smem_u32(&misc->w_peer[stage]), phase);
-        t_ww += NB2_CLK() - c0;
-        tc_fence_after();
-      };
-      auto release_stage = [&]() {
-        umma2_commit_mcast(smem_u32(&misc->w_empty[stage]), 3);
-        if (++stage == kStages3) { stage = 0; phase ^= 1u; }
-      };
-      for (int64_t it = 0; it < n_iters; ++it) {
-        for (int l = 0; l < net.n_layers; ++l) {
-          const TcLayer& L = net.layer[l];
-          const Tc3Layer& P = q.plan[l];
-          for (int h = 0; h < L.nc; ++h) {
-            const uint32_t d_half = tmem_base + (uint32_t)(128 * h);
-            for (int j = 0; j < P.n; ++j) {
-              if (h == 0 && j == 0) {
-                const long long c0 = NB2_CLK();
-                mbar_wait_cluster(smem_u32(&misc->a_ready[0]), pr0);
-                pr0 ^= 1u;
-                t_wa += NB2_CLK() - c0;
-                tc_fence_after();
-              }
-              if (h == 0 && j == P.n_early) {
-                const long long c0 = NB2_CLK();
-                mbar_wait_cluster(smem_u32(&misc->a_ready[1]), pr1);
-                pr1 ^= 1u;
-                t_wa += NB2_CLK() - c0;
-                tc_fence_after();
-              }
-              const uint32_t a0 = act_lo + (uint32_t)L.a_src[P.k[j]] * (kTileBytes >> 4);   // slot 0, hi part
-              wait_stage();
-              const uint32_t w0 = ring_lo + stage * (kStageBytes3 >> 4);
-#pragma unroll
-              for (int s = 0; s < NSLOTS; ++s) {
-                const uint32_t a_s = a0 + s * (LT::kSlotBytes >> 4);
-                const uint32_t d = d_half + (uint32_t)(s * 256);
-#pragma unroll
-                for (int ks = 0; ks < 4; ++ks)
-                  umma2_bf16_ss(d, umma_desc_from_lo(a_s + 2 * ks), umma_desc_from_lo(w0 + 2 * ks), idesc, (uint32_t)((j | ks) != 0));
-                if (SPLIT) {
-#pragma unroll
-                  for (int ks = 0; ks < 4; ++ks)
-                    umma2_bf16_ss(d + 256, umma_desc_from_lo(a_s + kLoPart + 2 * ks), umma_desc_from_lo(w0 + 2 * ks), idesc,
-                                  (uint32_t)((j | ks) != 0));
-                }
-              }
-              release_stage();
-              if (SPLIT) {
-                wait_stage();
-                const uint32_t wl = ring_lo + stage * (kStageBytes3 >> 4);
-#pragma unroll
-                for (int ks = 0; ks < 4; ++ks)
-                  umma2_bf16_ss(d_half + 256, umma_desc_from_lo(a0 + 2 * ks), umma_desc_from_lo(wl + 2 * ks), idesc, 1u);
-                release_stage();
-              }
-            }
-            if (h == 0 && P.n_early >= P.n) {   // (no late chunks: still consume the second readiness barrier)
-              mbar_wait_cluster(smem_u32(&misc->a_ready[1]), pr1);
-              pr1 ^= 1u;
-              tc_fence_after();
-            }
-            umma2_commit_mcast(smem_u32(&misc->acc_full[h]), 3);
-          }
-        }
-      }
-      if (NB2_PROF_ON) { p.prof[blockIdx.x * 16 + 3] = t_wa; p.prof[blockIdx.x * 16 + 4] = t_ww; p.prof[blockIdx.x * 16 + 5] = NB2_CLK() - t0m; }
+    } else if (lane == 0 && rank == 0) {
+      // =========================== leader: two MMA issuers for the pair =================================
+      if (warp == 1) mma_issuer3<NSLOTS, SPLIT, F16, 0>(q, misc, act_base, ring_base, tmem_base, n_iters);
+      else mma_issuer3<NSLOTS, SPLIT, F16, 1>(q, misc, act_base, ring_base, tmem_base, n_iters);
     }
   } else if (warp >= 4) {
     reg_alloc<kGroupRegs>();
@@ -644,12 +660,11 @@ int launch_mlp_tc3(nb2_handle* h, const TcParams& base, int precision, cudaStrea
     Tc3Layer& P = prm.plan[l];
     int n = 0;
     for (int k = 0; k < L.kc; ++k)
-      if (L.ks0[k] == 0 && L.a_src[k] < 2) P.k[n++] = (unsigned char)k;
+      if (L.a_src[k] < 2) { P.k[n] = (unsigned char)k; P.ks0[n++] = (unsigned char)L.ks0[k]; }
     P.n_early = (unsigned char)n;
     for (int k = 0; k < L.kc; ++k)
-      if (L.ks0[k] == 0 && L.a_src[k] >= 2) P.k[n++] = (unsigned char)k;
+      if (L.a_src[k] >= 2) { P.k[n] = (unsigned char)k; P.ks0[n++] = (unsigned char)L.ks0[k]; }
     P.n = (unsigned char)n;
-    P.bias_epi = (n != L.kc) ? 1 : 0;   // the bias-only chunk is skipped: the epilogue adds the bias
     if (L.epi == EPI_RELU_SIGMA && base.has_dir) prm.dir_layer = l - 1;
     if (L.nc != 2 && L.epi != EPI_RGB) {
       set_error("mlp_forward: layer %d has an unsupported shape for the N-half kernel", l);

@@ -113,8 +113,10 @@ def stage_roles(precision, H=400):
     _lib.check(lib.nb2_debug_tc_profile(h, buf, 148))
     a = np.array(buf[:], dtype=np.int64).reshape(148, 16)
     names = ["str_wait_empty", "str_total", "ring_entries", "mma_wait_A", "mma_wait_W", "mma_total", "g0_encode", "g0_wait_acc",
-             "g0_epi_hidden", "g0_epi_last", "g0_total", "iters", "layers"]
-    print(f"ROLES {precision} cluster={os.environ.get('NB2_TC_CLUSTER','dflt')} lockstep={os.environ.get('NB2_TC_LOCKSTEP','dflt')} (median over CTAs, cycles; last launch = fine kernel)")
+             "g0_epi_hidden", "g0_epi_last", "g0_total", "iters", "layers", "nhalf:wait_acc_h1", "nhalf:store_h0+publish", "nhalf:after_h1_total"]
+    if os.environ.get("NB2_TC_NHALF") == "1":
+        names[6:9] = ["nhalf:window_work", "nhalf:wait_acc_h0", "nhalf:drain_h0"]
+    print(f"ROLES {precision} nhalf={os.environ.get('NB2_TC_NHALF','dflt')} cluster={os.environ.get('NB2_TC_CLUSTER','dflt')} lockstep={os.environ.get('NB2_TC_LOCKSTEP','dflt')} (median over CTAs, cycles; last launch = fine kernel)")
     lead = a[a[:, 5] > 0] if (a[:, 5] > 0).any() else a       # MMA counters exist on issuing CTAs only
     med = np.median(a, axis=0)
     med[3:6] = np.median(lead[:, 3:6], axis=0)
