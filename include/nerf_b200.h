@@ -250,6 +250,11 @@ int nb2_debug_microbench(nb2_handle* h, int kind, int a0, int a1, int a2, int a3
 int nb2_selftest_umma(nb2_handle* h, const void* A_bf16, const void* B_bf16, void* scratch_16k,
                       float* D_out, void* stream);
 
+/* Same product with A written to tensor memory by tcgen05.st and consumed by the A-from-TMEM form of tcgen05.mma
+ * (the operand convention of the split-precision kernel in nb2_mlp_tc4.cu). */
+int nb2_selftest_umma_ts(nb2_handle* h, const void* A_bf16, const void* B_bf16, void* scratch_16k,
+                         float* D_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -74,6 +74,7 @@ SIGNATURES = {
     "nb2_debug_umma_bench": (c_int, [c_vp, c_vp, c_vp, c_f32p, c_vp, c_int, c_int, c_int, c_vp, c_vp]),
     "nb2_debug_microbench": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_int, c_vp, ctypes.POINTER(c_int), c_vp]),
     "nb2_selftest_umma": (c_int, [c_vp, c_vp, c_vp, c_vp, c_f32p, c_vp]),
+    "nb2_selftest_umma_ts": (c_int, [c_vp, c_vp, c_vp, c_vp, c_f32p, c_vp]),
 }
 
 _lib = None

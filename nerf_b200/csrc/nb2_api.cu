@@ -16,6 +16,7 @@ void set_error(const char* fmt, ...) {
 int selftest_umma(nb2_handle* h, const void* A, const void* B, void* Bswz_scratch, float* D, cudaStream_t st);
 int umma_bench(nb2_handle* h, const void* A, const void* B, float* D, long long* cycles, int mode, int iters, int flags,
                const void* gsrc, cudaStream_t st);
+int selftest_umma_ts(nb2_handle* h, const void* A, const void* B, void* Bswz_scratch, float* D, cudaStream_t st);
 int microbench(nb2_handle* h, int kind, int a0, int a1, int a2, int a3, int a4, const void* src, int n_chunks,
                long long* out, int* grid_out, cudaStream_t st);
 }  // namespace nb2
@@ -266,4 +267,10 @@ extern "C" int nb2_debug_microbench(nb2_handle* h, int kind, int a0, int a1, int
                                     long long* out_dev, int* grid_out, void* stream) {
   NB2_CHECK_ARG(h && out_dev && grid_out, "debug_microbench: null pointer");
   return microbench(h, kind, a0, a1, a2, a3, a4, src, n_chunks, out_dev, grid_out, (cudaStream_t)stream);
+}
+
+extern "C" int nb2_selftest_umma_ts(nb2_handle* h, const void* A_bf16, const void* B_bf16, void* scratch_16k, float* D_out,
+                                    void* stream) {
+  NB2_CHECK_ARG(h && A_bf16 && B_bf16 && scratch_16k && D_out, "selftest_umma_ts: null pointer");
+  return selftest_umma_ts(h, A_bf16, B_bf16, scratch_16k, D_out, (cudaStream_t)stream);
 }

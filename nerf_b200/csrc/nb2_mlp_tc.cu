@@ -67,34 +67,34 @@ __device__ __forceinline__ void slot_group_run(const TcParams& p, TcMisc* misc, 
   uint32_t pacc = 0;
   long long t_pe = 0, t_wacc = 0, t_epi = 0, t_last = 0, t0e = NB2_CLK();
 
-  // The encoding of tile it+1 is computed while tile it's first layer runs on the tensor core, and stored (tile
-  // "begun") inside tile it's last epilogue, as soon as its accumulator has been read.
+  // The encoding of tile it+1 is computed in the windows where this group would otherwise spin on the accumulator
+  // barrier (while layers 1 and 2 of tile it run on the tensor core), and stored (tile "begun") inside tile it's last
+  // epilogue, as soon as its accumulator has been read.  Measured before this change (profiles/r01_roles_pair2wg.txt):
+  // 7.8 k (single pass) / 4.4 k (split) exposed cycles per iteration for the encoding, plus the direction encoding.
   auto tile_of = [&](int64_t it) { return (it * gridDim.x + blockIdx.x) * NSLOTS + s; };   // may lie past n_tiles
-  EncRegs<SPLIT, F16, 0, 8 / EW> enc_a;          // column groups of warpgroup 0 (all 8 groups when EW == 1)
-  EncRegs<SPLIT, F16, 8 - 8 / EW, 8 / EW> enc_b; // column groups of warpgroup 1 (EW == 2 only)
-  auto enc_make = [&](const RowIn& r) {
-    if (EW == 1 || half == 0) enc_compute(enc_a, r.p, p.pos_levels, r.valid, r.enc); else enc_compute(enc_b, r.p, p.pos_levels, r.valid, r.enc);
+  EncRegs<SPLIT, F16, 0, 4> enc_a;   // encoding column groups 0-3: warpgroup 0 of a shared tile, or phase 0 of a whole-tile group
+  EncRegs<SPLIT, F16, 4, 4> enc_b;   // groups 4-7:                 warpgroup 1,                  or phase 1
+  auto enc_make = [&](const RowIn& r, int phase) {
+    if (EW == 2 ? (half == 0) : (phase == 0)) enc_compute(enc_a, r.p, p.pos_levels, r.valid, r.enc);
+    else enc_compute(enc_b, r.p, p.pos_levels, r.valid, r.enc);
   };
   auto begin_tile = [&]() {
-    if (EW == 1 || half == 0) enc_store(enc_a, e_hi, e_lo, row); else enc_store(enc_b, e_hi, e_lo, row);
+    if (EW == 1 || half == 0) enc_store(enc_a, e_hi, e_lo, row);
+    if (EW == 1 || half == 1) enc_store(enc_b, e_hi, e_lo, row);
     fence_proxy_async_smem();
     tc_fence_before();
     arrive_a(a_ready);
   };
   RowIn in = load_row(p.io, tile_of(0) * kTileRows + row);
-  enc_make(in);
+  enc_make(in, 0);
+  if (EW == 1) enc_make(in, 1);
   begin_tile();
 
   for (int64_t it = 0; it < n_iters; ++it) {
     const int64_t grow = tile_of(it) * kTileRows + row;
     const bool has_next = (it + 1 < n_iters);
     RowIn in_next = in;
-    const long long cpe = NB2_CLK();
-    if (has_next) {
-      in_next = load_row(p.io, tile_of(it + 1) * kTileRows + row);
-      enc_make(in_next);
-    }
-    t_pe += NB2_CLK() - cpe;
+    if (has_next) in_next = load_row(p.io, tile_of(it + 1) * kTileRows + row);   // consumed after layer 0's epilogue
 
     float sigma = 0.f;
     for (int l = 0; l < net.n_layers; ++l) {
@@ -214,12 +214,6 @@ __device__ __forceinline__ void slot_group_run(const TcParams& p, TcMisc* misc, 
         // (with two groups per tile each keeps the dot product over its own columns; the bias is added once)
         sigma = epilogue_hidden<EPI_RELU_SIGMA, SPLIT, F16>(acc, slot_base, lo_off, row, p.head, cb0, cb1) +
                 (half == 0 ? __ldg(p.head + kHeadSigmaB) : 0.f);
-        if (p.has_dir && half == 0) {
-          // the encoded position is dead after the skip layer: re-use its tile for the direction
-          float rot[3] = {0.f, 0.f, 0.f};
-          if (in.valid) normalize_dir(in.d, rot);
-          write_enc_row<SPLIT, F16, kDirCols, kMaxDirLevels>(e_hi, e_lo, row, rot, p.dir_levels, in.valid);
-        }
       } else {  // EPI_SIGMA_OUT
         sigma = epilogue_hidden<EPI_SIGMA_OUT, SPLIT, F16>(acc, slot_base, lo_off, row, p.head, cb0, cb1) +
                 (half == 0 ? __ldg(p.head + kHeadSigmaB) : 0.f);
@@ -241,6 +235,19 @@ __device__ __forceinline__ void slot_group_run(const TcParams& p, TcMisc* misc, 
         tc_fence_before();
         arrive_a(a_ready);
         t_epi += NB2_CLK() - ce;
+        // ---- work hidden behind the next layer's MMAs -------------------------------------------------------------
+        const long long cpe = NB2_CLK();
+        if (has_next && l == 0) enc_make(in_next, 0);
+        if (has_next && l == 1 && EW == 1) enc_make(in_next, 1);
+        if (l == p.dir_layer && half == 0) {
+          // the encoded position is dead after the skip layer: its tile now takes the encoded direction (columns 0-31;
+          // the bias k-step of the running layer reads columns 48-63 of the same rows, other 16-byte units)
+          float rot[3] = {0.f, 0.f, 0.f};
+          if (in.valid) normalize_dir(in.d, rot);
+          write_enc_row<SPLIT, F16, kDirCols, kMaxDirLevels>(e_hi, e_lo, row, rot, p.dir_levels, in.valid);
+          fence_proxy_async_smem();
+        }
+        t_pe += NB2_CLK() - cpe;
       } else {
         t_last += NB2_CLK() - ce;
       }
@@ -717,10 +724,16 @@ int launch_mlp_tc(nb2_handle* h, int net_id, int precision, const MlpIo& io, cud
   prm.pos_levels = pn.pos_levels;
   prm.dir_levels = pn.dir_levels;
   prm.has_dir = (net_id == NB2_NET_NERF);
+  prm.dir_layer = -1;   // the direction encoding is written after the epilogue of the layer before the density layer
+  for (int l = 0; l < pn.tc.n_layers; ++l)
+    if (prm.has_dir && pn.tc.layer[l].epi == EPI_RELU_SIGMA) prm.dir_layer = l - 1;
   prm.n_tiles = (io.n_rows + kTileRows - 1) / kTileRows;
   prm.prof = h->tc_prof;
+  const bool split = (precision == NB2_PREC_BF16X3 || precision == NB2_PREC_FP16X3);
   // NB2_TC_NHALF = 1: CTA-pair kernel pipelined by output halves (nb2_mlp_tc3.cu)
   if (env_int("NB2_TC_NHALF", 0) != 0) return launch_mlp_tc3(h, prm, precision, st);
+  // NB2_TC_TMEMA = 1: split precisions with the hidden activations in tensor memory (nb2_mlp_tc4.cu)
+  if (split && env_int("NB2_TC_TMEMA", 0) != 0) return launch_mlp_tc4(h, prm, precision, st);
   if (env_int("NB2_TC_PAIR", 1) != 0) {
     const bool ls = env_int("NB2_TC_LOCKSTEP", 1) != 0;
     if (precision == NB2_PREC_BF16) return ls ? launch_tc2_impl<2, false, false, true>(h, prm, st) : launch_tc2_impl<2, false, false, false>(h, prm, st);

@@ -41,7 +41,6 @@ struct Tc3Layer {
 struct Tc3Params {
   TcParams base;
   Tc3Layer plan[kMaxTcLayers];
-  int dir_layer;   // layer after whose epilogue the direction encoding is written (-1: none)
 };
 
 struct Tc3Misc {
@@ -405,7 +404,7 @@ __device__ __forceinline__ void slot_group_run3(const Tc3Params& q, Tc3Misc* mis
       t_h1 += cw - cs0;
       if (has_next && l == 0) enc_phase(in_next, 0);
       if (has_next && l == 1 && EW == 1) enc_phase(in_next, 1);
-      if (l == q.dir_layer && g == 0) {
+      if (l == p.dir_layer && g == 0) {
         // the encoded position is dead after the skip layer: its tile now takes the encoded direction (columns 0-31)
         float rot[3] = {0.f, 0.f, 0.f};
         if (in.valid) normalize_dir(in.d, rot);
@@ -653,7 +652,6 @@ int launch_mlp_tc3(nb2_handle* h, const TcParams& base, int precision, cudaStrea
   Tc3Params prm;
   memset(&prm, 0, sizeof(prm));
   prm.base = base;
-  prm.dir_layer = -1;
   const TcNet& net = base.net;
   for (int l = 0; l < net.n_layers; ++l) {
     const TcLayer& L = net.layer[l];
@@ -665,7 +663,6 @@ int launch_mlp_tc3(nb2_handle* h, const TcParams& base, int precision, cudaStrea
     for (int k = 0; k < L.kc; ++k)
       if (L.a_src[k] >= 2) { P.k[n] = (unsigned char)k; P.ks0[n++] = (unsigned char)L.ks0[k]; }
     P.n = (unsigned char)n;
-    if (L.epi == EPI_RELU_SIGMA && base.has_dir) prm.dir_layer = l - 1;
     if (L.nc != 2 && L.epi != EPI_RGB) {
       set_error("mlp_forward: layer %d has an unsupported shape for the N-half kernel", l);
       return NB2_ERR_UNSUPPORTED;

@@ -27,6 +27,7 @@ struct TcParams {
   const float* bias;
   const float* head;
   int pos_levels, dir_levels, has_dir;
+  int dir_layer;   // layer after whose epilogue the direction encoding replaces the position encoding (-1: none)
   int cluster;   // CTAs per cluster sharing every weight tile through multicast bulk copies (1, 2 or 4)
   int64_t n_tiles;
   long long* prof;   // optional (debug): 16 cycle counters per CTA, see nb2_debug_tc_profile
@@ -66,6 +67,30 @@ struct TcLayout {
   static_assert(kTotal <= 232448, "exceeds 227 KB of shared memory");
 };
 
+// ---- branch-free sin / cos for the fused encoders ------------------------------------------------------------------
+// Three-constant Cody-Waite reduction by pi/2 and the Cephes single-precision minimax polynomials on [-pi/4, pi/4]:
+// max |error| 9.3e-8 against fp64 for |x| <= 3300 (the largest argument is 2^9 * |position|; checked on the host over
+// 2e7 arguments), i.e. the accuracy of sincosf.  Unlike sincosf there is no large-argument branch, so the 30 (position)
+// + 12 (direction) evaluations of a row are straight-line code the scheduler can interleave: the library call made the
+// encoding ~350 cycles per evaluation with two warps per scheduler (profiles/r01_roles_*).
+__device__ __forceinline__ void enc_sincos(float x, float& sn, float& cs) {
+  const int q = __float2int_rn(x * 0.636619772f);
+  const float j = __int2float_rn(q);
+  float t = fmaf(-j, 1.57079601e+00f, x);
+  t = fmaf(-j, 3.13916473e-07f, t);
+  t = fmaf(-j, 5.39030253e-15f, t);
+  const float s = t * t;
+  float ps = fmaf(s, -1.9515295891e-4f, 8.3321608736e-3f);
+  ps = fmaf(ps, s, -1.6666654611e-1f);
+  ps = fmaf(ps * s, t, t);
+  float pc = fmaf(s, 2.443315711809948e-5f, -1.388731625493765e-3f);
+  pc = fmaf(pc, s, 4.166664568298827e-2f);
+  pc = fmaf(pc * s, s, fmaf(s, -0.5f, 1.0f));
+  const float rs = (q & 1) ? pc : ps, rc = (q & 1) ? ps : pc;
+  sn = (q & 2) ? -rs : rs;
+  cs = ((q + 1) & 2) ? -rc : rc;
+}
+
 // ---- writing one row of an A-operand tile ---------------------------------------------------
 // v[0..8) are 8 consecutive columns starting at column `col` (multiple of 8) of row `row`.
 template <bool SPLIT, bool F16>
@@ -103,7 +128,7 @@ __device__ __forceinline__ void write_enc_row(uint32_t tile_hi, uint32_t tile_lo
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
           float s, c;
-          sincosf(x[k] * sc, &s, &c);
+          enc_sincos(x[k] * sc, s, c);
           v[3 + 6 * l + k] = s;
           v[3 + 6 * l + 3 + k] = c;
         }
@@ -151,7 +176,7 @@ __device__ __forceinline__ void enc_compute(EncRegs<SPLIT, F16, G0, NG>& e, cons
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
           float sn, cs;
-          sincosf(x[k] * sc, &sn, &cs);
+          enc_sincos(x[k] * sc, sn, cs);
           v[3 + 6 * l + k] = sn;
           v[3 + 6 * l + 3 + k] = cs;
         }
@@ -266,5 +291,7 @@ __device__ __forceinline__ float epilogue_hidden(uint32_t acc, uint32_t slot_bas
 
 // N-half pipelined CTA-pair kernel (nb2_mlp_tc3.cu)
 int launch_mlp_tc3(nb2_handle* h, const TcParams& base, int precision, cudaStream_t st);
+// split-precision CTA-pair kernel with the hidden activations in tensor memory (nb2_mlp_tc4.cu)
+int launch_mlp_tc4(nb2_handle* h, const TcParams& base, int precision, cudaStream_t st);
 
 }  // namespace nb2

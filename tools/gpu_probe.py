@@ -35,6 +35,22 @@ def stage_selftest():
     np.savez(os.path.join(OUT, "selftest.npz"), A=A.float().numpy(), B=B.float().numpy(), D=D.cpu().numpy())
 
 
+def stage_selftest_ts():
+    """A-from-TMEM operand convention (tcgen05.st -> tcgen05.mma [d], [a], bdesc)."""
+    lib, h = _lib.load(), _lib.handle()
+    g = torch.Generator().manual_seed(1)
+    A = torch.randn(128, 64, generator=g).to(torch.bfloat16).to(DEV)
+    B = torch.randn(128, 64, generator=g).to(torch.bfloat16).to(DEV)
+    scratch = torch.empty(16384, dtype=torch.uint8, device=DEV)
+    D = torch.zeros(128, 128, device=DEV)
+    _lib.check(lib.nb2_selftest_umma_ts(h, _lib.ptr(A), _lib.ptr(B), _lib.ptr(scratch), _lib.ptr(D), _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    ref = A.float() @ B.float().T
+    err = (D - ref).abs()
+    print("selftest_ts max err", float(err.max()), "mean |ref|", float(ref.abs().mean()), "frac bad", float((err > 1e-2).float().mean()))
+    np.savez(os.path.join(OUT, "selftest_ts.npz"), A=A.float().cpu().numpy(), B=B.float().cpu().numpy(), D=D.cpu().numpy())
+
+
 def stage_mlp(kind, precision, n=1000):
     sd = O.make_params(kind, 1 if kind == "proposal" else 2, "he")
     mod = load(nerf_b200.ProposalNetwork(10, 256) if kind == "proposal" else nerf_b200.MipNeRF(10, 4, 256), sd)
@@ -66,7 +82,7 @@ def stage_time(precision, H=400):
         dt = time.time() - t0
         print(f"render {H}x{H} {precision}: {dt * 1e3:.2f} ms  {H * H / dt / 1e6:.3f} Mrays/s")
     img = nerf_b200.render_image(net, prop, pose, (H, H), focal, 2.0, 6.0, 128, white_bkg=True, precision=precision, seed=1)["rgb"]
-    print(f"VARIANT nhalf={os.environ.get('NB2_TC_NHALF','dflt')} cluster={os.environ.get('NB2_TC_CLUSTER','dflt')} lockstep={os.environ.get('NB2_TC_LOCKSTEP','dflt')} {precision} "
+    print(f"VARIANT tmema={os.environ.get('NB2_TC_TMEMA','dflt')} nhalf={os.environ.get('NB2_TC_NHALF','dflt')} cluster={os.environ.get('NB2_TC_CLUSTER','dflt')} lockstep={os.environ.get('NB2_TC_LOCKSTEP','dflt')} {precision} "
           f"ms={dt * 1e3:.2f} checksum={float(img.double().sum()):.6f} nan={int(torch.isnan(img).sum())}")
 
 
@@ -159,7 +175,9 @@ def stage_microbench():
 if __name__ == "__main__":
     stage = sys.argv[1]
     print("== stage", stage, sys.argv[2:], "on", torch.cuda.get_device_name(0))
-    if stage == "selftest":
+    if stage == "selftest_ts":
+        stage_selftest_ts()
+    elif stage == "selftest":
         stage_selftest()
     elif stage == "mlp":
         stage_mlp(sys.argv[2], sys.argv[3], int(sys.argv[4]) if len(sys.argv) > 4 else 1000)
