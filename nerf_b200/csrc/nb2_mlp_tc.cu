@@ -41,12 +41,14 @@ __device__ __forceinline__ void slot_group_run(const TcParams& p, TcMisc* misc, 
                                                int64_t n_iters, int warp, int lane, uint32_t cl_rank) {
   using LT = TcLayout<NSLOTS, SPLIT>;
   const TcNet& net = p.net;
-  // one arrival per warp: every lane has fenced its own shared-memory writes / TMEM reads, __syncwarp orders them
-  // before the elected lane's (release) arrive
+  // one arrival per warp: every lane has fenced its own shared-memory writes (fence.proxy.async) / TMEM reads, __syncwarp
+  // orders them before the elected lane's arrive.  The peer CTA's arrive is relaxed: the consumer of the data is the
+  // tensor core of this SM pair, not the waiting thread, and the release / acquire pair at cluster scope costs several
+  // hundred cycles per hand-over (see mbar_arrive_remote_relaxed)
   auto arrive_a = [&](uint32_t bar) {
     __syncwarp();
     if (lane == 0) {
-      if (PAIR && cl_rank != 0) mbar_arrive_remote(bar, 0); else mbar_arrive(bar);
+      if (PAIR && cl_rank != 0) mbar_arrive_remote_relaxed(bar, 0); else mbar_arrive(bar);
     }
   };
   // =========================== slot group: producer + epilogue ====================================
@@ -532,12 +534,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_tc2_kernel(const __grid_con
           const int n_entries = net.layer[l].kc * (SPLIT ? 2 : 1) * kPasses;
           for (int e = 0; e < n_entries; ++e) {
             mbar_wait(smem_u32(&misc->w_full[stage]), phase);
-            mbar_arrive_remote(smem_u32(&misc->w_peer[stage]), 0);
+            mbar_arrive_remote_relaxed(smem_u32(&misc->w_peer[stage]), 0);
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
         }
-    } else if (lane == 0) {
+    } else if (rank == 0) {
       // =========================== leader: MMA issuer for the pair ====================================
+      // (the whole warp runs the loop and elects one lane per tcgen05 instruction, see nb2_tc_ptx.cuh)
       uint32_t stage = 0, phase = 0;
       uint32_t pa[2] = {0u, 0u};
       long long t_wa = 0, t_ww = 0, t0m = NB2_CLK();
@@ -552,7 +555,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_tc2_kernel(const __grid_con
             const int s_lo = LOCKSTEP ? 0 : pass, s_hi = LOCKSTEP ? NSLOTS : pass + 1;
             { const long long c0 = NB2_CLK();
             for (int s = s_lo; s < s_hi; ++s) {
-              mbar_wait_cluster(smem_u32(&misc->a_ready[s]), pa[s]);
+              mbar_wait(smem_u32(&misc->a_ready[s]), pa[s]);
               pa[s] ^= 1u;
             }
             t_wa += NB2_CLK() - c0; }
@@ -562,7 +565,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_tc2_kernel(const __grid_con
               const uint32_t a_lo0 = umma_desc_lo(act_base + (uint32_t)L.a_src[k] * kTileBytes);   // slot 0, hi part
               { const long long c0 = NB2_CLK();
               mbar_wait(smem_u32(&misc->w_full[stage]), phase);
-              mbar_wait_cluster(smem_u32(&misc->w_peer[stage]), phase);
+              mbar_wait(smem_u32(&misc->w_peer[stage]), phase);
               t_ww += NB2_CLK() - c0; }
               tc_fence_after();
               const uint32_t w_lo0 = ring_lo + stage * (kTileBytes >> 4);
@@ -570,35 +573,35 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_tc2_kernel(const __grid_con
                 const uint32_t a_s = a_lo0 + s * (LT::kSlotBytes >> 4);
                 const uint32_t d_main = tmem_base + (uint32_t)(s * 256);
                 for (int ks = ks0; ks < 4; ++ks)
-                  umma2_bf16_ss(d_main, umma_desc_from_lo(a_s + 2 * ks), umma_desc_from_lo(w_lo0 + 2 * ks), idesc,
+                  umma2_f16_ss_elect(d_main, umma_desc_from_lo(a_s + 2 * ks), umma_desc_from_lo(w_lo0 + 2 * ks), idesc,
                                 (uint32_t)((k | ks) != 0));
                 if (SPLIT) {
                   const uint32_t a_l = a_s + (kChunksPerSlot * kTileBytes >> 4);
                   for (int ks = ks0; ks < 4; ++ks)
-                    umma2_bf16_ss(d_main + 256, umma_desc_from_lo(a_l + 2 * ks), umma_desc_from_lo(w_lo0 + 2 * ks), idesc,
+                    umma2_f16_ss_elect(d_main + 256, umma_desc_from_lo(a_l + 2 * ks), umma_desc_from_lo(w_lo0 + 2 * ks), idesc,
                                   (uint32_t)((k | ks) != 0));
                 }
               }
-              umma2_commit_mcast(smem_u32(&misc->w_empty[stage]), 3);
+              umma2_commit_mcast_elect(smem_u32(&misc->w_empty[stage]), 3);
               if (++stage == kStages) { stage = 0; phase ^= 1u; }
               if (SPLIT) {
                 { const long long c0 = NB2_CLK();
                 mbar_wait(smem_u32(&misc->w_full[stage]), phase);
-                mbar_wait_cluster(smem_u32(&misc->w_peer[stage]), phase);
+                mbar_wait(smem_u32(&misc->w_peer[stage]), phase);
                 t_ww += NB2_CLK() - c0; }
                 tc_fence_after();
                 const uint32_t wl = ring_lo + stage * (kTileBytes >> 4);
                 for (int ks = ks0; ks < 4; ++ks)
-                  umma2_bf16_ss(tmem_base + 256, umma_desc_from_lo(a_lo0 + 2 * ks), umma_desc_from_lo(wl + 2 * ks), idesc, 1u);
-                umma2_commit_mcast(smem_u32(&misc->w_empty[stage]), 3);
+                  umma2_f16_ss_elect(tmem_base + 256, umma_desc_from_lo(a_lo0 + 2 * ks), umma_desc_from_lo(wl + 2 * ks), idesc, 1u);
+                umma2_commit_mcast_elect(smem_u32(&misc->w_empty[stage]), 3);
                 if (++stage == kStages) { stage = 0; phase ^= 1u; }
               }
             }
-            for (int s = s_lo; s < s_hi; ++s) umma2_commit_mcast(smem_u32(&misc->acc_full[s]), 3);
+            for (int s = s_lo; s < s_hi; ++s) umma2_commit_mcast_elect(smem_u32(&misc->acc_full[s]), 3);
           }
         }
       }
-      if (NB2_PROF_ON) { p.prof[blockIdx.x * 16 + 3] = t_wa; p.prof[blockIdx.x * 16 + 4] = t_ww; p.prof[blockIdx.x * 16 + 5] = NB2_CLK() - t0m; }
+      if (NB2_PROF_ON && lane == 0) { p.prof[blockIdx.x * 16 + 3] = t_wa; p.prof[blockIdx.x * 16 + 4] = t_ww; p.prof[blockIdx.x * 16 + 5] = NB2_CLK() - t0m; }
     }
   } else if (warp >= 4) {
     reg_alloc<kGroupRegs>();
@@ -618,8 +621,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_tc2_kernel(const __grid_con
 
 // ---- host side ----------------------------------------------------------------------------------------
 // Variant knobs (defaults chosen from measurements; overridable for experiments):
-//   NB2_TC_CLUSTER = 1 | 2 | 4      CTAs sharing each weight tile via multicast
-//   NB2_TC_LOCKSTEP = 0 | 1         two-slot modes: both tiles consume each weight tile
+//   NB2_TC_TMEMA = 1 | 0            split precisions: TMEM-operand kernel (nb2_mlp_tc4.cu) | layer-serial pair kernel
+//   NB2_TC_NHALF = 0 | 1            N-half pipelined pair kernel (nb2_mlp_tc3.cu; measured slower, kept for the record)
+//   NB2_TC_PAIR = 1 | 0             CTA-pair kernel | single-CTA kernel
+//   NB2_TC_LOCKSTEP = 0 | 1         pair kernel, single pass: ping-pong tiles (one tile's epilogue under the other's MMAs) | both tiles
+//                                   consume each weight tile back to back (single-CTA kernel: default 1)
+//   NB2_TC_CLUSTER = 1 | 2 | 4      single-CTA kernel: CTAs sharing each weight tile via multicast
 static int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
   return v ? atoi(v) : dflt;
@@ -724,6 +731,7 @@ int launch_mlp_tc(nb2_handle* h, int net_id, int precision, const MlpIo& io, cud
   prm.pos_levels = pn.pos_levels;
   prm.dir_levels = pn.dir_levels;
   prm.has_dir = (net_id == NB2_NET_NERF);
+  prm.debug = env_int("NB2_TC_DEBUG", 0);
   prm.dir_layer = -1;   // the direction encoding is written after the epilogue of the layer before the density layer
   for (int l = 0; l < pn.tc.n_layers; ++l)
     if (prm.has_dir && pn.tc.layer[l].epi == EPI_RELU_SIGMA) prm.dir_layer = l - 1;
@@ -733,9 +741,9 @@ int launch_mlp_tc(nb2_handle* h, int net_id, int precision, const MlpIo& io, cud
   // NB2_TC_NHALF = 1: CTA-pair kernel pipelined by output halves (nb2_mlp_tc3.cu)
   if (env_int("NB2_TC_NHALF", 0) != 0) return launch_mlp_tc3(h, prm, precision, st);
   // NB2_TC_TMEMA = 1: split precisions with the hidden activations in tensor memory (nb2_mlp_tc4.cu)
-  if (split && env_int("NB2_TC_TMEMA", 0) != 0) return launch_mlp_tc4(h, prm, precision, st);
+  if (split && env_int("NB2_TC_TMEMA", 1) != 0) return launch_mlp_tc4(h, prm, precision, st);
   if (env_int("NB2_TC_PAIR", 1) != 0) {
-    const bool ls = env_int("NB2_TC_LOCKSTEP", 1) != 0;
+    const bool ls = env_int("NB2_TC_LOCKSTEP", 0) != 0;
     if (precision == NB2_PREC_BF16) return ls ? launch_tc2_impl<2, false, false, true>(h, prm, st) : launch_tc2_impl<2, false, false, false>(h, prm, st);
     if (precision == NB2_PREC_FP16) return ls ? launch_tc2_impl<2, false, true, true>(h, prm, st) : launch_tc2_impl<2, false, true, false>(h, prm, st);
     if (precision == NB2_PREC_BF16X3) return launch_tc2_impl<1, true, false, true>(h, prm, st);

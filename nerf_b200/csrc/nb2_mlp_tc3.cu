@@ -167,7 +167,7 @@ __device__ __forceinline__ void slot_group_run3(const Tc3Params& q, Tc3Misc* mis
   auto arrive = [&](uint32_t bar) {
     __syncwarp();
     if (lane == 0) {
-      if (rank != 0) mbar_arrive_remote(bar, 0); else mbar_arrive(bar);
+      if (rank != 0) mbar_arrive_remote_relaxed(bar, 0); else mbar_arrive(bar);
     }
   };
   auto publish = [&](uint32_t bar) {   // shared-memory writes -> visible to the tensor core, then signal
@@ -446,7 +446,7 @@ __device__ __forceinline__ void mma_issuer3(const Tc3Params& q, Tc3Misc* misc, u
   auto wait_stage = [&]() {
     const long long c0 = NB2_CLK();
     mbar_wait(smem_u32(&misc->w_full[stage]), phase);
-    mbar_wait_cluster(smem_u32(&misc->w_peer[stage]), phase);
+    mbar_wait(smem_u32(&misc->w_peer[stage]), phase);
     t_ww += NB2_CLK() - c0;
     tc_fence_after();
   };
@@ -456,7 +456,7 @@ __device__ __forceinline__ void mma_issuer3(const Tc3Params& q, Tc3Misc* misc, u
   };
   auto wait_ready = [&](int which, uint32_t& par) {
     const long long c0 = NB2_CLK();
-    mbar_wait_cluster(smem_u32(&misc->a_ready[which]), par);
+    mbar_wait(smem_u32(&misc->a_ready[which]), par);
     par ^= 1u;
     t_wa += NB2_CLK() - c0;
     tc_fence_after();
@@ -585,7 +585,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_tc3_kernel(const __grid_con
           const int n_entries = net.layer[l].nc * q.plan[l].n * kParts;
           for (int e = 0; e < n_entries; ++e) {
             mbar_wait(smem_u32(&misc->w_full[stage]), phase);
-            mbar_arrive_remote(smem_u32(&misc->w_peer[stage]), 0);
+            mbar_arrive_remote_relaxed(smem_u32(&misc->w_peer[stage]), 0);
             if (++stage == kStages3) { stage = 0; phase ^= 1u; }
           }
         }

@@ -129,7 +129,7 @@ __device__ __forceinline__ void slot_group_run4(const TcParams& p, Tc4Misc* misc
   auto arrive_a = [&]() {
     __syncwarp();
     if (lane == 0) {
-      if (rank != 0) mbar_arrive_remote(a_ready, 0); else mbar_arrive(a_ready);
+      if (rank != 0) mbar_arrive_remote_relaxed(a_ready, 0); else mbar_arrive(a_ready);
     }
   };
   auto tile_of = [&](int64_t it) { return it * gridDim.x + blockIdx.x; };   // may lie past n_tiles
@@ -338,7 +338,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_tc4_kernel(const __grid_con
     // =========================== weight streamer: this CTA's half of every tile ==========================
     // per layer: K chunks in table order, each as [Wh, Wl] (cross-term sweep), then every Wh again (main sweep)
     reg_dealloc<kRoleRegs>();
-    if (lane == 0) {
+    if (lane == 0 && !(p.debug & 1)) {
       uint32_t stage = 0, phase = 0;
       for (int64_t it = 0; it < n_iters; ++it) {
         for (int l = 0; l < net.n_layers; ++l) {
@@ -362,7 +362,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_tc4_kernel(const __grid_con
     }
   } else if (warp == 1) {
     reg_dealloc<kRoleRegs>();
-    if (lane == 0 && rank != 0) {
+    if (lane == 0 && rank != 0 && !(p.debug & 1)) {
       // =========================== peer: relay "my half has landed" to the leader =====================
       uint32_t stage = 0, phase = 0;
       for (int64_t it = 0; it < n_iters; ++it)
@@ -370,40 +370,43 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_tc4_kernel(const __grid_con
           const int n_entries = 3 * net.layer[l].kc;
           for (int e = 0; e < n_entries; ++e) {
             mbar_wait(smem_u32(&misc->w_full[stage]), phase);
-            mbar_arrive_remote(smem_u32(&misc->w_peer[stage]), 0);
+            mbar_arrive_remote_relaxed(smem_u32(&misc->w_peer[stage]), 0);
             if (++stage == kStages4) { stage = 0; phase ^= 1u; }
           }
         }
-    } else if (lane == 0) {
-      // =========================== leader: MMA issuer for the pair ====================================
+    } else if (rank == 0) {
+      // =========================== leader: MMA issuer for the pair (whole warp, one elected lane per instruction) ======
       uint32_t stage = 0, phase = 0, pa = 0;
       long long t_wa = 0, t_ww = 0, t0m = NB2_CLK();
       const uint32_t ring_lo = umma_desc_lo(ring_base);
       const uint32_t enc_lo = umma_desc_lo(enc_base);    // hi half of the encoding tile; the lo half is one tile further
+      const bool no_weights = (p.debug & 1) != 0, no_mma = (p.debug & 2) != 0;
       auto wait_stage = [&]() {
+        if (no_weights) return;
         const long long c0 = NB2_CLK();
         mbar_wait(smem_u32(&misc->w_full[stage]), phase);
-        mbar_wait_cluster(smem_u32(&misc->w_peer[stage]), phase);
+        mbar_wait(smem_u32(&misc->w_peer[stage]), phase);
         t_ww += NB2_CLK() - c0;
         tc_fence_after();
       };
       auto release_stage = [&]() {
-        umma2_commit_mcast(smem_u32(&misc->w_empty[stage]), 3);
+        if (!no_weights) umma2_commit_mcast_elect(smem_u32(&misc->w_empty[stage]), 3);
         if (++stage == kStages4) { stage = 0; phase ^= 1u; }
       };
       // one K chunk (up to four k-steps) of A (hi or lo half) against the weight stage that just landed
       auto issue_chunk = [&](int a_src, int ks0, bool lo_half, uint32_t idesc, bool first) {
+        if (no_mma) return;
         const uint32_t w0 = ring_lo + stage * (kTileBytes >> 4);
         if (a_src == kChunkE) {
           const uint32_t a0 = enc_lo + (lo_half ? (uint32_t)(kTileBytes >> 4) : 0u);
           for (int ks = ks0; ks < 4; ++ks)
-            umma2_bf16_ss(tmem_base, umma_desc_from_lo(a0 + 2 * ks), umma_desc_from_lo(w0 + 2 * ks), idesc,
+            umma2_f16_ss_elect(tmem_base, umma_desc_from_lo(a0 + 2 * ks), umma_desc_from_lo(w0 + 2 * ks), idesc,
                           (uint32_t)(!(first && ks == ks0)));
         } else {
           const uint32_t a0 = tmem_base + (uint32_t)(lo_half ? kALoCol : kAHiCol) + (uint32_t)(32 * a_src);
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks)
-            umma2_f16_ts(tmem_base, a0 + 8 * ks, umma_desc_from_lo(w0 + 2 * ks), idesc, (uint32_t)(!(first && ks == 0)));
+            umma2_f16_ts_elect(tmem_base, a0 + 8 * ks, umma_desc_from_lo(w0 + 2 * ks), idesc, (uint32_t)(!(first && ks == 0)));
         }
       };
       for (int64_t it = 0; it < n_iters; ++it) {
@@ -411,7 +414,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_tc4_kernel(const __grid_con
           const TcLayer& L = net.layer[l];
           const uint32_t idesc = umma_idesc_16(256, L.nc * 128, F16);
           { const long long c0 = NB2_CLK();
-          mbar_wait_cluster(smem_u32(&misc->a_ready), pa);
+          mbar_wait(smem_u32(&misc->a_ready), pa);
           pa ^= 1u;
           t_wa += NB2_CLK() - c0; }
           tc_fence_after();
@@ -430,10 +433,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_tc4_kernel(const __grid_con
             issue_chunk(L.a_src[k], L.ks0[k], false, idesc, false);
             release_stage();
           }
-          umma2_commit_mcast(smem_u32(&misc->acc_full), 3);
+          umma2_commit_mcast_elect(smem_u32(&misc->acc_full), 3);
         }
       }
-      if (NB2_PROF_ON) { p.prof[blockIdx.x * 16 + 3] = t_wa; p.prof[blockIdx.x * 16 + 4] = t_ww; p.prof[blockIdx.x * 16 + 5] = NB2_CLK() - t0m; }
+      if (NB2_PROF_ON && lane == 0) { p.prof[blockIdx.x * 16 + 3] = t_wa; p.prof[blockIdx.x * 16 + 4] = t_ww; p.prof[blockIdx.x * 16 + 5] = NB2_CLK() - t0m; }
     }
   } else if (warp >= 4) {
     reg_alloc<kGroupRegs>();

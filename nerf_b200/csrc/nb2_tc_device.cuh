@@ -27,6 +27,7 @@ struct TcParams {
   const float* bias;
   const float* head;
   int pos_levels, dir_levels, has_dir;
+  int debug;       // timing experiments only (results are garbage): 1 = no weight streaming / waits, 2 = no MMAs (handshake only)
   int dir_layer;   // layer after whose epilogue the direction encoding replaces the position encoding (-1: none)
   int cluster;   // CTAs per cluster sharing every weight tile through multicast bulk copies (1, 2 or 4)
   int64_t n_tiles;

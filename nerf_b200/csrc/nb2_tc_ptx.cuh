@@ -178,6 +178,49 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
       : "memory");
 }
 
+// Same without release semantics: used by the weight relay, which publishes no memory of its own -- it only forwards
+// "the bulk copy into my shared memory has completed" (observed through the local mbarrier) to the pair's leader, whose
+// consumer is the tensor core.  The release/acquire pair at cluster scope measured ~780 cycles per weight stage
+// (fence + L1 invalidate on every stage) and capped the weight stream at 20 B/cycle/SM.
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint32_t bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(bar), "r"(cta)
+      : "memory");
+}
+
+// The issuer warp stays converged and elects one lane per instruction (elect.sync): in a lane-0-only region every
+// tcgen05 instruction is wrapped in an ELECT / BRA.U.ANY loop and its uniform-register operands are rebuilt inside it,
+// which measured ~115 cycles per MMA and ~200-300 per weight stage -- more than the 512 tensor cycles a split-mode
+// stage is worth.  The three forms below are issued by the whole warp; one elected lane executes them.
+__device__ __forceinline__ void umma2_f16_ts_elect(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_f16_ss_elect(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_commit_mcast_elect(uint32_t bar, uint16_t cta_mask) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}"
+      ::"r"(bar), "h"(cta_mask)
+      : "memory");
+}
 // ---- TMEM -> registers: this warp's 32 lanes x 32 consecutive fp32 columns ---------------------
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(

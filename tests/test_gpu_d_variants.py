@@ -1,9 +1,14 @@
-"""GPU: every launch variant of the tensor-core MLP kernel computes the same thing.
+"""GPU: every launch variant of the tensor-core MLP kernels computes the same thing.
 
-The default is the CTA-pair kernel (cta_group::2, M256xN256 MMAs, lockstep slots).  The single-CTA kernel
-(cta_group::1, N=128 MMAs), its cluster-multicast weight streaming (2 and 4 CTAs) and the ping-pong slot
-schedule are selectable through NB2_TC_* environment variables (read at every launch).  All of them perform the
-same arithmetic in the same order per tile, so the rendered image must be bit-identical.
+Defaults (nb2_mlp_tc.cu:launch_mlp_tc): single-pass precisions run the CTA-pair kernel with ping-pong tiles; split
+precisions run the TMEM-operand kernel (nb2_mlp_tc4.cu).  The other kernels stay selectable
+through NB2_TC_* environment variables (read at every launch):
+
+* the layer-serial kernels (CTA pair in lockstep or ping-pong, single-CTA with cluster multicast 1/2/4) perform the same
+  arithmetic in the same order per tile, so their images must be BIT-IDENTICAL to each other;
+* the N-half and TMEM-operand kernels reorder fp32 sums (K chunks issued in another order, cross terms accumulated
+  first), so they are compared with the layer-serial image within the precision's own noise floor (a reordered fp32
+  sum moves a 16-bit rounding boundary now and then, which single-pass modes amplify to their operand precision).
 """
 import os
 
@@ -11,23 +16,46 @@ import pytest
 import torch
 
 import nerf_b200
-from nerf_b200 import ops
 from oracle import nerf_oracle as O
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
-VARIANTS = [
-    {"NB2_TC_PAIR": "1", "NB2_TC_LOCKSTEP": "1"},                       # default
-    {"NB2_TC_PAIR": "1", "NB2_TC_LOCKSTEP": "0"},
-    {"NB2_TC_PAIR": "0", "NB2_TC_CLUSTER": "1", "NB2_TC_LOCKSTEP": "0"},
-    {"NB2_TC_PAIR": "0", "NB2_TC_CLUSTER": "1", "NB2_TC_LOCKSTEP": "1"},
-    {"NB2_TC_PAIR": "0", "NB2_TC_CLUSTER": "2", "NB2_TC_LOCKSTEP": "1"},
-    {"NB2_TC_PAIR": "0", "NB2_TC_CLUSTER": "4", "NB2_TC_LOCKSTEP": "0"},
+KEYS = ("NB2_TC_PAIR", "NB2_TC_CLUSTER", "NB2_TC_LOCKSTEP", "NB2_TC_NHALF", "NB2_TC_TMEMA")
+SERIAL = [
+    {"NB2_TC_TMEMA": "0", "NB2_TC_PAIR": "1", "NB2_TC_LOCKSTEP": "1"},
+    {"NB2_TC_TMEMA": "0", "NB2_TC_PAIR": "1", "NB2_TC_LOCKSTEP": "0"},
+    {"NB2_TC_TMEMA": "0", "NB2_TC_PAIR": "0", "NB2_TC_CLUSTER": "1", "NB2_TC_LOCKSTEP": "0"},
+    {"NB2_TC_TMEMA": "0", "NB2_TC_PAIR": "0", "NB2_TC_CLUSTER": "1", "NB2_TC_LOCKSTEP": "1"},
+    {"NB2_TC_TMEMA": "0", "NB2_TC_PAIR": "0", "NB2_TC_CLUSTER": "2", "NB2_TC_LOCKSTEP": "1"},
+    {"NB2_TC_TMEMA": "0", "NB2_TC_PAIR": "0", "NB2_TC_CLUSTER": "4", "NB2_TC_LOCKSTEP": "0"},
 ]
+REORDERED = [
+    {},                                                   # the defaults
+    {"NB2_TC_TMEMA": "0", "NB2_TC_NHALF": "1"},          # N-half pipelined pair kernel
+    {"NB2_TC_TMEMA": "1"},                                # TMEM-operand kernel (split precisions only)
+]
+# max |rgb difference| against the layer-serial image: fp32 reordering noise through 13 layers and the resampling
+TOL = {"bf16": 3e-2, "fp16": 5e-3, "fp16x3": 1e-4, "bf16x3": 1e-4}
 
 
-@pytest.mark.parametrize("precision", ["bf16", "fp16x3"])
-def test_all_kernel_variants_are_bit_identical(precision):
+def render(env, precision, net, prop, pose, H, W, focal):
+    saved = {k: os.environ.get(k) for k in KEYS}
+    try:
+        for k in KEYS:
+            os.environ.pop(k, None)
+        os.environ.update(env)
+        img = nerf_b200.render_image(net, prop, pose, (H, W), focal, 2.0, 6.0, 128, white_bkg=True, precision=precision, seed=11)["rgb"]
+        torch.cuda.synchronize()
+        return img.clone()
+    finally:
+        for k, val in saved.items():
+            os.environ.pop(k, None)
+            if val is not None:
+                os.environ[k] = val
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp16", "fp16x3", "bf16x3"])
+def test_kernel_variants_agree(precision):
     prop = nerf_b200.ProposalNetwork(10, 256)
     net = nerf_b200.MipNeRF(10, 4, 256)
     prop.load_state_dict(O.make_params("proposal", 1, "smooth"))
@@ -36,21 +64,18 @@ def test_all_kernel_variants_are_bit_identical(precision):
     H = W = 96          # 9216 rays: several tiles per CTA pair, ragged against 148 SMs
     pose = nerf_b200.pose_spherical(75.0, -30.0, 4.0)[:3, :].to(DEV)
     focal = nerf_b200.fov2Focal(0.6911112070083618, (H, W))[0]
-    saved = {k: os.environ.get(k) for k in ("NB2_TC_PAIR", "NB2_TC_CLUSTER", "NB2_TC_LOCKSTEP")}
-    images = []
-    try:
-        for v in VARIANTS:
-            for k in saved:
-                os.environ.pop(k, None)
-            os.environ.update(v)
-            img = nerf_b200.render_image(net, prop, pose, (H, W), focal, 2.0, 6.0, 128, white_bkg=True, precision=precision, seed=11)["rgb"]
-            torch.cuda.synchronize()
-            images.append(img.clone())
-    finally:
-        for k, val in saved.items():
-            os.environ.pop(k, None)
-            if val is not None:
-                os.environ[k] = val
-    assert not torch.isnan(images[0]).any() and float(images[0].std()) > 0.01
-    for v, img in zip(VARIANTS[1:], images[1:]):
-        assert torch.equal(img, images[0]), f"variant {v} differs: max {float((img - images[0]).abs().max())}"
+    base = render(SERIAL[0], precision, net, prop, pose, H, W, focal)
+    assert not torch.isnan(base).any() and float(base.std()) > 0.01
+    for v in SERIAL[1:]:
+        img = render(v, precision, net, prop, pose, H, W, focal)
+        assert torch.equal(img, base), f"layer-serial variant {v} differs: max {float((img - base).abs().max())}"
+    for v in REORDERED:
+        img = render(v, precision, net, prop, pose, H, W, focal)
+        assert not torch.isnan(img).any()
+        err = (img - base).abs()
+        # two fp32-faithful evaluations differ by ~1e-6 in the proposal densities; on rays that graze a density edge this
+        # moves fine samples and the colour by a few 1e-4 (the field is ill-conditioned there: the oracle's own CPU / GPU
+        # runs differ the same way), hence a small allowed fraction and a bound on the worst ray
+        bad = float((err.amax(dim=0) > TOL[precision]).float().mean())
+        assert bad < 1e-2, f"variant {v}: {bad:.4f} of the rays differ by more than {TOL[precision]:g} (max {float(err.max()):.3e})"
+        assert float(err.max()) < 30 * TOL[precision], f"variant {v}: worst ray differs by {float(err.max()):.3e}"

@@ -1,0 +1,9 @@
+#!/bin/bash
+mkdir -p gpurun_out
+run() { name=$1; shift; echo "### $name"; timeout ${TMO:-300} "$@" > gpurun_out/$name.log 2>&1; echo "rc=$? $name"; tail -n ${TAILN:-3} gpurun_out/$name.log; }
+export NB2_TC_TMEMA=1
+for dbg in 0 2; do
+  NB2_TC_DEBUG=$dbg NB2_LIB=libnerfb200_prof.so TMO=200 TAILN=14 run roles4_dbg$dbg python tools/gpu_probe.py roles fp16x3
+done
+TMO=120 TAILN=1 run time1_fp16x3 python tools/gpu_probe.py time fp16x3
+TMO=120 TAILN=3 run mlp_nerf_fp16x3 python tools/gpu_probe.py mlp nerf fp16x3 5000
