@@ -34,9 +34,14 @@ FLOP_PROP_PER_RAY = 27262976       # 2*(63*256 + 3*256^2 + 256) 
 FLOP_NERF_PER_RAY = 135135232      # 2*(63*256 + 3*256^2 + 319*256 + 2*256^2 + 256^2 + 256 + 283*128 + 128*3) * 128
 METRIC = "rays/sec (64c+128f samples)"
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE fine-kernel launch over 160,000 rays, from the ncu --set full
-# captures summarised in profiles/r01_ncu_{fp16x3_pair2wg,fp16_pair}.txt (algorithmic: 556 B/ray = 89 MB; the
+# captures summarised in profiles/r01_ncu_{fp16x3_tmema,fp16_pp}.txt (algorithmic: 556 B/ray = 89 MB; the
 # 2.4 MB of packed weights stay L2-resident)
-NCU_FINE_TRAFFIC_BYTES_160K = {"fp16x3": 92.6e6, "bf16x3": 92.6e6, "fp16": 91.0e6, "bf16": 91.0e6}
+NCU_FINE_TRAFFIC_BYTES_160K = {"fp16x3": 93.1e6, "bf16x3": 93.1e6, "fp16": 91.9e6, "bf16": 91.9e6}
+FINE_KERNEL = {"fp16x3": "mlp_tc4_kernel (fine: encode + 8x256 MLP + composite; CTA-pair tcgen05, activations in TMEM)",
+               "bf16x3": "mlp_tc4_kernel (fine: encode + 8x256 MLP + composite; CTA-pair tcgen05, activations in TMEM)",
+               "fp16": "mlp_tc2_kernel (fine: encode + 8x256 MLP + composite; CTA-pair tcgen05, ping-pong tiles)",
+               "bf16": "mlp_tc2_kernel (fine: encode + 8x256 MLP + composite; CTA-pair tcgen05, ping-pong tiles)",
+               "fp32": "mlp_simt_kernel (fine: encode + 8x256 MLP on CUDA cores) + composite_kernel"}
 
 
 def load_peaks():
@@ -301,7 +306,7 @@ def main():
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
                 "traffic": (NCU_FINE_TRAFFIC_BYTES_160K.get(args.precision) if n_rays == 160000 else None),
                 "traffic_unit": "bytes per launch (ncu dram read+write; algorithmic 556 B/ray)",
-                "kernel": "mlp_tc2_kernel (fine: encode + 8x256 MLP + composite; CTA-pair tcgen05)", "kernel_ms": fine_ms,
+                "kernel": FINE_KERNEL[args.precision], "kernel_ms": fine_ms,
                 "algorithmic_flop_per_launch": FLOP_NERF_PER_RAY * n_rays, "peak_source": peaks["src"], "mma_passes_per_product": passes,
                 "issued_tensor_tflops": achieved * passes * 528384.0 / 527872.0,
                 "frac_issued": achieved * passes * 528384.0 / 527872.0 / peaks["tflops"], "step_share": {"proposal_kernel_ms": kms[0], "resample_kernel_ms": kms[1], "fine_kernel_ms": kms[2]}}
