@@ -182,6 +182,9 @@ __device__ __forceinline__ void slot_group_run4(const TcParams& p, Tc4Misc* misc
             c2 = fmaf(t0, w2.x, c2); c2 = fmaf(t1, w2.y, c2); c2 = fmaf(t2, w2.z, c2); c2 = fmaf(t3, w2.w, c2);
           }
         }
+        // the accumulator has been read and the encoding tile is free: hand the next tile to the issuer before the rest
+        // of this epilogue (head, compositing) so that its first layer runs underneath
+        if (has_next) begin_tile();
         // combine the two column halves: warpgroup 1 parks its partial sums (and its half of the density dot product)
         const uint32_t xaddr = park_base + (uint32_t)row * 16u;
         if (g == 1) st_shared_v4(xaddr, __float_as_uint(sigma), __float_as_uint(c0), __float_as_uint(c1), __float_as_uint(c2));
@@ -191,7 +194,6 @@ __device__ __forceinline__ void slot_group_run4(const TcParams& p, Tc4Misc* misc
           asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3) : "r"(xaddr));
           sigma += __uint_as_float(x0); c0 += __uint_as_float(x1); c1 += __uint_as_float(x2); c2 += __uint_as_float(x3);
         }
-        if (has_next) begin_tile();   // the accumulator of this tile is no longer needed
         if (g == 0) {
           c0 = 1.f / (1.f + expf(-(c0 + __ldg(p.head + kHeadRgbB + 0))));
           c1 = 1.f / (1.f + expf(-(c1 + __ldg(p.head + kHeadRgbB + 1))));
@@ -253,6 +255,7 @@ __device__ __forceinline__ void slot_group_run4(const TcParams& p, Tc4Misc* misc
       if (epi == EPI_SIGMA_OUT) {
         // ---- proposal tail: out = w_s . relu(acc) + b_s ------------------------------------------------------------------
         sigma = epilogue_hidden4<EPI_SIGMA_OUT, F16>(acc, g, p.head) + (g == 0 ? __ldg(p.head + kHeadSigmaB) : 0.f);
+        if (has_next) begin_tile();
         const uint32_t xaddr = park_base + (uint32_t)row * 16u;
         if (g == 1) asm volatile("st.shared.b32 [%0], %1;" ::"r"(xaddr), "r"(__float_as_uint(sigma)));
         named_bar_sync(3, 256);
@@ -261,7 +264,6 @@ __device__ __forceinline__ void slot_group_run4(const TcParams& p, Tc4Misc* misc
           asm volatile("ld.shared.b32 %0, [%1];" : "=r"(x0) : "r"(xaddr));
           sigma += __uint_as_float(x0);
         }
-        if (has_next) begin_tile();
         if (in.valid && g == 0) p.io.out[grow] = sigma;
         t_last += NB2_CLK() - ce;
         continue;

@@ -79,3 +79,22 @@ def test_kernel_variants_agree(precision):
         bad = float((err.amax(dim=0) > TOL[precision]).float().mean())
         assert bad < 1e-2, f"variant {v}: {bad:.4f} of the rays differ by more than {TOL[precision]:g} (max {float(err.max()):.3e})"
         assert float(err.max()) < 30 * TOL[precision], f"variant {v}: worst ray differs by {float(err.max()):.3e}"
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp16x3"])
+def test_default_kernels_are_deterministic(precision):
+    """The hand-overs between the CTAs of a pair use relaxed remote arrivals (nb2_tc_ptx.cuh); a stale operand or a
+    missed hand-over would show up as run-to-run differences.  Same inputs, same seed -> bit-identical images."""
+    prop = nerf_b200.ProposalNetwork(10, 256)
+    net = nerf_b200.MipNeRF(10, 4, 256)
+    prop.load_state_dict(O.make_params("proposal", 1, "he"))
+    net.load_state_dict(O.make_params("nerf", 2, "he"))
+    prop, net = prop.to(DEV), net.to(DEV)
+    H = W = 200         # 40,000 rays: ~35 tiles per CTA in the fine pass
+    pose = nerf_b200.pose_spherical(-40.0, -30.0, 4.0)[:3, :].to(DEV)
+    focal = nerf_b200.fov2Focal(0.6911112070083618, (H, W))[0]
+    first = render({}, precision, net, prop, pose, H, W, focal)
+    assert not torch.isnan(first).any()
+    for _ in range(4):
+        again = render({}, precision, net, prop, pose, H, W, focal)
+        assert torch.equal(again, first), f"run-to-run difference: max {float((again - first).abs().max()):.3e}"
