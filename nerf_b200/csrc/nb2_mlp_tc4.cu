@@ -41,7 +41,7 @@ struct Tc4Misc {
 struct Tc4Layout {
   static constexpr int kEncBytes = 2 * kTileBytes;              // encoding tile, hi + lo
   static constexpr int kRingBytes = kStages4 * kTileBytes;
-  static constexpr int kParkBytes = kTileRows * 16;             // warpgroup 1 -> warpgroup 0 partial sums (last epilogue)
+  static constexpr int kParkBytes = 3 * kTileRows * 16;         // warpgroups 1..3 -> warpgroup 0 partial sums (last epilogue)
   static constexpr int kMiscBytes = 1024;
   static constexpr int kTotal = kEncBytes + kRingBytes + kParkBytes + kMiscBytes + 1024 /* alignment slack */;
   static_assert(sizeof(Tc4Misc) <= kMiscBytes, "misc region too small");
@@ -68,28 +68,38 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
 __device__ __forceinline__ void tmem_st_wait4() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // ---- hidden-layer epilogue: accumulator -> activation -> hi / lo halves of the next A operand in TMEM -----------------
-// This thread owns row (TMEM lane) `row` and output columns [128 g, 128 g + 128).  Returns its part of the density dot product.
-template <int EPI, bool F16>
+// NG warpgroups share the tile: this thread owns row (TMEM lane) `row` and output columns [256 / NG * g, 256 / NG * (g + 1)).
+// Returns its part of the density dot product.  NG = 2: two 32-column blocks per tcgen05.wait::ld (216 registers per thread);
+// NG = 4: one block per wait (112 registers per thread, four warps per scheduler hide the round trips).
+template <int EPI, bool F16, int NG>
 __device__ __forceinline__ float epilogue_hidden4(uint32_t acc_lane, int g, const float* __restrict__ head) {
   constexpr bool kRelu = (EPI != EPI_LINEAR);
   constexpr bool kSigma = (EPI == EPI_RELU_SIGMA || EPI == EPI_SIGMA_OUT);
   constexpr bool kStore = (EPI != EPI_SIGMA_OUT);
+  constexpr int kBlocks = 8 / NG;          // 32-column blocks owned by this thread
+  constexpr int kBatch = (NG == 2) ? 2 : 1;
   float sg = 0.f;
 #pragma unroll 1
-  for (int b = 0; b < 4; b += 2) {
-    uint32_t r0[32], r1[32];
-    const int c0 = 128 * g + 32 * b;
+  for (int b = 0; b < kBlocks; b += kBatch) {
+    uint32_t r0[32], r1[kBatch == 2 ? 32 : 1];
+    const int c0 = (256 / NG) * g + 32 * b;
     tmem_ld32(acc_lane + c0, r0);
-    tmem_ld32(acc_lane + c0 + 32, r1);
+    if constexpr (kBatch == 2) tmem_ld32(acc_lane + c0 + 32, r1);
     tmem_ld_wait();
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      uint32_t (&r)[32] = u ? r1 : r0;
+    for (int u = 0; u < kBatch; ++u) {
       const int col = c0 + 32 * u;
       uint32_t hi[16], lo[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        float a = __uint_as_float(r[2 * i]), bq = __uint_as_float(r[2 * i + 1]);
+        float a, bq;
+        if constexpr (kBatch == 2) {
+          a = __uint_as_float(u ? r1[2 * i] : r0[2 * i]);
+          bq = __uint_as_float(u ? r1[2 * i + 1] : r0[2 * i + 1]);
+        } else {
+          a = __uint_as_float(r0[2 * i]);
+          bq = __uint_as_float(r0[2 * i + 1]);
+        }
         if (kRelu) { a = fmaxf(a, 0.f); bq = fmaxf(bq, 0.f); }
         if (kSigma) {
           const float2 w = __ldg(reinterpret_cast<const float2*>(head + kHeadSigmaW + col + 2 * i));
@@ -111,11 +121,11 @@ __device__ __forceinline__ float epilogue_hidden4(uint32_t acc_lane, int g, cons
   return sg;
 }
 
-template <bool F16, int G>
+template <bool F16, int NG, int G>
 __device__ __forceinline__ void slot_group_run4(const TcParams& p, Tc4Misc* misc, uint32_t enc_base, uint32_t park_base,
                                                 uint32_t tmem_base, int64_t n_iters, int warp, int lane, uint32_t rank) {
   const TcNet& net = p.net;
-  constexpr int g = G;                // column half of every layer's output owned by this warpgroup
+  constexpr int g = G;                // which 256 / NG columns of every layer's output this warpgroup owns
   const int wq = warp & 3;            // TMEM lane quadrant this warp may access
   const int row = wq * 32 + lane;     // row of the tile == TMEM lane
   const uint32_t e_hi = enc_base, e_lo = enc_base + kTileBytes;
@@ -133,7 +143,7 @@ __device__ __forceinline__ void slot_group_run4(const TcParams& p, Tc4Misc* misc
     }
   };
   auto tile_of = [&](int64_t it) { return it * gridDim.x + blockIdx.x; };   // may lie past n_tiles
-  EncRegs<true, F16, 4 * G, 4> enc;   // this warpgroup's four column groups of the next tile's encoding
+  EncRegs<true, F16, (8 / NG) * G, 8 / NG> enc;   // this warpgroup's column groups (8 columns each) of the next tile's encoding
   auto begin_tile = [&]() {
     enc_store(enc, e_hi, e_lo, row);
     fence_proxy_async_smem();
@@ -165,7 +175,7 @@ __device__ __forceinline__ void slot_group_run4(const TcParams& p, Tc4Misc* misc
         // ---- rgb_layer: t = relu(acc) (128 wide, bias folded), rgb = sigmoid(W1 t + b1) --------
         float c0 = 0.f, c1 = 0.f, c2 = 0.f;
 #pragma unroll 1
-        for (int cb = 2 * g; cb < 2 * g + 2; ++cb) {
+        for (int cb = (4 / NG) * g; cb < (4 / NG) * (g + 1); ++cb) {
           uint32_t r[32];
           tmem_ld32(acc + cb * 32, r);
           tmem_ld_wait();
@@ -185,14 +195,19 @@ __device__ __forceinline__ void slot_group_run4(const TcParams& p, Tc4Misc* misc
         // the accumulator has been read and the encoding tile is free: hand the next tile to the issuer before the rest
         // of this epilogue (head, compositing) so that its first layer runs underneath
         if (has_next) begin_tile();
-        // combine the two column halves: warpgroup 1 parks its partial sums (and its half of the density dot product)
+        // combine the column groups: warpgroups 1.. park their partial sums (and their part of the density dot product)
         const uint32_t xaddr = park_base + (uint32_t)row * 16u;
-        if (g == 1) st_shared_v4(xaddr, __float_as_uint(sigma), __float_as_uint(c0), __float_as_uint(c1), __float_as_uint(c2));
-        named_bar_sync(3, 256);
+        if (g != 0) st_shared_v4(xaddr + (uint32_t)(g - 1) * (kTileRows * 16), __float_as_uint(sigma), __float_as_uint(c0),
+                                 __float_as_uint(c1), __float_as_uint(c2));
+        named_bar_sync(3, 128 * NG);
         if (g == 0) {
-          uint32_t x0, x1, x2, x3;
-          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3) : "r"(xaddr));
-          sigma += __uint_as_float(x0); c0 += __uint_as_float(x1); c1 += __uint_as_float(x2); c2 += __uint_as_float(x3);
+#pragma unroll
+          for (int q = 0; q < NG - 1; ++q) {
+            uint32_t x0, x1, x2, x3;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3)
+                         : "r"(xaddr + (uint32_t)q * (kTileRows * 16)));
+            sigma += __uint_as_float(x0); c0 += __uint_as_float(x1); c1 += __uint_as_float(x2); c2 += __uint_as_float(x3);
+          }
         }
         if (g == 0) {
           c0 = 1.f / (1.f + expf(-(c0 + __ldg(p.head + kHeadRgbB + 0))));
@@ -254,26 +269,29 @@ __device__ __forceinline__ void slot_group_run4(const TcParams& p, Tc4Misc* misc
       }
       if (epi == EPI_SIGMA_OUT) {
         // ---- proposal tail: out = w_s . relu(acc) + b_s ------------------------------------------------------------------
-        sigma = epilogue_hidden4<EPI_SIGMA_OUT, F16>(acc, g, p.head) + (g == 0 ? __ldg(p.head + kHeadSigmaB) : 0.f);
+        sigma = epilogue_hidden4<EPI_SIGMA_OUT, F16, NG>(acc, g, p.head) + (g == 0 ? __ldg(p.head + kHeadSigmaB) : 0.f);
         if (has_next) begin_tile();
         const uint32_t xaddr = park_base + (uint32_t)row * 16u;
-        if (g == 1) asm volatile("st.shared.b32 [%0], %1;" ::"r"(xaddr), "r"(__float_as_uint(sigma)));
-        named_bar_sync(3, 256);
+        if (g != 0) asm volatile("st.shared.b32 [%0], %1;" ::"r"(xaddr + (uint32_t)(g - 1) * (kTileRows * 16)), "r"(__float_as_uint(sigma)));
+        named_bar_sync(3, 128 * NG);
         if (g == 0) {
-          uint32_t x0;
-          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(x0) : "r"(xaddr));
-          sigma += __uint_as_float(x0);
+#pragma unroll
+          for (int q = 0; q < NG - 1; ++q) {
+            uint32_t x0;
+            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(x0) : "r"(xaddr + (uint32_t)q * (kTileRows * 16)));
+            sigma += __uint_as_float(x0);
+          }
         }
         if (in.valid && g == 0) p.io.out[grow] = sigma;
         t_last += NB2_CLK() - ce;
         continue;
       }
       if (epi == EPI_RELU) {
-        epilogue_hidden4<EPI_RELU, F16>(acc, g, p.head);
+        epilogue_hidden4<EPI_RELU, F16, NG>(acc, g, p.head);
       } else if (epi == EPI_LINEAR) {
-        epilogue_hidden4<EPI_LINEAR, F16>(acc, g, p.head);
+        epilogue_hidden4<EPI_LINEAR, F16, NG>(acc, g, p.head);
       } else {   // EPI_RELU_SIGMA (each warpgroup keeps the dot product over its own columns; the bias is added once)
-        sigma = epilogue_hidden4<EPI_RELU_SIGMA, F16>(acc, g, p.head) + (g == 0 ? __ldg(p.head + kHeadSigmaB) : 0.f);
+        sigma = epilogue_hidden4<EPI_RELU_SIGMA, F16, NG>(acc, g, p.head) + (g == 0 ? __ldg(p.head + kHeadSigmaB) : 0.f);
       }
       tmem_st_wait4();      // the A operand is in TMEM ...
       tc_fence_before();    // ... ordered before the arrive that releases the MMA issuer
@@ -301,8 +319,12 @@ __device__ __forceinline__ void slot_group_run4(const TcParams& p, Tc4Misc* misc
   }
 }
 
-template <bool F16>
-__global__ void __launch_bounds__(kTcThreads, 1) mlp_tc4_kernel(const __grid_constant__ TcParams p) {
+// setmaxnreg moves registers inside the CTA's own allocation: what the slot groups gain must equal what warps 0-3 give up.
+// NG = 2: 384 threads launched at 168: roles 72 (-96 x 128), groups 216 (+48 x 256).
+// NG = 4: 640 threads launched at 96: roles 64 (-32 x 128), groups 104 (+8 x 512).
+template <int NG> struct Tc4Regs { static constexpr int role = (NG == 2) ? kRoleRegs : 64, group = (NG == 2) ? kGroupRegs : 104; };
+template <bool F16, int NG>
+__global__ void __launch_bounds__(128 + 128 * NG, 1) mlp_tc4_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ unsigned char smem_dyn[];
   const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   unsigned char* smem_al = smem_dyn + (smem_base - smem_u32(smem_dyn));
@@ -322,7 +344,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_tc4_kernel(const __grid_con
       mbar_init(smem_u32(&misc->w_peer[i]), 1);
       mbar_init(smem_u32(&misc->w_empty[i]), 1);
     }
-    mbar_init(smem_u32(&misc->a_ready), 16);   // every slot-group warp of both CTAs
+    mbar_init(smem_u32(&misc->a_ready), 8 * NG);   // every slot-group warp of both CTAs
     mbar_init(smem_u32(&misc->acc_full), 1);
     mbar_fence_init();
   }
@@ -339,7 +361,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_tc4_kernel(const __grid_con
   if (warp == 0) {
     // =========================== weight streamer: this CTA's half of every tile ==========================
     // per layer: K chunks in table order, each as [Wh, Wl] (cross-term sweep), then every Wh again (main sweep)
-    reg_dealloc<kRoleRegs>();
+    reg_dealloc<Tc4Regs<NG>::role>();
     if (lane == 0 && !(p.debug & 1)) {
       uint32_t stage = 0, phase = 0;
       for (int64_t it = 0; it < n_iters; ++it) {
@@ -363,7 +385,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_tc4_kernel(const __grid_con
       }
     }
   } else if (warp == 1) {
-    reg_dealloc<kRoleRegs>();
+    reg_dealloc<Tc4Regs<NG>::role>();
     if (lane == 0 && rank != 0 && !(p.debug & 1)) {
       // =========================== peer: relay "my half has landed" to the leader =====================
       uint32_t stage = 0, phase = 0;
@@ -441,11 +463,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_tc4_kernel(const __grid_con
       if (NB2_PROF_ON && lane == 0) { p.prof[blockIdx.x * 16 + 3] = t_wa; p.prof[blockIdx.x * 16 + 4] = t_ww; p.prof[blockIdx.x * 16 + 5] = NB2_CLK() - t0m; }
     }
   } else if (warp >= 4) {
-    reg_alloc<kGroupRegs>();
-    if (warp < 8) slot_group_run4<F16, 0>(p, misc, enc_base, park_base, tmem_base, n_iters, warp, lane, rank);
-    else slot_group_run4<F16, 1>(p, misc, enc_base, park_base, tmem_base, n_iters, warp, lane, rank);
+    reg_alloc<Tc4Regs<NG>::group>();
+    const int wgi = (warp - 4) >> 2;
+    if (wgi == 0) slot_group_run4<F16, NG, 0>(p, misc, enc_base, park_base, tmem_base, n_iters, warp, lane, rank);
+    else if (wgi == 1) slot_group_run4<F16, NG, 1>(p, misc, enc_base, park_base, tmem_base, n_iters, warp, lane, rank);
+    else if (NG == 4 && wgi == 2) slot_group_run4<F16, NG, (NG == 4 ? 2 : 0)>(p, misc, enc_base, park_base, tmem_base, n_iters, warp, lane, rank);
+    else if (NG == 4) slot_group_run4<F16, NG, (NG == 4 ? 3 : 0)>(p, misc, enc_base, park_base, tmem_base, n_iters, warp, lane, rank);
   } else {
-    reg_dealloc<kRoleRegs>();
+    reg_dealloc<Tc4Regs<NG>::role>();
   }
 
   tc_fence_before();
@@ -549,9 +574,9 @@ int selftest_umma_ts(nb2_handle* h, const void* A, const void* B, void* Bswz_scr
 }
 
 // ---- host side --------------------------------------------------------------------------------------------------------
-template <bool F16>
+template <bool F16, int NG>
 static int launch_tc4_impl(nb2_handle* h, TcParams& prm, cudaStream_t st) {
-  auto kern = mlp_tc4_kernel<F16>;
+  auto kern = mlp_tc4_kernel<F16, NG>;
   static bool attr_set = false;
   if (!attr_set) {
     NB2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Tc4Layout::kTotal));
@@ -559,7 +584,7 @@ static int launch_tc4_impl(nb2_handle* h, TcParams& prm, cudaStream_t st) {
   }
   int64_t ctas = (prm.n_tiles + 1) / 2 * 2;
   cudaLaunchConfig_t cfg = {};
-  cfg.blockDim = dim3(kTcThreads);
+  cfg.blockDim = dim3(128 + 128 * NG);
   cfg.dynamicSmemBytes = Tc4Layout::kTotal;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -593,8 +618,15 @@ int launch_mlp_tc4(nb2_handle* h, const TcParams& base, int precision, cudaStrea
         return NB2_ERR_UNSUPPORTED;
       }
   }
-  if (precision == NB2_PREC_FP16X3) return launch_tc4_impl<true>(h, prm, st);
-  if (precision == NB2_PREC_BF16X3) return launch_tc4_impl<false>(h, prm, st);
+  // NB2_TC_GROUPS = 2 | 4: epilogue warpgroups per tile
+  const char* ge = getenv("NB2_TC_GROUPS");
+  const int groups = ge ? atoi(ge) : 2;
+  if (groups != 2 && groups != 4) {
+    set_error("NB2_TC_GROUPS must be 2 or 4 (got %d)", groups);
+    return NB2_ERR_INVALID;
+  }
+  if (precision == NB2_PREC_FP16X3) return groups == 4 ? launch_tc4_impl<true, 4>(h, prm, st) : launch_tc4_impl<true, 2>(h, prm, st);
+  if (precision == NB2_PREC_BF16X3) return groups == 4 ? launch_tc4_impl<false, 4>(h, prm, st) : launch_tc4_impl<false, 2>(h, prm, st);
   set_error("mlp_forward: the TMEM-operand kernel runs the split precisions only (got %d)", precision);
   return NB2_ERR_INVALID;
 }

@@ -20,7 +20,7 @@ from oracle import nerf_oracle as O
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
-KEYS = ("NB2_TC_PAIR", "NB2_TC_CLUSTER", "NB2_TC_LOCKSTEP", "NB2_TC_NHALF", "NB2_TC_TMEMA")
+KEYS = ("NB2_TC_PAIR", "NB2_TC_CLUSTER", "NB2_TC_LOCKSTEP", "NB2_TC_NHALF", "NB2_TC_TMEMA", "NB2_TC_GROUPS")
 SERIAL = [
     {"NB2_TC_TMEMA": "0", "NB2_TC_PAIR": "1", "NB2_TC_LOCKSTEP": "1"},
     {"NB2_TC_TMEMA": "0", "NB2_TC_PAIR": "1", "NB2_TC_LOCKSTEP": "0"},
@@ -33,6 +33,7 @@ REORDERED = [
     {},                                                   # the defaults
     {"NB2_TC_TMEMA": "0", "NB2_TC_NHALF": "1"},          # N-half pipelined pair kernel
     {"NB2_TC_TMEMA": "1"},                                # TMEM-operand kernel (split precisions only)
+    {"NB2_TC_TMEMA": "1", "NB2_TC_GROUPS": "4"},         # ... with four epilogue warpgroups (640 threads)
 ]
 # max |rgb difference| against the layer-serial image: fp32 reordering noise through 13 layers and the resampling
 TOL = {"bf16": 3e-2, "fp16": 5e-3, "fp16x3": 1e-4, "bf16x3": 1e-4}

@@ -140,6 +140,55 @@ def stage_roles(precision, H=400):
         print(f"   {n:16s} {med[i]:14.0f}   per-iter {med[i] / max(med[11], 1):12.0f}")
 
 
+def stage_hbm(R=160000):
+    """Standalone HBM-bound ops at BASELINE config-2 sizes: achieved GB/s on the ALGORITHMIC bytes of SURVEY.md 8(d),
+    CUDA events over 20 launches, L2 flushed (512 MB memset) before each timed launch."""
+    import json
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0}
+    flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=DEV)
+    g = torch.Generator().manual_seed(3)
+    pose = nerf_b200.pose_spherical(30.0, -30.0, 4.0)[:3, :].to(DEV)
+    focal = float(nerf_b200.fov2Focal(0.6911112070083618, (400, 400))[0])
+    rays = ops.generate_rays(pose, 400, 400, focal, focal)[:R].contiguous()
+    base_z = torch.linspace(2.0, 6.0, 64, device=DEV)
+    jitter = torch.rand(R, 64, generator=g).to(DEV)
+    u = torch.rand(R, 129, generator=g).to(DEV)
+    z, pts = ops.sample_coarse(rays, base_z, 4.0 / 128, jitter=jitter)
+    sigma = (torch.rand(R, 64, generator=g) * 30.0).to(DEV)
+    dirs = rays[:, 3:].contiguous()
+    w = ops.weights_from_sigma(sigma, z, dirs)
+    zf = ops.resample(sigma, z, rays, 129, u=u)
+    rgbo = torch.rand(R, 128, 4, generator=g).to(DEV)
+    x3 = pts.view(-1, 3)[: R * 8].contiguous()          # 1.28 M points
+    cases = [
+        ("generate_rays (a1)", lambda: ops.generate_rays(pose, 400, 400, focal, focal), 160000 * 24),
+        ("sample_coarse (a3+a4)", lambda: ops.sample_coarse(rays, base_z, 4.0 / 128, jitter=jitter), R * (24 + 256 + 256 + 768)),
+        ("posenc L=10 (a5)", lambda: ops.posenc(x3, 10), x3.shape[0] * (12 + 240)),
+        ("ipe L=10 (a14)", lambda: ops.ipe(z, rays, 10, 0.01), R * 24 + R * 64 * 4 + R * 63 * (240 + 16)),
+        ("weights_from_sigma (a7)", lambda: ops.weights_from_sigma(sigma, z, dirs), R * (256 + 256 + 12 + 256)),
+        ("max_blur (a8)", lambda: ops.max_blur(w, 0.01), R * 512),
+        ("inverse_sample sort (a9)", lambda: ops.inverse_sample(w, z, 129, sort=True, u=u), R * (256 + 256 + 516 + 516 + 1032)),
+        ("resample fused (a7-a10)", lambda: ops.resample(sigma, z, rays, 129, u=u), R * (256 + 256 + 24 + 516 + 512)),
+        ("length2pts (a10)", lambda: ops.length2pts(rays, zf), R * (24 + 512 + 128 * 24)),
+        ("composite (a12)", lambda: ops.composite(rgbo, zf, dirs, white_bkg=True, near_far=(2.0, 6.0), want_weights=False), R * (128 * 20 + 12 + 16)),
+    ]
+    print(f"HBM ops at {R} rays; peak = {peaks['hbm_gbs']:.0f} GB/s (measured copy bandwidth)")
+    for name, fn, nbytes in cases:
+        for _ in range(3):
+            fn()
+        ts = []
+        for _ in range(20):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ts.sort()
+        ms = ts[len(ts) // 2]
+        gbs = nbytes / (ms * 1e-3) / 1e9
+        print(f"HBMOP {name:28s} {nbytes / 1e6:9.1f} MB  {ms * 1e3:9.1f} us  {gbs:8.1f} GB/s  {gbs / peaks['hbm_gbs']:.3f} of peak")
+
+
 def stage_microbench():
     """TMEM load/store bandwidth and the L2 -> shared weight-stream ceiling (nb2_microbench.cu)."""
     import ctypes
@@ -181,6 +230,8 @@ if __name__ == "__main__":
         stage_selftest()
     elif stage == "mlp":
         stage_mlp(sys.argv[2], sys.argv[3], int(sys.argv[4]) if len(sys.argv) > 4 else 1000)
+    elif stage == "hbm":
+        stage_hbm()
     elif stage == "microbench":
         stage_microbench()
     elif stage == "ummabench":
