@@ -218,6 +218,17 @@ int nb2_render_rays(nb2_handle* h, const nb2_render_params* p, const float* rays
 /* Kernel-launch counter (all launches made through this handle since creation). */
 int64_t nb2_launch_count(nb2_handle* h);
 
+/* ---- next rows (Ref-NeRF forward helpers) ------------------------------------------------------------
+ * Integrated directional encoding            nerf/ref_func.py:78-108 (closure built by generate_ide_fn, :51-76)
+ * xyz: (n, 3) directions, kappa_inv: (n) roughness; mat: (n_pow, n_pairs) spherical-harmonic coefficient matrix and
+ * ml: (2, n_pairs) int32 rows m then l, both built once on the host exactly as ref_func.py:38-76 does;
+ * out: (n, 2 n_pairs) = [real parts, imaginary parts].  n_pairs <= 36, n_pow <= 17 (deg_view <= 5). */
+int nb2_ide(nb2_handle* h, const float* xyz, const float* kappa_inv, int64_t n, const float* mat, const int* ml,
+            int n_pairs, int n_pow, float* out, void* stream);
+
+/* linear_to_srgb                              nerf/nerf_helper.py:50-56: elementwise over n floats. */
+int nb2_linear_to_srgb(nb2_handle* h, const float* linear, int64_t n, float* out, void* stream);
+
 /* Optional per-kernel timing of nb2_render_rays: four cudaEvent_t (created by the caller with timing
  * enabled) recorded on the render stream before launch 1 and after launches 1, 2, 3.  NULL disables. */
 int nb2_set_profile_events(nb2_handle* h, void* const* events4);

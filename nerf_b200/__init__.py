@@ -8,7 +8,8 @@ include/nerf_b200.h); there is no CPU or PyTorch fallback.
 from . import _lib, ops  # noqa: F401
 from ._lib import NB2Error  # noqa: F401
 from .ops import get_default_precision, set_default_precision  # noqa: F401
-from .nerf_helper import makeMLP, positional_encoding, saveModel  # noqa: F401
+from .nerf_helper import makeMLP, positional_encoding, saveModel, linear_to_srgb  # noqa: F401
+from .ref_func import generate_ide_fn  # noqa: F401
 from .nerf_base import NeRF, DecayLrScheduler  # noqa: F401
 from .mip_model import MipNeRF  # noqa: F401
 from .addtional import ProposalNetwork, LossPSNR, SoftL1Loss, ProposalLoss, getBounds  # noqa: F401

@@ -62,6 +62,8 @@ SIGNATURES = {
     "nb2_valid_sampler": (c_int, [c_vp, c_f32p, c_vp, c_f32p, c_vp, c_f32p, c_f32p, c_float, c_float, c_float, c_u64, c_i64, c_i64, c_i64,
                                   c_int, c_f32p, c_f32p, c_f32p, c_f32p, c_vp]),
     "nb2_get_bounds": (c_int, [c_vp, c_f32p, c_vp, c_i64, c_int, c_int, c_f32p, c_vp]),
+    "nb2_ide": (c_int, [c_vp, c_f32p, c_f32p, c_i64, c_f32p, c_vp, c_int, c_int, c_f32p, c_vp]),
+    "nb2_linear_to_srgb": (c_int, [c_vp, c_f32p, c_i64, c_f32p, c_vp]),
     "nb2_mlp_forward": (c_int, [c_vp, c_int, c_int, c_f32p, c_int, c_i64, c_f32p, c_vp]),
     "nb2_mlp_forward_encoded": (c_int, [c_vp, c_int, c_int, c_f32p, c_int, c_f32p, c_i64, c_f32p, c_vp]),
     "nb2_composite": (c_int, [c_vp, c_f32p, c_f32p, c_f32p, c_int, c_i64, c_int, c_int, c_float, c_float, c_f32p, c_f32p, c_f32p, c_f32p, c_vp]),

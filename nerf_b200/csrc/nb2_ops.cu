@@ -562,6 +562,79 @@ get_bounds_kernel(const float* __restrict__ w, const int64_t* __restrict__ inds,
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// next row 8f-3 (Ref-NeRF, forward): integrated directional encoding   /root/reference/nerf/ref_func.py:78-108
+//   out[p, i]           = Re((x + iy)^m_i) * (sum_k z^k mat[k, i]) * exp(-l_i (l_i + 1) / 2 * kappa_inv[p])
+//   out[p, n_pairs + i] = Im(...)                       for the (m_i, l_i) pairs of ref_func.py:38-49
+// One thread per direction; a block's 128 x 2 n_pairs tile is assembled in shared memory and written back coalesced.
+// ------------------------------------------------------------------------------------------
+constexpr int kIdeBlockPts = 128;
+constexpr int kIdeMaxPairs = 36;   // deg_view = 5
+constexpr int kIdeMaxPow = 17;     // l_max + 1
+__global__ void __launch_bounds__(kIdeBlockPts) ide_kernel(const float* __restrict__ xyz, const float* __restrict__ kappa_inv,
+                                                           int64_t n, int n_pairs, int n_pow, const float* __restrict__ mat,
+                                                           const int* __restrict__ ml, float* __restrict__ out) {
+  extern __shared__ float ide_smem[];
+  float* sh_mat = ide_smem;                        // [n_pow][n_pairs]
+  int* sh_ml = reinterpret_cast<int*>(sh_mat + kIdeMaxPow * kIdeMaxPairs);   // [2][n_pairs]: m then l
+  float* tile = reinterpret_cast<float*>(sh_ml + 2 * kIdeMaxPairs);         // [kIdeBlockPts][2 n_pairs]
+  for (int t = threadIdx.x; t < n_pow * n_pairs; t += blockDim.x) sh_mat[t] = __ldg(mat + t);
+  for (int t = threadIdx.x; t < 2 * n_pairs; t += blockDim.x) sh_ml[t] = __ldg(ml + t);
+  __syncthreads();
+  const int width = 2 * n_pairs;
+  const int64_t p0 = (int64_t)blockIdx.x * kIdeBlockPts;
+  const int npts = (int)min((int64_t)kIdeBlockPts, n - p0);
+  if ((int)threadIdx.x < npts) {
+    const int64_t p = p0 + threadIdx.x;
+    const float x = __ldg(xyz + 3 * p), y = __ldg(xyz + 3 * p + 1), z = __ldg(xyz + 3 * p + 2);
+    const float kinv = __ldg(kappa_inv + p);
+    float zp[kIdeMaxPow];          // z^k
+    float cr[kIdeMaxPow], ci[kIdeMaxPow];   // (x + iy)^m
+    zp[0] = 1.f; cr[0] = 1.f; ci[0] = 0.f;
+#pragma unroll
+    for (int k = 1; k < kIdeMaxPow; ++k) {
+      zp[k] = zp[k - 1] * z;
+      cr[k] = cr[k - 1] * x - ci[k - 1] * y;
+      ci[k] = cr[k - 1] * y + ci[k - 1] * x;
+    }
+    float* row = tile + threadIdx.x * width;
+    for (int i = 0; i < n_pairs; ++i) {
+      const int m = sh_ml[i], l = sh_ml[n_pairs + i];
+      float acc = 0.f;
+#pragma unroll
+      for (int k = 0; k < kIdeMaxPow; ++k)
+        if (k < n_pow) acc = fmaf(zp[k], sh_mat[k * n_pairs + i], acc);
+      const float att = expf(-(0.5f * (float)(l * (l + 1))) * kinv);
+      float pr = 0.f, pi = 0.f;
+#pragma unroll
+      for (int k = 0; k < kIdeMaxPow; ++k)
+        if (k == m) { pr = cr[k]; pi = ci[k]; }
+      row[i] = pr * acc * att;
+      row[n_pairs + i] = pi * acc * att;
+    }
+  }
+  __syncthreads();
+  float* dst = out + p0 * width;
+  const int total = npts * width;
+  if ((total & 3) == 0 && ((((uintptr_t)dst) & 15) == 0)) {
+    for (int t = threadIdx.x; t < total / 4; t += blockDim.x)
+      reinterpret_cast<float4*>(dst)[t] = reinterpret_cast<const float4*>(tile)[t];
+  } else {
+    for (int t = threadIdx.x; t < total; t += blockDim.x) dst[t] = tile[t];
+  }
+}
+
+// linear_to_srgb                                                        /root/reference/nerf/nerf_helper.py:50-56
+__global__ void linear_to_srgb_kernel(const float* __restrict__ lin, int64_t n, float* __restrict__ out) {
+  const float eps = 1.1920928955078125e-07f;   // torch.finfo(torch.float32).eps
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = __ldg(lin + i);
+    const float s0 = __fmul_rn(12.92f, v);
+    const float s1 = __fdiv_rn(__fsub_rn(__fmul_rn(211.f, powf(fmaxf(eps, v), 0.41666666f)), 11.f), 200.f);
+    out[i] = (v <= 0.0031308f) ? s0 : s1;
+  }
+}
+
 }  // namespace nb2
 
 // ==========================================================================================
@@ -778,6 +851,34 @@ extern "C" int nb2_get_bounds(nb2_handle* h, const float* weights, const int64_t
   NB2_CHECK_ARG(n_samples >= 1 && n_samples <= kMaxSamples && n_inds >= 2, "get_bounds: n_samples must be in [1,%d], n_inds >= 2", kMaxSamples);
   get_bounds_kernel<<<grid_for(n_rays, kWarpsPerBlock), 32 * kWarpsPerBlock, 0, (cudaStream_t)stream>>>(weights, inds, n_rays,
                                                                                                      n_samples, n_inds, out);
+  NB2_LAUNCH_CHECK(h);
+  return NB2_OK;
+}
+
+extern "C" int nb2_ide(nb2_handle* h, const float* xyz, const float* kappa_inv, int64_t n, const float* mat, const int* ml,
+                       int n_pairs, int n_pow, float* out, void* stream) {
+  NB2_H(h);
+  if (n == 0) return NB2_OK;
+  NB2_CHECK_ARG(xyz && kappa_inv && mat && ml && out && n > 0, "ide: bad arguments");
+  NB2_CHECK_ARG(n_pairs >= 1 && n_pairs <= kIdeMaxPairs && n_pow >= 1 && n_pow <= kIdeMaxPow,
+                "ide: at most %d (m, l) pairs and degree %d (deg_view <= 5, ref_func.py:67-68)", kIdeMaxPairs, kIdeMaxPow - 1);
+  const size_t smem = (size_t)(kIdeMaxPow * kIdeMaxPairs + 2 * kIdeMaxPairs + kIdeBlockPts * 2 * n_pairs) * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    NB2_CUDA(cudaFuncSetAttribute(ide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    attr_set = true;
+  }
+  ide_kernel<<<grid_for(n, kIdeBlockPts), kIdeBlockPts, smem, (cudaStream_t)stream>>>(xyz, kappa_inv, n, n_pairs, n_pow, mat, ml, out);
+  NB2_LAUNCH_CHECK(h);
+  return NB2_OK;
+}
+
+extern "C" int nb2_linear_to_srgb(nb2_handle* h, const float* linear, int64_t n, float* out, void* stream) {
+  NB2_H(h);
+  if (n == 0) return NB2_OK;
+  NB2_CHECK_ARG(linear && out && n > 0, "linear_to_srgb: bad arguments");
+  const int blocks = (int)std::min<int64_t>(grid_for(n, 256), 148 * 16);
+  linear_to_srgb_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(linear, n, out);
   NB2_LAUNCH_CHECK(h);
   return NB2_OK;
 }

@@ -40,3 +40,10 @@ def positional_encoding(x, freq_level):
     if x.dim() > 2:
         return enc.view(x.shape[0], x.shape[1], -1)
     return enc.view(*x.shape[:-1], -1)
+
+
+def linear_to_srgb(linear, eps=None):
+    """Reference nerf/nerf_helper.py:50-56 (eps is torch.finfo(float32).eps there; other values are not supported)."""
+    if eps is not None:
+        raise ValueError("linear_to_srgb: only the reference's default eps is implemented")
+    return ops.linear_to_srgb(linear)

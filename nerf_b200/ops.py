@@ -271,6 +271,26 @@ def composite(rgbo, z, dirs, white_bkg=False, near_far=None, want_weights=True):
     return rgb, w, depth, acc
 
 
+# ---- next rows: Ref-NeRF forward helpers ------------------------------------------------------------
+def ide(xyz, kappa_inv, mat, ml):
+    """Integrated directional encoding (ref_func.py:78-108).  mat (n_pow, n_pairs) fp32, ml (2, n_pairs) int32 on the device."""
+    xyz, kappa_inv = f32(xyz), f32(kappa_inv)
+    n = xyz.numel() // 3
+    if kappa_inv.numel() != n:
+        raise NB2Error(f"ide: kappa_inv must hold one value per direction ({kappa_inv.numel()} for {n} directions)")
+    n_pow, n_pairs = mat.shape
+    out = torch.empty((*xyz.shape[:-1], 2 * n_pairs), dtype=torch.float32, device=xyz.device)
+    check(load().nb2_ide(handle(xyz.device), ptr(xyz), ptr(kappa_inv), n, ptr(mat), ptr(ml), n_pairs, n_pow, ptr(out), stream_ptr()))
+    return out
+
+
+def linear_to_srgb(linear):
+    linear = f32(linear)
+    out = torch.empty_like(linear)
+    check(load().nb2_linear_to_srgb(handle(linear.device), ptr(linear), linear.numel(), ptr(out), stream_ptr()))
+    return out
+
+
 # ---- the fused path ---------------------------------------------------------------------------------
 def render_rays(rays, base_z, near, far, n_fine=128, white_bkg=False, precision=None, jitter=None, u=None, seed=0,
                 ray_offset=0, resolution=None, blur_alpha=0.01, softplus=False, debug=False, workspace=None):

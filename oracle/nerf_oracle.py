@@ -421,3 +421,53 @@ def philox_uniform(seed, ray_ids, n_samples, stream):
     sel = np.broadcast_to(smp & np.uint64(3), c[0].shape)
     x = np.choose(sel.astype(np.int64), c)
     return torch.from_numpy(((x >> np.uint64(8)).astype(np.float32) * np.float32(1.0 / 16777216.0)))
+
+
+# ---- Ref-NeRF directional front end (forward): integrated directional encoding, sRGB ---------------------
+def ide_tables(deg_view):
+    """(m, l) pairs and the (l_max + 1) x n_pairs coefficient matrix of /root/reference/nerf/ref_func.py:38-76
+    (associated-Legendre / spherical-harmonic coefficients, float64 arithmetic rounded to fp32 on assignment)."""
+    import math
+    if deg_view > 5:
+        raise ValueError("Only deg_view of at most 5 is numerically stable.")   # ref_func.py:67-68
+    ml = [(m, 2 ** i) for i in range(deg_view) for m in range(2 ** i + 1)]     # ref_func.py:38-49
+    l_max = 2 ** (deg_view - 1)
+
+    def gen_binom(a, k):                                                       # ref_func.py:10-12
+        return float(np.prod(a - np.arange(k))) / math.factorial(k)
+
+    def legendre(l, m, k):                                                     # ref_func.py:14-31
+        return ((-1) ** m * 2 ** l * math.factorial(l) / math.factorial(k) / math.factorial(l - k - m) *
+                gen_binom(0.5 * (l + k + m - 1.0), l))
+
+    def sph(l, m, k):                                                          # ref_func.py:33-36
+        return math.sqrt((2.0 * l + 1.0) * math.factorial(l - m) / (4.0 * math.pi * math.factorial(l + m))) * legendre(l, m, k)
+
+    mat = torch.zeros(l_max + 1, len(ml))
+    for i, (m, l) in enumerate(ml):
+        for k in range(l - m + 1):
+            mat[k, i] = sph(l, m, k)
+    return ml, mat
+
+
+def ide(xyz, kappa_inv, deg_view=4):
+    """integrated_dir_enc_fn, /root/reference/nerf/ref_func.py:78-108: xyz (..., 3), kappa_inv (..., 1) -> (..., 2 n_pairs)."""
+    ml, mat = ide_tables(deg_view)
+    mat = mat.to(xyz.device)
+    x, y, z = xyz[..., 0:1], xyz[..., 1:2], xyz[..., 2:3]
+    m_arr = torch.tensor([m for m, _ in ml], device=xyz.device)
+    l_arr = torch.tensor([l for _, l in ml], device=xyz.device)
+    vmz = torch.cat([z ** i for i in range(mat.shape[0])], dim=-1)
+    vmxy = torch.cat([(x + 1j * y) ** m for m in m_arr], dim=-1)
+    sph_harms = vmxy * (vmz @ mat)
+    sigma = 0.5 * l_arr * (l_arr + 1)
+    out = sph_harms * torch.exp(-sigma * kappa_inv)
+    return torch.cat([torch.real(out), torch.imag(out)], dim=-1)
+
+
+def linear_to_srgb(linear):
+    """/root/reference/nerf/nerf_helper.py:50-56."""
+    eps = torch.full((1,), torch.finfo(torch.float32).eps, device=linear.device)
+    srgb0 = 323 / 25 * linear
+    srgb1 = (211 * torch.maximum(eps, linear) ** (5 / 12) - 11) / 200
+    return torch.where(linear <= 0.0031308, srgb0, srgb1)

@@ -35,3 +35,10 @@ def gin():
     """The seeded inputs the golden outputs were produced from."""
     from tests.golden.make_golden import inputs_ops
     return inputs_ops()
+
+
+@pytest.fixture(scope="session")
+def golden_refnerf():
+    """Outputs of the unmodified reference's Ref-NeRF helpers (tests/golden/make_golden.py refnerf)."""
+    z = np.load(os.path.join(ROOT, "tests", "golden", "reference_outputs_refnerf.npz"))
+    return {k: torch.from_numpy(z[k]) for k in z.files}

@@ -226,5 +226,36 @@ def main():
     print("wrote", path, os.path.getsize(path) // 1024, "KiB;", len(arrays), "arrays; torch", torch.__version__)
 
 
+# ---- Ref-NeRF directional front end: a second, separate file so that the pinned one is never rewritten ----
+def inputs_refnerf():
+    g = {}
+    d = det_uniform((16, 16, 3), 41, -1.0, 1.0)
+    g["ide_dirs"] = d / d.norm(dim=-1, keepdim=True)
+    g["ide_kappa_inv"] = det_uniform((16, 16, 1), 42, 0.05, 1.0)          # roughness = softplus(. - 1) > 0 (ref_model.py:83)
+    g["srgb_lin"] = det_uniform((512, 3), 43, -0.01, 1.2)
+    return g
+
+
+def main_refnerf():
+    """nerf/ref_func.py needs `np.math` (removed in NumPy 2): shimmed with the stdlib module, no reference file is edited."""
+    import math
+    np.math = math
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    sys.path.insert(0, REF)
+    from nerf.ref_func import generate_ide_fn
+    from nerf.nerf_helper import linear_to_srgb
+    g = inputs_refnerf()
+    out = {}
+    for deg in (1, 4, 5):
+        out[f"ide_deg{deg}"] = generate_ide_fn(deg)(g["ide_dirs"], g["ide_kappa_inv"])
+    out["srgb"] = linear_to_srgb(g["srgb_lin"])
+    path = os.path.join(HERE, "reference_outputs_refnerf.npz")
+    np.savez_compressed(path, **{k: v.detach().cpu().numpy() for k, v in out.items()})
+    print("wrote", path, os.path.getsize(path) // 1024, "KiB;", len(out), "arrays; torch", torch.__version__)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "refnerf":
+        main_refnerf()
+    else:
+        main()

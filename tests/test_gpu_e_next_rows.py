@@ -49,3 +49,30 @@ def test_ipe_through_proposal_network(golden, gin, precision):
     tol = {"fp32": 2e-5, "fp16x3": 5e-5, "bf16": 6e-2}[precision]
     assert out.shape == ref.shape
     assert float((out - ref).abs().max()) <= tol * max(50.0, float(ref.abs().max())), float((out - ref).abs().max())
+
+
+@pytest.mark.parametrize("deg", [1, 4, 5])
+def test_integrated_directional_encoding(golden_refnerf, deg):
+    """generate_ide_fn(deg)(dirs, roughness) against the unmodified reference (ref_func.py:51-110).  The reference's own
+    fp32 result sits 7e-7 (deg 4) / 3e-6 (deg 5) from an fp64 evaluation (cancellation in the degree-8/16 polynomials)."""
+    from tests.golden.make_golden import inputs_refnerf
+    g = inputs_refnerf()
+    fn = nerf_b200.generate_ide_fn(deg)
+    out = fn(g["ide_dirs"].to(DEV), g["ide_kappa_inv"].to(DEV)).cpu()
+    ref = golden_refnerf[f"ide_deg{deg}"]
+    assert out.shape == ref.shape
+    tol = 1e-5 if deg == 5 else 2e-6
+    assert float((out - ref).abs().max()) <= tol, float((out - ref).abs().max())
+    # ragged size + flat input, against the oracle on the same device class
+    d = O.det_uniform((1000, 3), 77, -1.0, 1.0)
+    d = d / d.norm(dim=-1, keepdim=True)
+    k = O.det_uniform((1000, 1), 78, 0.01, 2.0)
+    assert float((fn(d.to(DEV), k.to(DEV)).cpu() - O.ide(d, k, deg)).abs().max()) <= tol
+    assert fn(d[:0].to(DEV), k[:0].to(DEV)).shape == (0, ref.shape[-1])
+
+
+def test_linear_to_srgb(golden_refnerf):
+    from tests.golden.make_golden import inputs_refnerf
+    g = inputs_refnerf()
+    out = nerf_b200.linear_to_srgb(g["srgb_lin"].to(DEV)).cpu()
+    assert float((out - golden_refnerf["srgb"]).abs().max()) <= 2e-6

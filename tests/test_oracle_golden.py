@@ -5,6 +5,7 @@ the fixtures it is bit-identical; a few ulp are allowed because the GPU box's ho
 different SIMD kernels for exp/sin/sum.
 """
 import numpy as np
+import pytest
 import torch
 
 from oracle import nerf_oracle as O
@@ -189,3 +190,33 @@ def test_training_side_callers(golden, gin):
     sp = O.make_params("proposal", 1, "smooth")
     out = O.proposal_forward(sp, golden["ipe_mu"], 10, encoded=golden["ipe_feat"])
     close(out, golden["prop_fwd_ipe"], rtol=1e-5, atol=1e-4)
+
+
+def test_refnerf_helpers_oracle_matches_reference(golden_refnerf):
+    """Ref-NeRF forward helpers: integrated directional encoding and linear_to_srgb, oracle vs the
+    unmodified reference's outputs (ref_func.py:51-110, nerf_helper.py:50-56)."""
+    from tests.golden.make_golden import inputs_refnerf
+    g = inputs_refnerf()
+    for deg in (1, 4, 5):
+        out = O.ide(g["ide_dirs"], g["ide_kappa_inv"], deg)
+        ref = golden_refnerf[f"ide_deg{deg}"]
+        assert out.shape == ref.shape == (16, 16, 2 * sum(2 ** i + 1 for i in range(deg)))
+        assert float((out - ref).abs().max()) <= 1e-6
+    assert float((O.linear_to_srgb(g["srgb_lin"]) - golden_refnerf["srgb"]).abs().max()) <= 1e-6
+
+
+def test_ide_tables_of_the_package_match_the_oracle():
+    """Host logic of nerf_b200.ref_func.generate_ide_fn: (m, l) list and coefficient matrix (no GPU needed)."""
+    import nerf_b200.ref_func as RF
+    for deg in (1, 2, 4, 5):
+        ml, mat = O.ide_tables(deg)
+        arr = RF.get_ml_array(deg)
+        assert [(int(m), int(l)) for m, l in arr.T] == ml
+        l_max = 2 ** (deg - 1)
+        m2 = torch.zeros(l_max + 1, arr.shape[1])
+        for i, (m, l) in enumerate(arr.T):
+            for k in range(l - m + 1):
+                m2[k, i] = RF.sph_harm_coeff(int(l), int(m), k)
+        assert torch.equal(m2, mat)
+    with pytest.raises(ValueError):
+        RF.generate_ide_fn(6)
