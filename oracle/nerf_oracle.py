@@ -453,7 +453,7 @@ def ide_tables(deg_view):
 def ide(xyz, kappa_inv, deg_view=4):
     """integrated_dir_enc_fn, /root/reference/nerf/ref_func.py:78-108: xyz (..., 3), kappa_inv (..., 1) -> (..., 2 n_pairs)."""
     ml, mat = ide_tables(deg_view)
-    mat = mat.to(xyz.device)
+    mat = mat.to(device=xyz.device, dtype=xyz.dtype)     # (float64 inputs: tolerance analysis with the same fp32 tables)
     x, y, z = xyz[..., 0:1], xyz[..., 1:2], xyz[..., 2:3]
     m_arr = torch.tensor([m for m, _ in ml], device=xyz.device)
     l_arr = torch.tensor([l for _, l in ml], device=xyz.device)

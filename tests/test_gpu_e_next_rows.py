@@ -63,11 +63,16 @@ def test_integrated_directional_encoding(golden_refnerf, deg):
     assert out.shape == ref.shape
     tol = 1e-5 if deg == 5 else 2e-6
     assert float((out - ref).abs().max()) <= tol, float((out - ref).abs().max())
-    # ragged size + flat input, against the oracle on the same device class
+    # ragged size + flat input + nearly unattenuated high degrees (kappa_inv down to 0.01).  The degree-8 / 16 polynomials
+    # cancel heavily there: the reference's own fp32 result is 2.4e-6 (deg 4) / 2.5e-4 (deg 5) from an fp64 evaluation of
+    # the same tables, so the kernel is held to that yardstick instead of to the reference's rounding
     d = O.det_uniform((1000, 3), 77, -1.0, 1.0)
     d = d / d.norm(dim=-1, keepdim=True)
     k = O.det_uniform((1000, 1), 78, 0.01, 2.0)
-    assert float((fn(d.to(DEV), k.to(DEV)).cpu() - O.ide(d, k, deg)).abs().max()) <= tol
+    ref64 = O.ide(d.double(), k.double(), deg)
+    e_ref = float((O.ide(d, k, deg).double() - ref64).abs().max())
+    e_gpu = float((fn(d.to(DEV), k.to(DEV)).cpu().double() - ref64).abs().max())
+    assert e_gpu <= 1.5 * e_ref + 1e-6, (e_gpu, e_ref)
     assert fn(d[:0].to(DEV), k[:0].to(DEV)).shape == (0, ref.shape[-1])
 
 
