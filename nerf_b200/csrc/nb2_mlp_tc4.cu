@@ -445,7 +445,8 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) mlp_tc4_kernel(const __grid
           // sweep 1: the small cross terms lo x Wh and hi x Wl
           for (int k = 0; k < L.kc; ++k) {
             wait_stage();
-            issue_chunk(L.a_src[k], L.ks0[k], true, idesc, k == 0);
+            // (bias-only chunk: its A column is the constant 1, whose lo half is 0 -- no lo x Wh term)
+            if (L.ks0[k] == 0) issue_chunk(L.a_src[k], 0, true, idesc, k == 0);
             release_stage();
             wait_stage();
             issue_chunk(L.a_src[k], L.ks0[k], false, idesc, false);
