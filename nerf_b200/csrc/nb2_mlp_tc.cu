@@ -453,7 +453,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_tc_kernel(const __grid_cons
 // resource: ~100 cycles of dependent issue latency per instruction), (b) the weight bytes each SM pulls from L2 and
 // writes to shared memory, so the 4 x 16 KB ring now covers 4 full K-chunks.
 //   leader CTA (rank 0): warp 1 issues all MMAs; waits for both CTAs' operands (a_ready counts 2 x 128 arrivals per slot)
-//                        and for both halves of each weight tile (own w_full + w_peer, relayed by the peer's warp 1);
+//                        and for both halves of each weight tile (one w_full barrier: own bulk copy + the peer's relaxed relay arrive);
 //   both CTAs          : warp 0 streams this CTA's half tiles; slot groups as in the single-CTA kernel; completion
 //                        (tcgen05.commit .multicast::cluster) is signalled into both CTAs.
 // Two-slot (single pass) mode runs the slots in lockstep: every weight half-tile feeds 2 x 4 MMAs = 1024 tensor cycles.
@@ -477,8 +477,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_tc2_kernel(const __grid_con
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kStages; ++i) {
-      mbar_init(smem_u32(&misc->w_full[i]), 1);
-      mbar_init(smem_u32(&misc->w_peer[i]), 1);
+      // leader: a stage is full when its own bulk copy has landed AND the peer has relayed that its half has landed
+      mbar_init(smem_u32(&misc->w_full[i]), rank == 0 ? 2 : 1);
       mbar_init(smem_u32(&misc->w_empty[i]), 1);
     }
     for (int s = 0; s < 2; ++s) {
@@ -534,7 +534,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_tc2_kernel(const __grid_con
           const int n_entries = net.layer[l].kc * (SPLIT ? 2 : 1) * kPasses;
           for (int e = 0; e < n_entries; ++e) {
             mbar_wait(smem_u32(&misc->w_full[stage]), phase);
-            mbar_arrive_remote_relaxed(smem_u32(&misc->w_peer[stage]), 0);
+            mbar_arrive_remote_relaxed(smem_u32(&misc->w_full[stage]), 0);
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
         }
@@ -565,7 +565,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_tc2_kernel(const __grid_con
               const uint32_t a_lo0 = umma_desc_lo(act_base + (uint32_t)L.a_src[k] * kTileBytes);   // slot 0, hi part
               { const long long c0 = NB2_CLK();
               mbar_wait(smem_u32(&misc->w_full[stage]), phase);
-              mbar_wait(smem_u32(&misc->w_peer[stage]), phase);
               t_ww += NB2_CLK() - c0; }
               tc_fence_after();
               const uint32_t w_lo0 = ring_lo + stage * (kTileBytes >> 4);
@@ -587,7 +586,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_tc2_kernel(const __grid_con
               if (SPLIT) {
                 { const long long c0 = NB2_CLK();
                 mbar_wait(smem_u32(&misc->w_full[stage]), phase);
-                mbar_wait(smem_u32(&misc->w_peer[stage]), phase);
                 t_ww += NB2_CLK() - c0; }
                 tc_fence_after();
                 const uint32_t wl = ring_lo + stage * (kTileBytes >> 4);

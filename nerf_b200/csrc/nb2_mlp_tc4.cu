@@ -31,7 +31,6 @@ constexpr int kALoCol = 384;
 struct Tc4Misc {
   uint64_t w_full[kStages4];
   uint64_t w_empty[kStages4];
-  uint64_t w_peer[kStages4];   // leader only: the peer CTA's half of the stage has landed
   uint64_t a_ready;            // leader only: next A operand complete in both CTAs (16 warp arrivals)
   uint64_t acc_full;
   uint32_t tmem_base;
@@ -340,8 +339,8 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) mlp_tc4_kernel(const __grid
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kStages4; ++i) {
-      mbar_init(smem_u32(&misc->w_full[i]), 1);
-      mbar_init(smem_u32(&misc->w_peer[i]), 1);
+      // leader: a stage is full when its own bulk copy has landed AND the peer has relayed that its half has landed
+      mbar_init(smem_u32(&misc->w_full[i]), rank == 0 ? 2 : 1);
       mbar_init(smem_u32(&misc->w_empty[i]), 1);
     }
     mbar_init(smem_u32(&misc->a_ready), 8 * NG);   // every slot-group warp of both CTAs
@@ -394,7 +393,7 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) mlp_tc4_kernel(const __grid
           const int n_entries = 3 * net.layer[l].kc;
           for (int e = 0; e < n_entries; ++e) {
             mbar_wait(smem_u32(&misc->w_full[stage]), phase);
-            mbar_arrive_remote_relaxed(smem_u32(&misc->w_peer[stage]), 0);
+            mbar_arrive_remote_relaxed(smem_u32(&misc->w_full[stage]), 0);
             if (++stage == kStages4) { stage = 0; phase ^= 1u; }
           }
         }
@@ -409,7 +408,6 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) mlp_tc4_kernel(const __grid
         if (no_weights) return;
         const long long c0 = NB2_CLK();
         mbar_wait(smem_u32(&misc->w_full[stage]), phase);
-        mbar_wait(smem_u32(&misc->w_peer[stage]), phase);
         t_ww += NB2_CLK() - c0;
         tc_fence_after();
       };
