@@ -166,6 +166,9 @@ def main():
     ap.add_argument("--precision", default="fp16x3", choices=["fp32", "fp16x3", "bf16x3", "fp16", "bf16"])
     ap.add_argument("--size", type=int, default=400)
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary precision modes / parity / cpu baseline")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak (default): every GPU renders its own --size x --size view; strong: ONE --size x --size image, its "
+                         "rays sharded contiguously across the GPUs and gathered (BASELINE configs[4] at --size 800)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -186,6 +189,10 @@ def main():
     K = args.steps
     H = Wd = args.size
     n_rays = H * Wd
+    strong = args.scaling == "strong"
+    from nerf_b200 import sharding
+    # strong scaling: this rank's contiguous slice of the one image
+    r_start, r_count = sharding.shard_range(n_rays, rank, world) if strong else (0, n_rays)
 
     # ---- model + inputs (random-init weights of the reference architecture, synthetic orbit poses) ----
     from oracle import nerf_oracle as O   # weight generator only here; the checker use is in parity_check()
@@ -196,18 +203,27 @@ def main():
     prop, net = prop.to(dev), net.to(dev)
     with torch.no_grad():
         prop._nb2_sync(); net._nb2_sync()
-    theta = -180.0 + 360.0 * rank / max(world, 1) + 30.0
+    theta = 30.0 if strong else -180.0 + 360.0 * rank / max(world, 1) + 30.0
     pose_host = nerf_b200.pose_spherical(theta, -30.0, 4.0)[:3, :].contiguous().pin_memory()
     pose = pose_host.to(dev)
     focal = float(nerf_b200.fov2Focal(FOV, (H, Wd))[0])
     base_z = torch.linspace(NEAR, FAR, N_COARSE, device=dev)
     flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)    # > 126 MB L2
     lib, h = _lib.load(), _lib.handle(dev)
-    gathered = torch.empty((world * n_rays, 3), dtype=torch.float32, device=dev) if world > 1 else None
+    gathered = torch.empty((world * n_rays, 3), dtype=torch.float32, device=dev) if (world > 1 and not strong) else None
     state = {"ws": None}
 
-    def step(precision, seed):
-        rays = ops.generate_rays(pose, H, Wd, focal, focal)
+    def step(precision, seed, pose_t=None):
+        pose_t = pose if pose_t is None else pose_t
+        if strong:
+            # device RNG is keyed on the GLOBAL ray id (ray_offset), so the image does not depend on the world size
+            rays = ops.generate_rays(pose_t, H, Wd, focal, focal, pix_offset=r_start, n_rays=r_count)
+            out = ops.render_rays(rays, base_z, NEAR, FAR, N_FINE, white_bkg=True, precision=precision, seed=seed,
+                                  ray_offset=r_start, workspace=state["ws"])
+            state["ws"] = out["_workspace"]
+            out["image_rows"] = sharding.gather_rows(out["rgb"], n_rays)     # the one exchange: final tile gather
+            return out
+        rays = ops.generate_rays(pose_t, H, Wd, focal, focal)
         out = ops.render_rays(rays, base_z, NEAR, FAR, N_FINE, white_bkg=True, precision=precision, seed=seed, workspace=state["ws"])
         state["ws"] = out["_workspace"]
         if world > 1:
@@ -258,14 +274,23 @@ def main():
             sampler.start()
         ms, launches, kms = timed(args.precision, K, kernel_events=True)
         clocks = sampler.stop() if rank == 0 else None
-        value = world * n_rays / (ms / 1e3)
+        total_rays = n_rays if strong else world * n_rays
+        value = total_rays / (ms / 1e3)
 
         # ---- e2e: public API, pose from pinned host memory, image back to pinned host memory, every step ----
         img_host = torch.empty((3, H, Wd), dtype=torch.float32).pin_memory()
         e_evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
 
+        rows_host = torch.empty((n_rays, 3), dtype=torch.float32).pin_memory() if strong else None
+
         def e2e_step(i):
             p_dev = pose_host.to(dev, non_blocking=True)
+            if strong:
+                # the sharded render has no single-call public API in the reference's surface: pose in, shard, gather, image out
+                res = step(args.precision, i, p_dev)
+                if rank == 0:
+                    rows_host.copy_(res["image_rows"], non_blocking=True)
+                return
             res = nerf_b200.render_image(net, prop, p_dev, (H, Wd), focal, NEAR, FAR, N_FINE, white_bkg=True, precision=args.precision, seed=i)
             img_host.copy_(res["rgb"], non_blocking=True)
         for i in range(W_):
@@ -282,17 +307,25 @@ def main():
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e_ms = float(t.item())
-        e2e = {"value": world * n_rays / (e_ms / 1e3), "unit": "rays/s", "h2d_bytes_per_step": pose_host.numel() * 4,
+        e2e = {"value": total_rays / (e_ms / 1e3), "unit": "rays/s", "h2d_bytes_per_step": pose_host.numel() * 4,
                "d2h_bytes_per_step": img_host.numel() * 4, "ms_per_step": e_ms}
 
+        shard_diff = None
+        if strong and world > 1 and not args.no_extras:
+            # the gathered image must not depend on the world size: rank 0 renders all rays itself with the same seed
+            res = step(args.precision, 4242)
+            if rank == 0:
+                full = ops.render_rays(ops.generate_rays(pose, H, Wd, focal, focal), base_z, NEAR, FAR, N_FINE, white_bkg=True,
+                                       precision=args.precision, seed=4242)
+                shard_diff = float((res["image_rows"] - full["rgb"]).abs().max())
         extras = {}
         if not args.no_extras:
             for mode in ("bf16", "fp16"):
                 if mode == args.precision:
                     continue
                 m_ms, _, m_k = timed(mode, max(5, K // 2), kernel_events=True)
-                extras[mode] = {"rays_per_s": world * n_rays / (m_ms / 1e3), "ms_per_step": m_ms,
-                                "fine_kernel_ms": m_k[2], "fine_kernel_tflops": FLOP_NERF_PER_RAY * n_rays / (m_k[2] * 1e-3) / 1e12}
+                extras[mode] = {"rays_per_s": total_rays / (m_ms / 1e3), "ms_per_step": m_ms,
+                                "fine_kernel_ms": m_k[2], "fine_kernel_tflops": FLOP_NERF_PER_RAY * r_count / (m_k[2] * 1e-3) / 1e12}
 
     if rank != 0:
         if world > 1:
@@ -301,13 +334,13 @@ def main():
 
     peaks = load_peaks()
     fine_ms = kms[2]
-    achieved = FLOP_NERF_PER_RAY * n_rays / (fine_ms * 1e-3) / 1e12
+    achieved = FLOP_NERF_PER_RAY * r_count / (fine_ms * 1e-3) / 1e12     # rank 0's launch
     passes = 3 if args.precision in ("fp16x3", "bf16x3") else 1
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
-                "traffic": (NCU_FINE_TRAFFIC_BYTES_160K.get(args.precision) if n_rays == 160000 else None),
+                "traffic": (NCU_FINE_TRAFFIC_BYTES_160K.get(args.precision) if r_count == 160000 else None),
                 "traffic_unit": "bytes per launch (ncu dram read+write; algorithmic 556 B/ray)",
                 "kernel": FINE_KERNEL[args.precision], "kernel_ms": fine_ms,
-                "algorithmic_flop_per_launch": FLOP_NERF_PER_RAY * n_rays, "peak_source": peaks["src"], "mma_passes_per_product": passes,
+                "algorithmic_flop_per_launch": FLOP_NERF_PER_RAY * r_count, "peak_source": peaks["src"], "mma_passes_per_product": passes,
                 "issued_tensor_tflops": achieved * passes * 528384.0 / 527872.0,
                 "frac_issued": achieved * passes * 528384.0 / 527872.0 / peaks["tflops"], "step_share": {"proposal_kernel_ms": kms[0], "resample_kernel_ms": kms[1], "fine_kernel_ms": kms[2]}}
     for mode, m in extras.items():
@@ -315,15 +348,18 @@ def main():
 
     line = {
         "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": K, "warmup": W_, "ms_per_step": ms,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": {"fp16x3": "f32-faithful: fp16 hi+lo split operands, 3 tcgen05 MMAs per product, f32 accumulate", "bf16x3": "bf16 hi+lo split, f32 accumulate",
                   "fp32": "f32 (CUDA cores)", "bf16": "bf16 operands, f32 accumulate", "fp16": "f16 operands, f32 accumulate"}[args.precision],
         "data": "synthetic",
-        "config": {"workload": f"Lego-shaped {H}x{Wd} orbit view per GPU, 64 coarse + 128 fine samples, proposal 4x256 + NeRF 8x256 (BASELINE configs[1])",
-                   "rays_per_gpu_per_step": n_rays, "precision": args.precision, "l2": "flushed between timed steps (512 MB memset)",
+        "config": {"workload": (f"ONE Lego-shaped {H}x{Wd} orbit view, rays sharded across the GPUs (BASELINE configs[4] at 800x800), " if strong
+                                else f"Lego-shaped {H}x{Wd} orbit view per GPU, ") + "64 coarse + 128 fine samples, proposal 4x256 + NeRF 8x256 (BASELINE configs[1])",
+                   "rays_per_gpu_per_step": r_count, "precision": args.precision, "l2": "flushed between timed steps (512 MB memset)",
                    "rng": "device Philox keyed on global ray id", "parallelism": f"ray-sharded x{world}, all_gather of rgb tiles"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "other_precisions": extras,
     }
+    if shard_diff is not None:
+        line["config"]["shard_invariance_max_abs_diff"] = shard_diff   # gathered image vs the same image rendered on one GPU
 
     if not args.no_extras and world == 1:
         # parity spot check against the oracle running the reference algorithm in PyTorch fp32 on the same GPU
