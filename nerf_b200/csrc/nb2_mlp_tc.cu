@@ -1,28 +1,38 @@
-// nb2_mlp_tc.cu — the per-sample MLP (proposal 4x256 / NeRF 8x256 + heads) as ONE persistent,
-// warp-specialised tcgen05 kernel.  NB2_PREC_BF16 / NB2_PREC_FP16 (single pass) and NB2_PREC_FP16X3 / NB2_PREC_BF16X3 (split).
+// nb2_mlp_tc.cu — the per-sample MLP (proposal 4x256 / NeRF 8x256 + heads) as ONE persistent, warp-specialised tcgen05
+// kernel with both operands in shared memory, plus the precision dispatch (launch_mlp_tc) for every tensor-core kernel.
 //
-//   warp 0      weight streamer: cp.async.bulk (TMA unit) of pre-swizzled 128x64 bf16 weight
-//               tiles from L2 into a 4-stage shared-memory ring, mbarrier full/empty handshake
-//   warp 1      MMA issuer: one thread issues tcgen05.mma (M=128, N=128, K=16) with both
-//               operands in shared memory and the fp32 accumulator in TMEM
+//   mlp_tc2_kernel   CTA pair (cta_group::2, M256 x N256 x K16): the DEFAULT for the single-pass precisions
+//                    (NB2_PREC_BF16 / NB2_PREC_FP16), two resident tiles in ping-pong; also the split precisions when the
+//                    TMEM-operand kernel (nb2_mlp_tc4.cu, their default) is switched off (NB2_TC_TMEMA=0).
+//   mlp_tc_kernel    single CTA (cta_group::1, N = 128 MMAs, optional cluster multicast of the weight tiles): the first
+//                    version, kept selectable (NB2_TC_PAIR=0); bit-identical results.
+//
+//   warp 0      weight streamer: cp.async.bulk (TMA unit) of pre-swizzled 128x64 16-bit weight tiles from L2 into a
+//               4-stage shared-memory ring, mbarrier full/empty handshake (pair kernel: each CTA streams its half of
+//               every tile, the peer relays "landed" onto the leader's stage-full barrier with a relaxed remote arrive)
+//   warp 1      MMA issuer (pair kernel: leader CTA only, the whole warp runs the loop and elects one lane per tcgen05
+//               instruction); fp32 accumulators in TMEM, completion through tcgen05.commit (multicast to both CTAs)
 //   warp 2      TMEM allocator
-//   warps 4..   one 128-thread "slot group" per resident 128-row tile: it produces the tile's
-//               first A operand (sample point -> sinusoidal encoding -> swizzled bf16 rows),
-//               and after every layer drains the accumulator from TMEM (tcgen05.ld), applies
-//               bias / ReLU, re-quantises to bf16 (hi [+ lo]) and writes the next layer's A
-//               operand in place.  The last epilogue evaluates the 128->3 / 256->1 heads on the
-//               fp32 values and either stores rgb-sigma or alpha-composites the ray.
+//   warps 4..   one 128-thread "slot group" per resident 128-row tile (split modes: both groups share the one tile by
+//               column halves): it produces the tile's first A operand (sample point -> sinusoidal encoding -> swizzled
+//               16-bit rows), and after every layer drains the accumulator from TMEM (tcgen05.ld), applies ReLU,
+//               re-quantises to 16 bit (hi [+ lo]) and writes the next layer's A operand in place.  The last epilogue
+//               evaluates the 128->3 / 256->1 heads on the fp32 values and either stores rgb-sigma or alpha-composites the
+//               ray.  The next tile's encoding and the direction encoding are computed while the group would otherwise
+//               wait for an accumulator.
 //
-// single pass (bf16 | fp16): two slots ping-pong, so one tile's epilogue overlaps the other tile's MMAs.
+// single pass (bf16 | fp16): two tiles; ping-pong (default in the pair kernel): the issuer alternates tiles layer by layer, so
+//                  one tile's epilogue runs under the other tile's MMAs; lockstep (NB2_TC_LOCKSTEP=1): both tiles consume every
+//                  weight stage back to back.
 // split (fp16x3 | bf16x3)   : every operand is split x = hi + lo (both 16-bit); each product is evaluated
 //                  as hi*hi + lo*hi + hi*lo with fp32 accumulation (fp16: 22-bit operands, ~2^-22 relative
-//                  per product, i.e. fp32-faithful; bf16: ~2^-16), one slot (the hi/lo activation pair
-//                  fills the shared memory of two slots).
+//                  per product, i.e. fp32-faithful; bf16: ~2^-16), one tile (the hi/lo activation pair
+//                  fills the shared memory of two tiles).
 //
 // Shared memory (bytes):  activations NSLOTS * (SPLIT ? 2 : 1) * 5 * 16 KB = 160 KB,
 //                         weight ring 4 * 16 KB = 64 KB, barriers + scratch < 1 KB.
-// TMEM: 512 columns; slot s owns columns [256 s, 256 s + 256) (128 lanes x 256 fp32).  Split mode has one
-//       slot and uses columns [256, 512) as a second accumulator for the hi*lo + lo*hi cross terms, so the
+// TMEM: 512 columns; tile s owns columns [256 s, 256 s + 256) (128 lanes x 256 fp32).  Split mode has one
+//       tile and uses columns [256, 512) as a second accumulator for the hi*lo + lo*hi cross terms, so the
 //       main accumulator sees a third of the (truncating) tensor-core additions; the two are summed in fp32
 //       by the epilogue.
 // Biases ride on the tensor core: encoding column 63 is the constant 1 and the matching weight column is

@@ -1,5 +1,9 @@
 // nb2_mlp_tc3.cu — the per-sample MLP as a CTA-pair tcgen05 kernel whose layers are pipelined by OUTPUT HALVES.
 //
+// STATUS: correct (runs the whole GPU suite with NB2_TC_NHALF=1) but SLOWER than the defaults, kept opt-in for the record:
+// an N = 128 tcgen05.mma with both operands in shared memory takes ~100 cycles instead of 64 (the shared-memory operand port
+// delivers ~64 B/cycle, which M256 x N256 x K16 exactly saturates), so halving N costs more than the hidden epilogue returns.
+//
 // Measured on B200 (profiles/r01_roles_pair2wg.txt, r01_microbench_tmem_l2.txt): in the layer-serial pair kernel
 // (nb2_mlp_tc.cu) the MMA issuer spends 36-50 % of every iteration waiting for the epilogue, although neither TMEM
 // reads (~900 B/cycle/SM) nor the L2 weight stream (60 B/cycle/SM) are near a limit: the time is the per-layer
@@ -7,7 +11,7 @@
 // This kernel takes most of that round trip off the critical path:
 //   * every 256-wide layer is issued as two N = 128 halves (M = 256 across the pair, K = 16), each with its own
 //     accumulator columns and its own completion barrier;
-//   * while half 1 accumulates, the slot groups drain half 0 from TMEM, add the bias, apply the activation and keep the
+//   * while half 1 accumulates, the slot groups drain half 0 from TMEM, apply the activation and keep the
 //     16-bit result in REGISTERS (the activation tiles are still being read by half 1's MMAs);
 //   * when half 1 completes they store those registers (K chunks 0-1 of the next layer's A operand), signal "chunks
 //     0-1 ready", and only then drain and store half 1 (K chunks 2-3), signalling "rest ready";
@@ -32,7 +36,7 @@ constexpr int kStages3 = 8;                     // weight ring: 8 x 8 KB (this C
 constexpr int kStageBytes3 = kTileBytes / 2;
 
 // Per-layer issue plan (host-built, lives in the kernel parameters): K chunks in issue order — first those reading
-// H chunks 0-1 (available early), then the rest — without the bias-only chunk.
+// H chunks 0-1 (available early), then the rest (encoding chunk, bias-only chunk).
 struct Tc3Layer {
   unsigned char n, n_early, pad0, pad1;
   unsigned char k[6];     // K chunk (index into TcLayer::a_src / the layer's weight tiles) per issue position

@@ -48,7 +48,6 @@ struct TcParams {
 struct TcMisc {
   uint64_t w_full[kStages];
   uint64_t w_empty[kStages];
-  uint64_t w_peer[kStages];   // pair kernel, leader only: the peer CTA's half of the weight tile has landed
   uint64_t a_ready[2];
   uint64_t acc_full[2];
   uint32_t tmem_base;
