@@ -274,6 +274,13 @@ def main():
             sampler.start()
         ms, launches, kms = timed(args.precision, K, kernel_events=True)
         clocks = sampler.stop() if rank == 0 else None
+        # sanity on what the timed loop produced (not timed): every pixel of the last step finite and inside [0, 1] + eps
+        last = step(args.precision, 1000 + K - 1)["rgb"]
+        sane = torch.tensor([float(torch.isfinite(last).all() and float(last.min()) > -1e-3 and float(last.max()) < 1.0 + 1e-3)], device=dev)
+        if world > 1:
+            dist.all_reduce(sane, op=dist.ReduceOp.MIN)
+        if float(sane.item()) != 1.0:
+            raise SystemExit("bench.py: the rendered image contains non-finite or out-of-range pixels")
         total_rays = n_rays if strong else world * n_rays
         value = total_rays / (ms / 1e3)
 
