@@ -291,6 +291,73 @@ __device__ __forceinline__ void rank_sort_warp(const float* sh_key, const int* s
 
 constexpr int kMaxDraw = 264;  // >= 129 (Mip), 193 merged (Ref)
 
+// Sorting the draws of one ray when only the values are needed (the fused resample): order them by their uniform u
+// first -- the inverse CDF is monotone, so that IS the sorted order except for 1-ulp effects at bin edges, and u is
+// uniform whatever the density looks like, so a counting sort over 128 buckets is O(n) with ~1 key per bucket -- then
+// repair with odd-even transposition passes until one pass swaps nothing (normally the first).  The result is the
+// sorted value sequence, i.e. exactly what rank_sort_warp / torch.sort produce; only the cost differs
+// (n^2 / 32 = 520 comparisons per lane before).
+constexpr int kSortBuckets = 128;
+__device__ __forceinline__ int u_bucket(float u) {
+  int b = (int)(u * (float)kSortBuckets);
+  return b < 0 ? 0 : (b >= kSortBuckets ? kSortBuckets - 1 : b);
+}
+__device__ __forceinline__ void sort_by_u_warp(const float* key, const float* su, int n, int* cnt, int* off, float* tmp_u,
+                                               float* tmp_z, float* out, int lane) {
+  for (int b = lane; b < kSortBuckets; b += 32) cnt[b] = 0;
+  __syncwarp();
+  for (int i = lane; i < n; i += 32) atomicAdd(&cnt[u_bucket(su[i])], 1);
+  __syncwarp();
+  int carry = 0;
+#pragma unroll
+  for (int base = 0; base < kSortBuckets; base += 32) {
+    const int v = cnt[base + lane];
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    off[base + lane] = carry + inc - v;
+    carry += __shfl_sync(0xffffffffu, inc, 31);
+  }
+  __syncwarp();
+  for (int b = lane; b < kSortBuckets; b += 32) cnt[b] = 0;
+  __syncwarp();
+  for (int i = lane; i < n; i += 32) {
+    const float uu = su[i];
+    const int b = u_bucket(uu);
+    const int p = off[b] + atomicAdd(&cnt[b], 1);
+    tmp_u[p] = uu;
+    tmp_z[p] = key[i];
+  }
+  __syncwarp();
+  for (int p = lane; p < n; p += 32) {
+    const float uu = tmp_u[p];
+    const int b = u_bucket(uu);
+    const int lo = off[b], hi = lo + cnt[b];
+    int r = 0;
+    for (int q = lo; q < hi; ++q) {
+      const float uq = tmp_u[q];
+      r += (uq < uu) || (uq == uu && q < p);
+    }
+    out[lo + r] = tmp_z[p];
+  }
+  __syncwarp();
+  for (;;) {
+    bool swapped = false;
+#pragma unroll
+    for (int phase = 0; phase < 2; ++phase) {
+      for (int a = phase + 2 * lane; a + 1 < n; a += 64) {
+        const float x = out[a], y = out[a + 1];
+        if (x > y) { out[a] = y; out[a + 1] = x; swapped = true; }
+      }
+      __syncwarp();
+    }
+    if (!__any_sync(0xffffffffu, swapped)) break;
+  }
+}
+
 // sample_pdf: bins (R,B), weights (R,B-1), u (R,N)
 __global__ void __launch_bounds__(32 * kWarpsPerBlock)
 sample_pdf_kernel(const float* __restrict__ bins, const float* __restrict__ weights, const float* __restrict__ u,
@@ -371,16 +438,22 @@ resample_kernel(int mode, const float* __restrict__ win /*weights or sigma (R,P)
   for (int i = lane; i < B; i += 32) s.bins[i] = __fmul_rn(0.5f, __fadd_rn(s.z[i + 1], s.z[i]));
   __syncwarp();
   build_cdf_warp(s.w + 1, s.cdf, B, lane);
+  const bool values_only = sort && below_out == nullptr && N <= kMaxSamples;   // the fused resample path
   for (int i = lane; i < N; i += 32) {
     float uu = u ? u[r * N + i] : philox_uniform(seed, (uint64_t)(ray_offset + r), (uint32_t)i, 1u);
     int b, a;
     s.key[i] = invert_cdf(s.cdf, s.bins, B, uu, &b, &a);
     s.pay[i] = b;
+    if (values_only) s.a[i] = uu;     // (the density / weight scratch is dead by now)
   }
   __syncwarp();
   const float* kk = s.key;
   const int* pp = s.pay;
-  if (sort) {
+  if (values_only) {
+    // w, bins, cdf, key_sorted and z are dead after the draws: counters, offsets, grouped u, grouped z, sorted output
+    sort_by_u_warp(s.key, s.a, N, reinterpret_cast<int*>(s.w), reinterpret_cast<int*>(s.bins), s.cdf, s.key_sorted, s.z, lane);
+    kk = s.z;
+  } else if (sort) {
     rank_sort_warp(s.key, s.pay, N, s.key_sorted, s.pay_sorted, lane);
     kk = s.key_sorted;
     pp = s.pay_sorted;

@@ -199,3 +199,30 @@ def test_argument_errors_are_loud(gin):
     m = nerf_b200.MipNeRF(10, 4)
     with pytest.raises(nerf_b200.NB2Error):
         m.forward(torch.zeros(2, 4, 6))  # module on the CPU
+
+
+def test_resample_value_sort_equals_rank_sort_at_scale():
+    """The fused resample orders its draws with a counting sort in u-space + repair passes; the staged inverse_sample
+    keeps the O(n^2) rank sort.  Same sorted values bit for bit, for flat, peaky and degenerate densities."""
+    R = 20000
+    g = torch.Generator().manual_seed(11)
+    z = (torch.linspace(2.0, 6.0, 64)[None, :] + torch.rand(R, 64, generator=g) * (4.0 / 128)).to(DEV)
+    rays = torch.cat((torch.zeros(R, 3), torch.randn(R, 3, generator=g)), -1).to(DEV)
+    sigma = (torch.randn(R, 64, generator=g) * 20.0)
+    sigma[:5000] = -1.0                                             # empty rays: uniform pdf
+    peak = torch.randint(0, 64, (5000,), generator=g)
+    sigma[5000:10000] = -1.0
+    sigma[torch.arange(5000, 10000), peak] = 3000.0                 # one opaque sample: all draws in one or two bins
+    sigma = sigma.to(DEV)
+    u = torch.rand(R, 129, generator=g)
+    u[:, 0] = 0.0
+    u[:100, 1] = u[:100, 2]                                         # exact ties
+    u = u.to(DEV)
+    zf = ops.resample(sigma, z, rays, 129, 0.01, u=u)
+    w = ops.max_blur(ops.weights_from_sigma(sigma, z, rays[:, 3:].contiguous()), 0.01)
+    zs, _ = ops.inverse_sample(w, z, 129, sort=True, u=u)
+    assert torch.equal(zf, zs[:, :-1])
+    assert bool((zf[:, 1:] >= zf[:, :-1]).all())
+    # device RNG path: sorted, inside the sampled range
+    zd = ops.resample(sigma, z, rays, 129, 0.01, seed=3)
+    assert bool((zd[:, 1:] >= zd[:, :-1]).all()) and float(zd.min()) >= 2.0 and float(zd.max()) <= 6.1
