@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(256) posenc_kernel(const float* __restrict__ x
     int l = j / dims, c = j % dims;
     float v = __ldg(x + (p0 + p) * dims + c) * exp2f((float)l);  // exact power-of-two scale
     float s, co;
-    sincosf(v, &s, &co);
+    sincos_any(v, s, co);
     pe_tile[p * width + 2 * dims * l + c] = s;
     pe_tile[p * width + 2 * dims * l + dims + c] = co;
   }
@@ -137,7 +137,7 @@ __global__ void ipe_kernel(const float* __restrict__ zvals, const float* __restr
       float scale = exp2f((float)l);
       float damp = expf(-0.5f * (scale * scale * diag));
       float s, co;
-      sincosf(scale * mu, &s, &co);
+      sincos_any(scale * mu, s, co);
       f[6 * l + k] = s * damp;
       f[6 * l + 3 + k] = co * damp;
     }

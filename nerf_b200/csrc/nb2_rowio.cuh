@@ -1,6 +1,6 @@
 // nb2_rowio.cuh — how an MLP row (one sample on one ray) gets its inputs.  Shared by the
 // CUDA-core and the tcgen05 MLP kernels so both see bit-identical sample points (the tensor kernels
-// evaluate the encoding with their own branch-free sin/cos, nb2_tc_device.cuh:enc_sincos, within 1e-7).
+// evaluate the encoding with their own branch-free sin/cos, nb2_common.cuh:enc_sincos, within 1e-7).
 #pragma once
 #include "nb2_common.cuh"
 

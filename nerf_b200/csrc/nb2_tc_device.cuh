@@ -67,30 +67,6 @@ struct TcLayout {
   static_assert(kTotal <= 232448, "exceeds 227 KB of shared memory");
 };
 
-// ---- branch-free sin / cos for the fused encoders ------------------------------------------------------------------
-// Three-constant Cody-Waite reduction by pi/2 and the Cephes single-precision minimax polynomials on [-pi/4, pi/4]:
-// max |error| 9.3e-8 against fp64 for |x| <= 3300 (the largest argument is 2^9 * |position|; checked on the host over
-// 2e7 arguments), i.e. the accuracy of sincosf.  Unlike sincosf there is no large-argument branch, so the 30 (position)
-// + 12 (direction) evaluations of a row are straight-line code the scheduler can interleave: the library call made the
-// encoding ~350 cycles per evaluation with two warps per scheduler (profiles/r01_roles_*).
-__device__ __forceinline__ void enc_sincos(float x, float& sn, float& cs) {
-  const int q = __float2int_rn(x * 0.636619772f);
-  const float j = __int2float_rn(q);
-  float t = fmaf(-j, 1.57079601e+00f, x);
-  t = fmaf(-j, 3.13916473e-07f, t);
-  t = fmaf(-j, 5.39030253e-15f, t);
-  const float s = t * t;
-  float ps = fmaf(s, -1.9515295891e-4f, 8.3321608736e-3f);
-  ps = fmaf(ps, s, -1.6666654611e-1f);
-  ps = fmaf(ps * s, t, t);
-  float pc = fmaf(s, 2.443315711809948e-5f, -1.388731625493765e-3f);
-  pc = fmaf(pc, s, 4.166664568298827e-2f);
-  pc = fmaf(pc * s, s, fmaf(s, -0.5f, 1.0f));
-  const float rs = (q & 1) ? pc : ps, rc = (q & 1) ? ps : pc;
-  sn = (q & 2) ? -rs : rs;
-  cs = ((q + 1) & 2) ? -rc : rc;
-}
-
 // ---- writing one row of an A-operand tile ---------------------------------------------------
 // v[0..8) are 8 consecutive columns starting at column `col` (multiple of 8) of row `row`.
 template <bool SPLIT, bool F16>
