@@ -15,7 +15,9 @@
  *     without synchronising.  Outputs are pre-allocated by the caller; the library never
  *     allocates or frees caller-visible memory (scratch comes from the caller-provided
  *     workspace, sized by nb2_render_workspace_bytes()).
- *   - one handle per device per process; a handle owns only its packed-weight buffers.
+ *   - one handle per device per process; a handle owns only its packed-weight buffers and per-device launch state.
+ *     Every entry point switches to the handle's device for the duration of the call and restores the caller's
+ *     current device, so handles of several GPUs can be driven from one thread.
  *   - `jitter` / `u` pointers may be NULL: the library then draws the uniforms on the device
  *     with Philox4x32-10 keyed by (seed, ray_offset + ray index, sample index), so results do
  *     not depend on how rays are sharded across launches or GPUs.
@@ -29,11 +31,14 @@
 extern "C" {
 #endif
 
-#define NB2_VERSION 100 /* 0.1.0 */
+#define NB2_VERSION 200 /* 0.2.0 */
 
 typedef struct nb2_handle nb2_handle;
 
-/* Network ids (layer tables are fixed by the reference architectures). */
+/* Network kinds (layer tables are fixed by the reference architectures).  A handle holds up to 64 packed networks
+ * ("slots"); slot ids 0 and 1 always exist and have kinds NB2_NET_PROPOSAL and NB2_NET_NERF, further slots come from
+ * nb2_net_create (several module instances -- train / eval / EMA copies -- each own their packed image).  Every
+ * `net_id` argument below is a slot id. */
 enum {
   NB2_NET_PROPOSAL = 0, /* nerf/addtional.py:53-72   ProposalNetwork(10, 256): 63-256-256-256-256-1 */
   NB2_NET_NERF = 1      /* nerf/mip_model.py:14-38   MipNeRF(10, 4, 256): 8x256 trunk + heads       */
@@ -86,6 +91,9 @@ int nb2_pack_weights(nb2_handle* h, int net_id, const float* const* W_ptrs_host,
                      const float* const* b_ptrs_host, int n_layers, int pos_levels,
                      int dir_levels, int hidden, void* stream);
 int nb2_weights_version(nb2_handle* h, int net_id);
+/* Allocate / release an additional packed-network slot of `kind`; *net_id_out >= 2. */
+int nb2_net_create(nb2_handle* h, int kind, int* net_id_out);
+int nb2_net_destroy(nb2_handle* h, int net_id);
 
 /* ---- a1: pixel grid -> camera rays           nerf/procedures.py:43-51,64 ----------------
  * pose: 12 floats (3x4 row-major, device).  rays_out: (n_rays, 6) = [origin, R*(cx/fx, cy/fy, -1)],
@@ -142,11 +150,12 @@ int nb2_search_cdf(nb2_handle* h, const float* cdf, const float* u, int64_t n_ra
                    int n_cdf, int n_draw, int64_t* inds_out, void* stream);
 
 /* ---- a7+a8+a9+drop-last fused (render path)   nerf/procedures.py:68-70,76 ----------------
- * sigma (R,P) raw proposal density, z (R,P), rays (R,6) -> z_fine (R, n_draw-1) ascending. */
+ * sigma (R,P) raw proposal density, z (R,P), rays (R,6) -> z_fine (R, n_draw-1) ascending;
+ * below_out (R, n_draw-1) int64 or NULL: bin index of every kept sample (costs the stable rank sort). */
 int nb2_resample(nb2_handle* h, const float* sigma, const float* z, const float* rays,
                  const float* u, uint64_t seed, int64_t ray_offset, int64_t n_rays,
                  int n_samples, int n_draw, float blur_alpha, int flags, float* z_fine_out,
-                 void* stream);
+                 int64_t* below_out, void* stream);
 
 /* ---- a10: depths -> sample points             nerf/nerf_base.py:52-56 -------------------
  * rays (R,6), z (R,P) -> (R,P,6) = [o + z*d, d]. */
@@ -195,7 +204,8 @@ int nb2_composite(nb2_handle* h, const float* rgbo, const float* z, const float*
 /* ---- the fused path: render_image's per-ray work   nerf/procedures.py:64-85 --------------
  * rays (R,6) -> rgb (R,3), depth (R) or NULL, acc (R) or NULL.  Three launches: fused
  * sample+encode+proposal-MLP, resample, fused encode+NeRF-MLP+composite.
- * Optional debug outputs (NULL to skip): z_coarse (R,Pc), sigma_prop (R,Pc), z_fine (R,Pf). */
+ * Optional debug outputs (NULL to skip): z_coarse (R,Pc), sigma_prop (R,Pc), z_fine (R,Pf) and below_fine (R,Pf)
+ * int64 = the cdf bin index of every kept fine sample (inverseSample's second result, nerf/utils.py:41-43). */
 typedef struct nb2_render_params {
   int n_coarse;       /* 64   RENDER_COARSE_PNUM, nerf/procedures.py:22 */
   int n_fine;         /* 128  sample_num; n_fine+1 are drawn, the largest dropped */
@@ -206,14 +216,32 @@ typedef struct nb2_render_params {
   int precision;      /* NB2_PREC_* */
   uint64_t seed;      /* Philox key when jitter/u are NULL */
   int64_t ray_offset; /* global index of rays[0] (shard invariance) */
+  int prop_net_id;    /* packed-network slots to render with; 0 / 0 (a zeroed struct) selects the default slots 0 / 1 */
+  int nerf_net_id;
+  /* Multi-GPU gather fused into the compositing epilogue: when n_peers > 0 the rgb row of ray r is also
+   * stored at peer_rgb[q] + 3 * (ray_offset + r) for q < n_peers <= 8 -- device pointers to the full (n_total_rays, 3)
+   * image buffers of the other GPUs, mapped with nb2_ipc_open; the stores travel over NVLink and no gather kernel or
+   * collective follows (callers fence with a barrier before reading the image). */
+  int n_peers;
+  int reserved;
+  float* peer_rgb[8];
 } nb2_render_params;
 
 int64_t nb2_render_workspace_bytes(int64_t n_rays, const nb2_render_params* p);
 int nb2_render_rays(nb2_handle* h, const nb2_render_params* p, const float* rays,
                     const float* base_z, const float* jitter, const float* u, int64_t n_rays,
                     float* rgb_out, float* depth_out, float* acc_out, float* z_coarse_out,
-                    float* sigma_prop_out, float* z_fine_out, void* workspace,
+                    float* sigma_prop_out, float* z_fine_out, int64_t* below_fine_out, void* workspace,
                     int64_t workspace_bytes, void* stream);
+
+/* ---- peer memory for the fused gather (one process per GPU, CUDA IPC over NVLink / NVSwitch) -----------------
+ * nb2_ipc_alloc: cudaMalloc `bytes` on the handle's device and export a 64-byte IPC handle for it.
+ * nb2_ipc_open : map another process's allocation into this process (peer access is enabled on demand).
+ * nb2_ipc_close / nb2_ipc_free: unmap / release. */
+int nb2_ipc_alloc(nb2_handle* h, int64_t bytes, void** dev_ptr_out, void* ipc_handle64_out);
+int nb2_ipc_open(nb2_handle* h, const void* ipc_handle64, void** dev_ptr_out);
+int nb2_ipc_close(nb2_handle* h, void* dev_ptr);
+int nb2_ipc_free(nb2_handle* h, void* dev_ptr);
 
 /* Kernel-launch counter (all launches made through this handle since creation). */
 int64_t nb2_launch_count(nb2_handle* h);
@@ -232,39 +260,6 @@ int nb2_linear_to_srgb(nb2_handle* h, const float* linear, int64_t n, float* out
 /* Optional per-kernel timing of nb2_render_rays: four cudaEvent_t (created by the caller with timing
  * enabled) recorded on the render stream before launch 1 and after launches 1, 2, 3.  NULL disables. */
 int nb2_set_profile_events(nb2_handle* h, void* const* events4);
-
-/* Debug instrumentation of the tensor-core MLP kernel.  First call (any arguments) enables it; later calls
- * synchronise the device and copy 16 cycle counters per CTA of the LAST launch into out_host (n_ctas <= 256):
- * weight-streamer / MMA-issuer / slot-group wait and work times (see nb2_api.cu). */
-int nb2_debug_tc_profile(nb2_handle* h, long long* out_host, int n_ctas);
-
-/* Debug: MMA micro-benchmark / 2-CTA convention check.  mode 0: cta_group::1 M128 N128, 1: cta_group::1 M128 N256,
- * 2: cta_group::2 M256 N256.  A, B: (256 x 64) bf16 row-major; D_out: (256 x 256) fp32 (rows/cols the mode covers);
- * cycles_out[cta]: cycles per MMA instruction on every SM (all SMs run the loop concurrently).
- * flags: stressors running beside the MMA loop (see nb2_mlp_tc.cu); gsrc_1mb: 1 MB of device memory to stream from. */
-int nb2_debug_umma_bench(nb2_handle* h, const void* A_bf16, const void* B_bf16, float* D_out, long long* cycles_out,
-                         int mode, int iters, int flags, const void* gsrc_1mb, void* stream);
-
-/* Debug: hardware micro-benchmarks behind the MLP kernel's design numbers (nb2_microbench.cu).
- * kind 0 / 1: TMEM -> register load / register -> TMEM store bandwidth (a0 = warps 4|8|16, a1 = loads in flight per
- * wait 1|2|4, a2 = sweeps over the 128 x 512 x 4 B TMEM);  kind 2: L2 -> shared bulk-copy stream of 16 KB tiles that
- * every CTA reads in the same order (a0 = multicast cluster size 1|2|4|8, a1 = ring stages <= 12, a2 = loads per CTA,
- * a3 = per-cluster address skew in tiles, a4 = 1: even/odd CTAs read alternate tiles like a CTA pair; src = n_chunks x 16 KB).
- * out_dev: 3 x int64 per CTA (cycles, bytes, checksum) in device memory; *grid_out = CTAs launched. */
-int nb2_debug_microbench(nb2_handle* h, int kind, int a0, int a1, int a2, int a3, int a4, const void* src, int n_chunks,
-                         long long* out_dev, int* grid_out, void* stream);
-
-/* Device-side self-test of the tcgen05 building blocks: D (128x128 fp32) = A (128x64 bf16,
- * row-major) * B^T (128x64 bf16, row-major), computed by ONE UMMA sequence through the same
- * operand swizzle, descriptors, bulk copy, commit and TMEM read-out the MLP kernel uses.
- * scratch_16k: 16 KB of device scratch. */
-int nb2_selftest_umma(nb2_handle* h, const void* A_bf16, const void* B_bf16, void* scratch_16k,
-                      float* D_out, void* stream);
-
-/* Same product with A written to tensor memory by tcgen05.st and consumed by the A-from-TMEM form of tcgen05.mma
- * (the operand convention of the split-precision kernel in nb2_mlp_tc4.cu). */
-int nb2_selftest_umma_ts(nb2_handle* h, const void* A_bf16, const void* B_bf16, void* scratch_16k,
-                         float* D_out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -35,6 +35,9 @@ class RenderParams(ctypes.Structure):
         ("resolution", c_float), ("blur_alpha", c_float),
         ("flags", c_int), ("precision", c_int),
         ("seed", c_u64), ("ray_offset", c_i64),
+        ("prop_net_id", c_int), ("nerf_net_id", c_int),
+        ("n_peers", c_int), ("reserved", c_int),
+        ("peer_rgb", c_vp * 8),
     ]
 
 
@@ -47,6 +50,12 @@ SIGNATURES = {
     "nb2_destroy": (c_int, [c_vp]),
     "nb2_pack_weights": (c_int, [c_vp, c_int, ctypes.POINTER(c_vp), ctypes.POINTER(c_vp), c_int, c_int, c_int, c_int, c_vp]),
     "nb2_weights_version": (c_int, [c_vp, c_int]),
+    "nb2_net_create": (c_int, [c_vp, c_int, ctypes.POINTER(c_int)]),
+    "nb2_net_destroy": (c_int, [c_vp, c_int]),
+    "nb2_ipc_alloc": (c_int, [c_vp, c_i64, ctypes.POINTER(c_vp), c_vp]),
+    "nb2_ipc_open": (c_int, [c_vp, c_vp, ctypes.POINTER(c_vp)]),
+    "nb2_ipc_close": (c_int, [c_vp, c_vp]),
+    "nb2_ipc_free": (c_int, [c_vp, c_vp]),
     "nb2_generate_rays": (c_int, [c_vp, c_f32p, c_int, c_int, c_float, c_float, c_i64, c_i64, c_f32p, c_vp]),
     "nb2_sample_coarse": (c_int, [c_vp, c_f32p, c_f32p, c_f32p, c_float, c_u64, c_i64, c_i64, c_int, c_f32p, c_f32p, c_vp]),
     "nb2_posenc": (c_int, [c_vp, c_f32p, c_i64, c_int, c_int, c_f32p, c_vp]),
@@ -56,7 +65,7 @@ SIGNATURES = {
     "nb2_sample_pdf": (c_int, [c_vp, c_f32p, c_f32p, c_f32p, c_u64, c_i64, c_i64, c_int, c_int, c_f32p, c_vp, c_vp, c_vp]),
     "nb2_inverse_sample": (c_int, [c_vp, c_f32p, c_f32p, c_f32p, c_u64, c_i64, c_i64, c_int, c_int, c_int, c_f32p, c_vp, c_vp]),
     "nb2_search_cdf": (c_int, [c_vp, c_f32p, c_f32p, c_i64, c_int, c_int, c_vp, c_vp]),
-    "nb2_resample": (c_int, [c_vp, c_f32p, c_f32p, c_f32p, c_f32p, c_u64, c_i64, c_i64, c_int, c_int, c_float, c_int, c_f32p, c_vp]),
+    "nb2_resample": (c_int, [c_vp, c_f32p, c_f32p, c_f32p, c_f32p, c_u64, c_i64, c_i64, c_int, c_int, c_float, c_int, c_f32p, c_vp, c_vp]),
     "nb2_length2pts": (c_int, [c_vp, c_f32p, c_f32p, c_i64, c_int, c_f32p, c_vp]),
     "nb2_coarse_fine_merge": (c_int, [c_vp, c_f32p, c_f32p, c_f32p, c_i64, c_int, c_int, c_f32p, c_f32p, c_vp]),
     "nb2_valid_sampler": (c_int, [c_vp, c_f32p, c_vp, c_f32p, c_vp, c_f32p, c_f32p, c_float, c_float, c_float, c_u64, c_i64, c_i64, c_i64,
@@ -69,7 +78,7 @@ SIGNATURES = {
     "nb2_composite": (c_int, [c_vp, c_f32p, c_f32p, c_f32p, c_int, c_i64, c_int, c_int, c_float, c_float, c_f32p, c_f32p, c_f32p, c_f32p, c_vp]),
     "nb2_render_workspace_bytes": (c_i64, [c_i64, ctypes.POINTER(RenderParams)]),
     "nb2_render_rays": (c_int, [c_vp, ctypes.POINTER(RenderParams), c_f32p, c_f32p, c_f32p, c_f32p, c_i64, c_f32p, c_f32p,
-                                c_f32p, c_f32p, c_f32p, c_f32p, c_vp, c_i64, c_vp]),
+                                c_f32p, c_f32p, c_f32p, c_f32p, c_vp, c_vp, c_i64, c_vp]),
     "nb2_launch_count": (c_i64, [c_vp]),
     "nb2_set_profile_events": (c_int, [c_vp, ctypes.POINTER(c_vp)]),
     "nb2_debug_tc_profile": (c_int, [c_vp, ctypes.POINTER(ctypes.c_longlong), c_int]),
@@ -133,8 +142,10 @@ def handle(device=None):
     return h
 
 
-def stream_ptr():
-    return c_vp(torch.cuda.current_stream().cuda_stream)
+def stream_ptr(device=None):
+    """The current CUDA stream of `device` (default: the current device).  Ops pass the device of their tensors, so a
+    tensor on a non-current GPU is processed on that GPU's stream by that GPU's handle."""
+    return c_vp(torch.cuda.current_stream(device).cuda_stream)
 
 
 def ptr(t):

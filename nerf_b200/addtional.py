@@ -44,7 +44,7 @@ class LossPSNR(nn.Module):
 
 
 class ProposalNetwork(PackedModule):
-    _nb2_net_id = _lib.NET_PROPOSAL
+    _nb2_kind = _lib.NET_PROPOSAL
 
     @staticmethod
     def init_weight(m):
@@ -91,15 +91,14 @@ class ProposalNetwork(PackedModule):
 
     def forward(self, pts: torch.Tensor, encoded_pt: torch.Tensor = None) -> torch.Tensor:
         """pts (ray_num, point_num, 3) -> raw density (ray_num, point_num)."""
-        if torch.is_grad_enabled() and pts.requires_grad:
-            raise _lib.NB2Error("ProposalNetwork.forward: backward is not built yet; call under torch.no_grad()")
-        self._nb2_sync()
+        self._nb2_refuse_autograd(pts, encoded_pt)
+        net_id = self._nb2_sync()
         if encoded_pt is not None:
             # the reference views encoded_pt as (R, P, position_dims) and concatenates it behind the raw points
             enc = encoded_pt.reshape(-1, self.position_dims)
-            out = ops.mlp_forward_encoded(_lib.NET_PROPOSAL, pts.reshape(-1, 3), enc, self.precision)
+            out = ops.mlp_forward_encoded(net_id, pts.reshape(-1, 3), enc, self.precision)
             return out.view(pts.shape[0], pts.shape[1])
-        out = ops.mlp_forward(_lib.NET_PROPOSAL, pts.reshape(-1, 3), self.precision)
+        out = ops.mlp_forward(net_id, pts.reshape(-1, 3), self.precision)
         return out.view(pts.shape[0], pts.shape[1])
 
     @staticmethod

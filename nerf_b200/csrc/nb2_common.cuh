@@ -6,8 +6,10 @@
 #include <stdio.h>
 #include <string.h>
 #include <algorithm>
+#include <unordered_map>
 
 #include "../../include/nerf_b200.h"
+#include "../../include/nerf_b200_debug.h"
 
 #if defined(__CUDA_ARCH__) && !defined(__CUDA_ARCH_FEAT_SM100_ALL)
 #error "libnerfb200 is written for sm_100a only: compile with -gencode arch=compute_100a,code=sm_100a"
@@ -106,6 +108,8 @@ struct SimtNet {
 };
 
 struct PackedNet {
+  bool in_use = false;   // slot allocated (slots 0 and 1 always are)
+  int kind = 0;          // NB2_NET_PROPOSAL | NB2_NET_NERF
   bool packed = false;
   int version = 0;
   int pos_levels = 0, dir_levels = 0;
@@ -124,13 +128,26 @@ constexpr int kHeadFloats = 652;
 
 }  // namespace nb2
 
+namespace nb2 {
+constexpr int kMaxNets = 64;   // packed-network slots per handle (0 / 1: the default proposal / NeRF slots)
+constexpr int kMaxPeers = 8;   // GPUs of one node whose image buffers the fused render can write directly
+// Per-kernel launch state.  cudaFuncSetAttribute and the co-resident cluster count are per DEVICE, so they are cached
+// in the handle (one handle per device), never in function-local statics.
+struct KernelCache {
+  bool attr_set = false;
+  int max_clusters = 0;
+};
+}  // namespace nb2
+
 struct nb2_handle {
   int device = 0;
   int sm_count = 0;
   int64_t launches = 0;
+  int tc_debug = 0;              // NB2_TC_DEBUG, read once in nb2_create (timing experiments: 1 = no weight waits, 2 = no MMAs)
   cudaEvent_t prof[4] = {nullptr, nullptr, nullptr, nullptr};
   long long* tc_prof = nullptr;  // debug: per-CTA role cycle counters of the last tensor-kernel launch
-  nb2::PackedNet net[2];
+  nb2::PackedNet net[nb2::kMaxNets];
+  std::unordered_map<const void*, nb2::KernelCache> kcache;
 };
 
 namespace nb2 {
@@ -224,6 +241,29 @@ __device__ __forceinline__ double warp_sum_d(double v) {
 
 #endif  // __CUDACC__
 
+// ------------------------------------------------------------------------------------------
+// per-handle launch helpers (nb2_api.cu)
+// ------------------------------------------------------------------------------------------
+// Every entry point runs on the handle's device whatever the caller's current device is, and restores it on exit.
+struct DeviceGuard {
+  int prev = -1, dev;
+  explicit DeviceGuard(int d) : dev(d) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) cudaSetDevice(dev);
+  }
+  ~DeviceGuard() {
+    if (prev >= 0 && prev != dev) cudaSetDevice(prev);
+  }
+};
+#define NB2_ENTER(h)                               \
+  NB2_CHECK_ARG((h) != nullptr, "null handle");    \
+  nb2::DeviceGuard nb2_device_guard_((h)->device)
+// opt-in dynamic shared memory above 48 KB: once per kernel per handle (= per device)
+int kernel_set_smem(nb2_handle* h, const void* fn, int bytes);
+// co-resident clusters of `fn` under `cfg` on the handle's device (cached)
+int kernel_max_clusters(nb2_handle* h, const void* fn, const cudaLaunchConfig_t* cfg, int* out);
+inline bool net_ok(const nb2_handle* h, int id) { return id >= 0 && id < kMaxNets && h->net[id].in_use; }
+
 // launchers implemented in the other translation units --------------------------------------
 struct MlpIo {
   // input selection
@@ -248,6 +288,11 @@ struct MlpIo {
   float* rgb_out;         // out_mode 2: (n_rays, 3)
   float* depth_out;       // out_mode 2: (n_rays) or NULL
   float* acc_out;         // out_mode 2: (n_rays) or NULL
+  // out_mode 2, optional: the composited rgb row of ray r is ALSO stored at peer_rgb[q][(peer_row0 + r) * 3 ..] for every
+  // q < n_peers -- the image buffers of the other GPUs of the node, mapped through CUDA IPC (stores travel over NVLink)
+  float* peer_rgb[kMaxPeers];
+  int n_peers;
+  int64_t peer_row0;
   int flags;
   float near_t, far_t;
 };

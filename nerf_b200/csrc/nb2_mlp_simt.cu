@@ -175,15 +175,14 @@ int launch_mlp_simt(nb2_handle* h, int net_id, const MlpIo& io, cudaStream_t st)
     return NB2_ERR_UNSUPPORTED;
   }
   if (io.n_rows == 0) return NB2_OK;
-  static bool attr_set = false;
-  if (!attr_set) {
-    NB2_CUDA(cudaFuncSetAttribute(mlp_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SimtSmem)));
-    attr_set = true;
+  {
+    const int rc = kernel_set_smem(h, (const void*)mlp_simt_kernel, (int)sizeof(SimtSmem));
+    if (rc != NB2_OK) return rc;
   }
   int64_t n_tiles = (io.n_rows + kSimtRows - 1) / kSimtRows;
   int grid = (int)std::min<int64_t>(n_tiles, (int64_t)h->sm_count);
   mlp_simt_kernel<<<grid, kSimtThreads, sizeof(SimtSmem), st>>>(pn.simt, io, pn.d_wt32, pn.d_bias, pn.d_head,
-                                                                pn.pos_levels, pn.dir_levels, net_id == NB2_NET_NERF);
+                                                                pn.pos_levels, pn.dir_levels, pn.kind == NB2_NET_NERF);
   NB2_LAUNCH_CHECK(h);
   return NB2_OK;
 }

@@ -1,11 +1,8 @@
 // nb2_mlp_tc.cu — the per-sample MLP (proposal 4x256 / NeRF 8x256 + heads) as ONE persistent, warp-specialised tcgen05
 // kernel with both operands in shared memory, plus the precision dispatch (launch_mlp_tc) for every tensor-core kernel.
 //
-//   mlp_tc2_kernel   CTA pair (cta_group::2, M256 x N256 x K16): the DEFAULT for the single-pass precisions
-//                    (NB2_PREC_BF16 / NB2_PREC_FP16), two resident tiles in ping-pong; also the split precisions when the
-//                    TMEM-operand kernel (nb2_mlp_tc4.cu, their default) is switched off (NB2_TC_TMEMA=0).
-//   mlp_tc_kernel    single CTA (cta_group::1, N = 128 MMAs, optional cluster multicast of the weight tiles): the first
-//                    version, kept selectable (NB2_TC_PAIR=0); bit-identical results.
+//   mlp_tc2_kernel   CTA pair (cta_group::2, M256 x N256 x K16): the single-pass precisions (NB2_PREC_BF16 /
+//                    NB2_PREC_FP16), two resident tiles in ping-pong.  The split precisions run nb2_mlp_tc4.cu.
 //
 //   warp 0      weight streamer: cp.async.bulk (TMA unit) of pre-swizzled 128x64 16-bit weight tiles from L2 into a
 //               4-stage shared-memory ring, mbarrier full/empty handshake (pair kernel: each CTA streams its half of
@@ -212,6 +209,11 @@ __device__ __forceinline__ void slot_group_run(const TcParams& p, TcMisc* misc, 
             p.io.rgb_out[in.ray * 3 + 0] = sr;
             p.io.rgb_out[in.ray * 3 + 1] = sg;
             p.io.rgb_out[in.ray * 3 + 2] = sb;
+            // fused gather: the same row goes to every peer GPU's image buffer over NVLink (nb2_render_params.peer_rgb)
+            for (int q = 0; q < p.io.n_peers; ++q) {
+              float* o = p.io.peer_rgb[q] + (p.io.peer_row0 + in.ray) * 3;
+              o[0] = sr; o[1] = sg; o[2] = sb;
+            }
             if (p.io.depth_out) p.io.depth_out[in.ray] = (sd - p.io.near_t) / (p.io.far_t - p.io.near_t);
             if (p.io.acc_out) p.io.acc_out[in.ray] = sa;
           }
@@ -269,189 +271,6 @@ __device__ __forceinline__ void slot_group_run(const TcParams& p, TcMisc* misc, 
   if (NB2_PROF_ON && threadIdx.x == kRolesThreads) {
     long long* o = p.prof + blockIdx.x * 16;
     o[6] = t_pe; o[7] = t_wacc; o[8] = t_epi; o[9] = t_last; o[10] = NB2_CLK() - t0e; o[11] = n_iters; o[12] = net.n_layers;
-  }
-}
-
-// LOCKSTEP (two-slot mode only): both resident tiles consume every weight tile back to back, halving the
-// L2 -> SM weight traffic per FLOP at the price of not overlapping one tile's epilogue with the other's MMAs.
-template <int NSLOTS, bool SPLIT, bool F16, bool LOCKSTEP>
-__global__ void __launch_bounds__(kTcThreads, 1) mlp_tc_kernel(const __grid_constant__ TcParams p) {
-  using LT = TcLayout<NSLOTS, SPLIT>;
-  extern __shared__ unsigned char smem_dyn[];
-  const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
-  unsigned char* smem_al = smem_dyn + (smem_base - smem_u32(smem_dyn));
-  const uint32_t act_base = smem_base;
-  const uint32_t ring_base = smem_base + LT::kActBytes;
-  TcMisc* misc = reinterpret_cast<TcMisc*>(smem_al + LT::kActBytes + LT::kRingBytes);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const TcNet& net = p.net;
-  const int64_t tiles_per_iter = (int64_t)gridDim.x * NSLOTS;
-  const int64_t n_iters = (p.n_tiles + tiles_per_iter - 1) / tiles_per_iter;   // identical for every CTA: the
-  // CTAs of a cluster walk the same (iteration, layer, slot) schedule; tiles past n_tiles run on zero rows
-  const uint32_t cl_size = (uint32_t)p.cluster;
-  const uint32_t cl_rank = cl_size > 1 ? cluster_ctarank() : 0u;
-  const uint16_t cl_mask = (uint16_t)((1u << cl_size) - 1u);
-
-  // ---- one-time setup ---------------------------------------------------------------------------
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < kStages; ++i) {
-      mbar_init(smem_u32(&misc->w_full[i]), 1);
-      mbar_init(smem_u32(&misc->w_empty[i]), cl_size);   // one arrive per consumer CTA of the cluster
-    }
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(smem_u32(&misc->a_ready[s]), 4 * GroupsPerSlot<NSLOTS>::value);   // one arrival per slot-group warp
-      mbar_init(smem_u32(&misc->acc_full[s]), 1);
-    }
-    mbar_fence_init();
-  }
-  if (warp == 2) {
-    tmem_alloc(smem_u32(&misc->tmem_base), 512);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (cl_size > 1) cluster_sync_all();   // every CTA's barriers exist before any remote arrive / multicast
-  tc_fence_after();
-  const uint32_t tmem_base = misc->tmem_base;
-
-  if (warp == 0) {
-    // =========================== weight streamer ==================================================
-    reg_dealloc<kRoleRegs>();
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0, q = 0;
-      long long t_empty = 0, t0s = NB2_CLK();
-      for (int64_t it = 0; it < n_iters; ++it) {
-        for (int l = 0; l < net.n_layers; ++l) {
-          const int n_chunks = net.layer[l].kc * net.layer[l].nc;
-          const int chunk0 = net.layer[l].chunk0;
-          for (int s = 0; s < (LOCKSTEP ? 1 : NSLOTS); ++s) {
-            for (int c = 0; c < n_chunks; ++c) {
-#pragma unroll
-              for (int part = 0; part < (SPLIT ? 2 : 1); ++part) {
-                const long long c0 = NB2_CLK();
-                mbar_wait(smem_u32(&misc->w_empty[stage]), phase ^ 1u);   // all consumers of the cluster released it
-                t_empty += NB2_CLK() - c0;
-                const uint32_t full = smem_u32(&misc->w_full[stage]);
-                mbar_arrive_expect_tx(full, kTileBytes);
-                const __nv_bfloat16* src = p.wchunks + ((size_t)(chunk0 + c) * 4 + (F16 ? 2 : 0) + part) * (kTileBytes / 2);
-                if (cl_size == 1) bulk_g2s(ring_base + stage * kTileBytes, src, kTileBytes, full);
-                else if (q % cl_size == cl_rank) bulk_g2s_mcast(ring_base + stage * kTileBytes, src, kTileBytes, full, cl_mask);
-                ++q;
-                if (++stage == kStages) { stage = 0; phase ^= 1u; }
-              }
-            }
-          }
-        }
-      }
-      if (NB2_PROF_ON) { p.prof[blockIdx.x * 16 + 0] = t_empty; p.prof[blockIdx.x * 16 + 1] = NB2_CLK() - t0s; p.prof[blockIdx.x * 16 + 2] = q; }
-    }
-  } else if (warp == 1) {
-    // =========================== MMA issuer =======================================================
-    reg_dealloc<kRoleRegs>();
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_16(128, 128, F16);
-      uint32_t stage = 0, phase = 0;
-      uint32_t pa[2] = {0u, 0u};
-      long long t_wa = 0, t_ww = 0, t0m = NB2_CLK();
-      auto release = [&](uint32_t bar) {
-        if (cl_size == 1) umma_commit(bar); else umma_commit_mcast(bar, cl_mask);
-      };
-      for (int64_t it = 0; it < n_iters; ++it) {
-        for (int l = 0; l < net.n_layers; ++l) {
-          const TcLayer& L = net.layer[l];
-          if (LOCKSTEP) {
-            // both tiles' operands are ready -> every weight tile is used twice
-            { const long long c0 = NB2_CLK();
-            for (int s = 0; s < NSLOTS; ++s) {
-              mbar_wait(smem_u32(&misc->a_ready[s]), pa[s]);
-              pa[s] ^= 1u;
-            }
-            t_wa += NB2_CLK() - c0; }
-            tc_fence_after();
-            for (int n = 0; n < L.nc; ++n) {
-              for (int k = 0; k < L.kc; ++k) {
-                const int ks0 = L.ks0[k];
-                { const long long c0 = NB2_CLK();
-                mbar_wait(smem_u32(&misc->w_full[stage]), phase);
-                t_ww += NB2_CLK() - c0; }
-                tc_fence_after();
-                const uint32_t w_hi = ring_base + stage * kTileBytes;
-                for (int s = 0; s < NSLOTS; ++s) {
-                  const uint32_t a_hi = act_base + s * LT::kSlotBytes + (uint32_t)L.a_src[k] * kTileBytes;
-                  const uint32_t d_main = tmem_base + (uint32_t)(s * 256) + n * 128;
-                  for (int ks = ks0; ks < 4; ++ks)
-                    umma_bf16_ss(d_main, umma_smem_desc(a_hi + ks * 32), umma_smem_desc(w_hi + ks * 32), idesc,
-                                 (uint32_t)((k | ks) != 0));
-                }
-                release(smem_u32(&misc->w_empty[stage]));
-                if (++stage == kStages) { stage = 0; phase ^= 1u; }
-              }
-            }
-            for (int s = 0; s < NSLOTS; ++s) umma_commit(smem_u32(&misc->acc_full[s]));
-            continue;
-          }
-          for (int s = 0; s < NSLOTS; ++s) {
-            { const long long c0 = NB2_CLK();
-            mbar_wait(smem_u32(&misc->a_ready[s]), pa[s]);
-            t_wa += NB2_CLK() - c0; }
-            pa[s] ^= 1u;
-            tc_fence_after();
-            const uint32_t slot_base = act_base + s * LT::kSlotBytes;
-            const uint32_t acc = tmem_base + (uint32_t)(s * 256);
-            for (int n = 0; n < L.nc; ++n) {
-              const uint32_t d_main = acc + n * 128;
-              const uint32_t d_corr = d_main + 256;   // SPLIT only: cross terms hi*lo + lo*hi
-              for (int k = 0; k < L.kc; ++k) {
-                const uint32_t a_hi = slot_base + (uint32_t)L.a_src[k] * kTileBytes;
-                const uint32_t a_lo = a_hi + kChunksPerSlot * kTileBytes;
-                const int ks0 = L.ks0[k];
-                { const long long c0 = NB2_CLK();
-                mbar_wait(smem_u32(&misc->w_full[stage]), phase);
-                t_ww += NB2_CLK() - c0; }
-                tc_fence_after();
-                const uint32_t w_hi = ring_base + stage * kTileBytes;
-                for (int ks = ks0; ks < 4; ++ks)
-                  umma_bf16_ss(d_main, umma_smem_desc(a_hi + ks * 32), umma_smem_desc(w_hi + ks * 32), idesc,
-                               (uint32_t)((k | ks) != 0));
-                if (SPLIT) {
-                  for (int ks = ks0; ks < 4; ++ks)
-                    umma_bf16_ss(d_corr, umma_smem_desc(a_lo + ks * 32), umma_smem_desc(w_hi + ks * 32), idesc,
-                                 (uint32_t)((k | ks) != 0));
-                }
-                release(smem_u32(&misc->w_empty[stage]));
-                if (++stage == kStages) { stage = 0; phase ^= 1u; }
-                if (SPLIT) {
-                  mbar_wait(smem_u32(&misc->w_full[stage]), phase);
-                  tc_fence_after();
-                  const uint32_t w_lo = ring_base + stage * kTileBytes;
-                  for (int ks = ks0; ks < 4; ++ks)
-                    umma_bf16_ss(d_corr, umma_smem_desc(a_hi + ks * 32), umma_smem_desc(w_lo + ks * 32), idesc, 1u);
-                  release(smem_u32(&misc->w_empty[stage]));
-                  if (++stage == kStages) { stage = 0; phase ^= 1u; }
-                }
-              }
-            }
-            umma_commit(smem_u32(&misc->acc_full[s]));
-          }
-        }
-      }
-      if (NB2_PROF_ON) { p.prof[blockIdx.x * 16 + 3] = t_wa; p.prof[blockIdx.x * 16 + 4] = t_ww; p.prof[blockIdx.x * 16 + 5] = NB2_CLK() - t0m; }
-    }
-  } else if (warp >= 4) {
-    reg_alloc<kGroupRegs>();
-    slot_group_run<NSLOTS, SPLIT, F16, false>(p, misc, act_base, tmem_base, n_iters, warp, lane, 0u);
-  } else {
-    reg_dealloc<kRoleRegs>();
-  }
-
-  // ---- teardown -----------------------------------------------------------------------------------
-  tc_fence_before();
-  __syncthreads();
-  if (cl_size > 1) cluster_sync_all();   // no CTA leaves while a peer may still multicast into it
-  if (warp == 2) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -628,73 +447,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_tc2_kernel(const __grid_con
 }
 
 // ---- host side ----------------------------------------------------------------------------------------
-// Variant knobs (defaults chosen from measurements; overridable for experiments):
-//   NB2_TC_TMEMA = 1 | 0            split precisions: TMEM-operand kernel (nb2_mlp_tc4.cu) | layer-serial pair kernel
-//   NB2_TC_NHALF = 0 | 1            N-half pipelined pair kernel (nb2_mlp_tc3.cu; measured slower, kept for the record)
-//   NB2_TC_PAIR = 1 | 0             CTA-pair kernel | single-CTA kernel
-//   NB2_TC_LOCKSTEP = 0 | 1         pair kernel, single pass: ping-pong tiles (one tile's epilogue under the other's MMAs) | both tiles
-//                                   consume each weight tile back to back (single-CTA kernel: default 1)
-//   NB2_TC_CLUSTER = 1 | 2 | 4      single-CTA kernel: CTAs sharing each weight tile via multicast
-static int env_int(const char* name, int dflt) {
-  const char* v = getenv(name);
-  return v ? atoi(v) : dflt;
-}
-
-template <int NSLOTS, bool SPLIT, bool F16, bool LOCKSTEP>
-static int launch_tc_impl(nb2_handle* h, TcParams& prm, cudaStream_t st) {
-  using LT = TcLayout<NSLOTS, SPLIT>;
-  auto kern = mlp_tc_kernel<NSLOTS, SPLIT, F16, LOCKSTEP>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    NB2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, LT::kTotal));
-    attr_set = true;
-  }
-  const int cluster = prm.cluster;
-  int64_t ctas = (prm.n_tiles + NSLOTS - 1) / NSLOTS;
-  ctas = (ctas + cluster - 1) / cluster * cluster;
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cfg.blockDim = dim3(kTcThreads);
-  cfg.dynamicSmemBytes = LT::kTotal;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = cluster;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  int max_ctas = h->sm_count / cluster * cluster;
-  if (cluster > 1) {
-    // co-resident clusters are limited by GPC boundaries: ask the driver
-    static int cached[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    if (!cached[cluster]) {
-      cfg.gridDim = dim3(max_ctas);
-      int n = 0;
-      NB2_CUDA(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
-      cached[cluster] = n > 0 ? n : 1;
-    }
-    max_ctas = cached[cluster] * cluster;
-  }
-  cfg.gridDim = dim3((unsigned)std::min<int64_t>(ctas, (int64_t)max_ctas));
-  NB2_CUDA(cudaLaunchKernelEx(&cfg, kern, prm));
-  h->launches++;
-  return NB2_OK;
-}
-
-template <int NSLOTS, bool SPLIT, bool F16, bool LOCKSTEP>
+template <bool F16>
 static int launch_tc2_impl(nb2_handle* h, TcParams& prm, cudaStream_t st) {
-  using LT = TcLayout<NSLOTS, SPLIT>;
-  auto kern = mlp_tc2_kernel<NSLOTS, SPLIT, F16, LOCKSTEP>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    NB2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, LT::kTotal));
-    attr_set = true;
-  }
-  int64_t ctas = (prm.n_tiles + NSLOTS - 1) / NSLOTS;
+  using LT = TcLayout<2, false>;
+  auto kern = mlp_tc2_kernel<2, false, F16, false>;
+  int rc = kernel_set_smem(h, (const void*)kern, LT::kTotal);
+  if (rc != NB2_OK) return rc;
+  int64_t ctas = (prm.n_tiles + 1) / 2;   // two resident tiles per CTA
   ctas = (ctas + 1) / 2 * 2;
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
+  cudaLaunchConfig_t cfg = {};
   cfg.blockDim = dim3(kTcThreads);
   cfg.dynamicSmemBytes = LT::kTotal;
   cfg.stream = st;
@@ -705,13 +466,10 @@ static int launch_tc2_impl(nb2_handle* h, TcParams& prm, cudaStream_t st) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  static int max_clusters = 0;
-  if (!max_clusters) {
-    cfg.gridDim = dim3(h->sm_count / 2 * 2);
-    int n = 0;
-    NB2_CUDA(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
-    max_clusters = n > 0 ? n : 1;
-  }
+  cfg.gridDim = dim3(h->sm_count / 2 * 2);
+  int max_clusters = 0;
+  rc = kernel_max_clusters(h, (const void*)kern, &cfg, &max_clusters);
+  if (rc != NB2_OK) return rc;
   cfg.gridDim = dim3((unsigned)std::min<int64_t>(ctas, (int64_t)max_clusters * 2));
   prm.cluster = 2;
   NB2_CUDA(cudaLaunchKernelEx(&cfg, kern, prm));
@@ -719,6 +477,9 @@ static int launch_tc2_impl(nb2_handle* h, TcParams& prm, cudaStream_t st) {
   return NB2_OK;
 }
 
+// Precision dispatch of the tensor-core kernels: split precisions -> TMEM-operand kernel (nb2_mlp_tc4.cu), single pass ->
+// the ping-pong pair kernel above.  (The single-CTA, lockstep, N-half and two-accumulator variants of round 1 measured
+// slower and were retired; DESIGN.md section 9 keeps their numbers.)
 int launch_mlp_tc(nb2_handle* h, int net_id, int precision, const MlpIo& io, cudaStream_t st) {
   PackedNet& pn = h->net[net_id];
   if (!pn.packed) {
@@ -738,37 +499,17 @@ int launch_mlp_tc(nb2_handle* h, int net_id, int precision, const MlpIo& io, cud
   prm.head = pn.d_head;
   prm.pos_levels = pn.pos_levels;
   prm.dir_levels = pn.dir_levels;
-  prm.has_dir = (net_id == NB2_NET_NERF);
-  prm.debug = env_int("NB2_TC_DEBUG", 0);
+  prm.has_dir = (pn.kind == NB2_NET_NERF);
+  prm.debug = h->tc_debug;
   prm.dir_layer = -1;   // the direction encoding is written after the epilogue of the layer before the density layer
   for (int l = 0; l < pn.tc.n_layers; ++l)
     if (prm.has_dir && pn.tc.layer[l].epi == EPI_RELU_SIGMA) prm.dir_layer = l - 1;
   prm.n_tiles = (io.n_rows + kTileRows - 1) / kTileRows;
   prm.prof = h->tc_prof;
-  const bool split = (precision == NB2_PREC_BF16X3 || precision == NB2_PREC_FP16X3);
-  // NB2_TC_NHALF = 1: CTA-pair kernel pipelined by output halves (nb2_mlp_tc3.cu)
-  if (env_int("NB2_TC_NHALF", 0) != 0) return launch_mlp_tc3(h, prm, precision, st);
-  // NB2_TC_TMEMA = 1: split precisions with the hidden activations in tensor memory (nb2_mlp_tc4.cu)
-  if (split && env_int("NB2_TC_TMEMA", 1) != 0) return launch_mlp_tc4(h, prm, precision, st);
-  if (env_int("NB2_TC_PAIR", 1) != 0) {
-    const bool ls = env_int("NB2_TC_LOCKSTEP", 0) != 0;
-    if (precision == NB2_PREC_BF16) return ls ? launch_tc2_impl<2, false, false, true>(h, prm, st) : launch_tc2_impl<2, false, false, false>(h, prm, st);
-    if (precision == NB2_PREC_FP16) return ls ? launch_tc2_impl<2, false, true, true>(h, prm, st) : launch_tc2_impl<2, false, true, false>(h, prm, st);
-    if (precision == NB2_PREC_BF16X3) return launch_tc2_impl<1, true, false, true>(h, prm, st);
-    if (precision == NB2_PREC_FP16X3) return launch_tc2_impl<1, true, true, true>(h, prm, st);
-  }
-  int cluster = env_int("NB2_TC_CLUSTER", 1);
-  if (cluster != 1 && cluster != 2 && cluster != 4) {
-    set_error("NB2_TC_CLUSTER must be 1, 2 or 4 (got %d)", cluster);
-    return NB2_ERR_INVALID;
-  }
-  if (prm.n_tiles < 2 * cluster) cluster = 1;
-  prm.cluster = cluster;
-  const bool lockstep = env_int("NB2_TC_LOCKSTEP", 1) != 0;
-  if (precision == NB2_PREC_BF16) return lockstep ? launch_tc_impl<2, false, false, true>(h, prm, st) : launch_tc_impl<2, false, false, false>(h, prm, st);
-  if (precision == NB2_PREC_FP16) return lockstep ? launch_tc_impl<2, false, true, true>(h, prm, st) : launch_tc_impl<2, false, true, false>(h, prm, st);
-  if (precision == NB2_PREC_BF16X3) return launch_tc_impl<1, true, false, false>(h, prm, st);
-  if (precision == NB2_PREC_FP16X3) return launch_tc_impl<1, true, true, false>(h, prm, st);
+  prm.cluster = 2;
+  if (precision == NB2_PREC_BF16X3 || precision == NB2_PREC_FP16X3) return launch_mlp_tc4(h, prm, precision, st);
+  if (precision == NB2_PREC_BF16) return launch_tc2_impl<false>(h, prm, st);
+  if (precision == NB2_PREC_FP16) return launch_tc2_impl<true>(h, prm, st);
   set_error("mlp_forward: unknown tensor-core precision %d", precision);
   return NB2_ERR_INVALID;
 }
@@ -979,9 +720,11 @@ int umma_bench(nb2_handle* h, const void* A, const void* B, float* D, long long*
   const int smem = 12 * kTileBytes + 1024 + 1024;
   void (*kern)(const __nv_bfloat16*, const __nv_bfloat16*, float*, long long*, int, int, const __nv_bfloat16*) =
       mode == 0 ? umma_bench_kernel<0> : (mode == 1 ? umma_bench_kernel<1> : umma_bench_kernel<2>);
-  NB2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
+  {
+    const int rc = kernel_set_smem(h, (const void*)kern, smem);
+    if (rc != NB2_OK) return rc;
+  }
+  cudaLaunchConfig_t cfg = {};
   cfg.blockDim = dim3(256);
   cfg.gridDim = dim3(h->sm_count / 2 * 2);
   cfg.dynamicSmemBytes = smem;
@@ -1012,10 +755,9 @@ int selftest_umma(nb2_handle* h, const void* A, const void* B, void* Bswz_scratc
                                                                           (__nv_bfloat16*)Bswz_scratch);
   NB2_LAUNCH_CHECK(h);
   const int smem = 2 * kTileBytes + 1024 + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
-    NB2_CUDA(cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
+  {
+    const int rc = kernel_set_smem(h, (const void*)umma_selftest_kernel, smem);
+    if (rc != NB2_OK) return rc;
   }
   umma_selftest_kernel<<<1, 128, smem, st>>>((const __nv_bfloat16*)A, (const __nv_bfloat16*)Bswz_scratch, D);
   NB2_LAUNCH_CHECK(h);

@@ -257,6 +257,11 @@ __device__ __forceinline__ void slot_group_run4(const TcParams& p, Tc4Misc* misc
               p.io.rgb_out[in.ray * 3 + 0] = sr;
               p.io.rgb_out[in.ray * 3 + 1] = sgn;
               p.io.rgb_out[in.ray * 3 + 2] = sb;
+              // fused gather: the same row goes to every peer GPU's image buffer over NVLink (nb2_render_params.peer_rgb)
+              for (int q = 0; q < p.io.n_peers; ++q) {
+                float* o = p.io.peer_rgb[q] + (p.io.peer_row0 + in.ray) * 3;
+                o[0] = sr; o[1] = sgn; o[2] = sb;
+              }
               if (p.io.depth_out) p.io.depth_out[in.ray] = (sd - p.io.near_t) / (p.io.far_t - p.io.near_t);
               if (p.io.acc_out) p.io.acc_out[in.ray] = sa;
             }
@@ -566,24 +571,24 @@ int selftest_umma_ts(nb2_handle* h, const void* A, const void* B, void* Bswz_scr
   swizzle_tile_kernel4<<<(kTileRows * kTileCols + 255) / 256, 256, 0, st>>>((const __nv_bfloat16*)B, (__nv_bfloat16*)Bswz_scratch);
   NB2_LAUNCH_CHECK(h);
   const int smem = kTileBytes + 1024 + 1024;
-  NB2_CUDA(cudaFuncSetAttribute(umma_ts_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  {
+    const int rc = kernel_set_smem(h, (const void*)umma_ts_selftest_kernel, smem);
+    if (rc != NB2_OK) return rc;
+  }
   umma_ts_selftest_kernel<<<1, 128, smem, st>>>((const __nv_bfloat16*)A, (const __nv_bfloat16*)Bswz_scratch, D);
   NB2_LAUNCH_CHECK(h);
   return NB2_OK;
 }
 
 // ---- host side --------------------------------------------------------------------------------------------------------
-template <bool F16, int NG>
+template <bool F16>
 static int launch_tc4_impl(nb2_handle* h, TcParams& prm, cudaStream_t st) {
-  auto kern = mlp_tc4_kernel<F16, NG>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    NB2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Tc4Layout::kTotal));
-    attr_set = true;
-  }
+  auto kern = mlp_tc4_kernel<F16, 2>;
+  int rc = kernel_set_smem(h, (const void*)kern, Tc4Layout::kTotal);
+  if (rc != NB2_OK) return rc;
   int64_t ctas = (prm.n_tiles + 1) / 2 * 2;
   cudaLaunchConfig_t cfg = {};
-  cfg.blockDim = dim3(128 + 128 * NG);
+  cfg.blockDim = dim3(128 + 128 * 2);
   cfg.dynamicSmemBytes = Tc4Layout::kTotal;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -593,13 +598,10 @@ static int launch_tc4_impl(nb2_handle* h, TcParams& prm, cudaStream_t st) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  static int max_clusters = 0;
-  if (!max_clusters) {
-    cfg.gridDim = dim3(h->sm_count / 2 * 2);
-    int n = 0;
-    NB2_CUDA(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
-    max_clusters = n > 0 ? n : 1;
-  }
+  cfg.gridDim = dim3(h->sm_count / 2 * 2);
+  int max_clusters = 0;
+  rc = kernel_max_clusters(h, (const void*)kern, &cfg, &max_clusters);
+  if (rc != NB2_OK) return rc;
   cfg.gridDim = dim3((unsigned)std::min<int64_t>(ctas, (int64_t)max_clusters * 2));
   prm.cluster = 2;
   NB2_CUDA(cudaLaunchKernelEx(&cfg, kern, prm));
@@ -617,15 +619,9 @@ int launch_mlp_tc4(nb2_handle* h, const TcParams& base, int precision, cudaStrea
         return NB2_ERR_UNSUPPORTED;
       }
   }
-  // NB2_TC_GROUPS = 2 | 4: epilogue warpgroups per tile
-  const char* ge = getenv("NB2_TC_GROUPS");
-  const int groups = ge ? atoi(ge) : 2;
-  if (groups != 2 && groups != 4) {
-    set_error("NB2_TC_GROUPS must be 2 or 4 (got %d)", groups);
-    return NB2_ERR_INVALID;
-  }
-  if (precision == NB2_PREC_FP16X3) return groups == 4 ? launch_tc4_impl<true, 4>(h, prm, st) : launch_tc4_impl<true, 2>(h, prm, st);
-  if (precision == NB2_PREC_BF16X3) return groups == 4 ? launch_tc4_impl<false, 4>(h, prm, st) : launch_tc4_impl<false, 2>(h, prm, st);
+  // (two epilogue warpgroups per tile; the four-warpgroup variant of round 1 spilled at 104 registers and was retired)
+  if (precision == NB2_PREC_FP16X3) return launch_tc4_impl<true>(h, prm, st);
+  if (precision == NB2_PREC_BF16X3) return launch_tc4_impl<false>(h, prm, st);
   set_error("mlp_forward: the TMEM-operand kernel runs the split precisions only (got %d)", precision);
   return NB2_ERR_INVALID;
 }

@@ -715,7 +715,7 @@ __global__ void linear_to_srgb_kernel(const float* __restrict__ lin, int64_t n, 
 // ==========================================================================================
 using namespace nb2;
 
-#define NB2_H(h) NB2_CHECK_ARG((h) != nullptr, "null handle")
+#define NB2_H(h) NB2_ENTER(h)
 
 extern "C" int nb2_generate_rays(nb2_handle* h, const float* pose, int H, int W, float fx, float fy,
                                  int64_t pix_offset, int64_t n, float* rays_out, void* stream) {
@@ -749,10 +749,9 @@ extern "C" int nb2_posenc(nb2_handle* h, const float* x, int64_t n, int dims, in
   NB2_CHECK_ARG(x && out && n >= 0 && dims >= 1 && dims <= 4 && levels >= 1 && levels <= 16, "posenc: bad arguments");
   if (n == 0) return NB2_OK;
   size_t smem = (size_t)kPeBlockPts * 2 * dims * levels * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
-    NB2_CUDA(cudaFuncSetAttribute(posenc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
-    attr_set = true;
+  {
+    const int rc = kernel_set_smem(h, (const void*)posenc_kernel, 128 * 1024);
+    if (rc != NB2_OK) return rc;
   }
   posenc_kernel<<<grid_for(n, kPeBlockPts), 256, smem, (cudaStream_t)stream>>>(x, n, dims, levels, out);
   NB2_LAUNCH_CHECK(h);
@@ -846,7 +845,7 @@ extern "C" int nb2_inverse_sample(nb2_handle* h, const float* weights, const flo
 
 extern "C" int nb2_resample(nb2_handle* h, const float* sigma, const float* z, const float* rays, const float* u,
                             uint64_t seed, int64_t ray_offset, int64_t n_rays, int n_samples, int n_draw,
-                            float blur_alpha, int flags, float* z_fine_out, void* stream) {
+                            float blur_alpha, int flags, float* z_fine_out, int64_t* below_out, void* stream) {
   NB2_H(h);
   if (n_rays == 0) return NB2_OK;
   NB2_CHECK_ARG(sigma && z && rays && z_fine_out, "resample: null pointer");
@@ -856,7 +855,7 @@ extern "C" int nb2_resample(nb2_handle* h, const float* sigma, const float* z, c
   int act = (flags & NB2_DENSITY_SOFTPLUS) ? 1 : 0;
   // softplus'd density is then passed through get_weights' own relu (a no-op on positives)
   resample_kernel<<<grid_for(n_rays, kResampleWarps), 32 * kResampleWarps, 0, (cudaStream_t)stream>>>(
-      1, sigma, z, rays, u, seed, ray_offset, n_rays, n_samples, n_draw, 1, n_draw - 1, blur_alpha, act, z_fine_out, nullptr);
+      1, sigma, z, rays, u, seed, ray_offset, n_rays, n_samples, n_draw, 1, n_draw - 1, blur_alpha, act, z_fine_out, below_out);
   NB2_LAUNCH_CHECK(h);
   return NB2_OK;
 }
@@ -936,10 +935,9 @@ extern "C" int nb2_ide(nb2_handle* h, const float* xyz, const float* kappa_inv, 
   NB2_CHECK_ARG(n_pairs >= 1 && n_pairs <= kIdeMaxPairs && n_pow >= 1 && n_pow <= kIdeMaxPow,
                 "ide: at most %d (m, l) pairs and degree %d (deg_view <= 5, ref_func.py:67-68)", kIdeMaxPairs, kIdeMaxPow - 1);
   const size_t smem = (size_t)(kIdeMaxPow * kIdeMaxPairs + 2 * kIdeMaxPairs + kIdeBlockPts * 2 * n_pairs) * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
-    NB2_CUDA(cudaFuncSetAttribute(ide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    attr_set = true;
+  {
+    const int rc = kernel_set_smem(h, (const void*)ide_kernel, 64 * 1024);
+    if (rc != NB2_OK) return rc;
   }
   ide_kernel<<<grid_for(n, kIdeBlockPts), kIdeBlockPts, smem, (cudaStream_t)stream>>>(xyz, kappa_inv, n, n_pairs, n_pow, mat, ml, out);
   NB2_LAUNCH_CHECK(h);

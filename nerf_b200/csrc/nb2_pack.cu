@@ -141,7 +141,9 @@ int pack_network(nb2_handle* h, int net_id, const float* const* W, const float* 
   NB2_CUDA(cudaMemsetAsync(pn.d_head, 0, kHeadFloats * sizeof(float), st));
   NB2_CUDA(cudaMemsetAsync(pn.d_bias, 0, n_bias_floats * sizeof(float), st));
 
-  if (net_id == NB2_NET_PROPOSAL) {
+  // a failed (re-)pack must not leave a half-written image marked valid
+  pn.packed = false;
+  if (pn.kind == NB2_NET_PROPOSAL) {
     NB2_CHECK_ARG(n_layers == 5, "pack_weights: the proposal network has 5 linear layers, got %d", n_layers);
     const int eE[1] = {kChunkE}, eo[1] = {0}, ev[1] = {enc};
     add_tc_layer(tc, chunks, W[0], b[0], enc, 1, 2, eE, eo, ev, EPI_RELU, 0);
@@ -202,17 +204,23 @@ int pack_network(nb2_handle* h, int net_id, const float* const* W, const float* 
   void* d_desc = nullptr;
   const size_t cbytes = chunks.size() * sizeof(PackChunkDesc), sbytes = sdescs.size() * sizeof(PackSimtDesc);
   NB2_CUDA(cudaMallocAsync(&d_desc, cbytes + sbytes, st));
-  NB2_CUDA(cudaMemcpyAsync(d_desc, chunks.data(), cbytes, cudaMemcpyHostToDevice, st));
-  NB2_CUDA(cudaMemcpyAsync((char*)d_desc + cbytes, sdescs.data(), sbytes, cudaMemcpyHostToDevice, st));
-  // pageable sources are staged before cudaMemcpyAsync returns; make that explicit
-  NB2_CUDA(cudaStreamSynchronize(st));
-  pack_chunks_kernel<<<(int)chunks.size(), 256, 0, st>>>((const PackChunkDesc*)d_desc, pn.d_wchunks);
-  NB2_LAUNCH_CHECK(h);
-  pack_simt_kernel<<<dim3(64, (int)sdescs.size()), 256, 0, st>>>((const PackSimtDesc*)((char*)d_desc + cbytes), pn.d_wt32);
-  NB2_LAUNCH_CHECK(h);
-  for (const Copy& c : copies)
-    NB2_CUDA(cudaMemcpyAsync(c.dst, c.src, c.n * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  NB2_CUDA(cudaFreeAsync(d_desc, st));
+  // every exit below releases the scratch (stream-ordered, so kernels already enqueued still see it)
+  auto run = [&]() -> int {
+    NB2_CUDA(cudaMemcpyAsync(d_desc, chunks.data(), cbytes, cudaMemcpyHostToDevice, st));
+    NB2_CUDA(cudaMemcpyAsync((char*)d_desc + cbytes, sdescs.data(), sbytes, cudaMemcpyHostToDevice, st));
+    // pageable sources are staged before cudaMemcpyAsync returns; make that explicit
+    NB2_CUDA(cudaStreamSynchronize(st));
+    pack_chunks_kernel<<<(int)chunks.size(), 256, 0, st>>>((const PackChunkDesc*)d_desc, pn.d_wchunks);
+    NB2_LAUNCH_CHECK(h);
+    pack_simt_kernel<<<dim3(64, (int)sdescs.size()), 256, 0, st>>>((const PackSimtDesc*)((char*)d_desc + cbytes), pn.d_wt32);
+    NB2_LAUNCH_CHECK(h);
+    for (const Copy& c : copies)
+      NB2_CUDA(cudaMemcpyAsync(c.dst, c.src, c.n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return NB2_OK;
+  };
+  const int rc = run();
+  cudaFreeAsync(d_desc, st);
+  if (rc != NB2_OK) return rc;
 
   pn.tc = tc;
   pn.simt = simt;

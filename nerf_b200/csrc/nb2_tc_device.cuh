@@ -1,6 +1,6 @@
-// nb2_tc_device.cuh — device-side pieces shared by the tcgen05 MLP kernels (nb2_mlp_tc.cu: single-CTA and CTA-pair
-// kernels; nb2_mlp_tc3.cu: N-half pipelined CTA-pair kernel): kernel parameters, shared-memory layout, A-operand row
-// writers (encoding, 16-bit hi/lo split) and the hidden-layer epilogue blocks.
+// nb2_tc_device.cuh — device-side pieces shared by the tcgen05 MLP kernels (nb2_mlp_tc.cu: single-pass CTA-pair kernel;
+// nb2_mlp_tc4.cu: split-precision CTA-pair kernel with the activations in tensor memory): kernel parameters,
+// shared-memory layout, A-operand row writers (encoding, 16-bit hi/lo split) and the hidden-layer epilogue blocks.
 #pragma once
 #include "nb2_common.cuh"
 #include "nb2_rowio.cuh"
@@ -265,8 +265,6 @@ __device__ __forceinline__ float epilogue_hidden(uint32_t acc, uint32_t slot_bas
 }
 
 
-// N-half pipelined CTA-pair kernel (nb2_mlp_tc3.cu)
-int launch_mlp_tc3(nb2_handle* h, const TcParams& base, int precision, cudaStream_t st);
 // split-precision CTA-pair kernel with the hidden activations in tensor memory (nb2_mlp_tc4.cu)
 int launch_mlp_tc4(nb2_handle* h, const TcParams& base, int precision, cudaStream_t st);
 

@@ -13,7 +13,7 @@ from .nerf_helper import makeMLP
 
 
 class MipNeRF(NeRF):
-    _nb2_net_id = _lib.NET_NERF
+    _nb2_kind = _lib.NET_NERF
 
     def __init__(self, position_flevel, direction_flevel, hidden_unit=256, cat_origin=True) -> None:
         super().__init__(position_flevel, cat_origin)
@@ -49,10 +49,7 @@ class MipNeRF(NeRF):
 
     def forward(self, pts: torch.Tensor) -> torch.Tensor:
         """pts (ray_num, point_num, 6) = [xyz, dir] -> (ray_num, point_num, 4) = [rgb, sigma]."""
-        if torch.is_grad_enabled() and (pts.requires_grad or any(p.requires_grad for p in self.parameters())):
-            # inference-only engine this round: refuse to silently drop gradients
-            if pts.requires_grad:
-                raise _lib.NB2Error("MipNeRF.forward: backward is not built yet; call under torch.no_grad()")
-        self._nb2_sync()
-        out = ops.mlp_forward(_lib.NET_NERF, pts.reshape(-1, pts.shape[-1]), self.precision)
+        self._nb2_refuse_autograd(pts)
+        net_id = self._nb2_sync()
+        out = ops.mlp_forward(net_id, pts.reshape(-1, pts.shape[-1]), self.precision)
         return out.view(pts.shape[0], pts.shape[1], 4)

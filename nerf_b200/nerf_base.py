@@ -6,6 +6,7 @@ Static methods keep the reference signatures and run as CUDA kernels:
   getNormedWeight -> nb2_weights_from_sigma (reference nerf/nerf_base.py:79-86)
   render          -> nb2_composite          (reference nerf/nerf_base.py:90-113)
 """
+import weakref
 from typing import Optional, Tuple
 
 import torch
@@ -28,10 +29,12 @@ def _act_name(density_act):
 class PackedModule(nn.Module):
     """nn.Module whose Linear parameters are mirrored into libnerfb200's packed operand images.
 
-    Packing is lazy and keyed on the parameters' storage pointers and in-place version counters,
-    so optimizer steps and load_state_dict() trigger a re-pack on the next forward.
+    Every instance owns one packed-network slot per device (nb2_net_create), so several modules -- train / eval /
+    EMA copies -- coexist on a handle without re-packing each other.  Packing is lazy and keyed on the parameters'
+    storage pointers and in-place version counters, so optimizer steps and load_state_dict() trigger a re-pack on
+    the next forward only.
     """
-    _nb2_net_id = None
+    _nb2_kind = None
 
     def _nb2_linears(self):
         raise NotImplementedError
@@ -40,25 +43,44 @@ class PackedModule(nn.Module):
         raise NotImplementedError
 
     def _nb2_sync(self):
+        """Returns this module's slot id on its parameters' device, (re-)packing if the parameters changed."""
         lin = self._nb2_linears()
         params = [p for l in lin for p in (l.weight, l.bias)]
-        if not params[0].is_cuda:
+        dev = params[0].device
+        if dev.type != "cuda":
             raise _lib.NB2Error("nerf_b200 modules run on CUDA only: call .cuda() first (there is no CPU path)")
-        key = (params[0].device.index,) + tuple((p.data_ptr(), p._version) for p in params)
-        if getattr(self, "_nb2_key", None) != key:
+        if self.__dict__.get("_nb2_owner") != id(self):
+            # first use, or a copy.deepcopy() of a packed module: the copy gets slots of its own
+            self.__dict__.update(_nb2_owner=id(self), _nb2_slots={}, _nb2_key=None)
+        slots = self.__dict__["_nb2_slots"]
+        if dev.index not in slots:
+            slots[dev.index] = ops.net_create(self._nb2_kind, dev)
+            weakref.finalize(self, _release_slot, slots[dev.index], dev)
+        net_id = slots[dev.index]
+        key = (dev.index,) + tuple((p.data_ptr(), p._version) for p in params)
+        if self.__dict__.get("_nb2_key") != key:
             pos, dirl, hidden = self._nb2_levels()
-            # one handle per device holds ONE network of each kind: re-packing is also how several
-            # module instances share the engine (last forward wins).
-            self._nb2_keepalive = ops.pack_weights(self._nb2_net_id, [l.weight for l in lin], [l.bias for l in lin], pos, dirl,
-                                                   hidden, device=params[0].device)
-            self._nb2_key = key
-            _OWNER[(params[0].device.index, self._nb2_net_id)] = id(self)
-        elif _OWNER.get((params[0].device.index, self._nb2_net_id)) != id(self):
-            self._nb2_key = None
-            return self._nb2_sync()
+            self.__dict__["_nb2_keepalive"] = ops.pack_weights(net_id, [l.weight for l in lin], [l.bias for l in lin], pos, dirl,
+                                                               hidden, device=dev)
+            self.__dict__["_nb2_key"] = key
+        return net_id
+
+    def _nb2_refuse_autograd(self, *inputs):
+        """The engine's forward kernels record no autograd graph: refuse to silently return a detached result when the
+        caller expects gradients (training goes through the layer-wise engine, see train_step / linear.py)."""
+        if torch.is_grad_enabled() and (any(t is not None and t.requires_grad for t in inputs)
+                                        or any(p.requires_grad for p in self.parameters())):
+            raise _lib.NB2Error(f"{type(self).__name__}.forward: the fused inference kernels do not record gradients; call under "
+                                "torch.no_grad() (render / eval), or set module.train_engine = True to run the differentiable "
+                                "layer-wise engine")
 
 
-_OWNER = {}
+def _release_slot(net_id, dev):
+    try:
+        if torch.cuda.is_available():
+            ops.net_destroy(net_id, dev)
+    except Exception:
+        pass   # interpreter shutdown: the handle may already be gone
 
 
 class NeRF(PackedModule):

@@ -40,12 +40,12 @@ def _seed_from_torch():
 
 
 # ---- a1 ---------------------------------------------------------------------------------------
-def generate_rays(pose, H, W, focal_x, focal_y, pix_offset=0, n_rays=None):
+def generate_rays(pose, H, W, focal_x, focal_y, pix_offset=0, n_rays=None, out=None):
     pose = f32(pose[:3, :4])
     n = H * W - pix_offset if n_rays is None else n_rays
-    rays = torch.empty((n, 6), dtype=torch.float32, device=pose.device)
+    rays = out if out is not None else torch.empty((n, 6), dtype=torch.float32, device=pose.device)
     check(load().nb2_generate_rays(handle(pose.device), ptr(pose), H, W, float(focal_x), float(focal_y), pix_offset, n,
-                                   ptr(rays), stream_ptr()))
+                                   ptr(rays), stream_ptr(pose.device)))
     return rays
 
 
@@ -58,7 +58,7 @@ def sample_coarse(rays, base_z, resolution, jitter=None, seed=0, ray_offset=0, w
     z = torch.empty((R, P), dtype=torch.float32, device=rays.device)
     pts = torch.empty((R, P, 3), dtype=torch.float32, device=rays.device) if want_pts else None
     check(load().nb2_sample_coarse(handle(rays.device), ptr(rays), ptr(base_z), ptr(jitter), float(resolution), seed,
-                                   ray_offset, R, P, ptr(z), ptr(pts), stream_ptr()))
+                                   ray_offset, R, P, ptr(z), ptr(pts), stream_ptr(rays.device)))
     return z, pts
 
 
@@ -68,7 +68,7 @@ def posenc(x, levels):
     dims = x.shape[-1]
     n = x.numel() // dims
     out = torch.empty((n, 2 * dims * levels), dtype=torch.float32, device=x.device)
-    check(load().nb2_posenc(handle(x.device), ptr(x), n, dims, levels, ptr(out), stream_ptr()))
+    check(load().nb2_posenc(handle(x.device), ptr(x), n, dims, levels, ptr(out), stream_ptr(x.device)))
     return out
 
 
@@ -82,7 +82,7 @@ def ipe(zvals, cam_rays, levels, radius):
     mu_t = torch.empty((R, C), dtype=torch.float32, device=dev)
     scratch = torch.empty(2, dtype=torch.float64, device=dev)
     check(load().nb2_ipe(handle(dev), ptr(zvals), ptr(cam_rays), R, C, levels, float(radius), ptr(feat), ptr(mu),
-                         ptr(mu_t), ptr(scratch), stream_ptr()))
+                         ptr(mu_t), ptr(scratch), stream_ptr(dev)))
     return feat, mu, mu_t
 
 
@@ -99,7 +99,7 @@ def weights_from_sigma(sigma, z, dirs=None, act="relu"):
         stride = dirs.shape[-1]
     w = torch.empty((R, P), dtype=torch.float32, device=z.device)
     check(load().nb2_weights_from_sigma(handle(z.device), ptr(sigma), ptr(z), ptr(dirs), stride, R, P, _ACTS[act],
-                                        ptr(w), stream_ptr()))
+                                        ptr(w), stream_ptr(z.device)))
     return w
 
 
@@ -109,7 +109,7 @@ def max_blur(weights, alpha):
     P = weights.shape[-1]
     R = weights.numel() // P
     out = torch.empty_like(weights)
-    check(load().nb2_max_blur(handle(weights.device), ptr(weights), R, P, float(alpha), ptr(out), stream_ptr()))
+    check(load().nb2_max_blur(handle(weights.device), ptr(weights), R, P, float(alpha), ptr(out), stream_ptr(weights.device)))
     return out
 
 
@@ -128,7 +128,7 @@ def sample_pdf(bins, weights, n_draw, u=None, seed=None, ray_offset=0):
     below = torch.empty((R, n_draw), dtype=torch.int64, device=dev)
     above = torch.empty((R, n_draw), dtype=torch.int64, device=dev)
     check(load().nb2_sample_pdf(handle(dev), ptr(bins), ptr(weights), ptr(u), seed or 0, ray_offset, R, B, n_draw,
-                                ptr(samples), ptr(below), ptr(above), stream_ptr()))
+                                ptr(samples), ptr(below), ptr(above), stream_ptr(dev)))
     return samples, below, above
 
 
@@ -143,7 +143,7 @@ def inverse_sample(weights, z, n_draw, sort=False, u=None, seed=None, ray_offset
     samples = torch.empty((R, n_draw), dtype=torch.float32, device=dev)
     below = torch.empty((R, n_draw), dtype=torch.int64, device=dev)
     check(load().nb2_inverse_sample(handle(dev), ptr(weights), ptr(z), ptr(u), seed or 0, ray_offset, R, P, n_draw,
-                                    1 if sort else 0, ptr(samples), ptr(below), stream_ptr()))
+                                    1 if sort else 0, ptr(samples), ptr(below), stream_ptr(dev)))
     return samples, below
 
 
@@ -152,20 +152,21 @@ def search_cdf(cdf, u):
     R, B = cdf.shape
     N = u.shape[1]
     inds = torch.empty((R, N), dtype=torch.int64, device=cdf.device)
-    check(load().nb2_search_cdf(handle(cdf.device), ptr(cdf), ptr(u), R, B, N, ptr(inds), stream_ptr()))
+    check(load().nb2_search_cdf(handle(cdf.device), ptr(cdf), ptr(u), R, B, N, ptr(inds), stream_ptr(cdf.device)))
     return inds
 
 
-def resample(sigma, z, rays, n_draw, blur_alpha=0.01, u=None, seed=0, ray_offset=0, softplus=False):
+def resample(sigma, z, rays, n_draw, blur_alpha=0.01, u=None, seed=0, ray_offset=0, softplus=False, want_below=False):
     sigma, z, rays = f32(sigma), f32(z), f32(rays)
     R, P = z.shape
     if u is not None:
         u = f32(u).view(R, n_draw)
     out = torch.empty((R, n_draw - 1), dtype=torch.float32, device=z.device)
+    below = torch.empty((R, n_draw - 1), dtype=torch.int64, device=z.device) if want_below else None
     flags = _lib.DENSITY_SOFTPLUS if softplus else 0
     check(load().nb2_resample(handle(z.device), ptr(sigma), ptr(z), ptr(rays), ptr(u), seed, ray_offset, R, P, n_draw,
-                              float(blur_alpha), flags, ptr(out), stream_ptr()))
-    return out
+                              float(blur_alpha), flags, ptr(out), ptr(below), stream_ptr(z.device)))
+    return (out, below) if want_below else out
 
 
 # ---- a10 / a13 ----------------------------------------------------------------------------------
@@ -173,7 +174,7 @@ def length2pts(rays, z):
     rays, z = f32(rays), f32(z)
     R, P = z.shape
     pts = torch.empty((R, P, 6), dtype=torch.float32, device=z.device)
-    check(load().nb2_length2pts(handle(z.device), ptr(rays), ptr(z), R, P, ptr(pts), stream_ptr()))
+    check(load().nb2_length2pts(handle(z.device), ptr(rays), ptr(z), R, P, ptr(pts), stream_ptr(z.device)))
     return pts
 
 
@@ -183,7 +184,7 @@ def coarse_fine_merge(rays, c_z, f_z):
     z = torch.empty((R, C + F - 1), dtype=torch.float32, device=c_z.device)
     pts = torch.empty((R, C + F - 1, 6), dtype=torch.float32, device=c_z.device)
     check(load().nb2_coarse_fine_merge(handle(c_z.device), ptr(rays), ptr(c_z), ptr(f_z), R, C, F, ptr(z), ptr(pts),
-                                       stream_ptr()))
+                                       stream_ptr(c_z.device)))
     return pts, z
 
 
@@ -206,7 +207,7 @@ def valid_sampler(rgbs, coords, cam_tf, ray_num, point_num, focal_x, focal_y, ne
     rays = torch.empty((ray_num, 6), dtype=torch.float32, device=dev)
     check(load().nb2_valid_sampler(handle(dev), ptr(rgbs), ptr(coords), ptr(cam_tf), ptr(indices), ptr(base_z), ptr(jitter),
                                    float(focal_x), float(focal_y), float(resolution), seed, 0, coords.shape[0], ray_num, point_num,
-                                   ptr(pts), ptr(lengths), ptr(rgb), ptr(rays), stream_ptr()))
+                                   ptr(pts), ptr(lengths), ptr(rgb), ptr(rays), stream_ptr(dev)))
     return pts, lengths, rgb, rays
 
 
@@ -216,20 +217,41 @@ def get_bounds(weights, inds):
     R, P = weights.shape
     K = inds.shape[1]
     out = torch.empty((R, K - 1), dtype=torch.float32, device=weights.device)
-    check(load().nb2_get_bounds(handle(weights.device), ptr(weights), ptr(inds), R, P, K, ptr(out), stream_ptr()))
+    check(load().nb2_get_bounds(handle(weights.device), ptr(weights), ptr(inds), R, P, K, ptr(out), stream_ptr(weights.device)))
     return out
 
 
 # ---- weights / MLP --------------------------------------------------------------------------------
+def net_create(kind, device):
+    """A packed-network slot of `kind` on `device`'s handle (include/nerf_b200.h: nb2_net_create)."""
+    out = ctypes.c_int(-1)
+    check(load().nb2_net_create(handle(device), kind, ctypes.byref(out)))
+    _NET_KIND[(torch.device(device).index, int(out.value))] = kind
+    return int(out.value)
+
+
+_NET_KIND = {}
+
+
+def net_kind(net_id, device):
+    """Kind (NET_PROPOSAL | NET_NERF) of a slot; the default slots 0 / 1 are their own kinds."""
+    return net_id if net_id < 2 else _NET_KIND[(torch.device(device).index, net_id)]
+
+
+def net_destroy(net_id, device):
+    check(load().nb2_net_destroy(handle(device), net_id))
+    _NET_KIND.pop((torch.device(device).index, net_id), None)
+
+
 def pack_weights(net_id, weights, biases, pos_levels, dir_levels, hidden, device=None):
-    """weights/biases: lists of fp32 CUDA tensors in reference state_dict order."""
+    """weights/biases: lists of fp32 CUDA tensors in reference state_dict order; net_id: a slot id."""
     ws = [f32(w.detach()) for w in weights]
     bs = [f32(b.detach()) for b in biases]
     n = len(ws)
     W = (ctypes.c_void_p * n)(*[w.data_ptr() for w in ws])
     B = (ctypes.c_void_p * n)(*[b.data_ptr() for b in bs])
     dev = ws[0].device if device is None else device
-    check(load().nb2_pack_weights(handle(dev), net_id, W, B, n, pos_levels, dir_levels, hidden, stream_ptr()))
+    check(load().nb2_pack_weights(handle(dev), net_id, W, B, n, pos_levels, dir_levels, hidden, stream_ptr(dev)))
     return ws, bs  # keep-alive until the stream has consumed them
 
 
@@ -238,8 +260,8 @@ def mlp_forward(net_id, pts, precision=None):
     stride = pts.shape[-1]
     n = pts.numel() // stride
     dev = pts.device
-    out = torch.empty((n, 4) if net_id == _lib.NET_NERF else (n,), dtype=torch.float32, device=dev)
-    check(load().nb2_mlp_forward(handle(dev), net_id, _prec(precision), ptr(pts), stride, n, ptr(out), stream_ptr()))
+    out = torch.empty((n, 4) if net_kind(net_id, dev) == _lib.NET_NERF else (n,), dtype=torch.float32, device=dev)
+    check(load().nb2_mlp_forward(handle(dev), net_id, _prec(precision), ptr(pts), stride, n, ptr(out), stream_ptr(dev)))
     return out
 
 
@@ -248,10 +270,10 @@ def mlp_forward_encoded(net_id, pts, encoded, precision=None):
     pts, encoded = f32(pts), f32(encoded)
     stride = pts.shape[-1]
     n = pts.numel() // stride
-    if encoded.numel() % n != 0:
-        raise NB2Error("mlp_forward_encoded: encoded features do not match the number of points")
+    if encoded.dim() < 2 or encoded.numel() // encoded.shape[-1] != n:
+        raise NB2Error(f"mlp_forward_encoded: encoded features must hold one row per point ({n}), got shape {tuple(encoded.shape)}")
     out = torch.empty((n,), dtype=torch.float32, device=pts.device)
-    check(load().nb2_mlp_forward_encoded(handle(pts.device), net_id, _prec(precision), ptr(pts), stride, ptr(encoded), n, ptr(out), stream_ptr()))
+    check(load().nb2_mlp_forward_encoded(handle(pts.device), net_id, _prec(precision), ptr(pts), stride, ptr(encoded), n, ptr(out), stream_ptr(pts.device)))
     return out
 
 
@@ -267,7 +289,7 @@ def composite(rgbo, z, dirs, white_bkg=False, near_far=None, want_weights=True):
     near, far = near_far if near_far is not None else (0.0, 1.0)
     check(load().nb2_composite(handle(dev), ptr(rgbo), ptr(z), ptr(dirs), dirs.shape[-1], R, P,
                                _lib.WHITE_BKG if white_bkg else 0, float(near), float(far), ptr(rgb), ptr(w), ptr(depth),
-                               ptr(acc), stream_ptr()))
+                               ptr(acc), stream_ptr(dev)))
     return rgb, w, depth, acc
 
 
@@ -280,21 +302,26 @@ def ide(xyz, kappa_inv, mat, ml):
         raise NB2Error(f"ide: kappa_inv must hold one value per direction ({kappa_inv.numel()} for {n} directions)")
     n_pow, n_pairs = mat.shape
     out = torch.empty((*xyz.shape[:-1], 2 * n_pairs), dtype=torch.float32, device=xyz.device)
-    check(load().nb2_ide(handle(xyz.device), ptr(xyz), ptr(kappa_inv), n, ptr(mat), ptr(ml), n_pairs, n_pow, ptr(out), stream_ptr()))
+    check(load().nb2_ide(handle(xyz.device), ptr(xyz), ptr(kappa_inv), n, ptr(mat), ptr(ml), n_pairs, n_pow, ptr(out), stream_ptr(xyz.device)))
     return out
 
 
 def linear_to_srgb(linear):
     linear = f32(linear)
     out = torch.empty_like(linear)
-    check(load().nb2_linear_to_srgb(handle(linear.device), ptr(linear), linear.numel(), ptr(out), stream_ptr()))
+    check(load().nb2_linear_to_srgb(handle(linear.device), ptr(linear), linear.numel(), ptr(out), stream_ptr(linear.device)))
     return out
 
 
 # ---- the fused path ---------------------------------------------------------------------------------
 def render_rays(rays, base_z, near, far, n_fine=128, white_bkg=False, precision=None, jitter=None, u=None, seed=0,
-                ray_offset=0, resolution=None, blur_alpha=0.01, softplus=False, debug=False, workspace=None):
-    """rays (R,6) -> dict(rgb (R,3), depth (R), acc (R) [, z_coarse, sigma_prop, z_fine])."""
+                ray_offset=0, resolution=None, blur_alpha=0.01, softplus=False, debug=False, workspace=None,
+                prop_net_id=_lib.NET_PROPOSAL, nerf_net_id=_lib.NET_NERF, out=None, peer_rgb=()):
+    """rays (R,6) -> dict(rgb (R,3), depth (R), acc (R) [, z_coarse, sigma_prop, z_fine, below_fine]).
+
+    `out` re-uses a previous result's buffers (no allocation in the step); `peer_rgb`: device pointers (ints) of the
+    other GPUs' full image buffers, which receive this shard's rgb rows at row offset `ray_offset` straight from the
+    compositing epilogue (nb2_render_params.peer_rgb)."""
     rays, base_z = f32(rays), f32(base_z)
     R, Pc = rays.shape[0], base_z.numel()
     dev = rays.device
@@ -306,6 +333,10 @@ def render_rays(rays, base_z, near, far, n_fine=128, white_bkg=False, precision=
     p.flags = (_lib.WHITE_BKG if white_bkg else 0) | (_lib.DENSITY_SOFTPLUS if softplus else 0)
     p.precision = _prec(precision)
     p.seed, p.ray_offset = seed, ray_offset
+    p.prop_net_id, p.nerf_net_id = prop_net_id, nerf_net_id
+    p.n_peers = len(peer_rgb)
+    for q, pp in enumerate(peer_rgb):
+        p.peer_rgb[q] = pp
     lib = load()
     need = lib.nb2_render_workspace_bytes(R, ctypes.byref(p))
     if workspace is None or workspace.numel() < need:
@@ -314,20 +345,22 @@ def render_rays(rays, base_z, near, far, n_fine=128, white_bkg=False, precision=
         jitter = f32(jitter).view(R, Pc)
     if u is not None:
         u = f32(u).view(R, n_fine + 1)
-    out = {
-        "rgb": torch.empty((R, 3), dtype=torch.float32, device=dev),
-        "depth": torch.empty((R,), dtype=torch.float32, device=dev),
-        "acc": torch.empty((R,), dtype=torch.float32, device=dev),
-    }
-    zc = sp = zf = None
+    if out is None or out["rgb"].shape[0] != R or out["rgb"].device != dev:
+        out = {
+            "rgb": torch.empty((R, 3), dtype=torch.float32, device=dev),
+            "depth": torch.empty((R,), dtype=torch.float32, device=dev),
+            "acc": torch.empty((R,), dtype=torch.float32, device=dev),
+        }
+    zc = sp = zf = bf = None
     if debug:
         zc = torch.empty((R, Pc), dtype=torch.float32, device=dev)
         sp = torch.empty((R, Pc), dtype=torch.float32, device=dev)
         zf = torch.empty((R, n_fine), dtype=torch.float32, device=dev)
-        out.update(z_coarse=zc, sigma_prop=sp, z_fine=zf)
+        bf = torch.empty((R, n_fine), dtype=torch.int64, device=dev)
+        out.update(z_coarse=zc, sigma_prop=sp, z_fine=zf, below_fine=bf)
     check(lib.nb2_render_rays(handle(dev), ctypes.byref(p), ptr(rays), ptr(base_z), ptr(jitter), ptr(u), R, ptr(out["rgb"]),
-                              ptr(out["depth"]), ptr(out["acc"]), ptr(zc), ptr(sp), ptr(zf), ptr(workspace),
-                              workspace.numel(), stream_ptr()))
+                              ptr(out["depth"]), ptr(out["acc"]), ptr(zc), ptr(sp), ptr(zf), ptr(bf), ptr(workspace),
+                              workspace.numel(), stream_ptr(dev)))
     out["_workspace"] = workspace
     return out
 
@@ -338,5 +371,5 @@ def selftest_umma(A, B):
     B = B.to(torch.bfloat16).contiguous()
     D = torch.empty((128, 128), dtype=torch.float32, device=A.device)
     scratch = torch.empty(16384, dtype=torch.uint8, device=A.device)
-    check(load().nb2_selftest_umma(handle(A.device), ptr(A), ptr(B), ptr(scratch), ptr(D), stream_ptr()))
+    check(load().nb2_selftest_umma(handle(A.device), ptr(A), ptr(B), ptr(scratch), ptr(D), stream_ptr(A.device)))
     return D

@@ -73,8 +73,8 @@ def render_image(
     else:
         fx = fy = float(focal)
     with torch.no_grad():
-        network._nb2_sync()
-        prop_net._nb2_sync()
+        nerf_id = network._nb2_sync()
+        prop_id = prop_net._nb2_sync()
         rays = ops.generate_rays(render_pose, H, W, fx, fy)
         base_z = torch.linspace(near, far, RENDER_COARSE_PNUM, device=dev)       # procedures.py:52
         resolution = (far - near) / sample_num                                    # procedures.py:59
@@ -87,7 +87,7 @@ def render_image(
             seed = ops._seed_from_torch() if (jitter is None or u is None) else 0
         prec = precision if precision is not None else (network.precision or prop_net.precision)
         out = ops.render_rays(rays, base_z, near, far, n_fine=sample_num, white_bkg=white_bkg, precision=prec,
-                              jitter=jitter, u=u, seed=seed, resolution=resolution)
+                              jitter=jitter, u=u, seed=seed, resolution=resolution, prop_net_id=prop_id, nerf_net_id=nerf_id)
         result = {"rgb": out["rgb"].view(H, W, 3).permute(2, 0, 1).contiguous()}
         if render_depth:
             result["depth_img"] = out["depth"].view(1, H, W).expand(3, H, W).contiguous()

@@ -13,10 +13,13 @@ from nerf_b200 import _lib
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def header_symbols():
-    src = open(os.path.join(ROOT, "include", "nerf_b200.h")).read()
-    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(nb2_[a-z0-9_]+)\s*\(", src)))
+def header_symbols(names=("nerf_b200.h", "nerf_b200_debug.h")):
+    out = set()
+    for name in names:
+        src = open(os.path.join(ROOT, "include", name)).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        out |= set(re.findall(r"\b(nb2_[a-z0-9_]+)\s*\(", src))
+    return sorted(out)
 
 
 def test_library_exports_every_declared_symbol():
@@ -31,12 +34,12 @@ def test_library_exports_every_declared_symbol():
 def test_python_binding_covers_the_header():
     assert sorted(_lib.SIGNATURES) == header_symbols()
     lib = _lib.load()
-    assert lib.nb2_version() == 100
+    assert lib.nb2_version() == 200
 
 
 def test_render_params_struct_matches_header():
-    # 2 int, 4 float, 2 int, u64, i64 -> 48 bytes with natural alignment
-    assert ctypes.sizeof(_lib.RenderParams) == 48
+    # 2 int, 4 float, 2 int, u64, i64, 4 int, 8 pointers -> 128 bytes with natural alignment
+    assert ctypes.sizeof(_lib.RenderParams) == 128
     p = _lib.RenderParams(n_coarse=64, n_fine=128, precision=_lib.PREC_BF16X3)
     assert _lib.load().nb2_render_workspace_bytes(1000, ctypes.byref(p)) == 2 * 256000 + 512000
     p.precision = _lib.PREC_FP32

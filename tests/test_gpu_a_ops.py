@@ -226,3 +226,29 @@ def test_resample_value_sort_equals_rank_sort_at_scale():
     # device RNG path: sorted, inside the sampled range
     zd = ops.resample(sigma, z, rays, 129, 0.01, seed=3)
     assert bool((zd[:, 1:] >= zd[:, :-1]).all()) and float(zd.min()) >= 2.0 and float(zd.max()) <= 6.1
+
+
+def test_cdf_agrees_given_same_sigma():
+    """tests/parity_tools.py TAU_INTERNAL: on IDENTICAL densities the engine's get_weights -> maxBlur and PyTorch's differ
+    only by expf / scan-order ulps, so the cdfs built from them (documented order) agree to well under 2e-6."""
+    from tests.parity_tools import TAU_INTERNAL
+    R = 40000
+    g = torch.Generator().manual_seed(5)
+    z = (torch.linspace(2.0, 6.0, 64) + torch.rand(R, 64, generator=g) * (4.0 / 128)).to(DEV)
+    sigma = (torch.randn(R, 64, generator=g) * 25.0 - 5.0).to(DEV)
+    sigma[: R // 4] *= 0.01                                  # near-empty rays: flat cdfs
+    dirs = (torch.randn(R, 3, generator=g) * 0.5).to(DEV)
+    w_e = ops.max_blur(ops.weights_from_sigma(sigma, z, dirs), 0.01)
+    w_o = O.max_blur(O.weights_from_sigma(sigma, z, dirs), 0.01)
+    d = float((O.build_cdf(w_e[:, 1:-1]) - O.build_cdf(w_o[:, 1:-1])).abs().max())
+    print("max |cdf(engine weights) - cdf(torch weights)| on identical densities:", d)
+    assert d <= 0.5 * TAU_INTERNAL
+
+
+def test_fused_resample_reports_sorted_bin_indices(golden, gin):
+    """nb2_resample's optional `below` output == inverseSample(sort=True)'s gathered indices, drop-last applied."""
+    zf, below = ops.resample(cu(gin["sigma"]), cu(gin["z"]), cu(gin["rays"]), 129, 0.01, u=cu(gin["u"]), want_below=True)
+    w = ops.max_blur(ops.weights_from_sigma(cu(gin["sigma"]), cu(gin["z"]), cu(gin["rays"][:, 3:].contiguous())), 0.01)
+    zs, bs = ops.inverse_sample(w, cu(gin["z"]), 129, sort=True, u=cu(gin["u"]))
+    assert torch.equal(zf, zs[:, :-1]) and torch.equal(below, bs[:, :-1])
+    assert torch.equal(zf, ops.resample(cu(gin["sigma"]), cu(gin["z"]), cu(gin["rays"]), 129, 0.01, u=cu(gin["u"])))

@@ -101,10 +101,12 @@ def test_repack_after_parameter_update():
     pts = torch.cat((O.det_uniform((256, 3), 9, -2.0, 2.0), O.det_uniform((256, 3), 10, -1.0, 1.0)), -1).to(DEV)[None]
     with torch.no_grad():
         a = net.forward(pts).clone()
-        v0 = _lib.load().nb2_weights_version(_lib.handle(), _lib.NET_NERF)
+        slot = net._nb2_sync()
+        assert slot >= 2                         # every module instance owns its packed-network slot
+        v0 = _lib.load().nb2_weights_version(_lib.handle(), slot)
         net.rgb_layer[2].bias.add_(0.5)          # in-place update, like an optimizer step
         b = net.forward(pts)
-        v1 = _lib.load().nb2_weights_version(_lib.handle(), _lib.NET_NERF)
+        v1 = _lib.load().nb2_weights_version(_lib.handle(), slot)
     assert v1 == v0 + 1
     assert float((a[..., :3] - b[..., :3]).abs().max()) > 1e-3 and torch.equal(a[..., 3], b[..., 3])
 
@@ -119,3 +121,56 @@ def test_unpacked_network_is_an_error():
     rc = lib.nb2_mlp_forward(h, _lib.NET_NERF, _lib.PREC_BF16, _lib.ptr(x), 6, 128, _lib.ptr(out), _lib.stream_ptr())
     assert rc == -3 and b"not been packed" in lib.nb2_last_error()
     lib.nb2_destroy(h)
+
+
+def test_two_models_coexist_on_one_handle():
+    """Train / eval / EMA copies: alternating forwards of two module instances do not re-pack each other."""
+    a = load(nerf_b200.MipNeRF(10, 4, 256), O.make_params("nerf", 2, "he"))
+    b = load(nerf_b200.MipNeRF(10, 4, 256), O.make_params("nerf", 3, "he"))
+    a.precision = b.precision = "bf16"
+    pts = torch.cat((O.det_uniform((512, 3), 9, -2.0, 2.0), O.det_uniform((512, 3), 10, -1.0, 1.0)), -1).to(DEV)[None]
+    lib, h = _lib.load(), _lib.handle()
+    with torch.no_grad():
+        ya, yb = a.forward(pts).clone(), b.forward(pts).clone()
+        sa, sb = a._nb2_sync(), b._nb2_sync()
+        assert sa != sb
+        va, vb = lib.nb2_weights_version(h, sa), lib.nb2_weights_version(h, sb)
+        for _ in range(3):
+            assert torch.equal(a.forward(pts), ya) and torch.equal(b.forward(pts), yb)
+        assert (lib.nb2_weights_version(h, sa), lib.nb2_weights_version(h, sb)) == (va, vb)
+    assert not torch.equal(ya, yb)
+    del b
+    import gc
+    gc.collect()                                  # the slot goes back to the handle with the module
+    c = load(nerf_b200.MipNeRF(10, 4, 256), O.make_params("nerf", 4, "he"))
+    c.precision = "bf16"
+    with torch.no_grad():
+        c.forward(pts)
+    assert c._nb2_sync() <= sb
+
+
+def test_autograd_is_refused_loudly_by_the_inference_kernels():
+    net = load(nerf_b200.MipNeRF(10, 4, 256), O.make_params("nerf", 2, "he"))
+    pts = torch.zeros(1, 128, 6, device=DEV)
+    with pytest.raises(nerf_b200.NB2Error):
+        net.forward(pts)                          # parameters require grad and grad mode is on: no silent detach
+    with torch.no_grad():
+        net.forward(pts)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_two_devices_in_one_process():
+    """Per-device launch state lives in the handle: a second GPU in the same process launches with its own shared-memory
+    opt-in and cluster occupancy, on its own stream, without touching the caller's current device."""
+    sn = O.make_params("nerf", 2, "he")
+    pts = torch.cat((O.det_uniform((1000, 3), 9, -2.0, 2.0), O.det_uniform((1000, 3), 10, -1.0, 1.0)), -1)[None]
+    outs = []
+    for d in (0, 1):
+        net = nerf_b200.MipNeRF(10, 4, 256)
+        net.load_state_dict(sn)
+        net = net.to(f"cuda:{d}")
+        net.precision = "fp16x3"
+        with torch.no_grad():
+            outs.append(net.forward(pts.to(f"cuda:{d}")).cpu())
+        assert torch.cuda.current_device() == 0
+    assert torch.equal(outs[0], outs[1])
