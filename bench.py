@@ -4,15 +4,20 @@
   python bench.py --gpus N --steps K --warmup W            the engine (libnerfb200.so)
   python bench.py --impl reference ...                     the reference algorithm on the host CPU cores
                                                            (the oracle port; /root/reference does not travel)
-Workload (BASELINE.json configs[1]): Lego-shaped 400x400 orbit view, 64 coarse + 128 fine samples per ray,
-vanilla NeRF 8x256 + 4x256 proposal MLP, fp32-faithful arithmetic, synthetic poses and random-init weights
-(band-limited 'smooth' field, oracle/nerf_oracle.py:make_params).  A step = one pass of the hot path over one
-400x400 ray batch per GPU (weak scaling: every rank renders its own view; the rendered tiles are all-gathered).
+Workloads (synthetic orbit poses, random-init weights of the reference architectures, 64 coarse + 128 fine samples,
+proposal 4x256 + vanilla NeRF 8x256, fp32-faithful arithmetic unless --precision says otherwise):
+  N = 1   BASELINE configs[1]: one Lego-shaped 400x400 view per step.
+  N > 1   BASELINE configs[4]: ONE 800x800 view per step, its 640,000 rays sharded contiguously across the N GPUs,
+          rows gathered into the full image on every rank ("scaling": "strong").  The gather is fused into the
+          compositing epilogue: finished rgb rows are stored straight into every GPU's image over NVLink (CUDA IPC peer
+          mappings, nerf_b200/sharding.py:PeerImage); `--gather nccl` runs the all_gather baseline instead, and the
+          line carries both numbers.  `--scaling weak` (one 400x400 view per GPU) is kept and reported as an extra key.
 
-One JSON line on stdout (rank 0).  `value` = rays/s with inputs resident in HBM (CUDA events, max over ranks,
-L2 flushed between timed steps); `e2e` = the same through the public API with the pose in pinned host memory
-and the image copied back to the host inside the timed region; `roofline` = the fused encode+MLP+composite
-kernel against the measured bf16 tensor peak; `cpu_baseline` = the oracle on this box's host cores.
+One JSON line on stdout (rank 0).  `value` = rays/s with inputs resident in HBM (CUDA events, max over ranks, L2 flushed
+between timed steps); `e2e` = the same through the public API with the pose in pinned host memory and the full image
+copied back to the host inside the timed region; `roofline` = the fused encode+MLP+composite kernel against the measured
+bf16 tensor peak; `cpu_baseline` = the oracle on this box's host cores; `torch_cuda_baseline` = the reference algorithm
+as PyTorch ops on the same B200 (fp32 with TF32 off, reference-style tile loop and whole-image chunks; fp16 autocast).
 """
 import argparse
 import json
@@ -33,15 +38,17 @@ NEAR, FAR, N_COARSE, N_FINE = 2.0, 6.0, 64, 128
 FLOP_PROP_PER_RAY = 27262976       # 2*(63*256 + 3*256^2 + 256) * 64
 FLOP_NERF_PER_RAY = 135135232      # 2*(63*256 + 3*256^2 + 319*256 + 2*256^2 + 256^2 + 256 + 283*128 + 128*3) * 128
 METRIC = "rays/sec (64c+128f samples)"
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE fine-kernel launch over 160,000 rays, from the ncu --set full
-# captures summarised in profiles/r01_ncu_{fp16x3_tmema,fp16_pp}.txt (algorithmic: 556 B/ray = 89 MB; the
-# 2.4 MB of packed weights stay L2-resident)
-NCU_FINE_TRAFFIC_BYTES_160K = {"fp16x3": 93.1e6, "bf16x3": 93.1e6, "fp16": 91.9e6, "bf16": 91.9e6}
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE fine-kernel launch, per ray, from the ncu --set full captures
+# summarised in profiles/ (algorithmic: 556 B/ray; the 2.4 MB of packed weights stay L2-resident)
+NCU_FINE_TRAFFIC_BYTES_PER_RAY = {"fp16x3": 93.1e6 / 160000, "bf16x3": 93.1e6 / 160000, "fp16": 91.9e6 / 160000, "bf16": 91.9e6 / 160000}
 FINE_KERNEL = {"fp16x3": "mlp_tc4_kernel (fine: encode + 8x256 MLP + composite; CTA-pair tcgen05, activations in TMEM)",
                "bf16x3": "mlp_tc4_kernel (fine: encode + 8x256 MLP + composite; CTA-pair tcgen05, activations in TMEM)",
                "fp16": "mlp_tc2_kernel (fine: encode + 8x256 MLP + composite; CTA-pair tcgen05, ping-pong tiles)",
                "bf16": "mlp_tc2_kernel (fine: encode + 8x256 MLP + composite; CTA-pair tcgen05, ping-pong tiles)",
                "fp32": "mlp_simt_kernel (fine: encode + 8x256 MLP on CUDA cores) + composite_kernel"}
+DTYPE = {"fp16x3": "f32-faithful: fp16 hi+lo split operands, 3 tcgen05 MMAs per product, f32 accumulate", "bf16x3": "bf16 hi+lo split, f32 accumulate",
+         "fp32": "f32 (CUDA cores)", "bf16": "bf16 operands, f32 accumulate", "fp16": "f16 operands, f32 accumulate"}
+CPU_SAMPLE_HW = 100                # the CPU arms render a full 100x100 view (four reference tiles of 50x50)
 
 
 def load_peaks():
@@ -92,69 +99,137 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def oracle_setup(device):
-    from oracle import nerf_oracle as O
-    sp, sn = O.make_params("proposal", 1, "smooth"), O.make_params("nerf", 2, "smooth")
-    return O, O.params_to(sp, device), O.params_to(sn, device)
+def synthetic_state_dicts():
+    """Random-init weights of the reference architectures (band-limited 'smooth' field): nerf_b200/synthetic.py."""
+    from nerf_b200 import synthetic as S
+    return S.make_params("proposal", 1, "smooth"), S.make_params("nerf", 2, "smooth")
 
 
-def cpu_oracle_rays_per_s(n_rays, reps, threads):
-    """The reference algorithm (oracle port, PyTorch fp32 CPU ops = the reference's own arithmetic) on the host."""
+# ---- CPU arms (the oracle port of the reference algorithm; checker code, never on the engine's path) -------------------
+def cpu_reference_render(steps, warmup, threads):
+    """One step = the reference algorithm over a full 100x100 view in its own 50x50 tile order, PyTorch fp32 on the host."""
     import nerf_b200
+    from oracle import nerf_oracle as O
     torch.set_num_threads(threads)
-    O, sp, sn = oracle_setup("cpu")
-    H = W = 400
+    sp, sn = synthetic_state_dicts()
+    H = W = CPU_SAMPLE_HW
     pose = nerf_b200.pose_spherical(30.0, -30.0, 4.0)[:3, :]
     focal = nerf_b200.fov2Focal(FOV, (H, W))[0]
-    rays = O.generate_rays(pose, H, W, focal)
-    # one reference tile = 50x50 pixels (nerf/procedures.py:21,60-64); take the centre tile(s)
-    sel = torch.arange(n_rays) + (H // 2) * W
-    rays = rays[sel]
+    rays = O.generate_rays(pose, H, W, focal).view(H, W, 6)
     base_z = torch.linspace(NEAR, FAR, N_COARSE)
     times = []
     with torch.no_grad():
-        for i in range(reps + 1):
-            g = torch.Generator().manual_seed(i)
-            jit, u = torch.rand(n_rays, N_COARSE, generator=g), torch.rand(n_rays, N_FINE + 1, generator=g)   # the CPU draws of the reference
+        for i in range(warmup + steps):
             t0 = time.perf_counter()
-            O.render_rays(sp, sn, rays, base_z, jit, u, NEAR, FAR, N_FINE, white_bkg=True, chunk=2500)
-            times.append(time.perf_counter() - t0)
-    t = sum(times[1:]) / reps
-    return n_rays / t, t
+            for k in range(H // 50):
+                for j in range(W // 50):
+                    r = rays[50 * k:50 * (k + 1), 50 * j:50 * (j + 1)].reshape(-1, 6)
+                    jit, u = torch.rand(2500, N_COARSE), torch.rand(2500, N_FINE + 1)   # the reference's CPU draws, per tile
+                    O.render_rays(sp, sn, r, base_z, jit, u, NEAR, FAR, N_FINE, white_bkg=True, chunk=2500)
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+    t = sum(times) / len(times)
+    return H * W / t, t
 
 
 def run_reference_arm(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    if int(os.environ.get("RANK", "0")) != 0:
         return
     threads = os.cpu_count() or 1
-    n_rays = 2500
-    torch.set_num_threads(threads)
-    O, sp, sn = oracle_setup("cpu")
-    import nerf_b200
-    H = W = 400
-    pose = nerf_b200.pose_spherical(30.0, -30.0, 4.0)[:3, :]
-    focal = nerf_b200.fov2Focal(FOV, (H, W))[0]
-    rays = O.generate_rays(pose, H, W, focal)[torch.arange(n_rays) + (H // 2) * W]
-    base_z = torch.linspace(NEAR, FAR, N_COARSE)
-    times = []
-    with torch.no_grad():
-        for i in range(args.warmup + args.steps):
-            jit, u = torch.rand(n_rays, N_COARSE), torch.rand(n_rays, N_FINE + 1)
-            t0 = time.perf_counter()
-            O.render_rays(sp, sn, rays, base_z, jit, u, NEAR, FAR, N_FINE, white_bkg=True, chunk=2500)
-            if i >= args.warmup:
-                times.append(time.perf_counter() - t0)
-    ms = 1e3 * sum(times) / len(times)
-    value = n_rays / (ms / 1e3)
-    sample = f"{n_rays} rays (one 50x50 reference tile of the 400x400 view) per step, PyTorch {torch.__version__} CPU fp32, {threads} threads"
+    value, t = cpu_reference_render(args.steps, args.warmup, threads)
+    n_rays = CPU_SAMPLE_HW * CPU_SAMPLE_HW
+    sample = (f"{n_rays} rays per step: a full {CPU_SAMPLE_HW}x{CPU_SAMPLE_HW} view of the same scene in the reference's 50x50 tile order "
+              f"(bounded sample of the 400x400 / 800x800 workload; rays/s normalises it), PyTorch {torch.__version__} CPU fp32, {threads} threads")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": {"workload": "Lego-shaped 400x400 orbit view, 64 coarse + 128 fine, vanilla NeRF (configs[1]); bounded sample", "rays_per_step": n_rays},
+        "warmup": args.warmup, "ms_per_step": 1e3 * t, "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "Lego-shaped orbit view, 64 coarse + 128 fine, proposal 4x256 + vanilla NeRF 8x256 (BASELINE configs[1]/[4]); bounded sample",
+                   "rays_per_step": n_rays, "same_config": False},
         "cpu_baseline": {"value": value, "unit": "rays/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+def torch_cuda_baseline(dev, H, W):
+    """The like-for-like "before": the reference algorithm as PyTorch ops on the SAME B200 (oracle port; the reference's own
+    files do not travel to the GPU box).  fp32 with TF32 off in the reference's 50x50 tile loop with its per-tile CPU draws
+    (nerf/procedures.py:60-90), fp32 in whole-image chunks with device-resident uniforms, and fp16 autocast
+    (nerf/procedures.py:149-152)."""
+    import nerf_b200
+    from oracle import nerf_oracle as O
+    tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    sp, sn = synthetic_state_dicts()
+    sp, sn = O.params_to(sp, dev), O.params_to(sn, dev)
+    pose = nerf_b200.pose_spherical(30.0, -30.0, 4.0)[:3, :].to(dev)
+    focal = nerf_b200.fov2Focal(FOV, (H, W))[0]
+    base_z = torch.linspace(NEAR, FAR, N_COARSE, device=dev)
+    n = H * W
+    out = {}
+
+    def tile_loop():
+        rays = O.generate_rays(pose, H, W, focal).view(H, W, 6)
+        for k in range(H // 50):
+            for j in range(W // 50):
+                r = rays[50 * k:50 * (k + 1), 50 * j:50 * (j + 1)].reshape(-1, 6)
+                jit, u = torch.rand(2500, N_COARSE).to(dev), torch.rand(2500, N_FINE + 1).to(dev)
+                O.render_rays(sp, sn, r, base_z, jit, u, NEAR, FAR, N_FINE, white_bkg=True, chunk=2500)
+
+    jit_d, u_d = torch.rand(n, N_COARSE, device=dev), torch.rand(n, N_FINE + 1, device=dev)
+
+    def chunked():
+        O.render_rays(sp, sn, O.generate_rays(pose, H, W, focal), base_z, jit_d, u_d, NEAR, FAR, N_FINE, white_bkg=True, chunk=20000)
+
+    def autocast():
+        with torch.autocast("cuda", dtype=torch.float16):
+            chunked()
+
+    with torch.no_grad():
+        for name, fn in (("fp32_tile_loop", tile_loop), ("fp32_chunked", chunked), ("fp16_autocast_chunked", autocast)):
+            fn()
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            for _ in range(2):
+                fn()
+            torch.cuda.synchronize(dev)
+            t = (time.perf_counter() - t0) / 2
+            out[name] = {"rays_per_s": n / t, "ms_per_image": 1e3 * t}
+    torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
+    out["what"] = (f"oracle port of the reference algorithm, PyTorch {torch.__version__} CUDA ops on this GPU, one {H}x{W} view, TF32 off; "
+                   "tile_loop = 50x50 tiles with per-tile CPU torch.rand + H2D as the reference does")
+    return out
+
+
+def parity_leg(dev, pose, H, W, focal, base_z, ids, precisions):
+    """The ray-by-ray parity theorem (tests/parity_tools.py) on 8,192 rays of the timed view, plus PSNR figures."""
+    from nerf_b200 import ops
+    from oracle import nerf_oracle as O
+    from tests.parity_tools import render_parity_report
+    sp, sn = synthetic_state_dicts()
+    sp, sn = O.params_to(sp, dev), O.params_to(sn, dev)
+    R = 8192
+    n = H * W
+    rays = ops.generate_rays(pose, H, W, focal, focal)[n // 2: n // 2 + R].contiguous()
+    g = torch.Generator().manual_seed(7)
+    jit, u = torch.rand(R, N_COARSE, generator=g).to(dev), torch.rand(R, N_FINE + 1, generator=g).to(dev)
+    ref = O.render_rays(sp, sn, rays, base_z, jit, u, NEAR, FAR, N_FINE, white_bkg=True)
+    gt = ref["rgb"] + 0.0316 * torch.randn(ref["rgb"].shape, generator=torch.Generator().manual_seed(1)).to(dev)   # a ground truth 30 dB away
+
+    def psnr(a):
+        return -10.0 * math.log10(float(((a - gt) ** 2).mean()))
+    par = {"rays": R}
+    for mode in precisions:
+        got = ops.render_rays(rays, base_z, NEAR, FAR, N_FINE, white_bkg=True, precision=mode, jitter=jit, u=u, debug=True, **ids)
+        err = (got["rgb"] - ref["rgb"]).abs()
+        mse = float((err ** 2).mean())
+        par[mode] = {"max_abs_rgb_err": float(err.max()), "frac_rays_over_1e-4": float((err.amax(-1) > 1e-4).float().mean()),
+                     "psnr_vs_reference_db": (99.0 if mse == 0 else -10.0 * math.log10(mse)),
+                     "psnr_delta_db_at_30dB_gt": psnr(got["rgb"]) - psnr(ref["rgb"])}
+        if mode in ("fp16x3", "bf16x3", "fp32"):
+            par[mode]["theorem"] = render_parity_report(O, sp, sn, rays, base_z, jit, u, NEAR, FAR, got)
+    return par
 
 
 def main():
@@ -164,18 +239,19 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--precision", default="fp16x3", choices=["fp32", "fp16x3", "bf16x3", "fp16", "bf16"])
-    ap.add_argument("--size", type=int, default=400)
-    ap.add_argument("--no-extras", action="store_true", help="skip the secondary precision modes / parity / cpu baseline")
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
-                    help="weak (default): every GPU renders its own --size x --size view; strong: ONE --size x --size image, its "
-                         "rays sharded contiguously across the GPUs and gathered (BASELINE configs[4] at --size 800)")
+    ap.add_argument("--size", type=int, default=0, help="image side; default 400 (N = 1, weak) / 800 (strong)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary precision modes / parity / baselines")
+    ap.add_argument("--scaling", default="auto", choices=["auto", "weak", "strong"],
+                    help="auto: strong for N > 1 (ONE 800x800 image sharded across the GPUs, BASELINE configs[4]); weak: one view per GPU")
+    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
+                    help="strong scaling: rgb rows stored into every GPU's image from the compositing epilogue (peer) | NCCL all_gather")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
 
     import torch.distributed as dist
     import nerf_b200
-    from nerf_b200 import _lib, ops
+    from nerf_b200 import _lib, ops, sharding
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -187,62 +263,91 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     W_ = max(args.warmup, 3)
     K = args.steps
-    H = Wd = args.size
+    strong = (args.scaling == "strong") or (args.scaling == "auto" and world > 1)
+    H = Wd = args.size if args.size else (800 if strong else 400)
     n_rays = H * Wd
-    strong = args.scaling == "strong"
-    from nerf_b200 import sharding
-    # strong scaling: this rank's contiguous slice of the one image
-    r_start, r_count = sharding.shard_range(n_rays, rank, world) if strong else (0, n_rays)
 
     # ---- model + inputs (random-init weights of the reference architecture, synthetic orbit poses) ----
-    from oracle import nerf_oracle as O   # weight generator only here; the checker use is in parity_check()
+    sd_prop, sd_nerf = synthetic_state_dicts()
     prop = nerf_b200.ProposalNetwork(10, 256)
     net = nerf_b200.MipNeRF(10, 4, 256)
-    prop.load_state_dict(O.make_params("proposal", 1, "smooth"))
-    net.load_state_dict(O.make_params("nerf", 2, "smooth"))
+    prop.load_state_dict(sd_prop)
+    net.load_state_dict(sd_nerf)
     prop, net = prop.to(dev), net.to(dev)
     with torch.no_grad():
-        prop._nb2_sync(); net._nb2_sync()
-    theta = 30.0 if strong else -180.0 + 360.0 * rank / max(world, 1) + 30.0
-    pose_host = nerf_b200.pose_spherical(theta, -30.0, 4.0)[:3, :].contiguous().pin_memory()
-    pose = pose_host.to(dev)
-    focal = float(nerf_b200.fov2Focal(FOV, (H, Wd))[0])
+        ids = dict(prop_net_id=prop._nb2_sync(), nerf_net_id=net._nb2_sync())
     base_z = torch.linspace(NEAR, FAR, N_COARSE, device=dev)
     flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)    # > 126 MB L2
     lib, h = _lib.load(), _lib.handle(dev)
-    gathered = torch.empty((world * n_rays, 3), dtype=torch.float32, device=dev) if (world > 1 and not strong) else None
-    state = {"ws": None}
 
-    def step(precision, seed, pose_t=None):
-        pose_t = pose if pose_t is None else pose_t
-        if strong:
+    class Scene:
+        """One workload: geometry of the view, this rank's shard, pre-allocated buffers (nothing allocates in a step)."""
+
+        def __init__(self, H, W, strong, gather):
+            self.H, self.W, self.strong, self.gather = H, W, strong, gather
+            self.n = H * W
+            self.start, self.count = sharding.shard_range(self.n, rank, world) if strong else (0, self.n)
+            theta = 30.0 if strong else -180.0 + 360.0 * rank / max(world, 1) + 30.0
+            self.pose_host = nerf_b200.pose_spherical(theta, -30.0, 4.0)[:3, :].contiguous().pin_memory()
+            self.pose = self.pose_host.to(dev)
+            self.focal = float(nerf_b200.fov2Focal(FOV, (H, W))[0])
+            self.rays = torch.empty((self.count, 6), dtype=torch.float32, device=dev)
+            self.peer = self.gbuf = self.weak_out = None
+            self.out = None
+            self.ws = None
+            if strong and world > 1 and gather == "peer":
+                self.peer = sharding.PeerImage(self.n, 3, dev)
+                self.out = {"rgb": self.peer.local_rows(self.start, self.count),
+                            "depth": torch.empty((self.count,), dtype=torch.float32, device=dev),
+                            "acc": torch.empty((self.count,), dtype=torch.float32, device=dev)}
+            elif strong and world > 1:
+                self.gbuf = sharding.GatherBuffers(self.n, 3, world, dev)
+            elif world > 1:
+                self.weak_out = torch.empty((world * self.n, 3), dtype=torch.float32, device=dev)
+
+        def step(self, precision, seed, pose_t=None):
+            """ray generation + the three launches of nb2_render_rays (+ the gather).  Returns the full image rows on
+            every rank in strong mode, this rank's own view otherwise."""
+            pose_t = self.pose if pose_t is None else pose_t
+            ops.generate_rays(pose_t, self.H, self.W, self.focal, self.focal, pix_offset=self.start, n_rays=self.count, out=self.rays)
             # device RNG is keyed on the GLOBAL ray id (ray_offset), so the image does not depend on the world size
-            rays = ops.generate_rays(pose_t, H, Wd, focal, focal, pix_offset=r_start, n_rays=r_count)
-            out = ops.render_rays(rays, base_z, NEAR, FAR, N_FINE, white_bkg=True, precision=precision, seed=seed,
-                                  ray_offset=r_start, workspace=state["ws"])
-            state["ws"] = out["_workspace"]
-            out["image_rows"] = sharding.gather_rows(out["rgb"], n_rays)     # the one exchange: final tile gather
-            return out
-        rays = ops.generate_rays(pose_t, H, Wd, focal, focal)
-        out = ops.render_rays(rays, base_z, NEAR, FAR, N_FINE, white_bkg=True, precision=precision, seed=seed, workspace=state["ws"])
-        state["ws"] = out["_workspace"]
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, out["rgb"])     # the one exchange: final tile gather
-        return out
+            out = ops.render_rays(self.rays, base_z, NEAR, FAR, N_FINE, white_bkg=True, precision=precision, seed=seed,
+                                  ray_offset=self.start, workspace=self.ws, out=self.out,
+                                  peer_rgb=self.peer.peer_ptrs if self.peer is not None else (), **ids)
+            self.out, self.ws = out, out["_workspace"]
+            if self.peer is not None:
+                self.peer.fence()                    # every rank's rows have landed in every image
+                return self.peer.image
+            if self.gbuf is not None:
+                return sharding.gather_rows(out["rgb"], self.n, buffers=self.gbuf)     # the one exchange: final tile gather
+            if self.weak_out is not None:
+                dist.all_gather_into_tensor(self.weak_out, out["rgb"])
+            return out["rgb"]
+
+        def close(self):
+            if self.peer is not None:
+                self.peer.close()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(precision, steps, kernel_events=False):
+    def reduce_max(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(scene, precision, steps, kernel_events=False, fn=None):
+        fn = fn or (lambda i: scene.step(precision, i))
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         kev = None
         if kernel_events:
             import ctypes
             kev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(steps)]
         for i in range(W_):
-            step(precision, i)
+            fn(i)
         barrier()
         n0 = lib.nb2_launch_count(h)
         for i in range(steps):
@@ -253,29 +358,26 @@ def main():
                 arr = (ctypes.c_void_p * 4)(*[e.cuda_event for e in kev[i]])
                 _lib.check(lib.nb2_set_profile_events(h, arr))
             evs[i][0].record()
-            step(precision, 1000 + i)
+            fn(1000 + i)
             evs[i][1].record()
         barrier()
         if kev is not None:
             _lib.check(lib.nb2_set_profile_events(h, None))
         launches = lib.nb2_launch_count(h) - n0
-        ms = sum(a.elapsed_time(b) for a, b in evs) / steps
-        kms = None
-        if kev is not None:
-            kms = [sum(k[j].elapsed_time(k[j + 1]) for k in kev) / steps for j in range(3)]
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()), launches, kms
+        ms = reduce_max(sum(a.elapsed_time(b) for a, b in evs) / steps)
+        kms = [sum(k[j].elapsed_time(k[j + 1]) for k in kev) / steps for j in range(3)] if kev is not None else None
+        return ms, launches, kms
 
     with torch.no_grad():
+        scene = Scene(H, Wd, strong, args.gather)
         sampler = ClockSampler(local)
         if rank == 0:
             sampler.start()
-        ms, launches, kms = timed(args.precision, K, kernel_events=True)
+        ms, launches, kms = timed(scene, args.precision, K, kernel_events=True)
         clocks = sampler.stop() if rank == 0 else None
         # sanity on what the timed loop produced (not timed): every pixel of the last step finite and inside [0, 1] + eps
-        last = step(args.precision, 1000 + K - 1)["rgb"]
+        last = scene.step(args.precision, 1000 + K - 1)
+        torch.cuda.synchronize()
         sane = torch.tensor([float(torch.isfinite(last).all() and float(last.min()) > -1e-3 and float(last.max()) < 1.0 + 1e-3)], device=dev)
         if world > 1:
             dist.all_reduce(sane, op=dist.ReduceOp.MIN)
@@ -284,116 +386,106 @@ def main():
         total_rays = n_rays if strong else world * n_rays
         value = total_rays / (ms / 1e3)
 
-        # ---- e2e: public API, pose from pinned host memory, image back to pinned host memory, every step ----
-        img_host = torch.empty((3, H, Wd), dtype=torch.float32).pin_memory()
-        e_evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-
-        rows_host = torch.empty((n_rays, 3), dtype=torch.float32).pin_memory() if strong else None
+        # ---- e2e: pose from pinned host memory, FULL image back to pinned host memory, every step ----
+        img_host = torch.empty((n_rays, 3) if strong else (3, H, Wd), dtype=torch.float32).pin_memory()
 
         def e2e_step(i):
-            p_dev = pose_host.to(dev, non_blocking=True)
+            p_dev = scene.pose_host.to(dev, non_blocking=True)
             if strong:
-                # the sharded render has no single-call public API in the reference's surface: pose in, shard, gather, image out
-                res = step(args.precision, i, p_dev)
+                # the sharded render has no single-call API in the reference's surface: pose in, shard, gather, image out
+                img = scene.step(args.precision, i, p_dev)
                 if rank == 0:
-                    rows_host.copy_(res["image_rows"], non_blocking=True)
+                    img_host.copy_(img, non_blocking=True)
                 return
-            res = nerf_b200.render_image(net, prop, p_dev, (H, Wd), focal, NEAR, FAR, N_FINE, white_bkg=True, precision=args.precision, seed=i)
+            res = nerf_b200.render_image(net, prop, p_dev, (H, Wd), scene.focal, NEAR, FAR, N_FINE, white_bkg=True, precision=args.precision, seed=i)
             img_host.copy_(res["rgb"], non_blocking=True)
-        for i in range(W_):
-            e2e_step(i)
-        barrier()
-        for i in range(K):
-            flush.zero_()
-            e_evs[i][0].record()
-            e2e_step(2000 + i)
-            e_evs[i][1].record()
-        barrier()
-        e_ms = sum(a.elapsed_time(b) for a, b in e_evs) / K
-        t = torch.tensor([e_ms], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e_ms = float(t.item())
-        e2e = {"value": total_rays / (e_ms / 1e3), "unit": "rays/s", "h2d_bytes_per_step": pose_host.numel() * 4,
-               "d2h_bytes_per_step": img_host.numel() * 4, "ms_per_step": e_ms}
+        e_ms, _, _ = timed(scene, args.precision, K, fn=e2e_step)
+        e2e = {"value": total_rays / (e_ms / 1e3), "unit": "rays/s", "h2d_bytes_per_step": scene.pose_host.numel() * 4,
+               "d2h_bytes_per_step": img_host.numel() * 4, "ms_per_step": e_ms,
+               "api": "pose (pinned host) -> shard render -> fused gather -> full image to pinned host on rank 0" if strong
+                      else "nerf_b200.render_image (pose from pinned host memory, image to pinned host memory)"}
 
-        shard_diff = None
+        extras, multi = {}, {}
         if strong and world > 1 and not args.no_extras:
-            # the gathered image must not depend on the world size: rank 0 renders all rays itself with the same seed
-            res = step(args.precision, 4242)
+            # (a) the gathered image must not depend on the world size: rank 0 renders all rays itself with the same seed
+            img = scene.step(args.precision, 4242).clone()
+            torch.cuda.synchronize()
             if rank == 0:
-                full = ops.render_rays(ops.generate_rays(pose, H, Wd, focal, focal), base_z, NEAR, FAR, N_FINE, white_bkg=True,
-                                       precision=args.precision, seed=4242)
-                shard_diff = float((res["image_rows"] - full["rgb"]).abs().max())
-        extras = {}
+                full = ops.render_rays(ops.generate_rays(scene.pose, H, Wd, scene.focal, scene.focal), base_z, NEAR, FAR, N_FINE,
+                                       white_bkg=True, precision=args.precision, seed=4242, **ids)
+                multi["shard_invariance_max_abs_diff"] = float((img - full["rgb"]).abs().max())
+            barrier()
+            # (b) the other gather implementation on the same workload
+            other = "nccl" if args.gather == "peer" else "peer"
+            sc2 = Scene(H, Wd, True, other)
+            o_ms, _, _ = timed(sc2, args.precision, max(5, K // 2))
+            sc2.close()
+            multi[f"gather_{other}"] = {"ms_per_step": o_ms, "rays_per_s": n_rays / (o_ms / 1e3)}
+            multi[f"gather_{args.gather}"] = {"ms_per_step": ms, "rays_per_s": value}
+            # (c) weak scaling (round 1's multi-GPU line): one 400x400 view per GPU, tiles all-gathered
+            sc3 = Scene(400, 400, False, "nccl")
+            w_ms, _, _ = timed(sc3, args.precision, max(5, K // 2))
+            multi["weak_scaling"] = {"workload": "one 400x400 view per GPU, all_gather of the tiles", "ms_per_step": w_ms,
+                                     "rays_per_s": world * 160000 / (w_ms / 1e3)}
         if not args.no_extras:
             for mode in ("bf16", "fp16"):
                 if mode == args.precision:
                     continue
-                m_ms, _, m_k = timed(mode, max(5, K // 2), kernel_events=True)
-                extras[mode] = {"rays_per_s": total_rays / (m_ms / 1e3), "ms_per_step": m_ms,
-                                "fine_kernel_ms": m_k[2], "fine_kernel_tflops": FLOP_NERF_PER_RAY * r_count / (m_k[2] * 1e-3) / 1e12}
+                m_ms, _, m_k = timed(scene, mode, max(5, K // 2), kernel_events=True)
+                extras[mode] = {"rays_per_s": total_rays / (m_ms / 1e3), "ms_per_step": m_ms, "fine_kernel_ms": m_k[2],
+                                "fine_kernel_tflops": FLOP_NERF_PER_RAY * scene.count / (m_k[2] * 1e-3) / 1e12}
 
     if rank != 0:
+        scene.close()
         if world > 1:
             dist.destroy_process_group()
         return
 
     peaks = load_peaks()
     fine_ms = kms[2]
-    achieved = FLOP_NERF_PER_RAY * r_count / (fine_ms * 1e-3) / 1e12     # rank 0's launch
+    achieved = FLOP_NERF_PER_RAY * scene.count / (fine_ms * 1e-3) / 1e12     # rank 0's launch
     passes = 3 if args.precision in ("fp16x3", "bf16x3") else 1
+    traffic = NCU_FINE_TRAFFIC_BYTES_PER_RAY.get(args.precision)
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
-                "traffic": (NCU_FINE_TRAFFIC_BYTES_160K.get(args.precision) if r_count == 160000 else None),
-                "traffic_unit": "bytes per launch (ncu dram read+write; algorithmic 556 B/ray)",
+                "traffic": traffic * scene.count if traffic else None,
+                "traffic_unit": "bytes per launch (ncu dram read+write per ray x rays of the launch; algorithmic 556 B/ray)",
                 "kernel": FINE_KERNEL[args.precision], "kernel_ms": fine_ms,
-                "algorithmic_flop_per_launch": FLOP_NERF_PER_RAY * r_count, "peak_source": peaks["src"], "mma_passes_per_product": passes,
+                "algorithmic_flop_per_launch": FLOP_NERF_PER_RAY * scene.count, "peak_source": peaks["src"], "mma_passes_per_product": passes,
                 "issued_tensor_tflops": achieved * passes * 528384.0 / 527872.0,
-                "frac_issued": achieved * passes * 528384.0 / 527872.0 / peaks["tflops"], "step_share": {"proposal_kernel_ms": kms[0], "resample_kernel_ms": kms[1], "fine_kernel_ms": kms[2]}}
+                "frac_issued": achieved * passes * 528384.0 / 527872.0 / peaks["tflops"],
+                "frac_of_precision_ceiling": achieved * passes / peaks["tflops"],
+                "step_share": {"proposal_kernel_ms": kms[0], "resample_kernel_ms": kms[1], "fine_kernel_ms": kms[2]}}
     for mode, m in extras.items():
         m["fine_kernel_frac_of_peak"] = m["fine_kernel_tflops"] / peaks["tflops"]
 
+    if strong:
+        workload = (f"ONE Lego-shaped {H}x{Wd} orbit view per step, its {n_rays} rays sharded contiguously across {world} GPU(s) and gathered into "
+                    "the full image on every rank (BASELINE configs[4]), ")
+        par = f"ray-sharded x{world}; gather = " + ("rgb rows stored into every GPU's image by the compositing epilogue over NVLink (CUDA IPC), one 4-byte all_reduce as fence"
+                                                      if args.gather == "peer" and world > 1 else "all_gather_into_tensor of the rgb rows")
+    else:
+        workload = f"Lego-shaped {H}x{Wd} orbit view per GPU (BASELINE configs[1]), "
+        par = f"independent views x{world}" + (", all_gather of the rgb tiles" if world > 1 else "")
     line = {
         "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": K, "warmup": W_, "ms_per_step": ms,
-        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
-        "dtype": {"fp16x3": "f32-faithful: fp16 hi+lo split operands, 3 tcgen05 MMAs per product, f32 accumulate", "bf16x3": "bf16 hi+lo split, f32 accumulate",
-                  "fp32": "f32 (CUDA cores)", "bf16": "bf16 operands, f32 accumulate", "fp16": "f16 operands, f32 accumulate"}[args.precision],
-        "data": "synthetic",
-        "config": {"workload": (f"ONE Lego-shaped {H}x{Wd} orbit view, rays sharded across the GPUs (BASELINE configs[4] at 800x800), " if strong
-                                else f"Lego-shaped {H}x{Wd} orbit view per GPU, ") + "64 coarse + 128 fine samples, proposal 4x256 + NeRF 8x256 (BASELINE configs[1])",
-                   "rays_per_gpu_per_step": r_count, "precision": args.precision, "l2": "flushed between timed steps (512 MB memset)",
-                   "rng": "device Philox keyed on global ray id", "parallelism": f"ray-sharded x{world}, all_gather of rgb tiles"},
+        "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
+        "dtype": DTYPE[args.precision], "data": "synthetic",
+        "config": {"workload": workload + "64 coarse + 128 fine samples, proposal 4x256 + NeRF 8x256",
+                   "rays_per_gpu_per_step": scene.count, "precision": args.precision, "l2": "flushed between timed steps (512 MB memset)",
+                   "rng": "device Philox keyed on global ray id", "parallelism": par, **multi},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "other_precisions": extras,
     }
-    if shard_diff is not None:
-        line["config"]["shard_invariance_max_abs_diff"] = shard_diff   # gathered image vs the same image rendered on one GPU
 
     if not args.no_extras and world == 1:
-        # parity spot check against the oracle running the reference algorithm in PyTorch fp32 on the same GPU
-        O2, sp, sn = oracle_setup(dev)
         with torch.no_grad():
-            R = 8192
-            rays = ops.generate_rays(pose, H, Wd, focal, focal)[n_rays // 2: n_rays // 2 + R].contiguous()
-            g = torch.Generator().manual_seed(7)
-            jit, u = torch.rand(R, N_COARSE, generator=g).to(dev), torch.rand(R, N_FINE + 1, generator=g).to(dev)
-            ref = O2.render_rays(sp, sn, rays, base_z, jit, u, NEAR, FAR, N_FINE, white_bkg=True)
-            par = {}
-            for mode in dict.fromkeys([args.precision, "bf16", "fp16"]):
-                got = ops.render_rays(rays, base_z, NEAR, FAR, N_FINE, white_bkg=True, precision=mode, jitter=jit, u=u)
-                err = (got["rgb"] - ref["rgb"]).abs()
-                mse = float((err ** 2).mean())
-                # PSNR delta against a synthetic ground truth 30 dB away from the reference render
-                gt = (ref["rgb"] + 0.0316 * torch.randn(ref["rgb"].shape, generator=torch.Generator().manual_seed(1)).to(dev))
-                psnr = lambda a: -10.0 * math.log10(float(((a - gt) ** 2).mean()))
-                par[mode] = {"max_abs_rgb_err": float(err.max()), "frac_rays_over_1e-4": float((err.amax(-1) > 1e-4).float().mean()),
-                             "psnr_vs_reference_db": (99.0 if mse == 0 else -10.0 * math.log10(mse)),
-                             "psnr_delta_db_at_30dB_gt": psnr(got["rgb"]) - psnr(ref["rgb"])}
-            line["parity_vs_oracle"] = {"rays": R, **par}
+            line["parity_vs_oracle"] = parity_leg(dev, scene.pose, H, Wd, scene.focal, base_z, ids, list(dict.fromkeys([args.precision, "bf16", "fp16"])))
+        line["torch_cuda_baseline"] = torch_cuda_baseline(dev, 400, 400)
         cores = os.cpu_count() or 1
-        cpu_v, cpu_t = cpu_oracle_rays_per_s(2500, 3, cores)
+        cpu_v, cpu_t = cpu_reference_render(2, 1, cores)
         line["cpu_baseline"] = {"value": cpu_v, "unit": "rays/s", "cores": cores, "kind": "port",
-                                "sample": f"3 x 2500 rays (one 50x50 reference tile of the same view), {cpu_t:.2f} s each, PyTorch CPU fp32"}
+                                "sample": f"2 x a full {CPU_SAMPLE_HW}x{CPU_SAMPLE_HW} view of the same scene (four 50x50 reference tiles, {cpu_t:.2f} s each), PyTorch CPU fp32"}
     print(json.dumps(line))
+    scene.close()
     if world > 1:
         dist.destroy_process_group()
 

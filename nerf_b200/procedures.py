@@ -18,32 +18,39 @@ RENDER_COARSE_PNUM = 64
 
 
 def get_patch_size(image_size):
-    """Tile size the reference would use (nerf/procedures.py:24-31).  Only the 'reference' RNG mode
-    needs it (to replay the reference's per-tile draw order); unlike the reference it returns a
-    single whole-image tile instead of crashing when no candidate divides the width."""
+    """Tile size of the reference (nerf/procedures.py:24-31): the first of [50, 40, 60, 30] that divides the WIDTH, and
+    a (H // sz, W // sz) tile grid -- so when the height is not a multiple of sz the reference never renders the rows
+    past (H // sz) * sz and leaves them at zero; render_image below reproduces that.  The one divergence: when no
+    candidate divides the width the reference raises UnboundLocalError (e.g. 64x64); here that case is a single
+    whole-image tile, (None, (1, 1))."""
     for patch_size in POSSIBLE_PATCH_SIZE:
-        if image_size[1] % patch_size == 0 and image_size[0] % patch_size == 0:
+        if image_size[1] % patch_size == 0:
             return patch_size, (image_size[0] // patch_size, image_size[1] // patch_size)
     return None, (1, 1)
+
+
+def rendered_rows(image_size):
+    """Rows of the image the reference's tile loop covers (all of them when no tile size applies)."""
+    sz, patch_num = get_patch_size(image_size)
+    return image_size[0] if sz is None else sz * patch_num[0]
 
 
 def _reference_rng_draws(image_size, n_coarse, n_draw):
     """Replay the reference's CPU draws in its tile order and scatter them to raster order:
     per tile torch.rand((sz, sz, 64)) for the jitter (procedures.py:65) then torch.rand((sz*sz, 129))
-    inside sample_pdf (utils.py:115)."""
+    inside sample_pdf (utils.py:115).  Returns draws for the rendered rows only."""
     H, W = image_size
     sz, patch_num = get_patch_size(image_size)
-    jitter = torch.empty((H, W, n_coarse), dtype=torch.float32)
-    u = torch.empty((H, W, n_draw), dtype=torch.float32)
     if sz is None:
-        jitter.copy_(torch.rand((H, W, n_coarse)))
-        u.copy_(torch.rand((H * W, n_draw)).view(H, W, n_draw))
-        return jitter.view(H * W, n_coarse), u.view(H * W, n_draw)
+        return torch.rand((H, W, n_coarse)).view(H * W, n_coarse), torch.rand((H * W, n_draw))
+    He = sz * patch_num[0]
+    jitter = torch.empty((He, W, n_coarse), dtype=torch.float32)
+    u = torch.empty((He, W, n_draw), dtype=torch.float32)
     for k in range(patch_num[0]):
         for j in range(patch_num[1]):
             jitter[sz * k:sz * (k + 1), sz * j:sz * (j + 1)] = torch.rand((sz, sz, n_coarse))
             u[sz * k:sz * (k + 1), sz * j:sz * (j + 1)] = torch.rand((sz * sz, n_draw)).view(sz, sz, n_draw)
-    return jitter.view(H * W, n_coarse), u.view(H * W, n_draw)
+    return jitter.view(He * W, n_coarse), u.view(He * W, n_draw)
 
 
 def render_image(
@@ -54,11 +61,11 @@ def render_image(
     """Same positional signature and return value as the reference (nerf/procedures.py:34-97):
     {"rgb": (3,H,W)[, "depth_img": (3,H,W)]} on render_pose.device.
 
-    Keyword-only extensions: `precision` ('fp32' | 'bf16x3' | 'bf16'); `rng` = 'philox' (device
-    counter-based RNG, seed from torch's CPU generator unless `seed` is given) or 'reference'
-    (replays the reference's CPU torch.rand draws tile by tile, so the same torch.manual_seed gives
-    the same samples as the reference); `jitter` (H*W, 64) / `u` (H*W, sample_num+1) inject the
-    uniforms directly (raster order).
+    Keyword-only extensions: `precision` ('fp16x3' (default, fp32-faithful) | 'fp32' | 'bf16x3' | 'fp16' | 'bf16');
+    `rng` = 'philox' (device counter-based RNG, seed from torch's CPU generator unless `seed` is given) or 'reference'
+    (replays the reference's CPU torch.rand draws tile by tile, so the same torch.manual_seed gives the same samples
+    as the reference); `jitter` (rows*W, 64) / `u` (rows*W, sample_num+1) inject the uniforms directly (raster order
+    over the rendered rows).  Like the reference, rows past (H // tile) * tile stay zero (see get_patch_size).
     """
     if not isinstance(image_size, Iterable):
         image_size = (image_size, image_size)
@@ -75,7 +82,11 @@ def render_image(
     with torch.no_grad():
         nerf_id = network._nb2_sync()
         prop_id = prop_net._nb2_sync()
-        rays = ops.generate_rays(render_pose, H, W, fx, fy)
+        He = rendered_rows((H, W))
+        if He == 0:
+            zero = torch.zeros((3, H, W), dtype=torch.float32, device=dev)
+            return {"rgb": zero, "depth_img": zero.clone()} if render_depth else {"rgb": zero}
+        rays = ops.generate_rays(render_pose, H, W, fx, fy, n_rays=He * W)
         base_z = torch.linspace(near, far, RENDER_COARSE_PNUM, device=dev)       # procedures.py:52
         resolution = (far - near) / sample_num                                    # procedures.py:59
         if jitter is None and u is None and rng == "reference":
@@ -88,7 +99,14 @@ def render_image(
         prec = precision if precision is not None else (network.precision or prop_net.precision)
         out = ops.render_rays(rays, base_z, near, far, n_fine=sample_num, white_bkg=white_bkg, precision=prec,
                               jitter=jitter, u=u, seed=seed, resolution=resolution, prop_net_id=prop_id, nerf_net_id=nerf_id)
-        result = {"rgb": out["rgb"].view(H, W, 3).permute(2, 0, 1).contiguous()}
+        def image(rows, channels):
+            img = rows.view(He, W, channels).permute(2, 0, 1)
+            if He == H:
+                return img.contiguous()
+            full = torch.zeros((channels, H, W), dtype=torch.float32, device=dev)   # the reference's never-rendered rows
+            full[:, :He] = img
+            return full
+        result = {"rgb": image(out["rgb"], 3)}
         if render_depth:
-            result["depth_img"] = out["depth"].view(1, H, W).expand(3, H, W).contiguous()
+            result["depth_img"] = image(out["depth"], 1).expand(3, H, W).contiguous()
     return result

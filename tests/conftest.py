@@ -42,3 +42,11 @@ def golden_refnerf():
     """Outputs of the unmodified reference's Ref-NeRF helpers (tests/golden/make_golden.py refnerf)."""
     z = np.load(os.path.join(ROOT, "tests", "golden", "reference_outputs_refnerf.npz"))
     return {k: torch.from_numpy(z[k]) for k in z.files}
+
+
+@pytest.fixture(scope="session")
+def golden_round2():
+    """Round-2 outputs of the unmodified reference (tests/golden/make_golden.py round2): seeded multi-tile render_image,
+    Ref-NeRF forward / Ref branch of render_image, one training step's losses and gradient summaries."""
+    z = np.load(os.path.join(ROOT, "tests", "golden", "reference_outputs_round2.npz"))
+    return {k: torch.from_numpy(z[k].astype(np.int64) if z[k].dtype == np.int16 else z[k]) for k in z.files}

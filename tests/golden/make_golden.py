@@ -254,8 +254,124 @@ def main_refnerf():
     print("wrote", path, os.path.getsize(path) // 1024, "KiB;", len(out), "arrays; torch", torch.__version__)
 
 
+# ---- round 2: multi-tile render_image under torch.manual_seed, Ref-NeRF forward, one training step ----------------------
+def refnerf_inputs():
+    g = {}
+    g["pts"] = torch.cat((det_uniform((6, 24, 3), 71, -1.5, 1.5), det_uniform((6, 1, 3), 72, -1.0, 1.0).expand(6, 24, 3)), dim=-1).contiguous()
+    return g
+
+
+def train_inputs():
+    """One training batch (train.py:157-163): 48 rays of the 40x30 image of inputs_train(), 64 coarse + 128 fine."""
+    vs = inputs_train()
+    return {"vs": vs, "indices": (torch.arange(48) * 23 + 3) % (30 * 40), "jitter": det_uniform((48, 64), 81, 0.0, 1.0),
+            "u": det_uniform((48, 129), 82, 0.0, 1.0)}
+
+
+GRAD_HEAD = 48   # leading entries of every gradient tensor that are stored next to its norm and sum
+
+
+def main_round2():
+    import math
+    np.math = math
+    ref = import_reference()
+    from nerf_b200.synthetic import det_state_dict
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    out = {}
+    rq = RandQueue()
+    with torch.no_grad():
+        # (1) render_image over several tiles with the reference's OWN torch.rand draws (no injection): 100x100 = 2x2 tiles
+        # of 50, and 70x100 where the reference leaves rows 50..69 unrendered (procedures.py:24-31,60-64)
+        prop = load_sd(ref.ProposalNetwork(10, 256), make_params("proposal", 1, "smooth"))
+        net = load_sd(ref.MipNeRF(10, 4, 256), make_params("nerf", 2, "smooth"))
+        for (H, W) in ((100, 100), (70, 100)):
+            pose, _, _, _ = render_case(H, W)
+            focal = float(W / np.tan(0.5 * 0.6911112070083618))
+            torch.manual_seed(2024)
+            res = ref.procedures.render_image(net, prop, pose, (H, W), focal, 2.0, 6.0, 128, white_bkg=True, render_depth=True)
+            out[f"seeded_rgb_{H}x{W}"] = res["rgb"]
+            out[f"seeded_depth_{H}x{W}"] = res["depth_img"][0]
+
+        # (2) Ref-NeRF (nerf/ref_model.py:16-118), eval mode (no bottleneck noise), deterministic parameters
+        from nerf.ref_model import RefNeRF
+        rn = RefNeRF(10, 4)
+        rn.load_state_dict(det_state_dict(rn, 7, gain=1.0))
+        rn.eval()
+        g = refnerf_inputs()
+        rgbo, normal = rn.forward(g["pts"])
+        out["ref_fwd_rgbo"], out["ref_fwd_normal"] = rgbo, normal
+        rn_srgb = RefNeRF(10, 4, use_srgb=True)
+        rn_srgb.load_state_dict(det_state_dict(rn_srgb, 7, gain=1.0))
+        rn_srgb.eval()
+        out["ref_fwd_rgbo_srgb"] = rn_srgb.forward(g["pts"])[0]
+        # coarseFineMerge with index bookkeeping (nerf_base.py:58-73)
+        go = inputs_ops()
+        w_blur = ref.mip_methods.maxBlurFilter(ref.ProposalNetwork.get_weights(go["sigma"], go["z"], go["dirs"]), 0.01)
+        torch.rand = rq
+        rq.push(go["u"])
+        zs, bs = ref.utils.inverseSample(w_blur, go["z"], 129, sort=True)
+        torch.rand = rq.real
+        mp, mz, minds, msort = ref.NeRF.coarseFineMerge(go["rays"], go["z"], zs, bs)
+        out["merge_inds"], out["merge_sort"], out["merge_z2"] = minds, msort, mz
+        # the Ref branch of render_image on one 50x50 tile (procedures.py:71-74,80-90), normals and depth on
+        H = W = 50
+        pose, jitter, u, focal = render_case(H, W)
+        torch.rand = rq
+        rq.push(jitter.view(H, W, 64))
+        rq.push(u)
+        res = ref.procedures.render_image(rn, prop, pose, (H, W), focal, 2.0, 6.0, 128, white_bkg=True, render_depth=True, render_normal=True)
+        torch.rand = rq.real
+        out["ref_img_rgb"], out["ref_img_depth"], out["ref_img_normal"] = res["rgb"], res["depth_img"][0], res["normal_img"][0]
+
+    # (3) one training step of the non-Ref model: the run() closure of train.py:164-199 executed with the reference's own
+    # functions on injected draws, loss.backward(), gradient summaries of every parameter
+    import nerf.addtional as addtional
+    ti = train_inputs()
+    vs = ti["vs"]
+    prop = load_sd(ref.ProposalNetwork(10, 256), make_params("proposal", 1, "smooth"))
+    net = load_sd(ref.MipNeRF(10, 4, 256), make_params("nerf", 2, "smooth"))
+    real_randint = torch.randint
+    torch.randint = lambda *a, **k: ti["indices"].clone()
+    torch.rand = rq
+    rq.push(ti["jitter"])
+    coarse_samples, coarse_lengths, rgb_targets, coarse_cam_rays = ref.utils.validSampler(
+        vs["rgbs"], vs["coords"], vs["cam_tf"], ti["indices"].numel(), 64, vs["focal"], 2.0, 6.0, True)
+    torch.randint = real_randint
+    density = torch.nn.functional.softplus(prop.forward(coarse_samples))                                   # train.py:166,169
+    prop_weights_raw = ref.ProposalNetwork.get_weights(density, coarse_lengths, coarse_cam_rays[:, 3:])
+    prop_weights = ref.mip_methods.maxBlurFilter(prop_weights_raw, 0.01)
+    rq.push(ti["u"])
+    fine_lengths, below_idxs = ref.utils.inverseSample(prop_weights, coarse_lengths, 129, sort=True)
+    torch.rand = rq.real
+    fine_lengths = fine_lengths[..., :-1]
+    fine_samples = ref.NeRF.length2pts(coarse_cam_rays, fine_lengths)
+    fine_rgbo = net.forward(fine_samples)
+    fine_rendered, weights, _ = ref.NeRF.render(fine_rgbo, fine_lengths, coarse_cam_rays[:, 3:])
+    weight_bounds = addtional.getBounds(prop_weights, below_idxs)
+    img_loss = addtional.SoftL1Loss()(fine_rendered, rgb_targets)
+    prop_loss = addtional.ProposalLoss()(weight_bounds, weights.detach())
+    loss = prop_loss + img_loss
+    loss.backward()
+    out["train_loss"] = torch.stack((loss.detach(), img_loss.detach(), prop_loss.detach()))
+    out["train_rendered"], out["train_bounds"], out["train_weights"] = fine_rendered.detach(), weight_bounds.detach(), weights.detach()
+    for tag, m in (("prop", prop), ("nerf", net)):
+        for k, p_ in m.named_parameters():
+            gk = p_.grad.reshape(-1)
+            out[f"grad_{tag}_{k}"] = torch.cat((gk.norm().reshape(1), gk.sum().reshape(1), gk[:GRAD_HEAD]))
+
+    arrays = {}
+    for k, v in out.items():
+        v = v.detach().cpu()
+        arrays[k] = v.numpy().astype(np.int16) if v.dtype == torch.int64 else v.numpy()
+    path = os.path.join(HERE, "reference_outputs_round2.npz")
+    np.savez_compressed(path, **arrays)
+    print("wrote", path, os.path.getsize(path) // 1024, "KiB;", len(arrays), "arrays; torch", torch.__version__)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "refnerf":
         main_refnerf()
+    elif len(sys.argv) > 1 and sys.argv[1] == "round2":
+        main_round2()
     else:
         main()

@@ -40,6 +40,12 @@ def _worker(rank, world, port, n_rays, q):
         return O.render_rays(sp, sn, rays[start:start + count], base_z, jit, u, 2.0, 6.0, n_fine=32, white_bkg=True)["rgb"]
 
     img = sharding.render_image_sharded(render_rows, n_rays)
+    # the pre-allocated staging path bench.py uses (nothing allocated per step): same bits, twice in a row
+    start, count = sharding.shard_range(n_rays, rank, world)
+    buf = sharding.GatherBuffers(n_rays, 3, world, "cpu")
+    for _ in range(2):
+        again = sharding.gather_rows(img[start:start + count].contiguous(), n_rays, buffers=buf)
+        assert torch.equal(again, img)
     if rank == 0:
         q.put(img.clone())
     dist.barrier()

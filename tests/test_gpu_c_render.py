@@ -221,3 +221,36 @@ def test_reference_rng_mode_is_seed_reproducible():
     torch.manual_seed(3)
     b = nerf_b200.render_image(net, prop, pose, (H, W), focal, 2.0, 6.0, 128, rng="reference")["rgb"]
     assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("size", [(100, 100), (70, 100)])
+def test_reference_rng_mode_reproduces_the_seeded_reference_image(golden_round2, size):
+    """rng='reference' + the reference's torch.manual_seed -> the image the UNMODIFIED reference rendered with its own
+    CPU draws over several 50x50 tiles (tests/golden/make_golden.py round2), including the rows the reference leaves
+    unrendered when the height is not a whole number of tiles (nerf/procedures.py:24-31: width-only tile rule)."""
+    H, W = size
+    pose, _, _, _ = render_case(H, W)
+    focal = float(W / math.tan(0.5 * FOV))
+    net, prop = nets("smooth", "fp16x3")
+    torch.manual_seed(2024)
+    res = nerf_b200.render_image(net, prop, pose.to(DEV), (H, W), focal, 2.0, 6.0, 128, white_bkg=True, render_depth=True, rng="reference")
+    g_rgb, g_dep = golden_round2[f"seeded_rgb_{H}x{W}"], golden_round2[f"seeded_depth_{H}x{W}"]
+    He = nerf_b200.procedures.rendered_rows((H, W))
+    assert bool((res["rgb"][:, He:] == 0).all()) and bool((g_rgb[:, He:] == 0).all())
+    # the theorem on the same draws (replayed exactly as render_image does), then the image itself
+    torch.manual_seed(2024)
+    jit, u = nerf_b200.procedures._reference_rng_draws((H, W), 64, 129)
+    rays = ops.generate_rays(pose.to(DEV), H, W, focal, focal, n_rays=He * W)
+    base = torch.linspace(2.0, 6.0, 64, device=DEV)
+    eng = ops.render_rays(rays, base, 2.0, 6.0, 128, white_bkg=True, precision="fp16x3", jitter=jit.to(DEV), u=u.to(DEV), debug=True,
+                          **slots(net, prop))
+    assert torch.equal(res["rgb"][:, :He], eng["rgb"].view(He, W, 3).permute(2, 0, 1))
+    sp, sn = O.make_params("proposal", 1, "smooth"), O.make_params("nerf", 2, "smooth")
+    rep = render_parity_report(O, sp, sn, O.generate_rays(pose, H, W, focal)[:He * W], base.cpu(), jit, u, 2.0, 6.0,
+                               {k: v.cpu() for k, v in eng.items() if torch.is_tensor(v)})
+    print(size, rep)
+    assert_render_parity(rep, label=f"seeded {H}x{W}")
+    err = (res["rgb"].cpu() - g_rgb).abs().amax(0)
+    derr = (res["depth_img"][0].cpu() - g_dep).abs()
+    print("vs the reference's seeded image: max rgb err", float(err.max()), "frac > 1e-4", float((err > 1e-4).float().mean()))
+    assert float(((err > 1e-4) | (derr > 1e-4)).float().mean()) <= 0.01 and psnr(res["rgb"].cpu(), g_rgb) > 85.0

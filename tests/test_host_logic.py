@@ -14,6 +14,25 @@ def test_get_patch_size_and_64x64():
     assert procedures.get_patch_size((120, 120)) == (40, (3, 3))
     # the reference raises UnboundLocalError here (nerf/procedures.py:24-31); the engine renders one tile
     assert procedures.get_patch_size((64, 64)) == (None, (1, 1))
+    # width-only rule, like the reference: the height is truncated to whole tiles (rows past it are never rendered)
+    assert procedures.get_patch_size((70, 100)) == (50, (1, 2)) and procedures.rendered_rows((70, 100)) == 50
+    assert procedures.get_patch_size((420, 400)) == (50, (8, 8)) and procedures.rendered_rows((420, 400)) == 400
+    assert procedures.get_patch_size((30, 100)) == (50, (0, 2)) and procedures.rendered_rows((30, 100)) == 0
+    assert procedures.get_patch_size((100, 80)) == (40, (2, 2))
+    assert procedures.rendered_rows((64, 64)) == 64
+
+
+def test_reference_rng_replay_truncated_rows():
+    """70x100: the reference draws for the two 50x50 tiles of the first tile row only."""
+    torch.manual_seed(9)
+    jit, u = procedures._reference_rng_draws((70, 100), 64, 129)
+    assert jit.shape == (50 * 100, 64) and u.shape == (50 * 100, 129)
+    torch.manual_seed(9)
+    for j in range(2):
+        a = torch.rand((50, 50, 64))
+        b = torch.rand([2500, 129])
+        assert torch.equal(jit.view(50, 100, 64)[:, 50 * j:50 * (j + 1)], a)
+        assert torch.equal(u.view(50, 100, 129)[:, 50 * j:50 * (j + 1)], b.view(50, 50, 129))
 
 
 def test_reference_rng_replay_order():
