@@ -228,7 +228,7 @@ def parity_leg(dev, pose, H, W, focal, base_z, ids, precisions):
                      "psnr_vs_reference_db": (99.0 if mse == 0 else -10.0 * math.log10(mse)),
                      "psnr_delta_db_at_30dB_gt": psnr(got["rgb"]) - psnr(ref["rgb"])}
         if mode in ("fp16x3", "bf16x3", "fp32"):
-            par[mode]["theorem"] = render_parity_report(O, sp, sn, rays, base_z, jit, u, NEAR, FAR, got)
+            par[mode]["theorem"] = render_parity_report(O, sp, sn, rays, base_z, jit, u, NEAR, FAR, got, dep_tol=1e-4 if mode == "fp32" else 1.5e-4)
     return par
 
 

@@ -1,0 +1,468 @@
+// nb2_gemm.cu — the layer-wise engine: one generic tcgen05 GEMM behind nb2_gemm_bf16.
+//
+//   D[M, N] = epilogue( sum over segments s of  A_s[M, K_s] * B_s[N, K_s]^T ),   bf16 operands, fp32 accumulation in TMEM
+//
+// It is what the TRAINING step and the Ref-NeRF forward (8f-3) are built from: every nn.Linear forward,
+// its dgrad and its wgrad are instances of it, with the matrices left in their natural row-major layouts:
+//   forward   Y  = X  W^T         A = X  [rows][in]   K-major      B = W  [out][in]  K-major
+//   dgrad     dX = dY W           A = dY [rows][out]  K-major      B = W  [out][in]  MN-major (its N = `in` is contiguous)
+//   wgrad     dW = dY^T X         A = dY [rows][out]  MN-major     B = X  [rows][in] MN-major, split-K over CTAs
+// "MN-major" is the tcgen05 name for an operand whose non-contracted dimension is contiguous; the tensor core transposes
+// it for free through the matrix descriptor (a_major / b_major bits of the instruction descriptor), so no transposed
+// copies of activations or weights exist anywhere.  Segments concatenate along K: the three passes of the split
+// precision (lo x hi, hi x lo, hi x hi; small terms first) and the reference's torch.cat inputs
+// (skip connection, bottleneck + encoded direction) are just more segments accumulating into the same tile.
+//
+// Kernel (persistent, one CTA per SM, cta_group::1, 128 x BN output tile, K chunks of 64):
+//   warps 0-3   epilogue: TMEM accumulator (two buffers, so tile i+1 accumulates while tile i drains) -> bias / act /
+//               relu-mask -> bf16 hi (+ lo residual) and / or fp32 rows, 64-128 B contiguous per thread
+//   warps 4-7   producers: 16-byte cp.async copies of row-major global blocks into the 128-byte-swizzled shared-memory
+//               layout both operand kinds share ([rows][64 elements], 16-byte unit index XOR (row & 7)); bounds are
+//               zero-filled; a stage is published to the async proxy (fence.proxy.async) two stages behind the issue
+//   warp 8      TMEM allocation + MMA issue (tcgen05.mma.kind::f16, M128 x BN x K16), tcgen05.commit frees stages
+// The kernel is HBM-bound for the network's 256-wide layers (a 128 x 256 tile reads 64 KB and writes 64-128 KB for
+// 2048 tensor cycles); its roofline is the measured copy bandwidth, DESIGN.md section 12.
+#include "nb2_common.cuh"
+#include "nb2_tc_ptx.cuh"
+
+namespace nb2 {
+using namespace ptx;
+
+constexpr int kGStages = 4;
+constexpr int kGLag = 2;                    // a stage is published kGLag issues after its copies were started
+constexpr int kGABytes = 128 * 128;         // A operand stage: 128 rows x 64 bf16 (K-major) or 2 blocks of 64 x 64 (MN-major)
+constexpr int kGBBytes = 256 * 128;         // B operand stage: up to 256 rows (K-major) or 4 blocks of 64 x 64 (MN-major)
+constexpr int kGStageBytes = kGABytes + kGBBytes;
+constexpr int kGThreads = 288;
+constexpr int kGSmem = kGStages * kGStageBytes + 1024 /* barriers */ + 1024 /* alignment slack */;
+
+struct GemmBars {
+  uint64_t full[kGStages];
+  uint64_t empty[kGStages];
+  uint64_t acc_full[2];
+  uint64_t acc_empty[2];
+  uint32_t tmem_base;
+};
+
+struct GemmKParams {
+  nb2_gemm_desc d;
+  int bn;                 // N tile (multiple of 32, <= 256)
+  int m_tiles, n_tiles;
+  int64_t k_per_split;    // rows of K per split (multiple of 64); splits == 1: unused
+};
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
+  const uint32_t sz = valid ? 16u : 0u;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// D (128 x N, fp32, TMEM) (+)= A (smem) * B^T (smem), single CTA
+__device__ __forceinline__ void umma1_elect(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma1_commit_elect(uint32_t bar) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+      ::"r"(bar)
+      : "memory");
+}
+// shared-memory matrix descriptor, 128-byte swizzle.  K-major: LBO unused, SBO = 1024 (8 rows x 128 B).
+// MN-major: atoms of 64 MN-elements x 8 k-rows; SBO = 1024 (next 8 k-rows), LBO = 8192 (next 64 MN-elements: one
+// [64 k-rows][128 B] block per 64 MN-elements).  Field layout: cute::UMMA::SmemDescriptor.
+__device__ __forceinline__ uint64_t gemm_smem_desc(uint32_t saddr, bool mn_major) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(mn_major ? (8192u >> 4) : 1u) << 16;
+  d |= (uint64_t)(1024u >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__device__ __forceinline__ uint32_t gemm_idesc(int N, bool a_mn, bool b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(128 >> 4) << 24);
+}
+
+// Copy `rows` x 64 bf16 of a row-major matrix (element (r, c) at ptr[r * ld + c]) starting at (row0, col0) into a
+// [rows][128 B] shared-memory block with the 128-byte swizzle; rows >= row_lim / columns >= col_lim are zero-filled.
+__device__ __forceinline__ void load_block(uint32_t dst, const __nv_bfloat16* __restrict__ ptr, int64_t ld, int64_t row0, int rows,
+                                           int64_t row_lim, int64_t col0, int64_t col_lim, int tid) {
+  for (int c = tid; c < rows * 8; c += 128) {
+    const int r = c >> 3, ch = c & 7;
+    const int64_t gr = row0 + r, gc = col0 + 8 * ch;
+    const bool ok = (gr < row_lim) && (gc < col_lim);
+    const __nv_bfloat16* src = ok ? ptr + gr * ld + gc : ptr;
+    cp_async16(dst + (uint32_t)r * 128u + (uint32_t)((ch ^ (r & 7)) << 4), src, ok);
+  }
+}
+
+__global__ void __launch_bounds__(kGThreads, 1) gemm_bf16_kernel(const __grid_constant__ GemmKParams p) {
+  extern __shared__ unsigned char smem_dyn[];
+  const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+  unsigned char* smem_al = smem_dyn + (smem_base - smem_u32(smem_dyn));
+  GemmBars* bars = reinterpret_cast<GemmBars*>(smem_al + kGStages * kGStageBytes);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const nb2_gemm_desc& d = p.d;
+  const int splits = d.splits > 1 ? d.splits : 1;
+  const int64_t n_items = (int64_t)p.m_tiles * p.n_tiles * splits;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kGStages; ++i) {
+      mbar_init(smem_u32(&bars->full[i]), 4);      // one arrival per producer warp
+      mbar_init(smem_u32(&bars->empty[i]), 1);     // tcgen05.commit
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&bars->acc_full[i]), 1);
+      mbar_init(smem_u32(&bars->acc_empty[i]), 4); // one arrival per epilogue warp
+    }
+    mbar_fence_init();
+  }
+  if (warp == 8) {
+    tmem_alloc(smem_u32(&bars->tmem_base), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  // the K range of one work item inside segment s (split-K shares the range across the segments)
+  auto k_range = [&](int s, int split, int64_t& k0, int64_t& k1) {
+    k0 = 0;
+    k1 = d.seg[s].K;
+    if (splits > 1) {
+      k0 = (int64_t)split * p.k_per_split;
+      k1 = k0 + p.k_per_split < d.seg[s].K ? k0 + p.k_per_split : d.seg[s].K;
+      if (k0 > k1) k0 = k1;
+    }
+  };
+
+  if (warp >= 4 && warp < 8) {
+    // =========================================== producers ===========================================
+    const int tid = threadIdx.x - 128;
+    uint32_t issued = 0, published = 0;
+    auto publish = [&]() {
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bars->full[published % kGStages]));
+      ++published;
+    };
+    for (int64_t it = blockIdx.x; it < n_items; it += gridDim.x) {
+      const int m_tile = (int)(it % p.m_tiles);
+      const int n_tile = (int)((it / p.m_tiles) % p.n_tiles);
+      const int split = (int)(it / ((int64_t)p.m_tiles * p.n_tiles));
+      const int64_t m0 = (int64_t)m_tile * 128, n0 = (int64_t)n_tile * p.bn;
+      for (int s = 0; s < d.n_seg; ++s) {
+        const nb2_gemm_operand& A = d.seg[s].a;
+        const nb2_gemm_operand& B = d.seg[s].b;
+        int64_t k0, k1;
+        k_range(s, split, k0, k1);
+        for (int64_t k = k0; k < k1; k += 64) {
+          const uint32_t stage = issued % kGStages;
+          if (issued >= kGStages) mbar_wait(smem_u32(&bars->empty[stage]), ((issued / kGStages) - 1) & 1u);
+          const uint32_t a_dst = smem_base + stage * kGStageBytes, b_dst = a_dst + kGABytes;
+          const __nv_bfloat16* ap = reinterpret_cast<const __nv_bfloat16*>(A.ptr);
+          const __nv_bfloat16* bp = reinterpret_cast<const __nv_bfloat16*>(B.ptr);
+          if (!A.mn_major) {
+            load_block(a_dst, ap, A.ld, m0, 128, d.M, k, k1, tid);
+          } else {
+            for (int j = 0; j < 2; ++j) load_block(a_dst + j * 8192, ap, A.ld, k, 64, k1, m0 + 64 * j, d.M, tid);
+          }
+          if (!B.mn_major) {
+            load_block(b_dst, bp, B.ld, n0, p.bn, d.N, k, k1, tid);
+          } else {
+            for (int j = 0; j < (p.bn + 63) / 64; ++j) load_block(b_dst + j * 8192, bp, B.ld, k, 64, k1, n0 + 64 * j, d.N, tid);
+          }
+          cp_async_commit();
+          ++issued;
+          if (issued - published > kGLag) {
+            cp_async_wait<kGLag>();
+            publish();
+          }
+        }
+      }
+    }
+    cp_async_wait<0>();
+    while (published < issued) publish();
+  } else if (warp == 8) {
+    // =========================================== MMA issuer (whole warp, one elected lane per instruction) ===========
+    uint32_t consumed = 0, item = 0;
+    for (int64_t it = blockIdx.x; it < n_items; it += gridDim.x, ++item) {
+      const int split = (int)(it / ((int64_t)p.m_tiles * p.n_tiles));
+      const uint32_t buf = item & 1u;
+      if (item >= 2) mbar_wait(smem_u32(&bars->acc_empty[buf]), ((item >> 1) - 1) & 1u);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + buf * 256;
+      bool first = true;
+      for (int s = 0; s < d.n_seg; ++s) {
+        const bool a_mn = d.seg[s].a.mn_major != 0, b_mn = d.seg[s].b.mn_major != 0;
+        const uint32_t idesc = gemm_idesc(p.bn, a_mn, b_mn);
+        int64_t k0, k1;
+        k_range(s, split, k0, k1);
+        for (int64_t k = k0; k < k1; k += 64) {
+          const uint32_t stage = consumed % kGStages;
+          mbar_wait(smem_u32(&bars->full[stage]), (consumed / kGStages) & 1u);
+          tc_fence_after();
+          const uint32_t a_s = smem_base + stage * kGStageBytes, b_s = a_s + kGABytes;
+          const int ksteps = (int)((k1 - k + 15) / 16 < 4 ? (k1 - k + 15) / 16 : 4);
+          for (int ks = 0; ks < ksteps; ++ks) {
+            const uint64_t ad = gemm_smem_desc(a_s + (a_mn ? ks * 2048 : ks * 32), a_mn);
+            const uint64_t bd = gemm_smem_desc(b_s + (b_mn ? ks * 2048 : ks * 32), b_mn);
+            umma1_elect(tmem_d, ad, bd, idesc, first ? 0u : 1u);
+            first = false;
+          }
+          umma1_commit_elect(smem_u32(&bars->empty[stage]));
+          ++consumed;
+        }
+      }
+      umma1_commit_elect(smem_u32(&bars->acc_full[buf]));
+    }
+  } else {
+    // =========================================== epilogue ============================================================
+    uint32_t item = 0;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    for (int64_t it = blockIdx.x; it < n_items; it += gridDim.x, ++item) {
+      const int m_tile = (int)(it % p.m_tiles);
+      const int n_tile = (int)((it / p.m_tiles) % p.n_tiles);
+      const int split = (int)(it / ((int64_t)p.m_tiles * p.n_tiles));
+      const uint32_t buf = item & 1u;
+      const int64_t row = (int64_t)m_tile * 128 + warp * 32 + lane;
+      const int64_t n0 = (int64_t)n_tile * p.bn;
+      // a work item whose K range is empty issued no MMA: its accumulator is undefined -> contributes zeros
+      bool empty_k = true;
+      for (int s = 0; s < d.n_seg; ++s) {
+        int64_t k0, k1;
+        k_range(s, split, k0, k1);
+        if (k1 > k0) empty_k = false;
+      }
+      mbar_wait(smem_u32(&bars->acc_full[buf]), (item >> 1) & 1u);
+      __syncwarp();
+      tc_fence_after();
+      float* out32 = d.out_f32 ? d.out_f32 + (int64_t)split * d.split_stride : nullptr;
+      for (int cb = 0; cb < p.bn / 32; ++cb) {
+        uint32_t r[32];
+        tmem_ld32(lane_addr + buf * 256 + cb * 32, r);
+        tmem_ld_wait();
+        const int64_t c0 = n0 + cb * 32;
+        if (row < d.M && c0 < d.N) {
+          const int nv = (int)(d.N - c0 < 32 ? d.N - c0 : 32);
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float x = empty_k ? 0.f : __uint_as_float(r[j]);
+            if (d.bias != nullptr && j < nv) x += __ldg(d.bias + c0 + j);
+            if (d.act == 1) x = fmaxf(x, 0.f);
+            else if (d.act == 2) x = 1.f / (1.f + expf(-x));
+            v[j] = x;
+          }
+          if (d.mask != nullptr) {
+            const __nv_bfloat16* mrow = reinterpret_cast<const __nv_bfloat16*>(d.mask) + row * d.ld_mask + c0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < nv && !(__bfloat162float(mrow[j]) > 0.f)) v[j] = 0.f;
+          }
+          if (out32 != nullptr) {
+            float* o = out32 + row * d.ld_f32 + c0;
+            if (nv == 32 && (d.ld_f32 & 3) == 0 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) reinterpret_cast<float4*>(o)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < nv) o[j] = v[j];
+            }
+          }
+          if (d.out_hi != nullptr) {
+            __nv_bfloat16* oh = reinterpret_cast<__nv_bfloat16*>(d.out_hi) + row * d.ld_16 + c0;
+            __nv_bfloat16* ol = d.out_lo ? reinterpret_cast<__nv_bfloat16*>(d.out_lo) + row * d.ld_16 + c0 : nullptr;
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              hi[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+              lo[j] = pack_bf16x2(v[2 * j] - bf16_lo_to_f32(hi[j]), v[2 * j + 1] - bf16_hi_to_f32(hi[j]));
+            }
+            if (nv == 32 && (d.ld_16 & 7) == 0 && ((reinterpret_cast<uintptr_t>(oh) & 15) == 0)) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) reinterpret_cast<uint4*>(oh)[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+              if (ol != nullptr) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) reinterpret_cast<uint4*>(ol)[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < nv) {
+                  const uint32_t hw = (j & 1) ? (hi[j >> 1] >> 16) : (hi[j >> 1] & 0xFFFFu);
+                  reinterpret_cast<unsigned short*>(oh)[j] = (unsigned short)hw;
+                  if (ol != nullptr) {
+                    const uint32_t lw = (j & 1) ? (lo[j >> 1] >> 16) : (lo[j >> 1] & 0xFFFFu);
+                    reinterpret_cast<unsigned short*>(ol)[j] = (unsigned short)lw;
+                  }
+                }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bars->acc_empty[buf]));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---- small companions of the layer-wise engine ------------------------------------------------------------------------
+// fp32 (rows x cols, row stride ld_src) -> bf16 hi (+ lo residual) with row stride ld_dst >= cols (multiple of 8); the
+// pad columns [cols, ld_dst) are zeroed.  col_perm (optional, cols entries): destination column of source column c --
+// how a weight matrix that multiplies a torch.cat input is stored in the column order of the engine's buffers.
+__global__ void to_bf16_kernel(const float* __restrict__ src, int64_t rows, int cols, int64_t ld_src, const int* __restrict__ col_perm,
+                               __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int ld_dst) {
+  const int64_t n = rows * ld_dst;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / ld_dst;
+    const int c = (int)(i - r * ld_dst);
+    if (c >= cols) {
+      if (col_perm == nullptr) {     // with a permutation the pad columns are whatever the permutation leaves unassigned
+        hi[i] = __float2bfloat16_rn(0.f);
+        if (lo) lo[i] = __float2bfloat16_rn(0.f);
+      }
+      continue;
+    }
+    const float v = src[r * ld_src + c];
+    const int64_t o = col_perm ? r * ld_dst + col_perm[c] : i;
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    hi[o] = h;
+    if (lo) lo[o] = __float2bfloat16_rn(v - __bfloat162float(h));
+  }
+}
+
+// out[m][c] (fp32, row stride ld_out, c < cols) = sum over splits of ws[s][m][perm(c)] (row stride ld_ws): the
+// deterministic second stage of the split-K wgrad (no atomics: gradients are bit-reproducible run to run).
+__global__ void reduce_splits_kernel(const float* __restrict__ ws, int splits, int64_t split_stride, int rows, int cols, int ld_ws,
+                                     const int* __restrict__ col_perm, float* __restrict__ out, int ld_out, int accumulate) {
+  const int64_t n = (int64_t)rows * cols;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int m = (int)(i / cols), c = (int)(i - (int64_t)m * cols);
+    const int wc = col_perm ? col_perm[c] : c;
+    float acc = 0.f;
+    for (int s = 0; s < splits; ++s) acc += ws[(int64_t)s * split_stride + (int64_t)m * ld_ws + wc];
+    float* o = out + (int64_t)m * ld_out + c;
+    *o = accumulate ? *o + acc : acc;
+  }
+}
+
+// out[c] = sum over rows of (hi[r][c] + lo[r][c]) : the bias gradient.  One block per 32 columns, fp32 tree per block.
+__global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo, int64_t rows,
+                                                     int cols, int ld, float* __restrict__ out, int accumulate) {
+  __shared__ float part[8][32];
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int w = threadIdx.x >> 5;
+  float acc = 0.f;
+  if (c < cols)
+    for (int64_t r = w; r < rows; r += 8) {
+      acc += __bfloat162float(hi[r * ld + c]);
+      if (lo) acc += __bfloat162float(lo[r * ld + c]);
+    }
+  part[w][threadIdx.x & 31] = acc;
+  __syncthreads();
+  if (w == 0 && c < cols) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += part[k][threadIdx.x];
+    out[c] = accumulate ? out[c] + s : s;
+  }
+}
+
+}  // namespace nb2
+
+using namespace nb2;
+
+extern "C" int nb2_gemm_bf16(nb2_handle* h, const nb2_gemm_desc* d, void* stream) {
+  NB2_ENTER(h);
+  NB2_CHECK_ARG(d != nullptr, "gemm: null descriptor");
+  if (d->M == 0 || d->N == 0) return NB2_OK;
+  NB2_CHECK_ARG(d->M > 0 && d->N > 0 && d->n_seg >= 1 && d->n_seg <= NB2_GEMM_MAX_SEG, "gemm: bad shape / segment count");
+  NB2_CHECK_ARG(d->out_f32 || d->out_hi, "gemm: no output");
+  NB2_CHECK_ARG(!d->out_lo || d->out_hi, "gemm: out_lo needs out_hi");
+  const int splits = d->splits > 1 ? d->splits : 1;
+  for (int s = 0; s < d->n_seg; ++s) {
+    const nb2_gemm_operand& A = d->seg[s].a;
+    const nb2_gemm_operand& B = d->seg[s].b;
+    NB2_CHECK_ARG(A.ptr && B.ptr && d->seg[s].K > 0, "gemm: segment %d has a null operand or K <= 0", s);
+    NB2_CHECK_ARG((A.ld & 7) == 0 && (B.ld & 7) == 0, "gemm: leading dimensions must be multiples of 8 elements (16-byte rows)");
+    NB2_CHECK_ARG(((uintptr_t)A.ptr & 15) == 0 && ((uintptr_t)B.ptr & 15) == 0, "gemm: operands must be 16-byte aligned");
+    // 16-byte units must be wholly inside or outside the valid extent of the contiguous dimension
+    NB2_CHECK_ARG(A.mn_major ? (d->M & 7) == 0 || A.ld >= ((d->M + 7) & ~7LL) : (d->seg[s].K & 7) == 0 || A.ld >= ((d->seg[s].K + 7) & ~7LL),
+                  "gemm: segment %d: A rows must be padded to a multiple of 8 elements", s);
+    NB2_CHECK_ARG(B.mn_major ? (d->N & 7) == 0 || B.ld >= ((d->N + 7) & ~7) : (d->seg[s].K & 7) == 0 || B.ld >= ((d->seg[s].K + 7) & ~7LL),
+                  "gemm: segment %d: B rows must be padded to a multiple of 8 elements", s);
+    if (splits > 1) NB2_CHECK_ARG(d->seg[s].K == d->seg[0].K, "gemm: split-K needs the same K in every segment");
+  }
+  NB2_CHECK_ARG(splits == 1 || (d->out_f32 && !d->out_hi && !d->bias && d->act == 0 && !d->mask),
+                "gemm: split-K writes plain fp32 partial sums (no bias / activation / mask / 16-bit output)");
+  GemmKParams p;
+  p.d = *d;
+  const int n_pad = (d->N + 31) / 32 * 32;
+  p.bn = n_pad <= 256 ? n_pad : 256;
+  // wide outputs: balance the N tiles (e.g. N = 320 -> 2 x 160) so no tile is mostly padding
+  p.n_tiles = (n_pad + 255) / 256;
+  if (p.n_tiles > 1) p.bn = ((n_pad / 32 + p.n_tiles - 1) / p.n_tiles) * 32;
+  p.m_tiles = (int)((d->M + 127) / 128);
+  p.k_per_split = 0;
+  if (splits > 1) p.k_per_split = ((d->seg[0].K + splits - 1) / splits + 63) / 64 * 64;
+  int rc = kernel_set_smem(h, (const void*)gemm_bf16_kernel, kGSmem);
+  if (rc != NB2_OK) return rc;
+  const int64_t items = (int64_t)p.m_tiles * p.n_tiles * splits;
+  const int grid = (int)std::min<int64_t>(items, h->sm_count);
+  gemm_bf16_kernel<<<grid, kGThreads, kGSmem, (cudaStream_t)stream>>>(p);
+  NB2_LAUNCH_CHECK(h);
+  return NB2_OK;
+}
+
+extern "C" int nb2_to_bf16(nb2_handle* h, const float* src, int64_t rows, int cols, int64_t ld_src, const int* col_perm, void* hi, void* lo,
+                           int ld_dst, void* stream) {
+  NB2_ENTER(h);
+  if (rows == 0) return NB2_OK;
+  NB2_CHECK_ARG(src && hi && rows > 0 && cols > 0 && ld_dst >= cols && (ld_dst & 7) == 0 && ld_src >= cols, "to_bf16: bad arguments");
+  const int64_t n = rows * ld_dst;
+  const int blocks = (int)std::min<int64_t>((n + 255) / 256, (int64_t)h->sm_count * 16);
+  to_bf16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, rows, cols, ld_src, col_perm, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, ld_dst);
+  NB2_LAUNCH_CHECK(h);
+  return NB2_OK;
+}
+
+extern "C" int nb2_reduce_splits(nb2_handle* h, const float* ws, int splits, int64_t split_stride, int rows, int cols, int ld_ws,
+                                 const int* col_perm, float* out, int ld_out, int accumulate, void* stream) {
+  NB2_ENTER(h);
+  NB2_CHECK_ARG(ws && out && splits >= 1 && rows > 0 && cols > 0 && ld_ws > 0 && ld_out >= cols, "reduce_splits: bad arguments");
+  const int64_t n = (int64_t)rows * cols;
+  const int blocks = (int)std::min<int64_t>((n + 255) / 256, (int64_t)h->sm_count * 8);
+  reduce_splits_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(ws, splits, split_stride, rows, cols, ld_ws, col_perm, out, ld_out, accumulate);
+  NB2_LAUNCH_CHECK(h);
+  return NB2_OK;
+}
+
+extern "C" int nb2_colsum_bf16(nb2_handle* h, const void* hi, const void* lo, int64_t rows, int cols, int ld, float* out, int accumulate,
+                               void* stream) {
+  NB2_ENTER(h);
+  NB2_CHECK_ARG(hi && out && rows >= 0 && cols > 0 && ld >= cols, "colsum: bad arguments");
+  colsum_kernel<<<(cols + 31) / 32, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)hi, (const __nv_bfloat16*)lo, rows, cols, ld, out, accumulate);
+  NB2_LAUNCH_CHECK(h);
+  return NB2_OK;
+}

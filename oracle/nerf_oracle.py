@@ -253,12 +253,13 @@ def render_rays(sd_prop, sd_nerf, rays, base_z, jitter, u, near, far, n_fine=128
                 blur_alpha=0.01, softplus=False, pos_levels=10, dir_levels=4, torch_sum=False, chunk=4096):
     """rays (R,6), jitter (R,Pc), u (R,n_fine+1) -> dict with every intermediate the tests compare."""
     resolution = (far - near) / n_fine if resolution is None else resolution
-    outs = {k: [] for k in ("rgb", "depth", "acc", "z_coarse", "sigma_prop", "z_fine", "below", "weights", "rgbo")}
+    outs = {k: [] for k in ("rgb", "depth", "acc", "z_coarse", "sigma_prop", "sigma_prop_raw", "z_fine", "below", "weights", "rgbo")}
     for s in range(0, rays.shape[0], chunk):
         r, j, uu = rays[s:s + chunk], jitter[s:s + chunk], u[s:s + chunk]
         z_c = base_z + j * resolution                                             # :65
         pts = r[:, None, :3] + z_c[..., None] * r[:, None, 3:]                    # :66
         sigma_p = proposal_forward(sd_prop, pts, pos_levels)                      # :67
+        sigma_raw = sigma_p
         if softplus:
             sigma_p = F.softplus(sigma_p)                                         # train.py:169
         w_p = max_blur(weights_from_sigma(sigma_p, z_c, r[:, 3:]), blur_alpha)    # :68-69
@@ -267,7 +268,7 @@ def render_rays(sd_prop, sd_nerf, rays, base_z, jitter, u, near, far, n_fine=128
         rgbo = nerf_forward(sd_nerf, length2pts(r, z_keep), pos_levels, dir_levels)  # :77-78
         comp = composite(rgbo, z_keep, r[:, 3:], white_bkg, (near, far))          # :80-85
         for k, v in (("rgb", comp["rgb"]), ("depth", comp["depth"]), ("acc", comp["acc"]), ("z_coarse", z_c),
-                     ("sigma_prop", sigma_p), ("z_fine", z_keep), ("below", below), ("weights", comp["weights"]),
+                     ("sigma_prop", sigma_p), ("sigma_prop_raw", sigma_raw), ("z_fine", z_keep), ("below", below), ("weights", comp["weights"]),
                      ("rgbo", rgbo)):
             outs[k].append(v)
     return {k: torch.cat(v, dim=0) for k, v in outs.items()}

@@ -32,7 +32,7 @@ def standin(H, W, perturb):
 def test_theorem_holds_for_an_ulp_level_perturbation():
     rep = standin(32, 32, 0.0)
     assert rep["B_rays"] > 0                      # flips do happen at this perturbation size ...
-    assert_render_parity(rep, max_over_frac=0.02)  # ... and every one of them is within the reference's own bound
+    assert_render_parity(rep, max_over_frac=0.02, max_flip_frac=0.05)  # ... and every one of them is within the reference's own bound
 
 
 def test_theorem_rejects_a_real_regression():
