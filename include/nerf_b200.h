@@ -234,6 +234,58 @@ int nb2_render_rays(nb2_handle* h, const nb2_render_params* p, const float* rays
                     float* sigma_prop_out, float* z_fine_out, int64_t* below_fine_out, void* workspace,
                     int64_t workspace_bytes, void* stream);
 
+/* ---- the layer-wise engine: training step and Ref-NeRF (8f-3) ----------------------------------------
+ * One generic tensor-core GEMM on bf16 operands with fp32 accumulation:
+ *     D[M, N] = epilogue( sum over segments s of  A_s[M, K_s] * B_s[N, K_s]^T )
+ * Operands stay in their natural row-major layouts; `mn_major` = 0: element (i, k) at ptr[i * ld + k] (K contiguous);
+ * `mn_major` = 1: element (i, k) at ptr[k * ld + i] (the M / N index contiguous: a transposed view, free on tcgen05).
+ *   nn.Linear forward   Y  = X W^T     A = X (0), B = W (0)            reference: every F.linear of nerf/mip_model.py:53-59,
+ *   its dgrad           dX = dY W      A = dY (0), B = W (1)                      nerf/addtional.py:92-96, nerf/ref_model.py:76-105
+ *   its wgrad           dW = dY^T X    A = dY (1), B = X (1), splits > 1          (autograd's addmm backward in train.py:206)
+ * Segments concatenate along K: the passes of the split precision (x = hi + lo: lo*hi, hi*lo, hi*hi) and torch.cat inputs.
+ * Epilogue: + bias[n]; act 0 none | 1 relu | 2 sigmoid; * (mask[m][n] > 0) (relu backward on a saved activation);
+ * outputs fp32 (ld_f32) and / or bf16 hi (+ lo residual) (ld_16).  splits > 1: split-K over M-tile x N-tile x split work
+ * items, partial sums written to out_f32 + split * split_stride (reduce with nb2_reduce_splits: deterministic, no atomics).
+ * All ld multiples of 8 elements, pointers 16-byte aligned, contiguous dimensions zero-padded to multiples of 8. */
+#define NB2_GEMM_MAX_SEG 8
+typedef struct nb2_gemm_operand {
+  const void* ptr; /* bf16 */
+  int64_t ld;
+  int mn_major;
+  int reserved;
+} nb2_gemm_operand;
+typedef struct nb2_gemm_desc {
+  int64_t M;
+  int N;
+  int n_seg;
+  struct {
+    nb2_gemm_operand a, b;
+    int64_t K;
+  } seg[NB2_GEMM_MAX_SEG];
+  const float* bias;
+  int act;
+  int ld_mask;
+  const void* mask; /* bf16 (M, ld_mask) */
+  float* out_f32;
+  void* out_hi;     /* bf16 */
+  void* out_lo;     /* bf16 */
+  int64_t ld_f32, ld_16;
+  int splits;
+  int reserved;
+  int64_t split_stride; /* floats */
+} nb2_gemm_desc;
+int nb2_gemm_bf16(nb2_handle* h, const nb2_gemm_desc* d, void* stream);
+/* fp32 (rows, cols; row stride ld_src) -> bf16 hi (+ lo residual or NULL), row stride ld_dst (multiple of 8, pad zeroed);
+ * col_perm (device, cols ints, or NULL): destination column of every source column. */
+int nb2_to_bf16(nb2_handle* h, const float* src, int64_t rows, int cols, int64_t ld_src, const int* col_perm, void* hi, void* lo,
+                int ld_dst, void* stream);
+/* out[m][c] (=|+=) sum_s ws[s * split_stride + m * ld_ws + perm(c)]: second stage of the split-K wgrad. */
+int nb2_reduce_splits(nb2_handle* h, const float* ws, int splits, int64_t split_stride, int rows, int cols, int ld_ws,
+                      const int* col_perm, float* out, int ld_out, int accumulate, void* stream);
+/* out[c] (=|+=) sum over rows of hi[r][c] (+ lo[r][c]): bias gradients. */
+int nb2_colsum_bf16(nb2_handle* h, const void* hi, const void* lo, int64_t rows, int cols, int ld, float* out, int accumulate,
+                    void* stream);
+
 /* ---- peer memory for the fused gather (one process per GPU, CUDA IPC over NVLink / NVSwitch) -----------------
  * nb2_ipc_alloc: cudaMalloc `bytes` on the handle's device and export a 64-byte IPC handle for it.
  * nb2_ipc_open : map another process's allocation into this process (peer access is enabled on demand).

@@ -41,6 +41,30 @@ class RenderParams(ctypes.Structure):
     ]
 
 
+class GemmOperand(ctypes.Structure):
+    """Mirror of nb2_gemm_operand."""
+    _fields_ = [("ptr", c_vp), ("ld", c_i64), ("mn_major", c_int), ("reserved", c_int)]
+
+
+class GemmSeg(ctypes.Structure):
+    _fields_ = [("a", GemmOperand), ("b", GemmOperand), ("K", c_i64)]
+
+
+GEMM_MAX_SEG = 8
+
+
+class GemmDesc(ctypes.Structure):
+    """Mirror of nb2_gemm_desc."""
+    _fields_ = [
+        ("M", c_i64), ("N", c_int), ("n_seg", c_int),
+        ("seg", GemmSeg * GEMM_MAX_SEG),
+        ("bias", c_vp), ("act", c_int), ("ld_mask", c_int), ("mask", c_vp),
+        ("out_f32", c_vp), ("out_hi", c_vp), ("out_lo", c_vp),
+        ("ld_f32", c_i64), ("ld_16", c_i64),
+        ("splits", c_int), ("reserved", c_int), ("split_stride", c_i64),
+    ]
+
+
 # name -> (restype, argtypes).  Every symbol include/nerf_b200.h declares is listed here; the
 # CPU test-suite checks the library exports all of them.
 SIGNATURES = {
@@ -52,6 +76,10 @@ SIGNATURES = {
     "nb2_weights_version": (c_int, [c_vp, c_int]),
     "nb2_net_create": (c_int, [c_vp, c_int, ctypes.POINTER(c_int)]),
     "nb2_net_destroy": (c_int, [c_vp, c_int]),
+    "nb2_gemm_bf16": (c_int, [c_vp, ctypes.POINTER(GemmDesc), c_vp]),
+    "nb2_to_bf16": (c_int, [c_vp, c_f32p, c_i64, c_int, c_i64, c_vp, c_vp, c_vp, c_int, c_vp]),
+    "nb2_reduce_splits": (c_int, [c_vp, c_f32p, c_int, c_i64, c_int, c_int, c_int, c_vp, c_f32p, c_int, c_int, c_vp]),
+    "nb2_colsum_bf16": (c_int, [c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_f32p, c_int, c_vp]),
     "nb2_ipc_alloc": (c_int, [c_vp, c_i64, ctypes.POINTER(c_vp), c_vp]),
     "nb2_ipc_open": (c_int, [c_vp, c_vp, ctypes.POINTER(c_vp)]),
     "nb2_ipc_close": (c_int, [c_vp, c_vp]),
@@ -149,7 +177,7 @@ def stream_ptr(device=None):
 
 
 def ptr(t):
-    """Device pointer of a contiguous fp32/int64 CUDA tensor (None -> NULL)."""
+    """Device pointer of a contiguous CUDA tensor (None -> NULL)."""
     if t is None:
         return None
     if not t.is_cuda:
@@ -157,6 +185,10 @@ def ptr(t):
     if not t.is_contiguous():
         raise NB2Error("tensor must be contiguous")
     return c_vp(t.data_ptr())
+
+
+def ptr_int(t):
+    return 0 if t is None else t.data_ptr()
 
 
 def f32(t):

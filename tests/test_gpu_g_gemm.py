@@ -1,0 +1,100 @@
+"""GPU: the generic tcgen05 GEMM of the layer-wise engine (nb2_gemm_bf16) against torch.matmul on the same bf16 operands,
+in the three operand-layout combinations the training step uses (forward, dgrad, wgrad), with K segments (split-precision
+passes, torch.cat inputs), ragged sizes, N tiling, split-K and every epilogue option."""
+import pytest
+import torch
+
+from nerf_b200 import linear
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def rnd(shape, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(DEV)
+
+
+def bf(x):
+    return x.to(torch.bfloat16)
+
+
+def close(got, ref, tol):
+    err = float((got.float() - ref).abs().max())
+    assert err <= tol * max(1.0, float(ref.abs().max())), (err, float(ref.abs().max()))
+
+
+@pytest.mark.parametrize("M,K,N", [(1000, 64, 256), (128, 256, 256), (777, 320, 256), (4096, 256, 128), (130, 128, 3), (5, 64, 1), (3000, 424, 256)])
+def test_forward_shape(M, K, N):
+    """Y = act(X W^T + b): A K-major, B K-major; outputs fp32 + bf16 hi / lo; ragged M, padded K, tiny N."""
+    X, W, b = bf(rnd((M, K), 1)), bf(rnd((N, K), 2, K ** -0.5)), rnd((N,), 3)
+    ref = torch.relu(X.float() @ W.float().T + b)
+    ld = (N + 7) // 8 * 8
+    y32 = torch.full((M, N), -7.0, device=DEV)
+    hi = torch.zeros((M, ld), dtype=torch.bfloat16, device=DEV)
+    lo = torch.zeros((M, ld), dtype=torch.bfloat16, device=DEV)
+    linear.gemm(M, N, [(X, False, W, False, K)], bias=b, act=linear.ACT_RELU, out_f32=y32, out_hi=hi[:, :N], out_lo=lo[:, :N])
+    close(y32, ref, 2e-5)
+    close(hi[:, :N].float() + lo[:, :N].float(), ref, 3e-5)
+    close(hi[:, :N], ref, 8e-3)
+    assert float(hi[:, N:].abs().max()) == 0.0 if ld > N else True
+
+
+def test_segments_and_split_precision():
+    """Three passes (lo*hi, hi*lo, hi*hi) and a concatenated input as K segments: fp32-faithful product of fp32 matrices."""
+    M, K1, K2, N = 900, 256, 64, 256
+    X1, X2, W = rnd((M, K1), 1), rnd((M, K2), 2), rnd((N, K1 + K2), 3, 0.06)
+    x1h, x1l = linear.to_bf16(X1)
+    x2h, x2l = linear.to_bf16(X2)
+    wh, wl = linear.to_bf16(W)
+    out = torch.empty((M, N), device=DEV)
+    segs = []
+    for (a1, a2, w) in ((x1l, x2l, wh), (x1h, x2h, wl), (x1h, x2h, wh)):
+        segs += [(a1, False, w[:, :K1], False, K1), (a2, False, w[:, K1:], False, K2)]
+    linear.gemm(M, N, segs, out_f32=out)
+    ref = (torch.cat((X1, X2), -1).double() @ W.double().T).float()
+    close(out, ref, 2e-5)          # bf16 hi+lo carries 16 bits: ~1e-5 relative
+
+
+@pytest.mark.parametrize("M,N_out,K_in", [(1000, 256, 256), (513, 256, 320), (2000, 128, 288), (300, 16, 128)])
+def test_dgrad_shape(M, N_out, K_in):
+    """dX = (dY W) * (X > 0): A = dY K-major, B = W (out, in) MN-major; N = in may exceed 256 (two N tiles)."""
+    dY, W, Xs = bf(rnd((M, N_out), 1)), bf(rnd((N_out, K_in), 2, 0.06)), bf(rnd((M, K_in), 3))
+    ref = (dY.float() @ W.float()) * (Xs.float() > 0)
+    hi = torch.empty((M, K_in), dtype=torch.bfloat16, device=DEV)
+    lo = torch.empty((M, K_in), dtype=torch.bfloat16, device=DEV)
+    linear.gemm(M, K_in, [(dY, False, W, True, N_out)], mask=Xs, out_hi=hi, out_lo=lo)
+    close(hi.float() + lo.float(), ref, 3e-5)
+
+
+@pytest.mark.parametrize("rows,N_out,K_in,splits", [(4096, 256, 256, 8), (10000, 256, 320, 37), (777, 128, 288, 3), (5000, 16, 128, 148), (64, 256, 64, 4)])
+def test_wgrad_shape(rows, N_out, K_in, splits):
+    """dW = dY^T X: both operands MN-major, split-K partial sums + deterministic reduction; empty splits contribute zero."""
+    dY, X = bf(rnd((rows, N_out), 1)), bf(rnd((rows, K_in), 2))
+    ref = dY.float().T @ X.float()
+    ld_ws = (K_in + 31) // 32 * 32
+    m_pad = (N_out + 127) // 128 * 128
+    ws = torch.full((splits, m_pad, ld_ws), float("nan"), device=DEV)
+    linear.gemm(N_out, K_in, [(dY, True, X, True, rows)], out_f32=ws.view(splits * m_pad, ld_ws)[:N_out], splits=splits, split_stride=m_pad * ld_ws)
+    out = torch.empty((N_out, K_in), device=DEV)
+    linear.reduce_splits(ws, splits, m_pad * ld_ws, N_out, K_in, ld_ws, out)
+    close(out, ref, 1e-5 * rows ** 0.5)
+    again = torch.empty_like(out)
+    ws.fill_(float("nan"))
+    linear.gemm(N_out, K_in, [(dY, True, X, True, rows)], out_f32=ws.view(splits * m_pad, ld_ws)[:N_out], splits=splits, split_stride=m_pad * ld_ws)
+    linear.reduce_splits(ws, splits, m_pad * ld_ws, N_out, K_in, ld_ws, again)
+    assert torch.equal(out, again)          # no atomics: bit-reproducible
+
+
+def test_to_bf16_permutation_and_colsum():
+    W = rnd((256, 319), 5)
+    perm = torch.cat((torch.arange(63) + 256, torch.arange(256))).to(torch.int32).to(DEV)     # [enc | hidden] -> [hidden | enc]
+    hi, lo = linear.to_bf16(W, ld_dst=320, col_perm=perm)
+    back = (hi.float() + lo.float())
+    assert float((back[:, 256:319] - W[:, :63]).abs().max()) < 1e-4 and float((back[:, :256] - W[:, 63:]).abs().max()) < 1e-4
+    assert float(back[:, 319].abs().max()) == 0.0
+    x = rnd((5000, 256), 6)
+    xh, xl = linear.to_bf16(x)
+    s = torch.empty(256, device=DEV)
+    linear.colsum(xh, xl, 256, s)
+    close(s, x.sum(0), 2e-4)
