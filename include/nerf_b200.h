@@ -286,6 +286,30 @@ int nb2_reduce_splits(nb2_handle* h, const float* ws, int splits, int64_t split_
 int nb2_colsum_bf16(nb2_handle* h, const void* hi, const void* lo, int64_t rows, int cols, int ld, float* out, int accumulate,
                     void* stream);
 
+/* ---- training step, HBM-bound pieces: encodings as GEMM operands and the backward of the ray ops --------
+ * In the reference these are autograd's derivatives of the torch ops the functions are written in (train.py:206).
+ * nb2_encode_bf16: x (n, x_stride) fp32, point / direction in columns [x_col0, x_col0+3) (normalize != 0: d / ||d|| first,
+ *   nerf/mip_model.py:44-45) -> rows [x, sin(2^l x), cos(2^l x) ...] (nerf/nerf_helper.py:38-48) as bf16 hi (+ lo) with
+ *   row stride ld, zero-padded to `width` columns.
+ * nb2_weights_from_sigma_backward: g_weights (R,P) -> d_sigma (R,P)          nerf/addtional.py:99-107, nerf_base.py:79-86
+ * nb2_composite_backward: g_rgb (R,3), g_weights (R,P) or NULL -> d_rgbo (R,P,4)             nerf/nerf_base.py:90-113
+ * nb2_max_blur_backward: weights (R,P), g_out (R,P) -> d_weights (R,P)                        nerf/mip_methods.py:61-66
+ * nb2_get_bounds_backward: inds (R,K) int64, g_out (R,K-1) -> d_weights (R,P)                 nerf/addtional.py:14-18
+ * nb2_nerf_head_backward: out (n,4) = MipNeRF.forward's result, g_out (n,4) -> d_z (n,8) bf16 hi/lo = g_rgb * rgb (1 - rgb)
+ *   (rgb_layer.2 pre-activation gradient, columns 0..2) and d_s (n,8) bf16 hi/lo = g_sigma (column 0).  nerf/mip_model.py:57-60 */
+int nb2_encode_bf16(nb2_handle* h, const float* x, int x_stride, int x_col0, int64_t n, int levels, int normalize, void* hi, void* lo,
+                    int64_t ld, int width, void* stream);
+int nb2_weights_from_sigma_backward(nb2_handle* h, const float* sigma, const float* z, const float* dirs, int dir_stride,
+                                    int64_t n_rays, int n_samples, int act, const float* g_weights, float* d_sigma, void* stream);
+int nb2_composite_backward(nb2_handle* h, const float* rgbo, const float* z, const float* dirs, int dir_stride, int64_t n_rays,
+                           int n_samples, int flags, const float* g_rgb, const float* g_weights, float* d_rgbo, void* stream);
+int nb2_max_blur_backward(nb2_handle* h, const float* weights, const float* g_out, int64_t n_rays, int n_samples, float* d_weights,
+                          void* stream);
+int nb2_get_bounds_backward(nb2_handle* h, const int64_t* inds, const float* g_out, int64_t n_rays, int n_samples, int n_inds,
+                            float* d_weights, void* stream);
+int nb2_nerf_head_backward(nb2_handle* h, const float* out, const float* g_out, int64_t n, void* dz_hi, void* dz_lo, void* ds_hi,
+                           void* ds_lo, void* stream);
+
 /* ---- peer memory for the fused gather (one process per GPU, CUDA IPC over NVLink / NVSwitch) -----------------
  * nb2_ipc_alloc: cudaMalloc `bytes` on the handle's device and export a 64-byte IPC handle for it.
  * nb2_ipc_open : map another process's allocation into this process (peer access is enabled on demand).

@@ -13,6 +13,9 @@ from .nerf_helper import makeMLP
 
 def getBounds(weights: torch.Tensor, inds: torch.Tensor):
     """Proposal-weight mass between consecutive fine samples (reference nerf/addtional.py:14-18)."""
+    if torch.is_grad_enabled() and weights.requires_grad:
+        from .train_engine import GetBounds
+        return GetBounds.apply(weights, inds)
     return ops.get_bounds(weights, inds)
 
 
@@ -67,6 +70,7 @@ class ProposalNetwork(PackedModule):
         )
         self.apply(self.init_weight)
         self.precision = None
+        self.train_precision = None
 
     def loadFromFile(self, load_path: str, use_amp=False, other_stuff=None):
         save = torch.load(load_path, map_location="cpu")
@@ -91,7 +95,12 @@ class ProposalNetwork(PackedModule):
 
     def forward(self, pts: torch.Tensor, encoded_pt: torch.Tensor = None) -> torch.Tensor:
         """pts (ray_num, point_num, 3) -> raw density (ray_num, point_num)."""
-        self._nb2_refuse_autograd(pts, encoded_pt)
+        if self._nb2_wants_grad(pts, encoded_pt):
+            if encoded_pt is not None:
+                raise _lib.NB2Error("ProposalNetwork.forward(encoded_pt=...) is inference-only (the reference never trains through it)")
+            from .train_engine import ProposalEngine, differentiable_forward
+            out = differentiable_forward(self, ProposalEngine, _lib.f32(pts.detach()).reshape(-1, 3), self.train_precision)
+            return out.view(pts.shape[0], pts.shape[1])
         net_id = self._nb2_sync()
         if encoded_pt is not None:
             # the reference views encoded_pt as (R, P, position_dims) and concatenates it behind the raw points
@@ -103,4 +112,7 @@ class ProposalNetwork(PackedModule):
 
     @staticmethod
     def get_weights(density: torch.Tensor, zvals: torch.Tensor, ray_dirs: torch.Tensor = None) -> torch.Tensor:
+        if torch.is_grad_enabled() and density.requires_grad:
+            from .train_engine import WeightsFromSigma
+            return WeightsFromSigma.apply(density, zvals.detach(), ray_dirs.detach() if ray_dirs is not None else None, "relu")
         return ops.weights_from_sigma(density, zvals, ray_dirs, "relu")

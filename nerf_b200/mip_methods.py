@@ -4,6 +4,10 @@ from . import ops
 
 def maxBlurFilter(weights, alpha):
     """2-tap max then 2-tap mean + alpha (reference nerf/mip_methods.py:61-66)."""
+    import torch
+    if torch.is_grad_enabled() and weights.requires_grad:
+        from .train_engine import MaxBlur
+        return MaxBlur.apply(weights, alpha)
     return ops.max_blur(weights, alpha)
 
 

@@ -35,7 +35,8 @@ class MipNeRF(NeRF):
             *makeMLP(128, 3, nn.Sigmoid())
         )
         self.apply(self.init_weight)
-        self.precision = None  # None -> ops.get_default_precision()
+        self.precision = None        # fused inference kernels: None -> ops.get_default_precision()
+        self.train_precision = None  # differentiable layer-wise engine: None -> 'bf16x3' (or 'bf16')
 
     def _nb2_linears(self):
         return [self.lin_block1[0], self.lin_block1[2], self.lin_block1[4], self.lin_block1[6],
@@ -49,7 +50,10 @@ class MipNeRF(NeRF):
 
     def forward(self, pts: torch.Tensor) -> torch.Tensor:
         """pts (ray_num, point_num, 6) = [xyz, dir] -> (ray_num, point_num, 4) = [rgb, sigma]."""
-        self._nb2_refuse_autograd(pts)
+        if self._nb2_wants_grad(pts):
+            from .train_engine import NerfEngine, differentiable_forward
+            out = differentiable_forward(self, NerfEngine, _lib.f32(pts.detach()).reshape(-1, pts.shape[-1]), self.train_precision)
+            return out.view(pts.shape[0], pts.shape[1], 4)
         net_id = self._nb2_sync()
         out = ops.mlp_forward(net_id, pts.reshape(-1, pts.shape[-1]), self.precision)
         return out.view(pts.shape[0], pts.shape[1], 4)

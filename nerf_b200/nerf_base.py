@@ -65,14 +65,11 @@ class PackedModule(nn.Module):
             self.__dict__["_nb2_key"] = key
         return net_id
 
-    def _nb2_refuse_autograd(self, *inputs):
-        """The engine's forward kernels record no autograd graph: refuse to silently return a detached result when the
-        caller expects gradients (training goes through the layer-wise engine, see train_step / linear.py)."""
-        if torch.is_grad_enabled() and (any(t is not None and t.requires_grad for t in inputs)
-                                        or any(p.requires_grad for p in self.parameters())):
-            raise _lib.NB2Error(f"{type(self).__name__}.forward: the fused inference kernels do not record gradients; call under "
-                                "torch.no_grad() (render / eval), or set module.train_engine = True to run the differentiable "
-                                "layer-wise engine")
+    def _nb2_wants_grad(self, *inputs):
+        """True when the caller expects gradients (grad mode on and an input or a parameter requires grad): forward then
+        runs the differentiable layer-wise engine (train_engine.py) instead of the fused inference kernels."""
+        return torch.is_grad_enabled() and (any(t is not None and t.requires_grad for t in inputs)
+                                            or any(p.requires_grad for p in self.parameters()))
 
 
 def _release_slot(net_id, dev):
@@ -129,6 +126,9 @@ class NeRF(PackedModule):
 
     @staticmethod
     def getNormedWeight(opacity: torch.Tensor, depth: torch.Tensor, density_act=F.relu) -> torch.Tensor:
+        if torch.is_grad_enabled() and opacity.requires_grad:
+            from .train_engine import WeightsFromSigma
+            return WeightsFromSigma.apply(opacity, depth.detach(), None, _act_name(density_act))
         return ops.weights_from_sigma(opacity, depth, None, _act_name(density_act))
 
     @staticmethod
@@ -141,6 +141,13 @@ class NeRF(PackedModule):
         if not mul_norm:
             ray_dirs = torch.zeros_like(ray_dirs[..., :3])
             ray_dirs[..., 0] = 1.0  # unit norm: depth is used as given
+        if torch.is_grad_enabled() and rgbo.requires_grad:
+            # training (train.py:192): gradients flow to rgb-sigma; the depth image is an eval-only output
+            if render_depth is not None:
+                raise _lib.NB2Error("render(): render_depth is not differentiable here; call it under torch.no_grad()")
+            from .train_engine import Composite
+            rgb, weights = Composite.apply(rgbo, depth.detach(), ray_dirs.detach(), bool(white_bkg))
+            return rgb, weights, dict()
         rgb, weights, d, _ = ops.composite(rgbo, depth, ray_dirs, white_bkg=white_bkg, near_far=render_depth)
         extras = dict()
         if render_depth is not None:

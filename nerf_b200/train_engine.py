@@ -1,0 +1,420 @@
+"""The differentiable, layer-wise engine behind MipNeRF.forward / ProposalNetwork.forward when gradients are wanted
+(the `run()` closure of the reference's train.py:164-199 and its `loss.backward()`).
+
+The fused inference kernels keep activations in shared / tensor memory and record nothing; training needs every layer's
+input for the weight gradients.  Here each nn.Linear is one launch of the generic tcgen05 GEMM (nb2_gemm_bf16,
+csrc/nb2_gemm.cu) whose epilogue writes the activation as bf16 hi (+ lo residual) rows -- exactly the operand format of the
+next layer's forward, of the dgrad and of the wgrad -- so the forward pass saves what the backward pass reads and nothing is
+converted or transposed in between:
+
+    forward   H_{l+1} = relu(H_l W_l^T + b_l)                 A = H_l (K-major),   B = W_l (K-major)
+    dgrad     dH_l    = (dH_{l+1} W_l) * (H_l > 0)            A = dH_{l+1},        B = W_l (MN-major)   relu mask = saved H_l
+    wgrad     dW_l    = dH_{l+1}^T H_l                        A = dH_{l+1} (MN),   B = H_l (MN), split-K + deterministic reduce
+    bgrad     db_l    = column sums of dH_{l+1}
+
+torch.cat inputs of the reference (mip_model.py:55 skip connection, :59 bottleneck + encoded direction) are column ranges
+of one wider buffer; the matching weight columns are permuted once when the weights are converted, and the gradient is
+permuted back by the split-K reduction.  precision 'bf16x3' (default): every product as lo*hi + hi*lo + hi*hi (three K
+segments, 16 significant bits, no fp16 range problem for gradients); 'bf16': one pass (the analogue of the reference's
+autocast training, train.py:201-207, without needing a GradScaler because bf16 keeps fp32's exponent).
+"""
+import ctypes
+
+import torch
+
+from . import _lib, linear
+from ._lib import check, handle, load, stream_ptr
+
+BF16 = torch.bfloat16
+
+
+def _pad8(n):
+    return (n + 7) // 8 * 8
+
+
+def _empty16(rows, cols, dev, lo=True):
+    return (torch.empty((rows, cols), dtype=BF16, device=dev), torch.empty((rows, cols), dtype=BF16, device=dev) if lo else None)
+
+
+def encode(x, x_col0, levels, normalize, hi, lo):
+    """Rows [x, sin(2^l x), cos(2^l x) ...] of points x[:, x_col0:x_col0+3] into the (column view) hi / lo."""
+    dev = x.device
+    check(load().nb2_encode_bf16(handle(dev), x.data_ptr(), x.stride(0), x_col0, x.shape[0], levels, 1 if normalize else 0, hi.data_ptr(),
+                                 _lib.ptr_int(lo), hi.stride(0), hi.shape[1], stream_ptr(dev)))
+
+
+class PackedLinear:
+    """bf16 hi / lo image of one nn.Linear in the engine's column order, refreshed when the parameter changes."""
+
+    def __init__(self, lin, col_perm=None, in_pad=None):
+        self.lin = lin
+        self.out_f, self.in_f = lin.weight.shape
+        self.in_pad = _pad8(self.in_f) if in_pad is None else in_pad
+        self.perm_host = col_perm
+        self.perm = None
+        self.key = None
+        self.hi = self.lo = None
+
+    def sync(self):
+        w = self.lin.weight
+        key = (w.data_ptr(), w._version, w.device)
+        if key != self.key:
+            if self.perm_host is not None and (self.perm is None or self.perm.device != w.device):
+                self.perm = self.perm_host.to(device=w.device, dtype=torch.int32)
+            self.hi, self.lo = linear.to_bf16(w.detach(), ld_dst=self.in_pad, col_perm=self.perm)
+            self.key = key
+        return self
+
+    def cols(self, c0, c1):
+        return self.hi[:, c0:c1], self.lo[:, c0:c1]
+
+
+def _fwd_segs(x, w, K, x3):
+    """x, w: (hi, lo) pairs; small terms first."""
+    if x3:
+        return [(x[1], False, w[0], False, K), (x[0], False, w[1], False, K), (x[0], False, w[0], False, K)]
+    return [(x[0], False, w[0], False, K)]
+
+
+def _dgrad_segs(dy, w, K, x3):
+    if x3:
+        return [(dy[1], False, w[0], True, K), (dy[0], False, w[1], True, K), (dy[0], False, w[0], True, K)]
+    return [(dy[0], False, w[0], True, K)]
+
+
+class _Workspace:
+    """Split-K partial sums of the weight gradients (one buffer per device, grown on demand)."""
+    bufs = {}
+
+    @classmethod
+    def get(cls, dev, floats):
+        b = cls.bufs.get(dev)
+        if b is None or b.numel() < floats:
+            b = torch.empty(floats, dtype=torch.float32, device=dev)
+            cls.bufs[dev] = b
+        return b
+
+
+def wgrad(dy, x, n_out, n_in, rows, x3, grad_w, perm=None, sm_count=148):
+    """grad_w (n_out, n_in) fp32 = dy^T x over `rows` samples; dy (rows, >= n_out), x (rows, ld >= n_in) as (hi, lo)."""
+    dev = x[0].device
+    ld_ws = (x[0].shape[1] + 31) // 32 * 32
+    n_cols = x[0].shape[1]
+    m_pad = (n_out + 127) // 128 * 128
+    tiles = (m_pad // 128) * ((ld_ws + 255) // 256)
+    splits = max(1, min(sm_count // tiles, (rows + 255) // 256))
+    ws = _Workspace.get(dev, splits * m_pad * ld_ws)
+    out = ws[: splits * m_pad * ld_ws].view(splits * m_pad, ld_ws)
+    if x3:
+        segs = [(dy[1], True, x[0], True, rows), (dy[0], True, x[1], True, rows), (dy[0], True, x[0], True, rows)]
+    else:
+        segs = [(dy[0], True, x[0], True, rows)]
+    linear.gemm(n_out, n_cols, segs, out_f32=out[:n_out], splits=max(splits, 1) if splits > 1 else 1, split_stride=m_pad * ld_ws)
+    linear.reduce_splits(ws, splits, m_pad * ld_ws, n_out, n_in, ld_ws, grad_w, col_perm=perm)
+
+
+class ProposalEngine:
+    """ProposalNetwork(10, 256): 63 -> 256 -> 256 -> 256 -> 256 -> 1 (nerf/addtional.py:61-72,88-96)."""
+
+    keep_last_acts = False     # tests: keep a reference to the saved activations of the last forward (relu patterns)
+    last_acts = None
+
+    def __init__(self, module):
+        self.m = module
+        L = module.layers
+        self.lins = [L[0], L[2], L[4], L[6], L[8]]
+        self.packed = [PackedLinear(l) for l in self.lins]
+        self.levels = module.position_flevel
+
+    def forward(self, pts, x3):
+        """pts (n, 3) fp32 -> (sigma (n,) fp32, saved activations)."""
+        dev, n = pts.device, pts.shape[0]
+        W = [p.sync() for p in self.packed]
+        H = self.lins[0].out_features
+        enc_w = _pad8(3 + 6 * self.levels)
+        E = _empty16(n, enc_w, dev, x3)
+        encode(pts, 0, self.levels, False, E[0], E[1])
+        acts = [E]
+        x, K = E, 3 + 6 * self.levels
+        for l in range(4):
+            y = _empty16(n, H, dev, x3)
+            linear.gemm(n, H, _fwd_segs(x, (W[l].hi, W[l].lo), K, x3), bias=self.lins[l].bias.detach(), act=linear.ACT_RELU,
+                        out_hi=y[0], out_lo=y[1])
+            acts.append(y)
+            x, K = y, H
+        sigma = torch.empty((n, 1), dtype=torch.float32, device=dev)
+        linear.gemm(n, 1, _fwd_segs(x, (W[4].hi, W[4].lo), H, x3), bias=self.lins[4].bias.detach(), out_f32=sigma)
+        return sigma.view(n), acts
+
+    def backward(self, acts, g_sigma, x3):
+        """g_sigma (n,) fp32 -> list of (grad_weight, grad_bias) in state_dict order."""
+        dev, n = g_sigma.device, g_sigma.shape[0]
+        W = [p.sync() for p in self.packed]
+        H = self.lins[0].out_features
+        sm = torch.cuda.get_device_properties(dev).multi_processor_count
+        grads = [None] * 5
+        ds = linear.to_bf16(g_sigma.contiguous().view(n, 1), ld_dst=8, want_lo=x3)
+        gw = torch.empty_like(self.lins[4].weight)
+        gb = torch.empty_like(self.lins[4].bias)
+        wgrad(ds, acts[4], 1, H, n, x3, gw, sm_count=sm)
+        linear.colsum(ds[0], ds[1], 1, gb)
+        grads[4] = (gw, gb)
+        dy = _empty16(n, H, dev, x3)
+        linear.gemm(n, H, _dgrad_segs(ds, (W[4].hi, W[4].lo), 1, x3), mask=acts[4][0], out_hi=dy[0], out_lo=dy[1])
+        for l in (3, 2, 1, 0):
+            x = acts[l]
+            in_f = self.lins[l].in_features
+            gw = torch.empty_like(self.lins[l].weight)
+            gb = torch.empty_like(self.lins[l].bias)
+            wgrad(dy, x, H, in_f, n, x3, gw, sm_count=sm)
+            linear.colsum(dy[0], dy[1], H, gb)
+            grads[l] = (gw, gb)
+            if l > 0:
+                dx = _empty16(n, H, dev, x3)
+                linear.gemm(n, H, _dgrad_segs(dy, (W[l].hi, W[l].lo), H, x3), mask=x[0], out_hi=dx[0], out_lo=dx[1])
+                dy = dx
+        return grads
+
+
+class NerfEngine:
+    """MipNeRF(10, 4, 256): the vanilla 8x256 NeRF MLP with skip connection and heads (nerf/mip_model.py:14-60)."""
+
+    keep_last_acts = False
+    last_acts = None
+
+    def __init__(self, module):
+        self.m = module
+        b1, b2 = module.lin_block1, module.lin_block2
+        self.lins = [b1[0], b1[2], b1[4], b1[6], b2[0], b2[2], b2[4], module.bottle_neck[0], module.opacity_head[0],
+                     module.rgb_layer[0], module.rgb_layer[2]]
+        self.pl, self.dl = module.position_flevel, module.direction_flevel
+        self.enc = 3 + 6 * self.pl
+        self.denc = 3 + 6 * self.dl
+        H = self.lins[0].out_features
+        self.H = H
+        # lin_block2.0 multiplies cat(enc, h) (mip_model.py:55); the engine's buffer is [h | enc | pad]
+        perm4 = torch.cat((torch.arange(self.enc) + H, torch.arange(H)))
+        self.packed = [PackedLinear(l) for l in self.lins]
+        self.packed[4] = PackedLinear(self.lins[4], col_perm=perm4, in_pad=H + _pad8(self.enc))
+
+    def forward(self, pts, x3):
+        """pts (n, 6) fp32 = [xyz, dir] -> (out (n, 4) fp32 = [sigmoid rgb, raw sigma], saved activations)."""
+        dev, n = pts.device, pts.shape[0]
+        W = [p.sync() for p in self.packed]
+        H, enc_w, denc_w = self.H, _pad8(self.enc), _pad8(self.denc)
+        b = [l.bias.detach() for l in self.lins]
+        C5 = _empty16(n, H + enc_w, dev, x3)                      # [h4 | enc]
+        E = (C5[0][:, H:], C5[1][:, H:] if x3 else None)
+        encode(pts, 0, self.pl, False, E[0], E[1])
+        C9 = _empty16(n, H + denc_w, dev, x3)                     # [bottleneck | enc(dir)]
+        encode(pts, 3, self.dl, True, C9[0][:, H:], C9[1][:, H:] if x3 else None)
+        wl = lambda i: (W[i].hi, W[i].lo)
+        h1, h2, h3 = (_empty16(n, H, dev, x3) for _ in range(3))
+        linear.gemm(n, H, _fwd_segs(E, wl(0), self.enc, x3), bias=b[0], act=linear.ACT_RELU, out_hi=h1[0], out_lo=h1[1])
+        linear.gemm(n, H, _fwd_segs(h1, wl(1), H, x3), bias=b[1], act=linear.ACT_RELU, out_hi=h2[0], out_lo=h2[1])
+        linear.gemm(n, H, _fwd_segs(h2, wl(2), H, x3), bias=b[2], act=linear.ACT_RELU, out_hi=h3[0], out_lo=h3[1])
+        h4 = (C5[0][:, :H], C5[1][:, :H] if x3 else None)
+        linear.gemm(n, H, _fwd_segs(h3, wl(3), H, x3), bias=b[3], act=linear.ACT_RELU, out_hi=h4[0], out_lo=h4[1])
+        h5, h6, h7 = (_empty16(n, H, dev, x3) for _ in range(3))
+        linear.gemm(n, H, _fwd_segs(C5, wl(4), H + self.enc, x3), bias=b[4], act=linear.ACT_RELU, out_hi=h5[0], out_lo=h5[1])
+        linear.gemm(n, H, _fwd_segs(h5, wl(5), H, x3), bias=b[5], act=linear.ACT_RELU, out_hi=h6[0], out_lo=h6[1])
+        linear.gemm(n, 256, _fwd_segs(h6, wl(6), H, x3), bias=b[6], act=linear.ACT_RELU, out_hi=h7[0], out_lo=h7[1])
+        out = torch.empty((n, 4), dtype=torch.float32, device=dev)
+        linear.gemm(n, 1, _fwd_segs(h7, wl(8), 256, x3), bias=b[8], out_f32=out[:, 3:])                     # opacity_head
+        bn = (C9[0][:, :256], C9[1][:, :256] if x3 else None)
+        linear.gemm(n, 256, _fwd_segs(h7, wl(7), 256, x3), bias=b[7], out_hi=bn[0], out_lo=bn[1])           # bottle_neck (linear)
+        t = _empty16(n, 128, dev, x3)
+        linear.gemm(n, 128, _fwd_segs(C9, wl(9), 256 + self.denc, x3), bias=b[9], act=linear.ACT_RELU, out_hi=t[0], out_lo=t[1])
+        linear.gemm(n, 3, _fwd_segs(t, wl(10), 128, x3), bias=b[10], act=linear.ACT_SIGMOID, out_f32=out[:, :3])
+        return out, dict(E=E, h1=h1, h2=h2, h3=h3, C5=C5, h5=h5, h6=h6, h7=h7, C9=C9, t=t, out=out)
+
+    def backward(self, a, g_out, x3):
+        """g_out (n, 4) fp32 -> list of 11 (grad_weight, grad_bias) in state_dict order."""
+        dev, n = g_out.device, g_out.shape[0]
+        W = [p.sync() for p in self.packed]
+        H = self.H
+        sm = torch.cuda.get_device_properties(dev).multi_processor_count
+        wl = lambda i: (W[i].hi, W[i].lo)
+        grads = [None] * 11
+
+        def wg(i, dy, x, n_out, n_in, perm=None):
+            gw, gb = torch.empty_like(self.lins[i].weight), torch.empty_like(self.lins[i].bias)
+            wgrad(dy, x, n_out, n_in, n, x3, gw, perm=perm, sm_count=sm)
+            linear.colsum(dy[0], dy[1], n_out, gb)
+            grads[i] = (gw, gb)
+
+        dz, ds = _empty16(n, 8, dev, x3), _empty16(n, 8, dev, x3)
+        check(load().nb2_nerf_head_backward(handle(dev), a["out"].data_ptr(), g_out.contiguous().data_ptr(), n, dz[0].data_ptr(),
+                                            _lib.ptr_int(dz[1]), ds[0].data_ptr(), _lib.ptr_int(ds[1]), stream_ptr(dev)))
+        wg(10, dz, a["t"], 3, 128)                                                                   # rgb_layer.2
+        dt = _empty16(n, 128, dev, x3)
+        linear.gemm(n, 128, _dgrad_segs(dz, wl(10), 3, x3), mask=a["t"][0], out_hi=dt[0], out_lo=dt[1])
+        wg(9, dt, a["C9"], 128, 256 + self.denc)                                                     # rgb_layer.0
+        db = _empty16(n, 256, dev, x3)
+        w9 = W[9].cols(0, 256)
+        linear.gemm(n, 256, _dgrad_segs(dt, w9, 128, x3), out_hi=db[0], out_lo=db[1])                # -> bottleneck (no activation)
+        wg(7, db, a["h7"], 256, 256)                                                                 # bottle_neck
+        wg(8, ds, a["h7"], 1, 256)                                                                   # opacity_head
+        d7 = _empty16(n, 256, dev, x3)
+        linear.gemm(n, 256, _dgrad_segs(db, wl(7), 256, x3) + _dgrad_segs(ds, wl(8), 1, x3), mask=a["h7"][0], out_hi=d7[0], out_lo=d7[1])
+        wg(6, d7, a["h6"], 256, H)
+        d6 = _empty16(n, H, dev, x3)
+        linear.gemm(n, H, _dgrad_segs(d7, wl(6), 256, x3), mask=a["h6"][0], out_hi=d6[0], out_lo=d6[1])
+        wg(5, d6, a["h5"], H, H)
+        d5 = _empty16(n, H, dev, x3)
+        linear.gemm(n, H, _dgrad_segs(d6, wl(5), H, x3), mask=a["h5"][0], out_hi=d5[0], out_lo=d5[1])
+        wg(4, d5, a["C5"], H, H + self.enc, perm=W[4].perm)                                          # lin_block2.0 on cat(enc, h)
+        d4 = _empty16(n, H, dev, x3)
+        linear.gemm(n, H, _dgrad_segs(d5, W[4].cols(0, H), H, x3), mask=a["C5"][0][:, :H], out_hi=d4[0], out_lo=d4[1])
+        wg(3, d4, a["h3"], H, H)
+        d3 = _empty16(n, H, dev, x3)
+        linear.gemm(n, H, _dgrad_segs(d4, wl(3), H, x3), mask=a["h3"][0], out_hi=d3[0], out_lo=d3[1])
+        wg(2, d3, a["h2"], H, H)
+        d2 = _empty16(n, H, dev, x3)
+        linear.gemm(n, H, _dgrad_segs(d3, wl(2), H, x3), mask=a["h2"][0], out_hi=d2[0], out_lo=d2[1])
+        wg(1, d2, a["h1"], H, H)
+        d1 = _empty16(n, H, dev, x3)
+        linear.gemm(n, H, _dgrad_segs(d2, wl(1), H, x3), mask=a["h1"][0], out_hi=d1[0], out_lo=d1[1])
+        wg(0, d1, a["E"], H, self.enc)
+        return grads
+
+
+class _MLPFunction(torch.autograd.Function):
+    """forward(engine, x3, pts, *params): params are passed so autograd routes their gradients; values come from the module."""
+
+    @staticmethod
+    def forward(ctx, engine, x3, pts, *params):
+        out, acts = engine.forward(pts, x3)
+        ctx.engine, ctx.x3, ctx.acts = engine, x3, acts
+        if engine.keep_last_acts:
+            engine.last_acts = acts
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        grads = ctx.engine.backward(ctx.acts, g.contiguous(), ctx.x3)
+        ctx.acts = None
+        flat = []
+        for gw, gb in grads:
+            flat += [gw, gb]
+        return (None, None, None, *flat)
+
+
+def train_engine_of(module, engine_cls):
+    eng = module.__dict__.get("_nb2_train_engine")
+    if eng is None:
+        eng = engine_cls(module)
+        module.__dict__["_nb2_train_engine"] = eng
+    return eng
+
+
+def differentiable_forward(module, engine_cls, pts2d, precision):
+    eng = train_engine_of(module, engine_cls)
+    if precision not in (None, "bf16x3", "bf16"):
+        raise _lib.NB2Error(f"the differentiable layer-wise engine runs 'bf16x3' (default) or 'bf16', not {precision!r}")
+    params = [p for l in eng.lins for p in (l.weight, l.bias)]
+    return _MLPFunction.apply(eng, precision != "bf16", pts2d, *params)
+
+
+# ---- autograd wrappers of the ray ops (reference-named entry points call these when a gradient is required) ----------
+class WeightsFromSigma(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, sigma, z, dirs, act):
+        from . import ops
+        w = ops.weights_from_sigma(sigma, z, dirs, act)
+        ctx.save_for_backward(sigma, z, dirs if dirs is not None else torch.empty(0, device=z.device))
+        ctx.act, ctx.has_dirs = act, dirs is not None
+        return w
+
+    @staticmethod
+    def backward(ctx, g):
+        from . import ops
+        sigma, z, dirs = ctx.saved_tensors
+        sigma, z, g = _lib.f32(sigma), _lib.f32(z), _lib.f32(g)
+        dirs = _lib.f32(dirs) if ctx.has_dirs else None
+        R, P = z.shape
+        d = torch.empty_like(sigma)
+        check(load().nb2_weights_from_sigma_backward(handle(z.device), sigma.data_ptr(), z.data_ptr(), _lib.ptr_int(dirs),
+                                                     dirs.shape[-1] if dirs is not None else 0, R, P, ops._ACTS[ctx.act], g.data_ptr(),
+                                                     d.data_ptr(), stream_ptr(z.device)))
+        return d, None, None, None
+
+
+class Composite(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, rgbo, z, dirs, white_bkg):
+        from . import ops
+        rgb, w, _, _ = ops.composite(rgbo, z, dirs, white_bkg=white_bkg)
+        ctx.save_for_backward(rgbo, z, dirs)
+        ctx.white = white_bkg
+        return rgb, w
+
+    @staticmethod
+    def backward(ctx, g_rgb, g_w):
+        rgbo, z, dirs = ctx.saved_tensors
+        rgbo, z, dirs = _lib.f32(rgbo), _lib.f32(z), _lib.f32(dirs)
+        R, P = z.shape
+        g_rgb = _lib.f32(g_rgb) if g_rgb is not None else torch.zeros((R, 3), dtype=torch.float32, device=z.device)
+        g_w = _lib.f32(g_w) if g_w is not None else None
+        d = torch.empty_like(rgbo)
+        check(load().nb2_composite_backward(handle(z.device), rgbo.data_ptr(), z.data_ptr(), dirs.data_ptr(), dirs.shape[-1], R, P,
+                                            _lib.WHITE_BKG if ctx.white else 0, g_rgb.data_ptr(), _lib.ptr_int(g_w), d.data_ptr(),
+                                            stream_ptr(z.device)))
+        return d, None, None, None
+
+
+class MaxBlur(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, w, alpha):
+        from . import ops
+        ctx.save_for_backward(w)
+        return ops.max_blur(w, alpha)
+
+    @staticmethod
+    def backward(ctx, g):
+        (w,) = ctx.saved_tensors
+        w, g = _lib.f32(w), _lib.f32(g)
+        P = w.shape[-1]
+        d = torch.empty_like(w)
+        check(load().nb2_max_blur_backward(handle(w.device), w.data_ptr(), g.data_ptr(), w.numel() // P, P, d.data_ptr(), stream_ptr(w.device)))
+        return d, None
+
+
+class GetBounds(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, w, inds):
+        from . import ops
+        ctx.save_for_backward(inds)
+        ctx.P = w.shape[-1]
+        return ops.get_bounds(w, inds)
+
+    @staticmethod
+    def backward(ctx, g):
+        (inds,) = ctx.saved_tensors
+        inds = inds.to(torch.int64).contiguous()
+        g = _lib.f32(g)
+        R, K = inds.shape
+        d = torch.empty((R, ctx.P), dtype=torch.float32, device=g.device)
+        check(load().nb2_get_bounds_backward(handle(g.device), inds.data_ptr(), g.data_ptr(), R, ctx.P, K, d.data_ptr(), stream_ptr(g.device)))
+        return d, None
+
+
+def allreduce_gradients(modules, group=None, average=True):
+    """ONE flat all-reduce of every gradient of `modules` (the collective DistributedDataParallel performs for the reference,
+    ddp_train.py:98; 530,052 fp32 values = 2.12 MB for MipNeRF).  NCCL over NVLink on GPUs, gloo in the CPU tests."""
+    import torch.distributed as dist
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return 0
+    params = [p for m in modules for p in m.parameters() if p.grad is not None]
+    if not params:
+        return 0
+    flat = torch.cat([p.grad.reshape(-1) for p in params])
+    dist.all_reduce(flat, group=group)
+    if average:
+        flat /= dist.get_world_size(group)
+    off = 0
+    for p in params:
+        n = p.numel()
+        p.grad.copy_(flat[off:off + n].view_as(p.grad))
+        off += n
+    return flat.numel()

@@ -48,33 +48,40 @@ def positional_encoding(x, levels):
 # ----------------------------------------------------------------------------------------------
 # a6  proposal MLP                                             nerf/addtional.py:61-72,88-96
 # ----------------------------------------------------------------------------------------------
-def proposal_forward(sd, pts, pos_levels=10, encoded=None):
+def _relu(x, masks, i):
+    """ReLU, or -- when `masks` is given -- multiplication by a fixed 0/1 pattern: the gradient of a ReLU network is
+    discontinuous in the sign of every pre-activation, so a gradient check against another implementation (whose forward
+    pass differs by rounding) has to hold the activation pattern fixed to compare like with like."""
+    return F.relu(x) if masks is None else x * masks[i].to(x.dtype)
+
+
+def proposal_forward(sd, pts, pos_levels=10, encoded=None, relu_masks=None):
     """pts (..., 3) -> raw density (...).  `encoded` (..., 6L) replaces the sinusoidal features (addtional.py:89-91)."""
     enc = positional_encoding(pts, pos_levels) if encoded is None else encoded.reshape(*pts.shape[:-1], 6 * pos_levels)
     h = torch.cat((pts, enc), dim=-1)       # cat_origin
-    for key in PROPOSAL_KEYS[:-1]:
-        h = F.relu(F.linear(h, sd[key + ".weight"], sd[key + ".bias"]))
+    for i, key in enumerate(PROPOSAL_KEYS[:-1]):
+        h = _relu(F.linear(h, sd[key + ".weight"], sd[key + ".bias"]), relu_masks, i)
     return F.linear(h, sd["layers.8.weight"], sd["layers.8.bias"]).squeeze(-1)
 
 
 # ----------------------------------------------------------------------------------------------
 # a11  NeRF MLP                                                nerf/mip_model.py:41-60
 # ----------------------------------------------------------------------------------------------
-def nerf_forward(sd, pts6, pos_levels=10, dir_levels=4):
-    """pts6 (..., 6) = [xyz, dir] -> (..., 4) = [sigmoid rgb, raw sigma]."""
+def nerf_forward(sd, pts6, pos_levels=10, dir_levels=4, relu_masks=None):
+    """pts6 (..., 6) = [xyz, dir] -> (..., 4) = [sigmoid rgb, raw sigma].  relu_masks: see _relu (8 patterns: 7 trunk layers + rgb_layer.0)."""
     x, d = pts6[..., :3], pts6[..., 3:6]
     rot = d / d.norm(dim=-1, keepdim=True)                                    # :44-45
     enc_x = torch.cat((x, positional_encoding(x, pos_levels)), dim=-1)       # :50-51
     enc_r = torch.cat((rot, positional_encoding(rot, dir_levels)), dim=-1)   # :52
     h = enc_x
-    for key in NERF_KEYS[:4]:                                                 # lin_block1  :54
-        h = F.relu(F.linear(h, sd[key + ".weight"], sd[key + ".bias"]))
+    for i, key in enumerate(NERF_KEYS[:4]):                                   # lin_block1  :54
+        h = _relu(F.linear(h, sd[key + ".weight"], sd[key + ".bias"]), relu_masks, i)
     h = torch.cat((enc_x, h), dim=-1)                                         # skip concat :55
-    for key in NERF_KEYS[4:7]:                                                # lin_block2  :56
-        h = F.relu(F.linear(h, sd[key + ".weight"], sd[key + ".bias"]))
+    for i, key in enumerate(NERF_KEYS[4:7]):                                  # lin_block2  :56
+        h = _relu(F.linear(h, sd[key + ".weight"], sd[key + ".bias"]), relu_masks, 4 + i)
     sigma = F.linear(h, sd["opacity_head.0.weight"], sd["opacity_head.0.bias"])   # :57
     b = F.linear(h, sd["bottle_neck.0.weight"], sd["bottle_neck.0.bias"])         # :58
-    t = F.relu(F.linear(torch.cat((b, enc_r), dim=-1), sd["rgb_layer.0.weight"], sd["rgb_layer.0.bias"]))
+    t = _relu(F.linear(torch.cat((b, enc_r), dim=-1), sd["rgb_layer.0.weight"], sd["rgb_layer.0.bias"]), relu_masks, 7)
     rgb = torch.sigmoid(F.linear(t, sd["rgb_layer.2.weight"], sd["rgb_layer.2.bias"]))  # :59
     return torch.cat((rgb, sigma), dim=-1)                                    # :60
 
@@ -242,8 +249,33 @@ def valid_sampler(rgbs, coords, cam_tf, indices, jitter, point_num, focal, near,
 
 def get_bounds(weights, inds):
     starts, ends = inds[:, :-1], inds[:, 1:] + 1
-    sat = torch.cat((torch.zeros(weights.shape[0], 1), torch.cumsum(weights, dim=-1)), dim=-1)
+    sat = torch.cat((torch.zeros(weights.shape[0], 1, device=weights.device), torch.cumsum(weights, dim=-1)), dim=-1)
     return torch.gather(sat, -1, ends) - torch.gather(sat, -1, starts)
+
+
+# ----------------------------------------------------------------------------------------------
+# f1  one training step of the non-Ref model: the run() closure + loss.backward()      train.py:164-199,206
+# ----------------------------------------------------------------------------------------------
+def train_step(sd_prop, sd_nerf, coarse_pts, coarse_lengths, rgb_targets, rays, u, n_fine=128, blur_alpha=0.01):
+    """Losses and parameter gradients by torch autograd over the restated functions (which is what the reference does)."""
+    sp = {k: v.detach().clone().requires_grad_(True) for k, v in sd_prop.items()}
+    sn = {k: v.detach().clone().requires_grad_(True) for k, v in sd_nerf.items()}
+    density = F.softplus(proposal_forward(sp, coarse_pts))                               # :166,169
+    w_raw = weights_from_sigma(density, coarse_lengths, rays[:, 3:])                     # :170
+    w_p = max_blur(w_raw, blur_alpha)                                                    # :171
+    fine, below = inverse_sample(w_p.detach(), coarse_lengths, u, sort=True)             # :174
+    fine = fine[..., :-1]                                                                # :189
+    rgbo = nerf_forward(sn, length2pts(rays, fine))                                      # :190-191
+    comp = composite(rgbo, fine, rays[:, 3:], white_bkg=False)                           # :192
+    bounds = get_bounds(w_p, below)                                                      # :193
+    img_loss = torch.mean((comp["rgb"] - rgb_targets) ** 2)                              # :195 (SoftL1Loss is MSE, addtional.py:38-43)
+    wd = comp["weights"].detach()
+    prop_loss = torch.sum(torch.relu(wd - bounds) ** 2 / (wd + 1e-8))                    # :197, addtional.py:20-24
+    loss = prop_loss + img_loss                                                          # :198
+    loss.backward()
+    return {"loss": loss.detach(), "img_loss": img_loss.detach(), "prop_loss": prop_loss.detach(), "rendered": comp["rgb"].detach(),
+            "bounds": bounds.detach(), "weights": wd, "fine": fine.detach(), "below": below,
+            "grad_prop": {k: v.grad for k, v in sp.items()}, "grad_nerf": {k: v.grad for k, v in sn.items()}}
 
 
 # ----------------------------------------------------------------------------------------------

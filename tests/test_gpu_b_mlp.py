@@ -149,13 +149,17 @@ def test_two_models_coexist_on_one_handle():
     assert c._nb2_sync() <= sb
 
 
-def test_autograd_is_refused_loudly_by_the_inference_kernels():
-    net = load(nerf_b200.MipNeRF(10, 4, 256), O.make_params("nerf", 2, "he"))
-    pts = torch.zeros(1, 128, 6, device=DEV)
-    with pytest.raises(nerf_b200.NB2Error):
-        net.forward(pts)                          # parameters require grad and grad mode is on: no silent detach
+def test_grad_mode_selects_the_differentiable_engine():
+    """Parameters require grad and grad mode is on (every training call of train.py): forward records a graph through the
+    layer-wise engine; under torch.no_grad() the fused inference kernel runs.  Both agree to the engines' precisions."""
+    net = load(nerf_b200.MipNeRF(10, 4, 256), O.make_params("nerf", 2, "smooth"))
+    pts = torch.cat((O.det_uniform((256, 3), 9, -2.0, 2.0), O.det_uniform((256, 3), 10, -1.0, 1.0)), -1).to(DEV)[None]
+    a = net.forward(pts)
+    assert a.requires_grad and a.grad_fn is not None
     with torch.no_grad():
-        net.forward(pts)
+        b = net.forward(pts)
+    assert not b.requires_grad
+    assert float((a.detach()[..., :3] - b[..., :3]).abs().max()) < 1e-4
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")

@@ -245,3 +245,27 @@ def test_seeded_multi_tile_render_image(golden_round2):
         assert bool((g[:, He:] == 0).all())
         # per-tile evaluation (2,500-row GEMMs) vs one 10,000-row batch: a few rays flip a cdf index
         assert float((err > 1e-4).float().mean()) < 5e-3 and float(err.median()) < 2e-6, (float(err.max()), float((err > 1e-4).float().mean()))
+
+
+def test_training_step_gradients_match_the_reference(golden_round2):
+    """The oracle's restated training step (train.py:164-199 + loss.backward()) against the UNMODIFIED reference's losses
+    and parameter gradients on the same injected draws (tests/golden/make_golden.py round2)."""
+    from tests.golden.make_golden import GRAD_HEAD, train_inputs
+    ti = train_inputs()
+    vs = ti["vs"]
+    pts, lengths, rgb, rays = O.valid_sampler(vs["rgbs"], vs["coords"], vs["cam_tf"], ti["indices"], ti["jitter"], 64, vs["focal"], 2.0, 6.0)
+    sp, sn = O.make_params("proposal", 1, "smooth"), O.make_params("nerf", 2, "smooth")
+    out = O.train_step(sp, sn, pts, lengths, rgb, rays, ti["u"])
+    g = golden_round2
+    losses = torch.stack((out["loss"], out["img_loss"], out["prop_loss"]))
+    assert float((losses - g["train_loss"]).abs().max()) <= 1e-5 * max(1.0, float(g["train_loss"].abs().max())), (losses, g["train_loss"])
+    assert float((out["rendered"] - g["train_rendered"]).abs().max()) < 1e-5
+    assert float((out["bounds"] - g["train_bounds"]).abs().max()) < 1e-5
+    for tag, grads in (("prop", out["grad_prop"]), ("nerf", out["grad_nerf"])):
+        for k, gr in grads.items():
+            ref = g[f"grad_{tag}_{k}"]
+            flat = gr.reshape(-1)
+            got = torch.cat((flat.norm().reshape(1), flat.sum().reshape(1), flat[:GRAD_HEAD]))
+            scale = max(float(ref[0]), 1e-12)
+            assert float((got[0] - ref[0]).abs()) <= 1e-4 * scale, (tag, k, float(got[0]), float(ref[0]))
+            assert float((got[2:] - ref[2:]).abs().max()) <= 1e-4 * scale, (tag, k)
