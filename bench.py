@@ -202,6 +202,102 @@ def torch_cuda_baseline(dev, H, W):
     return out
 
 
+def train_step_leg(dev, precision="bf16x3", batches=(1024, 8192), steps=10):
+    """One training step of the non-Ref model as the reference's trainer runs it (train.py:157-218): validSampler ->
+    run() closure -> loss.backward() -> Adam step, on `R` rays x (64 coarse + 128 fine) samples, through the layer-wise
+    tcgen05 engine (nerf_b200/train_engine.py).  R = 1024 is the reference's default --sample_ray_num; the larger batch
+    shows the engine once the ~75 launches of a step stop being launch-bound.  Next to it: the same step as PyTorch ops on
+    the same GPU (oracle port, fp32, TF32 off)."""
+    import torch.nn.functional as F
+    import nerf_b200
+    from nerf_b200 import NeRF, ProposalNetwork, getBounds, inverseSample, maxBlurFilter
+    from oracle import nerf_oracle as O
+    peaks = load_peaks()
+    sd_prop, sd_nerf = synthetic_state_dicts()
+    prop_net, mip_net = nerf_b200.ProposalNetwork(10, 256), nerf_b200.MipNeRF(10, 4, 256)
+    prop_net.load_state_dict(sd_prop); mip_net.load_state_dict(sd_nerf)
+    prop_net, mip_net = prop_net.to(dev), mip_net.to(dev)
+    prop_net.train_precision = mip_net.train_precision = precision
+    grad_vars = list(mip_net.parameters()) + list(prop_net.parameters())
+    opt = torch.optim.Adam(params=grad_vars, lr=1.5e-4, betas=(0.9, 0.999))
+    loss_func, prop_loss_func = nerf_b200.SoftL1Loss(), nerf_b200.ProposalLoss()
+    Hh = Ww = 400
+    g = torch.Generator().manual_seed(3)
+    rgbs = torch.rand(Hh * Ww, 3, generator=g).to(dev)
+    rows, cols = torch.meshgrid(torch.arange(Hh), torch.arange(Ww), indexing="ij")
+    coords = torch.stack((cols - Ww // 2, Hh // 2 - rows), dim=-1).reshape(-1, 2).to(dev)
+    cam_tf = nerf_b200.pose_spherical(30.0, -30.0, 4.0)[:3, :].contiguous().to(dev)
+    focal = nerf_b200.fov2Focal(FOV, (Hh, Ww))
+    passes = 3 if precision == "bf16x3" else 1
+    # algorithmic HBM bytes per MLP row of the layer-wise engine: every Linear (in k, out n) reads X and writes Y in the
+    # forward, reads dY + the relu mask and writes dX in the dgrad, reads dY and X in the wgrad; bf16 hi (+ lo) operands
+    b16 = 2 * (2 if precision == "bf16x3" else 1)
+
+    def layer_bytes(layers, first_has_dgrad=False):
+        t = 0
+        for i, (k, n) in enumerate(layers):
+            t += b16 * k + b16 * n                      # forward
+            t += b16 * n + b16 * k                      # wgrad
+            if i > 0 or first_has_dgrad:
+                t += b16 * n + 2 * k + b16 * k          # dgrad (+ mask)
+        return t
+    nerf_layers = [(64, 256), (256, 256), (256, 256), (256, 256), (320, 256), (256, 256), (256, 256), (256, 256), (256, 8), (288, 128), (128, 8)]
+    prop_layers = [(64, 256), (256, 256), (256, 256), (256, 256), (256, 8)]
+    bytes_per_ray = N_FINE * layer_bytes(nerf_layers) + N_COARSE * layer_bytes(prop_layers)
+    out = {"precision": precision, "mma_passes_per_product": passes, "what": train_step_leg.__doc__.split("\n")[0]}
+    for R in batches:
+        def step(i):
+            coarse_samples, coarse_lengths, rgb_targets, coarse_cam_rays = nerf_b200.validSampler(rgbs, coords, cam_tf, R, N_COARSE, focal, NEAR, FAR, True)
+            density = F.softplus(prop_net.forward(coarse_samples))
+            prop_weights = maxBlurFilter(ProposalNetwork.get_weights(density, coarse_lengths, coarse_cam_rays[:, 3:]), 0.01)
+            fine_lengths, below_idxs = inverseSample(prop_weights, coarse_lengths, N_FINE + 1, sort=True)
+            fine_lengths = fine_lengths[..., :-1]
+            fine_rgbo = mip_net.forward(NeRF.length2pts(coarse_cam_rays, fine_lengths))
+            fine_rendered, weights, _ = NeRF.render(fine_rgbo, fine_lengths, coarse_cam_rays[:, 3:])
+            weight_bounds = getBounds(prop_weights, below_idxs)
+            opt.zero_grad()
+            loss = prop_loss_func(weight_bounds, weights.detach()) + loss_func(fine_rendered, rgb_targets)
+            loss.backward()
+            opt.step()
+            return loss
+        for i in range(3):
+            step(i)
+        torch.cuda.synchronize(dev)
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        t0 = time.perf_counter()
+        for i in range(steps):
+            ev[i][0].record()
+            loss = step(10 + i)
+            ev[i][1].record()
+        torch.cuda.synchronize(dev)
+        wall = (time.perf_counter() - t0) / steps
+        ms = sum(a.elapsed_time(b) for a, b in ev) / steps
+        flop = 3 * (FLOP_PROP_PER_RAY + FLOP_NERF_PER_RAY) * R
+        # the reference algorithm's step as PyTorch ops on this GPU
+        sp, sn = O.params_to(sd_prop, dev), O.params_to(sd_nerf, dev)
+        cs, cl, rt, cr = nerf_b200.validSampler(rgbs, coords, cam_tf, R, N_COARSE, focal, NEAR, FAR, True)
+        u = torch.rand(R, N_FINE + 1, device=dev)
+        tf32 = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = False
+        O.train_step(sp, sn, cs, cl, rt, cr, u)
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            O.train_step(sp, sn, cs, cl, rt, cr, u)
+        torch.cuda.synchronize(dev)
+        ref_ms = 1e3 * (time.perf_counter() - t0) / 3
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        out[f"rays_{R}"] = {
+            "rays_per_step": R, "ms_per_step": ms, "host_ms_per_step": 1e3 * wall, "rays_per_s": R / (ms * 1e-3), "loss": float(loss),
+            "roofline": {"bound": "hbm", "achieved": bytes_per_ray * R / (ms * 1e-3) / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
+                         "frac": bytes_per_ray * R / (ms * 1e-3) / 1e9 / peaks["hbm"], "algorithmic_bytes_per_step": bytes_per_ray * R,
+                         "algorithmic_flop_per_step": flop, "tensor_tflops": flop / (ms * 1e-3) / 1e12,
+                         "frac_of_tensor_peak": flop / (ms * 1e-3) / 1e12 / peaks["tflops"],
+                         "frac_of_tensor_peak_issued": passes * flop / (ms * 1e-3) / 1e12 / peaks["tflops"]},
+            "torch_cuda_fp32_ms_per_step": ref_ms, "speedup_vs_torch_cuda_fp32": ref_ms / ms}
+    return out
+
+
 def parity_leg(dev, pose, H, W, focal, base_z, ids, precisions):
     """The ray-by-ray parity theorem (tests/parity_tools.py) on 8,192 rays of the timed view, plus PSNR figures."""
     from nerf_b200 import ops
@@ -480,6 +576,7 @@ def main():
         with torch.no_grad():
             line["parity_vs_oracle"] = parity_leg(dev, scene.pose, H, Wd, scene.focal, base_z, ids, list(dict.fromkeys([args.precision, "bf16", "fp16"])))
         line["torch_cuda_baseline"] = torch_cuda_baseline(dev, 400, 400)
+        line["train_step"] = train_step_leg(dev)
         cores = os.cpu_count() or 1
         cpu_v, cpu_t = cpu_reference_render(2, 1, cores)
         line["cpu_baseline"] = {"value": cpu_v, "unit": "rays/s", "cores": cores, "kind": "port",

@@ -242,6 +242,7 @@ int nb2_render_rays(nb2_handle* h, const nb2_render_params* p, const float* rays
  *   nn.Linear forward   Y  = X W^T     A = X (0), B = W (0)            reference: every F.linear of nerf/mip_model.py:53-59,
  *   its dgrad           dX = dY W      A = dY (0), B = W (1)                      nerf/addtional.py:92-96, nerf/ref_model.py:76-105
  *   its wgrad           dW = dY^T X    A = dY (1), B = X (1), splits > 1          (autograd's addmm backward in train.py:206)
+ *   its bias gradient   db = dY^T 1    the same with B = a column of ones
  * Segments concatenate along K: the passes of the split precision (x = hi + lo: lo*hi, hi*lo, hi*hi) and torch.cat inputs.
  * Epilogue: + bias[n]; act 0 none | 1 relu | 2 sigmoid; * (mask[m][n] > 0) (relu backward on a saved activation);
  * outputs fp32 (ld_f32) and / or bf16 hi (+ lo residual) (ld_16).  splits > 1: split-K over M-tile x N-tile x split work
@@ -282,9 +283,6 @@ int nb2_to_bf16(nb2_handle* h, const float* src, int64_t rows, int cols, int64_t
 /* out[m][c] (=|+=) sum_s ws[s * split_stride + m * ld_ws + perm(c)]: second stage of the split-K wgrad. */
 int nb2_reduce_splits(nb2_handle* h, const float* ws, int splits, int64_t split_stride, int rows, int cols, int ld_ws,
                       const int* col_perm, float* out, int ld_out, int accumulate, void* stream);
-/* out[c] (=|+=) sum over rows of hi[r][c] (+ lo[r][c]): bias gradients. */
-int nb2_colsum_bf16(nb2_handle* h, const void* hi, const void* lo, int64_t rows, int cols, int ld, float* out, int accumulate,
-                    void* stream);
 
 /* ---- training step, HBM-bound pieces: encodings as GEMM operands and the backward of the ray ops --------
  * In the reference these are autograd's derivatives of the torch ops the functions are written in (train.py:206).

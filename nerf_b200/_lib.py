@@ -79,7 +79,6 @@ SIGNATURES = {
     "nb2_gemm_bf16": (c_int, [c_vp, ctypes.POINTER(GemmDesc), c_vp]),
     "nb2_to_bf16": (c_int, [c_vp, c_f32p, c_i64, c_int, c_i64, c_vp, c_vp, c_vp, c_int, c_vp]),
     "nb2_reduce_splits": (c_int, [c_vp, c_f32p, c_int, c_i64, c_int, c_int, c_int, c_vp, c_f32p, c_int, c_int, c_vp]),
-    "nb2_colsum_bf16": (c_int, [c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_f32p, c_int, c_vp]),
     "nb2_encode_bf16": (c_int, [c_vp, c_f32p, c_int, c_int, c_i64, c_int, c_int, c_vp, c_vp, c_i64, c_int, c_vp]),
     "nb2_weights_from_sigma_backward": (c_int, [c_vp, c_f32p, c_f32p, c_f32p, c_int, c_i64, c_int, c_int, c_f32p, c_f32p, c_vp]),
     "nb2_composite_backward": (c_int, [c_vp, c_f32p, c_f32p, c_f32p, c_int, c_i64, c_int, c_int, c_f32p, c_f32p, c_f32p, c_vp]),

@@ -15,7 +15,8 @@
 //
 // Kernel (persistent, one CTA per SM, cta_group::1, 128 x BN output tile, K chunks of 64):
 //   warps 0-3   epilogue: TMEM accumulator (two buffers, so tile i+1 accumulates while tile i drains) -> bias / act /
-//               relu-mask -> bf16 hi (+ lo residual) and / or fp32 rows, 64-128 B contiguous per thread
+//               relu-mask -> bf16 hi (+ lo residual) and / or fp32 rows, transposed through a swizzled staging tile so
+//               that every global store / mask load instruction covers whole 128-byte rows
 //   warps 4-7   producers: 16-byte cp.async copies of row-major global blocks into the 128-byte-swizzled shared-memory
 //               layout both operand kinds share ([rows][64 elements], 16-byte unit index XOR (row & 7)); bounds are
 //               zero-filled; a stage is published to the async proxy (fence.proxy.async) two stages behind the issue
@@ -34,7 +35,9 @@ constexpr int kGABytes = 128 * 128;         // A operand stage: 128 rows x 64 bf
 constexpr int kGBBytes = 256 * 128;         // B operand stage: up to 256 rows (K-major) or 4 blocks of 64 x 64 (MN-major)
 constexpr int kGStageBytes = kGABytes + kGBBytes;
 constexpr int kGThreads = 288;
-constexpr int kGSmem = kGStages * kGStageBytes + 1024 /* barriers */ + 1024 /* alignment slack */;
+constexpr int kGStagingBytes = 4 * 8192;   // epilogue: per warp 32 rows x 128 B x 2 (hi / fp32 rows, lo / mask rows)
+constexpr int kGSmem = kGStages * kGStageBytes + kGStagingBytes + 1024 /* barriers */ + 1024 /* alignment slack */;
+static_assert(kGSmem <= 232448, "exceeds 227 KB of shared memory");
 
 struct GemmBars {
   uint64_t full[kGStages];
@@ -110,7 +113,8 @@ __global__ void __launch_bounds__(kGThreads, 1) gemm_bf16_kernel(const __grid_co
   extern __shared__ unsigned char smem_dyn[];
   const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   unsigned char* smem_al = smem_dyn + (smem_base - smem_u32(smem_dyn));
-  GemmBars* bars = reinterpret_cast<GemmBars*>(smem_al + kGStages * kGStageBytes);
+  GemmBars* bars = reinterpret_cast<GemmBars*>(smem_al + kGStages * kGStageBytes + kGStagingBytes);
+  const uint32_t stg_base = smem_base + kGStages * kGStageBytes;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const nb2_gemm_desc& d = p.d;
   const int splits = d.splits > 1 ? d.splits : 1;
@@ -249,56 +253,108 @@ __global__ void __launch_bounds__(kGThreads, 1) gemm_bf16_kernel(const __grid_co
       __syncwarp();
       tc_fence_after();
       float* out32 = d.out_f32 ? d.out_f32 + (int64_t)split * d.split_stride : nullptr;
-      for (int cb = 0; cb < p.bn / 32; ++cb) {
-        uint32_t r[32];
-        tmem_ld32(lane_addr + buf * 256 + cb * 32, r);
-        tmem_ld_wait();
+      // Global accesses go through a warp-private shared-memory staging tile (32 rows x 128 B, 128-byte swizzle) so that
+      // consecutive lanes touch consecutive 16-byte units of a row: one thread owns one accumulator ROW (TMEM lane), and
+      // row-per-lane stores / mask loads cost one 128-byte line request per lane per instruction (measured: the first
+      // version of this kernel spent 30 us per 128-row tile in them).  Unaligned / odd shapes take the scalar path.
+      const bool vec16 = d.out_hi && (d.ld_16 & 7) == 0 && (d.N & 7) == 0 && ((reinterpret_cast<uintptr_t>(d.out_hi) & 15) == 0) &&
+                         (!d.out_lo || (reinterpret_cast<uintptr_t>(d.out_lo) & 15) == 0);
+      const bool vecm = d.mask && (d.ld_mask & 7) == 0 && (d.N & 7) == 0 && ((reinterpret_cast<uintptr_t>(d.mask) & 15) == 0);
+      const bool vec32 = out32 && !d.out_hi && (d.ld_f32 & 3) == 0 && (d.N & 3) == 0 && ((reinterpret_cast<uintptr_t>(out32) & 15) == 0);
+      const int64_t row0 = (int64_t)m_tile * 128 + warp * 32;
+      const uint32_t stg = stg_base + (uint32_t)warp * 8192u;        // [0, 4096): hi / fp32 rows, [4096, 8192): lo rows / mask rows
+      auto sw = [](int r, int ch) { return (uint32_t)r * 128u + (uint32_t)((ch ^ (r & 7)) << 4); };
+      const __nv_bfloat16* mask = reinterpret_cast<const __nv_bfloat16*>(d.mask);
+      __nv_bfloat16* out_hi = reinterpret_cast<__nv_bfloat16*>(d.out_hi);
+      __nv_bfloat16* out_lo = reinterpret_cast<__nv_bfloat16*>(d.out_lo);
+      for (int cb = 0; cb < p.bn / 32; cb += 2) {
+        const int nb = (cb + 1 < p.bn / 32) ? 2 : 1;          // 32-column blocks in this pass (64 columns = one 128-byte bf16 row)
+        const int sh = nb == 2 ? 3 : 2;                       // 16-byte units per bf16 row of the pass: 8 or 4
         const int64_t c0 = n0 + cb * 32;
-        if (row < d.M && c0 < d.N) {
-          const int nv = (int)(d.N - c0 < 32 ? d.N - c0 : 32);
+        if (vecm) {
+          for (int q = lane; q < (32 << sh); q += 32) {
+            const int r = q >> sh, ch = q & ((1 << sh) - 1);
+            const int64_t grow = row0 + r, gcol = c0 + 8 * ch;
+            uint4 m = make_uint4(0u, 0u, 0u, 0u);
+            if (grow < d.M && gcol < d.N) m = __ldg(reinterpret_cast<const uint4*>(mask + grow * d.ld_mask + gcol));
+            st_shared_v4(stg + 4096u + sw(r, ch), m.x, m.y, m.z, m.w);
+          }
+          __syncwarp();
+        }
+        uint32_t ra[32], rb[32];
+        tmem_ld32(lane_addr + buf * 256 + cb * 32, ra);
+        if (nb == 2) tmem_ld32(lane_addr + buf * 256 + cb * 32 + 32, rb);
+        tmem_ld_wait();
+#pragma unroll
+        for (int hb = 0; hb < 2; ++hb) {
+          if (hb >= nb) break;
+          const int64_t cc = c0 + 32 * hb;
+          const int nv = (int)(d.N - cc < 32 ? (d.N - cc > 0 ? d.N - cc : 0) : 32);
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            float x = empty_k ? 0.f : __uint_as_float(r[j]);
-            if (d.bias != nullptr && j < nv) x += __ldg(d.bias + c0 + j);
+            float x = empty_k ? 0.f : __uint_as_float(hb ? rb[j] : ra[j]);
+            if (d.bias != nullptr && j < nv) x += __ldg(d.bias + cc + j);
             if (d.act == 1) x = fmaxf(x, 0.f);
             else if (d.act == 2) x = 1.f / (1.f + expf(-x));
             v[j] = x;
           }
-          if (d.mask != nullptr) {
-            const __nv_bfloat16* mrow = reinterpret_cast<const __nv_bfloat16*>(d.mask) + row * d.ld_mask + c0;
+          if (vecm) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              uint32_t m[4];
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(m[0]), "=r"(m[1]), "=r"(m[2]), "=r"(m[3])
+                           : "r"(stg + 4096u + sw(lane, 4 * hb + k)));
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                if (!(bf16_lo_to_f32(m[e]) > 0.f)) v[8 * k + 2 * e] = 0.f;
+                if (!(bf16_hi_to_f32(m[e]) > 0.f)) v[8 * k + 2 * e + 1] = 0.f;
+              }
+            }
+          } else if (mask != nullptr && row < d.M) {
+            const __nv_bfloat16* mrow = mask + row * d.ld_mask + cc;
 #pragma unroll
             for (int j = 0; j < 32; ++j)
               if (j < nv && !(__bfloat162float(mrow[j]) > 0.f)) v[j] = 0.f;
           }
-          if (out32 != nullptr) {
-            float* o = out32 + row * d.ld_f32 + c0;
-            if (nv == 32 && (d.ld_f32 & 3) == 0 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+          if (vec32) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) reinterpret_cast<float4*>(o)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (j < nv) o[j] = v[j];
+            for (int k = 0; k < 8; ++k)
+              st_shared_v4(stg + sw(lane, k), __float_as_uint(v[4 * k]), __float_as_uint(v[4 * k + 1]), __float_as_uint(v[4 * k + 2]),
+                           __float_as_uint(v[4 * k + 3]));
+            __syncwarp();
+            for (int q = lane; q < 256; q += 32) {
+              const int r = q >> 3, ch = q & 7;
+              const int64_t grow = row0 + r, gcol = cc + 4 * ch;
+              if (grow < d.M && gcol < d.N) {
+                uint4 x;
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x.x), "=r"(x.y), "=r"(x.z), "=r"(x.w) : "r"(stg + sw(r, ch)));
+                *reinterpret_cast<uint4*>(out32 + grow * d.ld_f32 + gcol) = x;
+              }
             }
+            __syncwarp();
+          } else if (out32 != nullptr && row < d.M) {
+            float* o = out32 + row * d.ld_f32 + cc;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < nv) o[j] = v[j];
           }
-          if (d.out_hi != nullptr) {
-            __nv_bfloat16* oh = reinterpret_cast<__nv_bfloat16*>(d.out_hi) + row * d.ld_16 + c0;
-            __nv_bfloat16* ol = d.out_lo ? reinterpret_cast<__nv_bfloat16*>(d.out_lo) + row * d.ld_16 + c0 : nullptr;
+          if (out_hi != nullptr) {
             uint32_t hi[16], lo[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               hi[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
               lo[j] = pack_bf16x2(v[2 * j] - bf16_lo_to_f32(hi[j]), v[2 * j + 1] - bf16_hi_to_f32(hi[j]));
             }
-            if (nv == 32 && (d.ld_16 & 7) == 0 && ((reinterpret_cast<uintptr_t>(oh) & 15) == 0)) {
+            if (vec16) {
 #pragma unroll
-              for (int j = 0; j < 4; ++j) reinterpret_cast<uint4*>(oh)[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-              if (ol != nullptr) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) reinterpret_cast<uint4*>(ol)[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+              for (int k = 0; k < 4; ++k) {
+                st_shared_v4(stg + sw(lane, 4 * hb + k), hi[4 * k], hi[4 * k + 1], hi[4 * k + 2], hi[4 * k + 3]);
+                if (out_lo != nullptr) st_shared_v4(stg + 4096u + sw(lane, 4 * hb + k), lo[4 * k], lo[4 * k + 1], lo[4 * k + 2], lo[4 * k + 3]);
               }
-            } else {
+            } else if (row < d.M) {
+              __nv_bfloat16* oh = out_hi + row * d.ld_16 + cc;
+              __nv_bfloat16* ol = out_lo ? out_lo + row * d.ld_16 + cc : nullptr;
 #pragma unroll
               for (int j = 0; j < 32; ++j)
                 if (j < nv) {
@@ -311,6 +367,23 @@ __global__ void __launch_bounds__(kGThreads, 1) gemm_bf16_kernel(const __grid_co
                 }
             }
           }
+        }
+        if (vec16) {
+          __syncwarp();
+          for (int q = lane; q < (32 << sh); q += 32) {
+            const int r = q >> sh, ch = q & ((1 << sh) - 1);
+            const int64_t grow = row0 + r, gcol = c0 + 8 * ch;
+            if (grow < d.M && gcol < d.N) {
+              uint4 x;
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x.x), "=r"(x.y), "=r"(x.z), "=r"(x.w) : "r"(stg + sw(r, ch)));
+              *reinterpret_cast<uint4*>(out_hi + grow * d.ld_16 + gcol) = x;
+              if (out_lo != nullptr) {
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x.x), "=r"(x.y), "=r"(x.z), "=r"(x.w) : "r"(stg + 4096u + sw(r, ch)));
+                *reinterpret_cast<uint4*>(out_lo + grow * d.ld_16 + gcol) = x;
+              }
+            }
+          }
+          __syncwarp();
         }
       }
       tc_fence_before();
@@ -364,28 +437,6 @@ __global__ void reduce_splits_kernel(const float* __restrict__ ws, int splits, i
     for (int s = 0; s < splits; ++s) acc += ws[(int64_t)s * split_stride + (int64_t)m * ld_ws + wc];
     float* o = out + (int64_t)m * ld_out + c;
     *o = accumulate ? *o + acc : acc;
-  }
-}
-
-// out[c] = sum over rows of (hi[r][c] + lo[r][c]) : the bias gradient.  One block per 32 columns, fp32 tree per block.
-__global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo, int64_t rows,
-                                                     int cols, int ld, float* __restrict__ out, int accumulate) {
-  __shared__ float part[8][32];
-  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
-  const int w = threadIdx.x >> 5;
-  float acc = 0.f;
-  if (c < cols)
-    for (int64_t r = w; r < rows; r += 8) {
-      acc += __bfloat162float(hi[r * ld + c]);
-      if (lo) acc += __bfloat162float(lo[r * ld + c]);
-    }
-  part[w][threadIdx.x & 31] = acc;
-  __syncthreads();
-  if (w == 0 && c < cols) {
-    float s = 0.f;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) s += part[k][threadIdx.x];
-    out[c] = accumulate ? out[c] + s : s;
   }
 }
 
@@ -454,15 +505,6 @@ extern "C" int nb2_reduce_splits(nb2_handle* h, const float* ws, int splits, int
   const int64_t n = (int64_t)rows * cols;
   const int blocks = (int)std::min<int64_t>((n + 255) / 256, (int64_t)h->sm_count * 8);
   reduce_splits_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(ws, splits, split_stride, rows, cols, ld_ws, col_perm, out, ld_out, accumulate);
-  NB2_LAUNCH_CHECK(h);
-  return NB2_OK;
-}
-
-extern "C" int nb2_colsum_bf16(nb2_handle* h, const void* hi, const void* lo, int64_t rows, int cols, int ld, float* out, int accumulate,
-                               void* stream) {
-  NB2_ENTER(h);
-  NB2_CHECK_ARG(hi && out && rows >= 0 && cols > 0 && ld >= cols, "colsum: bad arguments");
-  colsum_kernel<<<(cols + 31) / 32, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)hi, (const __nv_bfloat16*)lo, rows, cols, ld, out, accumulate);
   NB2_LAUNCH_CHECK(h);
   return NB2_OK;
 }

@@ -74,9 +74,3 @@ def reduce_splits(ws, splits, split_stride, rows, cols, ld_ws, out, col_perm=Non
     dev = ws.device
     check(load().nb2_reduce_splits(handle(dev), ws.data_ptr(), splits, split_stride, rows, cols, ld_ws, _lib.ptr_int(col_perm),
                                    out.data_ptr(), out.stride(0) if out.dim() == 2 else cols, 1 if accumulate else 0, stream_ptr(dev)))
-
-
-def colsum(hi, lo, cols, out, accumulate=False):
-    dev = hi.device
-    check(load().nb2_colsum_bf16(handle(dev), hi.data_ptr(), _lib.ptr_int(lo), hi.shape[0], cols, hi.stride(0), out.data_ptr(),
-                                 1 if accumulate else 0, stream_ptr(dev)))

@@ -10,7 +10,7 @@ converted or transposed in between:
     forward   H_{l+1} = relu(H_l W_l^T + b_l)                 A = H_l (K-major),   B = W_l (K-major)
     dgrad     dH_l    = (dH_{l+1} W_l) * (H_l > 0)            A = dH_{l+1},        B = W_l (MN-major)   relu mask = saved H_l
     wgrad     dW_l    = dH_{l+1}^T H_l                        A = dH_{l+1} (MN),   B = H_l (MN), split-K + deterministic reduce
-    bgrad     db_l    = column sums of dH_{l+1}
+    bgrad     db_l    = dH_{l+1}^T 1                          the wgrad GEMM against a column of ones
 
 torch.cat inputs of the reference (mip_model.py:55 skip connection, :59 bottleneck + encoded direction) are column ranges
 of one wider buffer; the matching weight columns are permuted once when the weights are converted, and the gradient is
@@ -95,6 +95,33 @@ class _Workspace:
         return b
 
 
+class _Ones:
+    """(rows, 8) bf16 with column 0 = 1: the B operand that turns the wgrad GEMM into the bias gradient (column sums of dY)."""
+    bufs = {}
+
+    @classmethod
+    def get(cls, dev, rows):
+        b = cls.bufs.get(dev)
+        if b is None or b.shape[0] < rows:
+            b = torch.zeros((rows, 8), dtype=BF16, device=dev)
+            b[:, 0] = 1.0
+            cls.bufs[dev] = b
+        return b[:rows]
+
+
+def bgrad(dy, n_out, rows, x3, grad_b, sm_count=148):
+    """grad_b (n_out,) fp32 = column sums of dy over `rows` samples, as dy^T @ ones on the tensor cores (split-K, deterministic)."""
+    dev = dy[0].device
+    ones = _Ones.get(dev, rows)
+    m_pad = (n_out + 127) // 128 * 128
+    splits = max(1, min(sm_count // (m_pad // 128), (rows + 255) // 256))
+    ws = _Workspace.get(dev, splits * m_pad * 32)
+    out = ws[: splits * m_pad * 32].view(splits * m_pad, 32)
+    segs = [(dy[0], True, ones, True, rows)] + ([(dy[1], True, ones, True, rows)] if x3 else [])
+    linear.gemm(n_out, 8, segs, out_f32=out[:n_out], splits=splits, split_stride=m_pad * 32)
+    linear.reduce_splits(ws, splits, m_pad * 32, n_out, 1, 32, grad_b.view(n_out, 1))
+
+
 def wgrad(dy, x, n_out, n_in, rows, x3, grad_w, perm=None, sm_count=148):
     """grad_w (n_out, n_in) fp32 = dy^T x over `rows` samples; dy (rows, >= n_out), x (rows, ld >= n_in) as (hi, lo)."""
     dev = x[0].device
@@ -157,7 +184,7 @@ class ProposalEngine:
         gw = torch.empty_like(self.lins[4].weight)
         gb = torch.empty_like(self.lins[4].bias)
         wgrad(ds, acts[4], 1, H, n, x3, gw, sm_count=sm)
-        linear.colsum(ds[0], ds[1], 1, gb)
+        bgrad(ds, 1, n, x3, gb, sm_count=sm)
         grads[4] = (gw, gb)
         dy = _empty16(n, H, dev, x3)
         linear.gemm(n, H, _dgrad_segs(ds, (W[4].hi, W[4].lo), 1, x3), mask=acts[4][0], out_hi=dy[0], out_lo=dy[1])
@@ -167,7 +194,7 @@ class ProposalEngine:
             gw = torch.empty_like(self.lins[l].weight)
             gb = torch.empty_like(self.lins[l].bias)
             wgrad(dy, x, H, in_f, n, x3, gw, sm_count=sm)
-            linear.colsum(dy[0], dy[1], H, gb)
+            bgrad(dy, H, n, x3, gb, sm_count=sm)
             grads[l] = (gw, gb)
             if l > 0:
                 dx = _empty16(n, H, dev, x3)
@@ -240,7 +267,7 @@ class NerfEngine:
         def wg(i, dy, x, n_out, n_in, perm=None):
             gw, gb = torch.empty_like(self.lins[i].weight), torch.empty_like(self.lins[i].bias)
             wgrad(dy, x, n_out, n_in, n, x3, gw, perm=perm, sm_count=sm)
-            linear.colsum(dy[0], dy[1], n_out, gb)
+            bgrad(dy, n_out, n, x3, gb, sm_count=sm)
             grads[i] = (gw, gb)
 
         dz, ds = _empty16(n, 8, dev, x3), _empty16(n, 8, dev, x3)

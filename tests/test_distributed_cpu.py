@@ -72,3 +72,39 @@ def test_two_rank_gather_equals_single_rank():
                         2.0, 6.0, n_fine=32, white_bkg=True)["rgb"]
     assert img2.shape == (n_rays, 3)
     assert float((img2 - ref).abs().max()) < 1e-5
+
+
+def _grad_worker(rank, world, port, q):
+    """ddp_train.py:98 wraps mip_net in DistributedDataParallel, whose one collective is the gradient all-reduce; the engine's
+    flat equivalent (train_engine.allreduce_gradients) on two gloo ranks: every rank ends with the average."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import nerf_b200
+    from nerf_b200.train_engine import allreduce_gradients
+    torch.manual_seed(0)
+    net = nerf_b200.MipNeRF(10, 4, 256)
+    for i, p in enumerate(net.parameters()):
+        p.grad = torch.full_like(p, float(rank + 1)) * (i + 1)
+    n = allreduce_gradients([net])
+    ok = n == 530052 and all(torch.allclose(p.grad, torch.full_like(p, 1.5 * (i + 1))) for i, p in enumerate(net.parameters()))
+    # and DistributedDataParallel itself accepts the module (the reference's call surface)
+    ddp = torch.nn.parallel.DistributedDataParallel(net)
+    ok = ok and ddp.module is net
+    q.put((rank, bool(ok), n))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_flat_gradient_allreduce_two_ranks():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_grad_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=300) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=300)
+        assert p.exitcode == 0
+    assert all(ok for _, ok, _ in got) and all(n == 530052 for _, _, n in got), got

@@ -86,15 +86,19 @@ def test_wgrad_shape(rows, N_out, K_in, splits):
     assert torch.equal(out, again)          # no atomics: bit-reproducible
 
 
-def test_to_bf16_permutation_and_colsum():
+def test_to_bf16_permutation():
     W = rnd((256, 319), 5)
     perm = torch.cat((torch.arange(63) + 256, torch.arange(256))).to(torch.int32).to(DEV)     # [enc | hidden] -> [hidden | enc]
     hi, lo = linear.to_bf16(W, ld_dst=320, col_perm=perm)
     back = (hi.float() + lo.float())
     assert float((back[:, 256:319] - W[:, :63]).abs().max()) < 1e-4 and float((back[:, :256] - W[:, 63:]).abs().max()) < 1e-4
     assert float(back[:, 319].abs().max()) == 0.0
+
+
+def test_bias_gradient_as_ones_gemm():
+    from nerf_b200.train_engine import bgrad
     x = rnd((5000, 256), 6)
     xh, xl = linear.to_bf16(x)
     s = torch.empty(256, device=DEV)
-    linear.colsum(xh, xl, 256, s)
+    bgrad((xh, xl), 256, 5000, True, s)
     close(s, x.sum(0), 2e-4)
