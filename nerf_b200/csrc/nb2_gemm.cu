@@ -14,15 +14,23 @@
 // (skip connection, bottleneck + encoded direction) are just more segments accumulating into the same tile.
 //
 // Kernel (persistent, one CTA per SM, cta_group::1, 128 x BN output tile, K chunks of 64):
-//   warps 0-3   epilogue: TMEM accumulator (two buffers, so tile i+1 accumulates while tile i drains) -> bias / act /
+//   warps 0-3, 6-9   epilogue, one group of four warps per accumulator buffer (two tiles drain at once while a third
+//               accumulates... the MMA warp waits for a buffer's group): TMEM accumulator -> bias / act /
 //               relu-mask -> bf16 hi (+ lo residual) and / or fp32 rows, transposed through a swizzled staging tile so
 //               that every global store / mask load instruction covers whole 128-byte rows
-//   warps 4-7   producers: 16-byte cp.async copies of row-major global blocks into the 128-byte-swizzled shared-memory
-//               layout both operand kinds share ([rows][64 elements], 16-byte unit index XOR (row & 7)); bounds are
-//               zero-filled; a stage is published to the async proxy (fence.proxy.async) two stages behind the issue
-//   warp 8      TMEM allocation + MMA issue (tcgen05.mma.kind::f16, M128 x BN x K16), tcgen05.commit frees stages
+//   warp 4      producer: one elected thread issues TMA tensor copies (cp.async.bulk.tensor.2d, SWIZZLE_128B tensor maps
+//               built on the host per operand) of [rows][64 elements] boxes of the row-major global matrices into the
+//               shared-memory layout both operand kinds share; out-of-bounds rows / columns are zero-filled by the TMA
+//               unit; completion is counted in bytes on the stage's mbarrier.  (The first version used 128 threads of
+//               16-byte cp.async copies and measured 15 B/cycle/SM; the TMA unit sustains ~60.)
+//   warp 5      TMEM allocation + MMA issue (tcgen05.mma.kind::f16, M128 x BN x K16), tcgen05.commit frees stages
 // The kernel is HBM-bound for the network's 256-wide layers (a 128 x 256 tile reads 64 KB and writes 64-128 KB for
 // 2048 tensor cycles); its roofline is the measured copy bandwidth, DESIGN.md section 12.
+#include <cuda.h>
+
+#include <mutex>
+#include <unordered_map>
+
 #include "nb2_common.cuh"
 #include "nb2_tc_ptx.cuh"
 
@@ -30,12 +38,11 @@ namespace nb2 {
 using namespace ptx;
 
 constexpr int kGStages = 4;
-constexpr int kGLag = 2;                    // a stage is published kGLag issues after its copies were started
 constexpr int kGABytes = 128 * 128;         // A operand stage: 128 rows x 64 bf16 (K-major) or 2 blocks of 64 x 64 (MN-major)
 constexpr int kGBBytes = 256 * 128;         // B operand stage: up to 256 rows (K-major) or 4 blocks of 64 x 64 (MN-major)
 constexpr int kGStageBytes = kGABytes + kGBBytes;
-constexpr int kGThreads = 288;
-constexpr int kGStagingBytes = 4 * 8192;   // epilogue: per warp 32 rows x 128 B x 2 (hi / fp32 rows, lo / mask rows)
+constexpr int kGThreads = 320;            // warps 0-3 / 6-9: epilogue groups 0 / 1; warp 4: TMA producer; warp 5: MMA issuer
+constexpr int kGStagingBytes = 8 * 4096;   // epilogue: per warp one 32 rows x 128 B staging tile (mask, hi, lo / fp32 rows in turn)
 constexpr int kGSmem = kGStages * kGStageBytes + kGStagingBytes + 1024 /* barriers */ + 1024 /* alignment slack */;
 static_assert(kGSmem <= 232448, "exceeds 227 KB of shared memory");
 
@@ -48,18 +55,20 @@ struct GemmBars {
 };
 
 struct GemmKParams {
+  CUtensorMap amap[NB2_GEMM_MAX_SEG];   // per segment: A as [rows][cols] row-major, box 64 columns x (128 | 64) rows
+  CUtensorMap bmap[NB2_GEMM_MAX_SEG];   // per segment: B, box 64 columns x (bn | 64) rows
   nb2_gemm_desc d;
   int bn;                 // N tile (multiple of 32, <= 256)
   int m_tiles, n_tiles;
   int64_t k_per_split;    // rows of K per split (multiple of 64); splits == 1: unused
 };
 
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
-  const uint32_t sz = valid ? 16u : 0u;
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+// TMA: one [box rows][64 columns] box of a 2-D tensor map -> shared memory (128-byte swizzle), bytes counted on `bar`
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int col, int row, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(dst), "l"(map), "r"(col), "r"(row), "r"(bar)
+               : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // D (128 x N, fp32, TMEM) (+)= A (smem) * B^T (smem), single CTA
 __device__ __forceinline__ void umma1_elect(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -96,19 +105,6 @@ __device__ __forceinline__ uint32_t gemm_idesc(int N, bool a_mn, bool b_mn) {
          ((uint32_t)(128 >> 4) << 24);
 }
 
-// Copy `rows` x 64 bf16 of a row-major matrix (element (r, c) at ptr[r * ld + c]) starting at (row0, col0) into a
-// [rows][128 B] shared-memory block with the 128-byte swizzle; rows >= row_lim / columns >= col_lim are zero-filled.
-__device__ __forceinline__ void load_block(uint32_t dst, const __nv_bfloat16* __restrict__ ptr, int64_t ld, int64_t row0, int rows,
-                                           int64_t row_lim, int64_t col0, int64_t col_lim, int tid) {
-  for (int c = tid; c < rows * 8; c += 128) {
-    const int r = c >> 3, ch = c & 7;
-    const int64_t gr = row0 + r, gc = col0 + 8 * ch;
-    const bool ok = (gr < row_lim) && (gc < col_lim);
-    const __nv_bfloat16* src = ok ? ptr + gr * ld + gc : ptr;
-    cp_async16(dst + (uint32_t)r * 128u + (uint32_t)((ch ^ (r & 7)) << 4), src, ok);
-  }
-}
-
 __global__ void __launch_bounds__(kGThreads, 1) gemm_bf16_kernel(const __grid_constant__ GemmKParams p) {
   extern __shared__ unsigned char smem_dyn[];
   const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
@@ -122,7 +118,7 @@ __global__ void __launch_bounds__(kGThreads, 1) gemm_bf16_kernel(const __grid_co
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kGStages; ++i) {
-      mbar_init(smem_u32(&bars->full[i]), 4);      // one arrival per producer warp
+      mbar_init(smem_u32(&bars->full[i]), 1);      // the producer's arrive.expect_tx; the TMA unit completes the bytes
       mbar_init(smem_u32(&bars->empty[i]), 1);     // tcgen05.commit
     }
     for (int i = 0; i < 2; ++i) {
@@ -131,7 +127,7 @@ __global__ void __launch_bounds__(kGThreads, 1) gemm_bf16_kernel(const __grid_co
     }
     mbar_fence_init();
   }
-  if (warp == 8) {
+  if (warp == 5) {
     tmem_alloc(smem_u32(&bars->tmem_base), 512);
     tmem_relinquish();
   }
@@ -151,54 +147,44 @@ __global__ void __launch_bounds__(kGThreads, 1) gemm_bf16_kernel(const __grid_co
     }
   };
 
-  if (warp >= 4 && warp < 8) {
-    // =========================================== producers ===========================================
-    const int tid = threadIdx.x - 128;
-    uint32_t issued = 0, published = 0;
-    auto publish = [&]() {
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&bars->full[published % kGStages]));
-      ++published;
-    };
-    for (int64_t it = blockIdx.x; it < n_items; it += gridDim.x) {
-      const int m_tile = (int)(it % p.m_tiles);
-      const int n_tile = (int)((it / p.m_tiles) % p.n_tiles);
-      const int split = (int)(it / ((int64_t)p.m_tiles * p.n_tiles));
-      const int64_t m0 = (int64_t)m_tile * 128, n0 = (int64_t)n_tile * p.bn;
-      for (int s = 0; s < d.n_seg; ++s) {
-        const nb2_gemm_operand& A = d.seg[s].a;
-        const nb2_gemm_operand& B = d.seg[s].b;
-        int64_t k0, k1;
-        k_range(s, split, k0, k1);
-        for (int64_t k = k0; k < k1; k += 64) {
-          const uint32_t stage = issued % kGStages;
-          if (issued >= kGStages) mbar_wait(smem_u32(&bars->empty[stage]), ((issued / kGStages) - 1) & 1u);
-          const uint32_t a_dst = smem_base + stage * kGStageBytes, b_dst = a_dst + kGABytes;
-          const __nv_bfloat16* ap = reinterpret_cast<const __nv_bfloat16*>(A.ptr);
-          const __nv_bfloat16* bp = reinterpret_cast<const __nv_bfloat16*>(B.ptr);
-          if (!A.mn_major) {
-            load_block(a_dst, ap, A.ld, m0, 128, d.M, k, k1, tid);
-          } else {
-            for (int j = 0; j < 2; ++j) load_block(a_dst + j * 8192, ap, A.ld, k, 64, k1, m0 + 64 * j, d.M, tid);
-          }
-          if (!B.mn_major) {
-            load_block(b_dst, bp, B.ld, n0, p.bn, d.N, k, k1, tid);
-          } else {
-            for (int j = 0; j < (p.bn + 63) / 64; ++j) load_block(b_dst + j * 8192, bp, B.ld, k, 64, k1, n0 + 64 * j, d.N, tid);
-          }
-          cp_async_commit();
-          ++issued;
-          if (issued - published > kGLag) {
-            cp_async_wait<kGLag>();
-            publish();
+  if (warp == 4) {
+    // =========================================== producer (one thread drives the TMA unit) ===========================
+    if (lane == 0) {
+      uint32_t issued = 0;
+      for (int64_t it = blockIdx.x; it < n_items; it += gridDim.x) {
+        const int m_tile = (int)(it % p.m_tiles);
+        const int n_tile = (int)((it / p.m_tiles) % p.n_tiles);
+        const int split = (int)(it / ((int64_t)p.m_tiles * p.n_tiles));
+        const int m0 = m_tile * 128, n0 = n_tile * p.bn;
+        for (int s = 0; s < d.n_seg; ++s) {
+          const bool a_mn = d.seg[s].a.mn_major != 0, b_mn = d.seg[s].b.mn_major != 0;
+          const int b_boxes = b_mn ? (p.bn + 63) / 64 : 1;
+          const uint32_t bytes = (uint32_t)kGABytes + (uint32_t)(b_mn ? b_boxes * 8192 : p.bn * 128);
+          int64_t k0, k1;
+          k_range(s, split, k0, k1);
+          for (int64_t k = k0; k < k1; k += 64) {
+            const uint32_t stage = issued % kGStages;
+            if (issued >= kGStages) mbar_wait(smem_u32(&bars->empty[stage]), ((issued / kGStages) - 1) & 1u);
+            const uint32_t a_dst = smem_base + stage * kGStageBytes, b_dst = a_dst + kGABytes;
+            const uint32_t full = smem_u32(&bars->full[stage]);
+            mbar_arrive_expect_tx(full, bytes);
+            if (!a_mn) {
+              tma_load_2d(a_dst, &p.amap[s], (int)k, m0, full);                       // 128 rows (M) x 64 columns (K)
+            } else {
+              tma_load_2d(a_dst, &p.amap[s], m0, (int)k, full);                       // 64 rows (K) x 64 columns (M), twice
+              tma_load_2d(a_dst + 8192, &p.amap[s], m0 + 64, (int)k, full);
+            }
+            if (!b_mn) {
+              tma_load_2d(b_dst, &p.bmap[s], (int)k, n0, full);                       // bn rows (N) x 64 columns (K)
+            } else {
+              for (int j = 0; j < b_boxes; ++j) tma_load_2d(b_dst + j * 8192, &p.bmap[s], n0 + 64 * j, (int)k, full);
+            }
+            ++issued;
           }
         }
       }
     }
-    cp_async_wait<0>();
-    while (published < issued) publish();
-  } else if (warp == 8) {
+  } else if (warp == 5) {
     // =========================================== MMA issuer (whole warp, one elected lane per instruction) ===========
     uint32_t consumed = 0, item = 0;
     for (int64_t it = blockIdx.x; it < n_items; it += gridDim.x, ++item) {
@@ -233,14 +219,19 @@ __global__ void __launch_bounds__(kGThreads, 1) gemm_bf16_kernel(const __grid_co
     }
   } else {
     // =========================================== epilogue ============================================================
-    uint32_t item = 0;
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
-    for (int64_t it = blockIdx.x; it < n_items; it += gridDim.x, ++item) {
+    // two groups of four warps: group g drains accumulator buffer g, i.e. this CTA's items g, g + 2, ... -- two tiles are
+    // in the epilogue at once and each scheduler has two epilogue warps to hide the TMEM / L1 round trips of the other
+    const int ew = warp < 4 ? warp : warp - 2;          // 0..7
+    const int group = ew >> 2;
+    const int quad = warp & 3;                          // TMEM lane quadrant this warp may read
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
+    uint32_t item = (uint32_t)group;
+    for (int64_t it = blockIdx.x + (int64_t)group * gridDim.x; it < n_items; it += 2 * (int64_t)gridDim.x, item += 2) {
       const int m_tile = (int)(it % p.m_tiles);
       const int n_tile = (int)((it / p.m_tiles) % p.n_tiles);
       const int split = (int)(it / ((int64_t)p.m_tiles * p.n_tiles));
-      const uint32_t buf = item & 1u;
-      const int64_t row = (int64_t)m_tile * 128 + warp * 32 + lane;
+      const uint32_t buf = (uint32_t)group;
+      const int64_t row = (int64_t)m_tile * 128 + quad * 32 + lane;
       const int64_t n0 = (int64_t)n_tile * p.bn;
       // a work item whose K range is empty issued no MMA: its accumulator is undefined -> contributes zeros
       bool empty_k = true;
@@ -261,8 +252,8 @@ __global__ void __launch_bounds__(kGThreads, 1) gemm_bf16_kernel(const __grid_co
                          (!d.out_lo || (reinterpret_cast<uintptr_t>(d.out_lo) & 15) == 0);
       const bool vecm = d.mask && (d.ld_mask & 7) == 0 && (d.N & 7) == 0 && ((reinterpret_cast<uintptr_t>(d.mask) & 15) == 0);
       const bool vec32 = out32 && !d.out_hi && (d.ld_f32 & 3) == 0 && (d.N & 3) == 0 && ((reinterpret_cast<uintptr_t>(out32) & 15) == 0);
-      const int64_t row0 = (int64_t)m_tile * 128 + warp * 32;
-      const uint32_t stg = stg_base + (uint32_t)warp * 8192u;        // [0, 4096): hi / fp32 rows, [4096, 8192): lo rows / mask rows
+      const int64_t row0 = (int64_t)m_tile * 128 + quad * 32;
+      const uint32_t stg = stg_base + (uint32_t)ew * 4096u;
       auto sw = [](int r, int ch) { return (uint32_t)r * 128u + (uint32_t)((ch ^ (r & 7)) << 4); };
       const __nv_bfloat16* mask = reinterpret_cast<const __nv_bfloat16*>(d.mask);
       __nv_bfloat16* out_hi = reinterpret_cast<__nv_bfloat16*>(d.out_hi);
@@ -271,17 +262,32 @@ __global__ void __launch_bounds__(kGThreads, 1) gemm_bf16_kernel(const __grid_co
         const int nb = (cb + 1 < p.bn / 32) ? 2 : 1;          // 32-column blocks in this pass (64 columns = one 128-byte bf16 row)
         const int sh = nb == 2 ? 3 : 2;                       // 16-byte units per bf16 row of the pass: 8 or 4
         const int64_t c0 = n0 + cb * 32;
+        uint32_t keep[2] = {0u, 0u};                          // relu mask of this thread's row: bit j of keep[hb] = column 32 hb + j passes
         if (vecm) {
           for (int q = lane; q < (32 << sh); q += 32) {
             const int r = q >> sh, ch = q & ((1 << sh) - 1);
             const int64_t grow = row0 + r, gcol = c0 + 8 * ch;
             uint4 m = make_uint4(0u, 0u, 0u, 0u);
             if (grow < d.M && gcol < d.N) m = __ldg(reinterpret_cast<const uint4*>(mask + grow * d.ld_mask + gcol));
-            st_shared_v4(stg + 4096u + sw(r, ch), m.x, m.y, m.z, m.w);
+            st_shared_v4(stg + sw(r, ch), m.x, m.y, m.z, m.w);
+          }
+          __syncwarp();
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            if (k < (1 << sh)) {
+              uint32_t m[4];
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(m[0]), "=r"(m[1]), "=r"(m[2]), "=r"(m[3]) : "r"(stg + sw(lane, k)));
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                keep[k >> 2] |= (bf16_lo_to_f32(m[e]) > 0.f ? 1u : 0u) << (8 * (k & 3) + 2 * e);
+                keep[k >> 2] |= (bf16_hi_to_f32(m[e]) > 0.f ? 1u : 0u) << (8 * (k & 3) + 2 * e + 1);
+              }
+            }
           }
           __syncwarp();
         }
         uint32_t ra[32], rb[32];
+        uint32_t lo_keep[2][16];                              // lo residuals wait in registers while the hi rows use the staging tile
         tmem_ld32(lane_addr + buf * 256 + cb * 32, ra);
         if (nb == 2) tmem_ld32(lane_addr + buf * 256 + cb * 32 + 32, rb);
         tmem_ld_wait();
@@ -290,27 +296,35 @@ __global__ void __launch_bounds__(kGThreads, 1) gemm_bf16_kernel(const __grid_co
           if (hb >= nb) break;
           const int64_t cc = c0 + 32 * hb;
           const int nv = (int)(d.N - cc < 32 ? (d.N - cc > 0 ? d.N - cc : 0) : 32);
+          // (straight-line code: per-element branches around the bias loads serialised 64 dependent L1 round trips per
+          //  pass and made the epilogue 10x longer than the main loop)
           float v[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float x = empty_k ? 0.f : __uint_as_float(hb ? rb[j] : ra[j]);
-            if (d.bias != nullptr && j < nv) x += __ldg(d.bias + cc + j);
-            if (d.act == 1) x = fmaxf(x, 0.f);
-            else if (d.act == 2) x = 1.f / (1.f + expf(-x));
-            v[j] = x;
+          for (int j = 0; j < 32; ++j) v[j] = empty_k ? 0.f : __uint_as_float(hb ? rb[j] : ra[j]);
+          if (d.bias != nullptr) {
+            if (nv == 32 && (reinterpret_cast<uintptr_t>(d.bias) & 15) == 0) {
+              const float4* b4 = reinterpret_cast<const float4*>(d.bias + cc);
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                const float4 bq = __ldg(b4 + k);
+                v[4 * k] += bq.x; v[4 * k + 1] += bq.y; v[4 * k + 2] += bq.z; v[4 * k + 3] += bq.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] += __ldg(d.bias + (j < nv ? cc + j : 0)) * (j < nv ? 1.f : 0.f);
+            }
+          }
+          if (d.act == 1) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          } else if (d.act == 2) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 1.f / (1.f + __expf(-v[j]));
           }
           if (vecm) {
+            const uint32_t kb = keep[hb];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              uint32_t m[4];
-              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(m[0]), "=r"(m[1]), "=r"(m[2]), "=r"(m[3])
-                           : "r"(stg + 4096u + sw(lane, 4 * hb + k)));
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                if (!(bf16_lo_to_f32(m[e]) > 0.f)) v[8 * k + 2 * e] = 0.f;
-                if (!(bf16_hi_to_f32(m[e]) > 0.f)) v[8 * k + 2 * e + 1] = 0.f;
-              }
-            }
+            for (int j = 0; j < 32; ++j) v[j] = ((kb >> j) & 1u) ? v[j] : 0.f;
           } else if (mask != nullptr && row < d.M) {
             const __nv_bfloat16* mrow = mask + row * d.ld_mask + cc;
 #pragma unroll
@@ -350,7 +364,7 @@ __global__ void __launch_bounds__(kGThreads, 1) gemm_bf16_kernel(const __grid_co
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
                 st_shared_v4(stg + sw(lane, 4 * hb + k), hi[4 * k], hi[4 * k + 1], hi[4 * k + 2], hi[4 * k + 3]);
-                if (out_lo != nullptr) st_shared_v4(stg + 4096u + sw(lane, 4 * hb + k), lo[4 * k], lo[4 * k + 1], lo[4 * k + 2], lo[4 * k + 3]);
+                lo_keep[hb][4 * k] = lo[4 * k]; lo_keep[hb][4 * k + 1] = lo[4 * k + 1]; lo_keep[hb][4 * k + 2] = lo[4 * k + 2]; lo_keep[hb][4 * k + 3] = lo[4 * k + 3];
               }
             } else if (row < d.M) {
               __nv_bfloat16* oh = out_hi + row * d.ld_16 + cc;
@@ -369,21 +383,29 @@ __global__ void __launch_bounds__(kGThreads, 1) gemm_bf16_kernel(const __grid_co
           }
         }
         if (vec16) {
-          __syncwarp();
-          for (int q = lane; q < (32 << sh); q += 32) {
-            const int r = q >> sh, ch = q & ((1 << sh) - 1);
-            const int64_t grow = row0 + r, gcol = c0 + 8 * ch;
-            if (grow < d.M && gcol < d.N) {
-              uint4 x;
-              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x.x), "=r"(x.y), "=r"(x.z), "=r"(x.w) : "r"(stg + sw(r, ch)));
-              *reinterpret_cast<uint4*>(out_hi + grow * d.ld_16 + gcol) = x;
-              if (out_lo != nullptr) {
-                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x.x), "=r"(x.y), "=r"(x.z), "=r"(x.w) : "r"(stg + 4096u + sw(r, ch)));
-                *reinterpret_cast<uint4*>(out_lo + grow * d.ld_16 + gcol) = x;
+          for (int part = 0; part < (out_lo != nullptr ? 2 : 1); ++part) {
+            __nv_bfloat16* dst = part ? out_lo : out_hi;
+            if (part) {
+#pragma unroll
+              for (int hb = 0; hb < 2; ++hb)
+                if (hb < nb) {
+#pragma unroll
+                  for (int k = 0; k < 4; ++k)
+                    st_shared_v4(stg + sw(lane, 4 * hb + k), lo_keep[hb][4 * k], lo_keep[hb][4 * k + 1], lo_keep[hb][4 * k + 2], lo_keep[hb][4 * k + 3]);
+                }
+            }
+            __syncwarp();
+            for (int q = lane; q < (32 << sh); q += 32) {
+              const int r = q >> sh, ch = q & ((1 << sh) - 1);
+              const int64_t grow = row0 + r, gcol = c0 + 8 * ch;
+              if (grow < d.M && gcol < d.N) {
+                uint4 x;
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x.x), "=r"(x.y), "=r"(x.z), "=r"(x.w) : "r"(stg + sw(r, ch)));
+                *reinterpret_cast<uint4*>(dst + grow * d.ld_16 + gcol) = x;
               }
             }
+            __syncwarp();
           }
-          __syncwarp();
         }
       }
       tc_fence_before();
@@ -394,7 +416,7 @@ __global__ void __launch_bounds__(kGThreads, 1) gemm_bf16_kernel(const __grid_co
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == 5) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
@@ -444,6 +466,65 @@ __global__ void reduce_splits_kernel(const float* __restrict__ ws, int splits, i
 
 using namespace nb2;
 
+// ---- tensor maps -----------------------------------------------------------------------------------------------------
+// cuTensorMapEncodeTiled is a driver entry point; it is resolved through the runtime (no link against libcuda) and its
+// results are cached per (pointer, shape, box): a training step re-uses the same few dozen buffers.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+struct MapKey {
+  const void* ptr;
+  int64_t rows, cols, ld;
+  int box_rows;
+  bool operator==(const MapKey& o) const { return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows; }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    size_t h = std::hash<const void*>()(k.ptr);
+    h = h * 1000003u ^ std::hash<int64_t>()(k.rows);
+    h = h * 1000003u ^ std::hash<int64_t>()(k.cols);
+    h = h * 1000003u ^ std::hash<int64_t>()(k.ld);
+    return h * 1000003u ^ (size_t)k.box_rows;
+  }
+};
+static std::mutex g_map_mutex;
+static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_map_cache;
+static EncodeTiledFn g_encode = nullptr;
+
+// [rows][cols] bf16, row stride ld elements; boxes of box_rows x 64 columns, 128-byte swizzle, zero fill out of bounds
+static int make_map(CUtensorMap* out, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  std::lock_guard<std::mutex> lock(g_map_mutex);
+  if (!g_encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+      set_error("gemm: cuTensorMapEncodeTiled is not available from this driver (%s)", e == cudaSuccess ? "symbol not found" : cudaGetErrorString(e));
+      return NB2_ERR_CUDA;
+    }
+    g_encode = (EncodeTiledFn)fn;
+  }
+  const MapKey key{ptr, rows, cols, ld, box_rows};
+  auto it = g_map_cache.find(key);
+  if (it != g_map_cache.end()) {
+    *out = it->second;
+    return NB2_OK;
+  }
+  const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
+  const cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("gemm: cuTensorMapEncodeTiled failed (%d) for a %lld x %lld matrix with row stride %lld, box %d x 64", (int)r, (long long)rows,
+              (long long)cols, (long long)ld, box_rows);
+    return NB2_ERR_CUDA;
+  }
+  if (g_map_cache.size() > 8192) g_map_cache.clear();
+  g_map_cache.emplace(key, *out);
+  return NB2_OK;
+}
+
 extern "C" int nb2_gemm_bf16(nb2_handle* h, const nb2_gemm_desc* d, void* stream) {
   NB2_ENTER(h);
   NB2_CHECK_ARG(d != nullptr, "gemm: null descriptor");
@@ -479,6 +560,16 @@ extern "C" int nb2_gemm_bf16(nb2_handle* h, const nb2_gemm_desc* d, void* stream
   if (splits > 1) p.k_per_split = ((d->seg[0].K + splits - 1) / splits + 63) / 64 * 64;
   int rc = kernel_set_smem(h, (const void*)gemm_bf16_kernel, kGSmem);
   if (rc != NB2_OK) return rc;
+  for (int s = 0; s < d->n_seg; ++s) {
+    const nb2_gemm_operand& A = d->seg[s].a;
+    const nb2_gemm_operand& B = d->seg[s].b;
+    const int64_t K = d->seg[s].K, K8 = (K + 7) & ~7LL, M8 = (d->M + 7) & ~7LL, N8 = ((int64_t)d->N + 7) & ~7LL;
+    // the contiguous extent is declared up to its zero padding (a multiple of 8 elements: 16-byte rows for the TMA unit)
+    rc = A.mn_major ? make_map(&p.amap[s], A.ptr, K, M8, A.ld, 64) : make_map(&p.amap[s], A.ptr, d->M, K8, A.ld, 128);
+    if (rc != NB2_OK) return rc;
+    rc = B.mn_major ? make_map(&p.bmap[s], B.ptr, K, N8, B.ld, 64) : make_map(&p.bmap[s], B.ptr, d->N, K8, B.ld, p.bn);
+    if (rc != NB2_OK) return rc;
+  }
   const int64_t items = (int64_t)p.m_tiles * p.n_tiles * splits;
   const int grid = (int)std::min<int64_t>(items, h->sm_count);
   gemm_bf16_kernel<<<grid, kGThreads, kGSmem, (cudaStream_t)stream>>>(p);
