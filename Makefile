@@ -4,7 +4,7 @@ ARCH      := -gencode arch=compute_100a,code=sm_100a
 PROFILE   ?= 0
 NVCCFLAGS := -DNB2_TC_PROFILE=$(PROFILE) -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC -Xcompiler -Wall -Iinclude
 CSRC      := nerf_b200/csrc
-SRCS      := $(CSRC)/nb2_api.cu $(CSRC)/nb2_ops.cu $(CSRC)/nb2_pack.cu $(CSRC)/nb2_mlp_simt.cu $(CSRC)/nb2_mlp_tc.cu $(CSRC)/nb2_mlp_tc4.cu $(CSRC)/nb2_gemm.cu $(CSRC)/nb2_train.cu $(CSRC)/nb2_microbench.cu
+SRCS      := $(CSRC)/nb2_api.cu $(CSRC)/nb2_ops.cu $(CSRC)/nb2_pack.cu $(CSRC)/nb2_mlp_simt.cu $(CSRC)/nb2_mlp_tc.cu $(CSRC)/nb2_mlp_tc4.cu $(CSRC)/nb2_gemm.cu $(CSRC)/nb2_train.cu $(CSRC)/nb2_refnerf.cu $(CSRC)/nb2_microbench.cu
 OBJS      := $(SRCS:.cu=.o)
 LIB       := nerf_b200/libnerfb200.so
 

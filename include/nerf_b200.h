@@ -167,6 +167,11 @@ int nb2_length2pts(nb2_handle* h, const float* rays, const float* z, int64_t n_r
 int nb2_coarse_fine_merge(nb2_handle* h, const float* rays, const float* c_z, const float* f_z,
                           int64_t n_rays, int n_coarse, int n_fine, float* z_out,
                           float* pts_out, void* stream);
+/* The same with the index bookkeeping of the training path (nerf_base.py:62-65,70-71): f_inds (R,F) int64 ->
+ * all_inds (R, F+C) = gather(cat(f_inds, arange(C)), sort order), sort_inds (R, F+C-1) = the sort permutation, last dropped. */
+int nb2_coarse_fine_merge_inds(nb2_handle* h, const float* rays, const float* c_z, const float* f_z, const int64_t* f_inds,
+                               int64_t n_rays, int n_coarse, int n_fine, float* z_out, float* pts_out, int64_t* all_inds_out,
+                               int64_t* sort_inds_out, void* stream);
 
 /* ---- f1 (training-side callers of the path, forward only) -----------------------------------
  * validSampler  nerf/utils.py:72-94: ray r takes pixel indices[r] (NULL -> device Philox) of the flattened image:
@@ -200,6 +205,11 @@ int nb2_composite(nb2_handle* h, const float* rgbo, const float* z, const float*
                   int dir_stride, int64_t n_rays, int n_samples, int flags, float near_t,
                   float far_t, float* rgb_out, float* weights_out, float* depth_out,
                   float* acc_out, void* stream);
+/* The same with one auxiliary per-sample channel: aux (R,P) -> aux_out (R) = sum_i w_i aux_i (the normal image of the
+ * Ref-NeRF branch, nerf/nerf_base.py:110-112: aux = normal . cam_dir; the caller applies (x + 1) / 2). */
+int nb2_composite_aux(nb2_handle* h, const float* rgbo, const float* z, const float* dirs, int dir_stride, int64_t n_rays,
+                      int n_samples, int flags, float near_t, float far_t, const float* aux, float* rgb_out, float* weights_out,
+                      float* depth_out, float* acc_out, float* aux_out, void* stream);
 
 /* ---- the fused path: render_image's per-ray work   nerf/procedures.py:64-85 --------------
  * rays (R,6) -> rgb (R,3), depth (R) or NULL, acc (R) or NULL.  Three launches: fused
@@ -307,6 +317,23 @@ int nb2_get_bounds_backward(nb2_handle* h, const int64_t* inds, const float* g_o
                             float* d_weights, void* stream);
 int nb2_nerf_head_backward(nb2_handle* h, const float* out, const float* g_out, int64_t n, void* dz_hi, void* dz_lo, void* ds_hi,
                            void* ds_lo, void* stream);
+
+/* ---- Ref-NeRF forward glue (the GEMMs run on nb2_gemm_bf16, the directional encoding on nb2_ide) -----------
+ * heads (n, ld_heads) fp32 = [normal(3), diffuse(3), tint(3), rho(1), density(1)]: norm_col_tint_head | rho_tau_head outputs.
+ * nb2_ref_geometry: normal = -n / (||n|| + 1e-7), reflect = d - 2 (d . normal) normal, roughness = softplus(rho - 1),
+ *   nv_dot = normal . d                                                                     nerf/ref_model.py:83-94
+ * nb2_ref_dir_inputs: [ide (ide_width) | nv_dot | 0 ...] as bf16 hi / lo columns of the directional MLP input  nerf/ref_model.py:96
+ * nb2_ref_color: rgb = [linear_to_srgb](spec * sigmoid(tint) + sigmoid(diffuse [- ln 3])), out (n,4) = [rgb, density]
+ *   (density -> softplus(density + 0.5) when shift_softplus, nerf/procedures.py:74); ndot_out = normal . cam_dir (nerf_base.py:111)
+ *                                                                                           nerf/ref_model.py:102-109 */
+int nb2_ref_geometry(nb2_handle* h, const float* heads, int ld_heads, const float* dirs, int dir_stride, int64_t n, float* normal_out,
+                     float* reflect_out, float* rough_out, float* nv_out, void* stream);
+int nb2_ref_dir_inputs(nb2_handle* h, const float* ide, int ide_width, const float* nv_dot, int64_t n, void* hi, void* lo, int64_t ld,
+                       int width, void* stream);
+int nb2_ref_color(nb2_handle* h, const float* spec, const float* heads, int ld_heads, int use_srgb, int shift_softplus, const float* normal,
+                  const float* cam_dir, int64_t n, float* out, float* ndot_out, void* stream);
+/* out[i] = a[i] . b for a (n,3), b (3): `normal @ cam_dir` of NeRF.render's normal image (nerf/nerf_base.py:111). */
+int nb2_dot3(nb2_handle* h, const float* a, const float* b, int64_t n, float* out, void* stream);
 
 /* ---- peer memory for the fused gather (one process per GPU, CUDA IPC over NVLink / NVSwitch) -----------------
  * nb2_ipc_alloc: cudaMalloc `bytes` on the handle's device and export a 64-byte IPC handle for it.

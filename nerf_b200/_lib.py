@@ -85,6 +85,13 @@ SIGNATURES = {
     "nb2_max_blur_backward": (c_int, [c_vp, c_f32p, c_f32p, c_i64, c_int, c_f32p, c_vp]),
     "nb2_get_bounds_backward": (c_int, [c_vp, c_vp, c_f32p, c_i64, c_int, c_int, c_f32p, c_vp]),
     "nb2_nerf_head_backward": (c_int, [c_vp, c_f32p, c_f32p, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "nb2_dot3": (c_int, [c_vp, c_f32p, c_f32p, c_i64, c_f32p, c_vp]),
+    "nb2_ref_geometry": (c_int, [c_vp, c_f32p, c_int, c_f32p, c_int, c_i64, c_f32p, c_f32p, c_f32p, c_f32p, c_vp]),
+    "nb2_ref_dir_inputs": (c_int, [c_vp, c_f32p, c_int, c_f32p, c_i64, c_vp, c_vp, c_i64, c_int, c_vp]),
+    "nb2_ref_color": (c_int, [c_vp, c_f32p, c_f32p, c_int, c_int, c_int, c_f32p, c_f32p, c_i64, c_f32p, c_f32p, c_vp]),
+    "nb2_coarse_fine_merge_inds": (c_int, [c_vp, c_f32p, c_f32p, c_f32p, c_vp, c_i64, c_int, c_int, c_f32p, c_f32p, c_vp, c_vp, c_vp]),
+    "nb2_composite_aux": (c_int, [c_vp, c_f32p, c_f32p, c_f32p, c_int, c_i64, c_int, c_int, c_float, c_float, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p,
+                                  c_f32p, c_vp]),
     "nb2_ipc_alloc": (c_int, [c_vp, c_i64, ctypes.POINTER(c_vp), c_vp]),
     "nb2_ipc_open": (c_int, [c_vp, c_vp, ctypes.POINTER(c_vp)]),
     "nb2_ipc_close": (c_int, [c_vp, c_vp]),

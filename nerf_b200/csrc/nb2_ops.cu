@@ -482,23 +482,32 @@ __global__ void length2pts_kernel(const float* __restrict__ rays, const float* _
 }
 
 // a13  NeRF.coarseFineMerge                          /root/reference/nerf/nerf_base.py:58-73
+// Optional index bookkeeping (training path, :62-65,70-71): sort_inds = the stable sort permutation of cat(f_z, c_z) (last
+// dropped), all_inds = gather(cat(f_inds, arange(C)), permutation) (full length).
 __global__ void __launch_bounds__(32 * kResampleWarps)
 merge_kernel(const float* __restrict__ rays, const float* __restrict__ cz, const float* __restrict__ fz,
-             int64_t n_rays, int C, int F, float* __restrict__ z_out, float* __restrict__ pts_out) {
+             const int64_t* __restrict__ f_inds, int64_t n_rays, int C, int F, float* __restrict__ z_out, float* __restrict__ pts_out,
+             int64_t* __restrict__ all_inds_out, int64_t* __restrict__ sort_inds_out) {
   __shared__ float key[kResampleWarps][2 * kMaxDraw];
   __shared__ float srt[kResampleWarps][2 * kMaxDraw];
+  __shared__ int pay[kResampleWarps][2 * kMaxDraw];
+  __shared__ int pay_srt[kResampleWarps][2 * kMaxDraw];
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int64_t r = (int64_t)blockIdx.x * kResampleWarps + warp;
   if (r >= n_rays) return;
   const int n = C + F;
+  const bool want_inds = (all_inds_out != nullptr) || (sort_inds_out != nullptr);
   for (int i = lane; i < F; i += 32) key[warp][i] = fz[r * F + i];      // cat((f_zvals, c_zvals))
   for (int i = lane; i < C; i += 32) key[warp][F + i] = cz[r * C + i];
+  if (want_inds)
+    for (int i = lane; i < n; i += 32) pay[warp][i] = i;
   __syncwarp();
-  rank_sort_warp(key[warp], nullptr, n, srt[warp], nullptr, lane);
+  rank_sort_warp(key[warp], want_inds ? pay[warp] : nullptr, n, srt[warp], pay_srt[warp], lane);
   const float* ray = rays + r * 6;
   for (int i = lane; i < n - 1; i += 32) {
     float zz = srt[warp][i];
     z_out[r * (n - 1) + i] = zz;
+    if (sort_inds_out) sort_inds_out[r * (n - 1) + i] = pay_srt[warp][i];
     if (pts_out) {
       float* o = pts_out + (r * (n - 1) + i) * 6;
 #pragma unroll
@@ -509,6 +518,11 @@ merge_kernel(const float* __restrict__ rays, const float* __restrict__ cz, const
       }
     }
   }
+  if (all_inds_out)
+    for (int i = lane; i < n; i += 32) {
+      const int src = pay_srt[warp][i];
+      all_inds_out[r * n + i] = src < F ? f_inds[r * F + src] : (int64_t)(src - F);
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -518,7 +532,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock)
 composite_kernel(const float* __restrict__ rgbo, const float* __restrict__ z, const float* __restrict__ dirs,
                  int dir_stride, int64_t n_rays, int P, int flags, float near_t, float far_t,
                  float* __restrict__ rgb_out, float* __restrict__ w_out, float* __restrict__ depth_out,
-                 float* __restrict__ acc_out) {
+                 float* __restrict__ acc_out, const float* __restrict__ aux, float* __restrict__ aux_out) {
   __shared__ float sh[kWarpsPerBlock][3][kMaxSamples];
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int64_t r = (int64_t)blockIdx.x * kWarpsPerBlock + warp;
@@ -531,10 +545,11 @@ composite_kernel(const float* __restrict__ rgbo, const float* __restrict__ z, co
   }
   __syncwarp();
   ray_weights_warp(sh[warp][0], sh[warp][1], sh[warp][2], P, 0, lane);
-  float cr = 0.f, cg = 0.f, cb = 0.f, acc = 0.f, dep = 0.f;
+  float cr = 0.f, cg = 0.f, cb = 0.f, acc = 0.f, dep = 0.f, ax = 0.f;
   for (int i = lane; i < P; i += 32) {
     float w = sh[warp][2][i];
     float4 c = c4[i];
+    if (aux) ax = fmaf(w, aux[r * P + i], ax);
     cr = fmaf(w, c.x, cr);
     cg = fmaf(w, c.y, cg);
     cb = fmaf(w, c.z, cb);
@@ -543,7 +558,9 @@ composite_kernel(const float* __restrict__ rgbo, const float* __restrict__ z, co
     if (w_out) w_out[r * P + i] = w;
   }
   cr = warp_sum(cr); cg = warp_sum(cg); cb = warp_sum(cb); acc = warp_sum(acc); dep = warp_sum(dep);
+  if (aux) ax = warp_sum(ax);
   if (lane == 0) {
+    if (aux_out) aux_out[r] = ax;
     if (flags & NB2_WHITE_BKG) {
       float bg = 1.f - acc;
       cr += bg; cg += bg; cb += bg;
@@ -880,7 +897,21 @@ extern "C" int nb2_coarse_fine_merge(nb2_handle* h, const float* rays, const flo
   NB2_CHECK_ARG(n_coarse >= 1 && n_fine >= 1 && n_coarse + n_fine <= 2 * kMaxDraw, "coarse_fine_merge: too many samples");
   if (n_rays == 0) return NB2_OK;
   merge_kernel<<<grid_for(n_rays, kResampleWarps), 32 * kResampleWarps, 0, (cudaStream_t)stream>>>(
-      rays, c_z, f_z, n_rays, n_coarse, n_fine, z_out, pts_out);
+      rays, c_z, f_z, nullptr, n_rays, n_coarse, n_fine, z_out, pts_out, nullptr, nullptr);
+  NB2_LAUNCH_CHECK(h);
+  return NB2_OK;
+}
+
+extern "C" int nb2_coarse_fine_merge_inds(nb2_handle* h, const float* rays, const float* c_z, const float* f_z, const int64_t* f_inds,
+                                          int64_t n_rays, int n_coarse, int n_fine, float* z_out, float* pts_out, int64_t* all_inds_out,
+                                          int64_t* sort_inds_out, void* stream) {
+  NB2_H(h);
+  if (n_rays == 0) return NB2_OK;
+  NB2_CHECK_ARG(rays && c_z && f_z && z_out, "coarse_fine_merge_inds: null pointer");
+  NB2_CHECK_ARG(!all_inds_out || f_inds, "coarse_fine_merge_inds: all_inds_out needs f_inds");
+  NB2_CHECK_ARG(n_coarse >= 1 && n_fine >= 1 && n_coarse + n_fine <= 2 * kMaxDraw, "coarse_fine_merge_inds: too many samples");
+  merge_kernel<<<grid_for(n_rays, kResampleWarps), 32 * kResampleWarps, 0, (cudaStream_t)stream>>>(
+      rays, c_z, f_z, f_inds, n_rays, n_coarse, n_fine, z_out, pts_out, all_inds_out, sort_inds_out);
   NB2_LAUNCH_CHECK(h);
   return NB2_OK;
 }
@@ -895,7 +926,21 @@ extern "C" int nb2_composite(nb2_handle* h, const float* rgbo, const float* z, c
   NB2_CHECK_ARG(n_samples >= 1 && n_samples <= kMaxSamples, "composite: n_samples must be in [1,%d]", kMaxSamples);
   if (n_rays == 0) return NB2_OK;
   composite_kernel<<<grid_for(n_rays, kWarpsPerBlock), 32 * kWarpsPerBlock, 0, (cudaStream_t)stream>>>(
-      rgbo, z, dirs, dir_stride, n_rays, n_samples, flags, near_t, far_t, rgb_out, weights_out, depth_out, acc_out);
+      rgbo, z, dirs, dir_stride, n_rays, n_samples, flags, near_t, far_t, rgb_out, weights_out, depth_out, acc_out, nullptr, nullptr);
+  NB2_LAUNCH_CHECK(h);
+  return NB2_OK;
+}
+
+extern "C" int nb2_composite_aux(nb2_handle* h, const float* rgbo, const float* z, const float* dirs, int dir_stride, int64_t n_rays,
+                                 int n_samples, int flags, float near_t, float far_t, const float* aux, float* rgb_out, float* weights_out,
+                                 float* depth_out, float* acc_out, float* aux_out, void* stream) {
+  NB2_H(h);
+  if (n_rays == 0) return NB2_OK;
+  NB2_CHECK_ARG(rgbo && z && dirs && rgb_out && aux && aux_out, "composite_aux: null pointer");
+  NB2_CHECK_ARG(dir_stride >= 3, "composite_aux: dir_stride < 3");
+  NB2_CHECK_ARG(n_samples >= 1 && n_samples <= kMaxSamples, "composite_aux: n_samples must be in [1,%d]", kMaxSamples);
+  composite_kernel<<<grid_for(n_rays, kWarpsPerBlock), 32 * kWarpsPerBlock, 0, (cudaStream_t)stream>>>(
+      rgbo, z, dirs, dir_stride, n_rays, n_samples, flags, near_t, far_t, rgb_out, weights_out, depth_out, acc_out, aux, aux_out);
   NB2_LAUNCH_CHECK(h);
   return NB2_OK;
 }

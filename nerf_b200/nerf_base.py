@@ -80,6 +80,13 @@ def _release_slot(net_id, dev):
         pass   # interpreter shutdown: the handle may already be gone
 
 
+class _NormalDot:
+    """normal . cam_dir already evaluated per sample by the Ref-NeRF colour kernel (render_image's Ref branch)."""
+
+    def __init__(self, ndot):
+        self.ndot = ndot
+
+
 class NeRF(PackedModule):
     @staticmethod
     def init_weight(m):
@@ -120,9 +127,8 @@ class NeRF(PackedModule):
 
     @staticmethod
     def coarseFineMerge(rays: torch.Tensor, c_zvals: torch.Tensor, f_zvals: torch.Tensor, f_inds: Optional[torch.Tensor] = None):
-        if f_inds is not None:
-            raise _lib.NB2Error("coarseFineMerge with index bookkeeping (training of Ref-NeRF) is not built yet")
-        return ops.coarse_fine_merge(rays, c_zvals, f_zvals)
+        """(samples, zvals) or, with f_inds, (samples, zvals, all_inds, sort_inds[..., :-1]) as the reference (nerf_base.py:58-73)."""
+        return ops.coarse_fine_merge(rays, c_zvals, f_zvals, f_inds)
 
     @staticmethod
     def getNormedWeight(opacity: torch.Tensor, depth: torch.Tensor, density_act=F.relu) -> torch.Tensor:
@@ -134,8 +140,6 @@ class NeRF(PackedModule):
     @staticmethod
     def render(rgbo: torch.Tensor, depth: torch.Tensor, ray_dirs: torch.Tensor, mul_norm: bool = True, white_bkg: bool = False,
                density_act=F.relu, render_depth: Optional[Tuple[float, float]] = None, normal_info: Optional[Tuple] = None):
-        if normal_info is not None:
-            raise _lib.NB2Error("normal rendering belongs to the Ref-NeRF branch, which is not built yet")
         if _act_name(density_act) != "relu":
             raise _lib.NB2Error("render(): the compositing kernel implements density_act = relu (the render path's choice)")
         if not mul_norm:
@@ -148,8 +152,15 @@ class NeRF(PackedModule):
             from .train_engine import Composite
             rgb, weights = Composite.apply(rgbo, depth.detach(), ray_dirs.detach(), bool(white_bkg))
             return rgb, weights, dict()
-        rgb, weights, d, _ = ops.composite(rgbo, depth, ray_dirs, white_bkg=white_bkg, near_far=render_depth)
         extras = dict()
+        if normal_info is not None:
+            # nerf_base.py:110-112: normal image = (sum_i w_i (normal_i . cam_dir) + 1) / 2
+            normal, cam_dir = normal_info
+            ndot = normal.ndot if isinstance(normal, _NormalDot) else ops.dot3(normal, cam_dir).view(rgbo.shape[0], rgbo.shape[1])
+            rgb, weights, d, _, n_img = ops.composite(rgbo, depth, ray_dirs, white_bkg=white_bkg, near_far=render_depth, aux=ndot)
+            extras["normal_img"] = (n_img + 1.0) * 0.5
+        else:
+            rgb, weights, d, _ = ops.composite(rgbo, depth, ray_dirs, white_bkg=white_bkg, near_far=render_depth)
         if render_depth is not None:
             extras["depth_img"] = d
         return rgb, weights, extras

@@ -178,14 +178,22 @@ def length2pts(rays, z):
     return pts
 
 
-def coarse_fine_merge(rays, c_z, f_z):
+def coarse_fine_merge(rays, c_z, f_z, f_inds=None):
+    """-> (pts, z) or, with f_inds (R,F) int64, (pts, z, all_inds (R,F+C), sort_inds (R,F+C-1))  (nerf_base.py:58-73)."""
     rays, c_z, f_z = f32(rays), f32(c_z), f32(f_z)
     R, C, F = c_z.shape[0], c_z.shape[1], f_z.shape[1]
-    z = torch.empty((R, C + F - 1), dtype=torch.float32, device=c_z.device)
-    pts = torch.empty((R, C + F - 1, 6), dtype=torch.float32, device=c_z.device)
-    check(load().nb2_coarse_fine_merge(handle(c_z.device), ptr(rays), ptr(c_z), ptr(f_z), R, C, F, ptr(z), ptr(pts),
-                                       stream_ptr(c_z.device)))
-    return pts, z
+    dev = c_z.device
+    z = torch.empty((R, C + F - 1), dtype=torch.float32, device=dev)
+    pts = torch.empty((R, C + F - 1, 6), dtype=torch.float32, device=dev)
+    if f_inds is None:
+        check(load().nb2_coarse_fine_merge(handle(dev), ptr(rays), ptr(c_z), ptr(f_z), R, C, F, ptr(z), ptr(pts), stream_ptr(dev)))
+        return pts, z
+    f_inds = f_inds.to(torch.int64).contiguous()
+    all_inds = torch.empty((R, C + F), dtype=torch.int64, device=dev)
+    sort_inds = torch.empty((R, C + F - 1), dtype=torch.int64, device=dev)
+    check(load().nb2_coarse_fine_merge_inds(handle(dev), ptr(rays), ptr(c_z), ptr(f_z), ptr(f_inds), R, C, F, ptr(z), ptr(pts), ptr(all_inds),
+                                            ptr(sort_inds), stream_ptr(dev)))
+    return pts, z, all_inds, sort_inds
 
 
 # ---- f1: training-side callers (forward only) -------------------------------------------------------
@@ -278,7 +286,8 @@ def mlp_forward_encoded(net_id, pts, encoded, precision=None):
 
 
 # ---- a12 ------------------------------------------------------------------------------------------
-def composite(rgbo, z, dirs, white_bkg=False, near_far=None, want_weights=True):
+def composite(rgbo, z, dirs, white_bkg=False, near_far=None, want_weights=True, aux=None):
+    """-> (rgb, weights, depth, acc) [+ aux_out (R) = sum_i w_i aux_i when aux (R,P) is given]."""
     rgbo, z, dirs = f32(rgbo), f32(z), f32(dirs)
     R, P = z.shape
     dev = z.device
@@ -287,10 +296,24 @@ def composite(rgbo, z, dirs, white_bkg=False, near_far=None, want_weights=True):
     depth = torch.empty((R,), dtype=torch.float32, device=dev) if near_far is not None else None
     acc = torch.empty((R,), dtype=torch.float32, device=dev)
     near, far = near_far if near_far is not None else (0.0, 1.0)
+    if aux is not None:
+        aux = f32(aux).view(R, P)
+        aux_out = torch.empty((R,), dtype=torch.float32, device=dev)
+        check(load().nb2_composite_aux(handle(dev), ptr(rgbo), ptr(z), ptr(dirs), dirs.shape[-1], R, P, _lib.WHITE_BKG if white_bkg else 0,
+                                       float(near), float(far), ptr(aux), ptr(rgb), ptr(w), ptr(depth), ptr(acc), ptr(aux_out), stream_ptr(dev)))
+        return rgb, w, depth, acc, aux_out
     check(load().nb2_composite(handle(dev), ptr(rgbo), ptr(z), ptr(dirs), dirs.shape[-1], R, P,
                                _lib.WHITE_BKG if white_bkg else 0, float(near), float(far), ptr(rgb), ptr(w), ptr(depth),
                                ptr(acc), stream_ptr(dev)))
     return rgb, w, depth, acc
+
+
+def dot3(a, b):
+    """a (..., 3) . b (3) -> (...)   (normal @ cam_dir, nerf_base.py:111)."""
+    a, b = f32(a), f32(b).reshape(3)
+    out = torch.empty(a.shape[:-1], dtype=torch.float32, device=a.device)
+    check(load().nb2_dot3(handle(a.device), ptr(a), ptr(b), a.numel() // 3, ptr(out), stream_ptr(a.device)))
+    return out
 
 
 # ---- next rows: Ref-NeRF forward helpers ------------------------------------------------------------

@@ -70,8 +70,9 @@ def render_image(
     if not isinstance(image_size, Iterable):
         image_size = (image_size, image_size)
     H, W = int(image_size[0]), int(image_size[1])
-    if render_normal:
-        raise _lib.NB2Error("render_normal is a Ref-NeRF feature, which is not built yet")
+    from .ref_model import RefNeRF
+    is_ref_model = type(network) == RefNeRF
+    render_normal = bool(render_normal) and is_ref_model                        # procedures.py:41-42
     dev = render_pose.device
     if dev.type != "cuda":
         raise _lib.NB2Error("render_image: render_pose must live on a CUDA device (there is no CPU path)")
@@ -79,6 +80,9 @@ def render_image(
         fx, fy = float(focal[1]), float(focal[0])
     else:
         fx = fy = float(focal)
+    if is_ref_model:
+        return _render_image_ref(network, prop_net, render_pose, (H, W), (fx, fy), near, far, sample_num, white_bkg, render_depth,
+                                 render_normal, precision, rng, seed, jitter, u)
     with torch.no_grad():
         nerf_id = network._nb2_sync()
         prop_id = prop_net._nb2_sync()
@@ -109,4 +113,64 @@ def render_image(
         result = {"rgb": image(out["rgb"], 3)}
         if render_depth:
             result["depth_img"] = image(out["depth"], 1).expand(3, H, W).contiguous()
+    return result
+
+
+def _render_image_ref(network, prop_net, render_pose, image_size, focal_xy, near, far, sample_num, white_bkg, render_depth, render_normal,
+                      precision, rng, seed, jitter, u):
+    """The Ref-NeRF branch of render_image (nerf/procedures.py:71-74,80-90): fused proposal kernel -> get_weights -> maxBlur ->
+    inverseSample (129 kept) -> coarseFineMerge (193 sorted, last dropped = 192) -> RefNeRF.forward on the layer-wise
+    engine -> softplus(density + 0.5) -> compositing with the normal image.  Staged launches (the fused fine kernel is
+    MipNeRF's): ~40 kernels per image instead of 3."""
+    H, W = image_size
+    fx, fy = focal_xy
+    dev = render_pose.device
+    with torch.no_grad():
+        He = rendered_rows((H, W))
+        zero = torch.zeros((3, H, W), dtype=torch.float32, device=dev)
+        if He == 0:
+            res = {"rgb": zero}
+            if render_depth:
+                res["depth_img"] = zero.clone()
+            if render_normal:
+                res["normal_img"] = zero.clone()
+            return res
+        rays = ops.generate_rays(render_pose, H, W, fx, fy, n_rays=He * W)
+        base_z = torch.linspace(near, far, RENDER_COARSE_PNUM, device=dev)
+        resolution = (far - near) / sample_num
+        if jitter is None and u is None and rng == "reference":
+            jitter, u = _reference_rng_draws((H, W), RENDER_COARSE_PNUM, sample_num + 1)
+            jitter, u = jitter.to(dev, non_blocking=True), u.to(dev, non_blocking=True)
+        elif rng not in ("philox", "reference"):
+            raise ValueError(f"unknown rng mode {rng!r}")
+        if seed is None:
+            seed = ops._seed_from_torch() if (jitter is None or u is None) else 0
+        R = rays.shape[0]
+        z_c, pts_c = ops.sample_coarse(rays, base_z, resolution, jitter=jitter, seed=seed)                  # procedures.py:65-66
+        density = prop_net.forward(pts_c)                                                                   # :67
+        w = ops.max_blur(ops.weights_from_sigma(density, z_c, rays[:, 3:].contiguous(), "relu"), 0.01)       # :68-69
+        z_f, _ = ops.inverse_sample(w, z_c, sample_num + 1, sort=True, u=u, seed=seed)                       # :70
+        pts, z = ops.coarse_fine_merge(rays, z_c, z_f)                                                       # :72
+        P = z.shape[1]
+        cam_dir = render_pose[:, -2].contiguous() if render_normal else None                                # :84
+        rgbo, normal, ndot = network._forward_engine(pts.view(R * P, 6), pts.view(R * P, 6)[:, 3:6], cam_dir=cam_dir, shift_softplus=True)  # :73-74
+        if render_normal:
+            rgb, _, depth, _, n_img = ops.composite(rgbo.view(R, P, 4), z, rays[:, 3:].contiguous(), white_bkg=white_bkg,
+                                                    near_far=(near, far) if render_depth else None, aux=ndot.view(R, P))
+        else:
+            rgb, _, depth, _ = ops.composite(rgbo.view(R, P, 4), z, rays[:, 3:].contiguous(), white_bkg=white_bkg,
+                                             near_far=(near, far) if render_depth else None)
+
+        def image(rows, channels):
+            img = rows.view(He, W, channels).permute(2, 0, 1)
+            if He == H:
+                return img.contiguous()
+            full = torch.zeros((channels, H, W), dtype=torch.float32, device=dev)
+            full[:, :He] = img
+            return full
+        result = {"rgb": image(rgb, 3)}
+        if render_depth:
+            result["depth_img"] = image(depth, 1).expand(3, H, W).contiguous()
+        if render_normal:
+            result["normal_img"] = image((n_img + 1.0) * 0.5, 1).expand(3, H, W).contiguous()               # nerf_base.py:112
     return result

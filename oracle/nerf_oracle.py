@@ -376,3 +376,36 @@ def linear_to_srgb(linear):
     srgb0 = 323 / 25 * linear
     srgb1 = (211 * torch.maximum(eps, linear) ** (5 / 12) - 11) / 200
     return torch.where(linear <= 0.0031308, srgb0, srgb1)
+
+
+# ----------------------------------------------------------------------------------------------
+# f3  Ref-NeRF forward (eval mode: no bottleneck noise)                        nerf/ref_model.py:67-109
+# ----------------------------------------------------------------------------------------------
+def refnerf_forward(sd, pts6, pos_levels=10, sh_level=4, use_srgb=False):
+    """pts6 (..., 6) = [xyz, dir] -> (rgbo (..., 4) = [rgb, density], normal (..., 3))."""
+    def seq(h, prefix, idxs):
+        for i in idxs:
+            h = F.relu(F.linear(h, sd[f"{prefix}.{i}.weight"], sd[f"{prefix}.{i}.bias"]))
+        return h
+    x, ray_d = pts6[..., :3], pts6[..., 3:6]
+    enc_x = torch.cat((x, positional_encoding(x, pos_levels)), dim=-1)                                  # :68-73
+    x_tmp = seq(enc_x, "spa_block1", (0, 2, 4, 6))                                                      # :75
+    inter = seq(torch.cat((enc_x, x_tmp), dim=-1), "spa_block2", (0, 2, 4, 6))                           # :76-77
+    nct = F.linear(inter, sd["norm_col_tint_head.weight"], sd["norm_col_tint_head.bias"])               # :79
+    normal, diffuse, tint = nct[..., :3], nct[..., 3:6], nct[..., 6:9]
+    rt = F.linear(inter, sd["rho_tau_head.weight"], sd["rho_tau_head.bias"])                            # :80
+    roughness, density = F.softplus(rt[..., :1] - 1.0), rt[..., 1:2]                                    # :81
+    b = F.linear(inter, sd["bottle_neck.weight"], sd["bottle_neck.bias"])                               # :82
+    normal = -normal / (normal.norm(dim=-1, keepdim=True) + 1e-7)                                       # :86
+    reflect = ray_d - 2.0 * torch.sum(ray_d * normal, dim=-1, keepdim=True) * normal                    # :89
+    wr_ide = ide(reflect, roughness, sh_level)                                                          # :90
+    nv_dot = torch.sum(normal * ray_d, dim=-1, keepdim=True)                                            # :92
+    all_in = torch.cat((b, wr_ide, nv_dot), dim=-1)                                                     # :94
+    r_tmp = seq(all_in, "dir_block1", (0, 2, 4, 6))                                                     # :95
+    q = seq(torch.cat((all_in, r_tmp), dim=-1), "dir_block2", (0, 2, 4, 6))                              # :96-98
+    spec = torch.sigmoid(F.linear(q, sd["spec_rgb_head.0.weight"], sd["spec_rgb_head.0.bias"])) * torch.sigmoid(tint)
+    if use_srgb:                                                                                         # :99-104
+        rgb = linear_to_srgb(spec + torch.sigmoid(diffuse - math.log(3.0)))
+    else:
+        rgb = spec + torch.sigmoid(diffuse)
+    return torch.cat((rgb, density), dim=-1), normal                                                    # :105

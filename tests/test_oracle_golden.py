@@ -269,3 +269,24 @@ def test_training_step_gradients_match_the_reference(golden_round2):
             scale = max(float(ref[0]), 1e-12)
             assert float((got[0] - ref[0]).abs()) <= 1e-4 * scale, (tag, k, float(got[0]), float(ref[0]))
             assert float((got[2:] - ref[2:]).abs().max()) <= 1e-4 * scale, (tag, k)
+
+
+def test_refnerf_forward_and_merge_indices(golden_round2):
+    """The oracle's Ref-NeRF forward and coarseFineMerge index bookkeeping against the UNMODIFIED reference
+    (nerf/ref_model.py:67-109, nerf/nerf_base.py:58-73; tests/golden/make_golden.py round2)."""
+    from nerf_b200.ref_model import RefNeRF
+    from tests.golden.make_golden import inputs_ops, refnerf_inputs
+    g = golden_round2
+    rn = RefNeRF(10, 4)
+    sd = O.det_state_dict(rn, 7, gain=1.0)
+    pts = refnerf_inputs()["pts"]
+    rgbo, normal = O.refnerf_forward(sd, pts)
+    assert float((rgbo - g["ref_fwd_rgbo"]).abs().max()) < 2e-5 and float((normal - g["ref_fwd_normal"]).abs().max()) < 2e-5
+    rgbo_s, _ = O.refnerf_forward(sd, pts, use_srgb=True)
+    assert float((rgbo_s - g["ref_fwd_rgbo_srgb"]).abs().max()) < 2e-5
+    # merge with indices, restated: stable sort of cat(fine, coarse)
+    go = inputs_ops()
+    w = O.max_blur(O.weights_from_sigma(go["sigma"], go["z"], go["dirs"]), 0.01)
+    zs, bs = O.inverse_sample(w, go["z"], go["u"], sort=True, torch_sum=True)
+    zz, order = torch.sort(torch.cat((zs, go["z"]), dim=-1), dim=-1)
+    assert float((zz[:, :-1] - g["merge_z2"]).abs().max()) < 1e-5
