@@ -298,6 +298,70 @@ def train_step_leg(dev, precision="bf16x3", batches=(1024, 8192), steps=10):
     return out
 
 
+def config3_leg(dev, prop, net, ids, steps=5):
+    """BASELINE configs[2]: Mip-NeRF-style integrated positional encoding feeding the proposal network, 400x400, single-pass
+    tensor precision.  IPE is evaluated in the proposal kernel's producer (NB2_PROPOSAL_IPE); PSNR delta against the
+    fp32-faithful IPE render at a 30 dB synthetic ground truth (north_star: within 0.05 dB)."""
+    import nerf_b200
+    from nerf_b200 import ops
+    H = W = 400
+    pose = nerf_b200.pose_spherical(30.0, -30.0, 4.0)[:3, :].to(dev)
+    focal = float(nerf_b200.fov2Focal(FOV, (H, W))[0])
+    radius = 2.0 / (focal * 12 ** 0.5)
+    base_z = torch.linspace(NEAR, FAR, N_COARSE, device=dev)
+    rays = ops.generate_rays(pose, H, W, focal, focal)
+    ref = ops.render_rays(rays, base_z, NEAR, FAR, N_FINE, white_bkg=True, precision="fp16x3", seed=5, ipe_radius=radius, **ids)["rgb"].clone()
+    gt = ref + 0.0316 * torch.randn(ref.shape, generator=torch.Generator().manual_seed(1)).to(dev)
+    psnr = lambda a: -10.0 * math.log10(float(((a - gt) ** 2).mean()))
+    out = {"workload": "400x400 view, 64 coarse + 128 fine, integrated positional encoding (cone radius 2/sqrt(12) pixel) in the proposal kernel's producer",
+           "what": config3_leg.__doc__.split("\n")[0]}
+    for mode in ("fp16", "bf16", "fp16m", "bf16m", "fp16x3"):
+        res = None
+        for _ in range(2):
+            res = ops.render_rays(rays, base_z, NEAR, FAR, N_FINE, white_bkg=True, precision=mode, seed=5, ipe_radius=radius, out=res, **ids)
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            res = ops.render_rays(rays, base_z, NEAR, FAR, N_FINE, white_bkg=True, precision=mode, seed=5, ipe_radius=radius, out=res,
+                                  workspace=res["_workspace"], **ids)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / steps
+        out[mode] = {"rays_per_s": H * W / (ms * 1e-3), "ms_per_step": ms, "psnr_delta_db_at_30dB_gt": psnr(res["rgb"]) - psnr(ref)}
+    return out
+
+
+def config4_leg(dev, prop, steps=5):
+    """BASELINE configs[3]: Ref-NeRF forward on 512-ray batches (64 coarse + 129 fine merged to 192 samples, proposal + IDE):
+    fused proposal kernel -> resample -> coarseFineMerge -> RefNeRF (17 layers on the layer-wise tcgen05 engine, IDE kernel)
+    -> compositing with depth and normal outputs.  (The training-side normal / orientation losses are not built.)"""
+    import nerf_b200
+    from nerf_b200 import synthetic
+    rn = nerf_b200.RefNeRF(10, 4)
+    rn.load_state_dict(synthetic.det_state_dict(rn, 7, gain=1.0))
+    rn = rn.to(dev).eval()
+    pose = nerf_b200.pose_spherical(30.0, -30.0, 4.0)[:3, :].to(dev)
+    out = {"what": config4_leg.__doc__.split("\n")[0]}
+    for (Hh, Ww) in ((16, 32), (100, 100)):                     # 512 rays (the config's batch) and a 10,000-ray image
+        focal = float(nerf_b200.fov2Focal(FOV, (Ww, Ww))[0])
+        for _ in range(2):
+            nerf_b200.render_image(rn, prop, pose, (Hh, Ww), focal, NEAR, FAR, N_FINE, white_bkg=True, render_depth=True, render_normal=True, seed=3)
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            nerf_b200.render_image(rn, prop, pose, (Hh, Ww), focal, NEAR, FAR, N_FINE, white_bkg=True, render_depth=True, render_normal=True, seed=3)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / steps
+        flop = Hh * Ww * (FLOP_PROP_PER_RAY + 192 * 2143232)
+        out[f"rays_{Hh * Ww}"] = {"rays_per_s": Hh * Ww / (ms * 1e-3), "ms_per_step": ms, "host_ms_per_step": 1e3 * (time.perf_counter() - t0) / steps,
+                                  "tensor_tflops": flop / (ms * 1e-3) / 1e12}
+    return out
+
+
 def parity_leg(dev, pose, H, W, focal, base_z, ids, precisions):
     """The ray-by-ray parity theorem (tests/parity_tools.py) on 8,192 rays of the timed view, plus PSNR figures."""
     from nerf_b200 import ops
@@ -577,6 +641,8 @@ def main():
             line["parity_vs_oracle"] = parity_leg(dev, scene.pose, H, Wd, scene.focal, base_z, ids, list(dict.fromkeys([args.precision, "bf16", "fp16"])))
         line["torch_cuda_baseline"] = torch_cuda_baseline(dev, 400, 400)
         line["train_step"] = train_step_leg(dev)
+        with torch.no_grad():
+            line["other_configs"] = {"config3_ipe": config3_leg(dev, prop, net, ids), "config4_refnerf": config4_leg(dev, prop)}
         cores = os.cpu_count() or 1
         cpu_v, cpu_t = cpu_reference_render(2, 1, cores)
         line["cpu_baseline"] = {"value": cpu_v, "unit": "rays/s", "cores": cores, "kind": "port",

@@ -51,13 +51,23 @@ enum {
                           products exact to ~2^-22 -> fp32-faithful                                   */
   NB2_PREC_BF16 = 2,   /* tcgen05, single bf16 pass, fp32 accumulate                                  */
   NB2_PREC_FP16 = 3,   /* tcgen05, single fp16 pass (the reference's own AMP dtype), fp32 accumulate  */
-  NB2_PREC_BF16X3 = 4  /* tcgen05, hi+lo bf16 split (16-bit), 3 MMAs                                  */
+  NB2_PREC_BF16X3 = 4, /* tcgen05, hi+lo bf16 split (16-bit), 3 MMAs                                  */
+  /* nb2_render_rays only: the proposal network (17 % of the FLOPs, but it places the fine samples, and the resampling
+     step amplifies its density errors) in the split precision, the NeRF network in a single pass */
+  NB2_PREC_FP16_MIXED = 5, /* proposal NB2_PREC_FP16X3, NeRF NB2_PREC_FP16 */
+  NB2_PREC_BF16_MIXED = 6  /* proposal NB2_PREC_BF16X3, NeRF NB2_PREC_BF16 */
 };
 
 /* Flags for nb2_composite / nb2_render_rays. */
 enum {
   NB2_WHITE_BKG = 1,      /* rgb += 1 - sum(w)                    nerf/nerf_base.py:103-105 */
-  NB2_DENSITY_SOFTPLUS = 2 /* proposal density softplus'd (train.py:169) instead of raw     */
+  NB2_DENSITY_SOFTPLUS = 2, /* proposal density softplus'd (train.py:169) instead of raw     */
+  NB2_PROPOSAL_IPE = 4    /* nb2_render_rays: the proposal network reads the INTEGRATED positional encoding of the conical
+                             frustum [z_s, z_{s+1}) of every coarse sample (z_P = z_{P-1} + (far - near) / (P - 1)) and the
+                             frustum's mean as its position: ipe_feature -> ProposalNetwork.forward(mu, encoded_pt)
+                             (nerf/mip_methods.py:47-58, nerf/addtional.py:88-91), evaluated in the kernel's producer.  The
+                             reference never connects the two; depths, weights and resampling are unchanged.  Keeps the
+                             reference's batch-global ||d|| (mip_methods.py:31) over the rays of the call. */
 };
 
 /* Error codes. */
@@ -233,7 +243,7 @@ typedef struct nb2_render_params {
    * image buffers of the other GPUs, mapped with nb2_ipc_open; the stores travel over NVLink and no gather kernel or
    * collective follows (callers fence with a barrier before reading the image). */
   int n_peers;
-  int reserved;
+  float ipe_radius;   /* NB2_PROPOSAL_IPE: pixel-footprint radius r of coneParameters (mip_methods.py:15-23) */
   float* peer_rgb[8];
 } nb2_render_params;
 

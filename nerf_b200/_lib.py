@@ -16,8 +16,9 @@ LIB_PATH = os.path.join(_HERE, os.environ.get("NB2_LIB", "libnerfb200.so"))
 
 NET_PROPOSAL, NET_NERF = 0, 1
 PREC_FP32, PREC_FP16X3, PREC_BF16, PREC_FP16, PREC_BF16X3 = 0, 1, 2, 3, 4
-PRECISIONS = {"fp32": PREC_FP32, "fp16x3": PREC_FP16X3, "bf16": PREC_BF16, "fp16": PREC_FP16, "bf16x3": PREC_BF16X3}
-WHITE_BKG, DENSITY_SOFTPLUS = 1, 2
+PRECISIONS = {"fp32": PREC_FP32, "fp16x3": PREC_FP16X3, "bf16": PREC_BF16, "fp16": PREC_FP16, "bf16x3": PREC_BF16X3,
+              "fp16m": 5, "bf16m": 6}     # mixed (render_rays only): proposal network split precision, NeRF network single pass
+WHITE_BKG, DENSITY_SOFTPLUS, PROPOSAL_IPE = 1, 2, 4
 
 c_f32p = ctypes.c_void_p
 c_i64 = ctypes.c_int64
@@ -36,7 +37,7 @@ class RenderParams(ctypes.Structure):
         ("flags", c_int), ("precision", c_int),
         ("seed", c_u64), ("ray_offset", c_i64),
         ("prop_net_id", c_int), ("nerf_net_id", c_int),
-        ("n_peers", c_int), ("reserved", c_int),
+        ("n_peers", c_int), ("ipe_radius", c_float),
         ("peer_rgb", c_vp * 8),
     ]
 

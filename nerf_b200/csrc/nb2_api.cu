@@ -226,6 +226,7 @@ extern "C" int64_t nb2_render_workspace_bytes(int64_t n_rays, const nb2_render_p
   b += align256(n_rays * p->n_coarse * 4);  // z_coarse
   b += align256(n_rays * p->n_coarse * 4);  // sigma_prop
   b += align256(n_rays * p->n_fine * 4);    // z_fine
+  b += 256;                                 // scalars (batch-global direction norm of the IPE mode)
   const bool fused = (p->precision != NB2_PREC_FP32) && (p->n_fine == 32 || p->n_fine == 64 || p->n_fine == 128);
   if (!fused) b += align256(n_rays * p->n_fine * 16);  // rgb-sigma per sample
   return b;
@@ -255,10 +256,13 @@ extern "C" int nb2_render_rays(nb2_handle* h, const nb2_render_params* p, const 
   float* z_coarse = (float*)ws; ws += align256(n_rays * p->n_coarse * 4);
   float* sigma_prop = (float*)ws; ws += align256(n_rays * p->n_coarse * 4);
   float* z_fine = (float*)ws; ws += align256(n_rays * p->n_fine * 4);
+  double* scalars = (double*)ws; ws += 256;
   if (z_coarse_out) z_coarse = z_coarse_out;
   if (sigma_prop_out) sigma_prop = sigma_prop_out;
   if (z_fine_out) z_fine = z_fine_out;
   const bool fused = (p->precision != NB2_PREC_FP32) && (p->n_fine == 32 || p->n_fine == 64 || p->n_fine == 128);
+  const int prec_prop = p->precision == NB2_PREC_FP16_MIXED ? (int)NB2_PREC_FP16X3 : (p->precision == NB2_PREC_BF16_MIXED ? (int)NB2_PREC_BF16X3 : p->precision);
+  const int prec_fine = p->precision == NB2_PREC_FP16_MIXED ? (int)NB2_PREC_FP16 : (p->precision == NB2_PREC_BF16_MIXED ? (int)NB2_PREC_BF16 : p->precision);
 
   // 1. stratified sampling + encoding + proposal MLP           nerf/procedures.py:65-67
   MlpIo io;
@@ -275,8 +279,19 @@ extern "C" int nb2_render_rays(nb2_handle* h, const nb2_render_params* p, const 
   io.out_mode = 0;
   io.out = sigma_prop;
   io.z_out = z_coarse;
+  if (p->flags & NB2_PROPOSAL_IPE) {
+    // BASELINE configs[2]: the proposal network reads the integrated positional encoding of the conical frustums between
+    // consecutive coarse depths (nerf/mip_methods.py:47-58 -> ProposalNetwork.forward(mu, encoded_pt), addtional.py:88-91)
+    NB2_CHECK_ARG(p->ipe_radius > 0.f, "render_rays: NB2_PROPOSAL_IPE needs ipe_radius > 0");
+    int rc0 = launch_ipe_sumsq(h, rays, n_rays, scalars, st);
+    if (rc0 != NB2_OK) return rc0;
+    io.ipe = 1;
+    io.ipe_radius = p->ipe_radius;
+    io.ipe_last_step = (p->far_t - p->near_t) / (float)(p->n_coarse - 1);
+    io.ipe_sumsq = scalars;
+  }
   if (h->prof[0]) NB2_CUDA(cudaEventRecord(h->prof[0], st));
-  int rc = mlp_dispatch(h, prop_id, p->precision, io, st);
+  int rc = mlp_dispatch(h, prop_id, prec_prop, io, st);
   if (rc != NB2_OK) return rc;
   if (h->prof[1]) NB2_CUDA(cudaEventRecord(h->prof[1], st));
 
@@ -304,14 +319,14 @@ extern "C" int nb2_render_rays(nb2_handle* h, const nb2_render_params* p, const 
     io.n_peers = p->n_peers;
     io.peer_row0 = p->ray_offset;
     for (int q = 0; q < p->n_peers; ++q) io.peer_rgb[q] = p->peer_rgb[q];
-    rc = mlp_dispatch(h, nerf_id, p->precision, io, st);
+    rc = mlp_dispatch(h, nerf_id, prec_fine, io, st);
     if (rc == NB2_OK && h->prof[3]) NB2_CUDA(cudaEventRecord(h->prof[3], st));
     return rc;
   }
   float* rgbo = (float*)ws;
   io.out_mode = 1;
   io.out = rgbo;
-  rc = mlp_dispatch(h, nerf_id, p->precision, io, st);
+  rc = mlp_dispatch(h, nerf_id, prec_fine, io, st);
   if (rc != NB2_OK) return rc;
   rc = nb2_composite(h, rgbo, z_fine, rays + 3, 6, n_rays, p->n_fine, p->flags, p->near_t, p->far_t, rgb_out, nullptr,
                      depth_out, acc_out, stream);

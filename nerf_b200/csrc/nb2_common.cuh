@@ -279,6 +279,11 @@ struct MlpIo {
   float resolution;
   uint64_t seed;
   int64_t ray_offset;
+  // in_mode 2, optional (NB2_PROPOSAL_IPE): the network input is the integrated positional encoding of the conical frustum
+  // [z_s, z_{s+1}) (z_P = z_{P-1} + ipe_last_step) instead of the point encoding at z_s        nerf/mip_methods.py:15-58
+  int ipe;
+  float ipe_radius, ipe_last_step;
+  const double* ipe_sumsq;  // device: sum over the launch's rays of ||d||^2 (the reference's batch-global norm, mip_methods.py:31)
   int P;                  // samples per ray (in_mode 1/2)
   int64_t n_rows;         // total MLP rows (= n_rays * P)
   // output selection
@@ -298,6 +303,7 @@ struct MlpIo {
 };
 int launch_mlp_simt(nb2_handle* h, int net_id, const MlpIo& io, cudaStream_t st);
 int launch_mlp_tc(nb2_handle* h, int net_id, int precision, const MlpIo& io, cudaStream_t st);
+int launch_ipe_sumsq(nb2_handle* h, const float* rays, int64_t n_rays, double* out, cudaStream_t st);
 int pack_network(nb2_handle* h, int net_id, const float* const* W, const float* const* b,
                  int n_layers, int pos_levels, int dir_levels, cudaStream_t st);
 

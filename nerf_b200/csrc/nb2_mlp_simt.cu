@@ -61,7 +61,7 @@ mlp_simt_kernel(SimtNet net, MlpIo io, const float* __restrict__ wt32, const flo
     {
       const int row = tid & (kSimtRows - 1), part = tid / kSimtRows;  // part in [0,4)
       RowIn in = load_row(io, row_base + row);
-      for (int c = part; c < kEncCols; c += 4) sm.E[c][row] = in.valid ? enc_column(in.p, c, pos_levels, in.enc) : 0.f;
+      for (int c = part; c < kEncCols; c += 4) sm.E[c][row] = in.valid ? enc_column(in.p, c, pos_levels, in.enc, in.ipe ? in.cov : nullptr) : 0.f;
       if (has_dir) {
         float rot[3] = {0.f, 0.f, 0.f};
         if (in.valid) normalize_dir(in.d, rot);

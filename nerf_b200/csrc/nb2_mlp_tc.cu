@@ -84,8 +84,8 @@ __device__ __forceinline__ void slot_group_run(const TcParams& p, TcMisc* misc, 
   EncRegs<SPLIT, F16, 0, 4> enc_a;   // encoding column groups 0-3: warpgroup 0 of a shared tile, or phase 0 of a whole-tile group
   EncRegs<SPLIT, F16, 4, 4> enc_b;   // groups 4-7:                 warpgroup 1,                  or phase 1
   auto enc_make = [&](const RowIn& r, int phase) {
-    if (EW == 2 ? (half == 0) : (phase == 0)) enc_compute(enc_a, r.p, p.pos_levels, r.valid, r.enc);
-    else enc_compute(enc_b, r.p, p.pos_levels, r.valid, r.enc);
+    if (EW == 2 ? (half == 0) : (phase == 0)) enc_compute(enc_a, r.p, p.pos_levels, r.valid, r.enc, r.ipe ? r.cov : nullptr);
+    else enc_compute(enc_b, r.p, p.pos_levels, r.valid, r.enc, r.ipe ? r.cov : nullptr);
   };
   auto begin_tile = [&]() {
     if (EW == 1 || half == 0) enc_store(enc_a, e_hi, e_lo, row);

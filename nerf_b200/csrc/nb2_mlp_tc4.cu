@@ -150,7 +150,7 @@ __device__ __forceinline__ void slot_group_run4(const TcParams& p, Tc4Misc* misc
     arrive_a();
   };
   RowIn in = load_row(p.io, tile_of(0) * kTileRows + row);
-  enc_compute(enc, in.p, p.pos_levels, in.valid, in.enc);
+  enc_compute(enc, in.p, p.pos_levels, in.valid, in.enc, in.ipe ? in.cov : nullptr);
   begin_tile();
 
   for (int64_t it = 0; it < n_iters; ++it) {
@@ -304,7 +304,7 @@ __device__ __forceinline__ void slot_group_run4(const TcParams& p, Tc4Misc* misc
 
       // ---- work hidden behind the next layer's MMAs ------------------------------------------------------------------
       const long long cpe = NB2_CLK();
-      if (has_next && l == 0) enc_compute(enc, in_next.p, p.pos_levels, in_next.valid, in_next.enc);
+      if (has_next && l == 0) enc_compute(enc, in_next.p, p.pos_levels, in_next.valid, in_next.enc, in_next.ipe ? in_next.cov : nullptr);
       if (l == p.dir_layer && g == 0) {
         // the encoded position is dead after the skip layer: its tile now takes the encoded direction (columns 0-31;
         // the bias k-step of the running layer reads columns 48-63 of the same rows, other 16-byte units)

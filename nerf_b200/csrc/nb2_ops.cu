@@ -725,6 +725,14 @@ __global__ void linear_to_srgb_kernel(const float* __restrict__ lin, int64_t n, 
   }
 }
 
+int launch_ipe_sumsq(nb2_handle* h, const float* rays, int64_t n_rays, double* out, cudaStream_t st) {
+  NB2_CUDA(cudaMemsetAsync(out, 0, sizeof(double), st));
+  int g = (int)std::min<int64_t>(grid_for(n_rays, 256), 1184);
+  ipe_sumsq_kernel<<<g, 256, 0, st>>>(rays, n_rays, out);
+  NB2_LAUNCH_CHECK(h);
+  return NB2_OK;
+}
+
 }  // namespace nb2
 
 // ==========================================================================================

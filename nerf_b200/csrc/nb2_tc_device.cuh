@@ -133,7 +133,7 @@ struct EncRegs {
 };
 template <bool SPLIT, bool F16, int G0, int NG>
 __device__ __forceinline__ void enc_compute(EncRegs<SPLIT, F16, G0, NG>& e, const float x[3], int levels, bool valid,
-                                            const float* ext) {
+                                            const float* ext, const float* cov = nullptr) {
   float v[kEncCols];
 #pragma unroll
   for (int c = 0; c < kEncCols; ++c) v[c] = 0.f;
@@ -153,6 +153,12 @@ __device__ __forceinline__ void enc_compute(EncRegs<SPLIT, F16, G0, NG>& e, cons
         for (int k = 0; k < 3; ++k) {
           float sn, cs;
           enc_sincos(x[k] * sc, sn, cs);
+          if (cov != nullptr) {
+            // integrated positional encoding (mip_methods.py:36-58): attenuation exp(-0.5 * 4^l * var_k) of the level
+            const float damp = expf(-0.5f * (sc * sc * cov[k]));
+            sn *= damp;
+            cs *= damp;
+          }
           v[3 + 6 * l + k] = sn;
           v[3 + 6 * l + 3 + k] = cs;
         }

@@ -339,7 +339,7 @@ def linear_to_srgb(linear):
 # ---- the fused path ---------------------------------------------------------------------------------
 def render_rays(rays, base_z, near, far, n_fine=128, white_bkg=False, precision=None, jitter=None, u=None, seed=0,
                 ray_offset=0, resolution=None, blur_alpha=0.01, softplus=False, debug=False, workspace=None,
-                prop_net_id=_lib.NET_PROPOSAL, nerf_net_id=_lib.NET_NERF, out=None, peer_rgb=()):
+                prop_net_id=_lib.NET_PROPOSAL, nerf_net_id=_lib.NET_NERF, out=None, peer_rgb=(), ipe_radius=None):
     """rays (R,6) -> dict(rgb (R,3), depth (R), acc (R) [, z_coarse, sigma_prop, z_fine, below_fine]).
 
     `out` re-uses a previous result's buffers (no allocation in the step); `peer_rgb`: device pointers (ints) of the
@@ -353,7 +353,8 @@ def render_rays(rays, base_z, near, far, n_fine=128, white_bkg=False, precision=
     p.near_t, p.far_t = float(near), float(far)
     p.resolution = float((far - near) / n_fine if resolution is None else resolution)
     p.blur_alpha = float(blur_alpha)
-    p.flags = (_lib.WHITE_BKG if white_bkg else 0) | (_lib.DENSITY_SOFTPLUS if softplus else 0)
+    p.flags = (_lib.WHITE_BKG if white_bkg else 0) | (_lib.DENSITY_SOFTPLUS if softplus else 0) | (_lib.PROPOSAL_IPE if ipe_radius else 0)
+    p.ipe_radius = float(ipe_radius or 0.0)
     p.precision = _prec(precision)
     p.seed, p.ray_offset = seed, ray_offset
     p.prop_net_id, p.nerf_net_id = prop_net_id, nerf_net_id

@@ -41,9 +41,9 @@ def test_render_params_struct_matches_header():
     # 2 int, 4 float, 2 int, u64, i64, 4 int, 8 pointers -> 128 bytes with natural alignment
     assert ctypes.sizeof(_lib.RenderParams) == 128
     p = _lib.RenderParams(n_coarse=64, n_fine=128, precision=_lib.PREC_BF16X3)
-    assert _lib.load().nb2_render_workspace_bytes(1000, ctypes.byref(p)) == 2 * 256000 + 512000
+    assert _lib.load().nb2_render_workspace_bytes(1000, ctypes.byref(p)) == 2 * 256000 + 512000 + 256
     p.precision = _lib.PREC_FP32
-    assert _lib.load().nb2_render_workspace_bytes(1000, ctypes.byref(p)) == 2 * 256000 + 512000 + 2048000
+    assert _lib.load().nb2_render_workspace_bytes(1000, ctypes.byref(p)) == 2 * 256000 + 512000 + 256 + 2048000
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")

@@ -81,3 +81,41 @@ def test_linear_to_srgb(golden_refnerf):
     g = inputs_refnerf()
     out = nerf_b200.linear_to_srgb(g["srgb_lin"].to(DEV)).cpu()
     assert float((out - golden_refnerf["srgb"]).abs().max()) <= 2e-6
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 2e-5), ("fp16x3", 3e-5), ("fp16", 2e-2), ("bf16", 8e-2)])
+def test_ipe_fused_into_the_proposal_producer(precision, tol):
+    """BASELINE configs[2]: NB2_PROPOSAL_IPE evaluates ipe_feature inside the proposal kernel's producer.
+    Parity against the staged reference composition ipe_feature -> ProposalNetwork.forward(mu, encoded_pt=feature)
+    (nerf/mip_methods.py:47-58, nerf/addtional.py:88-91; the oracle restatements of both are pinned by golden vectors),
+    on the conical frustums [z_s, z_{s+1}) of the 64 coarse depths (z_64 = z_63 + (far - near) / 63)."""
+    import nerf_b200
+    from nerf_b200 import ops
+    from oracle import nerf_oracle as O
+    H = W = 40
+    pose = nerf_b200.pose_spherical(30.0, -30.0, 4.0)[:3, :]
+    focal = nerf_b200.fov2Focal(0.6911112070083618, (H, W))[0]
+    rays = O.generate_rays(pose, H, W, focal)
+    R = rays.shape[0]
+    jitter, u = O.det_uniform((R, 64), 31, 0.0, 1.0), O.det_uniform((R, 129), 32, 0.0, 1.0)
+    base = torch.linspace(2.0, 6.0, 64)
+    radius = 2.0 / (focal * 12 ** 0.5)                       # mip-NeRF's pixel footprint radius: 2 / sqrt(12) pixel widths
+    sp, sn = O.make_params("proposal", 1, "smooth"), O.make_params("nerf", 2, "smooth")
+    prop = nerf_b200.ProposalNetwork(10, 256); net = nerf_b200.MipNeRF(10, 4, 256)
+    prop.load_state_dict(sp); net.load_state_dict(sn)
+    prop, net = prop.to(DEV), net.to(DEV)
+    ids = dict(prop_net_id=prop._nb2_sync(), nerf_net_id=net._nb2_sync())
+    out = ops.render_rays(rays.to(DEV), base.to(DEV), 2.0, 6.0, 128, white_bkg=True, precision=precision, jitter=jitter.to(DEV), u=u.to(DEV),
+                          debug=True, ipe_radius=radius, **ids)
+    # the reference composition on the same cones
+    z = base + jitter * (4.0 / 128)
+    edges = torch.cat((z, z[:, -1:] + 4.0 / 63), dim=-1)
+    feat, mu, _ = O.ipe_feature(edges, rays, 10, radius)
+    ref_sigma = O.proposal_forward(sp, mu, encoded=feat)
+    assert torch.equal(out["z_coarse"].cpu(), z)
+    err = float((out["sigma_prop"].cpu() - ref_sigma).abs().max()) / max(50.0, float(ref_sigma.abs().max()))
+    print(precision, "IPE proposal density: max relative error", err)
+    assert err <= tol
+    # and the image differs from the point-encoded render (the cones blur the high frequencies) but stays a valid image
+    plain = ops.render_rays(rays.to(DEV), base.to(DEV), 2.0, 6.0, 128, white_bkg=True, precision=precision, jitter=jitter.to(DEV), u=u.to(DEV), **ids)
+    assert bool(torch.isfinite(out["rgb"]).all()) and not torch.equal(out["rgb"], plain["rgb"])
