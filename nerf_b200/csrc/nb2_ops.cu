@@ -59,6 +59,45 @@ __global__ void sample_coarse_kernel(const float* __restrict__ rays, const float
   }
 }
 
+// Vectorised form (P % 4 == 0, 16-byte aligned pointers): one thread = four consecutive samples of a ray, so every global
+// access is a 16-byte vector and a warp covers whole 128-byte lines (the scalar form stores pts with a 12-byte stride).
+__global__ void sample_coarse_vec4_kernel(const float* __restrict__ rays, const float* __restrict__ base_z,
+                                          const float* __restrict__ jitter, float resolution, uint64_t seed, int64_t ray_offset,
+                                          int64_t n_rays, int P, float* __restrict__ z_out, float* __restrict__ pts_out) {
+  const int P4 = P >> 2;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rays * P4) return;
+  const int64_t r = i / P4;
+  const int s0 = (int)(i - r * P4) * 4;
+  float j[4];
+  if (jitter) {
+    const float4 jv = __ldg(reinterpret_cast<const float4*>(jitter) + i);
+    j[0] = jv.x; j[1] = jv.y; j[2] = jv.z; j[3] = jv.w;
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) j[k] = philox_uniform(seed, (uint64_t)(ray_offset + r), (uint32_t)(s0 + k), 0u);
+  }
+  const float4 bz = __ldg(reinterpret_cast<const float4*>(base_z + s0));
+  const float b[4] = {bz.x, bz.y, bz.z, bz.w};
+  float z[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) z[k] = __fadd_rn(b[k], __fmul_rn(j[k], resolution));
+  reinterpret_cast<float4*>(z_out)[i] = make_float4(z[0], z[1], z[2], z[3]);
+  if (pts_out) {
+    const float* ray = rays + r * 6;
+    const float o[3] = {__ldg(ray), __ldg(ray + 1), __ldg(ray + 2)}, d[3] = {__ldg(ray + 3), __ldg(ray + 4), __ldg(ray + 5)};
+    float v[12];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) v[3 * k + c] = __fadd_rn(o[c], __fmul_rn(z[k], d[c]));
+    float4* dst = reinterpret_cast<float4*>(pts_out) + i * 3;
+    dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+    dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+    dst[2] = make_float4(v[8], v[9], v[10], v[11]);
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // a5  sinusoidal positional encoding                /root/reference/nerf/nerf_helper.py:38-48
 //   out[p, 6l + c] = sin(2^l x[p,c]), out[p, 6l + 3 + c] = cos(2^l x[p,c])
@@ -106,41 +145,57 @@ __global__ void ipe_sumsq_kernel(const float* __restrict__ rays, int64_t n_rays,
   if ((threadIdx.x & 31) == 0) atomicAdd(acc, s);
 }
 
-__global__ void ipe_kernel(const float* __restrict__ zvals, const float* __restrict__ rays,
-                           int64_t n_rays, int C, int L, float radius, const double* __restrict__ sumsq,
-                           float* __restrict__ feat, float* __restrict__ mu_out, float* __restrict__ mu_t_out) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_rays * C) return;
-  int64_t r = i / C;
-  int c = (int)(i % C);
-  const float gnorm = (float)sqrt(*sumsq);  // batch-global ||d||_F  (mip_methods.py:31)
-  float z0 = zvals[r * (C + 1) + c], z1 = zvals[r * (C + 1) + c + 1];
-  // coneParameters (mip_methods.py:15-23)
-  float mid = (z1 + z0) / 2.f;
-  float hw = (z1 - z0) / 2.f;
-  float diff = hw * hw;
-  float tmp1 = 3.f * mid * mid + diff;
-  float mu_t = mid + 2.f * mid * diff / tmp1;
-  float sigma_t2 = diff / 3.f - 4.f * (diff * diff) * (12.f * mid * mid - diff) / 15.f / (tmp1 * tmp1);
-  float sigma_r2 = (radius * radius) * (0.25f * mid * mid + 5.f / 12.f * diff - 4.f * diff * diff / (15.f * tmp1));
-  if (mu_t_out) mu_t_out[i] = mu_t;
-  const float* ray = rays + r * 6;
-  float* f = feat + i * (int64_t)(6 * L);
+// One thread per cone; a block's 128 x 6L feature tile is assembled in shared memory (row pitch 6L + 1: conflict-free for
+// the per-thread writes) and written back with coalesced stores -- the direct form (60 scalar stores per thread at a
+// 240-byte thread stride) ran at 0.10 of the copy bandwidth.
+constexpr int kIpeBlock = 128;
+__global__ void __launch_bounds__(kIpeBlock)
+ipe_kernel(const float* __restrict__ zvals, const float* __restrict__ rays, int64_t n_rays, int C, int L, float radius,
+           const double* __restrict__ sumsq, float* __restrict__ feat, float* __restrict__ mu_out, float* __restrict__ mu_t_out) {
+  extern __shared__ float ipe_tile[];          // [kIpeBlock][6 L + 1]
+  const int width = 6 * L, pitch = width + 1;
+  const int64_t i0 = (int64_t)blockIdx.x * kIpeBlock;
+  const int64_t i = i0 + threadIdx.x;
+  const int64_t total = n_rays * C;
+  if (i < total) {
+    const int64_t r = i / C;
+    const int c = (int)(i % C);
+    const float gnorm = (float)sqrt(*sumsq);  // batch-global ||d||_F  (mip_methods.py:31)
+    float z0 = zvals[r * (C + 1) + c], z1 = zvals[r * (C + 1) + c + 1];
+    // coneParameters (mip_methods.py:15-23)
+    float mid = (z1 + z0) / 2.f;
+    float hw = (z1 - z0) / 2.f;
+    float diff = hw * hw;
+    float tmp1 = 3.f * mid * mid + diff;
+    float mu_t = mid + 2.f * mid * diff / tmp1;
+    float sigma_t2 = diff / 3.f - 4.f * (diff * diff) * (12.f * mid * mid - diff) / 15.f / (tmp1 * tmp1);
+    float sigma_r2 = (radius * radius) * (0.25f * mid * mid + 5.f / 12.f * diff - 4.f * diff * diff / (15.f * tmp1));
+    if (mu_t_out) mu_t_out[i] = mu_t;
+    const float* ray = rays + r * 6;
+    float* f = ipe_tile + threadIdx.x * pitch;
 #pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    float o = __ldg(ray + k), d = __ldg(ray + 3 + k);
-    float mu = o + mu_t * d;                       // coneMeanCov (mip_methods.py:27-33)
-    float dd = d * d;
-    float diag = sigma_t2 * dd + sigma_r2 * (1.f - dd / gnorm);
-    if (mu_out) mu_out[i * 3 + k] = mu;
-    for (int l = 0; l < L; ++l) {                   // multFreq + ipe_feature (mip_methods.py:36-58)
-      float scale = exp2f((float)l);
-      float damp = expf(-0.5f * (scale * scale * diag));
-      float s, co;
-      sincos_any(scale * mu, s, co);
-      f[6 * l + k] = s * damp;
-      f[6 * l + 3 + k] = co * damp;
+    for (int k = 0; k < 3; ++k) {
+      float o = __ldg(ray + k), d = __ldg(ray + 3 + k);
+      float mu = o + mu_t * d;                       // coneMeanCov (mip_methods.py:27-33)
+      float dd = d * d;
+      float diag = sigma_t2 * dd + sigma_r2 * (1.f - dd / gnorm);
+      if (mu_out) mu_out[i * 3 + k] = mu;
+      for (int l = 0; l < L; ++l) {                   // multFreq + ipe_feature (mip_methods.py:36-58)
+        float scale = exp2f((float)l);
+        float damp = expf(-0.5f * (scale * scale * diag));
+        float s, co;
+        sincos_any(scale * mu, s, co);
+        f[6 * l + k] = s * damp;
+        f[6 * l + 3 + k] = co * damp;
+      }
     }
+  }
+  __syncthreads();
+  const int ncones = (int)min((int64_t)kIpeBlock, total - i0);
+  float* dst = feat + i0 * width;
+  for (int t = threadIdx.x; t < ncones * width; t += kIpeBlock) {
+    const int cn = t / width, j = t - cn * width;
+    dst[t] = ipe_tile[cn * pitch + j];
   }
 }
 
@@ -179,23 +234,40 @@ __device__ __forceinline__ float dir_norm(const float* d) {
 }
 
 // a7  ProposalNetwork.get_weights / NeRF.getNormedWeight
+// One warp per ray, warps loop over rays (persistent grid) and keep the NEXT ray's rows in flight in registers while the
+// current ray is scanned out of shared memory: a warp-per-ray kernel is latency-bound otherwise (two 256-byte rows per
+// warp in flight = 0.30 of the copy bandwidth at 64 samples).
 __global__ void __launch_bounds__(32 * kWarpsPerBlock)
 weights_kernel(const float* __restrict__ sigma, const float* __restrict__ z, const float* __restrict__ dirs,
                int dir_stride, int64_t n_rays, int P, int act, float* __restrict__ w_out) {
   __shared__ float sh[kWarpsPerBlock][3][kMaxSamples];
-  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t stride = (int64_t)gridDim.x * kWarpsPerBlock;
   int64_t r = (int64_t)blockIdx.x * kWarpsPerBlock + warp;
-  if (r >= n_rays) return;
+  constexpr int kPer = kMaxSamples / 32;
+  float zr[kPer], sr[kPer];
   float nrm = 1.f;
-  if (dirs) nrm = dir_norm(dirs + r * dir_stride);
-  for (int i = lane; i < P; i += 32) {
-    float zz = z[r * P + i];
-    sh[warp][0][i] = dirs ? __fmul_rn(zz, nrm) : zz;
-    sh[warp][1][i] = sigma[r * P + i];
+  auto fetch = [&](int64_t ray) {
+#pragma unroll
+    for (int q = 0; q < kPer; ++q) {
+      const int i = lane + 32 * q;
+      if (i < P) { zr[q] = __ldg(z + ray * P + i); sr[q] = __ldg(sigma + ray * P + i); }
+    }
+    nrm = dirs ? dir_norm(dirs + ray * dir_stride) : 1.f;
+  };
+  if (r < n_rays) fetch(r);
+  for (; r < n_rays; r += stride) {
+#pragma unroll
+    for (int q = 0; q < kPer; ++q) {
+      const int i = lane + 32 * q;
+      if (i < P) { sh[warp][0][i] = dirs ? __fmul_rn(zr[q], nrm) : zr[q]; sh[warp][1][i] = sr[q]; }
+    }
+    if (r + stride < n_rays) fetch(r + stride);          // in flight during the scan below
+    __syncwarp();
+    ray_weights_warp(sh[warp][0], sh[warp][1], sh[warp][2], P, act, lane);
+    for (int i = lane; i < P; i += 32) w_out[r * P + i] = sh[warp][2][i];
+    __syncwarp();
   }
-  __syncwarp();
-  ray_weights_warp(sh[warp][0], sh[warp][1], sh[warp][2], P, act, lane);
-  for (int i = lane; i < P; i += 32) w_out[r * P + i] = sh[warp][2][i];
 }
 
 // a8  maxBlurFilter                                  /root/reference/nerf/mip_methods.py:61-66
@@ -211,6 +283,26 @@ __global__ void max_blur_kernel(const float* __restrict__ w, int64_t n_rays, int
   int64_t r = i / P;
   int s = (int)(i % P);
   out[i] = max_blur_at(w + r * P, s, P, alpha);
+}
+
+// vectorised: four samples per thread (P % 4 == 0): one float4 load (+ two neighbours through L1), one float4 store
+__global__ void max_blur_vec4_kernel(const float* __restrict__ w, int64_t n_rays, int P, float alpha, float* __restrict__ out) {
+  const int P4 = P >> 2;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rays * P4) return;
+  const int64_t r = i / P4;
+  const int s0 = (int)(i - r * P4) * 4;
+  const float* wr = w + r * P;
+  const float4 c = __ldg(reinterpret_cast<const float4*>(wr + s0));
+  const float v[6] = {s0 > 0 ? __ldg(wr + s0 - 1) : c.x, c.x, c.y, c.z, c.w, s0 + 4 < P ? __ldg(wr + s0 + 4) : c.w};
+  float o[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float front = (s0 + k == 0) ? v[1] : fmaxf(v[k], v[k + 1]);
+    const float rear = (s0 + k == P - 1) ? v[k + 1] : fmaxf(v[k + 1], v[k + 2]);
+    o[k] = __fadd_rn(__fmul_rn(0.5f, __fadd_rn(front, rear)), alpha);
+  }
+  reinterpret_cast<float4*>(out)[i] = make_float4(o[0], o[1], o[2], o[3]);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -479,6 +571,32 @@ __global__ void length2pts_kernel(const float* __restrict__ rays, const float* _
     o[k] = __fadd_rn(__ldg(ray + k), __fmul_rn(d, zz));
     o[3 + k] = d;
   }
+}
+
+// vectorised: four samples per thread (P % 4 == 0): a float4 of depths in, six float4 (4 x [point, direction]) out.
+// (A flat one-float4-per-thread form with fully contiguous stores measured SLOWER, 292 vs 137 us: the 64-bit index
+// divisions per output element cost more than the 96-byte thread stride of the stores.)
+__global__ void length2pts_vec4_kernel(const float* __restrict__ rays, const float* __restrict__ z, int64_t n_rays, int P,
+                                       float* __restrict__ pts) {
+  const int P4 = P >> 2;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rays * P4) return;
+  const int64_t r = i / P4;
+  const float* ray = rays + r * 6;
+  const float o[3] = {__ldg(ray), __ldg(ray + 1), __ldg(ray + 2)}, d[3] = {__ldg(ray + 3), __ldg(ray + 4), __ldg(ray + 5)};
+  const float4 zv = __ldg(reinterpret_cast<const float4*>(z) + i);
+  const float zz[4] = {zv.x, zv.y, zv.z, zv.w};
+  float v[24];
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      v[6 * k + c] = __fadd_rn(o[c], __fmul_rn(d[c], zz[k]));
+      v[6 * k + 3 + c] = d[c];
+    }
+  float4* dst = reinterpret_cast<float4*>(pts) + i * 6;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) dst[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
 }
 
 // a13  NeRF.coarseFineMerge                          /root/reference/nerf/nerf_base.py:58-73
@@ -762,8 +880,14 @@ extern "C" int nb2_sample_coarse(nb2_handle* h, const float* rays, const float* 
   NB2_CHECK_ARG(base_z && z_out && n_samples > 0 && n_rays >= 0, "sample_coarse: bad arguments");
   NB2_CHECK_ARG(!pts_out || rays, "sample_coarse: pts_out requires rays");
   if (n_rays == 0) return NB2_OK;
-  sample_coarse_kernel<<<grid_for(n_rays * n_samples, 256), 256, 0, (cudaStream_t)stream>>>(
-      rays, base_z, jitter, resolution, seed, ray_offset, n_rays, n_samples, z_out, pts_out);
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  if ((n_samples & 3) == 0 && al16(base_z) && al16(jitter) && al16(z_out) && al16(pts_out)) {
+    sample_coarse_vec4_kernel<<<grid_for(n_rays * (n_samples >> 2), 256), 256, 0, (cudaStream_t)stream>>>(
+        rays, base_z, jitter, resolution, seed, ray_offset, n_rays, n_samples, z_out, pts_out);
+  } else {
+    sample_coarse_kernel<<<grid_for(n_rays * n_samples, 256), 256, 0, (cudaStream_t)stream>>>(
+        rays, base_z, jitter, resolution, seed, ray_offset, n_rays, n_samples, z_out, pts_out);
+  }
   NB2_LAUNCH_CHECK(h);
   return NB2_OK;
 }
@@ -795,8 +919,13 @@ extern "C" int nb2_ipe(nb2_handle* h, const float* zvals, const float* rays, int
   int g = (int)std::min<int64_t>(grid_for(n_rays, 256), 1184);
   ipe_sumsq_kernel<<<g, 256, 0, st>>>(rays, n_rays, (double*)scratch);
   NB2_LAUNCH_CHECK(h);
-  ipe_kernel<<<grid_for(n_rays * n_cones, 128), 128, 0, st>>>(zvals, rays, n_rays, n_cones, levels, radius,
-                                                             (const double*)scratch, feat_out, mu_out, mu_t_out);
+  {
+    const int smem = kIpeBlock * (6 * levels + 1) * (int)sizeof(float);
+    const int rc = kernel_set_smem(h, (const void*)ipe_kernel, 64 * 1024);
+    if (rc != NB2_OK) return rc;
+    ipe_kernel<<<grid_for(n_rays * n_cones, kIpeBlock), kIpeBlock, smem, st>>>(zvals, rays, n_rays, n_cones, levels, radius,
+                                                                              (const double*)scratch, feat_out, mu_out, mu_t_out);
+  }
   NB2_LAUNCH_CHECK(h);
   return NB2_OK;
 }
@@ -810,8 +939,11 @@ extern "C" int nb2_weights_from_sigma(nb2_handle* h, const float* sigma, const f
   NB2_CHECK_ARG(!dirs || dir_stride >= 3, "weights_from_sigma: dir_stride < 3");
   NB2_CHECK_ARG(act >= 0 && act <= 2, "weights_from_sigma: unknown activation %d", act);
   if (n_rays == 0) return NB2_OK;
-  weights_kernel<<<grid_for(n_rays, kWarpsPerBlock), 32 * kWarpsPerBlock, 0, (cudaStream_t)stream>>>(
-      sigma, z, dirs, dir_stride, n_rays, n_samples, act, weights_out);
+  {
+    const int64_t blocks = grid_for(n_rays, kWarpsPerBlock);
+    const int grid = (int)std::min<int64_t>(blocks, (int64_t)h->sm_count * 8);     // 64 resident warps per SM, each looping over rays
+    weights_kernel<<<grid, 32 * kWarpsPerBlock, 0, (cudaStream_t)stream>>>(sigma, z, dirs, dir_stride, n_rays, n_samples, act, weights_out);
+  }
   NB2_LAUNCH_CHECK(h);
   return NB2_OK;
 }
@@ -822,7 +954,10 @@ extern "C" int nb2_max_blur(nb2_handle* h, const float* weights, int64_t n_rays,
   if (n_rays == 0) return NB2_OK;
   NB2_CHECK_ARG(weights && out && n_samples >= 1, "max_blur: bad arguments");
   if (n_rays == 0) return NB2_OK;
-  max_blur_kernel<<<grid_for(n_rays * n_samples, 256), 256, 0, (cudaStream_t)stream>>>(weights, n_rays, n_samples, alpha, out);
+  if ((n_samples & 3) == 0 && n_samples >= 8 && (reinterpret_cast<uintptr_t>(weights) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0)
+    max_blur_vec4_kernel<<<grid_for(n_rays * (n_samples >> 2), 256), 256, 0, (cudaStream_t)stream>>>(weights, n_rays, n_samples, alpha, out);
+  else
+    max_blur_kernel<<<grid_for(n_rays * n_samples, 256), 256, 0, (cudaStream_t)stream>>>(weights, n_rays, n_samples, alpha, out);
   NB2_LAUNCH_CHECK(h);
   return NB2_OK;
 }
@@ -891,7 +1026,10 @@ extern "C" int nb2_length2pts(nb2_handle* h, const float* rays, const float* z, 
   if (n_rays == 0) return NB2_OK;
   NB2_CHECK_ARG(rays && z && pts_out && n_samples >= 1, "length2pts: bad arguments");
   if (n_rays == 0) return NB2_OK;
-  length2pts_kernel<<<grid_for(n_rays * n_samples, 256), 256, 0, (cudaStream_t)stream>>>(rays, z, n_rays, n_samples, pts_out);
+  if ((n_samples & 3) == 0 && (reinterpret_cast<uintptr_t>(z) & 15) == 0 && (reinterpret_cast<uintptr_t>(pts_out) & 15) == 0)
+    length2pts_vec4_kernel<<<grid_for(n_rays * (n_samples >> 2), 256), 256, 0, (cudaStream_t)stream>>>(rays, z, n_rays, n_samples, pts_out);
+  else
+    length2pts_kernel<<<grid_for(n_rays * n_samples, 256), 256, 0, (cudaStream_t)stream>>>(rays, z, n_rays, n_samples, pts_out);
   NB2_LAUNCH_CHECK(h);
   return NB2_OK;
 }
@@ -924,6 +1062,15 @@ extern "C" int nb2_coarse_fine_merge_inds(nb2_handle* h, const float* rays, cons
   return NB2_OK;
 }
 
+static int launch_composite(nb2_handle* h, const float* rgbo, const float* z, const float* dirs, int dir_stride, int64_t n_rays, int n_samples,
+                            int flags, float near_t, float far_t, float* rgb_out, float* weights_out, float* depth_out, float* acc_out,
+                            const float* aux, float* aux_out, cudaStream_t st) {
+  composite_kernel<<<grid_for(n_rays, kWarpsPerBlock), 32 * kWarpsPerBlock, 0, st>>>(
+      rgbo, z, dirs, dir_stride, n_rays, n_samples, flags, near_t, far_t, rgb_out, weights_out, depth_out, acc_out, aux, aux_out);
+  NB2_LAUNCH_CHECK(h);
+  return NB2_OK;
+}
+
 extern "C" int nb2_composite(nb2_handle* h, const float* rgbo, const float* z, const float* dirs, int dir_stride,
                              int64_t n_rays, int n_samples, int flags, float near_t, float far_t, float* rgb_out,
                              float* weights_out, float* depth_out, float* acc_out, void* stream) {
@@ -933,10 +1080,8 @@ extern "C" int nb2_composite(nb2_handle* h, const float* rgbo, const float* z, c
   NB2_CHECK_ARG(dir_stride >= 3, "composite: dir_stride < 3");
   NB2_CHECK_ARG(n_samples >= 1 && n_samples <= kMaxSamples, "composite: n_samples must be in [1,%d]", kMaxSamples);
   if (n_rays == 0) return NB2_OK;
-  composite_kernel<<<grid_for(n_rays, kWarpsPerBlock), 32 * kWarpsPerBlock, 0, (cudaStream_t)stream>>>(
-      rgbo, z, dirs, dir_stride, n_rays, n_samples, flags, near_t, far_t, rgb_out, weights_out, depth_out, acc_out, nullptr, nullptr);
-  NB2_LAUNCH_CHECK(h);
-  return NB2_OK;
+  return launch_composite(h, rgbo, z, dirs, dir_stride, n_rays, n_samples, flags, near_t, far_t, rgb_out, weights_out, depth_out, acc_out,
+                          nullptr, nullptr, (cudaStream_t)stream);
 }
 
 extern "C" int nb2_composite_aux(nb2_handle* h, const float* rgbo, const float* z, const float* dirs, int dir_stride, int64_t n_rays,
@@ -947,10 +1092,8 @@ extern "C" int nb2_composite_aux(nb2_handle* h, const float* rgbo, const float* 
   NB2_CHECK_ARG(rgbo && z && dirs && rgb_out && aux && aux_out, "composite_aux: null pointer");
   NB2_CHECK_ARG(dir_stride >= 3, "composite_aux: dir_stride < 3");
   NB2_CHECK_ARG(n_samples >= 1 && n_samples <= kMaxSamples, "composite_aux: n_samples must be in [1,%d]", kMaxSamples);
-  composite_kernel<<<grid_for(n_rays, kWarpsPerBlock), 32 * kWarpsPerBlock, 0, (cudaStream_t)stream>>>(
-      rgbo, z, dirs, dir_stride, n_rays, n_samples, flags, near_t, far_t, rgb_out, weights_out, depth_out, acc_out, aux, aux_out);
-  NB2_LAUNCH_CHECK(h);
-  return NB2_OK;
+  return launch_composite(h, rgbo, z, dirs, dir_stride, n_rays, n_samples, flags, near_t, far_t, rgb_out, weights_out, depth_out, acc_out,
+                          aux, aux_out, (cudaStream_t)stream);
 }
 
 extern "C" int nb2_valid_sampler(nb2_handle* h, const float* rgbs, const int64_t* coords, const float* cam_tf,
