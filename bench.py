@@ -40,7 +40,7 @@ FLOP_NERF_PER_RAY = 135135232      # 2*(63*256 + 3*256^2 + 319*256 + 2*256^2 + 2
 METRIC = "rays/sec (64c+128f samples)"
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE fine-kernel launch, per ray, from the ncu --set full captures
 # summarised in profiles/ (algorithmic: 556 B/ray; the 2.4 MB of packed weights stay L2-resident)
-NCU_FINE_TRAFFIC_BYTES_PER_RAY = {"fp16x3": 93.1e6 / 160000, "bf16x3": 93.1e6 / 160000, "fp16": 91.9e6 / 160000, "bf16": 91.9e6 / 160000}
+NCU_FINE_TRAFFIC_BYTES_PER_RAY = {"fp16x3": 93.34e6 / 160000, "bf16x3": 93.34e6 / 160000, "fp16": 92.16e6 / 160000, "bf16": 92.16e6 / 160000}   # profiles/r02_ncu_tc{4_fp16x3,2_fp16}_fine.txt
 FINE_KERNEL = {"fp16x3": "mlp_tc4_kernel (fine: encode + 8x256 MLP + composite; CTA-pair tcgen05, activations in TMEM)",
                "bf16x3": "mlp_tc4_kernel (fine: encode + 8x256 MLP + composite; CTA-pair tcgen05, activations in TMEM)",
                "fp16": "mlp_tc2_kernel (fine: encode + 8x256 MLP + composite; CTA-pair tcgen05, ping-pong tiles)",

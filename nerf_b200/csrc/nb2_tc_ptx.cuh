@@ -257,10 +257,13 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 }
 __device__ __forceinline__ float bf16_lo_to_f32(uint32_t packed) { return __uint_as_float(packed << 16); }
 __device__ __forceinline__ float bf16_hi_to_f32(uint32_t packed) { return __uint_as_float(packed & 0xFFFF0000u); }
-// two fp32 -> packed f16x2 (lo half = first argument), round-to-nearest-even (overflow -> inf)
+// two fp32 -> packed f16x2 (lo half = first argument), round-to-nearest-even, SATURATING at +-65504: a hidden activation
+// beyond the fp16 range must not become inf (hi = inf makes the residual -inf and the split product inf - inf = NaN for the
+// whole row); with both halves saturating, x ~ hi + lo stays finite and exact up to |x| < 65504 and monotone up to 131008.
+// (The bf16x3 mode has fp32's exponent range and is the choice for networks whose activations exceed that.)
 __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
   uint32_t r;
-  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
 __device__ __forceinline__ float2 f16x2_to_f32(uint32_t packed) {
@@ -272,7 +275,7 @@ __device__ __forceinline__ float2 f16x2_to_f32(uint32_t packed) {
 template <bool F16>
 __device__ __forceinline__ uint32_t pack16x2_relu(float lo, float hi) {
   uint32_t r;
-  if (F16) asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  if (F16) asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   else     asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
@@ -282,8 +285,14 @@ __device__ __forceinline__ uint32_t pack16x2(float lo, float hi) { return F16 ? 
 template <bool F16>
 __device__ __forceinline__ uint32_t residual16x2(float a, float b, uint32_t hi_packed) {
   if (F16) {
-    const float2 h = f16x2_to_f32(hi_packed);
-    return pack_f16x2(a - h.x, b - h.y);
+    // a - float(hi) in ONE mixed-precision instruction per element (fma.rn.f32.f16 = FHFMA, fp16 x fp16 + fp32 -> fp32,
+    // reading either half of the packed register): hi * (-1) + a.  The difference is exact, so the bits are those of the
+    // convert-then-subtract form it replaces (two conversions + two subtractions per pair).
+    float l0, l1;
+    asm("{\n\t.reg .b16 lo, hi, m1;\n\tmov.b32 {lo, hi}, %2;\n\tmov.b16 m1, 0xBC00;\n\t"
+        "fma.rn.f32.f16 %0, lo, m1, %3;\n\tfma.rn.f32.f16 %1, hi, m1, %4;\n\t}"
+        : "=f"(l0), "=f"(l1) : "r"(hi_packed), "f"(a), "f"(b));
+    return pack_f16x2(l0, l1);
   }
   return pack_bf16x2(a - bf16_lo_to_f32(hi_packed), b - bf16_hi_to_f32(hi_packed));
 }

@@ -178,3 +178,25 @@ def test_two_devices_in_one_process():
             outs.append(net.forward(pts.to(f"cuda:{d}")).cpu())
         assert torch.cuda.current_device() == 0
     assert torch.equal(outs[0], outs[1])
+
+
+def test_fp16_modes_saturate_instead_of_overflowing():
+    """Hidden activations beyond the fp16 range (65504): the fp16 packs saturate (cvt.rn.satfinite), so the fp16x3 / fp16
+    modes return finite values instead of inf - inf = NaN rows; bf16x3 (fp32's exponent range) stays accurate."""
+    sn = O.make_params("nerf", 2, "he")
+    sn = {k: v.clone() for k, v in sn.items()}
+    sn["lin_block1.0.weight"] *= 3.0e4                      # first hidden layer ~1e5
+    sn["lin_block1.2.weight"] *= 1.0 / 3.0e4                # ... rescaled back by the next layer
+    net = load(nerf_b200.MipNeRF(10, 4, 256), sn)
+    pts = torch.cat((O.det_uniform((1024, 3), 9, -2.0, 2.0), O.det_uniform((1024, 3), 10, -1.0, 1.0)), -1).to(DEV)
+    ref = O.nerf_forward(O.params_to(sn, DEV), pts)
+    h1 = torch.relu(torch.nn.functional.linear(torch.cat((pts[:, :3], O.positional_encoding(pts[:, :3], 10)), -1), sn["lin_block1.0.weight"].to(DEV),
+                                               sn["lin_block1.0.bias"].to(DEV)))
+    assert float(h1.max()) > 65504.0
+    with torch.no_grad():
+        for precision in ("fp16x3", "fp16"):
+            net.precision = precision
+            assert bool(torch.isfinite(net.forward(pts[None])).all()), precision
+        net.precision = "bf16x3"
+        out = net.forward(pts[None])[0]
+    assert float((out[:, :3] - ref[:, :3]).abs().max()) <= 1e-3
