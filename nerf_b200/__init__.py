@@ -16,6 +16,6 @@ from .ref_model import RefNeRF  # noqa: F401
 from .addtional import ProposalNetwork, LossPSNR, SoftL1Loss, ProposalLoss, getBounds  # noqa: F401
 from .mip_methods import maxBlurFilter, ipe_feature  # noqa: F401
 from .utils import inverseSample, sample_pdf, fov2Focal, pose_spherical, validSampler  # noqa: F401
-from .procedures import render_image, get_patch_size  # noqa: F401
+from .procedures import render_image, get_patch_size, get_parser, render_only  # noqa: F401
 
 __version__ = "0.1.0"

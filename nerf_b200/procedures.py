@@ -5,6 +5,7 @@ per tile (reference nerf/procedures.py:60-90).  Here the whole image is one ray 
 generated on the device, and nb2_render_rays runs three kernels (fused sample+encode+proposal
 MLP, resample, fused encode+NeRF MLP+composite) over all H*W rays.
 """
+import os
 from collections.abc import Iterable
 
 import torch
@@ -174,3 +175,86 @@ def _render_image_ref(network, prop_net, render_pose, image_size, focal_xy, near
         if render_normal:
             result["normal_img"] = image((n_img + 1.0) * 0.5, 1).expand(3, H, W).contiguous()               # nerf_base.py:112
     return result
+
+
+# ---- executables' call surface: argument parser and the render-only driver ---------------------------------
+def get_parser():
+    """The reference's command line (nerf/procedures.py:166-213): same flags, types and defaults, so train.py / ddp_train.py
+    style drivers parse identically.  (tests/golden/reference_parser_defaults.json pins the defaults.)"""
+    import argparse
+    parser = argparse.ArgumentParser()
+    ints = [("epochs", 2400), ("max_save", 3), ("sample_ray_num", 1024), ("coarse_sample_pnum", 64), ("fine_sample_pnum", 128),
+            ("eval_time", 5), ("output_time", 20), ("center_crop_iter", 0), ("prop_net_width", 256), ("nerf_net_width", 256),
+            ("decay_step", 100000), ("warmup_step", 500), ("ide_level", 4)]
+    floats = [("near", 2.), ("far", 6.), ("center_crop_x", 0.5), ("center_crop_y", 0.5), ("img_scale", 0.5), ("scene_scale", 1.0),
+              ("grad_clip", -0.01), ("pe_period_scale", 0.5), ("min_ratio", 0.01), ("decay_rate", 0.1), ("lr", 1.5e-4), ("bottle_neck_noise", 0.02)]
+    strs = [("name", "model_1"), ("dataset_name", "lego"), ("opt_mode", "O1")]
+    for name, default in ints:
+        parser.add_argument("--" + name, type=int, default=default)
+    for name, default in floats:
+        parser.add_argument("--" + name, type=float, default=default)
+    for name, default in strs:
+        parser.add_argument("--" + name, type=str, default=default)
+    for short, name in (("-d", "del_dir"), ("-l", "load"), ("-s", "use_scaler"), ("-b", "debug"), ("-v", "visualize"), ("-r", "do_render"),
+                        ("-w", "white_bkg"), ("-t", "ref_nerf"), ("-u", "use_srgb"), ("-e", "eval_poses")):
+        parser.add_argument(short, "--" + name, default=False, action="store_true")
+    for name in ("render_depth", "render_normal", "prop_normal"):
+        parser.add_argument("--" + name, default=False, action="store_true")
+    return parser
+
+
+def render_only(args, model_path: str, opt_level: str = "O1", dataset_root="../dataset/", output_root="./output/", max_frames=None):
+    """The reference's render-only driver (nerf/procedures.py:99-164): load the two checkpoints, render the 120-pose orbit
+    (or the test-set poses with PSNR against the ground truth when args.eval_poses) and save result_%03d.png.
+    `args.use_scaler` selects the single-pass tensor precision (the analogue of the reference's AMP render); apex is not used."""
+    from torchvision import transforms
+    from torchvision.utils import save_image
+    from .addtional import LossPSNR, SoftL1Loss
+    from .dataset import AdaptiveResize, CustomDataSet
+    from .mip_model import MipNeRF
+    from .ref_model import RefNeRF
+    from .utils import fov2Focal, pose_spherical
+    eval_poses = args.eval_poses
+    render_normal = args.render_normal & (not eval_poses)
+    render_depth = args.render_depth & (not eval_poses)
+    transform_funcs = transforms.Compose([AdaptiveResize(args.img_scale), transforms.ToTensor()])
+    testset = CustomDataSet("%s%s/" % (dataset_root, args.dataset_name), transform_funcs, args.scene_scale, False, use_alpha=False)
+    cam_fov_test, _ = testset.getCameraParam()
+    r_c = testset.r_c()
+    if eval_poses:
+        all_poses = testset.tfs.cuda()
+        loss_func, psnr_func = SoftL1Loss(), LossPSNR()
+    else:
+        all_poses = torch.stack([pose_spherical(angle, -30.0, 4.0) for angle in torch.linspace(-180, 180, 120 + 1)[:-1]], 0).cuda()
+    test_focal = fov2Focal(cam_fov_test, r_c)
+    if args.ref_nerf:
+        mip_net = RefNeRF(10, args.ide_level, hidden_unit=args.nerf_net_width, perturb_bottle_neck_w=args.bottle_neck_noise, use_srgb=args.use_srgb).cuda()
+    else:
+        mip_net = MipNeRF(10, 4, hidden_unit=args.nerf_net_width).cuda()
+    prop_net = ProposalNetwork(10, hidden_unit=args.prop_net_width).cuda()
+    mip_net.loadFromFile(model_path + args.name + "_mip.pth", False)
+    prop_net.loadFromFile(model_path + args.name + "_prop.pth", False)
+    mip_net.eval()
+    prop_net.eval()
+    precision = "fp16m" if (args.use_scaler and not args.ref_nerf) else None
+    output_dir = os.path.join(output_root, "given" if eval_poses else "sphere")
+    os.makedirs(output_dir, exist_ok=True)
+    psnrs = []
+    with torch.no_grad():
+        for i, pose in enumerate(all_poses):
+            if max_frames is not None and i >= max_frames:
+                break
+            pose = pose.clone()
+            pose[:3, -1] *= args.scene_scale
+            result = render_image(mip_net, prop_net, pose[:3, :], r_c, test_focal, args.near, args.far, 128, white_bkg=args.white_bkg,
+                                  render_normal=render_normal, render_depth=render_depth, precision=precision)
+            if eval_poses:
+                gt_img, _ = testset[i]
+                gt_img = gt_img.cuda()
+                loss = loss_func(result["rgb"], gt_img)
+                psnr = psnr_func(loss)
+                psnrs.append(float(psnr))
+                print("Image loss:%.6f\tPSNR:%.4f" % (loss.item(), psnr.item()))
+                result["gt_img"] = gt_img
+            save_image(list(result.values()), os.path.join(output_dir, "result_%03d.png" % i), nrow=1 + render_depth + render_depth + eval_poses)
+    return psnrs

@@ -119,3 +119,37 @@ def test_ipe_fused_into_the_proposal_producer(precision, tol):
     # and the image differs from the point-encoded render (the cones blur the high frequencies) but stays a valid image
     plain = ops.render_rays(rays.to(DEV), base.to(DEV), 2.0, 6.0, 128, white_bkg=True, precision=precision, jitter=jitter.to(DEV), u=u.to(DEV), **ids)
     assert bool(torch.isfinite(out["rgb"]).all()) and not torch.equal(out["rgb"], plain["rgb"])
+
+
+def test_render_only_driver(tmp_path):
+    """nerf/procedures.py:99-164: checkpoints written by saveModel are loaded by loadFromFile, the orbit / test poses are
+    rendered through render_image and written as PNGs (a tiny synthetic Blender-format scene stands in for the dataset)."""
+    import json
+    import os
+    import numpy as np
+    from PIL import Image
+    import nerf_b200
+    from oracle import nerf_oracle as O
+    root = tmp_path / "data" / "toy"
+    (root / "test").mkdir(parents=True)
+    frames = []
+    for i in range(2):
+        Image.fromarray((np.random.RandomState(i).rand(100, 100, 4) * 255).astype(np.uint8), "RGBA").save(root / "test" / f"r_{i}.png")
+        frames.append({"transform_matrix": nerf_b200.pose_spherical(40.0 * i, -30.0, 4.0).tolist()})
+    json.dump({"camera_angle_x": 0.6911112070083618, "frames": frames}, open(root / "transforms_test.json", "w"))
+    ckpt = tmp_path / "ckpt"
+    ckpt.mkdir()
+    net, prop = nerf_b200.MipNeRF(10, 4, 256), nerf_b200.ProposalNetwork(10, 256)
+    net.load_state_dict(O.make_params("nerf", 2, "smooth")); prop.load_state_dict(O.make_params("proposal", 1, "smooth"))
+    nerf_b200.saveModel(net, str(ckpt / "model_1_mip.pth")); nerf_b200.saveModel(prop, str(ckpt / "model_1_prop.pth"))
+    out = tmp_path / "out"
+    for extra in (["-e"], ["--render_depth"]):
+        args = nerf_b200.get_parser().parse_args(["--dataset_name", "toy", "-w", "--img_scale", "0.5"] + extra)
+        psnrs = nerf_b200.render_only(args, str(ckpt) + "/", dataset_root=str(tmp_path / "data") + "/", output_root=str(out) + "/", max_frames=2)
+        sub = "given" if "-e" in extra else "sphere"
+        files = sorted(os.listdir(out / sub))
+        assert files == ["result_000.png", "result_001.png"]
+        w, h = Image.open(out / sub / files[0]).size
+        assert h >= 50 and w >= 2 * 50                       # two 50x50 panels side by side (rgb + gt / rgb + depth)
+        if "-e" in extra:
+            assert len(psnrs) == 2 and all(np.isfinite(psnrs))

@@ -78,3 +78,48 @@ def test_lr_schedule_matches_formula():
     assert abs(s.update_opt_lr(5)[1] - 1e-3 * (0.1 * 0.5 + 0.5)) < 1e-12
     assert abs(s.update_opt_lr(110)[1] - 1e-3 * 0.5) < 1e-12
     assert abs(s.update_opt_lr(100000)[1] - 1e-4) < 1e-12
+
+
+def test_get_parser_matches_the_reference_defaults():
+    """tests/golden/reference_parser_defaults.json = vars(get_parser().parse_args([])) of the UNMODIFIED reference
+    (nerf/procedures.py:166-213)."""
+    import json
+    import os
+    ref = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_parser_defaults.json")))
+    got = vars(nerf_b200.get_parser().parse_args([]))
+    assert got == ref
+    a = nerf_b200.get_parser().parse_args(["-w", "-t", "--render_depth", "--sample_ray_num", "512", "--lr", "1e-3", "-e"])
+    assert a.white_bkg and a.ref_nerf and a.render_depth and a.eval_poses and a.sample_ray_num == 512 and a.lr == 1e-3
+
+
+def test_blender_dataset_loader(tmp_path):
+    """nerf/dataset.py:22-114 behaviour on a tiny synthetic Blender-format scene: natural file order, fov / transforms from
+    the JSON, white-background alpha compositing, scene_scale on the translation, AdaptiveResize."""
+    import json
+    from PIL import Image
+    from torchvision import transforms
+    from nerf_b200.dataset import AdaptiveResize, CustomDataSet
+    root = tmp_path / "toy"
+    (root / "test").mkdir(parents=True)
+    frames = []
+    for i in (0, 1, 2, 10):
+        arr = np.zeros((8, 8, 4), dtype=np.uint8)
+        arr[..., 0] = 10 * i + 5
+        arr[..., 3] = 128 if i == 2 else 255
+        Image.fromarray(arr, "RGBA").save(root / "test" / f"r_{i}.png")
+        tf = np.eye(4)
+        tf[:3, 3] = [i, 2 * i, 3.0]
+        frames.append({"transform_matrix": tf.tolist()})
+    Image.fromarray(np.zeros((8, 8, 4), dtype=np.uint8), "RGBA").save(root / "test" / "r_0_normal.png")
+    json.dump({"camera_angle_x": 0.69, "frames": frames}, open(root / "transforms_test.json", "w"))
+    tfm = transforms.Compose([AdaptiveResize(0.5), transforms.ToTensor()])
+    ds = CustomDataSet(str(root) + "/", tfm, scene_scale=2.0, is_train=False, white_bkg=True)
+    assert ds.total_imgs == ["r_0.png", "r_1.png", "r_2.png", "r_10.png"] and len(ds) == 4       # natural order, no *normal*
+    fov, tfs = ds.getCameraParam()
+    assert fov == 0.69 and tfs.shape == (4, 3, 4) and ds.r_c() == (4, 4)
+    img, tf = ds[2]
+    assert img.shape == (3, 4, 4)
+    a = 128 / 255
+    assert abs(float(img[0, 0, 0]) - ((25 / 255) * a + (1 - a))) < 2e-2 and abs(float(img[1, 0, 0]) - (1 - a)) < 2e-2
+    assert torch.allclose(tf[:, 3], torch.tensor([2.0, 4.0, 3.0]) * 2.0)
+    assert torch.allclose(ds.tfs[2][:, 3], torch.tensor([2.0, 4.0, 3.0]))                      # the stored transforms stay unscaled
