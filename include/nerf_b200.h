@@ -303,6 +303,19 @@ int nb2_to_bf16(nb2_handle* h, const float* src, int64_t rows, int cols, int64_t
 /* out[m][c] (=|+=) sum_s ws[s * split_stride + m * ld_ws + perm(c)]: second stage of the split-K wgrad. */
 int nb2_reduce_splits(nb2_handle* h, const float* ws, int splits, int64_t split_stride, int rows, int cols, int ld_ws,
                       const int* col_perm, float* out, int ld_out, int accumulate, void* stream);
+/* Launch plans: the same two calls over arrays of descriptors, in order, on one stream.  The training step records its
+ * GEMMs once per (network, batch size) and replays them with one host call per group (at the reference's 1024-ray batch,
+ * train.py:236, the per-launch host cost is what bounds the step).  Stops at, and returns, the first error.
+ * nb2_reduce_splits_batch runs up to 32 reductions per launch (they must write disjoint outputs; accumulate = 0). */
+typedef struct nb2_reduce_desc {
+  const float* ws;
+  int splits, rows, cols, ld_ws, ld_out, accumulate;
+  int64_t split_stride; /* floats */
+  const int* col_perm;
+  float* out;
+} nb2_reduce_desc;
+int nb2_gemm_bf16_batch(nb2_handle* h, const nb2_gemm_desc* descs, int n, void* stream);
+int nb2_reduce_splits_batch(nb2_handle* h, const nb2_reduce_desc* descs, int n, void* stream);
 
 /* ---- training step, HBM-bound pieces: encodings as GEMM operands and the backward of the ray ops --------
  * In the reference these are autograd's derivatives of the torch ops the functions are written in (train.py:206).

@@ -66,6 +66,14 @@ class GemmDesc(ctypes.Structure):
     ]
 
 
+class ReduceDesc(ctypes.Structure):
+    """Mirror of nb2_reduce_desc."""
+    _fields_ = [
+        ("ws", c_vp), ("splits", c_int), ("rows", c_int), ("cols", c_int), ("ld_ws", c_int), ("ld_out", c_int), ("accumulate", c_int),
+        ("split_stride", c_i64), ("col_perm", c_vp), ("out", c_vp),
+    ]
+
+
 # name -> (restype, argtypes).  Every symbol include/nerf_b200.h declares is listed here; the
 # CPU test-suite checks the library exports all of them.
 SIGNATURES = {
@@ -80,6 +88,8 @@ SIGNATURES = {
     "nb2_gemm_bf16": (c_int, [c_vp, ctypes.POINTER(GemmDesc), c_vp]),
     "nb2_to_bf16": (c_int, [c_vp, c_f32p, c_i64, c_int, c_i64, c_vp, c_vp, c_vp, c_int, c_vp]),
     "nb2_reduce_splits": (c_int, [c_vp, c_f32p, c_int, c_i64, c_int, c_int, c_int, c_vp, c_f32p, c_int, c_int, c_vp]),
+    "nb2_gemm_bf16_batch": (c_int, [c_vp, c_vp, c_int, c_vp]),
+    "nb2_reduce_splits_batch": (c_int, [c_vp, c_vp, c_int, c_vp]),
     "nb2_encode_bf16": (c_int, [c_vp, c_f32p, c_int, c_int, c_i64, c_int, c_int, c_vp, c_vp, c_i64, c_int, c_vp]),
     "nb2_weights_from_sigma_backward": (c_int, [c_vp, c_f32p, c_f32p, c_f32p, c_int, c_i64, c_int, c_int, c_f32p, c_f32p, c_vp]),
     "nb2_composite_backward": (c_int, [c_vp, c_f32p, c_f32p, c_f32p, c_int, c_i64, c_int, c_int, c_f32p, c_f32p, c_f32p, c_vp]),
@@ -165,13 +175,14 @@ def check(rc):
 
 def handle(device=None):
     """One nb2_handle per CUDA device per process."""
+    if device is not None:
+        try:
+            return _handles_fast[device]              # a torch.device with an index (what tensors carry): no torch calls
+        except (KeyError, TypeError):
+            pass
     if not torch.cuda.is_available():
         raise NB2Error("nerf_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
-    if device is None:
-        device = torch.cuda.current_device()
-    idx = torch.device(device).index if not isinstance(device, int) else device
-    if idx is None:
-        idx = torch.cuda.current_device()
+    idx = _device_index(device)
     h = _handles.get(idx)
     if h is None:
         lib = load()
@@ -180,12 +191,28 @@ def handle(device=None):
         check(lib.nb2_create(ctypes.byref(out), idx))
         h = out
         _handles[idx] = h
+    if isinstance(device, torch.device) and device.index is not None:
+        _handles_fast[device] = h
     return h
+
+
+_handles_fast = {}
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
+def _device_index(device):
+    if device is None:
+        return torch.cuda.current_device()
+    idx = torch.device(device).index if not isinstance(device, int) else device
+    return torch.cuda.current_device() if idx is None else idx
 
 
 def stream_ptr(device=None):
     """The current CUDA stream of `device` (default: the current device).  Ops pass the device of their tensors, so a
     tensor on a non-current GPU is processed on that GPU's stream by that GPU's handle."""
+    if _raw_stream is not None:
+        idx = device.index if isinstance(device, torch.device) and device.index is not None else _device_index(device)
+        return c_vp(_raw_stream(idx))
     return c_vp(torch.cuda.current_stream(device).cuda_stream)
 
 

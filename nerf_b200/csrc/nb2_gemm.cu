@@ -449,17 +449,46 @@ __global__ void to_bf16_kernel(const float* __restrict__ src, int64_t rows, int 
 
 // out[m][c] (fp32, row stride ld_out, c < cols) = sum over splits of ws[s][m][perm(c)] (row stride ld_ws): the
 // deterministic second stage of the split-K wgrad (no atomics: gradients are bit-reproducible run to run).
-__global__ void reduce_splits_kernel(const float* __restrict__ ws, int splits, int64_t split_stride, int rows, int cols, int ld_ws,
-                                     const int* __restrict__ col_perm, float* __restrict__ out, int ld_out, int accumulate) {
+// Eight independent loads in flight per thread (one dependent load per split made the kernel latency-bound: 36 us for a
+// 256 x 256 gradient over 74 splits); the additions stay in split order, so the result does not depend on the batching.
+__device__ __forceinline__ void reduce_splits_body(const float* __restrict__ ws, int splits, int64_t split_stride, int rows, int cols, int ld_ws,
+                                                   const int* __restrict__ col_perm, float* __restrict__ out, int ld_out, int accumulate,
+                                                   int64_t first, int64_t stride) {
   const int64_t n = (int64_t)rows * cols;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+  for (int64_t i = first; i < n; i += stride) {
     const int m = (int)(i / cols), c = (int)(i - (int64_t)m * cols);
     const int wc = col_perm ? col_perm[c] : c;
+    const float* src = ws + (int64_t)m * ld_ws + wc;
     float acc = 0.f;
-    for (int s = 0; s < splits; ++s) acc += ws[(int64_t)s * split_stride + (int64_t)m * ld_ws + wc];
+    int s = 0;
+    for (; s + 8 <= splits; s += 8) {
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = __ldg(src + (int64_t)(s + j) * split_stride);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc += v[j];
+    }
+    for (; s < splits; ++s) acc += __ldg(src + (int64_t)s * split_stride);
     float* o = out + (int64_t)m * ld_out + c;
     *o = accumulate ? *o + acc : acc;
   }
+}
+
+__global__ void reduce_splits_kernel(const float* __restrict__ ws, int splits, int64_t split_stride, int rows, int cols, int ld_ws,
+                                     const int* __restrict__ col_perm, float* __restrict__ out, int ld_out, int accumulate) {
+  reduce_splits_body(ws, splits, split_stride, rows, cols, ld_ws, col_perm, out, ld_out, accumulate,
+                     (int64_t)blockIdx.x * blockDim.x + threadIdx.x, (int64_t)gridDim.x * blockDim.x);
+}
+
+// every reduction of a launch plan in one launch: blockIdx.y selects the descriptor
+constexpr int kReduceBatch = 32;
+struct ReduceBatch {
+  nb2_reduce_desc d[kReduceBatch];
+};
+__global__ void reduce_splits_batch_kernel(const __grid_constant__ ReduceBatch b) {
+  const nb2_reduce_desc& d = b.d[blockIdx.y];
+  reduce_splits_body(d.ws, d.splits, d.split_stride, d.rows, d.cols, d.ld_ws, d.col_perm, d.out, d.ld_out, d.accumulate,
+                     (int64_t)blockIdx.x * blockDim.x + threadIdx.x, (int64_t)gridDim.x * blockDim.x);
 }
 
 }  // namespace nb2
@@ -597,5 +626,39 @@ extern "C" int nb2_reduce_splits(nb2_handle* h, const float* ws, int splits, int
   const int blocks = (int)std::min<int64_t>((n + 255) / 256, (int64_t)h->sm_count * 8);
   reduce_splits_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(ws, splits, split_stride, rows, cols, ld_ws, col_perm, out, ld_out, accumulate);
   NB2_LAUNCH_CHECK(h);
+  return NB2_OK;
+}
+
+// ---- batched entry points: one host call for a recorded sequence (the training step's launch plans) ----------------------
+extern "C" int nb2_gemm_bf16_batch(nb2_handle* h, const nb2_gemm_desc* d, int n, void* stream) {
+  NB2_ENTER(h);
+  NB2_CHECK_ARG(n >= 0 && (d != nullptr || n == 0), "gemm_batch: bad arguments");
+  for (int i = 0; i < n; ++i) {
+    const int rc = nb2_gemm_bf16(h, d + i, stream);
+    if (rc != NB2_OK) return rc;
+  }
+  return NB2_OK;
+}
+
+extern "C" int nb2_reduce_splits_batch(nb2_handle* h, const nb2_reduce_desc* d, int n, void* stream) {
+  NB2_ENTER(h);
+  NB2_CHECK_ARG(n >= 0 && (d != nullptr || n == 0), "reduce_splits_batch: bad arguments");
+  for (int i0 = 0; i0 < n; i0 += kReduceBatch) {
+    const int cnt = std::min(kReduceBatch, n - i0);
+    ReduceBatch b;
+    int64_t n_max = 0;
+    for (int i = 0; i < cnt; ++i) {
+      const nb2_reduce_desc& r = d[i0 + i];
+      NB2_CHECK_ARG(r.ws && r.out && r.splits >= 1 && r.rows > 0 && r.cols > 0 && r.ld_ws > 0 && r.ld_out >= r.cols,
+                    "reduce_splits_batch: bad descriptor %d", i0 + i);
+      // accumulating descriptors read what an earlier descriptor of the same launch may write: keep those in order
+      NB2_CHECK_ARG(!r.accumulate, "reduce_splits_batch: descriptor %d accumulates; use nb2_reduce_splits for ordered accumulation", i0 + i);
+      b.d[i] = r;
+      n_max = std::max<int64_t>(n_max, (int64_t)r.rows * r.cols);
+    }
+    const int blocks = (int)std::min<int64_t>((n_max + 255) / 256, (int64_t)h->sm_count * 8);
+    reduce_splits_batch_kernel<<<dim3(blocks, cnt), 256, 0, (cudaStream_t)stream>>>(b);
+    NB2_LAUNCH_CHECK(h);
+  }
   return NB2_OK;
 }

@@ -31,8 +31,10 @@ constexpr int kALoCol = 384;
 struct Tc4Misc {
   uint64_t w_full[kStages4];
   uint64_t w_empty[kStages4];
-  uint64_t a_ready;            // leader only: next A operand complete in both CTAs (16 warp arrivals)
+  uint64_t a_ready;            // leader only: the next tile's encoding is in shared memory and the accumulator has been read (16 warp arrivals)
   uint64_t acc_full;
+  uint64_t acc_free;           // leader only: every warp of both CTAs has the accumulator in registers (16 warp arrivals)
+  uint64_t a_chunk[4];         // leader only: K chunk c (64 columns, hi + lo) of the next A operand is in TMEM in both CTAs (8 warp arrivals)
   uint32_t tmem_base;
   uint32_t pad;
   float scratch[4][8];
@@ -120,6 +122,60 @@ __device__ __forceinline__ float epilogue_hidden4(uint32_t acc_lane, int g, cons
   return sg;
 }
 
+// The pipelined form for the two-warpgroup kernel.  The accumulator and the hi / lo A operand fill all 512 TMEM columns, so
+// the next layer cannot own a second accumulator; what CAN overlap is the conversion: the A operand of the finished layer is
+// dead, so each 64-column K chunk is converted and published on its own barrier (`arrive_chunk`), and the accumulator is
+// released (`arrive_free`) as soon as its last columns are in registers.  The issuer starts the next layer's first K chunk
+// while this warpgroup still converts its second one (round 1 / early round 2: one hand-over after all 256 columns).
+template <int EPI, bool F16, class ArriveFree, class ArriveChunk>
+__device__ __forceinline__ float epilogue_hidden5(uint32_t acc_lane, int g, const float* __restrict__ head, ArriveFree&& arrive_free,
+                                                  ArriveChunk&& arrive_chunk, bool late) {
+  constexpr bool kRelu = (EPI != EPI_LINEAR);
+  constexpr bool kSigma = (EPI == EPI_RELU_SIGMA);
+  float sg = 0.f;
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    uint32_t r0[32], r1[32];
+    const int c0 = 128 * g + 64 * half;
+    tmem_ld32(acc_lane + c0, r0);
+    tmem_ld32(acc_lane + c0 + 32, r1);
+    tmem_ld_wait();
+    if (half == 1 && !late) {
+      tc_fence_before();
+      arrive_free();
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int col = c0 + 32 * u;
+      uint32_t hi[16], lo[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        float a = __uint_as_float(u ? r1[2 * i] : r0[2 * i]);
+        float bq = __uint_as_float(u ? r1[2 * i + 1] : r0[2 * i + 1]);
+        if (kRelu) { a = fmaxf(a, 0.f); bq = fmaxf(bq, 0.f); }
+        if (kSigma) {
+          const float2 w = __ldg(reinterpret_cast<const float2*>(head + kHeadSigmaW + col + 2 * i));
+          sg = fmaf(a, w.x, sg);
+          sg = fmaf(bq, w.y, sg);
+        }
+        hi[i] = pack16x2<F16>(a, bq);
+        lo[i] = residual16x2<F16>(a, bq, hi[i]);
+      }
+      tmem_st16(acc_lane + kAHiCol + (col >> 1), hi);
+      tmem_st16(acc_lane + kALoCol + (col >> 1), lo);
+    }
+    tmem_st_wait4();      // this K chunk of the A operand is in TMEM ...
+    tc_fence_before();    // ... ordered before the arrive that lets the issuer read it
+    if (!late) arrive_chunk(2 * g + half);
+  }
+  if (late) {             // NB2_TC_DEBUG & 4 (A/B timing): one hand-over after all columns, as before the chunked scheme
+    arrive_free();
+    arrive_chunk(2 * g);
+    arrive_chunk(2 * g + 1);
+  }
+  return sg;
+}
+
 template <bool F16, int NG, int G>
 __device__ __forceinline__ void slot_group_run4(const TcParams& p, Tc4Misc* misc, uint32_t enc_base, uint32_t park_base,
                                                 uint32_t tmem_base, int64_t n_iters, int warp, int lane, uint32_t rank) {
@@ -141,6 +197,17 @@ __device__ __forceinline__ void slot_group_run4(const TcParams& p, Tc4Misc* misc
       if (rank != 0) mbar_arrive_remote_relaxed(a_ready, 0); else mbar_arrive(a_ready);
     }
   };
+  auto arrive_on = [&](uint32_t bar) {
+    __syncwarp();
+    if (lane == 0) {
+      if (rank != 0) mbar_arrive_remote_relaxed(bar, 0); else mbar_arrive(bar);
+    }
+  };
+  const uint32_t acc_free = smem_u32(&misc->acc_free);
+  const uint32_t a_chunk0 = smem_u32(&misc->a_chunk[0]);
+  const bool late = (p.debug & 4) != 0;
+  auto arrive_free = [&]() { arrive_on(acc_free); };
+  auto arrive_chunk = [&](int c) { arrive_on(a_chunk0 + 8u * (uint32_t)c); };
   auto tile_of = [&](int64_t it) { return it * gridDim.x + blockIdx.x; };   // may lie past n_tiles
   EncRegs<true, F16, (8 / NG) * G, 8 / NG> enc;   // this warpgroup's column groups (8 columns each) of the next tile's encoding
   auto begin_tile = [&]() {
@@ -290,16 +357,14 @@ __device__ __forceinline__ void slot_group_run4(const TcParams& p, Tc4Misc* misc
         t_last += NB2_CLK() - ce;
         continue;
       }
+      static_assert(NG == 2, "the chunked hand-over is written for two warpgroups per tile");
       if (epi == EPI_RELU) {
-        epilogue_hidden4<EPI_RELU, F16, NG>(acc, g, p.head);
+        epilogue_hidden5<EPI_RELU, F16>(acc, g, p.head, arrive_free, arrive_chunk, late);
       } else if (epi == EPI_LINEAR) {
-        epilogue_hidden4<EPI_LINEAR, F16, NG>(acc, g, p.head);
+        epilogue_hidden5<EPI_LINEAR, F16>(acc, g, p.head, arrive_free, arrive_chunk, late);
       } else {   // EPI_RELU_SIGMA (each warpgroup keeps the dot product over its own columns; the bias is added once)
-        sigma = epilogue_hidden4<EPI_RELU_SIGMA, F16, NG>(acc, g, p.head) + (g == 0 ? __ldg(p.head + kHeadSigmaB) : 0.f);
+        sigma = epilogue_hidden5<EPI_RELU_SIGMA, F16>(acc, g, p.head, arrive_free, arrive_chunk, late) + (g == 0 ? __ldg(p.head + kHeadSigmaB) : 0.f);
       }
-      tmem_st_wait4();      // the A operand is in TMEM ...
-      tc_fence_before();    // ... ordered before the arrive that releases the MMA issuer
-      arrive_a();
       t_epi += NB2_CLK() - ce;
 
       // ---- work hidden behind the next layer's MMAs ------------------------------------------------------------------
@@ -350,6 +415,8 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) mlp_tc4_kernel(const __grid
     }
     mbar_init(smem_u32(&misc->a_ready), 8 * NG);   // every slot-group warp of both CTAs
     mbar_init(smem_u32(&misc->acc_full), 1);
+    mbar_init(smem_u32(&misc->acc_free), 8 * NG);
+    for (int c = 0; c < 4; ++c) mbar_init(smem_u32(&misc->a_chunk[c]), 2 * (8 / NG));   // the four warps that own the chunk, both CTAs
     mbar_fence_init();
   }
   if (warp == 2) {
@@ -404,7 +471,7 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) mlp_tc4_kernel(const __grid
         }
     } else if (rank == 0) {
       // =========================== leader: MMA issuer for the pair (whole warp, one elected lane per instruction) ======
-      uint32_t stage = 0, phase = 0, pa = 0;
+      uint32_t stage = 0, phase = 0, pa = 0, pf = 0, pc = 0;
       long long t_wa = 0, t_ww = 0, t0m = NB2_CLK();
       const uint32_t ring_lo = umma_desc_lo(ring_base);
       const uint32_t enc_lo = umma_desc_lo(enc_base);    // hi half of the encoding tile; the lo half is one tile further
@@ -440,13 +507,30 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) mlp_tc4_kernel(const __grid
         for (int l = 0; l < net.n_layers; ++l) {
           const TcLayer& L = net.layer[l];
           const uint32_t idesc = umma_idesc_16(256, L.nc * 128, F16);
+          // layer 0 reads the encoding tile (a_ready: written, and the previous tile's accumulator read); every other layer
+          // may overwrite the accumulator once it is in registers and reads K chunk c of its A operand once c is published
           { const long long c0 = NB2_CLK();
-          mbar_wait(smem_u32(&misc->a_ready), pa);
-          pa ^= 1u;
+          if (l == 0) {
+            mbar_wait(smem_u32(&misc->a_ready), pa);
+            pa ^= 1u;
+          } else {
+            mbar_wait(smem_u32(&misc->acc_free), pf);
+            pf ^= 1u;
+          }
           t_wa += NB2_CLK() - c0; }
           tc_fence_after();
+          uint32_t pending = l == 0 ? 0u : 0xFu;       // chunk barriers of this layer not consumed yet
+          auto wait_chunk = [&](int c) {
+            if (!(pending >> c & 1u)) return;
+            const long long c0 = NB2_CLK();
+            mbar_wait(smem_u32(&misc->a_chunk[c]), pc);
+            t_wa += NB2_CLK() - c0;
+            tc_fence_after();
+            pending &= ~(1u << c);
+          };
           // sweep 1: the small cross terms lo x Wh and hi x Wl
           for (int k = 0; k < L.kc; ++k) {
+            if (L.a_src[k] != kChunkE) wait_chunk(L.a_src[k]);
             wait_stage();
             // (bias-only chunk: its A column is the constant 1, whose lo half is 0 -- no lo x Wh term)
             if (L.ks0[k] == 0) issue_chunk(L.a_src[k], 0, true, idesc, k == 0);
@@ -455,6 +539,8 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) mlp_tc4_kernel(const __grid
             issue_chunk(L.a_src[k], L.ks0[k], false, idesc, false);
             release_stage();
           }
+          for (int c = 0; c < 4; ++c) wait_chunk(c);   // (a layer that does not read every chunk still consumes each phase)
+          if (l != 0) pc ^= 1u;
           // sweep 2: hi x Wh on top
           for (int k = 0; k < L.kc; ++k) {
             wait_stage();

@@ -197,12 +197,27 @@ def coarse_fine_merge(rays, c_z, f_z, f_inds=None):
 
 
 # ---- f1: training-side callers (forward only) -------------------------------------------------------
+_BASE_Z = {}
+
+
+def _base_z(start, end, n, dev):
+    """The reference builds torch.linspace on the host every step (utils.py:88); the same values, uploaded once: a pageable
+    host-to-device copy waits for the stream, which would serialise the host with every training step."""
+    key = (start, end, n, dev)
+    z = _BASE_Z.get(key)
+    if z is None:
+        if len(_BASE_Z) > 64:
+            _BASE_Z.clear()
+        z = _BASE_Z[key] = torch.linspace(start, end, n).to(dev)
+    return z
+
+
 def valid_sampler(rgbs, coords, cam_tf, ray_num, point_num, focal_x, focal_y, near, far, indices=None, jitter=None, seed=None):
     rgbs, cam_tf = f32(rgbs), f32(cam_tf[:3, :4])
     coords = coords.to(torch.int64).contiguous()
     dev = rgbs.device
     resolution = (far - near) / point_num
-    base_z = torch.linspace(near, far - resolution, point_num).to(dev)              # utils.py:88
+    base_z = _base_z(float(near), float(far - resolution), int(point_num), dev)     # utils.py:88
     if indices is not None:
         indices = indices.to(device=dev, dtype=torch.int64).contiguous()
     if jitter is not None:

@@ -38,8 +38,13 @@ class _PackedCat(PackedLinear):
         key = tuple((l.weight.data_ptr(), l.weight._version, l.bias._version) for l in self.lins)
         if key != self.key:
             w = torch.cat([l.weight.detach() for l in self.lins], dim=0).contiguous()
-            self.hi, self.lo = linear.to_bf16(w, ld_dst=self.in_pad)
-            self.bias = torch.cat([l.bias.detach() for l in self.lins]).contiguous()
+            b = torch.cat([l.bias.detach() for l in self.lins]).contiguous()
+            if self.hi is not None and self.hi.device == w.device:      # in place: launch plans hold these pointers
+                linear.to_bf16(w, ld_dst=self.in_pad, out=(self.hi, self.lo))
+                self.bias.copy_(b)
+            else:
+                self.hi, self.lo = linear.to_bf16(w, ld_dst=self.in_pad)
+                self.bias = b
             self.key = key
         return self
 
@@ -106,27 +111,61 @@ class RefNeRF(NeRF):
             self.__dict__["_nb2_ref_engine"] = e
         return e
 
-    def _forward_engine(self, pts2d, dirs2d, cam_dir=None, shift_softplus=False):
-        """pts2d (n, >=3) positions, dirs2d (n, 3) view directions -> (rgbo (n,4), normal (n,3), ndot (n,) or None)."""
+    max_plans = 2      # recorded batch sizes kept per module (their activation buffers stay allocated)
+
+    def _packed(self):
         e = self._engine()
+        return [*e["spa"], e["heads"], e["bottle"], *e["dir"], e["spec"]]
+
+    def _forward_engine(self, pts2d, dirs2d, cam_dir=None, shift_softplus=False):
+        """pts2d (n, >=3) positions, dirs2d (n, 3) view directions -> (rgbo (n,4), normal (n,3), ndot (n,) or None).
+        The launches are recorded once per batch size as a linear.Program and replayed (one host call per run of GEMMs)."""
         x3 = self.precision != "bf16"
         if self.precision not in (None, "bf16x3", "bf16"):
             raise _lib.NB2Error(f"RefNeRF runs on the layer-wise engine: precision 'bf16x3' (default) or 'bf16', not {self.precision!r}")
         dev, n = pts2d.device, pts2d.shape[0]
+        packed = self._packed()
+        for pk in packed:
+            pk.sync()
+        has_cam = cam_dir is not None
+        plans = self.__dict__.setdefault("_nb2_ref_plans", {})
+        key = (n, x3, dev, self.training, has_cam, bool(shift_softplus)) + tuple(pk.hi.data_ptr() for pk in packed)
+        out = torch.empty((n, 4), dtype=torch.float32, device=dev)
+        normal = torch.empty((n, 3), dtype=torch.float32, device=dev)
+        ndot = torch.empty((n,), dtype=torch.float32, device=dev) if has_cam else None
+        cam = _lib.f32(cam_dir).reshape(3) if has_cam else None
+        dyn = dict(pts=pts2d, dirs=dirs2d, out=out, normal=normal)
+        if has_cam:
+            dyn.update(ndot=ndot, cam=cam)
+        prog = plans.get(key)
+        if prog is None:
+            while len(plans) >= self.max_plans:
+                plans.pop(next(iter(plans)))
+            with linear.Program(dev) as prog:
+                prog.bind(**dyn)
+                self._record(prog, n, x3, has_cam, shift_softplus)
+            plans[key] = prog
+        prog.run(**dyn)
+        prog.release()
+        return out, normal, ndot
+
+    def _record(self, prog, n, x3, has_cam, shift_softplus):
+        e = self._engine()
+        dev = prog.dev
         H, enc = self.hidden_unit, 3 + 6 * self.position_flevel
         enc_w = _pad8(enc)
         din = 1 + self.bottle_neck_dim + self.dir_enc_dim
         din_w = _pad8(din)
-        lib, h, st = load(), handle(dev), stream_ptr(dev)
+        lib, h = load(), handle(dev)
+        inp = prog.inp
 
         def lin(x, pk, K, out, bias, act=linear.ACT_RELU):
-            pk.sync()
             linear.gemm(n, pk.out_f, _fwd_segs(x, (pk.hi, pk.lo), K, x3), bias=bias, act=act, out_hi=out[0], out_lo=out[1])
 
         # ---- spatial MLP (ref_model.py:70-80) ----
         C5 = _empty16(n, H + enc_w, dev, x3)
         E = (C5[0][:, H:], C5[1][:, H:] if x3 else None)
-        encode(pts2d, 0, self.position_flevel, False, E[0], E[1])
+        prog.call(lambda: encode(inp["pts"], 0, self.position_flevel, False, E[0], E[1]))
         spa = e["spa"]
         bs = [p.lin.bias.detach() for p in spa]
         h1, h2, h3 = (_empty16(n, H, dev, x3) for _ in range(3))
@@ -141,34 +180,43 @@ class RefNeRF(NeRF):
         lin(h7, spa[7], H, inter, bs[7])
         # ---- heads (ref_model.py:82-87) ----
         heads = torch.empty((n, 12), dtype=torch.float32, device=dev)
-        hk = e["heads"].sync()
+        hk = e["heads"]
         linear.gemm(n, 11, _fwd_segs(inter, (hk.hi, hk.lo), H, x3), bias=hk.bias, out_f32=heads[:, :11])
         Cd = _empty16(n, H + din_w, dev, x3)                                   # [r4 | bottleneck | ide | nv_dot | pad]
         bd = self.bottle_neck_dim
-        bk = e["bottle"].sync()
+        bk = e["bottle"]
         bott = (Cd[0][:, H:H + bd], Cd[1][:, H:H + bd] if x3 else None)
         if self.training:
             # ref_model.py:86-87: Gaussian perturbation of the bottleneck (drawn by torch, applied before the bf16 split)
             b32 = torch.empty((n, bd), dtype=torch.float32, device=dev)
             linear.gemm(n, bd, _fwd_segs(inter, (bk.hi, bk.lo), H, x3), bias=self.bottle_neck.bias.detach(), out_f32=b32)
-            b32 += torch.normal(0, self.perturb_bottle_neck_w, b32.shape, device=dev)
-            hi_c, lo_c = linear.to_bf16(b32, ld_dst=bd, want_lo=x3)
-            bott[0].copy_(hi_c)
-            if x3:
-                bott[1].copy_(lo_c)
+
+            def perturb():
+                b32.add_(torch.normal(0, self.perturb_bottle_neck_w, b32.shape, device=dev))
+                hi_c, lo_c = linear.to_bf16(b32, ld_dst=bd, want_lo=x3)
+                bott[0].copy_(hi_c)
+                if x3:
+                    bott[1].copy_(lo_c)
+
+            prog.call(perturb)
         else:
             linear.gemm(n, bd, _fwd_segs(inter, (bk.hi, bk.lo), H, x3), bias=self.bottle_neck.bias.detach(), out_hi=bott[0], out_lo=bott[1])
         # ---- geometry + integrated directional encoding (ref_model.py:88-94) ----
-        normal = torch.empty((n, 3), dtype=torch.float32, device=dev)
         reflect = torch.empty((n, 3), dtype=torch.float32, device=dev)
         rough = torch.empty((n,), dtype=torch.float32, device=dev)
         nv = torch.empty((n,), dtype=torch.float32, device=dev)
-        check(lib.nb2_ref_geometry(h, heads.data_ptr(), 12, dirs2d.data_ptr(), dirs2d.stride(0), n, normal.data_ptr(), reflect.data_ptr(),
-                                   rough.data_ptr(), nv.data_ptr(), st))
-        ide = self.integrated_dir_enc(reflect, rough.view(n, 1))
         tail = (Cd[0][:, H + bd:], Cd[1][:, H + bd:] if x3 else None)
-        check(lib.nb2_ref_dir_inputs(h, ide.data_ptr(), self.dir_enc_dim, nv.data_ptr(), n, tail[0].data_ptr(), _lib.ptr_int(tail[1]),
-                                     tail[0].stride(0), tail[0].shape[1], st))
+
+        def geometry():
+            st = stream_ptr(dev)
+            dirs = inp["dirs"]
+            check(lib.nb2_ref_geometry(h, heads.data_ptr(), 12, dirs.data_ptr(), dirs.stride(0), n, inp["normal"].data_ptr(), reflect.data_ptr(),
+                                       rough.data_ptr(), nv.data_ptr(), st))
+            ide = self.integrated_dir_enc(reflect, rough.view(n, 1))
+            check(lib.nb2_ref_dir_inputs(h, ide.data_ptr(), self.dir_enc_dim, nv.data_ptr(), n, tail[0].data_ptr(), _lib.ptr_int(tail[1]),
+                                         tail[0].stride(0), tail[0].shape[1], st))
+
+        prog.call(geometry)
         # ---- directional MLP (ref_model.py:96-101) ----
         dr = e["dir"]
         bdm = [p.lin.bias.detach() for p in dr]
@@ -184,14 +232,11 @@ class RefNeRF(NeRF):
         lin(q2, dr[6], H, q3, bdm[6])
         lin(q3, dr[7], H, q4, bdm[7])
         spec = torch.empty((n, 3), dtype=torch.float32, device=dev)
-        sk = e["spec"].sync()
+        sk = e["spec"]
         linear.gemm(n, 3, _fwd_segs(q4, (sk.hi, sk.lo), H, x3), bias=self.spec_rgb_head[0].bias.detach(), act=linear.ACT_SIGMOID, out_f32=spec)
-        out = torch.empty((n, 4), dtype=torch.float32, device=dev)
-        ndot = torch.empty((n,), dtype=torch.float32, device=dev) if cam_dir is not None else None
-        cam = _lib.f32(cam_dir).reshape(3) if cam_dir is not None else None
-        check(lib.nb2_ref_color(h, spec.data_ptr(), heads.data_ptr(), 12, 1 if self.use_srgb else 0, 1 if shift_softplus else 0, normal.data_ptr(),
-                                _lib.ptr_int(cam), n, out.data_ptr(), _lib.ptr_int(ndot), st))
-        return out, normal, ndot
+        prog.call(lambda: check(lib.nb2_ref_color(h, spec.data_ptr(), heads.data_ptr(), 12, 1 if self.use_srgb else 0, 1 if shift_softplus else 0,
+                                                  inp["normal"].data_ptr(), _lib.ptr_int(inp.get("cam")), n, inp["out"].data_ptr(),
+                                                  _lib.ptr_int(inp.get("ndot")), stream_ptr(dev))))
 
     def forward(self, pts: torch.Tensor, ray_d: Optional[torch.Tensor] = None):
         """pts (ray_num, point_num, 6) = [xyz, dir] (or (.., 3) with ray_d) -> ((.., 4) = [rgb, density], normal (.., 3))."""

@@ -61,7 +61,9 @@ class PackedLinear:
         if key != self.key:
             if self.perm_host is not None and (self.perm is None or self.perm.device != w.device):
                 self.perm = self.perm_host.to(device=w.device, dtype=torch.int32)
-            self.hi, self.lo = linear.to_bf16(w.detach(), ld_dst=self.in_pad, col_perm=self.perm)
+            same = self.hi is not None and self.hi.device == w.device
+            # converted in place: launch plans hold pointers to these buffers
+            self.hi, self.lo = linear.to_bf16(w.detach(), ld_dst=self.in_pad, col_perm=self.perm, out=(self.hi, self.lo) if same else None)
             self.key = key
         return self
 
@@ -88,6 +90,8 @@ class _Workspace:
 
     @classmethod
     def get(cls, dev, floats):
+        if linear.recording() is not None:       # a launch plan defers its reductions: every wgrad keeps its own partial sums
+            return torch.empty(floats, dtype=torch.float32, device=dev)
         b = cls.bufs.get(dev)
         if b is None or b.numel() < floats:
             b = torch.empty(floats, dtype=torch.float32, device=dev)
@@ -140,11 +144,87 @@ def wgrad(dy, x, n_out, n_in, rows, x3, grad_w, perm=None, sm_count=148):
     linear.reduce_splits(ws, splits, m_pad * ld_ws, n_out, n_in, ld_ws, grad_w, col_perm=perm)
 
 
-class ProposalEngine:
-    """ProposalNetwork(10, 256): 63 -> 256 -> 256 -> 256 -> 256 -> 1 (nerf/addtional.py:61-72,88-96)."""
+class _Plan:
+    """The recorded forward and backward launch plans of one network at one batch size, with the activations between them."""
+
+    def __init__(self):
+        self.fwd = self.bwd = None
+        self.acts = None
+        self.out = None
+        self.busy = False      # between a forward and its backward the activations belong to that autograd node
+
+
+class _Engine:
+    """Shared plan bookkeeping.  Subclasses record `_forward(prog, plan, n, x3)` and `_backward(prog, plan, n, x3, flat)`."""
 
     keep_last_acts = False     # tests: keep a reference to the saved activations of the last forward (relu patterns)
     last_acts = None
+    max_plans = 2              # batch sizes kept recorded per network (activations stay allocated with their plan)
+
+    def _init_plans(self):
+        self.plans = {}
+        self.grad_shapes = [tuple(p.shape) for l in self.lins for p in (l.weight, l.bias)]
+        self.grad_numel = sum(l.weight.numel() + l.bias.numel() for l in self.lins)
+
+    def clear_plans(self):
+        self.plans.clear()
+
+    def _plan(self, n, x3, dev):
+        key = (n, x3, dev) + tuple(p.data_ptr() for l in self.lins for p in (l.weight, l.bias))
+        plan = self.plans.get(key)
+        if plan is None or plan.busy:
+            # busy: a second forward before the first one's backward (or a forward whose backward never ran) records anew
+            self.plans.pop(key, None)
+            while len(self.plans) >= self.max_plans:
+                self.plans.pop(next(iter(self.plans)))
+            plan = self.plans[key] = _Plan()
+        return plan
+
+    def forward(self, pts, x3):
+        dev, n = pts.device, pts.shape[0]
+        pts = pts.contiguous()
+        plan = self._plan(n, x3, dev)
+        for p in self.packed:
+            p.sync()
+        out = torch.empty((n, self.out_cols), dtype=torch.float32, device=dev)
+        if plan.fwd is None:
+            with linear.Program(dev) as prog:
+                prog.bind(pts=pts, out=out)
+                plan.acts = self._forward(prog, n, x3, out)
+            plan.fwd = prog
+        plan.fwd.run(pts=pts, out=out)
+        plan.fwd.release()
+        plan.out, plan.busy = out, True
+        return out, plan
+
+    def backward(self, plan, g_out, x3):
+        """g_out: gradient of forward's output -> list of (grad_weight, grad_bias) in state_dict order."""
+        dev, n = g_out.device, g_out.shape[0]
+        g_out = g_out.contiguous()
+        flat = torch.empty(self.grad_numel, dtype=torch.float32, device=dev)
+        if plan.bwd is None:
+            with linear.Program(dev) as prog:
+                prog.bind(g=g_out, out=plan.out, grads=flat)
+                self._backward(prog, plan.acts, n, x3, self._grad_views(flat))
+            plan.bwd = prog
+        plan.bwd.run(g=g_out, out=plan.out, grads=flat)
+        plan.bwd.release()
+        plan.out, plan.busy = None, False
+        return self._grad_views(flat)
+
+    def _grad_views(self, flat):
+        views, off = [], 0
+        for l in self.lins:
+            nw, nb = l.weight.numel(), l.bias.numel()
+            views.append((flat[off:off + nw].view(l.weight.shape), flat[off + nw:off + nw + nb]))
+            off += nw + nb
+        return views
+
+
+class ProposalEngine(_Engine):
+    """ProposalNetwork(10, 256): 63 -> 256 -> 256 -> 256 -> 256 -> 1 (nerf/addtional.py:61-72,88-96)."""
+
+    out_cols = 1
 
     def __init__(self, module):
         self.m = module
@@ -152,15 +232,16 @@ class ProposalEngine:
         self.lins = [L[0], L[2], L[4], L[6], L[8]]
         self.packed = [PackedLinear(l) for l in self.lins]
         self.levels = module.position_flevel
+        self._init_plans()
 
-    def forward(self, pts, x3):
-        """pts (n, 3) fp32 -> (sigma (n,) fp32, saved activations)."""
-        dev, n = pts.device, pts.shape[0]
-        W = [p.sync() for p in self.packed]
+    def _forward(self, prog, n, x3, sigma):
+        """pts (n, 3) fp32 -> sigma (n, 1) fp32; returns the saved activations."""
+        dev = prog.dev
+        W = self.packed
         H = self.lins[0].out_features
         enc_w = _pad8(3 + 6 * self.levels)
         E = _empty16(n, enc_w, dev, x3)
-        encode(pts, 0, self.levels, False, E[0], E[1])
+        prog.call(lambda: encode(prog.inp["pts"], 0, self.levels, False, E[0], E[1]))
         acts = [E]
         x, K = E, 3 + 6 * self.levels
         for l in range(4):
@@ -169,45 +250,34 @@ class ProposalEngine:
                         out_hi=y[0], out_lo=y[1])
             acts.append(y)
             x, K = y, H
-        sigma = torch.empty((n, 1), dtype=torch.float32, device=dev)
         linear.gemm(n, 1, _fwd_segs(x, (W[4].hi, W[4].lo), H, x3), bias=self.lins[4].bias.detach(), out_f32=sigma)
-        return sigma.view(n), acts
+        return acts
 
-    def backward(self, acts, g_sigma, x3):
-        """g_sigma (n,) fp32 -> list of (grad_weight, grad_bias) in state_dict order."""
-        dev, n = g_sigma.device, g_sigma.shape[0]
-        W = [p.sync() for p in self.packed]
+    def _backward(self, prog, acts, n, x3, grads):
+        dev = prog.dev
+        W = self.packed
         H = self.lins[0].out_features
         sm = torch.cuda.get_device_properties(dev).multi_processor_count
-        grads = [None] * 5
-        ds = linear.to_bf16(g_sigma.contiguous().view(n, 1), ld_dst=8, want_lo=x3)
-        gw = torch.empty_like(self.lins[4].weight)
-        gb = torch.empty_like(self.lins[4].bias)
-        wgrad(ds, acts[4], 1, H, n, x3, gw, sm_count=sm)
-        bgrad(ds, 1, n, x3, gb, sm_count=sm)
-        grads[4] = (gw, gb)
+        ds = _empty16(n, 8, dev, x3)
+        prog.call(lambda: linear.to_bf16(prog.inp["g"].view(n, 1), ld_dst=8, want_lo=x3, out=ds))
+        wgrad(ds, acts[4], 1, H, n, x3, grads[4][0], sm_count=sm)
+        bgrad(ds, 1, n, x3, grads[4][1], sm_count=sm)
         dy = _empty16(n, H, dev, x3)
         linear.gemm(n, H, _dgrad_segs(ds, (W[4].hi, W[4].lo), 1, x3), mask=acts[4][0], out_hi=dy[0], out_lo=dy[1])
         for l in (3, 2, 1, 0):
             x = acts[l]
-            in_f = self.lins[l].in_features
-            gw = torch.empty_like(self.lins[l].weight)
-            gb = torch.empty_like(self.lins[l].bias)
-            wgrad(dy, x, H, in_f, n, x3, gw, sm_count=sm)
-            bgrad(dy, H, n, x3, gb, sm_count=sm)
-            grads[l] = (gw, gb)
+            wgrad(dy, x, H, self.lins[l].in_features, n, x3, grads[l][0], sm_count=sm)
+            bgrad(dy, H, n, x3, grads[l][1], sm_count=sm)
             if l > 0:
                 dx = _empty16(n, H, dev, x3)
                 linear.gemm(n, H, _dgrad_segs(dy, (W[l].hi, W[l].lo), H, x3), mask=x[0], out_hi=dx[0], out_lo=dx[1])
                 dy = dx
-        return grads
 
 
-class NerfEngine:
+class NerfEngine(_Engine):
     """MipNeRF(10, 4, 256): the vanilla 8x256 NeRF MLP with skip connection and heads (nerf/mip_model.py:14-60)."""
 
-    keep_last_acts = False
-    last_acts = None
+    out_cols = 4
 
     def __init__(self, module):
         self.m = module
@@ -223,18 +293,25 @@ class NerfEngine:
         perm4 = torch.cat((torch.arange(self.enc) + H, torch.arange(H)))
         self.packed = [PackedLinear(l) for l in self.lins]
         self.packed[4] = PackedLinear(self.lins[4], col_perm=perm4, in_pad=H + _pad8(self.enc))
+        self._init_plans()
 
-    def forward(self, pts, x3):
-        """pts (n, 6) fp32 = [xyz, dir] -> (out (n, 4) fp32 = [sigmoid rgb, raw sigma], saved activations)."""
-        dev, n = pts.device, pts.shape[0]
-        W = [p.sync() for p in self.packed]
+    def _forward(self, prog, n, x3, out):
+        """pts (n, 6) fp32 = [xyz, dir] -> out (n, 4) fp32 = [sigmoid rgb, raw sigma]; returns the saved activations."""
+        dev = prog.dev
+        W = self.packed
         H, enc_w, denc_w = self.H, _pad8(self.enc), _pad8(self.denc)
         b = [l.bias.detach() for l in self.lins]
         C5 = _empty16(n, H + enc_w, dev, x3)                      # [h4 | enc]
         E = (C5[0][:, H:], C5[1][:, H:] if x3 else None)
-        encode(pts, 0, self.pl, False, E[0], E[1])
         C9 = _empty16(n, H + denc_w, dev, x3)                     # [bottleneck | enc(dir)]
-        encode(pts, 3, self.dl, True, C9[0][:, H:], C9[1][:, H:] if x3 else None)
+        D = (C9[0][:, H:], C9[1][:, H:] if x3 else None)
+
+        def encodings():
+            pts = prog.inp["pts"]
+            encode(pts, 0, self.pl, False, E[0], E[1])
+            encode(pts, 3, self.dl, True, D[0], D[1])
+
+        prog.call(encodings)
         wl = lambda i: (W[i].hi, W[i].lo)
         h1, h2, h3 = (_empty16(n, H, dev, x3) for _ in range(3))
         linear.gemm(n, H, _fwd_segs(E, wl(0), self.enc, x3), bias=b[0], act=linear.ACT_RELU, out_hi=h1[0], out_lo=h1[1])
@@ -246,33 +323,29 @@ class NerfEngine:
         linear.gemm(n, H, _fwd_segs(C5, wl(4), H + self.enc, x3), bias=b[4], act=linear.ACT_RELU, out_hi=h5[0], out_lo=h5[1])
         linear.gemm(n, H, _fwd_segs(h5, wl(5), H, x3), bias=b[5], act=linear.ACT_RELU, out_hi=h6[0], out_lo=h6[1])
         linear.gemm(n, 256, _fwd_segs(h6, wl(6), H, x3), bias=b[6], act=linear.ACT_RELU, out_hi=h7[0], out_lo=h7[1])
-        out = torch.empty((n, 4), dtype=torch.float32, device=dev)
         linear.gemm(n, 1, _fwd_segs(h7, wl(8), 256, x3), bias=b[8], out_f32=out[:, 3:])                     # opacity_head
         bn = (C9[0][:, :256], C9[1][:, :256] if x3 else None)
         linear.gemm(n, 256, _fwd_segs(h7, wl(7), 256, x3), bias=b[7], out_hi=bn[0], out_lo=bn[1])           # bottle_neck (linear)
         t = _empty16(n, 128, dev, x3)
         linear.gemm(n, 128, _fwd_segs(C9, wl(9), 256 + self.denc, x3), bias=b[9], act=linear.ACT_RELU, out_hi=t[0], out_lo=t[1])
         linear.gemm(n, 3, _fwd_segs(t, wl(10), 128, x3), bias=b[10], act=linear.ACT_SIGMOID, out_f32=out[:, :3])
-        return out, dict(E=E, h1=h1, h2=h2, h3=h3, C5=C5, h5=h5, h6=h6, h7=h7, C9=C9, t=t, out=out)
+        return dict(E=E, h1=h1, h2=h2, h3=h3, C5=C5, h5=h5, h6=h6, h7=h7, C9=C9, t=t)
 
-    def backward(self, a, g_out, x3):
-        """g_out (n, 4) fp32 -> list of 11 (grad_weight, grad_bias) in state_dict order."""
-        dev, n = g_out.device, g_out.shape[0]
-        W = [p.sync() for p in self.packed]
+    def _backward(self, prog, a, n, x3, grads):
+        dev = prog.dev
+        W = self.packed
         H = self.H
         sm = torch.cuda.get_device_properties(dev).multi_processor_count
         wl = lambda i: (W[i].hi, W[i].lo)
-        grads = [None] * 11
 
         def wg(i, dy, x, n_out, n_in, perm=None):
-            gw, gb = torch.empty_like(self.lins[i].weight), torch.empty_like(self.lins[i].bias)
-            wgrad(dy, x, n_out, n_in, n, x3, gw, perm=perm, sm_count=sm)
-            bgrad(dy, n_out, n, x3, gb, sm_count=sm)
-            grads[i] = (gw, gb)
+            wgrad(dy, x, n_out, n_in, n, x3, grads[i][0], perm=perm, sm_count=sm)
+            bgrad(dy, n_out, n, x3, grads[i][1], sm_count=sm)
 
         dz, ds = _empty16(n, 8, dev, x3), _empty16(n, 8, dev, x3)
-        check(load().nb2_nerf_head_backward(handle(dev), a["out"].data_ptr(), g_out.contiguous().data_ptr(), n, dz[0].data_ptr(),
-                                            _lib.ptr_int(dz[1]), ds[0].data_ptr(), _lib.ptr_int(ds[1]), stream_ptr(dev)))
+        prog.call(lambda: check(load().nb2_nerf_head_backward(handle(dev), prog.inp["out"].data_ptr(), prog.inp["g"].data_ptr(), n,
+                                                              dz[0].data_ptr(), _lib.ptr_int(dz[1]), ds[0].data_ptr(), _lib.ptr_int(ds[1]),
+                                                              stream_ptr(dev))))
         wg(10, dz, a["t"], 3, 128)                                                                   # rgb_layer.2
         dt = _empty16(n, 128, dev, x3)
         linear.gemm(n, 128, _dgrad_segs(dz, wl(10), 3, x3), mask=a["t"][0], out_hi=dt[0], out_lo=dt[1])
@@ -303,7 +376,6 @@ class NerfEngine:
         d1 = _empty16(n, H, dev, x3)
         linear.gemm(n, H, _dgrad_segs(d2, wl(1), H, x3), mask=a["h1"][0], out_hi=d1[0], out_lo=d1[1])
         wg(0, d1, a["E"], H, self.enc)
-        return grads
 
 
 class _MLPFunction(torch.autograd.Function):
@@ -311,16 +383,19 @@ class _MLPFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, engine, x3, pts, *params):
-        out, acts = engine.forward(pts, x3)
-        ctx.engine, ctx.x3, ctx.acts = engine, x3, acts
+        out, plan = engine.forward(pts, x3)
+        ctx.engine, ctx.x3, ctx.plan = engine, x3, plan
         if engine.keep_last_acts:
-            engine.last_acts = acts
+            engine.last_acts = plan.acts
         return out
 
     @staticmethod
     def backward(ctx, g):
-        grads = ctx.engine.backward(ctx.acts, g.contiguous(), ctx.x3)
-        ctx.acts = None
+        if ctx.plan is None or not ctx.plan.busy:
+            raise _lib.NB2Error("the layer-wise engine keeps one set of activations per forward: backward ran twice, or the same "
+                                "network ran forward again at this batch size before this backward")
+        grads = ctx.engine.backward(ctx.plan, g, ctx.x3)
+        ctx.plan = None
         flat = []
         for gw, gb in grads:
             flat += [gw, gb]

@@ -4,6 +4,7 @@ passes, torch.cat inputs), ragged sizes, N tiling, split-K and every epilogue op
 import pytest
 import torch
 
+import nerf_b200
 from nerf_b200 import linear
 
 pytestmark = pytest.mark.gpu
@@ -102,3 +103,48 @@ def test_bias_gradient_as_ones_gemm():
     s = torch.empty(256, device=DEV)
     bgrad((xh, xl), 256, 5000, True, s)
     close(s, x.sum(0), 2e-4)
+
+
+def test_launch_plan_replays_bit_identically_with_rebound_outputs():
+    """linear.Program: a forward GEMM, a split-K wgrad and two deferred reductions recorded once, replayed into other output
+    tensors: bit-identical to the eager launches (nb2_gemm_bf16_batch / nb2_reduce_splits_batch against the single calls)."""
+    rows, N_out, K_in, splits = 3000, 256, 320, 9
+    X, W, dY = bf(rnd((rows, K_in), 1)), bf(rnd((N_out, K_in), 2, 0.06)), bf(rnd((rows, N_out), 3))
+    perm = torch.cat((torch.arange(64) + 256, torch.arange(256))).to(torch.int32).to(DEV)
+    ld_ws, m_pad = 320, 256
+
+    def eager():
+        y = torch.empty((rows, N_out), device=DEV)
+        linear.gemm(rows, N_out, [(X, False, W, False, K_in)], out_f32=y)
+        outs = []
+        for p in (None, perm):
+            ws = torch.empty((splits, m_pad, ld_ws), device=DEV)
+            linear.gemm(N_out, K_in, [(dY, True, X, True, rows)], out_f32=ws.view(splits * m_pad, ld_ws)[:N_out], splits=splits, split_stride=m_pad * ld_ws)
+            g = torch.empty((N_out, K_in), device=DEV)
+            linear.reduce_splits(ws, splits, m_pad * ld_ws, N_out, K_in, ld_ws, g, col_perm=p)
+            outs.append(g)
+        return y, outs
+    y_ref, g_ref = eager()
+    y = torch.empty((rows, N_out), device=DEV)
+    flat = torch.empty(2 * N_out * K_in, device=DEV)
+    marks = []
+    with linear.Program(torch.device(DEV)) as prog:
+        prog.bind(y=y, grads=flat)
+        linear.gemm(rows, N_out, [(X, False, W, False, K_in)], out_f32=y)
+        prog.call(lambda: marks.append(1))
+        for i, p in enumerate((None, perm)):
+            ws = torch.empty((splits, m_pad, ld_ws), device=DEV)
+            linear.gemm(N_out, K_in, [(dY, True, X, True, rows)], out_f32=ws.view(splits * m_pad, ld_ws)[:N_out], splits=splits, split_stride=m_pad * ld_ws)
+            linear.reduce_splits(ws, splits, m_pad * ld_ws, N_out, K_in, ld_ws, flat[i * N_out * K_in:(i + 1) * N_out * K_in].view(N_out, K_in), col_perm=p)
+    assert not marks and float(torch.nan_to_num(y).abs().max()) >= 0       # recording launched nothing
+    for _ in range(2):
+        y2 = torch.full((rows, N_out), float("nan"), device=DEV)
+        flat2 = torch.full((2 * N_out * K_in,), float("nan"), device=DEV)
+        prog.run(y=y2, grads=flat2)
+        assert torch.equal(y2, y_ref)
+        assert torch.equal(flat2[:N_out * K_in].view(N_out, K_in), g_ref[0]) and torch.equal(flat2[N_out * K_in:].view(N_out, K_in), g_ref[1])
+    assert len(marks) == 2
+    with pytest.raises(nerf_b200.NB2Error):
+        with linear.Program(torch.device(DEV)):
+            linear.reduce_splits(ws, splits, m_pad * ld_ws, N_out, K_in, ld_ws, g_ref[0], accumulate=True)
+    assert linear.recording() is None

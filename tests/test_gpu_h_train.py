@@ -191,3 +191,60 @@ def test_reference_run_closure_and_adam_step(precision):
     with torch.no_grad():
         img = nerf_b200.render_image(mip_net, prop_net, vs["cam_tf"].to(DEV), (50, 50), 60.0, 2.0, 6.0, 128, white_bkg=True)["rgb"]
     assert bool(torch.isfinite(img).all())
+
+
+def test_launch_plans_are_reused_and_change_nothing():
+    """Three optimizer steps with the recorded launch plans (nerf_b200/linear.py: Program) against the same three steps with
+    the plans cleared before every forward (every step records anew): bit-identical weights.  Then the edge cases of the
+    plan bookkeeping: a second forward before the first backward, a forward whose backward never runs, backward twice."""
+    from nerf_b200.train_engine import NerfEngine, ProposalEngine, train_engine_of
+
+    def run(clear):
+        torch.manual_seed(0)
+        prop = load(nerf_b200.ProposalNetwork(10, 256), O.make_params("proposal", 1, "smooth"))
+        net = load(nerf_b200.MipNeRF(10, 4, 256), O.make_params("nerf", 2, "smooth"))
+        opt = torch.optim.Adam(list(net.parameters()) + list(prop.parameters()), lr=1e-3)
+        en, ep = train_engine_of(net, NerfEngine), train_engine_of(prop, ProposalEngine)
+        for step in range(3):
+            if clear:
+                en.clear_plans(), ep.clear_plans()
+            pts = torch.cat((O.det_uniform((2048, 3), 20 + step, -2.0, 2.0), O.det_uniform((2048, 3), 30 + step, -1.0, 1.0)), -1).to(DEV)
+            opt.zero_grad()
+            loss = (net.forward(pts[None]) ** 2).sum() + (prop.forward(pts[None, :, :3].contiguous()) ** 2).sum()
+            loss.backward()
+            opt.step()
+        assert clear or (len(en.plans) == 1 and len(ep.plans) == 1)
+        return net, prop, en
+    (na, pa, en), (nb, pb, _) = run(False), run(True)
+    for a, b in zip(list(na.parameters()) + list(pa.parameters()), list(nb.parameters()) + list(pb.parameters())):
+        assert torch.equal(a, b)
+    # two forwards in flight: the second records its own plan, both backward passes are right
+    pts = torch.cat((O.det_uniform((2048, 3), 40, -2.0, 2.0), O.det_uniform((2048, 3), 41, -1.0, 1.0)), -1).to(DEV)
+    pts2 = pts.flip(0).contiguous()
+
+    def grads_of(*outs_and_w):
+        for p in na.parameters():
+            p.grad = None
+        sum((o * w).sum() for o, w in outs_and_w).backward()
+        return [p.grad.clone() for p in na.parameters()]
+    g1 = grads_of((na.forward(pts[None]), 1.0))
+    g2 = grads_of((na.forward(pts2[None]), 0.5))
+    o1 = na.forward(pts[None])
+    o2 = na.forward(pts2[None])                  # same batch size, first backward still pending
+    both = grads_of((o1, 1.0), (o2, 0.5))
+    for a, b, c in zip(g1, g2, both):
+        assert float((a + b - c).abs().max()) <= 1e-5 * max(float(c.abs().max()), 1e-6) + 1e-7
+    # a forward whose backward never runs must not poison the next step
+    na.forward(pts[None])
+    g1b = grads_of((na.forward(pts[None]), 1.0))
+    for a, b in zip(g1, g1b):
+        assert torch.equal(a, b)
+    # outputs of earlier calls are not overwritten by later ones
+    oa = na.forward(pts[None])
+    keep = oa.detach().clone()
+    na.forward(pts2[None])
+    assert torch.equal(oa.detach(), keep)
+    out = na.forward(pts[None])
+    out.sum().backward(retain_graph=True)
+    with pytest.raises(nerf_b200.NB2Error):
+        out.sum().backward()

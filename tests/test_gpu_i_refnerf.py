@@ -104,3 +104,45 @@ def test_render_image_ref_branch_vs_reference(golden_round2):
     net.load_state_dict(O.make_params("nerf", 2, "smooth"))
     out = nerf_b200.render_image(net.to(DEV), prop, pose.to(DEV), (H, W), focal, 2.0, 6.0, 128, render_normal=True, jitter=jitter.to(DEV), u=u.to(DEV))
     assert set(out) == {"rgb"}
+
+
+def test_refnerf_launch_plan_reuse():
+    """The recorded launch plan of a batch size is replayed on later calls: other inputs of the same size, a weight update and
+    the training-mode perturbation path give what a freshly built module gives; outputs of earlier calls stay intact."""
+    rn = refnet()
+    a = O.det_uniform((64, 32, 6), 81, -1.0, 1.0).to(DEV)
+    b = O.det_uniform((64, 32, 6), 82, -1.0, 1.0).to(DEV)
+    with torch.no_grad():
+        ya, na_ = rn.forward(a)
+        keep = ya.clone()
+        yb, nb_ = rn.forward(b)
+        assert len(rn.__dict__["_nb2_ref_plans"]) == 1 and torch.equal(ya, keep)
+        fresh = refnet()
+        yb2, nb2_ = fresh.forward(b)
+        assert torch.equal(yb, yb2) and torch.equal(nb_, nb2_)
+        # a weight update is picked up (weights are re-converted in place, the plan's pointers stay valid)
+        for m in (rn, fresh):
+            m.spa_block1[0].weight.mul_(1.01)
+            m.rho_tau_head.bias.add_(0.01)
+        yc, _ = rn.forward(a)
+        yc2, _ = refnet_like(fresh).forward(a)
+        assert torch.equal(yc, yc2) and not torch.equal(yc, keep)
+        # three batch sizes: the oldest plan is dropped, results unaffected
+        for n in (16, 48):
+            rn.forward(O.det_uniform((n, 32, 6), 83, -1.0, 1.0).to(DEV))
+        assert len(rn.__dict__["_nb2_ref_plans"]) == rn.max_plans
+        ya3, _ = rn.forward(a)
+        assert torch.equal(ya3, yc)
+        rn.train()
+        torch.manual_seed(5)
+        t1, _ = rn.forward(a)
+        torch.manual_seed(5)
+        t2, _ = rn.forward(a)
+        assert torch.equal(t1, t2) and not torch.equal(t1, yc)
+
+
+def refnet_like(src):
+    """A new module holding src's current weights (no engine state)."""
+    rn = nerf_b200.RefNeRF(10, 4)
+    rn.load_state_dict(src.state_dict())
+    return rn.to(DEV).eval()

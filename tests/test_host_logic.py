@@ -123,3 +123,36 @@ def test_blender_dataset_loader(tmp_path):
     assert abs(float(img[0, 0, 0]) - ((25 / 255) * a + (1 - a))) < 2e-2 and abs(float(img[1, 0, 0]) - (1 - a)) < 2e-2
     assert torch.allclose(tf[:, 3], torch.tensor([2.0, 4.0, 3.0]) * 2.0)
     assert torch.allclose(ds.tfs[2][:, 3], torch.tensor([2.0, 4.0, 3.0]))                      # the stored transforms stay unscaled
+
+
+def test_launch_plan_records_batches_and_rebases_dynamic_pointers():
+    """linear.Program (host logic only: recording never calls the library): consecutive GEMMs form one batch, a non-GEMM
+    call splits batches, reductions are deferred, pointers into bound tensors are re-based on every run."""
+    import ctypes
+    from nerf_b200 import _lib, linear
+    assert ctypes.sizeof(_lib.ReduceDesc) == 56
+    bf = torch.bfloat16
+    x, w = torch.zeros((16, 8), dtype=bf), torch.zeros((4, 8), dtype=bf)
+    y = torch.zeros((16, 8), dtype=bf)
+    out = torch.zeros((16, 4), dtype=torch.float32)
+    ws = torch.zeros(2 * 128 * 32, dtype=torch.float32)
+    grads = torch.zeros(64, dtype=torch.float32)
+    calls = []
+    with linear.Program("cpu") as prog:
+        prog.bind(out=out, grads=grads)
+        linear.gemm(16, 8, [(x, False, w, False, 8)], out_hi=y)
+        linear.gemm(16, 1, [(y, False, w, False, 8)], out_f32=out[:, 3:])
+        prog.call(lambda: calls.append(1))
+        linear.gemm(16, 3, [(y, False, w, False, 8)], out_f32=out[:, :3])
+        linear.reduce_splits(ws, 2, 128 * 32, 4, 8, 32, grads[32:].view(4, 8))
+    assert linear.recording() is None
+    assert [n for _, n in prog._final] == [2, -1, 1] and len(prog._red) == 1 and prog.launches == 5
+    # re-base by hand what run() does (run() itself needs the CUDA library)
+    out2, grads2 = torch.zeros_like(out), torch.zeros_like(grads)
+    base = {"out": out2.data_ptr(), "grads": grads2.data_ptr()}
+    for elem, field, key, off in prog._patches:
+        setattr(elem, field, base[key] + off)
+    assert prog._final[0][0][1].out_f32 == out2.data_ptr() + 12
+    assert prog._final[2][0][0].out_f32 == out2.data_ptr()
+    assert prog._red[0].out == grads2.data_ptr() + 128 and prog._red[0].split_stride == 128 * 32
+    assert prog._final[0][0][0].out_f32 is None          # not dynamic, not an fp32 output
