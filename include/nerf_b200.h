@@ -358,6 +358,23 @@ int nb2_ref_color(nb2_handle* h, const float* spec, const float* heads, int ld_h
 /* out[i] = a[i] . b for a (n,3), b (3): `normal @ cam_dir` of NeRF.render's normal image (nerf/nerf_base.py:111). */
 int nb2_dot3(nb2_handle* h, const float* a, const float* b, int64_t n, float* out, void* stream);
 
+/* ---- Ref-NeRF training glue: backward of the three steps above (autograd's derivatives of nerf/ref_model.py:81-105 in the
+ * reference's train.py:164-199 with is_ref_model; RefNeRF.get_grad, ref_model.py:118-124, is the d_x output below).
+ * nb2_ref_color_backward: spec (n,3) = the sigmoid-ed specular head, g_out (n,4) = gradient of [rgb, density] ->
+ *   ds (n,8) bf16 hi / lo: columns 0..2 = gradient of the specular head's pre-activation (GEMM operand), rest zero;
+ *   d_heads (n, ld_dheads >= 11) fp32: columns 3..5 diffuse, 6..8 tint, 10 density, everything else zeroed.
+ * nb2_ref_geometry_backward: d_in (n, ld_in) fp32 = gradient of the directional MLP's input, IDE columns at
+ *   [ide_col0, ide_col0 + 2 n_pairs), nv_dot next; g_normal (n,3) = gradient of the returned normal or NULL; mat / ml as
+ *   nb2_ide -> d_heads columns 0..2 (raw normal) and 9 (rho), through reflect / IDE / softplus / the normalisation.
+ * nb2_encode_backward: d_enc (n, ld) fp32 = gradient of the rows nb2_encode_bf16 writes (normalize = 0) -> d_x (n,3). */
+int nb2_ref_color_backward(nb2_handle* h, const float* spec, const float* heads, int ld_heads, int use_srgb, const float* g_out,
+                           int64_t n, void* ds_hi, void* ds_lo, float* d_heads, int ld_dheads, void* stream);
+int nb2_ref_geometry_backward(nb2_handle* h, const float* heads, int ld_heads, const float* dirs, int dir_stride, int64_t n,
+                              const float* d_in, int64_t ld_in, int ide_col0, const float* g_normal, const float* mat, const int* ml,
+                              int n_pairs, int n_pow, float* d_heads, int ld_dheads, void* stream);
+int nb2_encode_backward(nb2_handle* h, const float* x, int x_stride, int x_col0, int64_t n, int levels, const float* d_enc, int64_t ld,
+                        float* d_x, void* stream);
+
 /* ---- peer memory for the fused gather (one process per GPU, CUDA IPC over NVLink / NVSwitch) -----------------
  * nb2_ipc_alloc: cudaMalloc `bytes` on the handle's device and export a 64-byte IPC handle for it.
  * nb2_ipc_open : map another process's allocation into this process (peer access is enabled on demand).

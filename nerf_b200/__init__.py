@@ -12,7 +12,8 @@ from .nerf_helper import makeMLP, positional_encoding, saveModel, linear_to_srgb
 from .ref_func import generate_ide_fn  # noqa: F401
 from .nerf_base import NeRF, DecayLrScheduler  # noqa: F401
 from .mip_model import MipNeRF  # noqa: F401
-from .ref_model import RefNeRF  # noqa: F401
+from .ref_model import BackFaceLoss, RefNeRF, WeightedNormalLoss  # noqa: F401
+from . import param_com  # noqa: F401
 from .addtional import ProposalNetwork, LossPSNR, SoftL1Loss, ProposalLoss, getBounds  # noqa: F401
 from .mip_methods import maxBlurFilter, ipe_feature  # noqa: F401
 from .utils import inverseSample, sample_pdf, fov2Focal, pose_spherical, validSampler  # noqa: F401

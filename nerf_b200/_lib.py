@@ -96,6 +96,10 @@ SIGNATURES = {
     "nb2_max_blur_backward": (c_int, [c_vp, c_f32p, c_f32p, c_i64, c_int, c_f32p, c_vp]),
     "nb2_get_bounds_backward": (c_int, [c_vp, c_vp, c_f32p, c_i64, c_int, c_int, c_f32p, c_vp]),
     "nb2_nerf_head_backward": (c_int, [c_vp, c_f32p, c_f32p, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "nb2_ref_color_backward": (c_int, [c_vp, c_f32p, c_f32p, c_int, c_int, c_f32p, c_i64, c_vp, c_vp, c_f32p, c_int, c_vp]),
+    "nb2_ref_geometry_backward": (c_int, [c_vp, c_f32p, c_int, c_f32p, c_int, c_i64, c_f32p, c_i64, c_int, c_f32p, c_f32p, c_vp, c_int, c_int,
+                                          c_f32p, c_int, c_vp]),
+    "nb2_encode_backward": (c_int, [c_vp, c_f32p, c_int, c_int, c_i64, c_int, c_f32p, c_i64, c_f32p, c_vp]),
     "nb2_dot3": (c_int, [c_vp, c_f32p, c_f32p, c_i64, c_f32p, c_vp]),
     "nb2_ref_geometry": (c_int, [c_vp, c_f32p, c_int, c_f32p, c_int, c_i64, c_f32p, c_f32p, c_f32p, c_f32p, c_vp]),
     "nb2_ref_dir_inputs": (c_int, [c_vp, c_f32p, c_int, c_f32p, c_i64, c_vp, c_vp, c_i64, c_int, c_vp]),

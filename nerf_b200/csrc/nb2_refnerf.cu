@@ -90,9 +90,194 @@ __global__ void dot3_kernel(const float* __restrict__ a, const float* __restrict
   out[i] = __fadd_rn(__fadd_rn(__fmul_rn(a[i * 3], b[0]), __fmul_rn(a[i * 3 + 1], b[1])), __fmul_rn(a[i * 3 + 2], b[2]));
 }
 
+// ---- backward of the glue (Ref-NeRF training, train.py:164-199 with is_ref_model) -------------------------------------------
+// In the reference these are autograd's derivatives of the torch expressions of ref_model.py:81-105; restated per kernel.
+
+// colour composition.  Forward: lin_k = spec_k sigmoid(tint_k) + sigmoid(diffuse_k [- ln 3]); rgb_k = [srgb](lin_k); density passes.
+// spec is the ALREADY sigmoid-ed specular head (the GEMM epilogue applied it), so d(pre-activation) = d spec * spec (1 - spec).
+//   ds (n,8) bf16 hi/lo: columns 0..2 = gradient of the specular head's pre-activation (wgrad / dgrad operand), 3..7 zero
+//   d_heads (n, ld_dh) fp32: columns 3..5 diffuse, 6..8 tint, 10 density; every other column < ld_dh zero
+//   (columns 0..2 and 9 are written afterwards by ref_geometry_backward_kernel)
+__global__ void ref_color_backward_kernel(const float* __restrict__ spec, const float* __restrict__ heads, int ld_h, int use_srgb,
+                                          const float* __restrict__ g_out, int64_t n, __nv_bfloat16* __restrict__ ds_hi,
+                                          __nv_bfloat16* __restrict__ ds_lo, float* __restrict__ d_heads, int ld_dh) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* hrow = heads + i * ld_h;
+  const float eps = 1.1920928955078125e-07f;
+  const float4 g = reinterpret_cast<const float4*>(g_out)[i];
+  const float gk[3] = {g.x, g.y, g.z};
+  float dsl[3], ddif[3], dtint[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const float tint = 1.f / (1.f + expf(-hrow[6 + k]));
+    const float sp = spec[i * 3 + k];
+    float dif, gv = gk[k];
+    if (use_srgb) {
+      dif = 1.f / (1.f + expf(-(hrow[3 + k] - 1.0986122886681098f)));
+      const float v = __fadd_rn(__fmul_rn(sp, tint), dif);
+      // d/dv of (v <= 0.0031308 ? 12.92 v : (211 max(eps, v)^(5/12) - 11) / 200)
+      const float dv = (v <= 0.0031308f) ? 12.92f : (v > eps ? 1.055f * 0.41666666f * powf(v, 0.41666666f - 1.f) : 0.f);
+      gv *= dv;
+    } else {
+      dif = 1.f / (1.f + expf(-hrow[3 + k]));
+    }
+    dsl[k] = gv * tint * sp * (1.f - sp);
+    dtint[k] = gv * sp * tint * (1.f - tint);
+    ddif[k] = gv * dif * (1.f - dif);
+  }
+  float* drow = d_heads + i * ld_dh;
+  for (int c = 0; c < ld_dh; ++c) drow[c] = 0.f;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { drow[3 + k] = ddif[k]; drow[6 + k] = dtint[k]; }
+  drow[10] = g.w;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const float v = c < 3 ? dsl[c] : 0.f;
+    const __nv_bfloat16 hb = __float2bfloat16_rn(v);
+    ds_hi[i * 8 + c] = hb;
+    if (ds_lo) ds_lo[i * 8 + c] = __float2bfloat16_rn(v - __bfloat162float(hb));
+  }
+}
+
+// geometry + integrated directional encoding.  Forward (ref_geometry_kernel, ide_kernel): h = heads[0:3], s = |h| + 1e-7,
+// nrm = -h / s, dot = d . nrm, r = d - 2 dot nrm, kinv = softplus(rho - 1), ide_i = (x + iy)^m P_i(z) exp(-l(l+1)/2 kinv) at r.
+// Upstream: d_in row = gradient of the directional MLP's input, IDE columns at [ide_col0, ide_col0 + 2 n_pairs), nv_dot next;
+// g_normal = gradient of the returned normal (or NULL).  Writes d_heads columns 0..2 (raw normal) and 9 (rho).
+constexpr int kRgMaxPairs = 36;
+constexpr int kRgMaxPow = 17;
+__global__ void __launch_bounds__(128) ref_geometry_backward_kernel(const float* __restrict__ heads, int ld_h, const float* __restrict__ dirs,
+                                                                    int dir_stride, int64_t n, const float* __restrict__ d_in, int64_t ld_in,
+                                                                    int ide_col0, const float* __restrict__ g_normal,
+                                                                    const float* __restrict__ mat, const int* __restrict__ ml, int n_pairs,
+                                                                    int n_pow, float* __restrict__ d_heads, int ld_dh) {
+  __shared__ float sh_mat[kRgMaxPow * kRgMaxPairs];
+  __shared__ int sh_ml[2 * kRgMaxPairs];
+  for (int t = threadIdx.x; t < n_pow * n_pairs; t += blockDim.x) sh_mat[t] = __ldg(mat + t);
+  for (int t = threadIdx.x; t < 2 * n_pairs; t += blockDim.x) sh_ml[t] = __ldg(ml + t);
+  __syncthreads();
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* hrow = heads + i * ld_h;
+  const float hx = hrow[0], hy = hrow[1], hz = hrow[2];
+  const float hn = sqrtf(hx * hx + hy * hy + hz * hz);
+  const float s = hn + 1e-7f;
+  const float ax = -hx / s, ay = -hy / s, az = -hz / s;
+  const float dx = dirs[i * dir_stride], dy = dirs[i * dir_stride + 1], dz = dirs[i * dir_stride + 2];
+  const float dot = dx * ax + dy * ay + dz * az;
+  const float x = dx - 2.f * dot * ax, y = dy - 2.f * dot * ay, z = dz - 2.f * dot * az;   // reflected direction
+  const float rho1 = hrow[9] - 1.f;
+  const float kinv = softplus_f(rho1);
+  float zp[kRgMaxPow], cr[kRgMaxPow], ci[kRgMaxPow];
+  zp[0] = 1.f; cr[0] = 1.f; ci[0] = 0.f;
+#pragma unroll
+  for (int k = 1; k < kRgMaxPow; ++k) {
+    zp[k] = zp[k - 1] * z;
+    cr[k] = cr[k - 1] * x - ci[k - 1] * y;
+    ci[k] = cr[k - 1] * y + ci[k - 1] * x;
+  }
+  const float* grow = d_in + i * ld_in + ide_col0;
+  float gx = 0.f, gy = 0.f, gz = 0.f, gk = 0.f;
+  for (int p = 0; p < n_pairs; ++p) {
+    const int m = sh_ml[p], l = sh_ml[n_pairs + p];
+    float acc = 0.f, dacc = 0.f;
+#pragma unroll
+    for (int k = 0; k < kRgMaxPow; ++k)
+      if (k < n_pow) {
+        const float c = sh_mat[k * n_pairs + p];
+        acc = fmaf(zp[k], c, acc);
+        if (k >= 1) dacc = fmaf((float)k * zp[k - 1], c, dacc);
+      }
+    const float sig = 0.5f * (float)(l * (l + 1));
+    const float att = expf(-sig * kinv);
+    float pr = 0.f, pi = 0.f, qr = 0.f, qi = 0.f;     // (x + iy)^m and (x + iy)^(m - 1)
+#pragma unroll
+    for (int k = 0; k < kRgMaxPow; ++k) {
+      if (k == m) { pr = cr[k]; pi = ci[k]; }
+      if (k == m - 1) { qr = cr[k]; qi = ci[k]; }
+    }
+    const float g_re = grow[p], g_im = grow[n_pairs + p];
+    const float base = acc * att;
+    gz += (g_re * pr + g_im * pi) * dacc * att;
+    gx += (float)m * (g_re * qr + g_im * qi) * base;
+    gy += (float)m * (g_im * qr - g_re * qi) * base;
+    gk -= sig * (g_re * pr + g_im * pi) * base;
+  }
+  const float g_nv = grow[2 * n_pairs];
+  // d nrm: returned normal, nv_dot = nrm . d, r = d - 2 (d . nrm) nrm
+  const float gr_n = gx * ax + gy * ay + gz * az;
+  float nx = g_nv * dx - 2.f * (gr_n * dx + dot * gx);
+  float ny = g_nv * dy - 2.f * (gr_n * dy + dot * gy);
+  float nz = g_nv * dz - 2.f * (gr_n * dz + dot * gz);
+  if (g_normal != nullptr) { nx += g_normal[i * 3]; ny += g_normal[i * 3 + 1]; nz += g_normal[i * 3 + 2]; }
+  // nrm = -h / (|h| + eps):  d h_b = -d nrm_b / s + (d nrm . h) h_b / (|h| s^2)
+  const float nh = nx * hx + ny * hy + nz * hz;
+  const float coef = hn > 0.f ? nh / (hn * s * s) : 0.f;
+  float* drow = d_heads + i * ld_dh;
+  drow[0] = -nx / s + coef * hx;
+  drow[1] = -ny / s + coef * hy;
+  drow[2] = -nz / s + coef * hz;
+  drow[9] = gk / (1.f + expf(-rho1));     // d softplus
+}
+
+// positional encoding.  Forward row = [x, sin(2^l x), cos(2^l x) ...] (3-wide terms); d x_k = d row_k + sum_l 2^l (cos(2^l x_k)
+// d sin_lk - sin(2^l x_k) d cos_lk).  d_enc (n, ld) fp32, d_x (n, 3).
+__global__ void encode_backward_kernel(const float* __restrict__ x, int x_stride, int x_col0, int64_t n, int levels,
+                                       const float* __restrict__ d_enc, int64_t ld, float* __restrict__ d_x) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * 3) return;
+  const int64_t r = i / 3;
+  const int k = (int)(i - r * 3);
+  const float xv = __ldg(x + r * x_stride + x_col0 + k);
+  const float* g = d_enc + r * ld;
+  float acc = g[k];
+  for (int l = 0; l < levels; ++l) {
+    const float f = exp2f((float)l);
+    float sn, cs;
+    sincos_any(xv * f, sn, cs);
+    acc += f * (cs * g[3 + 6 * l + k] - sn * g[3 + 6 * l + 3 + k]);
+  }
+  d_x[i] = acc;
+}
+
 }  // namespace nb2
 
 using namespace nb2;
+
+extern "C" int nb2_ref_color_backward(nb2_handle* h, const float* spec, const float* heads, int ld_heads, int use_srgb, const float* g_out,
+                                      int64_t n, void* ds_hi, void* ds_lo, float* d_heads, int ld_dheads, void* stream) {
+  NB2_ENTER(h);
+  if (n == 0) return NB2_OK;
+  NB2_CHECK_ARG(spec && heads && g_out && ds_hi && d_heads && ld_heads >= 11 && ld_dheads >= 11, "ref_color_backward: bad arguments");
+  ref_color_backward_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(spec, heads, ld_heads, use_srgb, g_out, n, (__nv_bfloat16*)ds_hi,
+                                                                                (__nv_bfloat16*)ds_lo, d_heads, ld_dheads);
+  NB2_LAUNCH_CHECK(h);
+  return NB2_OK;
+}
+
+extern "C" int nb2_ref_geometry_backward(nb2_handle* h, const float* heads, int ld_heads, const float* dirs, int dir_stride, int64_t n,
+                                         const float* d_in, int64_t ld_in, int ide_col0, const float* g_normal, const float* mat, const int* ml,
+                                         int n_pairs, int n_pow, float* d_heads, int ld_dheads, void* stream) {
+  NB2_ENTER(h);
+  if (n == 0) return NB2_OK;
+  NB2_CHECK_ARG(heads && dirs && d_in && mat && ml && d_heads && ld_heads >= 11 && ld_dheads >= 11 && dir_stride >= 3, "ref_geometry_backward: bad arguments");
+  NB2_CHECK_ARG(n_pairs >= 1 && n_pairs <= kRgMaxPairs && n_pow >= 1 && n_pow <= kRgMaxPow && ide_col0 >= 0 && ld_in >= ide_col0 + 2 * n_pairs + 1,
+                "ref_geometry_backward: at most %d (m, l) pairs, degree %d; d_in rows must hold the IDE and nv_dot columns", kRgMaxPairs, kRgMaxPow - 1);
+  ref_geometry_backward_kernel<<<grid_for(n, 128), 128, 0, (cudaStream_t)stream>>>(heads, ld_heads, dirs, dir_stride, n, d_in, ld_in, ide_col0, g_normal,
+                                                                                   mat, ml, n_pairs, n_pow, d_heads, ld_dheads);
+  NB2_LAUNCH_CHECK(h);
+  return NB2_OK;
+}
+
+extern "C" int nb2_encode_backward(nb2_handle* h, const float* x, int x_stride, int x_col0, int64_t n, int levels, const float* d_enc, int64_t ld,
+                                   float* d_x, void* stream) {
+  NB2_ENTER(h);
+  if (n == 0) return NB2_OK;
+  NB2_CHECK_ARG(x && d_enc && d_x && x_stride >= x_col0 + 3 && levels >= 0 && levels <= 16 && ld >= 3 + 6 * levels, "encode_backward: bad arguments");
+  encode_backward_kernel<<<grid_for(n * 3, 256), 256, 0, (cudaStream_t)stream>>>(x, x_stride, x_col0, n, levels, d_enc, ld, d_x);
+  NB2_LAUNCH_CHECK(h);
+  return NB2_OK;
+}
 
 extern "C" int nb2_dot3(nb2_handle* h, const float* a, const float* b, int64_t n, float* out, void* stream) {
   NB2_ENTER(h);

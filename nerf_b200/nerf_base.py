@@ -142,7 +142,7 @@ class NeRF(PackedModule):
                density_act=F.relu, render_depth: Optional[Tuple[float, float]] = None, normal_info: Optional[Tuple] = None):
         if _act_name(density_act) != "relu":
             raise _lib.NB2Error("render(): the compositing kernel implements density_act = relu (the render path's choice)")
-        if not mul_norm:
+        if not (mul_norm == True):  # noqa: E712 -- the reference's own test (nerf_base.py:96); train.py:182 passes a callable here, which is "false"
             ray_dirs = torch.zeros_like(ray_dirs[..., :3])
             ray_dirs[..., 0] = 1.0  # unit norm: depth is used as given
         if torch.is_grad_enabled() and rgbo.requires_grad:

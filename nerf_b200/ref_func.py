@@ -47,11 +47,15 @@ def generate_ide_fn(deg_view):
     ml = torch.from_numpy(ml_array.astype(np.int32)).contiguous()
     cache = {}
 
-    def integrated_dir_enc_fn(xyz, kappa_inv):
-        """xyz [..., 3] directions, kappa_inv [..., 1] -> [..., 2 * n_pairs] (real parts, then imaginary parts)."""
-        dev = xyz.device
+    def tables(dev):
+        """(mat (n_pow, n_pairs) fp32, ml (2, n_pairs) int32) on `dev` (also read by the backward kernel)."""
         if dev not in cache:
             cache[dev] = (mat.to(dev), ml.to(dev))
-        return ops.ide(xyz, kappa_inv, *cache[dev])
+        return cache[dev]
 
+    def integrated_dir_enc_fn(xyz, kappa_inv):
+        """xyz [..., 3] directions, kappa_inv [..., 1] -> [..., 2 * n_pairs] (real parts, then imaginary parts)."""
+        return ops.ide(xyz, kappa_inv, *tables(xyz.device))
+
+    integrated_dir_enc_fn.tables = tables
     return integrated_dir_enc_fn

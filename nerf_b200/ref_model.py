@@ -6,8 +6,13 @@ fp32 accumulation), the integrated directional encoding is `ide_kernel`, and the
 (normal / reflection / roughness, colour composition) are three small CUDA kernels (csrc/nb2_refnerf.cu).  The
 reference's torch.cat inputs are column ranges of wider buffers (the matching weight columns are permuted once).
 
-Not built: the training-side pieces of Ref-NeRF (density gradients w.r.t. position = double backward through the spatial
-MLP, WeightedNormalLoss / BackFaceLoss): forward() is inference-only and refuses to run under autograd.
+Training (train.py:164-199 with is_ref_model): forward() under autograd is one torch.autograd.Function over the same
+recorded forward plan; its backward is a second recorded plan on the same engine -- dgrad / wgrad / bias-gradient GEMMs for
+the 19 linear layers, and three CUDA kernels for the glue (colour composition, normal / reflection / integrated directional
+encoding / roughness, positional encoding) -- and returns the gradient of every parameter AND of the sample positions, which
+is what the reference's RefNeRF.get_grad (torch.autograd.grad(density, positions), ref_model.py:118-124: first order, the
+result carries no graph) and its normal / back-face losses need.  Gradients w.r.t. the view directions are not produced
+(the reference never asks for them).
 """
 from typing import Optional
 
@@ -19,7 +24,7 @@ from ._lib import check, handle, load, stream_ptr
 from .nerf_base import NeRF, _NormalDot
 from .nerf_helper import makeMLP
 from .ref_func import generate_ide_fn
-from .train_engine import PackedLinear, _empty16, _fwd_segs, _pad8, encode
+from .train_engine import PackedLinear, _dgrad_segs, _empty16, _fwd_segs, _pad8, bgrad, encode, wgrad
 
 
 class _PackedCat(PackedLinear):
@@ -117,8 +122,8 @@ class RefNeRF(NeRF):
         e = self._engine()
         return [*e["spa"], e["heads"], e["bottle"], *e["dir"], e["spec"]]
 
-    def _forward_engine(self, pts2d, dirs2d, cam_dir=None, shift_softplus=False):
-        """pts2d (n, >=3) positions, dirs2d (n, 3) view directions -> (rgbo (n,4), normal (n,3), ndot (n,) or None).
+    def _forward_engine(self, pts2d, dirs2d, cam_dir=None, shift_softplus=False, want_grad=False):
+        """pts2d (n, >=3) positions, dirs2d (n, 3) view directions -> (rgbo (n,4), normal (n,3), ndot (n,) or None[, plan]).
         The launches are recorded once per batch size as a linear.Program and replayed (one host call per run of GEMMs)."""
         x3 = self.precision != "bf16"
         if self.precision not in (None, "bf16x3", "bf16"):
@@ -137,16 +142,22 @@ class RefNeRF(NeRF):
         dyn = dict(pts=pts2d, dirs=dirs2d, out=out, normal=normal)
         if has_cam:
             dyn.update(ndot=ndot, cam=cam)
-        prog = plans.get(key)
-        if prog is None:
+        plan = plans.get(key)
+        if plan is None or plan.busy:          # busy: its activations belong to a forward whose backward is still to come
+            plans.pop(key, None)
             while len(plans) >= self.max_plans:
                 plans.pop(next(iter(plans)))
+            plan = plans[key] = _RefPlan()
             with linear.Program(dev) as prog:
                 prog.bind(**dyn)
-                self._record(prog, n, x3, has_cam, shift_softplus)
-            plans[key] = prog
-        prog.run(**dyn)
-        prog.release()
+                plan.acts = self._record(prog, n, x3, has_cam, shift_softplus)
+            plan.fwd = prog
+        plan.fwd.run(**dyn)
+        plan.fwd.release()
+        plan.epoch += 1
+        if want_grad:
+            plan.busy = True
+            return out, normal, ndot, plan
         return out, normal, ndot
 
     def _record(self, prog, n, x3, has_cam, shift_softplus):
@@ -237,14 +248,229 @@ class RefNeRF(NeRF):
         prog.call(lambda: check(lib.nb2_ref_color(h, spec.data_ptr(), heads.data_ptr(), 12, 1 if self.use_srgb else 0, 1 if shift_softplus else 0,
                                                   inp["normal"].data_ptr(), _lib.ptr_int(inp.get("cam")), n, inp["out"].data_ptr(),
                                                   _lib.ptr_int(inp.get("ndot")), stream_ptr(dev))))
+        return dict(E=E, h1=h1, h2=h2, h3=h3, C5=C5, h5=h5, h6=h6, h7=h7, inter=inter, heads=heads, Cd=Cd, A_in=A_in, r1=r1, r2=r2, r3=r3,
+                    q1=q1, q2=q2, q3=q3, q4=q4, spec=spec, shift_softplus=bool(shift_softplus))
+
+    # ---- backward plan (training) ---------------------------------------------------------------------------------
+    def _grad_slots(self, flat):
+        """{id(parameter): view of the flat gradient buffer}, in self.parameters() order."""
+        views, off = {}, 0
+        for p in self.parameters():
+            views[id(p)] = flat[off:off + p.numel()].view(p.shape)
+            off += p.numel()
+        return views
+
+    def _backward_engine(self, plan, pts2d, dirs2d, g_out, g_normal, x3):
+        """-> (flat parameter gradients in self.parameters() order, d_pts (n, 3))."""
+        dev, n = g_out.device, g_out.shape[0]
+        flat = torch.empty(sum(p.numel() for p in self.parameters()), dtype=torch.float32, device=dev)
+        d_pts = torch.empty((n, 3), dtype=torch.float32, device=dev)
+        dyn = dict(pts=pts2d, dirs=dirs2d, g=g_out, gn=g_normal, grads=flat, d_pts=d_pts)
+        if plan.bwd is None:
+            with linear.Program(dev) as prog:
+                prog.bind(**dyn)
+                self._record_backward(prog, plan.acts, n, x3, self._grad_slots(flat))
+            plan.bwd = prog
+        plan.bwd.run(**dyn)
+        plan.bwd.release()
+        plan.busy = False
+        return flat, d_pts
+
+    def _record_backward(self, prog, a, n, x3, slot):
+        e = self._engine()
+        dev = prog.dev
+        H, enc = self.hidden_unit, 3 + 6 * self.position_flevel
+        enc_w = _pad8(enc)
+        bd = self.bottle_neck_dim
+        din = 1 + bd + self.dir_enc_dim
+        din_w = _pad8(din)
+        lib, h = load(), handle(dev)
+        inp = prog.inp
+        sm = torch.cuda.get_device_properties(dev).multi_processor_count
+        spa, dr, hk, bk, sk = e["spa"], e["dir"], e["heads"], e["bottle"], e["spec"]
+        if a["shift_softplus"]:
+            raise _lib.NB2Error("RefNeRF: the density shift of the render path is applied by the caller during training (train.py:181)")
+
+        def wg(pk, dy, x, n_out, n_in, perm=None):
+            wgrad(dy, x, n_out, n_in, n, x3, slot[id(pk.lin.weight)], perm=perm, sm_count=sm)
+            bgrad(dy, n_out, n, x3, slot[id(pk.lin.bias)], sm_count=sm)
+
+        def dg(dy, w, K, mask, width=None):
+            """dX = (dY W) [* relu mask] as bf16 hi / lo rows."""
+            out = _empty16(n, H if width is None else width, dev, x3)
+            linear.gemm(n, out[0].shape[1], _dgrad_segs(dy, w, K, x3), mask=mask, out_hi=out[0], out_lo=out[1])
+            return out
+
+        wl = lambda pk: (pk.hi, pk.lo)
+        # ---- colour composition (ref_model.py:102-105) and the specular head ----
+        ds = _empty16(n, 8, dev, x3)
+        d_heads = torch.empty((n, 16), dtype=torch.float32, device=dev)
+        prog.call(lambda: check(lib.nb2_ref_color_backward(h, a["spec"].data_ptr(), a["heads"].data_ptr(), 12, 1 if self.use_srgb else 0,
+                                                           inp["g"].data_ptr(), n, ds[0].data_ptr(), _lib.ptr_int(ds[1]), d_heads.data_ptr(), 16,
+                                                           stream_ptr(dev))))
+        wg(sk, ds, a["q4"], 3, H)
+        dq4 = dg(ds, wl(sk), 3, a["q4"][0])
+        # ---- directional MLP (ref_model.py:96-101), last layer first ----
+        wg(dr[7], dq4, a["q3"], H, H)
+        dq3 = dg(dq4, wl(dr[7]), H, a["q3"][0])
+        wg(dr[6], dq3, a["q2"], H, H)
+        dq2 = dg(dq3, wl(dr[6]), H, a["q2"][0])
+        wg(dr[5], dq2, a["q1"], H, H)
+        dq1 = dg(dq2, wl(dr[5]), H, a["q1"][0])
+        wg(dr[4], dq1, a["Cd"], H, H + din, perm=dr[4].perm)                       # dir_block2.0 on cat(all_inputs, r)
+        dr4 = dg(dq1, dr[4].cols(0, H), H, a["Cd"][0][:, :H])
+        wg(dr[3], dr4, a["r3"], H, H)
+        dr3 = dg(dr4, wl(dr[3]), H, a["r3"][0])
+        wg(dr[2], dr3, a["r2"], H, H)
+        dr2 = dg(dr3, wl(dr[2]), H, a["r2"][0])
+        wg(dr[1], dr2, a["r1"], H, H)
+        dr1 = dg(dr2, wl(dr[1]), H, a["r1"][0])
+        wg(dr[0], dr1, a["A_in"], H, din)
+        # gradient of cat(bottleneck, ide, nv_dot): through dir_block1.0 and through the skip input of dir_block2.0
+        d_in32 = torch.empty((n, din_w), dtype=torch.float32, device=dev)
+        d_in = _empty16(n, din_w, dev, x3)
+        linear.gemm(n, din_w, _dgrad_segs(dr1, wl(dr[0]), H, x3) + _dgrad_segs(dq1, dr[4].cols(H, H + din_w), H, x3),
+                    out_f32=d_in32, out_hi=d_in[0], out_lo=d_in[1])
+        db = (d_in[0][:, :bd], d_in[1][:, :bd] if x3 else None)
+        wg(bk, db, a["inter"], bd, H)
+        # ---- normal / reflection / IDE / roughness (ref_model.py:83-94) ----
+        mat, ml = self.integrated_dir_enc.tables(dev)
+        n_pow, n_pairs = mat.shape
+
+        def geometry():
+            dirs = inp["dirs"]
+            check(lib.nb2_ref_geometry_backward(h, a["heads"].data_ptr(), 12, dirs.data_ptr(), dirs.stride(0), n, d_in32.data_ptr(), din_w, bd,
+                                                inp["gn"].data_ptr(), mat.data_ptr(), ml.data_ptr(), n_pairs, n_pow, d_heads.data_ptr(), 16,
+                                                stream_ptr(dev)))
+            linear.to_bf16(d_heads, ld_dst=16, want_lo=x3, out=dh)
+
+        dh = _empty16(n, 16, dev, x3)
+        prog.keep += [mat, ml]
+        prog.call(geometry)
+        # ---- heads (ref_model.py:81-82; packed rows: norm_col_tint_head 0..8, rho_tau_head 9..10) ----
+        nct, rt = self.norm_col_tint_head, self.rho_tau_head
+        wgrad(dh, a["inter"], 11, H, n, x3, [(0, 9, slot[id(nct.weight)]), (9, 11, slot[id(rt.weight)])], sm_count=sm)
+        bgrad(dh, 11, n, x3, [(0, 9, slot[id(nct.bias)]), (9, 11, slot[id(rt.bias)])], sm_count=sm)
+        d_inter = _empty16(n, H, dev, x3)
+        linear.gemm(n, H, _dgrad_segs(dh, wl(hk), 11, x3) + _dgrad_segs(db, wl(bk), bd, x3), mask=a["inter"][0],
+                    out_hi=d_inter[0], out_lo=d_inter[1])
+        # ---- spatial MLP (ref_model.py:70-80) ----
+        wg(spa[7], d_inter, a["h7"], H, H)
+        dh7 = dg(d_inter, wl(spa[7]), H, a["h7"][0])
+        wg(spa[6], dh7, a["h6"], H, H)
+        dh6 = dg(dh7, wl(spa[6]), H, a["h6"][0])
+        wg(spa[5], dh6, a["h5"], H, H)
+        dh5 = dg(dh6, wl(spa[5]), H, a["h5"][0])
+        wg(spa[4], dh5, a["C5"], H, H + enc, perm=spa[4].perm)                      # spa_block2.0 on cat(enc, h)
+        dh4 = dg(dh5, spa[4].cols(0, H), H, a["C5"][0][:, :H])
+        wg(spa[3], dh4, a["h3"], H, H)
+        dh3 = dg(dh4, wl(spa[3]), H, a["h3"][0])
+        wg(spa[2], dh3, a["h2"], H, H)
+        dh2 = dg(dh3, wl(spa[2]), H, a["h2"][0])
+        wg(spa[1], dh2, a["h1"], H, H)
+        dh1 = dg(dh2, wl(spa[1]), H, a["h1"][0])
+        wg(spa[0], dh1, a["E"], H, enc)
+        # ---- positions: the encoding enters spa_block1.0 and the skip input of spa_block2.0 (RefNeRF.get_grad) ----
+        d_enc = torch.empty((n, enc_w), dtype=torch.float32, device=dev)
+        linear.gemm(n, enc_w, _dgrad_segs(dh1, wl(spa[0]), H, x3) + _dgrad_segs(dh5, spa[4].cols(H, H + enc_w), H, x3), out_f32=d_enc)
+
+        def positions():
+            pts = inp["pts"]
+            check(lib.nb2_encode_backward(h, pts.data_ptr(), pts.stride(0), 0, n, self.position_flevel, d_enc.data_ptr(), enc_w,
+                                          inp["d_pts"].data_ptr(), stream_ptr(dev)))
+
+        prog.call(positions)
 
     def forward(self, pts: torch.Tensor, ray_d: Optional[torch.Tensor] = None):
-        """pts (ray_num, point_num, 6) = [xyz, dir] (or (.., 3) with ray_d) -> ((.., 4) = [rgb, density], normal (.., 3))."""
-        if torch.is_grad_enabled() and (pts.requires_grad or (ray_d is not None and ray_d.requires_grad)):
-            raise _lib.NB2Error("RefNeRF.forward: gradients w.r.t. positions (the reference's get_grad) are not built; run under torch.no_grad()")
+        """pts (ray_num, point_num, 6) = [xyz, dir] (or (.., 3) with ray_d) -> ((.., 4) = [rgb, density], normal (.., 3)).
+        Under autograd (a parameter or `pts` requires a gradient) the result is differentiable w.r.t. the parameters and the
+        positions (train.py:176-180: fine_pos.requires_grad = True; RefNeRF.get_grad(density, fine_pos))."""
         R, P = pts.shape[0], pts.shape[1]
-        p2 = _lib.f32(pts.detach()).reshape(R * P, pts.shape[-1])
-        d2 = p2[:, 3:6] if ray_d is None else _lib.f32(ray_d.detach()).reshape(R * P, 3)
-        with torch.no_grad():
-            out, normal, _ = self._forward_engine(p2, d2)
+        wants = torch.is_grad_enabled() and (pts.requires_grad or any(p.requires_grad for p in self.parameters()))
+        if torch.is_grad_enabled() and ray_d is not None and ray_d.requires_grad:
+            raise _lib.NB2Error("RefNeRF.forward: gradients w.r.t. the view directions are not built (the reference never takes them)")
+        if not wants:
+            p2 = _lib.f32(pts.detach()).reshape(R * P, pts.shape[-1])
+            d2 = p2[:, 3:6] if ray_d is None else _lib.f32(ray_d.detach()).reshape(R * P, 3)
+            with torch.no_grad():
+                out, normal, _ = self._forward_engine(p2, d2)
+            return out.view(R, P, 4), normal.view(R, P, 3)
+        p2 = _lib.f32(pts).reshape(R * P, pts.shape[-1])
+        d2 = p2.detach()[:, 3:6] if ray_d is None else _lib.f32(ray_d.detach()).reshape(R * P, 3)
+        out, normal = _RefFunction.apply(self, p2, d2, *self.parameters())
         return out.view(R, P, 4), normal.view(R, P, 3)
+
+    # ---- training-side helpers of the reference (ref_model.py:107-124) ----------------------------------------------------
+    @staticmethod
+    def coarse_grad_select(fine_grads: torch.Tensor, sort_inds: torch.Tensor, c_pnum: int) -> torch.Tensor:
+        """Rows of `fine_grads` (ray_num, all_pnum, C) that came from the coarse samples, in sorted order: the merged samples
+        are cat(fine, coarse) before the sort (nerf_base.py:58-73), so the last c_pnum pre-sort positions are the coarse ones."""
+        ray_num, all_pnum, _ = fine_grads.shape
+        selector = torch.arange(all_pnum, device=fine_grads.device).expand(ray_num, all_pnum) >= all_pnum - c_pnum
+        selector = torch.gather(selector, -1, sort_inds)
+        return fine_grads[selector].reshape(ray_num, c_pnum, -1)
+
+    @staticmethod
+    def get_grad(func_val: torch.Tensor, inputs: torch.Tensor) -> torch.Tensor:
+        """Normalised gradient of `func_val` (density) w.r.t. `inputs` (positions); first order, no graph (ref_model.py:118-124)."""
+        grad, = torch.autograd.grad(func_val, inputs, torch.ones_like(func_val), retain_graph=True)
+        grad_norm = grad.norm(dim=-1, keepdim=True)
+        return grad / torch.maximum(torch.full_like(grad_norm, 1e-5), grad_norm)
+
+
+class _RefPlan:
+    """The recorded forward (and, once needed, backward) launches of a RefNeRF at one batch size, with the activations."""
+
+    def __init__(self):
+        self.fwd = self.bwd = None
+        self.acts = None
+        self.busy = False
+        self.epoch = 0
+
+
+class _RefFunction(torch.autograd.Function):
+    """forward(module, pts2d, dirs2d, *params) -> (rgbo (n,4), normal (n,3)); params are passed so autograd routes their gradients."""
+
+    @staticmethod
+    def forward(ctx, module, pts2d, dirs2d, *params):
+        pts2d = pts2d.contiguous()
+        out, normal, _, plan = module._forward_engine(pts2d, dirs2d, want_grad=True)
+        ctx.module, ctx.plan, ctx.epoch, ctx.x3 = module, plan, plan.epoch, module.precision != "bf16"
+        ctx.pts, ctx.dirs = pts2d, dirs2d
+        return out, normal
+
+    @staticmethod
+    def backward(ctx, g_out, g_normal):
+        if ctx.plan.epoch != ctx.epoch:
+            raise _lib.NB2Error("RefNeRF keeps one set of activations per recorded plan: the module ran forward again at this batch size "
+                                "after this pass had been differentiated, so its activations are gone")
+        m = ctx.module
+        flat, d_pts = m._backward_engine(ctx.plan, ctx.pts, ctx.dirs, g_out.contiguous(), g_normal.contiguous(), ctx.x3)
+        grads, off = [], 0
+        for p in m.parameters():
+            grads.append(flat[off:off + p.numel()].view(p.shape))
+            off += p.numel()
+        if ctx.pts.shape[1] != 3:
+            full = torch.zeros_like(ctx.pts)
+            full[:, :3] = d_pts
+            d_pts = full
+        return (None, d_pts, None, *grads)
+
+
+class WeightedNormalLoss(nn.Module):
+    """ref_model.py:127-135: weight (ray_num, point_num) * (1 - <d_norm, p_norm>), mean over points or sum."""
+
+    def __init__(self, size_average=False):
+        super().__init__()
+        self.size_average = size_average
+
+    def forward(self, weight: torch.Tensor, d_norm: torch.Tensor, p_norm: torch.Tensor) -> torch.Tensor:
+        dot_diff = 1. - torch.sum(d_norm * p_norm, dim=-1)
+        return torch.mean(weight * dot_diff) if self.size_average else torch.sum(weight * dot_diff)
+
+
+class BackFaceLoss(nn.Module):
+    """ref_model.py:137-143: mean of weight * relu(<normal, ray_d>) (normals facing away from the camera)."""
+
+    def forward(self, weight: torch.Tensor, normal: torch.Tensor, ray_d: torch.Tensor) -> torch.Tensor:
+        return torch.mean(weight * torch.relu(torch.sum(normal * ray_d, dim=-1)))

@@ -113,6 +113,11 @@ class _Ones:
         return b[:rows]
 
 
+def _row_targets(grad, n_out):
+    """grad: one tensor for all n_out rows, or [(row0, row1, tensor)] when the rows belong to several parameters (packed heads)."""
+    return grad if isinstance(grad, list) else [(0, n_out, grad)]
+
+
 def bgrad(dy, n_out, rows, x3, grad_b, sm_count=148):
     """grad_b (n_out,) fp32 = column sums of dy over `rows` samples, as dy^T @ ones on the tensor cores (split-K, deterministic)."""
     dev = dy[0].device
@@ -123,7 +128,8 @@ def bgrad(dy, n_out, rows, x3, grad_b, sm_count=148):
     out = ws[: splits * m_pad * 32].view(splits * m_pad, 32)
     segs = [(dy[0], True, ones, True, rows)] + ([(dy[1], True, ones, True, rows)] if x3 else [])
     linear.gemm(n_out, 8, segs, out_f32=out[:n_out], splits=splits, split_stride=m_pad * 32)
-    linear.reduce_splits(ws, splits, m_pad * 32, n_out, 1, 32, grad_b.view(n_out, 1))
+    for r0, r1, g in _row_targets(grad_b, n_out):
+        linear.reduce_splits(ws[r0 * 32:], splits, m_pad * 32, r1 - r0, 1, 32, g.view(r1 - r0, 1))
 
 
 def wgrad(dy, x, n_out, n_in, rows, x3, grad_w, perm=None, sm_count=148):
@@ -141,7 +147,8 @@ def wgrad(dy, x, n_out, n_in, rows, x3, grad_w, perm=None, sm_count=148):
     else:
         segs = [(dy[0], True, x[0], True, rows)]
     linear.gemm(n_out, n_cols, segs, out_f32=out[:n_out], splits=max(splits, 1) if splits > 1 else 1, split_stride=m_pad * ld_ws)
-    linear.reduce_splits(ws, splits, m_pad * ld_ws, n_out, n_in, ld_ws, grad_w, col_perm=perm)
+    for r0, r1, g in _row_targets(grad_w, n_out):
+        linear.reduce_splits(ws[r0 * ld_ws:], splits, m_pad * ld_ws, r1 - r0, n_in, ld_ws, g, col_perm=perm)
 
 
 class _Plan:
@@ -151,7 +158,8 @@ class _Plan:
         self.fwd = self.bwd = None
         self.acts = None
         self.out = None
-        self.busy = False      # between a forward and its backward the activations belong to that autograd node
+        self.busy = False      # between a forward and its (first) backward the activations belong to that autograd node
+        self.epoch = 0         # forward passes run on this plan: a later backward of an older pass finds its activations gone
 
 
 class _Engine:
@@ -195,6 +203,7 @@ class _Engine:
         plan.fwd.run(pts=pts, out=out)
         plan.fwd.release()
         plan.out, plan.busy = out, True
+        plan.epoch += 1
         return out, plan
 
     def backward(self, plan, g_out, x3):
@@ -209,7 +218,7 @@ class _Engine:
             plan.bwd = prog
         plan.bwd.run(g=g_out, out=plan.out, grads=flat)
         plan.bwd.release()
-        plan.out, plan.busy = None, False
+        plan.busy = False      # the next forward may take the plan; until then this pass can be differentiated again
         return self._grad_views(flat)
 
     def _grad_views(self, flat):
@@ -384,18 +393,17 @@ class _MLPFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, engine, x3, pts, *params):
         out, plan = engine.forward(pts, x3)
-        ctx.engine, ctx.x3, ctx.plan = engine, x3, plan
+        ctx.engine, ctx.x3, ctx.plan, ctx.epoch = engine, x3, plan, plan.epoch
         if engine.keep_last_acts:
             engine.last_acts = plan.acts
         return out
 
     @staticmethod
     def backward(ctx, g):
-        if ctx.plan is None or not ctx.plan.busy:
-            raise _lib.NB2Error("the layer-wise engine keeps one set of activations per forward: backward ran twice, or the same "
-                                "network ran forward again at this batch size before this backward")
+        if ctx.plan.epoch != ctx.epoch:
+            raise _lib.NB2Error("the layer-wise engine keeps one set of activations per recorded plan: this network ran forward again "
+                                "at this batch size after this pass had been differentiated, so its activations are gone")
         grads = ctx.engine.backward(ctx.plan, g, ctx.x3)
-        ctx.plan = None
         flat = []
         for gw, gb in grads:
             flat += [gw, gb]

@@ -381,11 +381,15 @@ def linear_to_srgb(linear):
 # ----------------------------------------------------------------------------------------------
 # f3  Ref-NeRF forward (eval mode: no bottleneck noise)                        nerf/ref_model.py:67-109
 # ----------------------------------------------------------------------------------------------
-def refnerf_forward(sd, pts6, pos_levels=10, sh_level=4, use_srgb=False):
-    """pts6 (..., 6) = [xyz, dir] -> (rgbo (..., 4) = [rgb, density], normal (..., 3))."""
+def refnerf_forward(sd, pts6, pos_levels=10, sh_level=4, use_srgb=False, relu_masks=None):
+    """pts6 (..., 6) = [xyz, dir] -> (rgbo (..., 4) = [rgb, density], normal (..., 3)).
+    relu_masks: see _relu (16 patterns: spa_block1, spa_block2, dir_block1, dir_block2, four layers each)."""
+    counter = [0]
+
     def seq(h, prefix, idxs):
         for i in idxs:
-            h = F.relu(F.linear(h, sd[f"{prefix}.{i}.weight"], sd[f"{prefix}.{i}.bias"]))
+            h = _relu(F.linear(h, sd[f"{prefix}.{i}.weight"], sd[f"{prefix}.{i}.bias"]), relu_masks, counter[0])
+            counter[0] += 1
         return h
     x, ray_d = pts6[..., :3], pts6[..., 3:6]
     enc_x = torch.cat((x, positional_encoding(x, pos_levels)), dim=-1)                                  # :68-73

@@ -108,3 +108,108 @@ def test_flat_gradient_allreduce_two_ranks():
         p.join(timeout=300)
         assert p.exitcode == 0
     assert all(ok for _, ok, _ in got) and all(n == 530052 for _, _, n in got), got
+
+
+def _per_tensor_param_com():
+    """The reference's per-parameter exchange (nerf/param_com.py:13-54), restated as the oracle of the flat versions."""
+    def send(model, ranks, group=None):
+        for p in model.parameters():
+            for r in ranks:
+                dist.send(tensor=p.data, dst=r, group=group)
+
+    def recv(model, src, group=None):
+        for p in model.parameters():
+            dist.recv(tensor=p.data, src=src, group=group)
+
+    def recv_avg(model, tmp, weights, srcs, self_rank=0, group=None):
+        for p_tmp, p_model in zip(tmp.parameters(), model.parameters()):
+            p_model.data *= weights[self_rank]
+            for s in srcs:
+                dist.recv(tensor=p_tmp.data, src=s, group=group)
+                p_model.data += weights[s] * p_tmp.data
+
+    def reduce(model, weights, self_rank, dst=0, group=None):
+        for p in model.parameters():
+            p.data *= weights[self_rank]
+            dist.reduce(tensor=p.data, dst=dst, group=group)
+
+    def broadcast(model, src=0, group=None):
+        for p in model.parameters():
+            dist.broadcast(tensor=p.data, src=src, group=group)
+
+    def all_reduce(model, group=None):
+        for p in model.parameters():
+            dist.all_reduce(tensor=p.data, group=group)
+    return send, recv, recv_avg, reduce, broadcast, all_reduce
+
+
+def _param_com_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import copy
+    import nerf_b200
+    from nerf_b200 import param_com as pc
+    r_send, r_recv, r_recv_avg, r_reduce, r_broadcast, r_all_reduce = _per_tensor_param_com()
+    torch.manual_seed(100 + rank)
+    base = nerf_b200.ProposalNetwork(10, 256)
+    for p in base.parameters():
+        p.data.uniform_(-1.0, 1.0)
+    weights = [0.5, 0.3, 0.2]
+    others = [r for r in range(world) if r != 0]
+    results = []
+
+    def scenario(impl):
+        send, recv, recv_avg, reduce, broadcast, all_reduce = impl
+        out = []
+        # model_average.py:236-244: rank 0 averages what the others send, then sends the average back
+        m, tmp = copy.deepcopy(base), copy.deepcopy(base)
+        if rank == 0:
+            recv_avg(m, tmp, weights, others, 0)
+            send(m, others)
+        else:
+            send(m, [0])
+            recv(m, 0)
+        out.append([p.data.clone() for p in m.parameters()] + ([p.data.clone() for p in tmp.parameters()] if rank == 0 else []))
+        # :246-247: weighted reduce onto rank 0, broadcast back
+        m = copy.deepcopy(base)
+        reduce(m, weights, rank, 0)
+        broadcast(m, 0)
+        out.append([p.data.clone() for p in m.parameters()])
+        # :249-251: pre-weighted all-reduce
+        m = copy.deepcopy(base)
+        for p in m.parameters():
+            p.data *= weights[rank]
+        all_reduce(m)
+        out.append([p.data.clone() for p in m.parameters()])
+        return out
+    ours = scenario((pc.param_send, pc.param_recv, pc.param_recv_avg, pc.param_reduce, pc.param_broadcast, pc.param_all_reduce))
+    dist.barrier()
+    ref = scenario((r_send, r_recv, r_recv_avg, r_reduce, r_broadcast, r_all_reduce))
+    # point-to-point exchange + weighted average: the same element-wise arithmetic in the same order -> bit-identical;
+    # reduce / all-reduce: a ring sums an element in the order of the chunk it falls in, which moves with the buffer layout
+    # (3+ ranks) -> equal to a few ulps
+    same = all(len(sa) == len(sb) for sa, sb in zip(ours, ref)) and all(torch.equal(a, b) for a, b in zip(ours[0], ref[0]))
+    same = same and all(float((a - b).abs().max()) <= 4e-7 for s in (1, 2) for a, b in zip(ours[s], ref[s]))
+    # every rank ends each scenario with the same averaged model
+    digest = [float(sum(t.double().sum() for t in s[:10])) for s in ours]
+    q.put((rank, bool(same), digest))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_param_com_flat_exchange_equals_per_tensor_exchange():
+    """nerf_b200.param_com (one flat buffer per call) against the reference's per-parameter loops on three gloo ranks."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_param_com_worker, args=(r, 3, port, q)) for r in range(3)]
+    for p in procs:
+        p.start()
+    got = sorted(q.get(timeout=300) for _ in range(3))
+    for p in procs:
+        p.join(timeout=300)
+        assert p.exitcode == 0
+    assert all(same for _, same, _ in got), got
+    for s in range(3):
+        assert got[0][2][s] == got[1][2][s] == got[2][2][s], got       # every rank holds the same averaged model

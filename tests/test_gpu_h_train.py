@@ -244,7 +244,16 @@ def test_launch_plans_are_reused_and_change_nothing():
     keep = oa.detach().clone()
     na.forward(pts2[None])
     assert torch.equal(oa.detach(), keep)
+    # a pass may be differentiated again while its activations are intact (the reference's get_grad + loss.backward()) ...
     out = na.forward(pts[None])
+    for p in na.parameters():
+        p.grad = None
     out.sum().backward(retain_graph=True)
+    ga = [p.grad.clone() for p in na.parameters()]
+    out.sum().backward(retain_graph=True)
+    for a, p in zip(ga, na.parameters()):
+        assert float((2 * a - p.grad).abs().max()) <= 1e-5 * max(float(a.abs().max()), 1e-6) + 1e-7
+    # ... and not after the plan has been given to a later forward
+    na.forward(pts[None])
     with pytest.raises(nerf_b200.NB2Error):
         out.sum().backward()

@@ -146,3 +146,131 @@ def refnet_like(src):
     rn = nerf_b200.RefNeRF(10, 4)
     rn.load_state_dict(src.state_dict())
     return rn.to(DEV).eval()
+
+
+# ---- training side (train.py:164-199 with is_ref_model) -----------------------------------------------------
+def norm_err(got, ref):
+    return float((got.double() - ref.double()).norm()) / max(float(ref.double().norm()), 1e-30)
+
+
+def _ref_masks(rn, shape):
+    """The engine's own ReLU patterns of the last forward, in the oracle's layer order (see nerf_oracle._relu)."""
+    (plan,) = [p for p in rn.__dict__["_nb2_ref_plans"].values() if p.acts is not None and p.epoch > 0][-1:]
+    a = plan.acts
+    H = rn.hidden_unit
+    acts = [a["h1"][0], a["h2"][0], a["h3"][0], a["C5"][0][:, :H], a["h5"][0], a["h6"][0], a["h7"][0], a["inter"][0],
+            a["r1"][0], a["r2"][0], a["r3"][0], a["Cd"][0][:, :H], a["q1"][0], a["q2"][0], a["q3"][0], a["q4"][0]]
+    return [(t > 0).reshape(*shape, H) for t in acts]
+
+
+@pytest.mark.parametrize("use_srgb", [False, True])
+@pytest.mark.parametrize("precision,tol", [("bf16x3", 2e-4), ("bf16", 8e-2)])
+def test_refnerf_backward_vs_autograd(use_srgb, precision, tol):
+    """RefNeRF.forward under autograd: parameter gradients, position gradients and RefNeRF.get_grad (the normalised density
+    gradient, ref_model.py:118-124) against fp64 torch autograd over the oracle, with the engine's activation pattern
+    imposed on the oracle (tests/test_gpu_h_train.py explains why)."""
+    R, P = 24, 32
+    rn = refnet(use_srgb, precision)
+    pos = O.det_uniform((R, P, 3), 91, -1.5, 1.5).to(DEV).requires_grad_(True)
+    dirs = O.det_uniform((R, 1, 3), 92, -1.0, 1.0).expand(R, P, 3).contiguous().to(DEV)
+    g_rgbo = O.det_uniform((R, P, 4), 93, -1.0, 1.0).to(DEV)
+    g_n = O.det_uniform((R, P, 3), 94, -1.0, 1.0).to(DEV)
+    out, normal = rn.forward(pos, dirs)
+    assert out.requires_grad and normal.requires_grad
+    dgrad = -nerf_b200.RefNeRF.get_grad(out[..., -1], pos)
+    assert not dgrad.requires_grad
+    ((out * g_rgbo).sum() + (normal * g_n).sum()).backward()
+    masks = _ref_masks(rn, (R, P))
+    sd64 = {k: v.detach().double().requires_grad_(True) for k, v in rn.state_dict().items()}
+    pos64 = pos.detach().double().requires_grad_(True)
+    o64, n64 = O.refnerf_forward(sd64, torch.cat((pos64, dirs.double()), -1), use_srgb=use_srgb, relu_masks=masks)
+    assert float((out.detach() - o64.detach()).abs().max()) <= (1e-4 if precision == "bf16x3" else 0.2)
+    g64, = torch.autograd.grad(o64[..., -1], pos64, torch.ones_like(o64[..., -1]), retain_graph=True)
+    ref_dgrad = -g64 / torch.maximum(torch.full_like(g64[..., :1], 1e-5), g64.norm(dim=-1, keepdim=True))
+    ((o64 * g_rgbo.double()).sum() + (n64 * g_n.double()).sum()).backward()
+    worst = 0.0
+    for (name, p) in rn.named_parameters():
+        e = norm_err(p.grad, sd64[name].grad)
+        worst = max(worst, e)
+        assert e <= tol, (name, e)
+    e_pos, e_dg = norm_err(pos.grad, pos64.grad), norm_err(dgrad, ref_dgrad)
+    print(f"Ref-NeRF backward {precision} srgb={use_srgb}: worst parameter gradient {worst:.2e}, d positions {e_pos:.2e}, get_grad {e_dg:.2e}")
+    assert e_pos <= tol and e_dg <= tol
+
+
+def test_refnerf_training_closure_of_the_reference():
+    """train.py:164-199, is_ref_model branch, with nerf_b200 modules: proposal network -> weights -> resample -> coarseFineMerge ->
+    RefNeRF.forward(fine_pos, fine_dir) -> get_grad -> shifted softplus in place -> render -> normal / back-face / proposal /
+    image losses -> backward -> Adam step.  Loss against the oracle evaluated on the same samples; every gradient finite;
+    a second step runs on the recorded plans."""
+    from nerf_b200 import NeRF, ProposalNetwork, getBounds, inverseSample, maxBlurFilter
+    import torch.nn.functional as F
+    R, Pc, Pf = 96, 64, 128
+    torch.manual_seed(3)
+    rn = refnet()
+    rn.train()
+    rn.perturb_bottle_neck_w = 0.0       # (the Gaussian bottleneck noise is drawn by torch; zero width keeps the oracle comparison exact)
+    prop = nerf_b200.ProposalNetwork(10, 256)
+    prop.load_state_dict(O.make_params("proposal", 1, "smooth"))
+    prop = prop.to(DEV)
+    opt = torch.optim.Adam(list(rn.parameters()) + list(prop.parameters()), lr=1e-4)
+    normal_loss_func, bf_loss_func = nerf_b200.WeightedNormalLoss(True), nerf_b200.BackFaceLoss()
+    prop_loss_func, loss_func = nerf_b200.ProposalLoss(), nerf_b200.SoftL1Loss()
+    Hh = Ww = 64
+    rgbs = O.det_uniform((Hh * Ww, 3), 95, 0.0, 1.0).to(DEV)
+    rows, cols = torch.meshgrid(torch.arange(Hh), torch.arange(Ww), indexing="ij")
+    coords = torch.stack((cols - Ww // 2, Hh // 2 - rows), dim=-1).reshape(-1, 2).to(DEV)
+    cam_tf = nerf_b200.pose_spherical(30.0, -30.0, 4.0)[:3, :].contiguous().to(DEV)
+    focal = nerf_b200.fov2Focal(0.6911112070083618, (Hh, Ww))
+    saved = {}
+
+    def run():
+        coarse_samples, coarse_lengths, rgb_targets, coarse_cam_rays = nerf_b200.validSampler(rgbs, coords, cam_tf, R, Pc, focal, 2.0, 6.0, True)
+        density = F.softplus(prop.forward(coarse_samples))
+        prop_weights = maxBlurFilter(ProposalNetwork.get_weights(density, coarse_lengths, coarse_cam_rays[:, 3:]), 0.01)
+        fine_lengths, below_idxs = inverseSample(prop_weights, coarse_lengths, Pf + 1, sort=True)
+        fine_samples, fine_lengths, below_idxs, sort_ids = NeRF.coarseFineMerge(coarse_cam_rays, coarse_lengths, fine_lengths, below_idxs)
+        fine_pos, fine_dir = fine_samples.split((3, 3), dim=-1)
+        fine_pos.requires_grad = True
+        fine_rgbo, pred_normal = rn.forward(fine_pos, fine_dir)
+        density_grad = -nerf_b200.RefNeRF.get_grad(fine_rgbo[..., -1], fine_pos)
+        fine_rgbo[..., -1] = F.softplus(fine_rgbo[..., -1] + 0.5)
+        fine_rendered, weights, _ = NeRF.render(fine_rgbo, fine_lengths, coarse_cam_rays[:, 3:], rn.density_act)
+        normal_loss = normal_loss_func(weights, density_grad, pred_normal)
+        bf_loss = bf_loss_func(weights, pred_normal, fine_dir)
+        weight_bounds = getBounds(prop_weights, below_idxs)
+        opt.zero_grad()
+        img_loss = loss_func(fine_rendered, rgb_targets)
+        prop_loss = prop_loss_func(weight_bounds, weights.detach())
+        loss = prop_loss + img_loss + 4e-4 * normal_loss + 0.1 * bf_loss
+        saved.update(fine_pos=fine_pos.detach(), fine_dir=fine_dir.detach(), fine_lengths=fine_lengths.detach(), rgb_targets=rgb_targets,
+                     weight_bounds=weight_bounds.detach(), dgrad=density_grad, sort_ids=sort_ids)
+        return loss, img_loss
+    sd_before = {k: v.detach().clone() for k, v in rn.state_dict().items()}
+    loss, img_loss = run()
+    loss.backward()
+    for name, p in list(rn.named_parameters()) + list(prop.named_parameters()):
+        assert p.grad is not None and bool(torch.isfinite(p.grad).all()), name
+    assert float(rn.spa_block1[0].weight.grad.abs().max()) > 0 and float(rn.dir_block2[6].weight.grad.abs().max()) > 0
+    # the oracle on the same fine samples (fp32 on the GPU, the reference's own formulas)
+    pos32 = saved["fine_pos"].clone().requires_grad_(True)
+    o_rgbo, o_normal = O.refnerf_forward(sd_before, torch.cat((pos32, saved["fine_dir"]), -1))
+    g, = torch.autograd.grad(o_rgbo[..., -1], pos32, torch.ones_like(o_rgbo[..., -1]), retain_graph=True)
+    o_dgrad = -g / torch.maximum(torch.full_like(g[..., :1], 1e-5), g.norm(dim=-1, keepdim=True))
+    dens = F.softplus(o_rgbo[..., -1] + 0.5)
+    w = O.weights_from_sigma(dens, saved["fine_lengths"], None, act=F.relu)          # train.py:182 passes a callable as mul_norm: no ||d|| scaling
+    rendered = torch.sum(w[:, :, None] * o_rgbo[..., :3], dim=-2)
+    o_loss = (prop_loss_func(saved["weight_bounds"], w.detach()) + loss_func(rendered, saved["rgb_targets"])
+              + 4e-4 * normal_loss_func(w, o_dgrad.detach(), o_normal) + 0.1 * bf_loss_func(w, o_normal, saved["fine_dir"]))
+    rel = abs(float(loss) - float(o_loss)) / abs(float(o_loss))
+    cos = torch.sum(saved["dgrad"] * o_dgrad.detach(), dim=-1)
+    print("Ref-NeRF training closure: loss", float(loss), "oracle", float(o_loss), "rel", rel, "density-normal cosine min / mean", float(cos.min()), float(cos.mean()))
+    assert rel <= 2e-4 and float(cos.mean()) >= 0.9999
+    sel = nerf_b200.RefNeRF.coarse_grad_select(saved["dgrad"], saved["sort_ids"], Pc)
+    assert sel.shape == (R, Pc, 3)
+    opt.step()
+    assert not torch.equal(rn.spa_block1[0].weight.detach(), sd_before["spa_block1.0.weight"])
+    loss2, _ = run()                        # second step: recorded plans, updated weights
+    loss2.backward()
+    opt.step()
+    assert bool(torch.isfinite(loss2)) and len(rn.__dict__["_nb2_ref_plans"]) == 1
