@@ -335,7 +335,7 @@ def config3_leg(dev, prop, net, ids, steps=5):
 def config4_leg(dev, prop, steps=5):
     """BASELINE configs[3]: Ref-NeRF forward on 512-ray batches (64 coarse + 129 fine merged to 192 samples, proposal + IDE):
     fused proposal kernel -> resample -> coarseFineMerge -> RefNeRF (17 layers on the layer-wise tcgen05 engine, IDE kernel)
-    -> compositing with depth and normal outputs.  (The training-side normal / orientation losses are not built.)"""
+    -> compositing with depth and normal outputs; `train_512`: the reference's Ref-NeRF training step (refnerf_train_leg)."""
     import nerf_b200
     from nerf_b200 import synthetic
     rn = nerf_b200.RefNeRF(10, 4)
@@ -359,7 +359,103 @@ def config4_leg(dev, prop, steps=5):
         flop = Hh * Ww * (FLOP_PROP_PER_RAY + 192 * 2143232)
         out[f"rays_{Hh * Ww}"] = {"rays_per_s": Hh * Ww / (ms * 1e-3), "ms_per_step": ms, "host_ms_per_step": 1e3 * (time.perf_counter() - t0) / steps,
                                   "tensor_tflops": flop / (ms * 1e-3) / 1e12}
+    out["train_512"] = refnerf_train_leg(dev, rn, prop)
     return out
+
+
+def refnerf_train_leg(dev, rn, prop, R=512, steps=10):
+    """The reference's training step with is_ref_model (train.py:164-218) on 512 rays x (64 coarse, 129 fine merged to 192):
+    proposal network -> resample -> coarseFineMerge -> RefNeRF.forward(fine_pos, fine_dir) -> get_grad (density normals) ->
+    render -> image + proposal + normal + back-face losses -> backward -> Adam.  Next to it the same step written with
+    PyTorch fp32 ops on this GPU (the oracle's functions, TF32 off)."""
+    import torch.nn.functional as F
+    import nerf_b200
+    from nerf_b200 import NeRF, ProposalNetwork, RefNeRF, getBounds, inverseSample, maxBlurFilter
+    from oracle import nerf_oracle as O
+    prop_eval = prop
+    prop = nerf_b200.ProposalNetwork(10, 256)          # a copy: the optimizer steps must not touch the network the other legs render with
+    prop.load_state_dict(prop_eval.state_dict())
+    prop = prop.to(dev)
+    rn.train()
+    opt = torch.optim.Adam(list(rn.parameters()) + list(prop.parameters()), lr=1.5e-4)
+    normal_loss_func, bf_loss_func = nerf_b200.WeightedNormalLoss(True), nerf_b200.BackFaceLoss()
+    prop_loss_func, loss_func = nerf_b200.ProposalLoss(), nerf_b200.SoftL1Loss()
+    Hh = Ww = 400
+    g = torch.Generator().manual_seed(3)
+    rgbs = torch.rand(Hh * Ww, 3, generator=g).to(dev)
+    rows, cols = torch.meshgrid(torch.arange(Hh), torch.arange(Ww), indexing="ij")
+    coords = torch.stack((cols - Ww // 2, Hh // 2 - rows), dim=-1).reshape(-1, 2).to(dev)
+    cam_tf = nerf_b200.pose_spherical(30.0, -30.0, 4.0)[:3, :].contiguous().to(dev)
+    focal = nerf_b200.fov2Focal(FOV, (Hh, Ww))
+    keep = {}
+
+    def step():
+        cs, cl, rgb_targets, cr = nerf_b200.validSampler(rgbs, coords, cam_tf, R, N_COARSE, focal, NEAR, FAR, True)
+        density = F.softplus(prop.forward(cs))
+        prop_weights = maxBlurFilter(ProposalNetwork.get_weights(density, cl, cr[:, 3:]), 0.01)
+        fine_lengths, below_idxs = inverseSample(prop_weights, cl, N_FINE + 1, sort=True)
+        fine_samples, fine_lengths, below_idxs, _ = NeRF.coarseFineMerge(cr, cl, fine_lengths, below_idxs)
+        fine_pos, fine_dir = fine_samples.split((3, 3), dim=-1)
+        fine_pos.requires_grad = True
+        fine_rgbo, pred_normal = rn.forward(fine_pos, fine_dir)
+        density_grad = -RefNeRF.get_grad(fine_rgbo[..., -1], fine_pos)
+        fine_rgbo[..., -1] = F.softplus(fine_rgbo[..., -1] + 0.5)
+        fine_rendered, weights, _ = NeRF.render(fine_rgbo, fine_lengths, cr[:, 3:], rn.density_act)
+        normal_loss = normal_loss_func(weights, density_grad, pred_normal)
+        bf_loss = bf_loss_func(weights, pred_normal, fine_dir)
+        weight_bounds = getBounds(prop_weights, below_idxs)
+        opt.zero_grad()
+        loss = prop_loss_func(weight_bounds, weights.detach()) + loss_func(fine_rendered, rgb_targets) + 4e-4 * normal_loss + 0.1 * bf_loss
+        loss.backward()
+        opt.step()
+        keep.update(cs=cs.detach(), cl=cl, rt=rgb_targets, cr=cr, pos=fine_pos.detach(), dirs=fine_dir.detach(), fl=fine_lengths.detach(),
+                    wb=weight_bounds.detach())
+        return loss
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize(dev)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    t0 = time.perf_counter()
+    for i in range(steps):
+        ev[i][0].record()
+        loss = step()
+        ev[i][1].record()
+    torch.cuda.synchronize(dev)
+    wall = (time.perf_counter() - t0) / steps
+    ms = sum(a.elapsed_time(b) for a, b in ev) / steps
+    # the same arithmetic as PyTorch ops: both MLPs forward + backward on the same samples (sampling / sorting excluded: in favour of the baseline)
+    sd_r = {k: v.detach().clone().requires_grad_(True) for k, v in rn.state_dict().items()}
+    sd_p = {k: v.detach().clone().requires_grad_(True) for k, v in prop.state_dict().items()}
+    tf32 = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+    def torch_step():
+        dens = F.softplus(O.proposal_forward(sd_p, keep["cs"]))
+        pw = O.max_blur(O.weights_from_sigma(dens, keep["cl"], keep["cr"][:, 3:]), 0.01)
+        pos = keep["pos"].clone().requires_grad_(True)
+        rgbo, normal = O.refnerf_forward(sd_r, torch.cat((pos, keep["dirs"]), -1))
+        gd, = torch.autograd.grad(rgbo[..., -1], pos, torch.ones_like(rgbo[..., -1]), retain_graph=True)
+        dg = -gd / torch.maximum(torch.full_like(gd[..., :1], 1e-5), gd.norm(dim=-1, keepdim=True))
+        w = O.weights_from_sigma(F.softplus(rgbo[..., -1] + 0.5), keep["fl"], None)
+        rendered = torch.sum(w[:, :, None] * rgbo[..., :3], dim=-2)
+        l = (loss_func(rendered, keep["rt"]) + 4e-4 * normal_loss_func(w, dg, normal) + 0.1 * bf_loss_func(w, normal, keep["dirs"])
+             + (pw.sum() * 0.0))
+        l.backward()
+        return l
+    torch_step()
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for _ in range(3):
+        torch_step()
+    torch.cuda.synchronize(dev)
+    ref_ms = 1e3 * (time.perf_counter() - t0) / 3
+    torch.backends.cuda.matmul.allow_tf32 = tf32
+    rn.eval()
+    # forward + parameter backward twice (get_grad re-runs the backward plan) ~ 5 x forward FLOP of RefNeRF, 3 x of the proposal network
+    flop = R * (3 * FLOP_PROP_PER_RAY + 5 * 192 * 2143232)
+    return {"what": refnerf_train_leg.__doc__.split("\n")[0], "rays_per_step": R, "ms_per_step": ms, "host_ms_per_step": 1e3 * wall,
+            "rays_per_s": R / (ms * 1e-3), "loss": float(loss), "tensor_tflops": flop / (ms * 1e-3) / 1e12,
+            "torch_cuda_fp32_ms_per_step": ref_ms, "speedup_vs_torch_cuda_fp32": ref_ms / ms}
 
 
 def parity_leg(dev, pose, H, W, focal, base_z, ids, precisions):

@@ -99,7 +99,8 @@ class ProposalNetwork(PackedModule):
             if encoded_pt is not None:
                 raise _lib.NB2Error("ProposalNetwork.forward(encoded_pt=...) is inference-only (the reference never trains through it)")
             from .train_engine import ProposalEngine, differentiable_forward
-            out = differentiable_forward(self, ProposalEngine, _lib.f32(pts.detach()).reshape(-1, 3), self.train_precision)
+            # positions keep their graph when they ask for a gradient (train.py:165-168, --prop_normal: get_grad(density, samples))
+            out = differentiable_forward(self, ProposalEngine, _lib.f32(pts if pts.requires_grad else pts.detach()).reshape(-1, 3), self.train_precision)
             return out.view(pts.shape[0], pts.shape[1])
         net_id = self._nb2_sync()
         if encoded_pt is not None:

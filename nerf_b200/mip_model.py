@@ -52,7 +52,8 @@ class MipNeRF(NeRF):
         """pts (ray_num, point_num, 6) = [xyz, dir] -> (ray_num, point_num, 4) = [rgb, sigma]."""
         if self._nb2_wants_grad(pts):
             from .train_engine import NerfEngine, differentiable_forward
-            out = differentiable_forward(self, NerfEngine, _lib.f32(pts.detach()).reshape(-1, pts.shape[-1]), self.train_precision)
+            # (a gradient w.r.t. pts covers the positions, columns 0..2; the direction columns receive zeros)
+            out = differentiable_forward(self, NerfEngine, _lib.f32(pts if pts.requires_grad else pts.detach()).reshape(-1, pts.shape[-1]), self.train_precision)
             return out.view(pts.shape[0], pts.shape[1], 4)
         net_id = self._nb2_sync()
         out = ops.mlp_forward(net_id, pts.reshape(-1, pts.shape[-1]), self.precision)

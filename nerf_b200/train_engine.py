@@ -160,6 +160,8 @@ class _Plan:
         self.out = None
         self.busy = False      # between a forward and its (first) backward the activations belong to that autograd node
         self.epoch = 0         # forward passes run on this plan: a later backward of an older pass finds its activations gone
+        self.want_dx = False   # the backward plan also produces d loss / d positions
+        self.pts = None
 
 
 class _Engine:
@@ -177,8 +179,8 @@ class _Engine:
     def clear_plans(self):
         self.plans.clear()
 
-    def _plan(self, n, x3, dev):
-        key = (n, x3, dev) + tuple(p.data_ptr() for l in self.lins for p in (l.weight, l.bias))
+    def _plan(self, n, x3, dev, want_dx=False):
+        key = (n, x3, dev, want_dx) + tuple(p.data_ptr() for l in self.lins for p in (l.weight, l.bias))
         plan = self.plans.get(key)
         if plan is None or plan.busy:
             # busy: a second forward before the first one's backward (or a forward whose backward never ran) records anew
@@ -186,12 +188,14 @@ class _Engine:
             while len(self.plans) >= self.max_plans:
                 self.plans.pop(next(iter(self.plans)))
             plan = self.plans[key] = _Plan()
+            plan.want_dx = want_dx
         return plan
 
-    def forward(self, pts, x3):
+    def forward(self, pts, x3, want_dx=False):
+        """want_dx: the backward pass also produces the gradient of the positions (pts columns 0..2)."""
         dev, n = pts.device, pts.shape[0]
         pts = pts.contiguous()
-        plan = self._plan(n, x3, dev)
+        plan = self._plan(n, x3, dev, want_dx)
         for p in self.packed:
             p.sync()
         out = torch.empty((n, self.out_cols), dtype=torch.float32, device=dev)
@@ -202,7 +206,7 @@ class _Engine:
             plan.fwd = prog
         plan.fwd.run(pts=pts, out=out)
         plan.fwd.release()
-        plan.out, plan.busy = out, True
+        plan.out, plan.busy, plan.pts = out, True, (pts if want_dx else None)
         plan.epoch += 1
         return out, plan
 
@@ -211,15 +215,24 @@ class _Engine:
         dev, n = g_out.device, g_out.shape[0]
         g_out = g_out.contiguous()
         flat = torch.empty(self.grad_numel, dtype=torch.float32, device=dev)
+        dyn = dict(g=g_out, out=plan.out, grads=flat)
+        d_pts = None
+        if plan.want_dx:
+            d_pts = torch.empty((n, 3), dtype=torch.float32, device=dev)
+            dyn.update(pts=plan.pts, d_pts=d_pts)
         if plan.bwd is None:
             with linear.Program(dev) as prog:
-                prog.bind(g=g_out, out=plan.out, grads=flat)
-                self._backward(prog, plan.acts, n, x3, self._grad_views(flat))
+                prog.bind(**dyn)
+                d_enc = self._backward(prog, plan.acts, n, x3, self._grad_views(flat), plan.want_dx)
+                if plan.want_dx:
+                    levels, ld = self.pos_levels, d_enc.shape[1]
+                    prog.call(lambda: check(load().nb2_encode_backward(handle(dev), prog.inp["pts"].data_ptr(), prog.inp["pts"].stride(0), 0, n,
+                                                                       levels, d_enc.data_ptr(), ld, prog.inp["d_pts"].data_ptr(), stream_ptr(dev))))
             plan.bwd = prog
-        plan.bwd.run(g=g_out, out=plan.out, grads=flat)
+        plan.bwd.run(**dyn)
         plan.bwd.release()
         plan.busy = False      # the next forward may take the plan; until then this pass can be differentiated again
-        return self._grad_views(flat)
+        return self._grad_views(flat), d_pts
 
     def _grad_views(self, flat):
         views, off = [], 0
@@ -240,7 +253,7 @@ class ProposalEngine(_Engine):
         L = module.layers
         self.lins = [L[0], L[2], L[4], L[6], L[8]]
         self.packed = [PackedLinear(l) for l in self.lins]
-        self.levels = module.position_flevel
+        self.levels = self.pos_levels = module.position_flevel
         self._init_plans()
 
     def _forward(self, prog, n, x3, sigma):
@@ -262,7 +275,7 @@ class ProposalEngine(_Engine):
         linear.gemm(n, 1, _fwd_segs(x, (W[4].hi, W[4].lo), H, x3), bias=self.lins[4].bias.detach(), out_f32=sigma)
         return acts
 
-    def _backward(self, prog, acts, n, x3, grads):
+    def _backward(self, prog, acts, n, x3, grads, want_dx=False):
         dev = prog.dev
         W = self.packed
         H = self.lins[0].out_features
@@ -281,6 +294,12 @@ class ProposalEngine(_Engine):
                 dx = _empty16(n, H, dev, x3)
                 linear.gemm(n, H, _dgrad_segs(dy, (W[l].hi, W[l].lo), H, x3), mask=x[0], out_hi=dx[0], out_lo=dx[1])
                 dy = dx
+        if not want_dx:
+            return None
+        enc_w = _pad8(3 + 6 * self.levels)
+        d_enc = torch.empty((n, enc_w), dtype=torch.float32, device=dev)       # gradient of the encoded positions
+        linear.gemm(n, enc_w, _dgrad_segs(dy, (W[0].hi, W[0].lo), H, x3), out_f32=d_enc)
+        return d_enc
 
 
 class NerfEngine(_Engine):
@@ -294,6 +313,7 @@ class NerfEngine(_Engine):
         self.lins = [b1[0], b1[2], b1[4], b1[6], b2[0], b2[2], b2[4], module.bottle_neck[0], module.opacity_head[0],
                      module.rgb_layer[0], module.rgb_layer[2]]
         self.pl, self.dl = module.position_flevel, module.direction_flevel
+        self.pos_levels = self.pl
         self.enc = 3 + 6 * self.pl
         self.denc = 3 + 6 * self.dl
         H = self.lins[0].out_features
@@ -340,7 +360,7 @@ class NerfEngine(_Engine):
         linear.gemm(n, 3, _fwd_segs(t, wl(10), 128, x3), bias=b[10], act=linear.ACT_SIGMOID, out_f32=out[:, :3])
         return dict(E=E, h1=h1, h2=h2, h3=h3, C5=C5, h5=h5, h6=h6, h7=h7, C9=C9, t=t)
 
-    def _backward(self, prog, a, n, x3, grads):
+    def _backward(self, prog, a, n, x3, grads, want_dx=False):
         dev = prog.dev
         W = self.packed
         H = self.H
@@ -385,15 +405,23 @@ class NerfEngine(_Engine):
         d1 = _empty16(n, H, dev, x3)
         linear.gemm(n, H, _dgrad_segs(d2, wl(1), H, x3), mask=a["h1"][0], out_hi=d1[0], out_lo=d1[1])
         wg(0, d1, a["E"], H, self.enc)
+        if not want_dx:
+            return None
+        enc_w = _pad8(self.enc)                                                    # the encoding enters lin_block1.0 and the skip layer
+        d_enc = torch.empty((n, enc_w), dtype=torch.float32, device=dev)
+        linear.gemm(n, enc_w, _dgrad_segs(d1, wl(0), H, x3) + _dgrad_segs(d5, W[4].cols(H, H + enc_w), H, x3), out_f32=d_enc)
+        return d_enc
 
 
 class _MLPFunction(torch.autograd.Function):
-    """forward(engine, x3, pts, *params): params are passed so autograd routes their gradients; values come from the module."""
+    """forward(engine, x3, pts, *params): params are passed so autograd routes their gradients; values come from the module.
+    When pts requires a gradient, backward also returns d loss / d positions (RefNeRF.get_grad on the proposal network,
+    train.py:165-168)."""
 
     @staticmethod
     def forward(ctx, engine, x3, pts, *params):
-        out, plan = engine.forward(pts, x3)
-        ctx.engine, ctx.x3, ctx.plan, ctx.epoch = engine, x3, plan, plan.epoch
+        out, plan = engine.forward(pts, x3, want_dx=ctx.needs_input_grad[2])
+        ctx.engine, ctx.x3, ctx.plan, ctx.epoch, ctx.pts_cols = engine, x3, plan, plan.epoch, pts.shape[1]
         if engine.keep_last_acts:
             engine.last_acts = plan.acts
         return out
@@ -403,11 +431,15 @@ class _MLPFunction(torch.autograd.Function):
         if ctx.plan.epoch != ctx.epoch:
             raise _lib.NB2Error("the layer-wise engine keeps one set of activations per recorded plan: this network ran forward again "
                                 "at this batch size after this pass had been differentiated, so its activations are gone")
-        grads = ctx.engine.backward(ctx.plan, g, ctx.x3)
+        grads, d_pts = ctx.engine.backward(ctx.plan, g, ctx.x3)
         flat = []
         for gw, gb in grads:
             flat += [gw, gb]
-        return (None, None, None, *flat)
+        if d_pts is not None and ctx.pts_cols != 3:        # [xyz, dir] rows: no gradient is produced for the direction columns
+            full = torch.zeros((d_pts.shape[0], ctx.pts_cols), dtype=torch.float32, device=d_pts.device)
+            full[:, :3] = d_pts
+            d_pts = full
+        return (None, None, d_pts, *flat)
 
 
 def train_engine_of(module, engine_cls):

@@ -257,3 +257,45 @@ def test_launch_plans_are_reused_and_change_nothing():
     na.forward(pts[None])
     with pytest.raises(nerf_b200.NB2Error):
         out.sum().backward()
+
+
+def test_position_gradients_of_the_mip_networks():
+    """--prop_normal (train.py:165-168): coarse_samples.requires_grad = True; RefNeRF.get_grad(density, coarse_samples).
+    The proposal network's (and MipNeRF's) backward plan also produces d loss / d positions; against fp64 autograd over
+    the oracle with the engine's activation pattern, next to the parameter gradients of the same pass."""
+    from nerf_b200.train_engine import NerfEngine, ProposalEngine, train_engine_of
+    n = 3000
+    sp, sn = O.make_params("proposal", 1, "smooth"), O.make_params("nerf", 2, "smooth")
+    prop, net = load(nerf_b200.ProposalNetwork(10, 256), sp), load(nerf_b200.MipNeRF(10, 4, 256), sn)
+    en, ep = train_engine_of(net, NerfEngine), train_engine_of(prop, ProposalEngine)
+    en.keep_last_acts = ep.keep_last_acts = True
+    p3 = O.det_uniform((1, n, 3), 50, -2.0, 2.0).to(DEV).requires_grad_(True)
+    dens = prop.forward(p3)
+    normal = nerf_b200.RefNeRF.get_grad(dens, p3)                     # first backward pass of this forward ...
+    g_sig = O.det_uniform((1, n), 51, -1.0, 1.0).to(DEV)
+    (dens * g_sig).sum().backward()                                   # ... and the second
+    masks_p = [(h[0] > 0) for h in ep.last_acts[1:]]
+    sp64 = {k: v.to(DEV).double().requires_grad_(True) for k, v in sp.items()}
+    p64 = p3.detach().double().requires_grad_(True)
+    d64 = O.proposal_forward(sp64, p64[0], relu_masks=masks_p)
+    g64, = torch.autograd.grad(d64, p64, torch.ones_like(d64), retain_graph=True)
+    ref_normal = g64 / torch.maximum(torch.full_like(g64[..., :1], 1e-5), g64.norm(dim=-1, keepdim=True))
+    (d64 * g_sig[0].double()).sum().backward()
+    e_n, e_p = norm_err(normal, ref_normal), norm_err(p3.grad, p64.grad)
+    e_w = max(norm_err(p.grad, sp64[k].grad) for k, p in prop.named_parameters())
+    print("proposal network: get_grad", e_n, "d positions", e_p, "parameters", e_w)
+    assert e_n <= 1e-4 and e_p <= 1e-4 and e_w <= 1e-4
+    # MipNeRF: rows [xyz, dir]; the direction columns get zeros
+    p6 = torch.cat((O.det_uniform((n, 3), 52, -2.0, 2.0), O.det_uniform((n, 3), 53, -1.0, 1.0)), -1).to(DEV)[None].requires_grad_(True)
+    g_rgbo = O.det_uniform((1, n, 4), 54, -1.0, 1.0).to(DEV)
+    out = net.forward(p6)
+    (out * g_rgbo).sum().backward()
+    a = en.last_acts
+    masks_n = [(a[k][0][:, :256] > 0) for k in ("h1", "h2", "h3", "C5", "h5", "h6", "h7")] + [a["t"][0] > 0]
+    sn64 = {k: v.to(DEV).double().requires_grad_(True) for k, v in sn.items()}
+    x64 = p6.detach()[0, :, :3].double().requires_grad_(True)
+    o64 = O.nerf_forward(sn64, torch.cat((x64, p6.detach()[0, :, 3:].double()), -1), relu_masks=masks_n)
+    (o64 * g_rgbo[0].double()).sum().backward()
+    e_x = norm_err(p6.grad[0, :, :3], x64.grad)
+    print("MipNeRF: d positions", e_x)
+    assert e_x <= 1e-4 and float(p6.grad[0, :, 3:].abs().max()) == 0.0

@@ -224,9 +224,13 @@ def test_refnerf_training_closure_of_the_reference():
     focal = nerf_b200.fov2Focal(0.6911112070083618, (Hh, Ww))
     saved = {}
 
-    def run():
+    def run(prop_normal=False):
         coarse_samples, coarse_lengths, rgb_targets, coarse_cam_rays = nerf_b200.validSampler(rgbs, coords, cam_tf, R, Pc, focal, 2.0, 6.0, True)
-        density = F.softplus(prop.forward(coarse_samples))
+        coarse_samples.requires_grad = prop_normal
+        density = prop.forward(coarse_samples)
+        if prop_normal:
+            coarse_grad = -nerf_b200.RefNeRF.get_grad(density, coarse_samples)
+        density = F.softplus(density)
         prop_weights = maxBlurFilter(ProposalNetwork.get_weights(density, coarse_lengths, coarse_cam_rays[:, 3:]), 0.01)
         fine_lengths, below_idxs = inverseSample(prop_weights, coarse_lengths, Pf + 1, sort=True)
         fine_samples, fine_lengths, below_idxs, sort_ids = NeRF.coarseFineMerge(coarse_cam_rays, coarse_lengths, fine_lengths, below_idxs)
@@ -238,11 +242,15 @@ def test_refnerf_training_closure_of_the_reference():
         fine_rendered, weights, _ = NeRF.render(fine_rgbo, fine_lengths, coarse_cam_rays[:, 3:], rn.density_act)
         normal_loss = normal_loss_func(weights, density_grad, pred_normal)
         bf_loss = bf_loss_func(weights, pred_normal, fine_dir)
+        coarse_normal_loss = 0.
+        if prop_normal:
+            coarse_pt_fine_grad = nerf_b200.RefNeRF.coarse_grad_select(density_grad, sort_ids, Pc)
+            coarse_normal_loss = normal_loss_func(prop_weights, coarse_pt_fine_grad.detach(), coarse_grad)
         weight_bounds = getBounds(prop_weights, below_idxs)
         opt.zero_grad()
         img_loss = loss_func(fine_rendered, rgb_targets)
         prop_loss = prop_loss_func(weight_bounds, weights.detach())
-        loss = prop_loss + img_loss + 4e-4 * normal_loss + 0.1 * bf_loss
+        loss = prop_loss + img_loss + 4e-4 * (normal_loss + 0.1 * coarse_normal_loss) + 0.1 * bf_loss
         saved.update(fine_pos=fine_pos.detach(), fine_dir=fine_dir.detach(), fine_lengths=fine_lengths.detach(), rgb_targets=rgb_targets,
                      weight_bounds=weight_bounds.detach(), dgrad=density_grad, sort_ids=sort_ids)
         return loss, img_loss
@@ -274,3 +282,7 @@ def test_refnerf_training_closure_of_the_reference():
     loss2.backward()
     opt.step()
     assert bool(torch.isfinite(loss2)) and len(rn.__dict__["_nb2_ref_plans"]) == 1
+    loss3, _ = run(prop_normal=True)        # --prop_normal: the proposal network's density normals join the loss (train.py:165-168,185-187)
+    loss3.backward()
+    assert bool(torch.isfinite(loss3)) and all(bool(torch.isfinite(p.grad).all()) for p in prop.parameters())
+    opt.step()
