@@ -45,6 +45,14 @@ def golden_refnerf():
 
 
 @pytest.fixture(scope="session")
+def golden_ref_train():
+    """Training side of Ref-NeRF from the unmodified reference (tests/golden/make_golden.py round3): RefNeRF.get_grad,
+    the normal / back-face losses and every parameter gradient of one is_ref_model loss (train.py:176-199)."""
+    z = np.load(os.path.join(ROOT, "tests", "golden", "reference_outputs_ref_train.npz"))
+    return {k: torch.from_numpy(z[k]) for k in z.files}
+
+
+@pytest.fixture(scope="session")
 def golden_round2():
     """Round-2 outputs of the unmodified reference (tests/golden/make_golden.py round2): seeded multi-tile render_image,
     Ref-NeRF forward / Ref branch of render_image, one training step's losses and gradient summaries."""

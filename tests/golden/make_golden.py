@@ -368,7 +368,58 @@ def main_round2():
     print("wrote", path, os.path.getsize(path) // 1024, "KiB;", len(arrays), "arrays; torch", torch.__version__)
 
 
+# ---- round 2, late: the training side of Ref-NeRF (train.py:176-187 with is_ref_model) ----------------------------------
+def ref_train_inputs():
+    """6 rays x 24 merged samples: positions / directions of refnerf_inputs(), sorted sample depths, colour targets and a
+    sort permutation whose last 8 pre-sort positions play the coarse samples (coarse_grad_select)."""
+    g = refnerf_inputs()
+    z = torch.sort(det_uniform((6, 24), 73, 2.0, 6.0), dim=-1).values
+    sort_inds = torch.argsort(det_uniform((6, 24), 74, 0.0, 1.0), dim=-1)
+    return {"pos": g["pts"][..., :3].contiguous(), "dirs": g["pts"][..., 3:].contiguous(), "z": z, "sort_inds": sort_inds,
+            "targets": det_uniform((6, 3), 75, 0.0, 1.0)}
+
+
+def main_round3():
+    import math
+    np.math = math
+    ref = import_reference()
+    from nerf_b200.synthetic import det_state_dict
+    import nerf.addtional as addtional
+    from nerf.ref_model import BackFaceLoss, RefNeRF, WeightedNormalLoss
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    out = {}
+    ti = ref_train_inputs()
+    rn = RefNeRF(10, 4)
+    rn.load_state_dict(det_state_dict(rn, 7, gain=1.0))
+    rn.eval()                                                    # (train mode adds torch.normal noise to the bottleneck, ref_model.py:86-87)
+    fine_pos, fine_dir = ti["pos"].clone(), ti["dirs"]
+    fine_pos.requires_grad = True                                                                          # train.py:177
+    fine_rgbo, pred_normal = rn.forward(fine_pos, fine_dir)
+    density_grad = -RefNeRF.get_grad(fine_rgbo[..., -1], fine_pos)                                         # train.py:180
+    fine_rgbo[..., -1] = torch.nn.functional.softplus(fine_rgbo[..., -1] + 0.5)
+    fine_rendered, weights, _ = ref.NeRF.render(fine_rgbo, ti["z"], fine_dir[:, 0], rn.density_act)        # train.py:182 (sic: 4th positional)
+    normal_loss = WeightedNormalLoss(True)(weights, density_grad, pred_normal)
+    bf_loss = BackFaceLoss()(weights, pred_normal, fine_dir)
+    img_loss = addtional.SoftL1Loss()(fine_rendered, ti["targets"])
+    loss = img_loss + 4e-4 * normal_loss + 0.1 * bf_loss
+    loss.backward()
+    out["rt_density_grad"], out["rt_weights"], out["rt_rendered"] = density_grad.detach(), weights.detach(), fine_rendered.detach()
+    out["rt_losses"] = torch.stack((loss.detach(), img_loss.detach(), normal_loss.detach(), bf_loss.detach()))
+    out["rt_pos_grad"] = fine_pos.grad.detach()
+    out["rt_select"] = RefNeRF.coarse_grad_select(density_grad.detach(), ti["sort_inds"], 8)
+    for k, p_ in rn.named_parameters():
+        gk = p_.grad.reshape(-1)
+        out[f"rt_grad_{k}"] = torch.cat((gk.norm().reshape(1), gk.sum().reshape(1), gk[:GRAD_HEAD]))
+    arrays = {k: v.detach().cpu().numpy() for k, v in out.items()}
+    path = os.path.join(HERE, "reference_outputs_ref_train.npz")
+    np.savez_compressed(path, **arrays)
+    print("wrote", path, os.path.getsize(path) // 1024, "KiB;", len(arrays), "arrays; torch", torch.__version__)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "round3":
+        main_round3()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "refnerf":
         main_refnerf()
     elif len(sys.argv) > 1 and sys.argv[1] == "round2":

@@ -290,3 +290,47 @@ def test_refnerf_forward_and_merge_indices(golden_round2):
     zs, bs = O.inverse_sample(w, go["z"], go["u"], sort=True, torch_sum=True)
     zz, order = torch.sort(torch.cat((zs, go["z"]), dim=-1), dim=-1)
     assert float((zz[:, :-1] - g["merge_z2"]).abs().max()) < 1e-5
+
+
+def ref_train_losses(forward, ti, normal_loss_func, bf_loss_func, img_loss_func):
+    """train.py:176-199 (is_ref_model) on fixed samples; `forward(pos, dirs) -> (rgbo, normal)` with pos requiring grad."""
+    import torch.nn.functional as F
+    pos = ti["pos"].clone().requires_grad_(True)
+    rgbo, normal = forward(pos, ti["dirs"])
+    g, = torch.autograd.grad(rgbo[..., -1], pos, torch.ones_like(rgbo[..., -1]), retain_graph=True)
+    dgrad = -g / torch.maximum(torch.full_like(g[..., :1], 1e-5), g.norm(dim=-1, keepdim=True))
+    dens = F.softplus(rgbo[..., -1] + 0.5)
+    w = O.weights_from_sigma(dens, ti["z"], None)          # train.py:182 passes density_act in mul_norm's place: no ||d|| scaling, relu
+    rendered = torch.sum(w[:, :, None] * rgbo[..., :3], dim=-2)
+    nl, bf, il = normal_loss_func(w, dgrad, normal), bf_loss_func(w, normal, ti["dirs"]), img_loss_func(rendered, ti["targets"])
+    loss = il + 4e-4 * nl + 0.1 * bf
+    return dict(pos=pos, dgrad=dgrad, weights=w, rendered=rendered, losses=torch.stack((loss, il, nl, bf)), loss=loss)
+
+
+def test_refnerf_training_side_oracle_matches_reference(golden_ref_train):
+    """RefNeRF.get_grad, WeightedNormalLoss, BackFaceLoss, coarse_grad_select and the parameter / position gradients of one
+    is_ref_model loss: torch autograd over the oracle's forward against the UNMODIFIED reference (make_golden.py round3).
+    This is what pins the checker of tests/test_gpu_i_refnerf.py's gradient tests."""
+    import nerf_b200
+    from tests.golden.make_golden import GRAD_HEAD, ref_train_inputs
+    g = golden_ref_train
+    ti = ref_train_inputs()
+    rn = nerf_b200.RefNeRF(10, 4)
+    sd = {k: v.clone().requires_grad_(True) for k, v in O.det_state_dict(rn, 7, gain=1.0).items()}
+    r = ref_train_losses(lambda pos, dirs: O.refnerf_forward(sd, torch.cat((pos, dirs), -1)), ti,
+                         nerf_b200.WeightedNormalLoss(True), nerf_b200.BackFaceLoss(), nerf_b200.SoftL1Loss())
+    r["loss"].backward()
+    assert float((r["dgrad"] - g["rt_density_grad"]).abs().max()) <= 2e-4          # unit vectors; fp32 summation order
+    assert float((r["weights"] - g["rt_weights"]).abs().max()) <= 1e-5 and float((r["rendered"] - g["rt_rendered"]).abs().max()) <= 1e-5
+    assert float(((r["losses"].detach() - g["rt_losses"]).abs() / g["rt_losses"].abs().clamp_min(1e-6)).max()) <= 1e-4
+    assert float((r["pos"].grad - g["rt_pos_grad"]).norm() / g["rt_pos_grad"].norm()) <= 1e-3
+    sel = nerf_b200.RefNeRF.coarse_grad_select(g["rt_density_grad"], ti["sort_inds"], 8)
+    assert torch.equal(sel, g["rt_select"])
+    worst = 0.0
+    for k, p in sd.items():
+        ref = g[f"rt_grad_{k}"]
+        gk = p.grad.reshape(-1)
+        worst = max(worst, abs(float(gk.norm()) - float(ref[0])) / max(float(ref[0]), 1e-12),
+                    float((gk[:GRAD_HEAD] - ref[2:2 + GRAD_HEAD]).abs().max()) / max(float(ref[2:].abs().max()), 1e-12))
+    print("Ref-NeRF training side, oracle vs reference: worst gradient deviation", worst)
+    assert worst <= 2e-3
