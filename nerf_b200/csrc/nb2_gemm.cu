@@ -61,6 +61,8 @@ struct GemmKParams {
   int bn;                 // N tile (multiple of 32, <= 256)
   int m_tiles, n_tiles;
   int64_t k_per_split;    // rows of K per split (multiple of 64); splits == 1: unused
+  int fused3;             // segments come in split-precision triples (A_lo B_hi, A_hi B_lo, A_hi B_hi): tiles shared between passes
+  int dbg;                // NB2_TC_DEBUG (timing ablations only): 16 no global stores, 32 no bias loads, 128 no TMEM loads
 };
 
 // TMA: one [box rows][64 columns] box of a 2-D tensor map -> shared memory (128-byte swizzle), bytes counted on `bar`
@@ -156,30 +158,51 @@ __global__ void __launch_bounds__(kGThreads, 1) gemm_bf16_kernel(const __grid_co
         const int n_tile = (int)((it / p.m_tiles) % p.n_tiles);
         const int split = (int)(it / ((int64_t)p.m_tiles * p.n_tiles));
         const int m0 = m_tile * 128, n0 = n_tile * p.bn;
-        for (int s = 0; s < d.n_seg; ++s) {
-          const bool a_mn = d.seg[s].a.mn_major != 0, b_mn = d.seg[s].b.mn_major != 0;
+        // one ring stage: the A tile of segment sa and / or the B tile of segment sb (-1: that half of the stage stays unused)
+        auto load_stage = [&](int sa, int sb, int64_t k) {
+          const int sm = sa >= 0 ? sa : sb;
+          const bool a_mn = d.seg[sm].a.mn_major != 0, b_mn = d.seg[sm].b.mn_major != 0;
           const int b_boxes = b_mn ? (p.bn + 63) / 64 : 1;
-          const uint32_t bytes = (uint32_t)kGABytes + (uint32_t)(b_mn ? b_boxes * 8192 : p.bn * 128);
-          int64_t k0, k1;
-          k_range(s, split, k0, k1);
-          for (int64_t k = k0; k < k1; k += 64) {
-            const uint32_t stage = issued % kGStages;
-            if (issued >= kGStages) mbar_wait(smem_u32(&bars->empty[stage]), ((issued / kGStages) - 1) & 1u);
-            const uint32_t a_dst = smem_base + stage * kGStageBytes, b_dst = a_dst + kGABytes;
-            const uint32_t full = smem_u32(&bars->full[stage]);
-            mbar_arrive_expect_tx(full, bytes);
+          const uint32_t bytes = (sa >= 0 ? (uint32_t)kGABytes : 0u) + (sb >= 0 ? (uint32_t)(b_mn ? b_boxes * 8192 : p.bn * 128) : 0u);
+          const uint32_t stage = issued % kGStages;
+          if (issued >= kGStages) mbar_wait(smem_u32(&bars->empty[stage]), ((issued / kGStages) - 1) & 1u);
+          const uint32_t a_dst = smem_base + stage * kGStageBytes, b_dst = a_dst + kGABytes;
+          const uint32_t full = smem_u32(&bars->full[stage]);
+          mbar_arrive_expect_tx(full, bytes);
+          if (sa >= 0) {
             if (!a_mn) {
-              tma_load_2d(a_dst, &p.amap[s], (int)k, m0, full);                       // 128 rows (M) x 64 columns (K)
+              tma_load_2d(a_dst, &p.amap[sa], (int)k, m0, full);                      // 128 rows (M) x 64 columns (K)
             } else {
-              tma_load_2d(a_dst, &p.amap[s], m0, (int)k, full);                       // 64 rows (K) x 64 columns (M), twice
-              tma_load_2d(a_dst + 8192, &p.amap[s], m0 + 64, (int)k, full);
+              tma_load_2d(a_dst, &p.amap[sa], m0, (int)k, full);                      // 64 rows (K) x 64 columns (M), twice
+              tma_load_2d(a_dst + 8192, &p.amap[sa], m0 + 64, (int)k, full);
             }
+          }
+          if (sb >= 0) {
             if (!b_mn) {
-              tma_load_2d(b_dst, &p.bmap[s], (int)k, n0, full);                       // bn rows (N) x 64 columns (K)
+              tma_load_2d(b_dst, &p.bmap[sb], (int)k, n0, full);                      // bn rows (N) x 64 columns (K)
             } else {
-              for (int j = 0; j < b_boxes; ++j) tma_load_2d(b_dst + j * 8192, &p.bmap[s], n0 + 64 * j, (int)k, full);
+              for (int j = 0; j < b_boxes; ++j) tma_load_2d(b_dst + j * 8192, &p.bmap[sb], n0 + 64 * j, (int)k, full);
             }
-            ++issued;
+          }
+          ++issued;
+        };
+        if (p.fused3) {
+          // split-precision triples: per K chunk the four distinct tiles are loaded ONCE -- (A_lo, B_hi), then A_hi, then B_lo
+          // (96 KB instead of 144 KB for the three passes; the L2 -> shared stream is what bounds this kernel)
+          for (int t = 0; t < d.n_seg; t += 3) {
+            int64_t k0, k1;
+            k_range(t, split, k0, k1);
+            for (int64_t k = k0; k < k1; k += 64) {
+              load_stage(t, t, k);
+              load_stage(t + 2, -1, k);
+              load_stage(-1, t + 1, k);
+            }
+          }
+        } else {
+          for (int s = 0; s < d.n_seg; ++s) {
+            int64_t k0, k1;
+            k_range(s, split, k0, k1);
+            for (int64_t k = k0; k < k1; k += 64) load_stage(s, s, k);
           }
         }
       }
@@ -194,25 +217,46 @@ __global__ void __launch_bounds__(kGThreads, 1) gemm_bf16_kernel(const __grid_co
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + buf * 256;
       bool first = true;
-      for (int s = 0; s < d.n_seg; ++s) {
+      auto wait_full = [&]() {
+        const uint32_t stage = consumed % kGStages;
+        mbar_wait(smem_u32(&bars->full[stage]), (consumed / kGStages) & 1u);
+        tc_fence_after();
+        ++consumed;
+        return stage;
+      };
+      // the k-steps of one K chunk: A tile of ring stage sa against the B tile of ring stage sb
+      auto mma_chunk = [&](uint32_t sa, uint32_t sb, int ksteps, uint32_t idesc, bool a_mn, bool b_mn) {
+        const uint32_t a_s = smem_base + sa * kGStageBytes, b_s = smem_base + sb * kGStageBytes + kGABytes;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const uint64_t ad = gemm_smem_desc(a_s + (a_mn ? ks * 2048 : ks * 32), a_mn);
+          const uint64_t bd = gemm_smem_desc(b_s + (b_mn ? ks * 2048 : ks * 32), b_mn);
+          umma1_elect(tmem_d, ad, bd, idesc, first ? 0u : 1u);
+          first = false;
+        }
+      };
+      const int seg_step = p.fused3 ? 3 : 1;
+      for (int s = 0; s < d.n_seg; s += seg_step) {
         const bool a_mn = d.seg[s].a.mn_major != 0, b_mn = d.seg[s].b.mn_major != 0;
         const uint32_t idesc = gemm_idesc(p.bn, a_mn, b_mn);
         int64_t k0, k1;
         k_range(s, split, k0, k1);
         for (int64_t k = k0; k < k1; k += 64) {
-          const uint32_t stage = consumed % kGStages;
-          mbar_wait(smem_u32(&bars->full[stage]), (consumed / kGStages) & 1u);
-          tc_fence_after();
-          const uint32_t a_s = smem_base + stage * kGStageBytes, b_s = a_s + kGABytes;
           const int ksteps = (int)((k1 - k + 15) / 16 < 4 ? (k1 - k + 15) / 16 : 4);
-          for (int ks = 0; ks < ksteps; ++ks) {
-            const uint64_t ad = gemm_smem_desc(a_s + (a_mn ? ks * 2048 : ks * 32), a_mn);
-            const uint64_t bd = gemm_smem_desc(b_s + (b_mn ? ks * 2048 : ks * 32), b_mn);
-            umma1_elect(tmem_d, ad, bd, idesc, first ? 0u : 1u);
-            first = false;
+          if (!p.fused3) {
+            const uint32_t st = wait_full();
+            mma_chunk(st, st, ksteps, idesc, a_mn, b_mn);
+            umma1_commit_elect(smem_u32(&bars->empty[st]));
+          } else {
+            const uint32_t st0 = wait_full();                 // (A_lo, B_hi)
+            mma_chunk(st0, st0, ksteps, idesc, a_mn, b_mn);   // lo x hi
+            const uint32_t st1 = wait_full();                 // A_hi
+            mma_chunk(st1, st0, ksteps, idesc, a_mn, b_mn);   // hi x hi
+            umma1_commit_elect(smem_u32(&bars->empty[st0]));
+            const uint32_t st2 = wait_full();                 // B_lo
+            mma_chunk(st1, st2, ksteps, idesc, a_mn, b_mn);   // hi x lo
+            umma1_commit_elect(smem_u32(&bars->empty[st1]));
+            umma1_commit_elect(smem_u32(&bars->empty[st2]));
           }
-          umma1_commit_elect(smem_u32(&bars->empty[stage]));
-          ++consumed;
         }
       }
       umma1_commit_elect(smem_u32(&bars->acc_full[buf]));
@@ -288,9 +332,14 @@ __global__ void __launch_bounds__(kGThreads, 1) gemm_bf16_kernel(const __grid_co
         }
         uint32_t ra[32], rb[32];
         uint32_t lo_keep[2][16];                              // lo residuals wait in registers while the hi rows use the staging tile
-        tmem_ld32(lane_addr + buf * 256 + cb * 32, ra);
-        if (nb == 2) tmem_ld32(lane_addr + buf * 256 + cb * 32 + 32, rb);
-        tmem_ld_wait();
+        if (!(p.dbg & 128)) {
+          tmem_ld32(lane_addr + buf * 256 + cb * 32, ra);
+          if (nb == 2) tmem_ld32(lane_addr + buf * 256 + cb * 32 + 32, rb);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { ra[j] = 0x3f800000u + j; rb[j] = 0x3f800000u + j; }
+        }
 #pragma unroll
         for (int hb = 0; hb < 2; ++hb) {
           if (hb >= nb) break;
@@ -301,7 +350,7 @@ __global__ void __launch_bounds__(kGThreads, 1) gemm_bf16_kernel(const __grid_co
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = empty_k ? 0.f : __uint_as_float(hb ? rb[j] : ra[j]);
-          if (d.bias != nullptr) {
+          if (d.bias != nullptr && !(p.dbg & 32)) {
             if (nv == 32 && (reinterpret_cast<uintptr_t>(d.bias) & 15) == 0) {
               const float4* b4 = reinterpret_cast<const float4*>(d.bias + cc);
 #pragma unroll
@@ -401,7 +450,7 @@ __global__ void __launch_bounds__(kGThreads, 1) gemm_bf16_kernel(const __grid_co
               if (grow < d.M && gcol < d.N) {
                 uint4 x;
                 asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x.x), "=r"(x.y), "=r"(x.z), "=r"(x.w) : "r"(stg + sw(r, ch)));
-                *reinterpret_cast<uint4*>(dst + grow * d.ld_16 + gcol) = x;
+                if (!(p.dbg & 16)) *reinterpret_cast<uint4*>(dst + grow * d.ld_16 + gcol) = x;
               }
             }
             __syncwarp();
@@ -587,6 +636,21 @@ extern "C" int nb2_gemm_bf16(nb2_handle* h, const nb2_gemm_desc* d, void* stream
   p.m_tiles = (int)((d->M + 127) / 128);
   p.k_per_split = 0;
   if (splits > 1) p.k_per_split = ((d->seg[0].K + splits - 1) / splits + 63) / 64 * 64;
+  // split-precision triples (A_lo B_hi, A_hi B_lo, A_hi B_hi over the same K): the kernel loads the four tiles of a K chunk once
+  // Only for the weight-gradient shape (A = dY^T, MN-major): there the kernel is bound by the L2 -> shared stream.  The forward
+  // and dgrad shapes are bound by their epilogue (measured: no gain), and keep the more accurate order of additions -- all
+  // cross terms of the layer first, then hi x hi -- which sharing tiles per K chunk would interleave.
+  p.fused3 = (d->n_seg % 3 == 0 && d->seg[0].a.mn_major) ? 1 : 0;
+  for (int t = 0; p.fused3 && t < d->n_seg; t += 3) {
+    const nb2_gemm_operand &a0 = d->seg[t].a, &a1 = d->seg[t + 1].a, &a2 = d->seg[t + 2].a;
+    const nb2_gemm_operand &b0 = d->seg[t].b, &b1 = d->seg[t + 1].b, &b2 = d->seg[t + 2].b;
+    const bool same = d->seg[t].K == d->seg[t + 1].K && d->seg[t].K == d->seg[t + 2].K && a1.ptr == a2.ptr && a1.ld == a2.ld && b0.ptr == b2.ptr &&
+                      b0.ld == b2.ld && a0.ld == a1.ld && b0.ld == b1.ld && a0.mn_major == a1.mn_major && a1.mn_major == a2.mn_major &&
+                      b0.mn_major == b1.mn_major && b1.mn_major == b2.mn_major;
+    if (!same) p.fused3 = 0;
+  }
+  if (h->tc_debug & 8) p.fused3 = 0;      // NB2_TC_DEBUG & 8 (A/B timing): every pass loads its own tiles
+  p.dbg = h->tc_debug;
   int rc = kernel_set_smem(h, (const void*)gemm_bf16_kernel, kGSmem);
   if (rc != NB2_OK) return rc;
   for (int s = 0; s < d->n_seg; ++s) {
