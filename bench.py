@@ -359,7 +359,8 @@ def config4_leg(dev, prop, steps=5):
         flop = Hh * Ww * (FLOP_PROP_PER_RAY + 192 * 2143232)
         out[f"rays_{Hh * Ww}"] = {"rays_per_s": Hh * Ww / (ms * 1e-3), "ms_per_step": ms, "host_ms_per_step": 1e3 * (time.perf_counter() - t0) / steps,
                                   "tensor_tflops": flop / (ms * 1e-3) / 1e12}
-    out["train_512"] = refnerf_train_leg(dev, rn, prop)
+    with torch.enable_grad():      # the caller renders under no_grad
+        out["train_512"] = refnerf_train_leg(dev, rn, prop)
     return out
 
 
@@ -733,12 +734,20 @@ def main():
     }
 
     if not args.no_extras and world == 1:
-        with torch.no_grad():
-            line["parity_vs_oracle"] = parity_leg(dev, scene.pose, H, Wd, scene.focal, base_z, ids, list(dict.fromkeys([args.precision, "bf16", "fp16"])))
-        line["torch_cuda_baseline"] = torch_cuda_baseline(dev, 400, 400)
-        line["train_step"] = train_step_leg(dev)
-        with torch.no_grad():
-            line["other_configs"] = {"config3_ipe": config3_leg(dev, prop, net, ids), "config4_refnerf": config4_leg(dev, prop)}
+        def leg(name, fn, *a, grad=False):       # an extra leg that fails must not take the headline line with it
+            try:
+                with torch.set_grad_enabled(grad):
+                    return fn(*a)
+            except Exception as e:               # noqa: BLE001 -- reported in the line, rank 0 stderr has the traceback
+                import traceback
+                traceback.print_exc()
+                return {"error": f"{name}: {type(e).__name__}: {e}"}
+        line["parity_vs_oracle"] = leg("parity", parity_leg, dev, scene.pose, H, Wd, scene.focal, base_z, ids,
+                                       list(dict.fromkeys([args.precision, "bf16", "fp16"])))
+        line["torch_cuda_baseline"] = leg("torch_cuda_baseline", torch_cuda_baseline, dev, 400, 400, grad=True)
+        line["train_step"] = leg("train_step", train_step_leg, dev, grad=True)
+        line["other_configs"] = {"config3_ipe": leg("config3", config3_leg, dev, prop, net, ids),
+                                 "config4_refnerf": leg("config4", config4_leg, dev, prop)}
         cores = os.cpu_count() or 1
         cpu_v, cpu_t = cpu_reference_render(2, 1, cores)
         line["cpu_baseline"] = {"value": cpu_v, "unit": "rays/s", "cores": cores, "kind": "port",
