@@ -132,6 +132,38 @@ __global__ void __launch_bounds__(256) posenc_kernel(const float* __restrict__ x
   }
 }
 
+// dims == 3 (positions, directions): one thread per (point, component) runs down the levels with the exact doubling
+// v <- 2 v (= x * 2^l bit for bit), so a block's input is 384 consecutive floats and there is no per-element index
+// arithmetic; the generic kernel above spends ~4x the sin/cos cost on runtime divisions (0.29 of the copy bandwidth).
+constexpr int kPe3Pts = 128;
+__global__ void __launch_bounds__(3 * kPe3Pts) posenc3_kernel(const float* __restrict__ x, int64_t n, int levels, float* __restrict__ out) {
+  extern __shared__ float pe_tile[];  // [kPe3Pts][6 * levels]
+  const int width = 6 * levels;
+  const int64_t p0 = (int64_t)blockIdx.x * kPe3Pts;
+  const int npts = (int)min((int64_t)kPe3Pts, n - p0);
+  const int t = threadIdx.x;
+  if (t < 3 * npts) {
+    const int p = t / 3, c = t - 3 * p;
+    float v = __ldg(x + p0 * 3 + t);
+    float* row = pe_tile + p * width + c;
+    for (int l = 0; l < levels; ++l) {
+      float sn, cs;
+      sincos_any(v, sn, cs);
+      row[6 * l] = sn;
+      row[6 * l + 3] = cs;
+      v = __fmul_rn(v, 2.f);
+    }
+  }
+  __syncthreads();
+  float* dst = out + p0 * width;
+  const int total = npts * width;
+  if ((total & 3) == 0 && ((((uintptr_t)dst) & 15) == 0)) {
+    for (int q = t; q < total / 4; q += 3 * kPe3Pts) reinterpret_cast<float4*>(dst)[q] = reinterpret_cast<const float4*>(pe_tile)[q];
+  } else {
+    for (int q = t; q < total; q += 3 * kPe3Pts) dst[q] = pe_tile[q];
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // a14  integrated positional encoding              /root/reference/nerf/mip_methods.py:15-58
 // ------------------------------------------------------------------------------------------
@@ -180,22 +212,29 @@ ipe_kernel(const float* __restrict__ zvals, const float* __restrict__ rays, int6
       float dd = d * d;
       float diag = sigma_t2 * dd + sigma_r2 * (1.f - dd / gnorm);
       if (mu_out) mu_out[i * 3 + k] = mu;
+      float scale = 1.f;
       for (int l = 0; l < L; ++l) {                   // multFreq + ipe_feature (mip_methods.py:36-58)
-        float scale = exp2f((float)l);
-        float damp = expf(-0.5f * (scale * scale * diag));
+        // ex2.approx (2 ulp) behind one rounded multiply: relative error <= 2e-7 (1 + |x|), absolute <= 3e-7 on a factor in (0, 1]
+        // (a negative variance -- the reference's batch-global norm allows it -- takes the library path)
+        const float ex = -0.5f * (scale * scale * diag);
+        float damp = ex <= 0.f ? __expf(ex) : expf(ex);
         float s, co;
         sincos_any(scale * mu, s, co);
         f[6 * l + k] = s * damp;
         f[6 * l + 3 + k] = co * damp;
+        scale *= 2.f;
       }
     }
   }
   __syncthreads();
   const int ncones = (int)min((int64_t)kIpeBlock, total - i0);
+  // one warp per cone row (6 L contiguous floats; the rows of a block are contiguous too): no index division per element
   float* dst = feat + i0 * width;
-  for (int t = threadIdx.x; t < ncones * width; t += kIpeBlock) {
-    const int cn = t / width, j = t - cn * width;
-    dst[t] = ipe_tile[cn * pitch + j];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int cn = warp; cn < ncones; cn += kIpeBlock / 32) {
+    const float* src = ipe_tile + cn * pitch;
+    float* row = dst + (size_t)cn * width;
+    for (int j = lane; j < width; j += 32) row[j] = src[j];
   }
 }
 
@@ -205,11 +244,79 @@ ipe_kernel(const float* __restrict__ zvals, const float* __restrict__ rays, int6
 constexpr int kMaxSamples = 256;  // per-ray sample count supported by the warp kernels
 constexpr int kWarpsPerBlock = 8;
 
+// ---- register form: a group of `lpr` lanes (a power of two) owns one ray and every lane 4 * S4 CONSECUTIVE samples --------
+// One 16-byte load per four samples, the products of a lane's own samples taken serially, ONE log2(lpr)-step scan across the
+// group instead of one 5-step scan per 32 samples, no shared memory.  At 64 samples a warp carries two rays, at 32 four.
+// (The warp-per-ray kernels above stay as the fallback for sample counts that are not a multiple of four / unaligned rows.)
+template <int S4>
+__device__ __forceinline__ void ray_weights_regs(const float (&dep)[4 * S4], const float (&sig)[4 * S4], int s0, int P, int act,
+                                                 int lpr, int sub, float (&w)[4 * S4]) {
+  constexpr int S = 4 * S4;
+  const float nxt = __shfl_down_sync(0xffffffffu, dep[0], 1, lpr);   // the next lane's first depth (unused by a ray's last sample)
+  float alpha[S], pre[S];                                            // pre[j] = product of this lane's factors 0..j
+#pragma unroll
+  for (int j = 0; j < S; ++j) {
+    const int i = s0 + j;
+    float m = 1.f, f = 1.f;
+    alpha[j] = 0.f;
+    if (i < P) {
+      const float dn = (j + 1 < S) ? dep[(j + 1) % S] : nxt;
+      const float delta = (i + 1 < P) ? __fsub_rn(dn, dep[j]) : 1e10f;
+      m = expf(-apply_density_act(sig[j], act) * delta);
+      alpha[j] = 1.f - m;
+      f = m + 1e-10f;
+    }
+    pre[j] = (j == 0) ? f : pre[(j + S - 1) % S] * f;
+  }
+  float inc = pre[S - 1];
+  for (int d = 1; d < lpr; d <<= 1) {
+    const float o = __shfl_up_sync(0xffffffffu, inc, d, lpr);
+    if (sub >= d) inc *= o;
+  }
+  float exc = __shfl_up_sync(0xffffffffu, inc, 1, lpr);
+  if (sub == 0) exc = 1.f;
+#pragma unroll
+  for (int j = 0; j < S; ++j) w[j] = alpha[j] * (j == 0 ? exc : exc * pre[(j + S - 1) % S]);
+}
+
 // weights w_i = (1 - m_i) * prod_{j<i} (m_j + 1e-10), m_i = exp(-act(sigma_i) * delta_i),
 // delta_i = depth_{i+1} - depth_i (last = 1e10), depth = z * ||d||   (nerf_base.py:79-86)
 // sh_z holds the (already scaled) depths, sh_s the densities; weights are written to sh_w.
 __device__ __forceinline__ void ray_weights_warp(const float* sh_depth, const float* sh_sigma,
                                                  float* sh_w, int P, int act, int lane) {
+  if ((P & 3) == 0) {
+    // the register form's association order (serial inside groups of 4 * S4 consecutive samples, one scan across the groups),
+    // so that the fused resample kernel, the standalone kernels and their fallbacks produce the same bits
+    const int s4 = P <= 128 ? 1 : 2;
+    const int need = (P + 4 * s4 - 1) / (4 * s4);
+    int lpr = 1;
+    while (lpr < need) lpr <<= 1;
+    const int sub = lane & (lpr - 1), s0 = sub * 4 * s4;      // lanes >= lpr repeat the work of lane - lpr and write nothing
+    if (s4 == 1) {
+      float dep[4], sig[4], w[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { dep[j] = s0 + j < P ? sh_depth[s0 + j] : 0.f; sig[j] = s0 + j < P ? sh_sigma[s0 + j] : 0.f; }
+      ray_weights_regs<1>(dep, sig, s0, P, act, lpr, sub, w);
+      __syncwarp();                                             // sh_w may alias an input row
+      if (lane < lpr && s0 < P) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) sh_w[s0 + j] = w[j];
+      }
+    } else {
+      float dep[8], sig[8], w[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { dep[j] = s0 + j < P ? sh_depth[s0 + j] : 0.f; sig[j] = s0 + j < P ? sh_sigma[s0 + j] : 0.f; }
+      ray_weights_regs<2>(dep, sig, s0, P, act, lpr, sub, w);
+      __syncwarp();
+      if (lane < lpr) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (s0 + j < P) sh_w[s0 + j] = w[j];
+      }
+    }
+    __syncwarp();
+    return;
+  }
   float carry = 1.f;
   for (int base = 0; base < P; base += 32) {
     int i = base + lane;
@@ -268,6 +375,48 @@ weights_kernel(const float* __restrict__ sigma, const float* __restrict__ z, con
     for (int i = lane; i < P; i += 32) w_out[r * P + i] = sh[warp][2][i];
     __syncwarp();
   }
+}
+
+// lanes per ray for the register kernels: the power of two >= ceil(P / (4 * S4)); S4 = 1 up to 128 samples, 2 up to 256
+static inline void regs_geometry(int P, int& s4, int& lpr) {
+  s4 = P <= 128 ? 1 : 2;
+  const int need = (P + 4 * s4 - 1) / (4 * s4);
+  lpr = 1;
+  while (lpr < need) lpr <<= 1;
+}
+static inline bool aligned16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
+
+template <int S4>
+__global__ void __launch_bounds__(256)
+weights_regs_kernel(const float* __restrict__ sigma, const float* __restrict__ z, const float* __restrict__ dirs, int dir_stride,
+                    int64_t n_rays, int P, int act, int lpr, float* __restrict__ w_out) {
+  constexpr int S = 4 * S4;
+  const int lane = threadIdx.x & 31, sub = lane & (lpr - 1);
+  const int64_t warp_id = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t r = warp_id * (32 / lpr) + lane / lpr;
+  const int s0 = sub * S;
+  const bool rv = r < n_rays;
+  float dep[S], sig[S], w[S];
+#pragma unroll
+  for (int g = 0; g < S4; ++g) {
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    if (rv && s0 + 4 * g < P) {
+      a = __ldg(reinterpret_cast<const float4*>(z + r * P + s0 + 4 * g));
+      b = __ldg(reinterpret_cast<const float4*>(sigma + r * P + s0 + 4 * g));
+    }
+    dep[4 * g] = a.x; dep[4 * g + 1] = a.y; dep[4 * g + 2] = a.z; dep[4 * g + 3] = a.w;
+    sig[4 * g] = b.x; sig[4 * g + 1] = b.y; sig[4 * g + 2] = b.z; sig[4 * g + 3] = b.w;
+  }
+  if (dirs && rv) {
+    const float nrm = dir_norm(dirs + r * dir_stride);
+#pragma unroll
+    for (int j = 0; j < S; ++j) dep[j] = __fmul_rn(dep[j], nrm);
+  }
+  ray_weights_regs<S4>(dep, sig, s0, P, act, lpr, sub, w);
+#pragma unroll
+  for (int g = 0; g < S4; ++g)
+    if (rv && s0 + 4 * g < P)
+      *reinterpret_cast<float4*>(w_out + r * P + s0 + 4 * g) = make_float4(w[4 * g], w[4 * g + 1], w[4 * g + 2], w[4 * g + 3]);
 }
 
 // a8  maxBlurFilter                                  /root/reference/nerf/mip_methods.py:61-66
@@ -573,30 +722,45 @@ __global__ void length2pts_kernel(const float* __restrict__ rays, const float* _
   }
 }
 
-// vectorised: four samples per thread (P % 4 == 0): a float4 of depths in, six float4 (4 x [point, direction]) out.
-// (A flat one-float4-per-thread form with fully contiguous stores measured SLOWER, 292 vs 137 us: the 64-bit index
-// divisions per output element cost more than the 96-byte thread stride of the stores.)
-__global__ void length2pts_vec4_kernel(const float* __restrict__ rays, const float* __restrict__ z, int64_t n_rays, int P,
-                                       float* __restrict__ pts) {
+// vectorised: four samples per thread (P % 4 == 0): a float4 of depths in, six float4 (4 x [point, direction]) out.  A warp's
+// 32 x 96 output bytes are contiguous in global memory, so they are transposed through a 3 KB shared-memory slab and written
+// as six fully coalesced 512-byte rows (direct stores at the 96-byte thread stride half-fill every 32-byte sector per
+// instruction: 0.64 of the copy bandwidth).  (A flat one-float4-per-thread form measured SLOWER, 292 vs 137 us: 64-bit index
+// divisions per output element.)
+__global__ void __launch_bounds__(256) length2pts_vec4_kernel(const float* __restrict__ rays, const float* __restrict__ z, int64_t n_rays,
+                                                              int P, float* __restrict__ pts) {
+  __shared__ float4 slab[8][6 * 32];
   const int P4 = P >> 2;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t total = n_rays * P4;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_rays * P4) return;
-  const int64_t r = i / P4;
-  const float* ray = rays + r * 6;
-  const float o[3] = {__ldg(ray), __ldg(ray + 1), __ldg(ray + 2)}, d[3] = {__ldg(ray + 3), __ldg(ray + 4), __ldg(ray + 5)};
-  const float4 zv = __ldg(reinterpret_cast<const float4*>(z) + i);
-  const float zz[4] = {zv.x, zv.y, zv.z, zv.w};
-  float v[24];
+  const int64_t i_warp = i - lane;
+  if (i_warp >= total) return;                 // whole warps only: the slab hand-over below is warp-synchronous
+  if (i < total) {
+    const int64_t r = i / P4;
+    const float* ray = rays + r * 6;
+    const float o[3] = {__ldg(ray), __ldg(ray + 1), __ldg(ray + 2)}, d[3] = {__ldg(ray + 3), __ldg(ray + 4), __ldg(ray + 5)};
+    const float4 zv = __ldg(reinterpret_cast<const float4*>(z) + i);
+    const float zz[4] = {zv.x, zv.y, zv.z, zv.w};
+    float v[24];
 #pragma unroll
-  for (int k = 0; k < 4; ++k)
+    for (int k = 0; k < 4; ++k)
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      v[6 * k + c] = __fadd_rn(o[c], __fmul_rn(d[c], zz[k]));
-      v[6 * k + 3 + c] = d[c];
-    }
-  float4* dst = reinterpret_cast<float4*>(pts) + i * 6;
+      for (int c = 0; c < 3; ++c) {
+        v[6 * k + c] = __fadd_rn(o[c], __fmul_rn(d[c], zz[k]));
+        v[6 * k + 3 + c] = d[c];
+      }
 #pragma unroll
-  for (int k = 0; k < 6; ++k) dst[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+    for (int k = 0; k < 6; ++k) slab[warp][lane * 6 + k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+  }
+  __syncwarp();
+  const int n_valid = (int)min((int64_t)32, total - i_warp) * 6;      // float4s this warp owns
+  float4* dst = reinterpret_cast<float4*>(pts) + i_warp * 6;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    const int q = k * 32 + lane;
+    if (q < n_valid) dst[q] = slab[warp][q];
+  }
 }
 
 // a13  NeRF.coarseFineMerge                          /root/reference/nerf/nerf_base.py:58-73
@@ -687,6 +851,80 @@ composite_kernel(const float* __restrict__ rgbo, const float* __restrict__ z, co
     rgb_out[r * 3 + 1] = cg;
     rgb_out[r * 3 + 2] = cb;
     if (depth_out) depth_out[r] = (dep - near_t) / (far_t - near_t);
+    if (acc_out) acc_out[r] = acc;
+  }
+}
+
+// register form (ray_weights_regs): the lane's 4 * S4 [r,g,b,sigma] samples are 16 * S4 * 4 contiguous bytes, read once
+template <int S4>
+__global__ void __launch_bounds__(256)
+composite_regs_kernel(const float* __restrict__ rgbo, const float* __restrict__ z, const float* __restrict__ dirs, int dir_stride,
+                      int64_t n_rays, int P, int flags, float near_t, float far_t, int lpr, float* __restrict__ rgb_out,
+                      float* __restrict__ w_out, float* __restrict__ depth_out, float* __restrict__ acc_out,
+                      const float* __restrict__ aux, float* __restrict__ aux_out) {
+  constexpr int S = 4 * S4;
+  const int lane = threadIdx.x & 31, sub = lane & (lpr - 1);
+  const int64_t warp_id = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t r = warp_id * (32 / lpr) + lane / lpr;
+  const int s0 = sub * S;
+  const bool rv = r < n_rays;
+  float dep[S], sig[S], w[S], cr_[S], cg_[S], cb_[S], ax_[S];
+  const float4* c4 = reinterpret_cast<const float4*>(rgbo) + r * P;
+#pragma unroll
+  for (int g = 0; g < S4; ++g) {
+    const bool v = rv && s0 + 4 * g < P;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), x = a;
+    if (v) a = __ldg(reinterpret_cast<const float4*>(z + r * P + s0 + 4 * g));
+    if (v && aux) x = __ldg(reinterpret_cast<const float4*>(aux + r * P + s0 + 4 * g));
+    dep[4 * g] = a.x; dep[4 * g + 1] = a.y; dep[4 * g + 2] = a.z; dep[4 * g + 3] = a.w;
+    ax_[4 * g] = x.x; ax_[4 * g + 1] = x.y; ax_[4 * g + 2] = x.z; ax_[4 * g + 3] = x.w;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (v) c = __ldg(c4 + s0 + 4 * g + k);
+      cr_[4 * g + k] = c.x; cg_[4 * g + k] = c.y; cb_[4 * g + k] = c.z; sig[4 * g + k] = c.w;
+    }
+  }
+  if (rv) {
+    const float nrm = dir_norm(dirs + r * dir_stride);
+#pragma unroll
+    for (int j = 0; j < S; ++j) dep[j] = __fmul_rn(dep[j], nrm);
+  }
+  ray_weights_regs<S4>(dep, sig, s0, P, 0, lpr, sub, w);
+  float cr = 0.f, cg = 0.f, cb = 0.f, acc = 0.f, dp = 0.f, ax = 0.f;
+#pragma unroll
+  for (int j = 0; j < S; ++j) {
+    cr = fmaf(w[j], cr_[j], cr);
+    cg = fmaf(w[j], cg_[j], cg);
+    cb = fmaf(w[j], cb_[j], cb);
+    acc += w[j];
+    dp = fmaf(w[j], dep[j], dp);
+    ax = fmaf(w[j], ax_[j], ax);
+  }
+  if (w_out) {
+#pragma unroll
+    for (int g = 0; g < S4; ++g)
+      if (rv && s0 + 4 * g < P)
+        *reinterpret_cast<float4*>(w_out + r * P + s0 + 4 * g) = make_float4(w[4 * g], w[4 * g + 1], w[4 * g + 2], w[4 * g + 3]);
+  }
+  for (int d = lpr >> 1; d > 0; d >>= 1) {
+    cr += __shfl_xor_sync(0xffffffffu, cr, d);
+    cg += __shfl_xor_sync(0xffffffffu, cg, d);
+    cb += __shfl_xor_sync(0xffffffffu, cb, d);
+    acc += __shfl_xor_sync(0xffffffffu, acc, d);
+    dp += __shfl_xor_sync(0xffffffffu, dp, d);
+    if (aux) ax += __shfl_xor_sync(0xffffffffu, ax, d);
+  }
+  if (rv && sub == 0) {
+    if (aux_out) aux_out[r] = ax;
+    if (flags & NB2_WHITE_BKG) {
+      const float bg = 1.f - acc;
+      cr += bg; cg += bg; cb += bg;
+    }
+    rgb_out[r * 3 + 0] = cr;
+    rgb_out[r * 3 + 1] = cg;
+    rgb_out[r * 3 + 2] = cb;
+    if (depth_out) depth_out[r] = (dp - near_t) / (far_t - near_t);
     if (acc_out) acc_out[r] = acc;
   }
 }
@@ -902,7 +1140,13 @@ extern "C" int nb2_posenc(nb2_handle* h, const float* x, int64_t n, int dims, in
     const int rc = kernel_set_smem(h, (const void*)posenc_kernel, 128 * 1024);
     if (rc != NB2_OK) return rc;
   }
-  posenc_kernel<<<grid_for(n, kPeBlockPts), 256, smem, (cudaStream_t)stream>>>(x, n, dims, levels, out);
+  if (dims == 3) {
+    const int rc = kernel_set_smem(h, (const void*)posenc3_kernel, 128 * 1024);
+    if (rc != NB2_OK) return rc;
+    posenc3_kernel<<<grid_for(n, kPe3Pts), 3 * kPe3Pts, (size_t)kPe3Pts * 6 * levels * sizeof(float), (cudaStream_t)stream>>>(x, n, levels, out);
+  } else {
+    posenc_kernel<<<grid_for(n, kPeBlockPts), 256, smem, (cudaStream_t)stream>>>(x, n, dims, levels, out);
+  }
   NB2_LAUNCH_CHECK(h);
   return NB2_OK;
 }
@@ -939,7 +1183,15 @@ extern "C" int nb2_weights_from_sigma(nb2_handle* h, const float* sigma, const f
   NB2_CHECK_ARG(!dirs || dir_stride >= 3, "weights_from_sigma: dir_stride < 3");
   NB2_CHECK_ARG(act >= 0 && act <= 2, "weights_from_sigma: unknown activation %d", act);
   if (n_rays == 0) return NB2_OK;
-  {
+  if ((n_samples & 3) == 0 && aligned16(sigma) && aligned16(z) && aligned16(weights_out)) {
+    int s4, lpr;
+    regs_geometry(n_samples, s4, lpr);
+    const int grid = grid_for(grid_for(n_rays, 32 / lpr), 8);
+    if (s4 == 1)
+      weights_regs_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(sigma, z, dirs, dir_stride, n_rays, n_samples, act, lpr, weights_out);
+    else
+      weights_regs_kernel<2><<<grid, 256, 0, (cudaStream_t)stream>>>(sigma, z, dirs, dir_stride, n_rays, n_samples, act, lpr, weights_out);
+  } else {
     const int64_t blocks = grid_for(n_rays, kWarpsPerBlock);
     const int grid = (int)std::min<int64_t>(blocks, (int64_t)h->sm_count * 8);     // 64 resident warps per SM, each looping over rays
     weights_kernel<<<grid, 32 * kWarpsPerBlock, 0, (cudaStream_t)stream>>>(sigma, z, dirs, dir_stride, n_rays, n_samples, act, weights_out);
@@ -1065,8 +1317,20 @@ extern "C" int nb2_coarse_fine_merge_inds(nb2_handle* h, const float* rays, cons
 static int launch_composite(nb2_handle* h, const float* rgbo, const float* z, const float* dirs, int dir_stride, int64_t n_rays, int n_samples,
                             int flags, float near_t, float far_t, float* rgb_out, float* weights_out, float* depth_out, float* acc_out,
                             const float* aux, float* aux_out, cudaStream_t st) {
-  composite_kernel<<<grid_for(n_rays, kWarpsPerBlock), 32 * kWarpsPerBlock, 0, st>>>(
-      rgbo, z, dirs, dir_stride, n_rays, n_samples, flags, near_t, far_t, rgb_out, weights_out, depth_out, acc_out, aux, aux_out);
+  if ((n_samples & 3) == 0 && aligned16(rgbo) && aligned16(z) && (!weights_out || aligned16(weights_out)) && (!aux || aligned16(aux))) {
+    int s4, lpr;
+    regs_geometry(n_samples, s4, lpr);
+    const int grid = grid_for(grid_for(n_rays, 32 / lpr), 8);
+    if (s4 == 1)
+      composite_regs_kernel<1><<<grid, 256, 0, st>>>(rgbo, z, dirs, dir_stride, n_rays, n_samples, flags, near_t, far_t, lpr, rgb_out, weights_out,
+                                                     depth_out, acc_out, aux, aux_out);
+    else
+      composite_regs_kernel<2><<<grid, 256, 0, st>>>(rgbo, z, dirs, dir_stride, n_rays, n_samples, flags, near_t, far_t, lpr, rgb_out, weights_out,
+                                                     depth_out, acc_out, aux, aux_out);
+  } else {
+    composite_kernel<<<grid_for(n_rays, kWarpsPerBlock), 32 * kWarpsPerBlock, 0, st>>>(
+        rgbo, z, dirs, dir_stride, n_rays, n_samples, flags, near_t, far_t, rgb_out, weights_out, depth_out, acc_out, aux, aux_out);
+  }
   NB2_LAUNCH_CHECK(h);
   return NB2_OK;
 }

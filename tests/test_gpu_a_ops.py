@@ -191,6 +191,58 @@ def test_composite(golden, gin):
     assert maxerr(a, ref["rgb"]) < 3e-5   # vs torch's own CUDA exp / cumprod scan order
 
 
+@pytest.mark.parametrize("P", [4, 8, 32, 50, 63, 64, 100, 128, 132, 192, 256])
+def test_scan_kernels_across_sample_counts(P):
+    """get_weights / render at every lane geometry of the register kernels (4..256 samples: 1..32 lanes per ray, one or two
+    float4 groups per lane, partially filled groups) and through the warp-per-ray fallback (sample counts that are not a
+    multiple of four; rows that are not 16-byte aligned), against the fp64 evaluation of the reference's formulas
+    (nerf_base.py:79-113) on a ragged ray count."""
+    R = 1237
+    g = torch.Generator().manual_seed(P)
+    z = torch.sort(torch.rand(R, P, generator=g) * 4 + 2, dim=-1)[0].to(DEV)
+    sig = (torch.randn(R, P, generator=g) * 8).to(DEV)
+    d = torch.randn(R, 3, generator=g).to(DEV)
+    rgbo = torch.rand(R, P, 4, generator=g).to(DEV)
+    rgbo[..., 3] = sig
+    aux = torch.rand(R, P, generator=g).to(DEV)
+    ref_w = O.weights_from_sigma(sig.double(), z.double(), d.double())
+    ref = O.composite(rgbo.double(), z.double(), d.double(), white_bkg=True, near_far=(2.0, 6.0))
+    w = ops.weights_from_sigma(sig, z, d)
+    assert maxerr(w, ref_w.float()) < 2e-6
+    rgb, cw, depth, acc, ax = ops.composite(rgbo, z, d, white_bkg=True, near_far=(2.0, 6.0), aux=aux)
+    assert maxerr(cw, ref["weights"].float()) < 2e-6 and maxerr(rgb, ref["rgb"].float()) < 3e-6
+    assert maxerr(acc, ref["acc"].float()) < 3e-6 and maxerr(depth, ref["depth"].float()) < 1e-5
+    assert maxerr(ax, (ref["weights"] * aux.double()).sum(-1).float()) < 3e-6
+    # the same rows at a 4-byte offset take the warp-per-ray kernels: both forms agree to the scan-order ulps
+    def shifted(t):
+        buf = torch.empty(t.numel() + 1, dtype=torch.float32, device=DEV)
+        v = buf[1:].view(t.shape)
+        v.copy_(t)
+        assert v.data_ptr() % 16 != 0 and v.is_contiguous()
+        return v
+    w2 = ops.weights_from_sigma(shifted(sig), shifted(z), d)
+    assert maxerr(w2, w) < 1e-6
+    rgb2, cw2, depth2, acc2 = ops.composite(shifted(rgbo), shifted(z), d, white_bkg=True, near_far=(2.0, 6.0))
+    assert maxerr(rgb2, rgb) < 2e-6 and maxerr(cw2, cw) < 1e-6 and maxerr(depth2, depth) < 1e-5
+
+
+def test_posenc_and_length2pts_ragged_sizes():
+    """The dims == 3 encoder and the slab-staged length2pts on point / ray counts that end inside a block and inside a warp."""
+    for n in (1, 127, 128, 129, 1000, 4099):
+        x = (torch.rand(n, 3, device=DEV) - 0.5) * 8
+        for L in (4, 10):
+            got = ops.posenc(x, L)
+            xs = x.double()
+            want = torch.cat([f(xs * 2.0 ** l) for l in range(L) for f in (torch.sin, torch.cos)], -1).float()
+            assert got.shape == (n, 6 * L) and maxerr(got, want) < 5e-7
+    for R, P in ((1, 4), (3, 128), (7, 64), (33, 12), (257, 128)):
+        rays = torch.randn(R, 6, device=DEV)
+        z = torch.rand(R, P, device=DEV) * 4 + 2
+        pts = ops.length2pts(rays, z)
+        want = torch.cat((rays[:, None, :3] + z[..., None] * rays[:, None, 3:], rays[:, None, 3:].expand(R, P, 3)), -1)
+        assert torch.equal(pts, want)
+
+
 def test_argument_errors_are_loud(gin):
     with pytest.raises(nerf_b200.NB2Error):
         ops.inverse_sample(cu(torch.rand(4, 300)), cu(torch.rand(4, 300)), 129, u=cu(torch.rand(4, 129)))

@@ -24,7 +24,7 @@ x3 = pts.view(-1, 3)[: R * 8].contiguous()
 cases = [
     ("generate_rays_kernel", lambda: ops.generate_rays(pose, 400, 400, focal, focal), 160000 * 24),
     ("sample_coarse", lambda: ops.sample_coarse(rays, base_z, 4.0 / 128, jitter=jitter), R * (24 + 256 + 256 + 768)),
-    ("posenc_kernel", lambda: ops.posenc(x3, 10), x3.shape[0] * (12 + 240)),
+    ("posenc", lambda: ops.posenc(x3, 10), x3.shape[0] * (12 + 240)),
     ("ipe_kernel", lambda: ops.ipe(z, rays, 10, 0.01), R * 24 + R * 64 * 4 + R * 63 * (240 + 16)),
     ("weights", lambda: ops.weights_from_sigma(sigma, z, dirs), R * (256 + 256 + 12 + 256)),
     ("max_blur", lambda: ops.max_blur(w, 0.01), R * 512),
