@@ -202,16 +202,24 @@ def torch_cuda_baseline(dev, H, W):
     return out
 
 
-def train_step_leg(dev, precision="bf16x3", batches=(1024, 8192), steps=10):
+def train_step_leg(dev, precision="bf16x3", batches=(1024, 8192), steps=10, ddp=None):
     """One training step of the non-Ref model as the reference's trainer runs it (train.py:157-218): validSampler ->
     run() closure -> loss.backward() -> Adam step, on `R` rays x (64 coarse + 128 fine) samples, through the layer-wise
     tcgen05 engine (nerf_b200/train_engine.py).  R = 1024 is the reference's default --sample_ray_num; the larger batch
     shows the engine once the ~75 launches of a step stop being launch-bound.  Next to it: the same step as PyTorch ops on
-    the same GPU (oracle port, fp32, TF32 off)."""
+    the same GPU (oracle port, fp32, TF32 off).
+    ddp = (rank, world): the data-parallel step of ddp_train.py (every rank its own R rays; the one collective is the gradient
+    all-reduce, ddp_train.py:98, here ONE flat NCCL all-reduce of 743,051 fp32 values for both networks); times are the max
+    over ranks, rays/s the whole job's, and the replicas' parameters are checked to stay bit-identical."""
     import torch.nn.functional as F
     import nerf_b200
     from nerf_b200 import NeRF, ProposalNetwork, getBounds, inverseSample, maxBlurFilter
+    from nerf_b200.train_engine import allreduce_gradients
     from oracle import nerf_oracle as O
+    import torch.distributed as dist
+    world = ddp[1] if ddp else 1
+    if ddp:
+        torch.manual_seed(1234 + ddp[0])               # every rank samples its own rays
     peaks = load_peaks()
     sd_prop, sd_nerf = synthetic_state_dicts()
     prop_net, mip_net = nerf_b200.ProposalNetwork(10, 256), nerf_b200.MipNeRF(10, 4, 256)
@@ -258,11 +266,15 @@ def train_step_leg(dev, precision="bf16x3", batches=(1024, 8192), steps=10):
             opt.zero_grad()
             loss = prop_loss_func(weight_bounds, weights.detach()) + loss_func(fine_rendered, rgb_targets)
             loss.backward()
+            if ddp:
+                allreduce_gradients([mip_net, prop_net])
             opt.step()
             return loss
         for i in range(3):
             step(i)
         torch.cuda.synchronize(dev)
+        if ddp:
+            dist.barrier()
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         t0 = time.perf_counter()
         for i in range(steps):
@@ -273,6 +285,20 @@ def train_step_leg(dev, precision="bf16x3", batches=(1024, 8192), steps=10):
         wall = (time.perf_counter() - t0) / steps
         ms = sum(a.elapsed_time(b) for a, b in ev) / steps
         flop = 3 * (FLOP_PROP_PER_RAY + FLOP_NERF_PER_RAY) * R
+        if ddp:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t[0])
+            flat = torch.cat([p.detach().reshape(-1) for p in grad_vars])
+            lo, hi = flat.clone(), flat.clone()
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+            out[f"rays_{R}_per_gpu"] = {
+                "rays_per_step": R * world, "ms_per_step": ms, "host_ms_per_step": 1e3 * wall, "rays_per_s": R * world / (ms * 1e-3), "loss_rank0": float(loss),
+                "allreduce_bytes_per_step": 4 * flat.numel(), "replica_param_max_abs_diff": float((hi - lo).abs().max()),
+                "tensor_tflops": world * flop / (ms * 1e-3) / 1e12,
+                "hbm_frac_per_gpu": bytes_per_ray * R / (ms * 1e-3) / 1e9 / peaks["hbm"]}
+            continue
         # the reference algorithm's step as PyTorch ops on this GPU
         sp, sn = O.params_to(sd_prop, dev), O.params_to(sd_nerf, dev)
         cs, cl, rt, cr = nerf_b200.validSampler(rgbs, coords, cam_tf, R, N_COARSE, focal, NEAR, FAR, True)
@@ -498,6 +524,8 @@ def main():
     ap.add_argument("--precision", default="fp16x3", choices=["fp32", "fp16x3", "bf16x3", "fp16", "bf16"])
     ap.add_argument("--size", type=int, default=0, help="image side; default 400 (N = 1, weak) / 800 (strong)")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary precision modes / parity / baselines")
+    ap.add_argument("--train-ddp", action="store_true",
+                    help="N > 1: also time the data-parallel training step (ddp_train.py: per-rank ray batches, one flat gradient all-reduce)")
     ap.add_argument("--scaling", default="auto", choices=["auto", "weak", "strong"],
                     help="auto: strong for N > 1 (ONE 800x800 image sharded across the GPUs, BASELINE configs[4]); weak: one view per GPU")
     ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
@@ -692,6 +720,10 @@ def main():
                 extras[mode] = {"rays_per_s": total_rays / (m_ms / 1e3), "ms_per_step": m_ms, "fine_kernel_ms": m_k[2],
                                 "fine_kernel_tflops": FLOP_NERF_PER_RAY * scene.count / (m_k[2] * 1e-3) / 1e12}
 
+    train_ddp = None
+    if world > 1 and args.train_ddp:
+        with torch.enable_grad():
+            train_ddp = train_step_leg(dev, ddp=(rank, world))
     if rank != 0:
         scene.close()
         if world > 1:
@@ -733,6 +765,8 @@ def main():
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "other_precisions": extras,
     }
 
+    if train_ddp is not None:
+        line["train_step_ddp"] = train_ddp
     if not args.no_extras and world == 1:
         def leg(name, fn, *a, grad=False):       # an extra leg that fails must not take the headline line with it
             try:

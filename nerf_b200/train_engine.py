@@ -550,13 +550,40 @@ def allreduce_gradients(modules, group=None, average=True):
     params = [p for m in modules for p in m.parameters() if p.grad is not None]
     if not params:
         return 0
-    flat = torch.cat([p.grad.reshape(-1) for p in params])
-    dist.all_reduce(flat, group=group)
-    if average:
-        flat /= dist.get_world_size(group)
-    off = 0
+    # The engine's backward hands autograd VIEWS of one flat gradient buffer per network; when the optimizer's gradients still
+    # are those views (zero_grad(set_to_none=True), the default), consecutive gradients are adjacent in memory and every such
+    # run is reduced in place: no gather / scatter copies around the collective.  Anything else goes through one packed copy.
+    world = dist.get_world_size(group)
+    runs, loose = [], []
     for p in params:
-        n = p.numel()
-        p.grad.copy_(flat[off:off + n].view_as(p.grad))
-        off += n
-    return flat.numel()
+        g = p.grad
+        if not (g.is_contiguous() and g.dtype == torch.float32):
+            loose.append(p)
+            continue
+        last = runs[-1] if runs else None
+        if (last is not None and last["storage"] == g.untyped_storage().data_ptr() and last["device"] == g.device
+                and last["end"] == g.storage_offset()):
+            last["end"] += g.numel()
+        else:
+            runs.append({"storage": g.untyped_storage().data_ptr(), "device": g.device, "first": g, "start": g.storage_offset(),
+                         "end": g.storage_offset() + g.numel()})
+    total = 0
+    for r in runs:
+        n = r["end"] - r["start"]
+        flat = torch.empty(0, dtype=torch.float32, device=r["device"]).set_(r["first"].untyped_storage(), r["start"], (n,))
+        dist.all_reduce(flat, group=group)
+        if average:
+            flat /= world
+        total += n
+    if loose:
+        flat = torch.cat([p.grad.reshape(-1).float() for p in loose])
+        dist.all_reduce(flat, group=group)
+        if average:
+            flat /= world
+        off = 0
+        for p in loose:
+            n = p.numel()
+            p.grad.copy_(flat[off:off + n].view_as(p.grad))
+            off += n
+        total += flat.numel()
+    return total
