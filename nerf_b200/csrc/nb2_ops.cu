@@ -1317,7 +1317,8 @@ extern "C" int nb2_coarse_fine_merge_inds(nb2_handle* h, const float* rays, cons
 static int launch_composite(nb2_handle* h, const float* rgbo, const float* z, const float* dirs, int dir_stride, int64_t n_rays, int n_samples,
                             int flags, float near_t, float far_t, float* rgb_out, float* weights_out, float* depth_out, float* acc_out,
                             const float* aux, float* aux_out, cudaStream_t st) {
-  if ((n_samples & 3) == 0 && aligned16(rgbo) && aligned16(z) && (!weights_out || aligned16(weights_out)) && (!aux || aligned16(aux))) {
+  NB2_CHECK_ARG(aligned16(rgbo), "composite: rgbo must be 16-byte aligned ([r,g,b,sigma] samples are read as float4)");
+  if ((n_samples & 3) == 0 && aligned16(z) && (!weights_out || aligned16(weights_out)) && (!aux || aligned16(aux))) {
     int s4, lpr;
     regs_geometry(n_samples, s4, lpr);
     const int grid = grid_for(grid_for(n_rays, 32 / lpr), 8);

