@@ -62,6 +62,8 @@ struct GemmKParams {
   int m_tiles, n_tiles;
   int64_t k_per_split;    // rows of K per split (multiple of 64); splits == 1: unused
   int fused3;             // segments come in split-precision triples (A_lo B_hi, A_hi B_lo, A_hi B_hi): tiles shared between passes
+  int tma_out;            // out_hi / out_lo leave through the TMA unit (omap), one 32 x 64 box per warp and pass
+  CUtensorMap omap[2];    // out_hi, out_lo as [M][N] bf16, box 64 columns x 32 rows
   int dbg;                // NB2_TC_DEBUG (timing ablations only): 16 no global stores, 32 no bias loads, 128 no TMEM loads
 };
 
@@ -71,6 +73,15 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
                ::"r"(dst), "l"(map), "r"(col), "r"(row), "r"(bar)
                : "memory");
 }
+
+// TMA store: one [32 rows][64 columns] box of the staging tile (128-byte swizzle) -> global; rows / columns beyond the
+// tensor's extent are clipped by the TMA unit.  Bulk-group completion: wait_group.read = the shared-memory source may be reused.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int col, int row) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(col), "r"(row), "r"(src) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // D (128 x N, fp32, TMEM) (+)= A (smem) * B^T (smem), single CTA
 __device__ __forceinline__ void umma1_elect(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -270,6 +281,14 @@ __global__ void __launch_bounds__(kGThreads, 1) gemm_bf16_kernel(const __grid_co
     const int quad = warp & 3;                          // TMEM lane quadrant this warp may read
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
     uint32_t item = (uint32_t)group;
+    bool stg_busy = false;                              // a TMA store may still be reading this warp's staging tile
+    auto stg_acquire = [&]() {
+      if (stg_busy) {
+        if (lane == 0) tma_store_wait_read();
+        __syncwarp();
+        stg_busy = false;
+      }
+    };
     for (int64_t it = blockIdx.x + (int64_t)group * gridDim.x; it < n_items; it += 2 * (int64_t)gridDim.x, item += 2) {
       const int m_tile = (int)(it % p.m_tiles);
       const int n_tile = (int)((it / p.m_tiles) % p.n_tiles);
@@ -308,6 +327,7 @@ __global__ void __launch_bounds__(kGThreads, 1) gemm_bf16_kernel(const __grid_co
         const int64_t c0 = n0 + cb * 32;
         uint32_t keep[2] = {0u, 0u};                          // relu mask of this thread's row: bit j of keep[hb] = column 32 hb + j passes
         if (vecm) {
+          stg_acquire();
           for (int q = lane; q < (32 << sh); q += 32) {
             const int r = q >> sh, ch = q & ((1 << sh) - 1);
             const int64_t grow = row0 + r, gcol = c0 + 8 * ch;
@@ -381,6 +401,7 @@ __global__ void __launch_bounds__(kGThreads, 1) gemm_bf16_kernel(const __grid_co
               if (j < nv && !(__bfloat162float(mrow[j]) > 0.f)) v[j] = 0.f;
           }
           if (vec32) {
+            stg_acquire();
 #pragma unroll
             for (int k = 0; k < 8; ++k)
               st_shared_v4(stg + sw(lane, k), __float_as_uint(v[4 * k]), __float_as_uint(v[4 * k + 1]), __float_as_uint(v[4 * k + 2]),
@@ -410,6 +431,7 @@ __global__ void __launch_bounds__(kGThreads, 1) gemm_bf16_kernel(const __grid_co
               lo[j] = pack_bf16x2(v[2 * j] - bf16_lo_to_f32(hi[j]), v[2 * j + 1] - bf16_hi_to_f32(hi[j]));
             }
             if (vec16) {
+              stg_acquire();
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
                 st_shared_v4(stg + sw(lane, 4 * hb + k), hi[4 * k], hi[4 * k + 1], hi[4 * k + 2], hi[4 * k + 3]);
@@ -431,7 +453,26 @@ __global__ void __launch_bounds__(kGThreads, 1) gemm_bf16_kernel(const __grid_co
             }
           }
         }
-        if (vec16) {
+        if (vec16 && p.tma_out && nb == 2) {
+          // the staged 32 x 64 tile leaves as ONE bulk tensor store per part (the copy loops below were ~35 % of the
+          // epilogue's instructions); the lo part reuses the tile as soon as the TMA unit has read the hi part
+          for (int part = 0; part < (out_lo != nullptr ? 2 : 1); ++part) {
+            if (part) {
+              stg_acquire();
+#pragma unroll
+              for (int hb = 0; hb < 2; ++hb) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  st_shared_v4(stg + sw(lane, 4 * hb + k), lo_keep[hb][4 * k], lo_keep[hb][4 * k + 1], lo_keep[hb][4 * k + 2], lo_keep[hb][4 * k + 3]);
+              }
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0 && !(p.dbg & 16)) tma_store_2d(&p.omap[part], stg, (int)c0, (int)row0);
+            stg_busy = true;
+          }
+        } else if (vec16) {
+          stg_acquire();
           for (int part = 0; part < (out_lo != nullptr ? 2 : 1); ++part) {
             __nv_bfloat16* dst = part ? out_lo : out_hi;
             if (part) {
@@ -461,6 +502,7 @@ __global__ void __launch_bounds__(kGThreads, 1) gemm_bf16_kernel(const __grid_co
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&bars->acc_empty[buf]));
     }
+    if (lane == 0) tma_store_wait_all();                // the staging tile must outlive its last store
   }
 
   tc_fence_before();
@@ -662,6 +704,17 @@ extern "C" int nb2_gemm_bf16(nb2_handle* h, const nb2_gemm_desc* d, void* stream
     if (rc != NB2_OK) return rc;
     rc = B.mn_major ? make_map(&p.bmap[s], B.ptr, K, N8, B.ld, 64) : make_map(&p.bmap[s], B.ptr, d->N, K8, B.ld, p.bn);
     if (rc != NB2_OK) return rc;
+  }
+  p.tma_out = 0;
+  if (d->out_hi && (d->ld_16 & 7) == 0 && (d->N & 7) == 0 && ((uintptr_t)d->out_hi & 15) == 0 && (!d->out_lo || ((uintptr_t)d->out_lo & 15) == 0) &&
+      !(h->tc_debug & 64)) {                // NB2_TC_DEBUG & 64 (A/B timing): stores through the copy loops
+    rc = make_map(&p.omap[0], d->out_hi, d->M, d->N, d->ld_16, 32);
+    if (rc != NB2_OK) return rc;
+    if (d->out_lo) {
+      rc = make_map(&p.omap[1], d->out_lo, d->M, d->N, d->ld_16, 32);
+      if (rc != NB2_OK) return rc;
+    }
+    p.tma_out = 1;
   }
   const int64_t items = (int64_t)p.m_tiles * p.n_tiles * splits;
   const int grid = (int)std::min<int64_t>(items, h->sm_count);
