@@ -665,29 +665,81 @@ __global__ void search_cdf_kernel(const float* __restrict__ cdf, const float* __
 // The per-ray resampling core shared by inverse_sample (weights given) and resample (density
 // given).  mode 0: sh_w already holds the P proposal weights to sample from (already blurred).
 //          mode 1: sh_w holds raw density; do get_weights + maxBlur first.
-struct ResampleSmem {
-  float z[kMaxSamples];      // coarse depths
-  float a[kMaxSamples];      // density / weights scratch
-  float w[kMaxSamples];      // weights
-  float bins[kMaxSamples];   // mid points
-  float cdf[kMaxSamples];
-  float key[kMaxDraw];
-  float key_sorted[kMaxDraw];
-  int pay[kMaxDraw];
-  int pay_sorted[kMaxDraw];
+// CAP: capacity of the per-sample rows (and, + 8, of the per-draw rows).  The 64-sample / 129-draw render path takes
+// CAP = 136 (4.9 KB per warp instead of 9.3 KB: 44 instead of 24 resident warps per SM for a latency-bound kernel).
+template <int CAP>
+struct ResampleSmemT {
+  float z[CAP];      // coarse depths
+  float a[CAP];      // density / weights scratch
+  float w[CAP];      // weights
+  float bins[CAP];   // mid points
+  float cdf[CAP];
+  float key[CAP + 8];
+  float key_sorted[CAP + 8];
+  int pay[CAP + 8];
+  int pay_sorted[CAP + 8];
 };
+static_assert(kMaxSamples + 8 == kMaxDraw, "draw rows are sample rows + 8");
 
+// The draws of one lane, kDrawIL at a time: their binary searches advance in lockstep so that the dependent shared-memory
+// loads of one search hide under the others' (ncu: the one-draw-at-a-time loop held 27 % of the kernel's stall samples).
+// Same comparisons as upper_bound / invert_cdf, hence the same indices and values.
+constexpr int kDrawIL = 5;
 constexpr int kResampleWarps = 4;
+constexpr int kSmallCap = 136;     // >= 129 draws / 128 buckets of the u-ordered sort
+__device__ __forceinline__ void draw_samples_warp(const float* cdf, const float* bins, int B, const float* __restrict__ u_row, uint64_t seed,
+                                                  uint64_t ray_id, int N, float* key, int* pay, float* u_keep, int lane) {
+  const int steps = 32 - __clz(B);                       // |[0, B]| = B + 1 candidates
+  for (int base = 0; base < N; base += 32 * kDrawIL) {
+    float uu[kDrawIL];
+    int lo[kDrawIL], hi[kDrawIL];
+#pragma unroll
+    for (int q = 0; q < kDrawIL; ++q) {
+      const int i = base + lane + 32 * q;
+      uu[q] = 0.f;
+      if (i < N) uu[q] = u_row ? u_row[i] : philox_uniform(seed, ray_id, (uint32_t)i, 1u);
+      lo[q] = 0;
+      hi[q] = i < N ? B : 0;
+    }
+    for (int st = 0; st < steps; ++st) {
+#pragma unroll
+      for (int q = 0; q < kDrawIL; ++q) {
+        const int mid = (lo[q] + hi[q]) >> 1;
+        const float c = cdf[mid < B ? mid : B - 1];
+        if (lo[q] < hi[q]) {
+          if (c <= uu[q]) lo[q] = mid + 1; else hi[q] = mid;
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < kDrawIL; ++q) {
+      const int i = base + lane + 32 * q;
+      if (i < N) {
+        const int below = max(lo[q] - 1, 0), above = min(lo[q], B - 1);
+        const float cb = cdf[below], ca = cdf[above];
+        float denom = __fsub_rn(ca, cb);
+        if (denom < 1e-5f) denom = 1.f;
+        const float t = __fdiv_rn(__fsub_rn(uu[q], cb), denom);
+        const float bb = bins[below], ba = bins[above];
+        key[i] = __fadd_rn(bb, __fmul_rn(t, __fsub_rn(ba, bb)));
+        pay[i] = below;
+        if (u_keep) u_keep[i] = uu[q];
+      }
+    }
+  }
+}
+
+template <int CAP>
 __global__ void __launch_bounds__(32 * kResampleWarps)
 resample_kernel(int mode, const float* __restrict__ win /*weights or sigma (R,P)*/, const float* __restrict__ z,
                 const float* __restrict__ rays, const float* __restrict__ u, uint64_t seed, int64_t ray_offset,
                 int64_t n_rays, int P, int N, int sort, int n_keep, float blur_alpha, int act,
                 float* __restrict__ samples_out, int64_t* __restrict__ below_out) {
-  __shared__ ResampleSmem sm[kResampleWarps];
+  __shared__ ResampleSmemT<CAP> sm[kResampleWarps];
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int64_t r = (int64_t)blockIdx.x * kResampleWarps + warp;
   if (r >= n_rays) return;
-  ResampleSmem& s = sm[warp];
+  ResampleSmemT<CAP>& s = sm[warp];
   for (int i = lane; i < P; i += 32) {
     s.z[i] = z[r * P + i];
     s.a[i] = win[r * P + i];
@@ -710,14 +762,9 @@ resample_kernel(int mode, const float* __restrict__ win /*weights or sigma (R,P)
   for (int i = lane; i < B; i += 32) s.bins[i] = __fmul_rn(0.5f, __fadd_rn(s.z[i + 1], s.z[i]));
   __syncwarp();
   build_cdf_warp(s.w + 1, s.cdf, B, lane);
-  const bool values_only = sort && below_out == nullptr && N <= kMaxSamples;   // the fused resample path
-  for (int i = lane; i < N; i += 32) {
-    float uu = u ? u[r * N + i] : philox_uniform(seed, (uint64_t)(ray_offset + r), (uint32_t)i, 1u);
-    int b, a;
-    s.key[i] = invert_cdf(s.cdf, s.bins, B, uu, &b, &a);
-    s.pay[i] = b;
-    if (values_only) s.a[i] = uu;     // (the density / weight scratch is dead by now)
-  }
+  const bool values_only = sort && below_out == nullptr && N <= CAP;   // the fused resample path
+  // (the density / weight scratch s.a is dead by now: it keeps the uniforms for the u-ordered sort)
+  draw_samples_warp(s.cdf, s.bins, B, u ? u + r * N : nullptr, seed, (uint64_t)(ray_offset + r), N, s.key, s.pay, values_only ? s.a : nullptr, lane);
   __syncwarp();
   const float* kk = s.key;
   const int* pp = s.pay;
@@ -1280,8 +1327,12 @@ extern "C" int nb2_inverse_sample(nb2_handle* h, const float* weights, const flo
   NB2_CHECK_ARG(n_samples >= 3 && n_samples <= kMaxSamples, "inverse_sample: n_samples must be in [3,%d]", kMaxSamples);
   NB2_CHECK_ARG(n_draw >= 1 && n_draw <= kMaxDraw, "inverse_sample: n_draw must be in [1,%d]", kMaxDraw);
   if (n_rays == 0) return NB2_OK;
-  resample_kernel<<<grid_for(n_rays, kResampleWarps), 32 * kResampleWarps, 0, (cudaStream_t)stream>>>(
-      0, weights, z, nullptr, u, seed, ray_offset, n_rays, n_samples, n_draw, sort, n_draw, 0.f, 0, samples_out, below_out);
+  if (n_samples <= kSmallCap && n_draw <= kSmallCap)
+    resample_kernel<kSmallCap><<<grid_for(n_rays, kResampleWarps), 32 * kResampleWarps, 0, (cudaStream_t)stream>>>(
+        0, weights, z, nullptr, u, seed, ray_offset, n_rays, n_samples, n_draw, sort, n_draw, 0.f, 0, samples_out, below_out);
+  else
+    resample_kernel<kMaxSamples><<<grid_for(n_rays, kResampleWarps), 32 * kResampleWarps, 0, (cudaStream_t)stream>>>(
+        0, weights, z, nullptr, u, seed, ray_offset, n_rays, n_samples, n_draw, sort, n_draw, 0.f, 0, samples_out, below_out);
   NB2_LAUNCH_CHECK(h);
   return NB2_OK;
 }
@@ -1297,8 +1348,12 @@ extern "C" int nb2_resample(nb2_handle* h, const float* sigma, const float* z, c
   if (n_rays == 0) return NB2_OK;
   int act = (flags & NB2_DENSITY_SOFTPLUS) ? 1 : 0;
   // softplus'd density is then passed through get_weights' own relu (a no-op on positives)
-  resample_kernel<<<grid_for(n_rays, kResampleWarps), 32 * kResampleWarps, 0, (cudaStream_t)stream>>>(
-      1, sigma, z, rays, u, seed, ray_offset, n_rays, n_samples, n_draw, 1, n_draw - 1, blur_alpha, act, z_fine_out, below_out);
+  if (n_samples <= kSmallCap && n_draw <= kSmallCap)
+    resample_kernel<kSmallCap><<<grid_for(n_rays, kResampleWarps), 32 * kResampleWarps, 0, (cudaStream_t)stream>>>(
+        1, sigma, z, rays, u, seed, ray_offset, n_rays, n_samples, n_draw, 1, n_draw - 1, blur_alpha, act, z_fine_out, below_out);
+  else
+    resample_kernel<kMaxSamples><<<grid_for(n_rays, kResampleWarps), 32 * kResampleWarps, 0, (cudaStream_t)stream>>>(
+        1, sigma, z, rays, u, seed, ray_offset, n_rays, n_samples, n_draw, 1, n_draw - 1, blur_alpha, act, z_fine_out, below_out);
   NB2_LAUNCH_CHECK(h);
   return NB2_OK;
 }
