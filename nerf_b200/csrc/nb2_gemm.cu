@@ -64,7 +64,7 @@ struct GemmKParams {
   int fused3;             // segments come in split-precision triples (A_lo B_hi, A_hi B_lo, A_hi B_hi): tiles shared between passes
   int tma_out;            // out_hi / out_lo leave through the TMA unit (omap), one 32 x 64 box per warp and pass
   CUtensorMap omap[2];    // out_hi, out_lo as [M][N] bf16, box 64 columns x 32 rows
-  int dbg;                // NB2_TC_DEBUG (timing ablations only): 16 no global stores, 32 no bias loads, 128 no TMEM loads
+  int dbg;                // NB2_TC_DEBUG (timing ablations only): 16 no global stores, 32 no bias loads
 };
 
 // TMA: one [box rows][64 columns] box of a 2-D tensor map -> shared memory (128-byte swizzle), bytes counted on `bar`
@@ -326,6 +326,7 @@ __global__ void __launch_bounds__(kGThreads, 1) gemm_bf16_kernel(const __grid_co
         const int sh = nb == 2 ? 3 : 2;                       // 16-byte units per bf16 row of the pass: 8 or 4
         const int64_t c0 = n0 + cb * 32;
         uint32_t keep[2] = {0u, 0u};                          // relu mask of this thread's row: bit j of keep[hb] = column 32 hb + j passes
+        const bool mask_packed = vecm && vec16 && out32 == nullptr;   // the dgrad shape: mask applied to the packed hi / lo words
         if (vecm) {
           stg_acquire();
           for (int q = lane; q < (32 << sh); q += 32) {
@@ -336,9 +337,11 @@ __global__ void __launch_bounds__(kGThreads, 1) gemm_bf16_kernel(const __grid_co
             st_shared_v4(stg + sw(r, ch), m.x, m.y, m.z, m.w);
           }
           __syncwarp();
+          // dgrad shape (mask_packed): every lane re-reads its OWN row of the staged mask right before it packs that half
+          // (below); the other shapes expand the mask into one bit per column here
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
-            if (k < (1 << sh)) {
+            if (!mask_packed && k < (1 << sh)) {
               uint32_t m[4];
               asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(m[0]), "=r"(m[1]), "=r"(m[2]), "=r"(m[3]) : "r"(stg + sw(lane, k)));
 #pragma unroll
@@ -352,13 +355,14 @@ __global__ void __launch_bounds__(kGThreads, 1) gemm_bf16_kernel(const __grid_co
         }
         uint32_t ra[32], rb[32];
         uint32_t lo_keep[2][16];                              // lo residuals wait in registers while the hi rows use the staging tile
-        if (!(p.dbg & 128)) {
-          tmem_ld32(lane_addr + buf * 256 + cb * 32, ra);
-          if (nb == 2) tmem_ld32(lane_addr + buf * 256 + cb * 32 + 32, rb);
-          tmem_ld_wait();
-        } else {
+        // (an ablation branch that filled ra / rb with constants used to sit here: the compiler hoisted its 64 register
+        //  fills above the branch, i.e. into every pass -- ncu source page, 8 % of the epilogue's instructions)
+        tmem_ld32(lane_addr + buf * 256 + cb * 32, ra);
+        if (nb == 2) tmem_ld32(lane_addr + buf * 256 + cb * 32 + 32, rb);
+        tmem_ld_wait();
+        if (empty_k) {                                          // warp-uniform and rare: a branch, not 64 selects per pass
 #pragma unroll
-          for (int j = 0; j < 32; ++j) { ra[j] = 0x3f800000u + j; rb[j] = 0x3f800000u + j; }
+          for (int j = 0; j < 32; ++j) { ra[j] = 0u; rb[j] = 0u; }
         }
 #pragma unroll
         for (int hb = 0; hb < 2; ++hb) {
@@ -369,7 +373,7 @@ __global__ void __launch_bounds__(kGThreads, 1) gemm_bf16_kernel(const __grid_co
           //  pass and made the epilogue 10x longer than the main loop)
           float v[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = empty_k ? 0.f : __uint_as_float(hb ? rb[j] : ra[j]);
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(hb ? rb[j] : ra[j]);
           if (d.bias != nullptr && !(p.dbg & 32)) {
             if (nv == 32 && (reinterpret_cast<uintptr_t>(d.bias) & 15) == 0) {
               const float4* b4 = reinterpret_cast<const float4*>(d.bias + cc);
@@ -390,7 +394,9 @@ __global__ void __launch_bounds__(kGThreads, 1) gemm_bf16_kernel(const __grid_co
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = 1.f / (1.f + __expf(-v[j]));
           }
-          if (vecm) {
+          if (mask_packed) {
+            // applied to the packed words below
+          } else if (vecm) {
             const uint32_t kb = keep[hb];
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = ((kb >> j) & 1u) ? v[j] : 0.f;
@@ -429,6 +435,21 @@ __global__ void __launch_bounds__(kGThreads, 1) gemm_bf16_kernel(const __grid_co
             for (int j = 0; j < 16; ++j) {
               hi[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
               lo[j] = pack_bf16x2(v[2 * j] - bf16_lo_to_f32(hi[j]), v[2 * j + 1] - bf16_hi_to_f32(hi[j]));
+            }
+            if (mask_packed) {
+              // one packed compare per column pair (HSET2.BF16 with a mask result) instead of ~6 instructions per element;
+              // chunks 4 hb .. 4 hb + 3 of this lane's row still hold the mask: the hi rows of this half are stored after
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                uint32_t m[4];
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(m[0]), "=r"(m[1]), "=r"(m[2]), "=r"(m[3]) : "r"(stg + sw(lane, 4 * hb + k)));
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const uint32_t sel = __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&m[e]), __float2bfloat162_rn(0.f));
+                  hi[4 * k + e] &= sel;
+                  lo[4 * k + e] &= sel;
+                }
+              }
             }
             if (vec16) {
               stg_acquire();
