@@ -61,40 +61,56 @@ __global__ void sample_coarse_kernel(const float* __restrict__ rays, const float
 
 // Vectorised form (P % 4 == 0, 16-byte aligned pointers): one thread = four consecutive samples of a ray, so every global
 // access is a 16-byte vector and a warp covers whole 128-byte lines (the scalar form stores pts with a 12-byte stride).
-__global__ void sample_coarse_vec4_kernel(const float* __restrict__ rays, const float* __restrict__ base_z,
-                                          const float* __restrict__ jitter, float resolution, uint64_t seed, int64_t ray_offset,
-                                          int64_t n_rays, int P, float* __restrict__ z_out, float* __restrict__ pts_out) {
+__global__ void __launch_bounds__(256)
+sample_coarse_vec4_kernel(const float* __restrict__ rays, const float* __restrict__ base_z,
+                          const float* __restrict__ jitter, float resolution, uint64_t seed, int64_t ray_offset,
+                          int64_t n_rays, int P, float* __restrict__ z_out, float* __restrict__ pts_out) {
+  __shared__ float4 slab[8][3 * 32];          // a warp's 32 x 48 point bytes, written back as three coalesced 512-byte rows
   const int P4 = P >> 2;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t total = n_rays * P4;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_rays * P4) return;
-  const int64_t r = i / P4;
-  const int s0 = (int)(i - r * P4) * 4;
-  float j[4];
-  if (jitter) {
-    const float4 jv = __ldg(reinterpret_cast<const float4*>(jitter) + i);
-    j[0] = jv.x; j[1] = jv.y; j[2] = jv.z; j[3] = jv.w;
-  } else {
+  const int64_t i_warp = i - lane;
+  if (i_warp >= total) return;                 // whole warps only: the slab hand-over below is warp-synchronous
+  if (i < total) {
+    const int64_t r = i / P4;
+    const int s0 = (int)(i - r * P4) * 4;
+    float j[4];
+    if (jitter) {
+      const float4 jv = __ldg(reinterpret_cast<const float4*>(jitter) + i);
+      j[0] = jv.x; j[1] = jv.y; j[2] = jv.z; j[3] = jv.w;
+    } else {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) j[k] = philox_uniform(seed, (uint64_t)(ray_offset + r), (uint32_t)(s0 + k), 0u);
+      for (int k = 0; k < 4; ++k) j[k] = philox_uniform(seed, (uint64_t)(ray_offset + r), (uint32_t)(s0 + k), 0u);
+    }
+    const float4 bz = __ldg(reinterpret_cast<const float4*>(base_z + s0));
+    const float b[4] = {bz.x, bz.y, bz.z, bz.w};
+    float z[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) z[k] = __fadd_rn(b[k], __fmul_rn(j[k], resolution));
+    reinterpret_cast<float4*>(z_out)[i] = make_float4(z[0], z[1], z[2], z[3]);
+    if (pts_out) {
+      const float* ray = rays + r * 6;
+      const float o[3] = {__ldg(ray), __ldg(ray + 1), __ldg(ray + 2)}, d[3] = {__ldg(ray + 3), __ldg(ray + 4), __ldg(ray + 5)};
+      float v[12];
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) v[3 * k + c] = __fadd_rn(o[c], __fmul_rn(z[k], d[c]));
+      slab[warp][lane * 3 + 0] = make_float4(v[0], v[1], v[2], v[3]);
+      slab[warp][lane * 3 + 1] = make_float4(v[4], v[5], v[6], v[7]);
+      slab[warp][lane * 3 + 2] = make_float4(v[8], v[9], v[10], v[11]);
+    }
   }
-  const float4 bz = __ldg(reinterpret_cast<const float4*>(base_z + s0));
-  const float b[4] = {bz.x, bz.y, bz.z, bz.w};
-  float z[4];
-#pragma unroll
-  for (int k = 0; k < 4; ++k) z[k] = __fadd_rn(b[k], __fmul_rn(j[k], resolution));
-  reinterpret_cast<float4*>(z_out)[i] = make_float4(z[0], z[1], z[2], z[3]);
   if (pts_out) {
-    const float* ray = rays + r * 6;
-    const float o[3] = {__ldg(ray), __ldg(ray + 1), __ldg(ray + 2)}, d[3] = {__ldg(ray + 3), __ldg(ray + 4), __ldg(ray + 5)};
-    float v[12];
+    __syncwarp();
+    const int n_valid = (int)min((int64_t)32, total - i_warp) * 3;      // float4s this warp owns
+    float4* dst = reinterpret_cast<float4*>(pts_out) + i_warp * 3;
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
-#pragma unroll
-      for (int c = 0; c < 3; ++c) v[3 * k + c] = __fadd_rn(o[c], __fmul_rn(z[k], d[c]));
-    float4* dst = reinterpret_cast<float4*>(pts_out) + i * 3;
-    dst[0] = make_float4(v[0], v[1], v[2], v[3]);
-    dst[1] = make_float4(v[4], v[5], v[6], v[7]);
-    dst[2] = make_float4(v[8], v[9], v[10], v[11]);
+    for (int k = 0; k < 3; ++k) {
+      const int q = k * 32 + lane;
+      if (q < n_valid) dst[q] = slab[warp][q];
+    }
   }
 }
 
