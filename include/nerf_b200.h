@@ -294,6 +294,12 @@ typedef struct nb2_gemm_desc {
   int splits;
   int reserved;
   int64_t split_stride; /* floats */
+  /* optional, weight-gradient shape only (A MN-major, split-precision triples, one work item per CTA): the row sums of A
+   * over K, sum_k A[m][k] = the bias gradient db = dY^T 1 (autograd's sum over the batch for nn.Linear's bias), from one
+   * extra N = 16 MMA per k-step against a constant tile of ones: a_rowsum_out[split * a_rowsum_stride + m], fp32 partial
+   * sums per split (reduce like out_f32).  NULL: not computed. */
+  float* a_rowsum_out;
+  int64_t a_rowsum_stride; /* floats */
 } nb2_gemm_desc;
 int nb2_gemm_bf16(nb2_handle* h, const nb2_gemm_desc* d, void* stream);
 /* fp32 (rows, cols; row stride ld_src) -> bf16 hi (+ lo residual or NULL), row stride ld_dst (multiple of 8, pad zeroed);

@@ -63,6 +63,7 @@ class GemmDesc(ctypes.Structure):
         ("out_f32", c_vp), ("out_hi", c_vp), ("out_lo", c_vp),
         ("ld_f32", c_i64), ("ld_16", c_i64),
         ("splits", c_int), ("reserved", c_int), ("split_stride", c_i64),
+        ("a_rowsum_out", c_vp), ("a_rowsum_stride", c_i64),
     ]
 
 

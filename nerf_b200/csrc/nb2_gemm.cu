@@ -63,6 +63,7 @@ struct GemmKParams {
   int64_t k_per_split;    // rows of K per split (multiple of 64); splits == 1: unused
   int fused3;             // segments come in split-precision triples (A_lo B_hi, A_hi B_lo, A_hi B_hi): tiles shared between passes
   int tma_out;            // out_hi / out_lo leave through the TMA unit (omap), one 32 x 64 box per warp and pass
+  int rowsum;             // d.a_rowsum_out: one extra N = 16 MMA per k-step of the A_lo and A_hi tiles against a tile of ones
   CUtensorMap omap[2];    // out_hi, out_lo as [M][N] bf16, box 64 columns x 32 rows
   int dbg;                // NB2_TC_DEBUG (timing ablations only): 16 no global stores, 32 no bias loads
 };
@@ -143,6 +144,13 @@ __global__ void __launch_bounds__(kGThreads, 1) gemm_bf16_kernel(const __grid_co
   if (warp == 5) {
     tmem_alloc(smem_u32(&bars->tmem_base), 512);
     tmem_relinquish();
+  }
+  if (p.rowsum) {
+    // bias gradient riding on the weight gradient: an 8 KB MN-major B block [64 k-rows][64 columns] of bf16 ones (constant, so
+    // the 128-byte swizzle is irrelevant) in the first two staging tiles -- the host guarantees ONE work item per CTA in
+    // this mode, and its epilogue (the staging tiles' only other user) starts after the last MMA has completed
+    for (int i = threadIdx.x; i < 512; i += kGThreads) st_shared_v4(stg_base + 16u * i, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
+    fence_proxy_async_smem();
   }
   tc_fence_before();
   __syncthreads();
@@ -245,6 +253,18 @@ __global__ void __launch_bounds__(kGThreads, 1) gemm_bf16_kernel(const __grid_co
           first = false;
         }
       };
+      // row sums of A (the bias gradient): D[128, 16] at TMEM columns [256, 272) of the single item of this CTA; only the
+      // N tile 0 items compute them (the other N tiles of the same M tile would repeat the same sums)
+      const bool want_rowsum = p.rowsum && ((it / p.m_tiles) % p.n_tiles) == 0;
+      bool first_ones = true;
+      auto ones_chunk = [&](uint32_t sa, int ksteps) {
+        const uint32_t a_s = smem_base + sa * kGStageBytes;
+        const uint32_t idesc1 = gemm_idesc(16, true, true);
+        for (int ks = 0; ks < ksteps; ++ks) {
+          umma1_elect(tmem_base + 256, gemm_smem_desc(a_s + ks * 2048, true), gemm_smem_desc(stg_base + ks * 2048, true), idesc1, first_ones ? 0u : 1u);
+          first_ones = false;
+        }
+      };
       const int seg_step = p.fused3 ? 3 : 1;
       for (int s = 0; s < d.n_seg; s += seg_step) {
         const bool a_mn = d.seg[s].a.mn_major != 0, b_mn = d.seg[s].b.mn_major != 0;
@@ -260,8 +280,10 @@ __global__ void __launch_bounds__(kGThreads, 1) gemm_bf16_kernel(const __grid_co
           } else {
             const uint32_t st0 = wait_full();                 // (A_lo, B_hi)
             mma_chunk(st0, st0, ksteps, idesc, a_mn, b_mn);   // lo x hi
+            if (want_rowsum) ones_chunk(st0, ksteps);         // lo x 1
             const uint32_t st1 = wait_full();                 // A_hi
             mma_chunk(st1, st0, ksteps, idesc, a_mn, b_mn);   // hi x hi
+            if (want_rowsum) ones_chunk(st1, ksteps);         // hi x 1
             umma1_commit_elect(smem_u32(&bars->empty[st0]));
             const uint32_t st2 = wait_full();                 // B_lo
             mma_chunk(st1, st2, ksteps, idesc, a_mn, b_mn);   // hi x lo
@@ -519,6 +541,12 @@ __global__ void __launch_bounds__(kGThreads, 1) gemm_bf16_kernel(const __grid_co
           }
         }
       }
+      if (p.rowsum && n_tile == 0) {
+        uint32_t rs[32];
+        tmem_ld32(lane_addr + 256, rs);                   // 16 identical columns (+ 16 unused): column 0 is the sum
+        tmem_ld_wait();
+        if (row < d.M) d.a_rowsum_out[(int64_t)split * d.a_rowsum_stride + row] = empty_k ? 0.f : __uint_as_float(rs[0]);
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&bars->acc_empty[buf]));
@@ -713,6 +741,14 @@ extern "C" int nb2_gemm_bf16(nb2_handle* h, const nb2_gemm_desc* d, void* stream
     if (!same) p.fused3 = 0;
   }
   if (h->tc_debug & 8) p.fused3 = 0;      // NB2_TC_DEBUG & 8 (A/B timing): every pass loads its own tiles
+  p.rowsum = 0;
+  if (d->a_rowsum_out) {
+    const int64_t n_items = (int64_t)p.m_tiles * p.n_tiles * splits;
+    NB2_CHECK_ARG(p.fused3 && d->n_seg == 3 && n_items <= h->sm_count && d->a_rowsum_stride >= d->M,
+                  "gemm: a_rowsum_out needs the weight-gradient shape (MN-major split-precision triple), one work item per SM "
+                  "(%lld items, %d SMs) and a_rowsum_stride >= M", (long long)n_items, h->sm_count);
+    p.rowsum = 1;
+  }
   p.dbg = h->tc_debug;
   int rc = kernel_set_smem(h, (const void*)gemm_bf16_kernel, kGSmem);
   if (rc != NB2_OK) return rc;

@@ -142,8 +142,10 @@ def _out(t, dtype):
     return t.data_ptr(), t.stride(0)
 
 
-def gemm(M, N, segs, bias=None, act=ACT_NONE, mask=None, out_f32=None, out_hi=None, out_lo=None, splits=1, split_stride=0):
-    """D[M, N] = epi(sum_s A_s B_s^T).  segs: list of (A, a_mn_major, B, b_mn_major, K).  See nb2_gemm_desc."""
+def gemm(M, N, segs, bias=None, act=ACT_NONE, mask=None, out_f32=None, out_hi=None, out_lo=None, splits=1, split_stride=0,
+         a_rowsum=None, a_rowsum_stride=0):
+    """D[M, N] = epi(sum_s A_s B_s^T).  segs: list of (A, a_mn_major, B, b_mn_major, K).  See nb2_gemm_desc.
+    a_rowsum (fp32, splits x a_rowsum_stride): per-split sums over K of A's rows (the bias gradient riding on the wgrad)."""
     if not 1 <= len(segs) <= _lib.GEMM_MAX_SEG:
         raise NB2Error(f"gemm: 1..{_lib.GEMM_MAX_SEG} segments")
     dev = segs[0][0].device
@@ -166,8 +168,12 @@ def gemm(M, N, segs, bias=None, act=ACT_NONE, mask=None, out_f32=None, out_hi=No
             raise NB2Error("gemm: out_hi and out_lo must share their row stride")
         d.out_lo = lo_ptr
     d.splits, d.split_stride = splits, split_stride
+    if a_rowsum is not None:
+        if a_rowsum.dtype != torch.float32 or not a_rowsum.is_contiguous():
+            raise NB2Error("gemm: a_rowsum must be a contiguous fp32 tensor")
+        d.a_rowsum_out, d.a_rowsum_stride = a_rowsum.data_ptr(), a_rowsum_stride
     if _current is not None:
-        _current._add_gemm(d, [t for A, _, B, _, _ in segs for t in (A, B)] + [bias, mask, out_f32, out_hi, out_lo])
+        _current._add_gemm(d, [t for A, _, B, _, _ in segs for t in (A, B)] + [bias, mask, out_f32, out_hi, out_lo, a_rowsum])
         return
     check(load().nb2_gemm_bf16(handle(dev), ctypes.byref(d), stream_ptr(dev)))
 

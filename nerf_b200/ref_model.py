@@ -292,8 +292,7 @@ class RefNeRF(NeRF):
             raise _lib.NB2Error("RefNeRF: the density shift of the render path is applied by the caller during training (train.py:181)")
 
         def wg(pk, dy, x, n_out, n_in, perm=None):
-            wgrad(dy, x, n_out, n_in, n, x3, slot[id(pk.lin.weight)], perm=perm, sm_count=sm)
-            bgrad(dy, n_out, n, x3, slot[id(pk.lin.bias)], sm_count=sm)
+            wgrad(dy, x, n_out, n_in, n, x3, slot[id(pk.lin.weight)], perm=perm, sm_count=sm, grad_b=slot[id(pk.lin.bias)])
 
         def dg(dy, w, K, mask, width=None):
             """dX = (dY W) [* relu mask] as bf16 hi / lo rows."""
@@ -349,8 +348,8 @@ class RefNeRF(NeRF):
         prog.call(geometry)
         # ---- heads (ref_model.py:81-82; packed rows: norm_col_tint_head 0..8, rho_tau_head 9..10) ----
         nct, rt = self.norm_col_tint_head, self.rho_tau_head
-        wgrad(dh, a["inter"], 11, H, n, x3, [(0, 9, slot[id(nct.weight)]), (9, 11, slot[id(rt.weight)])], sm_count=sm)
-        bgrad(dh, 11, n, x3, [(0, 9, slot[id(nct.bias)]), (9, 11, slot[id(rt.bias)])], sm_count=sm)
+        wgrad(dh, a["inter"], 11, H, n, x3, [(0, 9, slot[id(nct.weight)]), (9, 11, slot[id(rt.weight)])], sm_count=sm,
+              grad_b=[(0, 9, slot[id(nct.bias)]), (9, 11, slot[id(rt.bias)])])
         d_inter = _empty16(n, H, dev, x3)
         linear.gemm(n, H, _dgrad_segs(dh, wl(hk), 11, x3) + _dgrad_segs(db, wl(bk), bd, x3), mask=a["inter"][0],
                     out_hi=d_inter[0], out_lo=d_inter[1])

@@ -132,23 +132,34 @@ def bgrad(dy, n_out, rows, x3, grad_b, sm_count=148):
         linear.reduce_splits(ws[r0 * 32:], splits, m_pad * 32, r1 - r0, 1, 32, g.view(r1 - r0, 1))
 
 
-def wgrad(dy, x, n_out, n_in, rows, x3, grad_w, perm=None, sm_count=148):
-    """grad_w (n_out, n_in) fp32 = dy^T x over `rows` samples; dy (rows, >= n_out), x (rows, ld >= n_in) as (hi, lo)."""
+def wgrad(dy, x, n_out, n_in, rows, x3, grad_w, perm=None, sm_count=148, grad_b=None):
+    """grad_w (n_out, n_in) fp32 = dy^T x over `rows` samples; dy (rows, >= n_out), x (rows, ld >= n_in) as (hi, lo).
+    grad_b (n_out,): the bias gradient dy^T 1 of the same layer.  In the split precision it rides on this GEMM (one extra
+    N = 16 MMA per k-step against a tile of ones, nb2_gemm_desc.a_rowsum_out) instead of re-reading dy in a GEMM of its own."""
     dev = x[0].device
     ld_ws = (x[0].shape[1] + 31) // 32 * 32
     n_cols = x[0].shape[1]
     m_pad = (n_out + 127) // 128 * 128
     tiles = (m_pad // 128) * ((ld_ws + 255) // 256)
     splits = max(1, min(sm_count // tiles, (rows + 255) // 256))
-    ws = _Workspace.get(dev, splits * m_pad * ld_ws)
-    out = ws[: splits * m_pad * ld_ws].view(splits * m_pad, ld_ws)
+    fuse_b = grad_b is not None and x3
+    n_ws = splits * m_pad * ld_ws
+    ws = _Workspace.get(dev, n_ws + (splits * m_pad if fuse_b else 0))
+    out = ws[:n_ws].view(splits * m_pad, ld_ws)
+    rs = ws[n_ws:n_ws + splits * m_pad] if fuse_b else None
     if x3:
         segs = [(dy[1], True, x[0], True, rows), (dy[0], True, x[1], True, rows), (dy[0], True, x[0], True, rows)]
     else:
         segs = [(dy[0], True, x[0], True, rows)]
-    linear.gemm(n_out, n_cols, segs, out_f32=out[:n_out], splits=max(splits, 1) if splits > 1 else 1, split_stride=m_pad * ld_ws)
+    linear.gemm(n_out, n_cols, segs, out_f32=out[:n_out], splits=max(splits, 1) if splits > 1 else 1, split_stride=m_pad * ld_ws,
+                a_rowsum=rs, a_rowsum_stride=m_pad)
     for r0, r1, g in _row_targets(grad_w, n_out):
         linear.reduce_splits(ws[r0 * ld_ws:], splits, m_pad * ld_ws, r1 - r0, n_in, ld_ws, g, col_perm=perm)
+    if fuse_b:
+        for r0, r1, g in _row_targets(grad_b, n_out):
+            linear.reduce_splits(rs[r0:], splits, m_pad, r1 - r0, 1, 1, g.view(r1 - r0, 1))
+    elif grad_b is not None:
+        bgrad(dy, n_out, rows, x3, grad_b, sm_count=sm_count)
 
 
 class _Plan:
@@ -282,14 +293,12 @@ class ProposalEngine(_Engine):
         sm = torch.cuda.get_device_properties(dev).multi_processor_count
         ds = _empty16(n, 8, dev, x3)
         prog.call(lambda: linear.to_bf16(prog.inp["g"].view(n, 1), ld_dst=8, want_lo=x3, out=ds))
-        wgrad(ds, acts[4], 1, H, n, x3, grads[4][0], sm_count=sm)
-        bgrad(ds, 1, n, x3, grads[4][1], sm_count=sm)
+        wgrad(ds, acts[4], 1, H, n, x3, grads[4][0], sm_count=sm, grad_b=grads[4][1])
         dy = _empty16(n, H, dev, x3)
         linear.gemm(n, H, _dgrad_segs(ds, (W[4].hi, W[4].lo), 1, x3), mask=acts[4][0], out_hi=dy[0], out_lo=dy[1])
         for l in (3, 2, 1, 0):
             x = acts[l]
-            wgrad(dy, x, H, self.lins[l].in_features, n, x3, grads[l][0], sm_count=sm)
-            bgrad(dy, H, n, x3, grads[l][1], sm_count=sm)
+            wgrad(dy, x, H, self.lins[l].in_features, n, x3, grads[l][0], sm_count=sm, grad_b=grads[l][1])
             if l > 0:
                 dx = _empty16(n, H, dev, x3)
                 linear.gemm(n, H, _dgrad_segs(dy, (W[l].hi, W[l].lo), H, x3), mask=x[0], out_hi=dx[0], out_lo=dx[1])
@@ -368,8 +377,7 @@ class NerfEngine(_Engine):
         wl = lambda i: (W[i].hi, W[i].lo)
 
         def wg(i, dy, x, n_out, n_in, perm=None):
-            wgrad(dy, x, n_out, n_in, n, x3, grads[i][0], perm=perm, sm_count=sm)
-            bgrad(dy, n_out, n, x3, grads[i][1], sm_count=sm)
+            wgrad(dy, x, n_out, n_in, n, x3, grads[i][0], perm=perm, sm_count=sm, grad_b=grads[i][1])
 
         dz, ds = _empty16(n, 8, dev, x3), _empty16(n, 8, dev, x3)
         prog.call(lambda: check(load().nb2_nerf_head_backward(handle(dev), prog.inp["out"].data_ptr(), prog.inp["g"].data_ptr(), n,

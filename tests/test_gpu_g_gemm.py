@@ -105,6 +105,34 @@ def test_bias_gradient_as_ones_gemm():
     close(s, x.sum(0), 2e-4)
 
 
+@pytest.mark.parametrize("rows,n_out,n_in", [(5000, 256, 256), (70000, 256, 320), (3001, 1, 256), (9000, 11, 128), (130, 128, 64), (40000, 256, 64)])
+def test_bias_gradient_rides_on_the_weight_gradient(rows, n_out, n_in):
+    """wgrad(..., grad_b=): the row sums of dY^T from one extra N = 16 MMA per k-step against a tile of ones
+    (nb2_gemm_desc.a_rowsum_out) equal the separate ones-GEMM and the fp64 sums; the weight gradient itself is bit-identical
+    with and without the extra MMAs; one and two N tiles, M below / at / above one 128-row tile, ragged row counts."""
+    from nerf_b200.train_engine import bgrad, wgrad
+    ld = (n_out + 7) // 8 * 8
+    dy = rnd((rows, ld), 11)
+    dy[:, n_out:] = 0
+    x = rnd((rows, n_in), 12)
+    dyp, xp = linear.to_bf16(dy), linear.to_bf16(x)
+    gw0, gw1 = torch.empty(n_out, n_in, device=DEV), torch.empty(n_out, n_in, device=DEV)
+    gb0, gb1 = torch.empty(n_out, device=DEV), torch.empty(n_out, device=DEV)
+    wgrad(dyp, xp, n_out, n_in, rows, True, gw0)
+    bgrad(dyp, n_out, rows, True, gb0)
+    wgrad(dyp, xp, n_out, n_in, rows, True, gw1, grad_b=gb1)
+    assert torch.equal(gw0, gw1)
+    ref = dy[:, :n_out].double().sum(0)
+    scale = float(dy[:, :n_out].double().abs().sum(0).max())
+    assert float((gb1.double() - ref).abs().max()) <= 2e-6 * scale
+    assert float((gb1 - gb0).abs().max()) <= 2e-6 * scale
+    # packed heads: the rows of one GEMM reduced into two parameters
+    if n_out == 11:
+        a, b = torch.empty(9, device=DEV), torch.empty(2, device=DEV)
+        wgrad(dyp, xp, n_out, n_in, rows, True, [(0, 9, gw1[:9]), (9, 11, gw1[9:])], grad_b=[(0, 9, a), (9, 11, b)])
+        assert torch.equal(torch.cat((a, b)), gb1)
+
+
 def test_launch_plan_replays_bit_identically_with_rebound_outputs():
     """linear.Program: a forward GEMM, a split-K wgrad and two deferred reductions recorded once, replayed into other output
     tensors: bit-identical to the eager launches (nb2_gemm_bf16_batch / nb2_reduce_splits_batch against the single calls)."""
