@@ -20,10 +20,12 @@ def wgrad():
     train_engine.wgrad((dyh, dyl), (xh, xl), N, K, M, True, gw)
 def bgrad():
     train_engine.bgrad((dyh, dyl), N, M, True, gb)
+def wgrad_b():
+    train_engine.wgrad((dyh, dyl), (xh, xl), N, K, M, True, gw, grad_b=gb)
 def fwd1():
     linear.gemm(M, N, [(xh, False, wh, False, K)], bias=b, act=linear.ACT_RELU, out_hi=hi)
 flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=DEV)
-for name, fn in (("forward x3", fwd), ("dgrad x3", dgrad), ("wgrad x3", wgrad), ("bgrad x3", bgrad), ("forward x1", fwd1)):
+for name, fn in (("forward x3", fwd), ("dgrad x3", dgrad), ("wgrad x3", wgrad), ("bgrad x3", bgrad), ("wgrad+bias x3", wgrad_b), ("forward x1", fwd1)):
     for _ in range(2): fn()
     torch.cuda.synchronize()
     ts = []
@@ -33,5 +35,5 @@ for name, fn in (("forward x3", fwd), ("dgrad x3", dgrad), ("wgrad x3", wgrad), 
         e0.record(); fn(); e1.record(); torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1) * 1e3)
     ts.sort()
-    print(f"{name:12s} {ts[2]:7.0f} us (min {ts[0]:.0f})")
+    print(f"{name:14s} {ts[2]:7.0f} us (min {ts[0]:.0f})")
 # correctness of the store path against the copy-loop path is covered by tests/test_gpu_g_gemm.py
