@@ -456,7 +456,7 @@ __global__ void __launch_bounds__(kGThreads, 1) gemm_bf16_kernel(const __grid_co
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               hi[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
-              lo[j] = pack_bf16x2(v[2 * j] - bf16_lo_to_f32(hi[j]), v[2 * j + 1] - bf16_hi_to_f32(hi[j]));
+              lo[j] = residual16x2<false>(v[2 * j], v[2 * j + 1], hi[j]);   // v - float(hi): one FHFMA.BF16 per element, exact
             }
             if (mask_packed) {
               // one packed compare per column pair (HSET2.BF16 with a mask result) instead of ~6 instructions per element;

@@ -294,7 +294,12 @@ __device__ __forceinline__ uint32_t residual16x2(float a, float b, uint32_t hi_p
         : "=f"(l0), "=f"(l1) : "r"(hi_packed), "f"(a), "f"(b));
     return pack_f16x2(l0, l1);
   }
-  return pack_bf16x2(a - bf16_lo_to_f32(hi_packed), b - bf16_hi_to_f32(hi_packed));
+  // bf16: the same with fma.rn.f32.bf16 (FHFMA.BF16); -1.0 = 0xBF80
+  float l0, l1;
+  asm("{\n\t.reg .b16 lo, hi, m1;\n\tmov.b32 {lo, hi}, %2;\n\tmov.b16 m1, 0xBF80;\n\t"
+      "fma.rn.f32.bf16 %0, lo, m1, %3;\n\tfma.rn.f32.bf16 %1, hi, m1, %4;\n\t}"
+      : "=f"(l0), "=f"(l1) : "r"(hi_packed), "f"(a), "f"(b));
+  return pack_bf16x2(l0, l1);
 }
 
 // Byte offset of element (row, col) inside a 128-row x 64-col bf16 tile with the 128 B swizzle.
