@@ -63,6 +63,8 @@ struct GemmKParams {
   int64_t k_per_split;    // rows of K per split (multiple of 64); splits == 1: unused
   int fused3;             // segments come in split-precision triples (A_lo B_hi, A_hi B_lo, A_hi B_hi): tiles shared between passes
   int tma_out;            // out_hi / out_lo leave through the TMA unit (omap), one 32 x 64 box per warp and pass
+  int reuse3;             // forward / dgrad split-precision triple with K = 256: pass order (hi x lo), (lo x hi), (hi x hi); the
+                          // last pass reuses the B tiles of the second one in place and reloads only the A slots
   int rowsum;             // d.a_rowsum_out: one extra N = 16 MMA per k-step of the A_lo and A_hi tiles against a tile of ones
   CUtensorMap omap[2];    // out_hi, out_lo as [M][N] bf16, box 64 columns x 32 rows
   int dbg;                // NB2_TC_DEBUG (timing ablations only): 16 no global stores, 32 no bias loads
@@ -119,7 +121,12 @@ __device__ __forceinline__ uint32_t gemm_idesc(int N, bool a_mn, bool b_mn) {
          ((uint32_t)(128 >> 4) << 24);
 }
 
-__global__ void __launch_bounds__(kGThreads, 1) gemm_bf16_kernel(const __grid_constant__ GemmKParams p) {
+// EPI = epilogue warps: 8 (two groups of four, one per accumulator buffer; every shape) or 16 (four groups: two per buffer,
+// each draining one half of the tile's columns in 32-column passes; the bf16-output shapes of the hot layers, whose epilogue
+// is latency-bound per warp -- two epilogue warps per scheduler ran at IPC 0.33).
+template <int EPI>
+__global__ void __launch_bounds__(32 * (EPI + 2), 1) gemm_bf16_kernel(const __grid_constant__ GemmKParams p) {
+  constexpr int kPW = EPI == 8 ? 4 : 16, kMW = EPI == 8 ? 5 : 17;     // producer / MMA warp (EPI == 8 keeps warps 0-3, 6-9 as epilogue)
   extern __shared__ unsigned char smem_dyn[];
   const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   unsigned char* smem_al = smem_dyn + (smem_base - smem_u32(smem_dyn));
@@ -137,11 +144,11 @@ __global__ void __launch_bounds__(kGThreads, 1) gemm_bf16_kernel(const __grid_co
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&bars->acc_full[i]), 1);
-      mbar_init(smem_u32(&bars->acc_empty[i]), 4); // one arrival per epilogue warp
+      mbar_init(smem_u32(&bars->acc_empty[i]), EPI / 2); // one arrival per epilogue warp of the buffer
     }
     mbar_fence_init();
   }
-  if (warp == 5) {
+  if (warp == kMW) {
     tmem_alloc(smem_u32(&bars->tmem_base), 512);
     tmem_relinquish();
   }
@@ -149,7 +156,7 @@ __global__ void __launch_bounds__(kGThreads, 1) gemm_bf16_kernel(const __grid_co
     // bias gradient riding on the weight gradient: an 8 KB MN-major B block [64 k-rows][64 columns] of bf16 ones (constant, so
     // the 128-byte swizzle is irrelevant) in the first two staging tiles -- the host guarantees ONE work item per CTA in
     // this mode, and its epilogue (the staging tiles' only other user) starts after the last MMA has completed
-    for (int i = threadIdx.x; i < 512; i += kGThreads) st_shared_v4(stg_base + 16u * i, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
+    for (int i = threadIdx.x; i < 512; i += 32 * (EPI + 2)) st_shared_v4(stg_base + 16u * i, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
     fence_proxy_async_smem();
   }
   tc_fence_before();
@@ -168,7 +175,7 @@ __global__ void __launch_bounds__(kGThreads, 1) gemm_bf16_kernel(const __grid_co
     }
   };
 
-  if (warp == 4) {
+  if (warp == kPW) {
     // =========================================== producer (one thread drives the TMA unit) ===========================
     if (lane == 0) {
       uint32_t issued = 0;
@@ -217,6 +224,13 @@ __global__ void __launch_bounds__(kGThreads, 1) gemm_bf16_kernel(const __grid_co
               load_stage(-1, t + 1, k);
             }
           }
+        } else if (p.reuse3) {
+          // both cross terms first, but (A_hi, B_lo) before (A_lo, B_hi): the four (A_lo, B_hi) stages
+          // are then exactly the ring's four stages, and the closing A_hi x B_hi pass finds its B tiles already in place --
+          // it reloads only the 16 KB A slots (448 KB instead of 576 KB of tiles per 128 x 256 output tile)
+          for (int64_t k = 0; k < d.seg[1].K; k += 64) load_stage(1, 1, k);
+          for (int64_t k = 0; k < d.seg[0].K; k += 64) load_stage(0, 0, k);
+          for (int64_t k = 0; k < d.seg[2].K; k += 64) load_stage(2, -1, k);
         } else {
           for (int s = 0; s < d.n_seg; ++s) {
             int64_t k0, k1;
@@ -226,7 +240,7 @@ __global__ void __launch_bounds__(kGThreads, 1) gemm_bf16_kernel(const __grid_co
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == kMW) {
     // =========================================== MMA issuer (whole warp, one elected lane per instruction) ===========
     uint32_t consumed = 0, item = 0;
     for (int64_t it = blockIdx.x; it < n_items; it += gridDim.x, ++item) {
@@ -266,7 +280,8 @@ __global__ void __launch_bounds__(kGThreads, 1) gemm_bf16_kernel(const __grid_co
         }
       };
       const int seg_step = p.fused3 ? 3 : 1;
-      for (int s = 0; s < d.n_seg; s += seg_step) {
+      for (int si = 0; si < d.n_seg; si += seg_step) {
+        const int s = p.reuse3 ? (si == 0 ? 1 : (si == 1 ? 0 : 2)) : si;     // reuse3: (hi x lo), (lo x hi), (hi x hi)
         const bool a_mn = d.seg[s].a.mn_major != 0, b_mn = d.seg[s].b.mn_major != 0;
         const uint32_t idesc = gemm_idesc(p.bn, a_mn, b_mn);
         int64_t k0, k1;
@@ -294,6 +309,108 @@ __global__ void __launch_bounds__(kGThreads, 1) gemm_bf16_kernel(const __grid_co
       }
       umma1_commit_elect(smem_u32(&bars->acc_full[buf]));
     }
+  } else if constexpr (EPI == 16) {
+    // =========================================== epilogue, 16 warps ===================================================
+    // Shapes the host selects it for: bf16 hi (+ lo) outputs through the TMA unit, optional aligned bias, activation, optional
+    // bf16 relu mask; no fp32 output, no split-K.  Warp w: TMEM lane quadrant w & 3, group w >> 2 = (column half) * 2 + buffer.
+    // A pass is 32 columns: TMEM -> bias / act -> bf16 hi + lo words (mask ANDed in) -> a 32 x 32 staging tile (64-byte
+    // rows, 64-byte swizzle) -> one bulk tensor store; hi and lo take the tile in turn.
+    const int group = warp >> 2, quad = warp & 3;
+    const uint32_t buf = (uint32_t)(group & 1), half = (uint32_t)(group >> 1);
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * 256;
+    const uint32_t stg = stg_base + (uint32_t)warp * 2048u;
+    auto sw64 = [](int r, int ch) { return (uint32_t)r * 64u + (uint32_t)((ch ^ ((r >> 1) & 3)) << 4); };
+    const __nv_bfloat16* mask = reinterpret_cast<const __nv_bfloat16*>(d.mask);
+    const int half_cols = p.bn >> 1;
+    uint32_t item = buf;
+    bool stg_busy = false;
+    auto stg_acquire = [&]() {
+      if (stg_busy) {
+        if (lane == 0) tma_store_wait_read();
+        __syncwarp();
+        stg_busy = false;
+      }
+    };
+    for (int64_t it = blockIdx.x + (int64_t)buf * gridDim.x; it < n_items; it += 2 * (int64_t)gridDim.x, item += 2) {
+      const int m_tile = (int)(it % p.m_tiles);
+      const int n_tile = (int)((it / p.m_tiles) % p.n_tiles);
+      const int64_t row0 = (int64_t)m_tile * 128 + quad * 32;
+      const int64_t n0 = (int64_t)n_tile * p.bn + half * half_cols;
+      mbar_wait(smem_u32(&bars->acc_full[buf]), (item >> 1) & 1u);
+      __syncwarp();
+      tc_fence_after();
+      for (int cb = 0; cb < half_cols / 32; ++cb) {
+        const int64_t c0 = n0 + cb * 32;
+        if (c0 >= d.N) break;                                   // (N is a multiple of 32 here: whole passes only)
+        if (mask != nullptr) {
+          stg_acquire();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int q = lane + 32 * i, r = q >> 2, ch = q & 3;
+            uint4 m = make_uint4(0u, 0u, 0u, 0u);
+            if (row0 + r < d.M) m = __ldg(reinterpret_cast<const uint4*>(mask + (row0 + r) * d.ld_mask + c0 + 8 * ch));
+            st_shared_v4(stg + sw64(r, ch), m.x, m.y, m.z, m.w);
+          }
+          __syncwarp();
+        }
+        uint32_t ra[32];
+        tmem_ld32(lane_addr + half * half_cols + cb * 32, ra);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(ra[j]);
+        if (d.bias != nullptr) {
+          const float4* b4 = reinterpret_cast<const float4*>(d.bias + c0);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const float4 bq = __ldg(b4 + k);
+            v[4 * k] += bq.x; v[4 * k + 1] += bq.y; v[4 * k + 2] += bq.z; v[4 * k + 3] += bq.w;
+          }
+        }
+        if (d.act == 1) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        } else if (d.act == 2) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 1.f / (1.f + __expf(-v[j]));
+        }
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          hi[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+          lo[j] = residual16x2<false>(v[2 * j], v[2 * j + 1], hi[j]);
+        }
+        if (mask != nullptr) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            uint32_t m[4];
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(m[0]), "=r"(m[1]), "=r"(m[2]), "=r"(m[3]) : "r"(stg + sw64(lane, k)));
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const uint32_t sel = __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&m[e]), __float2bfloat162_rn(0.f));
+              hi[4 * k + e] &= sel;
+              lo[4 * k + e] &= sel;
+            }
+          }
+        }
+        for (int part = 0; part < (d.out_lo != nullptr ? 2 : 1); ++part) {
+          stg_acquire();                                        // (own-row mask reads above are done: the tile may be overwritten)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (part == 0) st_shared_v4(stg + sw64(lane, k), hi[4 * k], hi[4 * k + 1], hi[4 * k + 2], hi[4 * k + 3]);
+            else st_shared_v4(stg + sw64(lane, k), lo[4 * k], lo[4 * k + 1], lo[4 * k + 2], lo[4 * k + 3]);
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) tma_store_2d(&p.omap[part], stg, (int)c0, (int)row0);
+          stg_busy = true;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bars->acc_empty[buf]));
+    }
+    if (lane == 0) tma_store_wait_all();
   } else {
     // =========================================== epilogue ============================================================
     // two groups of four warps: group g drains accumulator buffer g, i.e. this CTA's items g, g + 2, ... -- two tiles are
@@ -556,7 +673,7 @@ __global__ void __launch_bounds__(kGThreads, 1) gemm_bf16_kernel(const __grid_co
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == kMW) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
@@ -643,7 +760,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 struct MapKey {
   const void* ptr;
   int64_t rows, cols, ld;
-  int box_rows;
+  int box_rows;          // + 1000 * box columns when they are not 64 (the 32 x 32, 64-byte-swizzle boxes of the 16-warp epilogue)
   bool operator==(const MapKey& o) const { return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows; }
 };
 struct MapKeyHash {
@@ -660,7 +777,7 @@ static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_map_cache;
 static EncodeTiledFn g_encode = nullptr;
 
 // [rows][cols] bf16, row stride ld elements; boxes of box_rows x 64 columns, 128-byte swizzle, zero fill out of bounds
-static int make_map(CUtensorMap* out, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+static int make_map(CUtensorMap* out, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows, int box_cols = 64) {
   std::lock_guard<std::mutex> lock(g_map_mutex);
   if (!g_encode) {
     void* fn = nullptr;
@@ -672,7 +789,7 @@ static int make_map(CUtensorMap* out, const void* ptr, int64_t rows, int64_t col
     }
     g_encode = (EncodeTiledFn)fn;
   }
-  const MapKey key{ptr, rows, cols, ld, box_rows};
+  const MapKey key{ptr, rows, cols, ld, box_rows + (box_cols == 64 ? 0 : 1000 * box_cols)};
   auto it = g_map_cache.find(key);
   if (it != g_map_cache.end()) {
     *out = it->second;
@@ -680,10 +797,11 @@ static int make_map(CUtensorMap* out, const void* ptr, int64_t rows, int64_t col
   }
   const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   const cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
-  const cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+  const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1u, 1u};
   CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                        box_cols == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("gemm: cuTensorMapEncodeTiled failed (%d) for a %lld x %lld matrix with row stride %lld, box %d x 64", (int)r, (long long)rows,
               (long long)cols, (long long)ld, box_rows);
@@ -741,6 +859,13 @@ extern "C" int nb2_gemm_bf16(nb2_handle* h, const nb2_gemm_desc* d, void* stream
     if (!same) p.fused3 = 0;
   }
   if (h->tc_debug & 8) p.fused3 = 0;      // NB2_TC_DEBUG & 8 (A/B timing): every pass loads its own tiles
+  p.reuse3 = 0;
+  if (!p.fused3 && d->n_seg == 3 && splits == 1 && !(h->tc_debug & 8)) {
+    const nb2_gemm_operand &a1 = d->seg[1].a, &a2 = d->seg[2].a, &b0 = d->seg[0].b, &b2 = d->seg[2].b;
+    p.reuse3 = d->seg[0].K == 64 * kGStages && d->seg[1].K == d->seg[0].K && d->seg[2].K == d->seg[0].K && a1.ptr == a2.ptr && a1.ld == a2.ld &&
+               a1.mn_major == a2.mn_major && b0.ptr == b2.ptr && b0.ld == b2.ld && b0.mn_major == b2.mn_major &&
+               d->seg[0].a.mn_major == a1.mn_major && d->seg[1].b.mn_major == b0.mn_major;
+  }
   p.rowsum = 0;
   if (d->a_rowsum_out) {
     const int64_t n_items = (int64_t)p.m_tiles * p.n_tiles * splits;
@@ -750,7 +875,7 @@ extern "C" int nb2_gemm_bf16(nb2_handle* h, const nb2_gemm_desc* d, void* stream
     p.rowsum = 1;
   }
   p.dbg = h->tc_debug;
-  int rc = kernel_set_smem(h, (const void*)gemm_bf16_kernel, kGSmem);
+  int rc = kernel_set_smem(h, (const void*)gemm_bf16_kernel<8>, kGSmem);
   if (rc != NB2_OK) return rc;
   for (int s = 0; s < d->n_seg; ++s) {
     const nb2_gemm_operand& A = d->seg[s].a;
@@ -763,19 +888,30 @@ extern "C" int nb2_gemm_bf16(nb2_handle* h, const nb2_gemm_desc* d, void* stream
     if (rc != NB2_OK) return rc;
   }
   p.tma_out = 0;
-  if (d->out_hi && (d->ld_16 & 7) == 0 && (d->N & 7) == 0 && ((uintptr_t)d->out_hi & 15) == 0 && (!d->out_lo || ((uintptr_t)d->out_lo & 15) == 0) &&
-      !(h->tc_debug & 64)) {                // NB2_TC_DEBUG & 64 (A/B timing): stores through the copy loops
-    rc = make_map(&p.omap[0], d->out_hi, d->M, d->N, d->ld_16, 32);
+  const bool tma_ok = d->out_hi && (d->ld_16 & 7) == 0 && (d->N & 7) == 0 && ((uintptr_t)d->out_hi & 15) == 0 &&
+                      (!d->out_lo || ((uintptr_t)d->out_lo & 15) == 0) && !(h->tc_debug & 64);   // NB2_TC_DEBUG & 64 (A/B timing): copy loops
+  // the 16-warp epilogue: bf16 outputs only, whole 32-column passes, two column halves per tile, vector-aligned bias / mask
+  const bool epi16 = tma_ok && !d->out_f32 && splits == 1 && (d->N & 31) == 0 && (p.bn & 63) == 0 && (!d->bias || ((uintptr_t)d->bias & 15) == 0) &&
+                     (!d->mask || ((d->ld_mask & 7) == 0 && ((uintptr_t)d->mask & 15) == 0)) && d->M >= 8192 && !(h->tc_debug & 256);   // NB2_TC_DEBUG & 256 (A/B timing): the 8-warp epilogue
+  if (tma_ok) {
+    const int bc = epi16 ? 32 : 64;
+    rc = make_map(&p.omap[0], d->out_hi, d->M, d->N, d->ld_16, 32, bc);
     if (rc != NB2_OK) return rc;
     if (d->out_lo) {
-      rc = make_map(&p.omap[1], d->out_lo, d->M, d->N, d->ld_16, 32);
+      rc = make_map(&p.omap[1], d->out_lo, d->M, d->N, d->ld_16, 32, bc);
       if (rc != NB2_OK) return rc;
     }
     p.tma_out = 1;
   }
   const int64_t items = (int64_t)p.m_tiles * p.n_tiles * splits;
   const int grid = (int)std::min<int64_t>(items, h->sm_count);
-  gemm_bf16_kernel<<<grid, kGThreads, kGSmem, (cudaStream_t)stream>>>(p);
+  if (epi16) {
+    rc = kernel_set_smem(h, (const void*)gemm_bf16_kernel<16>, kGSmem);
+    if (rc != NB2_OK) return rc;
+    gemm_bf16_kernel<16><<<grid, 32 * 18, kGSmem, (cudaStream_t)stream>>>(p);
+  } else {
+    gemm_bf16_kernel<8><<<grid, kGThreads, kGSmem, (cudaStream_t)stream>>>(p);
+  }
   NB2_LAUNCH_CHECK(h);
   return NB2_OK;
 }

@@ -87,6 +87,44 @@ def test_wgrad_shape(rows, N_out, K_in, splits):
     assert torch.equal(out, again)          # no atomics: bit-reproducible
 
 
+@pytest.mark.parametrize("M,K,N", [(8192, 256, 256), (8229, 256, 128), (20000, 64, 64), (9000, 320, 512), (8197, 256, 320), (8192, 128, 32)])
+@pytest.mark.parametrize("act", [linear.ACT_NONE, linear.ACT_RELU, linear.ACT_SIGMOID])
+def test_bf16_output_shapes_of_the_sixteen_warp_epilogue(M, K, N, act):
+    """The shapes the training step and Ref-NeRF run most: bf16 hi (+ lo) outputs only, M >= 8192 -- N = 64 / 128 / 256 / 512
+    take the 16-warp epilogue (two column halves per tile, 32-column passes, 64-byte-swizzled staging tiles, TMA stores),
+    N = 320 (two 160-wide tiles) and N = 32 the 8-warp one; ragged M (rows clipped by the TMA unit), split-precision passes,
+    bias + every activation, hi only and hi + lo; outputs land inside a wider buffer without touching its other columns."""
+    X, W, b = rnd((M, K), 1), rnd((N, K), 2, K ** -0.5), rnd((N,), 3)
+    xh, xl = linear.to_bf16(X)
+    wh, wl = linear.to_bf16(W)
+    pre = (X.double() @ W.double().T + b.double())
+    ref = {linear.ACT_NONE: pre, linear.ACT_RELU: torch.relu(pre), linear.ACT_SIGMOID: torch.sigmoid(pre)}[act].float()
+    segs = [(xl, False, wh, False, K), (xh, False, wl, False, K), (xh, False, wh, False, K)]
+    wide_hi = torch.full((M, N + 64), 7.0, dtype=torch.bfloat16, device=DEV)
+    wide_lo = torch.full((M, N + 64), 7.0, dtype=torch.bfloat16, device=DEV)
+    linear.gemm(M, N, segs, bias=b, act=act, out_hi=wide_hi[:, 32:32 + N], out_lo=wide_lo[:, 32:32 + N])
+    close(wide_hi[:, 32:32 + N].float() + wide_lo[:, 32:32 + N].float(), ref, 3e-5)
+    for w in (wide_hi, wide_lo):
+        assert float((w[:, :32].float() - 7.0).abs().max()) == 0.0 and float((w[:, 32 + N:].float() - 7.0).abs().max()) == 0.0
+    only = torch.empty((M, N), dtype=torch.bfloat16, device=DEV)
+    linear.gemm(M, N, segs, bias=b, act=act, out_hi=only)
+    assert torch.equal(only, wide_hi[:, 32:32 + N])
+
+
+@pytest.mark.parametrize("M,N_out,K_in", [(8192, 256, 256), (8300, 256, 128), (30011, 128, 256), (8192, 256, 512)])
+def test_dgrad_shape_of_the_sixteen_warp_epilogue(M, N_out, K_in):
+    """dX = (dY W) * (X > 0) at M >= 8192: relu mask staged per 32-column pass and applied to the packed hi / lo words."""
+    dY, W, Xs = rnd((M, N_out), 1), rnd((N_out, K_in), 2, 0.06), bf(rnd((M, K_in), 3))
+    dh, dl = linear.to_bf16(dY)
+    wh, wl = linear.to_bf16(W)
+    ref = ((dY.double() @ W.double()) * (Xs.double() > 0)).float()
+    hi = torch.empty((M, K_in), dtype=torch.bfloat16, device=DEV)
+    lo = torch.empty((M, K_in), dtype=torch.bfloat16, device=DEV)
+    linear.gemm(M, K_in, [(dl, False, wh, True, N_out), (dh, False, wl, True, N_out), (dh, False, wh, True, N_out)], mask=Xs, out_hi=hi, out_lo=lo)
+    close(hi.float() + lo.float(), ref, 3e-5)
+    assert float((hi.float() + lo.float())[Xs.float() <= 0].abs().max()) == 0.0
+
+
 def test_to_bf16_permutation():
     W = rnd((256, 319), 5)
     perm = torch.cat((torch.arange(63) + 256, torch.arange(256))).to(torch.int32).to(DEV)     # [enc | hidden] -> [hidden | enc]
