@@ -445,6 +445,9 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) mlp_tc4_kernel(const __grid
           for (int e = 0; e < 3 * L.kc; ++e) {
             const int k = e < 2 * L.kc ? (e >> 1) : e - 2 * L.kc;
             const int part = e < 2 * L.kc ? (e & 1) : 0;
+            // a bias-only chunk (ks0 != 0: its A column is the constant 1, whose lo half is 0) has no lo x Wh term: its Wh
+            // tile is not streamed in the cross-term sweep (the issuer and the relay skip the same entry)
+            if (e < 2 * L.kc && part == 0 && L.ks0[k] != 0) continue;
             mbar_wait(smem_u32(&misc->w_empty[stage]), phase ^ 1u);
             const uint32_t full = smem_u32(&misc->w_full[stage]);
             mbar_arrive_expect_tx(full, bytes);
@@ -462,7 +465,8 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) mlp_tc4_kernel(const __grid
       uint32_t stage = 0, phase = 0;
       for (int64_t it = 0; it < n_iters; ++it)
         for (int l = 0; l < net.n_layers; ++l) {
-          const int n_entries = 3 * net.layer[l].kc;
+          int n_entries = 3 * net.layer[l].kc;
+          for (int k = 0; k < net.layer[l].kc; ++k) n_entries -= (net.layer[l].ks0[k] != 0);   // bias-only chunks: no Wh in sweep 1
           for (int e = 0; e < n_entries; ++e) {
             mbar_wait(smem_u32(&misc->w_full[stage]), phase);
             mbar_arrive_remote_relaxed(smem_u32(&misc->w_full[stage]), 0);
@@ -531,10 +535,12 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) mlp_tc4_kernel(const __grid
           // sweep 1: the small cross terms lo x Wh and hi x Wl
           for (int k = 0; k < L.kc; ++k) {
             if (L.a_src[k] != kChunkE) wait_chunk(L.a_src[k]);
-            wait_stage();
-            // (bias-only chunk: its A column is the constant 1, whose lo half is 0 -- no lo x Wh term)
-            if (L.ks0[k] == 0) issue_chunk(L.a_src[k], 0, true, idesc, k == 0);
-            release_stage();
+            // (bias-only chunk: its A column is the constant 1, whose lo half is 0 -- no lo x Wh term, no Wh stage)
+            if (L.ks0[k] == 0) {
+              wait_stage();
+              issue_chunk(L.a_src[k], 0, true, idesc, k == 0);
+              release_stage();
+            }
             wait_stage();
             issue_chunk(L.a_src[k], L.ks0[k], false, idesc, false);
             release_stage();
