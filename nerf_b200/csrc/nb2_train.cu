@@ -66,8 +66,9 @@ __global__ void __launch_bounds__(3 * kEncPts)
 encode3_bf16_kernel(const float* __restrict__ x, int x_stride, int x_col0, int64_t n, int levels, int normalize,
                     __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int64_t ld, int width) {
   extern __shared__ __align__(16) unsigned char enc_smem[];
-  __nv_bfloat16* t_hi = reinterpret_cast<__nv_bfloat16*>(enc_smem);              // [kEncPts][width]
-  __nv_bfloat16* t_lo = t_hi + kEncPts * width;
+  const int pitch = width + 8;                     // 16-byte aligned rows that do not all start in the same bank
+  __nv_bfloat16* t_hi = reinterpret_cast<__nv_bfloat16*>(enc_smem);              // [kEncPts][pitch]
+  __nv_bfloat16* t_lo = t_hi + kEncPts * pitch;
   const int64_t p0 = (int64_t)blockIdx.x * kEncPts;
   const int npts = (int)min((int64_t)kEncPts, n - p0);
   const int t = threadIdx.x;
@@ -79,8 +80,8 @@ encode3_bf16_kernel(const float* __restrict__ x, int x_stride, int x_col0, int64
       const float d[3] = {__ldg(src), __ldg(src + 1), __ldg(src + 2)};
       v = __fdiv_rn(v, dir_norm3(d));
     }
-    __nv_bfloat16* rh = t_hi + p * width;
-    __nv_bfloat16* rl = t_lo + p * width;
+    __nv_bfloat16* rh = t_hi + p * pitch;
+    __nv_bfloat16* rl = t_lo + p * pitch;
     auto put = [&](int c, float val) {
       const __nv_bfloat16 h = __float2bfloat16_rn(val);
       rh[c] = h;
@@ -103,8 +104,8 @@ encode3_bf16_kernel(const float* __restrict__ x, int x_stride, int x_col0, int64
   for (int q = t; q < npts * cpr; q += 3 * kEncPts) {
     const int row = q / cpr, ch = q - row * cpr;
     const int64_t off = (p0 + row) * ld + ch * 8;
-    *reinterpret_cast<uint4*>(hi + off) = *reinterpret_cast<const uint4*>(t_hi + row * width + ch * 8);
-    if (lo) *reinterpret_cast<uint4*>(lo + off) = *reinterpret_cast<const uint4*>(t_lo + row * width + ch * 8);
+    *reinterpret_cast<uint4*>(hi + off) = *reinterpret_cast<const uint4*>(t_hi + row * pitch + ch * 8);
+    if (lo) *reinterpret_cast<uint4*>(lo + off) = *reinterpret_cast<const uint4*>(t_lo + row * pitch + ch * 8);
   }
 }
 
@@ -307,7 +308,7 @@ extern "C" int nb2_encode_bf16(nb2_handle* h, const float* x, int x_stride, int 
   if (n == 0) return NB2_OK;
   NB2_CHECK_ARG(x && hi && n > 0 && x_stride >= x_col0 + 3 && levels >= 0 && levels <= 16 && width >= 3 + 6 * levels && ld >= width,
                 "encode_bf16: bad arguments");
-  const size_t tile_bytes = (size_t)kEncPts * width * 2 * sizeof(__nv_bfloat16);
+  const size_t tile_bytes = (size_t)kEncPts * (width + 8) * 2 * sizeof(__nv_bfloat16);
   if ((width & 7) == 0 && (ld & 7) == 0 && ((uintptr_t)hi & 15) == 0 && (!lo || ((uintptr_t)lo & 15) == 0) && tile_bytes <= 48 * 1024) {
     encode3_bf16_kernel<<<grid_for(n, kEncPts), 3 * kEncPts, tile_bytes, (cudaStream_t)stream>>>(x, x_stride, x_col0, n, levels, normalize,
                                                                                               (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, ld, width);
