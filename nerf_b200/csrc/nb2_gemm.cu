@@ -127,6 +127,7 @@ __device__ __forceinline__ uint32_t gemm_idesc(int N, bool a_mn, bool b_mn) {
 template <int EPI>
 __global__ void __launch_bounds__(32 * (EPI + 2), 1) gemm_bf16_kernel(const __grid_constant__ GemmKParams p) {
   constexpr int kPW = EPI == 8 ? 4 : 16, kMW = EPI == 8 ? 5 : 17;     // producer / MMA warp (EPI == 8 keeps warps 0-3, 6-9 as epilogue)
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");     // the next kernel of the stream may be scheduled as SMs free up
   extern __shared__ unsigned char smem_dyn[];
   const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   unsigned char* smem_al = smem_dyn + (smem_base - smem_u32(smem_dyn));
@@ -163,6 +164,10 @@ __global__ void __launch_bounds__(32 * (EPI + 2), 1) gemm_bf16_kernel(const __gr
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
+  // Programmatic dependent launch: consecutive GEMMs of a launch plan are launched with the stream-serialization attribute,
+  // so this CTA may have started (barriers, tensor memory, the prologue above) while the previous kernel of the stream was
+  // still draining its last tiles on other SMs; nothing before this point touches global memory.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   // the K range of one work item inside segment s (split-K shares the range across the segments)
   auto k_range = [&](int s, int split, int64_t& k0, int64_t& k1) {
@@ -905,12 +910,23 @@ extern "C" int nb2_gemm_bf16(nb2_handle* h, const nb2_gemm_desc* d, void* stream
   }
   const int64_t items = (int64_t)p.m_tiles * p.n_tiles * splits;
   const int grid = (int)std::min<int64_t>(items, h->sm_count);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.dynamicSmemBytes = kGSmem;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = (h->tc_debug & 512) ? 0 : 1;    // NB2_TC_DEBUG & 512 (A/B timing): plain launches
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
   if (epi16) {
     rc = kernel_set_smem(h, (const void*)gemm_bf16_kernel<16>, kGSmem);
     if (rc != NB2_OK) return rc;
-    gemm_bf16_kernel<16><<<grid, 32 * 18, kGSmem, (cudaStream_t)stream>>>(p);
+    cfg.blockDim = dim3(32 * 18);
+    NB2_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<16>, p));
   } else {
-    gemm_bf16_kernel<8><<<grid, kGThreads, kGSmem, (cudaStream_t)stream>>>(p);
+    cfg.blockDim = dim3(kGThreads);
+    NB2_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<8>, p));
   }
   NB2_LAUNCH_CHECK(h);
   return NB2_OK;
