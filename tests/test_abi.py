@@ -46,6 +46,33 @@ def test_render_params_struct_matches_header():
     assert _lib.load().nb2_render_workspace_bytes(1000, ctypes.byref(p)) == 2 * 256000 + 512000 + 256 + 2048000
 
 
+def test_ctypes_structs_match_the_header_as_compiled_by_gcc(tmp_path):
+    """Every struct that crosses the C ABI by pointer: sizeof and the offsets of the last fields as a C compiler lays out
+    include/nerf_b200.h must equal the ctypes mirrors in nerf_b200/_lib.py (a field added on one side only shifts everything
+    after it silently)."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "abi.c"
+    src.write_text(r"""
+#include <stdio.h>
+#include <stddef.h>
+#include "nerf_b200.h"
+int main(void) {
+  printf("%zu %zu %zu %zu %zu %zu %zu\n", sizeof(nb2_render_params), sizeof(nb2_gemm_desc), offsetof(nb2_gemm_desc, split_stride),
+         offsetof(nb2_gemm_desc, a_rowsum_out), offsetof(nb2_gemm_desc, a_rowsum_stride), sizeof(nb2_reduce_desc), offsetof(nb2_reduce_desc, out));
+  return 0;
+}
+""")
+    exe = tmp_path / "abi"
+    subprocess.run(["gcc", "-I", os.path.join(root, "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    G, R = _lib.GemmDesc, _lib.ReduceDesc
+    want = [ctypes.sizeof(_lib.RenderParams), ctypes.sizeof(G), G.split_stride.offset, G.a_rowsum_out.offset, G.a_rowsum_stride.offset,
+            ctypes.sizeof(R), R.out.offset]
+    assert got == want, (got, want)
+
+
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
 def test_fails_loudly_without_gpu():
     with pytest.raises(nerf_b200.NB2Error):
