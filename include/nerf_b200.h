@@ -306,6 +306,16 @@ int nb2_gemm_bf16(nb2_handle* h, const nb2_gemm_desc* d, void* stream);
  * col_perm (device, cols ints, or NULL): destination column of every source column. */
 int nb2_to_bf16(nb2_handle* h, const float* src, int64_t rows, int cols, int64_t ld_src, const int* col_perm, void* hi, void* lo,
                 int ld_dst, void* stream);
+/* The same for an array of matrices in one launch per 32 descriptors (the weight images of a network after an optimizer step). */
+typedef struct nb2_to_bf16_desc {
+  const float* src;
+  int64_t rows, ld_src;
+  int cols, ld_dst;
+  const int* col_perm;
+  void* hi;
+  void* lo;
+} nb2_to_bf16_desc;
+int nb2_to_bf16_batch(nb2_handle* h, const nb2_to_bf16_desc* descs, int n, void* stream);
 /* out[m][c] (=|+=) sum_s ws[s * split_stride + m * ld_ws + perm(c)]: second stage of the split-K wgrad. */
 int nb2_reduce_splits(nb2_handle* h, const float* ws, int splits, int64_t split_stride, int rows, int cols, int ld_ws,
                       const int* col_perm, float* out, int ld_out, int accumulate, void* stream);

@@ -67,6 +67,11 @@ class GemmDesc(ctypes.Structure):
     ]
 
 
+class ToBf16Desc(ctypes.Structure):
+    """Mirror of nb2_to_bf16_desc."""
+    _fields_ = [("src", c_vp), ("rows", c_i64), ("ld_src", c_i64), ("cols", c_int), ("ld_dst", c_int), ("col_perm", c_vp), ("hi", c_vp), ("lo", c_vp)]
+
+
 class ReduceDesc(ctypes.Structure):
     """Mirror of nb2_reduce_desc."""
     _fields_ = [
@@ -88,6 +93,7 @@ SIGNATURES = {
     "nb2_net_destroy": (c_int, [c_vp, c_int]),
     "nb2_gemm_bf16": (c_int, [c_vp, ctypes.POINTER(GemmDesc), c_vp]),
     "nb2_to_bf16": (c_int, [c_vp, c_f32p, c_i64, c_int, c_i64, c_vp, c_vp, c_vp, c_int, c_vp]),
+    "nb2_to_bf16_batch": (c_int, [c_vp, c_vp, c_int, c_vp]),
     "nb2_reduce_splits": (c_int, [c_vp, c_f32p, c_int, c_i64, c_int, c_int, c_int, c_vp, c_f32p, c_int, c_int, c_vp]),
     "nb2_gemm_bf16_batch": (c_int, [c_vp, c_vp, c_int, c_vp]),
     "nb2_reduce_splits_batch": (c_int, [c_vp, c_vp, c_int, c_vp]),

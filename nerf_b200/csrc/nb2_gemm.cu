@@ -709,6 +709,35 @@ __global__ void to_bf16_kernel(const float* __restrict__ src, int64_t rows, int 
   }
 }
 
+// every conversion of a launch in one grid: blockIdx.y selects the descriptor (a training step converts ~16-35 weight matrices
+// after each optimizer step; one launch each cost more than the conversions themselves)
+constexpr int kToBf16Batch = 32;
+struct ToBf16Batch {
+  nb2_to_bf16_desc d[kToBf16Batch];
+};
+__global__ void to_bf16_batch_kernel(const __grid_constant__ ToBf16Batch b) {
+  const nb2_to_bf16_desc& d = b.d[blockIdx.y];
+  __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(d.hi);
+  __nv_bfloat16* lo = reinterpret_cast<__nv_bfloat16*>(d.lo);
+  const int64_t n = d.rows * d.ld_dst;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / d.ld_dst;
+    const int c = (int)(i - r * d.ld_dst);
+    if (c >= d.cols) {
+      if (d.col_perm == nullptr) {
+        hi[i] = __float2bfloat16_rn(0.f);
+        if (lo) lo[i] = __float2bfloat16_rn(0.f);
+      }
+      continue;
+    }
+    const float v = d.src[r * d.ld_src + c];
+    const int64_t o = d.col_perm ? r * d.ld_dst + d.col_perm[c] : i;
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    hi[o] = h;
+    if (lo) lo[o] = __float2bfloat16_rn(v - __bfloat162float(h));
+  }
+}
+
 // out[m][c] (fp32, row stride ld_out, c < cols) = sum over splits of ws[s][m][perm(c)] (row stride ld_ws): the
 // deterministic second stage of the split-K wgrad (no atomics: gradients are bit-reproducible run to run).
 // Eight independent loads in flight per thread (one dependent load per split made the kernel latency-bound: 36 us for a
@@ -941,6 +970,27 @@ extern "C" int nb2_to_bf16(nb2_handle* h, const float* src, int64_t rows, int co
   const int blocks = (int)std::min<int64_t>((n + 255) / 256, (int64_t)h->sm_count * 16);
   to_bf16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, rows, cols, ld_src, col_perm, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, ld_dst);
   NB2_LAUNCH_CHECK(h);
+  return NB2_OK;
+}
+
+extern "C" int nb2_to_bf16_batch(nb2_handle* h, const nb2_to_bf16_desc* d, int n, void* stream) {
+  NB2_ENTER(h);
+  NB2_CHECK_ARG(n >= 0 && (d != nullptr || n == 0), "to_bf16_batch: bad arguments");
+  for (int i0 = 0; i0 < n; i0 += kToBf16Batch) {
+    const int cnt = std::min(kToBf16Batch, n - i0);
+    ToBf16Batch b;
+    int64_t n_max = 0;
+    for (int i = 0; i < cnt; ++i) {
+      const nb2_to_bf16_desc& t = d[i0 + i];
+      NB2_CHECK_ARG(t.src && t.hi && t.rows > 0 && t.cols > 0 && t.ld_dst >= t.cols && (t.ld_dst & 7) == 0 && t.ld_src >= t.cols,
+                    "to_bf16_batch: bad descriptor %d", i0 + i);
+      b.d[i] = t;
+      n_max = std::max<int64_t>(n_max, t.rows * t.ld_dst);
+    }
+    const int blocks = (int)std::min<int64_t>((n_max + 255) / 256, (int64_t)h->sm_count * 2);
+    to_bf16_batch_kernel<<<dim3(blocks, cnt), 256, 0, (cudaStream_t)stream>>>(b);
+    NB2_LAUNCH_CHECK(h);
+  }
   return NB2_OK;
 }
 

@@ -24,7 +24,7 @@ from ._lib import check, handle, load, stream_ptr
 from .nerf_base import NeRF, _NormalDot
 from .nerf_helper import makeMLP
 from .ref_func import generate_ide_fn
-from .train_engine import PackedLinear, _dgrad_segs, _empty16, _fwd_segs, _pad8, bgrad, encode, wgrad
+from .train_engine import PackedLinear, _dgrad_segs, _empty16, _fwd_segs, _pad8, bgrad, encode, sync_all, wgrad
 
 
 class _PackedCat(PackedLinear):
@@ -130,8 +130,7 @@ class RefNeRF(NeRF):
             raise _lib.NB2Error(f"RefNeRF runs on the layer-wise engine: precision 'bf16x3' (default) or 'bf16', not {self.precision!r}")
         dev, n = pts2d.device, pts2d.shape[0]
         packed = self._packed()
-        for pk in packed:
-            pk.sync()
+        sync_all(packed)
         has_cam = cam_dir is not None
         plans = self.__dict__.setdefault("_nb2_ref_plans", {})
         key = (n, x3, dev, self.training, has_cam, bool(shift_softplus)) + tuple(pk.hi.data_ptr() for pk in packed)

@@ -71,6 +71,39 @@ class PackedLinear:
         return self.hi[:, c0:c1], self.lo[:, c0:c1]
 
 
+def sync_all(packed):
+    """Refresh every stale weight image of `packed` (PackedLinear list): images that already own their buffers are converted
+    by ONE launch (nb2_to_bf16_batch) -- after an optimizer step all of a network's matrices are stale at once -- the others
+    (first use, device change) through PackedLinear.sync()."""
+    stale = []
+    for p in packed:
+        if type(p) is not PackedLinear:      # packed heads (ref_model._PackedCat) concatenate several matrices first
+            p.sync()
+            continue
+        w = p.lin.weight
+        key = (w.data_ptr(), w._version, w.device)
+        if key == p.key:
+            continue
+        if p.hi is None or p.hi.device != w.device or (p.perm_host is not None and (p.perm is None or p.perm.device != w.device)):
+            p.sync()
+            continue
+        stale.append((p, w, key))
+    by_dev = {}
+    for item in stale:
+        by_dev.setdefault(item[1].device, []).append(item)
+    for dev, items in by_dev.items():
+        arr = (_lib.ToBf16Desc * len(items))()
+        for d, (p, w, _) in zip(arr, items):
+            wd = w.detach()
+            if wd.dtype != torch.float32 or wd.dim() != 2 or wd.stride(1) != 1:
+                raise _lib.NB2Error("sync_all: weights are 2-D fp32 tensors with unit column stride")
+            d.src, d.rows, d.ld_src, d.cols, d.ld_dst = wd.data_ptr(), wd.shape[0], wd.stride(0), wd.shape[1], p.in_pad
+            d.col_perm, d.hi, d.lo = _lib.ptr_int(p.perm), p.hi.data_ptr(), p.lo.data_ptr()
+        check(load().nb2_to_bf16_batch(handle(dev), arr, len(items), stream_ptr(dev)))
+        for p, _, key in items:
+            p.key = key
+
+
 def _fwd_segs(x, w, K, x3):
     """x, w: (hi, lo) pairs; small terms first."""
     if x3:
@@ -207,8 +240,7 @@ class _Engine:
         dev, n = pts.device, pts.shape[0]
         pts = pts.contiguous()
         plan = self._plan(n, x3, dev, want_dx)
-        for p in self.packed:
-            p.sync()
+        sync_all(self.packed)
         out = torch.empty((n, self.out_cols), dtype=torch.float32, device=dev)
         if plan.fwd is None:
             with linear.Program(dev) as prog:

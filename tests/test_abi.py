@@ -59,17 +59,18 @@ def test_ctypes_structs_match_the_header_as_compiled_by_gcc(tmp_path):
 #include <stddef.h>
 #include "nerf_b200.h"
 int main(void) {
-  printf("%zu %zu %zu %zu %zu %zu %zu\n", sizeof(nb2_render_params), sizeof(nb2_gemm_desc), offsetof(nb2_gemm_desc, split_stride),
-         offsetof(nb2_gemm_desc, a_rowsum_out), offsetof(nb2_gemm_desc, a_rowsum_stride), sizeof(nb2_reduce_desc), offsetof(nb2_reduce_desc, out));
+  printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(nb2_render_params), sizeof(nb2_gemm_desc), offsetof(nb2_gemm_desc, split_stride),
+         offsetof(nb2_gemm_desc, a_rowsum_out), offsetof(nb2_gemm_desc, a_rowsum_stride), sizeof(nb2_reduce_desc), offsetof(nb2_reduce_desc, out),
+         sizeof(nb2_to_bf16_desc), offsetof(nb2_to_bf16_desc, lo));
   return 0;
 }
 """)
     exe = tmp_path / "abi"
     subprocess.run(["gcc", "-I", os.path.join(root, "include"), str(src), "-o", str(exe)], check=True)
     got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
-    G, R = _lib.GemmDesc, _lib.ReduceDesc
+    G, R, T = _lib.GemmDesc, _lib.ReduceDesc, _lib.ToBf16Desc
     want = [ctypes.sizeof(_lib.RenderParams), ctypes.sizeof(G), G.split_stride.offset, G.a_rowsum_out.offset, G.a_rowsum_stride.offset,
-            ctypes.sizeof(R), R.out.offset]
+            ctypes.sizeof(R), R.out.offset, ctypes.sizeof(T), T.lo.offset]
     assert got == want, (got, want)
 
 
