@@ -216,6 +216,91 @@ __device__ __forceinline__ void slot_group_run4(const TcParams& p, Tc4Misc* misc
     tc_fence_before();
     arrive_a();
   };
+  // ---- alpha compositing over the rows of each ray (nerf_base.py:79-113), warpgroup 0 -------------------------------------
+  // Deferred: the rgb-layer epilogue only collects a row's colour sums and density; the sigmoids, the transmittance scan and
+  // the stores run one layer-window later, under the NEXT tile's layer-2 MMAs.  Done in place (as it was), this tail made the
+  // group ~4 k cycles late for the next tile's layer-0 epilogue -- layer 0 is 12 MMAs -- and the issuer waited 6.8 k cycles
+  // before layer 1 against ~2.1 k before the other layers (per-layer wait counters of the PROFILE build).
+  struct Pend { float sigma, c0, c1, c2, depth; int s; int64_t ray, grow; bool valid; };
+  Pend pend = {0.f, 0.f, 0.f, 0.f, 0.f, 0, 0, 0, false};
+  bool has_pend = false;
+  auto composite_tail = [&](const Pend& q) {
+    const float c0 = 1.f / (1.f + expf(-(q.c0 + __ldg(p.head + kHeadRgbB + 0))));
+    const float c1 = 1.f / (1.f + expf(-(q.c1 + __ldg(p.head + kHeadRgbB + 1))));
+    const float c2 = 1.f / (1.f + expf(-(q.c2 + __ldg(p.head + kHeadRgbB + 2))));
+    const int P = p.io.P;                 // 32, 64 or 128: rays cover whole warps
+    const int wpr = P >> 5;               // warps per ray
+    const int wseg = wq % wpr;            // this warp's position inside its ray
+    const float depth = q.depth;
+    float next = __shfl_down_sync(0xffffffffu, depth, 1);
+    if (lane == 0) scratch[wq * 8 + 0] = depth;
+    named_bar_sync(1, 128);
+    if (lane == 31 && wq < 3) next = scratch[(wq + 1) * 8 + 0];
+    const bool last = (q.s == P - 1);
+    const float delta = last ? 1e10f : __fsub_rn(next, depth);
+    const float m = q.valid ? expf(-fmaxf(q.sigma, 0.f) * delta) : 1.f;
+    const float alpha = 1.f - m;
+    const float inc = warp_scan_mul(m + 1e-10f, lane);
+    float exc = __shfl_up_sync(0xffffffffu, inc, 1);
+    if (lane == 0) exc = 1.f;
+    if (lane == 31) scratch[wq * 8 + 1] = inc;
+    named_bar_sync(1, 128);
+    float carry = 1.f;
+    for (int w = wq - wseg; w < wq; ++w) carry *= scratch[w * 8 + 1];
+    const float wgt = q.valid ? alpha * (carry * exc) : 0.f;
+    float sr = warp_sum(wgt * c0), sgn = warp_sum(wgt * c1), sb = warp_sum(wgt * c2);
+    float sa = warp_sum(wgt), sd = warp_sum(wgt * depth);
+    if (lane == 0) {
+      scratch[wq * 8 + 2] = sr; scratch[wq * 8 + 3] = sgn; scratch[wq * 8 + 4] = sb;
+      scratch[wq * 8 + 5] = sa; scratch[wq * 8 + 6] = sd;
+    }
+    named_bar_sync(1, 128);
+    if (lane == 0 && wseg == 0 && q.valid) {
+      for (int w = wq + 1; w < wq + wpr; ++w) {
+        sr += scratch[w * 8 + 2]; sgn += scratch[w * 8 + 3]; sb += scratch[w * 8 + 4];
+        sa += scratch[w * 8 + 5]; sd += scratch[w * 8 + 6];
+      }
+      if (p.io.flags & NB2_WHITE_BKG) {
+        const float bg = 1.f - sa;
+        sr += bg; sgn += bg; sb += bg;
+      }
+      p.io.rgb_out[q.ray * 3 + 0] = sr;
+      p.io.rgb_out[q.ray * 3 + 1] = sgn;
+      p.io.rgb_out[q.ray * 3 + 2] = sb;
+      // fused gather: the same row goes to every peer GPU's image buffer over NVLink (nb2_render_params.peer_rgb)
+      for (int k = 0; k < p.io.n_peers; ++k) {
+        float* o = p.io.peer_rgb[k] + (p.io.peer_row0 + q.ray) * 3;
+        o[0] = sr; o[1] = sgn; o[2] = sb;
+      }
+      if (p.io.depth_out) p.io.depth_out[q.ray] = (sd - p.io.near_t) / (p.io.far_t - p.io.near_t);
+      if (p.io.acc_out) p.io.acc_out[q.ray] = sa;
+    }
+    named_bar_sync(1, 128);  // scratch is reused by the next tile
+  };
+
+  // every warpgroup: meet, then warpgroup 0 adds the parked partial sums of the others and finishes the row
+  auto finish_rgb = [&](const Pend& q0) {
+    named_bar_sync(3, 128 * NG);
+    if (g != 0) return;
+    Pend q = q0;
+    const uint32_t xaddr = park_base + (uint32_t)row * 16u;
+#pragma unroll
+    for (int k = 0; k < NG - 1; ++k) {
+      uint32_t x0, x1, x2, x3;
+      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3)
+                   : "r"(xaddr + (uint32_t)k * (kTileRows * 16)));
+      q.sigma += __uint_as_float(x0); q.c0 += __uint_as_float(x1); q.c1 += __uint_as_float(x2); q.c2 += __uint_as_float(x3);
+    }
+    if (p.io.out_mode == 1) {
+      const float c0 = 1.f / (1.f + expf(-(q.c0 + __ldg(p.head + kHeadRgbB + 0))));
+      const float c1 = 1.f / (1.f + expf(-(q.c1 + __ldg(p.head + kHeadRgbB + 1))));
+      const float c2 = 1.f / (1.f + expf(-(q.c2 + __ldg(p.head + kHeadRgbB + 2))));
+      if (q.valid) reinterpret_cast<float4*>(p.io.out)[q.grow] = make_float4(c0, c1, c2, q.sigma);
+    } else {
+      composite_tail(q);
+    }
+  };
+
   RowIn in = load_row(p.io, tile_of(0) * kTileRows + row);
   enc_compute(enc, in.p, p.pos_levels, in.valid, in.enc, in.ipe ? in.cov : nullptr);
   begin_tile();
@@ -259,81 +344,19 @@ __device__ __forceinline__ void slot_group_run4(const TcParams& p, Tc4Misc* misc
           }
         }
         // the accumulator has been read and the encoding tile is free: hand the next tile to the issuer before the rest
-        // of this epilogue (head, compositing) so that its first layer runs underneath
+        // of this epilogue (collecting the heads, compositing), which runs one layer-window later (finish_rgb)
         if (has_next) begin_tile();
-        // combine the column groups: warpgroups 1.. park their partial sums (and their part of the density dot product)
+        // combine the column groups: warpgroups 1.. park their partial sums (and their part of the density dot product);
+        // warpgroup 0 collects them in finish_rgb -- one layer-window later when another tile follows
         const uint32_t xaddr = park_base + (uint32_t)row * 16u;
         if (g != 0) st_shared_v4(xaddr + (uint32_t)(g - 1) * (kTileRows * 16), __float_as_uint(sigma), __float_as_uint(c0),
                                  __float_as_uint(c1), __float_as_uint(c2));
-        named_bar_sync(3, 128 * NG);
-        if (g == 0) {
-#pragma unroll
-          for (int q = 0; q < NG - 1; ++q) {
-            uint32_t x0, x1, x2, x3;
-            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3)
-                         : "r"(xaddr + (uint32_t)q * (kTileRows * 16)));
-            sigma += __uint_as_float(x0); c0 += __uint_as_float(x1); c1 += __uint_as_float(x2); c2 += __uint_as_float(x3);
-          }
-        }
-        if (g == 0) {
-          c0 = 1.f / (1.f + expf(-(c0 + __ldg(p.head + kHeadRgbB + 0))));
-          c1 = 1.f / (1.f + expf(-(c1 + __ldg(p.head + kHeadRgbB + 1))));
-          c2 = 1.f / (1.f + expf(-(c2 + __ldg(p.head + kHeadRgbB + 2))));
-          if (p.io.out_mode == 1) {
-            if (in.valid) reinterpret_cast<float4*>(p.io.out)[grow] = make_float4(c0, c1, c2, sigma);
-          } else {
-            // ---- alpha compositing over the rows of each ray (nerf_base.py:79-113) -------------
-            const int P = p.io.P;                 // 32, 64 or 128: rays cover whole warps
-            const int wpr = P >> 5;               // warps per ray
-            const int wseg = wq % wpr;            // this warp's position inside its ray
-            const float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(in.d[0], in.d[0]), __fmul_rn(in.d[1], in.d[1])),
-                                              __fmul_rn(in.d[2], in.d[2])));
-            const float depth = __fmul_rn(in.z, nrm);
-            float next = __shfl_down_sync(0xffffffffu, depth, 1);
-            if (lane == 0) scratch[wq * 8 + 0] = depth;
-            named_bar_sync(1, 128);
-            if (lane == 31 && wq < 3) next = scratch[(wq + 1) * 8 + 0];
-            const bool last = (in.s == P - 1);
-            const float delta = last ? 1e10f : __fsub_rn(next, depth);
-            const float m = in.valid ? expf(-fmaxf(sigma, 0.f) * delta) : 1.f;
-            const float alpha = 1.f - m;
-            const float inc = warp_scan_mul(m + 1e-10f, lane);
-            float exc = __shfl_up_sync(0xffffffffu, inc, 1);
-            if (lane == 0) exc = 1.f;
-            if (lane == 31) scratch[wq * 8 + 1] = inc;
-            named_bar_sync(1, 128);
-            float carry = 1.f;
-            for (int w = wq - wseg; w < wq; ++w) carry *= scratch[w * 8 + 1];
-            const float wgt = in.valid ? alpha * (carry * exc) : 0.f;
-            float sr = warp_sum(wgt * c0), sgn = warp_sum(wgt * c1), sb = warp_sum(wgt * c2);
-            float sa = warp_sum(wgt), sd = warp_sum(wgt * depth);
-            if (lane == 0) {
-              scratch[wq * 8 + 2] = sr; scratch[wq * 8 + 3] = sgn; scratch[wq * 8 + 4] = sb;
-              scratch[wq * 8 + 5] = sa; scratch[wq * 8 + 6] = sd;
-            }
-            named_bar_sync(1, 128);
-            if (lane == 0 && wseg == 0 && in.valid) {
-              for (int w = wq + 1; w < wq + wpr; ++w) {
-                sr += scratch[w * 8 + 2]; sgn += scratch[w * 8 + 3]; sb += scratch[w * 8 + 4];
-                sa += scratch[w * 8 + 5]; sd += scratch[w * 8 + 6];
-              }
-              if (p.io.flags & NB2_WHITE_BKG) {
-                const float bg = 1.f - sa;
-                sr += bg; sgn += bg; sb += bg;
-              }
-              p.io.rgb_out[in.ray * 3 + 0] = sr;
-              p.io.rgb_out[in.ray * 3 + 1] = sgn;
-              p.io.rgb_out[in.ray * 3 + 2] = sb;
-              // fused gather: the same row goes to every peer GPU's image buffer over NVLink (nb2_render_params.peer_rgb)
-              for (int q = 0; q < p.io.n_peers; ++q) {
-                float* o = p.io.peer_rgb[q] + (p.io.peer_row0 + in.ray) * 3;
-                o[0] = sr; o[1] = sgn; o[2] = sb;
-              }
-              if (p.io.depth_out) p.io.depth_out[in.ray] = (sd - p.io.near_t) / (p.io.far_t - p.io.near_t);
-              if (p.io.acc_out) p.io.acc_out[in.ray] = sa;
-            }
-            named_bar_sync(1, 128);  // scratch is reused by the next tile
-          }
+        const float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(in.d[0], in.d[0]), __fmul_rn(in.d[1], in.d[1])), __fmul_rn(in.d[2], in.d[2])));
+        pend = Pend{sigma, c0, c1, c2, __fmul_rn(in.z, nrm), in.s, in.ray, grow, in.valid};
+        has_pend = true;
+        if (!has_next) {                  // the CTA's last tile: nothing left to hide under
+          finish_rgb(pend);
+          has_pend = false;
         }
         t_last += NB2_CLK() - ce;
         continue;
@@ -370,6 +393,10 @@ __device__ __forceinline__ void slot_group_run4(const TcParams& p, Tc4Misc* misc
       // ---- work hidden behind the next layer's MMAs ------------------------------------------------------------------
       const long long cpe = NB2_CLK();
       if (has_next && l == 0) enc_compute(enc, in_next.p, p.pos_levels, in_next.valid, in_next.enc, in_next.ipe ? in_next.cov : nullptr);
+      if (l == 1 && has_pend) {           // the previous tile's heads and compositing, under this tile's layer-2 MMAs
+        finish_rgb(pend);
+        has_pend = false;
+      }
       if (l == p.dir_layer && g == 0) {
         // the encoded position is dead after the skip layer: its tile now takes the encoded direction (columns 0-31;
         // the bias k-step of the running layer reads columns 48-63 of the same rows, other 16-byte units)
@@ -477,6 +504,7 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) mlp_tc4_kernel(const __grid
       // =========================== leader: MMA issuer for the pair (whole warp, one elected lane per instruction) ======
       uint32_t stage = 0, phase = 0, pa = 0, pf = 0, pc = 0;
       long long t_wa = 0, t_ww = 0, t0m = NB2_CLK();
+      long long t_wl[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};   // PROFILE build: the issuer's operand waits by layer
       const uint32_t ring_lo = umma_desc_lo(ring_base);
       const uint32_t enc_lo = umma_desc_lo(enc_base);    // hi half of the encoding tile; the lo half is one tile further
       const bool no_weights = (p.debug & 1) != 0, no_mma = (p.debug & 2) != 0;
@@ -521,7 +549,7 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) mlp_tc4_kernel(const __grid
             mbar_wait(smem_u32(&misc->acc_free), pf);
             pf ^= 1u;
           }
-          t_wa += NB2_CLK() - c0; }
+          t_wa += NB2_CLK() - c0; if (NB2_PROF_ON) t_wl[l < 9 ? l : 8] += NB2_CLK() - c0; }
           tc_fence_after();
           uint32_t pending = l == 0 ? 0u : 0xFu;       // chunk barriers of this layer not consumed yet
           auto wait_chunk = [&](int c) {
@@ -529,6 +557,7 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) mlp_tc4_kernel(const __grid
             const long long c0 = NB2_CLK();
             mbar_wait(smem_u32(&misc->a_chunk[c]), pc);
             t_wa += NB2_CLK() - c0;
+            if (NB2_PROF_ON) t_wl[l < 9 ? l : 8] += NB2_CLK() - c0;
             tc_fence_after();
             pending &= ~(1u << c);
           };
@@ -557,6 +586,11 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) mlp_tc4_kernel(const __grid
         }
       }
       if (NB2_PROF_ON && lane == 0) { p.prof[blockIdx.x * 16 + 3] = t_wa; p.prof[blockIdx.x * 16 + 4] = t_ww; p.prof[blockIdx.x * 16 + 5] = NB2_CLK() - t0m; }
+      if (NB2_PROF_ON && lane == 0) {
+        // the per-layer split goes to the free slots of the PEER's row (0-5, 13-15: it has no streamer / issuer counters)
+        const int slot[9] = {0, 1, 2, 3, 4, 5, 13, 14, 15};
+        for (int l = 0; l < 9; ++l) p.prof[(blockIdx.x + 1) * 16 + slot[l]] = t_wl[l];
+      }
     }
   } else if (warp >= 4) {
     reg_alloc<Tc4Regs<NG>::group>();

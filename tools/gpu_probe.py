@@ -134,10 +134,17 @@ def stage_roles(precision, H=400):
         names[6:9] = ["nhalf:window_work", "nhalf:wait_acc_h0", "nhalf:drain_h0"]
     print(f"ROLES {precision} nhalf={os.environ.get('NB2_TC_NHALF','dflt')} cluster={os.environ.get('NB2_TC_CLUSTER','dflt')} lockstep={os.environ.get('NB2_TC_LOCKSTEP','dflt')} (median over CTAs, cycles; last launch = fine kernel)")
     lead = a[a[:, 5] > 0] if (a[:, 5] > 0).any() else a       # MMA counters exist on issuing CTAs only
+    if precision in ("fp16x3", "bf16x3"):
+        lead = a[0::2]                                        # split kernel: leaders are the even CTAs (odd rows carry the per-layer split)
     med = np.median(a, axis=0)
     med[3:6] = np.median(lead[:, 3:6], axis=0)
     for i, n in enumerate(names):
         print(f"   {n:16s} {med[i]:14.0f}   per-iter {med[i] / max(med[11], 1):12.0f}")
+    if precision in ("fp16x3", "bf16x3"):      # split kernel: the issuer's operand waits by layer, parked in the peer CTA's row
+        peer = a[1::2][:, [0, 1, 2, 3, 4, 5, 13, 14, 15]]
+        if (peer > 0).any():
+            pm = np.median(peer, axis=0)
+            print("   mma_wait_A by layer (per iter): " + "  ".join(f"L{l}={pm[l] / max(med[11], 1):.0f}" for l in range(9)))
 
 
 def stage_hbm(R=160000):
