@@ -189,7 +189,7 @@ __device__ __forceinline__ void slot_group_run4(const TcParams& p, Tc4Misc* misc
   const uint32_t acc_full = smem_u32(&misc->acc_full);
   float* scratch = &misc->scratch[0][0];
   uint32_t pacc = 0;
-  long long t_pe = 0, t_wacc = 0, t_epi = 0, t_last = 0, t0e = NB2_CLK();
+  long long t_pe = 0, t_wacc = 0, t_epi = 0, t_last = 0, t_head = 0, t_begin = 0, t0e = NB2_CLK();
 
   auto arrive_a = [&]() {
     __syncwarp();
@@ -345,7 +345,10 @@ __device__ __forceinline__ void slot_group_run4(const TcParams& p, Tc4Misc* misc
         }
         // the accumulator has been read and the encoding tile is free: hand the next tile to the issuer before the rest
         // of this epilogue (collecting the heads, compositing), which runs one layer-window later (finish_rgb)
+        const long long ch = NB2_CLK();
+        t_head += ch - ce;
         if (has_next) begin_tile();
+        t_begin += NB2_CLK() - ch;
         // combine the column groups: warpgroups 1.. park their partial sums (and their part of the density dot product);
         // warpgroup 0 collects them in finish_rgb -- one layer-window later when another tile follows
         const uint32_t xaddr = park_base + (uint32_t)row * 16u;
@@ -412,6 +415,7 @@ __device__ __forceinline__ void slot_group_run4(const TcParams& p, Tc4Misc* misc
   if (NB2_PROF_ON && threadIdx.x == kRolesThreads) {
     long long* o = p.prof + blockIdx.x * 16;
     o[6] = t_pe; o[7] = t_wacc; o[8] = t_epi; o[9] = t_last; o[10] = NB2_CLK() - t0e; o[11] = n_iters; o[12] = net.n_layers;
+    if ((blockIdx.x & 1) == 0) { o[13] = t_head; o[14] = t_begin; }     // (the odd rows' free slots carry the issuer's per-layer waits)
   }
 }
 

@@ -129,7 +129,7 @@ def stage_roles(precision, H=400):
     _lib.check(lib.nb2_debug_tc_profile(h, buf, 148))
     a = np.array(buf[:], dtype=np.int64).reshape(148, 16)
     names = ["str_wait_empty", "str_total", "ring_entries", "mma_wait_A", "mma_wait_W", "mma_total", "g0_encode", "g0_wait_acc",
-             "g0_epi_hidden", "g0_epi_last", "g0_total", "iters", "layers", "nhalf:wait_acc_h1", "nhalf:store_h0+publish", "nhalf:after_h1_total"]
+             "g0_epi_hidden", "g0_epi_last", "g0_total", "iters", "layers", "g0_rgb_head_math", "g0_begin_next_tile", "-"]
     if os.environ.get("NB2_TC_NHALF") == "1":
         names[6:9] = ["nhalf:window_work", "nhalf:wait_acc_h0", "nhalf:drain_h0"]
     print(f"ROLES {precision} nhalf={os.environ.get('NB2_TC_NHALF','dflt')} cluster={os.environ.get('NB2_TC_CLUSTER','dflt')} lockstep={os.environ.get('NB2_TC_LOCKSTEP','dflt')} (median over CTAs, cycles; last launch = fine kernel)")
@@ -140,6 +140,9 @@ def stage_roles(precision, H=400):
     med[3:6] = np.median(lead[:, 3:6], axis=0)
     for i, n in enumerate(names):
         print(f"   {n:16s} {med[i]:14.0f}   per-iter {med[i] / max(med[11], 1):12.0f}")
+    if precision in ("fp16x3", "bf16x3"):
+        ev = np.median(a[0::2][:, [13, 14]], axis=0) / max(med[11], 1)
+        print(f"   rgb epilogue of the leader CTAs (per iter): accumulator read + head arithmetic {ev[0]:.0f}, hand-over of the next tile {ev[1]:.0f}")
     if precision in ("fp16x3", "bf16x3"):      # split kernel: the issuer's operand waits by layer, parked in the peer CTA's row
         peer = a[1::2][:, [0, 1, 2, 3, 4, 5, 13, 14, 15]]
         if (peer > 0).any():
